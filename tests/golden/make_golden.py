@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libpu_ref.so, built by
+oracle/ref_build/Makefile from /root/reference).  Run in the build container (where /root/reference
+exists); the vectors then travel with the repo so that the oracle and the CUDA path can be pinned on
+boxes that have no reference checkout.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import refapi as R  # noqa: E402
+
+
+def ldpc_vectors():
+    rng = np.random.default_rng(20261017)
+    out = {}
+    # Eb/N0-ish operating points: easy / waterfall / stress per rate (sigma of BPSK AWGN)
+    sig = {R.R1_4: (0.7, 1.15, 1.4), R.R1_2: (0.5, 0.72, 0.9), R.R2_3: (0.45, 0.6, 0.8),
+           R.R3_4: (0.4, 0.58, 0.8), R.R5_6: (0.4, 0.6, 0.8)}
+    for rate, k in R.RATE_K.items():
+        data = rng.integers(0, 256, (k + 7) // 8, dtype=np.uint8)
+        cw = R.ldpc_encode(rate, data[:k // 8])
+        bits = np.unpackbits(cw)[:648].astype(np.float32)
+        llrs = []
+        for s in sig[rate]:
+            y = (1 - 2 * bits)[None, :] + s * rng.standard_normal((6, 648)).astype(np.float32)
+            l = np.clip(2 * y / s ** 2, -10, 10).astype(np.float32)
+            l = np.where(np.abs(l) < 0.5, np.where(l >= 0, 0.5, -0.5), l).astype(np.float32)
+            llrs.append(l)
+        # demod-realistic: exactly +-10 with iid sign flips -> all-tie minima
+        for p in (0.02, 0.06, 0.13):
+            flip = rng.random((4, 648)) < p
+            l = np.where((bits[None, :] > 0) ^ flip, -10.0, 10.0).astype(np.float32)
+            llrs.append(l)
+        # erasures and unclamped large values
+        l = llrs[0][:2].copy()
+        l[:, ::7] = 0.0
+        l[:, 5::11] *= 9.0
+        llrs.append(l)
+        llr = np.concatenate(llrs, 0)
+        info, ok, it = R.ldpc_decode_batch(rate, llr)
+        out[f"r{rate}_data"] = data
+        out[f"r{rate}_cw"] = cw
+        out[f"r{rate}_llr"] = llr
+        out[f"r{rate}_info"] = info
+        out[f"r{rate}_ok"] = ok
+        out[f"r{rate}_iters"] = it
+        # multi-block + partial block decodeSoft (ldpc_decoder.cpp:283-428)
+        mb = np.concatenate([llr[0], llr[7], llr[1][:300]])
+        o, okm, itm = R.ldpc_decode_soft(rate, mb)
+        out[f"r{rate}_mb_llr"] = mb
+        out[f"r{rate}_mb_out"] = o
+        out[f"r{rate}_mb_ok"] = np.array([okm, itm], np.int32)
+    np.savez_compressed(os.path.join(HERE, "ldpc_golden.npz"), **out)
+
+
+def awgn(x, snr_db, rng):
+    p = float((x.astype(np.float64) ** 2).mean())
+    return (x + np.sqrt(p / 10 ** (snr_db / 10)) * rng.standard_normal(len(x))).astype(np.float32)
+
+
+OFDM_CASES = [
+    # name, preset, mod, rate, payload, snr_db, (cfo_mode,cfo,phase), channel(delay_ms,doppler)|None
+    ("m1_dqpsk_awgn25", "m1", R.DQPSK, R.R1_2, 40, 25.0, (1, 0.0, 0.0), None),
+    ("m1_dqpsk_awgn0", "m1", R.DQPSK, R.R1_2, 40, 0.0, (1, 0.0, 0.0), None),
+    ("m1_dbpsk_awgn3", "m1", R.DBPSK, R.R1_4, 20, 3.0, (1, 0.0, 0.0), None),
+    ("m1_d8psk_awgn12", "m1", R.D8PSK, R.R1_2, 40, 12.0, (1, 0.0, 0.0), None),
+    ("m1_dqpsk_cfo", "m1", R.DQPSK, R.R1_2, 40, 18.0, (2, 12.5, 0.7), None),
+    ("m1_dqpsk_flutter", "m1", R.DQPSK, R.R1_2, 40, 15.0, (1, 0.0, 0.0), (0.5, 10.0)),
+    ("m1_bpsk_awgn6", "m1", R.BPSK, R.R1_2, 40, 6.0, (1, 0.0, 0.0), None),
+    ("m1_qpsk_poor", "m1", R.QPSK, R.R1_2, 40, 15.0, (1, 0.0, 0.0), (2.0, 1.0)),
+    ("m1_qam16_awgn14", "m1", R.QAM16, R.R1_2, 40, 14.0, (1, 0.0, 0.0), None),
+    ("m1_qam16_cfo", "m1", R.QAM16, R.R1_2, 40, 20.0, (2, -31.0, -2.9), None),
+    ("m1_qam64_awgn22", "m1", R.QAM64, R.R3_4, 60, 22.0, (1, 0.0, 0.0), None),
+    ("m3_dqpsk_awgn10", "m3", R.DQPSK, R.R3_4, 60, 10.0, (1, 0.0, 0.0), None),
+    ("m3_qam16_awgn12", "m3", R.QAM16, R.R3_4, 60, 12.0, (1, 0.0, 0.0), None),
+    ("m3_qam32_awgn14", "m3", R.QAM32, R.R3_4, 60, 14.0, (1, 0.0, 0.0), None),
+    ("m3_qam32_good25", "m3", R.QAM32, R.R3_4, 60, 25.0, (1, 0.0, 0.0), (0.5, 0.1)),
+]
+
+
+def ofdm_vectors():
+    out = {}
+    for i, (name, preset, mod, rate, nbytes, snr, (cm, cfo, ph), chan) in enumerate(OFDM_CASES):
+        rng = np.random.default_rng(1000 + i)
+        cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+        data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        cw = R.ldpc_encode(rate, data)
+        tx = R.ofdm_tx(cfg, cw, 0)
+        if chan is None:
+            rx = awgn(tx, snr, rng)
+        else:
+            rx = R.watterson(tx, snr, chan[0], chan[1], seed=42 + i)
+        st = R.ofdm_presynced_stages(cfg, rx, 2, cm, cfo, ph)
+        info, ok, it = R.ldpc_decode_soft(rate, st["llr"][:648])
+        out[name + "_cfg"] = np.frombuffer(bytes(cfg), dtype=np.uint8).copy()
+        out[name + "_cfo"] = np.array([cm, cfo, ph], np.float32)
+        out[name + "_data"] = data
+        out[name + "_rx"] = rx.astype(np.float16).astype(np.float32) if False else rx
+        out[name + "_llr"] = st["llr"]
+        out[name + "_scalars"] = st["scalars"]
+        out[name + "_h_last"] = st["h"][-1]
+        out[name + "_info"] = info
+        out[name + "_ok"] = np.array([ok, it], np.int32)
+    # transmitter golden: first presynced frame and first S-C frame, M1 DQPSK R1/2
+    rng = np.random.default_rng(7)
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    data = rng.integers(0, 256, 40, dtype=np.uint8)
+    cw = R.ldpc_encode(R.R1_2, data)
+    out["tx_m1_dqpsk_cw"] = cw
+    out["tx_m1_dqpsk_l0"] = R.ofdm_tx(cfg, cw, 0)
+    out["tx_m1_dqpsk_l1"] = R.ofdm_tx(cfg, cw, 1)
+    np.savez_compressed(os.path.join(HERE, "ofdm_golden.npz"), **out)
+
+
+def misc_vectors():
+    out = {}
+    for bps in (30, 60, 90, 118, 220, 708):
+        x = np.arange(648, dtype=np.float32)
+        out[f"ci_{bps}"] = R.channel_interleave(bps, x)
+    out["bi_6x108"] = R.block_interleave(6, 108, np.arange(648, dtype=np.float32))
+    out["nco_1500_48000"] = R.nco(1500, 48000, 2048)
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(512) + 1j * rng.standard_normal(512)).astype(np.complex64)
+    out["fft512_in"] = x
+    out["fft512_out"] = R.fft(x)
+    np.savez_compressed(os.path.join(HERE, "misc_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
+    ldpc_vectors()
+    ofdm_vectors()
+    misc_vectors()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

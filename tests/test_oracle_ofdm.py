@@ -1,0 +1,89 @@
+"""Pins the C oracle's OFDM layer (oracle/pu_oracle_ofdm.c) against golden vectors from the unmodified
+reference and, when oracle/_ref is built, bit-for-bit against the reference stage by stage.  CPU only."""
+import numpy as np
+import pytest
+
+import oracleapi as O
+import refapi as R
+from golden.make_golden import OFDM_CASES, awgn
+
+
+def cfg_from(g, name):
+    return R.ModemConfig.from_buffer_copy(bytes(g[name + "_cfg"]))
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a).view(np.uint32)
+    b = np.ascontiguousarray(b).view(np.uint32)
+    return a.shape == b.shape and bool((a == b).all())
+
+
+@pytest.mark.parametrize("case", [c[0] for c in OFDM_CASES])
+def test_golden_ofdm_rx(golden, case):
+    g = golden["ofdm"]
+    cfg = cfg_from(g, case)
+    cm, cfo, ph = g[case + "_cfo"]
+    st = O.ofdm_presynced_stages(cfg, g[case + "_rx"], 2, int(cm), float(cfo), float(ph))
+    assert same_bits(st["llr"], g[case + "_llr"])
+    assert same_bits(st["scalars"], g[case + "_scalars"])
+    assert same_bits(st["h"][-1], g[case + "_h_last"])
+    info, ok, it = O.ldpc_decode_soft(cfg.code_rate, st["llr"][:648])
+    assert (info == g[case + "_info"]).all() and [int(ok), it] == list(g[case + "_ok"])
+
+
+def test_golden_ofdm_tx(golden):
+    g = golden["ofdm"]
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    assert same_bits(O.ofdm_tx(cfg, g["tx_m1_dqpsk_cw"], 0), g["tx_m1_dqpsk_l0"])
+    assert same_bits(O.ofdm_tx(cfg, g["tx_m1_dqpsk_cw"], 1), g["tx_m1_dqpsk_l1"])
+    assert len(g["tx_m1_dqpsk_l0"]) == 7332 and len(g["tx_m1_dqpsk_l1"]) == 10124
+
+
+def test_golden_dsp(golden):
+    g = golden["misc"]
+    assert same_bits(O.nco(1500, 48000, 2048), g["nco_1500_48000"])
+    assert same_bits(O.fft(g["fft512_in"]), g["fft512_out"])
+    x = g["fft512_in"]
+    assert np.abs(O.fft(O.fft(x), inverse=True) - x).max() < 1e-5       # tests/test_fft.cpp round trip
+    tone = np.exp(2j * np.pi * 8 * np.arange(512) / 512).astype(np.complex64)
+    assert int(np.argmax(np.abs(O.fft(tone)))) == 8                      # tests/test_fft.cpp tone at bin 8
+
+
+def test_demapper_sign_conventions():
+    # tests/test_comprehensive_modem.cpp:270-377: + LLR <=> bit 0
+    assert O.soft_demap(R.BPSK, -1 + 0j)[0] > 0 and O.soft_demap(R.BPSK, 1 + 0j)[0] < 0
+    q = 0.70710678
+    assert (O.soft_demap(R.QPSK, complex(-q, -q)) > 0).all() and (O.soft_demap(R.QPSK, complex(q, q)) < 0).all()
+    for bits, ang in ((0b00, 0), (0b01, 90), (0b10, 180), (0b11, 270)):  # modulator.cpp:414-421
+        l = O.soft_demap(R.DQPSK, np.exp(1j * np.deg2rad(ang)), 1 + 0j)
+        assert [int(v < 0) for v in l] == [bits >> 1, bits & 1]
+    assert (O.soft_demap(R.DQPSK, 1e-4 + 0j, 1e-3 + 0j) == 0).all()       # weak-signal gate, soft_demap.hpp:199-201
+    assert O.soft_demap(R.QAM16, 0.01 + 0.0j, nv=10.0)[0] == -0.5          # clipLLR min magnitude, :22-29
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("mod", [R.DBPSK, R.DQPSK, R.D8PSK, R.BPSK, R.QPSK, R.QAM16, R.QAM32, R.QAM64, R.QAM256])
+@pytest.mark.parametrize("preset", ["m1", "m3"])
+def test_vs_reference_stages(mod, preset):
+    rate = R.R1_2 if preset == "m1" else R.R3_4
+    cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    for i, snr in enumerate((4.0, 16.0, 30.0)):
+        rng = np.random.default_rng(mod * 100 + i)
+        data = rng.integers(0, 256, 40 if preset == "m1" else 60, dtype=np.uint8)
+        cw = R.ldpc_encode(rate, data)
+        tx = R.ofdm_tx(cfg, cw, 0)
+        assert same_bits(tx, O.ofdm_tx(cfg, cw, 0))
+        rx = awgn(tx, snr, rng) if i != 1 else R.watterson(tx, snr, 1.0, 0.5, seed=42 + mod)
+        cm, cfo, ph = (1, 0.0, 0.0) if i != 2 else (2, 7.25, 1.1)
+        a = R.ofdm_presynced_stages(cfg, rx, 2, cm, cfo, ph)
+        b = O.ofdm_presynced_stages(cfg, rx, 2, cm, cfo, ph)
+        for key in ("carriers", "lts_bins", "h_lts", "bins", "h", "eq", "nv", "scalars", "llr"):
+            assert same_bits(a[key], b[key]), (key, snr)
+
+
+@pytest.mark.ref
+def test_vs_reference_sc_preamble_tx():
+    for mod in (R.DQPSK, R.QAM16):
+        cfg = R.config_m1(mod, R.R1_2)
+        cw = R.ldpc_encode(R.R1_2, np.arange(40, dtype=np.uint8))
+        assert same_bits(R.ofdm_tx(cfg, cw, 1), O.ofdm_tx(cfg, cw, 1))
