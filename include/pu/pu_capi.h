@@ -1,0 +1,122 @@
+/* include/pu/pu_capi.h — C ABI of libpu_b200.so, the B200-native receive-chain hot path of ProjectUltra.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference tree).  The C++20 classes
+ * in include/pu/pu_dropin.hpp wrap these calls to present the reference's own class surface
+ * (ultra::LDPCDecoder, ultra::OFDMDemodulator, ultra::ChannelInterleaver, ultra::IWaveform) unchanged;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - status codes, never exceptions (the reference decode path does not throw: SURVEY §8b "Errors");
+ *  - outputs are caller-allocated; `space` says whether ALL data pointers of a call are host or device memory;
+ *  - `stream` is a cudaStream_t passed as void*.  With PU_MEM_DEVICE the call only enqueues work on `stream`
+ *    (NULL = the CUDA default stream, as in the runtime API); with PU_MEM_HOST it stages through pinned memory
+ *    on `stream` (NULL = a stream owned by the context) and returns when the outputs are valid;
+ *  - there is NO CPU fallback: every compute entry point fails with PU_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PU_CAPI_H
+#define PU_CAPI_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PU_API __declspec(dllexport)
+#else
+#define PU_API __attribute__((visibility("default")))
+#endif
+
+typedef enum {
+    PU_OK = 0,
+    PU_ERR_INVALID = 1,      /* bad argument */
+    PU_ERR_CUDA = 2,         /* CUDA runtime / launch failure, or no usable device */
+    PU_ERR_NOMEM = 3,
+    PU_ERR_UNSUPPORTED = 4   /* configuration outside the implemented hot path */
+} pu_status;
+
+typedef enum { PU_MEM_HOST = 0, PU_MEM_DEVICE = 1 } pu_memspace;
+
+/* ultra::Modulation, include/ultra/types.hpp:27-39 */
+enum { PU_MOD_DBPSK = 0, PU_MOD_BPSK = 1, PU_MOD_DQPSK = 2, PU_MOD_QPSK = 3, PU_MOD_D8PSK = 4, PU_MOD_QAM8 = 5,
+       PU_MOD_QAM16 = 6, PU_MOD_QAM32 = 7, PU_MOD_QAM64 = 8, PU_MOD_QAM256 = 10 };
+/* ultra::CodeRate, include/ultra/types.hpp:92-101 */
+enum { PU_RATE_1_4 = 0, PU_RATE_1_3 = 1, PU_RATE_1_2 = 2, PU_RATE_2_3 = 3, PU_RATE_3_4 = 4, PU_RATE_5_6 = 5,
+       PU_RATE_7_8 = 6 };
+#define PU_LDPC_N 648 /* protocol::v2::LDPC_CODEWORD_BITS, src/protocol/frame_v2.hpp:546 */
+
+/* POD mirror of ultra::ModemConfig (include/ultra/types.hpp:139-234), the fields the receive path reads. */
+typedef struct {
+    uint32_t sample_rate;   /* 48000 */
+    uint32_t center_freq;   /* 1500 */
+    uint32_t fft_size;      /* 512 | 1024 */
+    uint32_t num_carriers;  /* 30 | 59 */
+    uint32_t cp_mode;       /* CyclicPrefixMode: 0 SHORT(32) 1 MEDIUM(48) 2 LONG(64), x fft_size/512 */
+    uint32_t symbol_guard;
+    uint32_t pilot_spacing;
+    uint32_t use_pilots;
+    uint32_t modulation;    /* PU_MOD_* */
+    uint32_t code_rate;     /* PU_RATE_* */
+    float output_scale;     /* TX only (40.0) */
+    float tx_cfo_hz;        /* TX only */
+} pu_modem_config;
+
+typedef struct pu_ctx pu_ctx;
+typedef struct pu_ldpc pu_ldpc;
+typedef struct pu_ofdm pu_ofdm;
+
+/* ---------------------------------------------------------------- context */
+PU_API int pu_abi_version(void);
+PU_API const char* pu_status_string(pu_status s);
+PU_API const char* pu_last_error(void);                 /* thread-local detail of the last failing call */
+PU_API pu_status pu_init(int device, pu_ctx** out);    /* one context per GPU / per process rank */
+PU_API void pu_destroy(pu_ctx* ctx);
+PU_API int pu_device_sm_count(const pu_ctx* ctx);
+PU_API pu_status pu_synchronize(pu_ctx* ctx, void* stream);
+PU_API uint64_t pu_kernel_launches(const pu_ctx* ctx);  /* kernels launched through this context so far */
+
+/* ---------------------------------------------------------------- LDPC decoder
+ * Replaces ultra::LDPCDecoder (include/ultra/fec.hpp:48-77; src/fec/ldpc_decoder.cpp). */
+/* LDPCDecoder::LDPCDecoder(CodeRate) + setMaxIterations, ldpc_decoder.cpp:262-263,448-450 (default 50, :43) */
+PU_API pu_status pu_ldpc_create(pu_ctx* ctx, int code_rate, int max_iter, pu_ldpc** out);
+PU_API void pu_ldpc_destroy(pu_ldpc* h);
+PU_API pu_status pu_ldpc_set_rate(pu_ldpc* h, int code_rate);      /* LDPCDecoder::setRate, :438-442 */
+PU_API pu_status pu_ldpc_set_max_iterations(pu_ldpc* h, int n);    /* LDPCDecoder::setMaxIterations, :448-450 */
+PU_API int pu_ldpc_rate(const pu_ldpc* h);                         /* LDPCDecoder::getRate, :444-446 */
+PU_API int pu_ldpc_info_bits(const pu_ldpc* h);                    /* k of getCodeParams, :21-36 */
+PU_API int pu_ldpc_num_edges(const pu_ldpc* h);                    /* edges of H incl. identity */
+/* H row i as variable indices in stored order (for inspection/tests); returns the degree or -1 */
+PU_API int pu_ldpc_row(const pu_ldpc* h, int check, int32_t* vars, int cap);
+/* B independent codewords of 648 LLRs (+ => bit 0).  One decodeBP each (ldpc_decoder.cpp:153-259):
+ * info_bytes[b*info_stride ...] = k info bits MSB-first, last byte left-justified; ok[b] = lastDecodeSuccess();
+ * iters[b] = lastIterations() (0-based converging iteration, max_iter on failure).  ok / iters may be NULL.
+ * llr_stride is in floats (>= 648). */
+PU_API pu_status pu_ldpc_decode_batch(pu_ldpc* h, const float* llr, size_t llr_stride, size_t B,
+                                      uint8_t* info_bytes, size_t info_stride, uint8_t* ok, int32_t* iters,
+                                      pu_memspace space, void* stream);
+/* LDPCDecoder::decodeSoft (ldpc_decoder.cpp:283-428) on HOST memory, including its multi-block rules:
+ * <=648 LLRs -> one zero-padded block; otherwise full blocks concatenated at bit level and a zero-padded
+ * trailing partial block.  *out_len receives the byte count; returns PU_ERR_INVALID if out_cap is too small. */
+PU_API pu_status pu_ldpc_decode_soft(pu_ldpc* h, const float* llr, size_t n_llr, uint8_t* out, size_t out_cap,
+                                     size_t* out_len, int* last_success, int* last_iters);
+/* LDPCDecoder::decode (hard bits -> +-6 LLR, ldpc_decoder.cpp:267-281) on HOST memory */
+PU_API pu_status pu_ldpc_decode_hard(pu_ldpc* h, const uint8_t* coded, size_t n_bytes, uint8_t* out, size_t out_cap,
+                                     size_t* out_len, int* last_success, int* last_iters);
+/* LDPCEncoder::encode (src/fec/ldpc_encoder.cpp:193-257), host side: TX stimulus for the link simulation */
+PU_API pu_status pu_ldpc_encode(int code_rate, const uint8_t* data, size_t n_bytes, uint8_t* out, size_t out_cap,
+                                size_t* out_len);
+
+/* ---------------------------------------------------------------- interleavers (host tables)
+ * ultra::ChannelInterleaver (include/ultra/fec.hpp:120-142; ldpc_decoder.cpp:547-620): perm[i] = (i*step)%total.
+ * Writes perm[total]; interleave: out[perm[i]] = in[i]; deinterleave: out[inv[i]] = in[i]. */
+PU_API pu_status pu_channel_interleaver_perm(size_t bits_per_symbol, size_t total_bits, uint32_t* perm,
+                                             uint32_t* inverse_perm, size_t* step);
+/* ultra::Interleaver (fec.hpp:85-107; ldpc_decoder.cpp:454-464): perm[i] = (i%cols)*rows + i/cols */
+PU_API pu_status pu_block_interleaver_perm(size_t rows, size_t cols, uint32_t* perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PU_CAPI_H */

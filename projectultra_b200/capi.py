@@ -1,0 +1,232 @@
+"""ctypes binding of libpu_b200.so (include/pu/pu_capi.h).
+
+This module is the thin Python view of the C ABI used by tests/ and bench.py.  numpy arrays are passed as HOST
+buffers (PU_MEM_HOST), torch CUDA tensors as DEVICE buffers (PU_MEM_DEVICE) on torch's current stream.
+There is no fallback of any kind: if the shared library is missing or no sm_100 GPU is usable the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpu_b200.so")
+
+PU_MEM_HOST, PU_MEM_DEVICE = 0, 1
+DBPSK, BPSK, DQPSK, QPSK, D8PSK, QAM8, QAM16, QAM32, QAM64, QAM256 = 0, 1, 2, 3, 4, 5, 6, 7, 8, 10
+R1_4, R1_3, R1_2, R2_3, R3_4, R5_6, R7_8 = range(7)
+LDPC_N = 648
+
+
+class PuError(RuntimeError):
+    pass
+
+
+class ModemConfig(C.Structure):
+    """pu_modem_config: POD mirror of ultra::ModemConfig (include/ultra/types.hpp:139-234)."""
+    _fields_ = [("sample_rate", C.c_uint32), ("center_freq", C.c_uint32), ("fft_size", C.c_uint32),
+                ("num_carriers", C.c_uint32), ("cp_mode", C.c_uint32), ("symbol_guard", C.c_uint32),
+                ("pilot_spacing", C.c_uint32), ("use_pilots", C.c_uint32), ("modulation", C.c_uint32),
+                ("code_rate", C.c_uint32), ("output_scale", C.c_float), ("tx_cfo_hz", C.c_float)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PuError(f"{LIB_PATH} is missing: run `python -m projectultra_b200.build` "
+                          "(the CUDA library is the product; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.pu_status_string.restype = C.c_char_p
+        L.pu_last_error.restype = C.c_char_p
+        L.pu_kernel_launches.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        L = lib()
+        raise PuError(f"{L.pu_status_string(status).decode()}: {L.pu_last_error().decode()}")
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x, ctype=None):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+def _space(*xs):
+    dev = [_is_torch(x) and x.is_cuda for x in xs if x is not None]
+    if any(dev) and not all(dev):
+        raise PuError("mixing host and device buffers in one call")
+    return PU_MEM_DEVICE if dev and dev[0] else PU_MEM_HOST
+
+
+def _stream(space):
+    if space == PU_MEM_DEVICE:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return None
+
+
+class Context:
+    """pu_ctx: one per GPU (per process rank)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib().pu_init(int(device), C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().pu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self):
+        return lib().pu_device_sm_count(self._h)
+
+    @property
+    def kernel_launches(self):
+        return int(lib().pu_kernel_launches(self._h))
+
+    def synchronize(self):
+        check(lib().pu_synchronize(self._h, None))
+
+
+class LdpcDecoder:
+    """pu_ldpc: batched drop-in for ultra::LDPCDecoder (include/ultra/fec.hpp:48-77)."""
+
+    def __init__(self, ctx, rate, max_iter=50):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        check(lib().pu_ldpc_create(ctx._h, int(rate), int(max_iter), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().pu_ldpc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def k(self):
+        return lib().pu_ldpc_info_bits(self._h)
+
+    @property
+    def info_bytes(self):
+        return (self.k + 7) // 8
+
+    @property
+    def rate(self):
+        return lib().pu_ldpc_rate(self._h)
+
+    @property
+    def num_edges(self):
+        return lib().pu_ldpc_num_edges(self._h)
+
+    def set_rate(self, rate):
+        check(lib().pu_ldpc_set_rate(self._h, int(rate)))
+
+    def set_max_iterations(self, n):
+        check(lib().pu_ldpc_set_max_iterations(self._h, int(n)))
+
+    def rows(self):
+        out = []
+        buf = (C.c_int32 * 16)()
+        for i in range(648 - self.k):
+            d = lib().pu_ldpc_row(self._h, i, buf, 16)
+            out.append([buf[e] for e in range(d)])
+        return out
+
+    def decode_batch(self, llr, info=None, ok=None, iters=None):
+        """llr: [B, >=648] float32 (numpy => host, torch.cuda => device).  Returns (info_bytes, ok, iters)."""
+        if _is_torch(llr):
+            import torch
+            assert llr.dtype == torch.float32 and llr.dim() == 2 and llr.stride(1) == 1
+            B, stride = llr.shape[0], llr.stride(0)
+            if info is None:
+                info = torch.empty((B, self.info_bytes), dtype=torch.uint8, device=llr.device)
+            if ok is None:
+                ok = torch.empty(B, dtype=torch.uint8, device=llr.device)
+            if iters is None:
+                iters = torch.empty(B, dtype=torch.int32, device=llr.device)
+            istride = info.stride(0)
+        else:
+            llr = np.ascontiguousarray(llr, dtype=np.float32)
+            if llr.ndim == 1:
+                llr = llr.reshape(1, -1)
+            B, stride = llr.shape[0], llr.shape[1]
+            if info is None:
+                info = np.zeros((B, self.info_bytes), np.uint8)
+            if ok is None:
+                ok = np.zeros(B, np.uint8)
+            if iters is None:
+                iters = np.zeros(B, np.int32)
+            istride = info.shape[1]
+        sp = _space(llr, info, ok, iters)
+        check(lib().pu_ldpc_decode_batch(self._h, _ptr(llr), C.c_size_t(stride), C.c_size_t(B), _ptr(info),
+                                         C.c_size_t(istride), _ptr(ok), _ptr(iters), sp, _stream(sp)))
+        return info, ok, iters
+
+    def decode_soft(self, llr):
+        """LDPCDecoder::decodeSoft on host memory -> (bytes, lastDecodeSuccess, lastIterations)."""
+        x = np.ascontiguousarray(llr, dtype=np.float32)
+        out = np.zeros(128 * (len(x) // 648 + 2), np.uint8)
+        n, ok, it = C.c_size_t(0), C.c_int(0), C.c_int(0)
+        check(lib().pu_ldpc_decode_soft(self._h, _ptr(x), C.c_size_t(len(x)), _ptr(out), C.c_size_t(len(out)),
+                                        C.byref(n), C.byref(ok), C.byref(it)))
+        return out[:n.value].copy(), bool(ok.value), it.value
+
+    def decode_hard(self, coded):
+        d = np.ascontiguousarray(np.frombuffer(bytes(coded), np.uint8) if isinstance(coded, (bytes, bytearray))
+                                 else coded, dtype=np.uint8)
+        out = np.zeros(128 * (len(d) // 81 + 2), np.uint8)
+        n, ok, it = C.c_size_t(0), C.c_int(0), C.c_int(0)
+        check(lib().pu_ldpc_decode_hard(self._h, _ptr(d), C.c_size_t(len(d)), _ptr(out), C.c_size_t(len(out)),
+                                        C.byref(n), C.byref(ok), C.byref(it)))
+        return out[:n.value].copy(), bool(ok.value), it.value
+
+
+def ldpc_encode(rate, data):
+    """LDPCEncoder::encode (host)."""
+    d = np.ascontiguousarray(np.frombuffer(bytes(data), np.uint8) if isinstance(data, (bytes, bytearray)) else data,
+                             dtype=np.uint8)
+    out = np.zeros(81 * (len(d) * 8 // 162 + 2), np.uint8)
+    n = C.c_size_t(0)
+    check(lib().pu_ldpc_encode(int(rate), _ptr(d), C.c_size_t(len(d)), _ptr(out), C.c_size_t(len(out)), C.byref(n)))
+    return out[:n.value].copy()
+
+
+def channel_interleaver_perm(bps, total=648):
+    perm = np.zeros(total, np.uint32)
+    inv = np.zeros(total, np.uint32)
+    step = C.c_size_t(0)
+    check(lib().pu_channel_interleaver_perm(C.c_size_t(bps), C.c_size_t(total), _ptr(perm), _ptr(inv), C.byref(step)))
+    return perm, inv, step.value
+
+
+def block_interleaver_perm(rows, cols):
+    perm = np.zeros(rows * cols, np.uint32)
+    check(lib().pu_block_interleaver_perm(C.c_size_t(rows), C.c_size_t(cols), _ptr(perm)))
+    return perm

@@ -1,0 +1,64 @@
+// projectultra_b200/csrc/pu_internal.h — shared internals of libpu_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pu/pu_capi.h"
+
+namespace pu {
+
+void set_error(const char* fmt, ...);
+
+#define PU_CUDA_TRY(expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::pu::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PU_ERR_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+
+#define PU_REQUIRE(cond, msg)                     \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::pu::set_error("%s", msg);           \
+            return PU_ERR_INVALID;                \
+        }                                         \
+    } while (0)
+
+// Grow-only device / pinned-host scratch buffer.
+struct Buffer {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+    pu_status reserve(size_t bytes);
+    void release();
+};
+
+}  // namespace pu
+
+struct pu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t stream = nullptr;  // context-owned stream used when the caller passes NULL
+    std::atomic<uint64_t> launches{0};
+    // staging for PU_MEM_HOST calls
+    pu::Buffer d_in, d_out, d_aux, h_in, h_out;
+};
+
+namespace pu {
+// PU_MEM_DEVICE: `stream` is the caller's stream, NULL meaning the CUDA default stream (as in the runtime API);
+// PU_MEM_HOST: NULL selects the context's own non-blocking stream for the staged copies and the kernel.
+inline cudaStream_t pick_stream(pu_ctx* ctx, void* stream, pu_memspace space = PU_MEM_HOST) {
+    if (stream || space == PU_MEM_DEVICE) return reinterpret_cast<cudaStream_t>(stream);
+    return ctx->stream;
+}
+}  // namespace pu

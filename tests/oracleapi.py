@@ -93,7 +93,7 @@ def ldpc_decode_soft(rate, llr, max_iter=-1):
 def ldpc_decode_batch(rate, llr, max_iter=-1):
     x = _f32(llr).reshape(-1, 648)
     B = x.shape[0]
-    kb = (RATE_K[rate] + 7) // 8
+    kb = (RATE_K.get(rate, 324) + 7) // 8
     out = np.zeros((B, kb), np.uint8)
     ok = np.zeros(B, np.uint8)
     it = np.zeros(B, np.int32)
@@ -212,7 +212,7 @@ def ofdm_presynced_batch(cfg, samples, n_llr, training=2, cfo_mode=1, cfo_hz=Non
 def time_presynced_decode(cfg, samples, rate):
     x = _f32(samples)
     B, L = x.shape
-    kb = (RATE_K[rate] + 7) // 8
+    kb = (RATE_K.get(rate, 324) + 7) // 8
     info = np.zeros((B, kb), np.uint8)
     ok = np.zeros(B, np.uint8)
     t = lib().orc_time_presynced_decode(C.byref(cfg), _p(x, C.c_float), C.c_size_t(B), C.c_size_t(L), rate,
@@ -223,7 +223,7 @@ def time_presynced_decode(cfg, samples, rate):
 def time_ldpc_decode(rate, llr, max_iter=-1):
     x = _f32(llr).reshape(-1, 648)
     B = x.shape[0]
-    kb = (RATE_K[rate] + 7) // 8
+    kb = (RATE_K.get(rate, 324) + 7) // 8
     out = np.zeros((B, kb), np.uint8)
     ok = np.zeros(B, np.uint8)
     it = np.zeros(B, np.int32)

@@ -133,7 +133,7 @@ def ldpc_decode_hard(rate, coded):
 def ldpc_decode_batch(rate, llr, max_iter=-1):
     x = _f32(llr).reshape(-1, 648)
     B = x.shape[0]
-    kb = (RATE_K[rate] + 7) // 8
+    kb = (RATE_K.get(rate, 324) + 7) // 8
     out = np.zeros((B, kb), np.uint8)
     ok = np.zeros(B, np.uint8)
     it = np.zeros(B, np.int32)
@@ -301,7 +301,7 @@ def dpsk_demod_soft(mod_order, sps, samples, data_start=-1):
 def time_presynced_decode(cfg, samples, rate):
     x = _f32(samples)
     B, L = x.shape
-    kb = (RATE_K[rate] + 7) // 8
+    kb = (RATE_K.get(rate, 324) + 7) // 8
     info = np.zeros((B, kb), np.uint8)
     ok = np.zeros(B, np.uint8)
     t = lib().ref_time_presynced_decode(C.byref(cfg), _p(x, C.c_float), C.c_size_t(B), C.c_size_t(L), rate,
@@ -312,7 +312,7 @@ def time_presynced_decode(cfg, samples, rate):
 def time_ldpc_decode(rate, llr, max_iter=-1):
     x = _f32(llr).reshape(-1, 648)
     B = x.shape[0]
-    kb = (RATE_K[rate] + 7) // 8
+    kb = (RATE_K.get(rate, 324) + 7) // 8
     out = np.zeros((B, kb), np.uint8)
     ok = np.zeros(B, np.uint8)
     it = np.zeros(B, np.int32)
