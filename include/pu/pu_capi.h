@@ -116,6 +116,44 @@ PU_API pu_status pu_channel_interleaver_perm(size_t bits_per_symbol, size_t tota
 /* ultra::Interleaver (fec.hpp:85-107; ldpc_decoder.cpp:454-464): perm[i] = (i%cols)*rows + i/cols */
 PU_API pu_status pu_block_interleaver_perm(size_t rows, size_t cols, uint32_t* perm);
 
+/* ---------------------------------------------------------------- OFDM demodulator (presynced path)
+ * Replaces ultra::OFDMDemodulator (include/ultra/ofdm.hpp:58-127) on the externally-timed path that
+ * OFDMChirpWaveform::process drives (src/waveform/ofdm_chirp_waveform.cpp:185-199):
+ *     reset(); setFrequencyOffset[WithPhase](cfo, phase); processPresynced(span, training); getSoftBits()...  */
+/* OFDMDemodulator::OFDMDemodulator(const ModemConfig&), src/ofdm/demodulator.cpp:26-43,457-458.
+ * PU_ERR_UNSUPPORTED for fft sizes other than 512/1024, QAM8/AUTO, or adaptive LMS/RLS equalisation
+ * (ModemConfig::adaptive_eq_enabled, default off, is not part of pu_modem_config). */
+PU_API pu_status pu_ofdm_create(pu_ctx* ctx, const pu_modem_config* cfg, pu_ofdm** out);
+PU_API void pu_ofdm_destroy(pu_ofdm* h);
+PU_API int pu_ofdm_symbol_samples(const pu_ofdm* h);   /* ModemConfig::getSymbolDuration, types.hpp:211-213 */
+PU_API int pu_ofdm_data_carriers(const pu_ofdm* h);
+PU_API int pu_ofdm_pilot_carriers(const pu_ofdm* h);
+PU_API int pu_ofdm_bits_per_symbol(const pu_ofdm* h);  /* OFDMModulator::bitsPerSymbol, modulator.cpp:342-346 */
+/* FFT bins of the used carriers, data carriers first then pilots (setupCarriers, demodulator.cpp:45-67) */
+PU_API int pu_ofdm_carrier_bins(const pu_ofdm* h, int32_t* bins, int cap);
+/* Fuse ChannelInterleaver(bits_per_symbol, total_bits)::deinterleave (ldpc_decoder.cpp:612-620) into the LLR
+ * write address for the first total_bits LLRs of every frame; bits_per_symbol = 0 switches it off. */
+PU_API pu_status pu_ofdm_set_deinterleave(pu_ofdm* h, size_t bits_per_symbol, size_t total_bits);
+/* B independent frames, each L samples starting at the first training symbol:
+ *   samples [B][L]; cfo_hz[B] / cfo_phase[B] = arguments of setFrequencyOffsetWithPhase (demodulator.cpp:816-825),
+ *   NULL meaning setFrequencyOffset(0) (:805-814);
+ *   llr_out [B][llr_stride] receives the soft bits in getSoftBits() order (symbol-major, carrier, bit), truncated
+ *   to llr_stride (648 = the first codeword, as tools/test_ofdm_chirp_pilots.cpp:244-246 consumes them);
+ *   snr_db[B] = getEstimatedSNR(), final_cfo_hz[B] = getFrequencyOffset() after the frame (either may be NULL).
+ * Each frame is demodulated by a fresh demodulator state, like one OFDMDemodulator object per frame. */
+PU_API pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, int training_symbols,
+                                         const float* cfo_hz, const float* cfo_phase, float* llr_out,
+                                         size_t llr_stride, float* snr_db, float* final_cfo_hz,
+                                         pu_memspace space, void* stream);
+/* One frame on HOST memory with per-symbol intermediates for stage-by-stage parity tests.  records holds, per
+ * data symbol: bins[n_used] (re,im), channel_estimate[n_used] (re,im), equalized[n_data] (re,im),
+ * carrier_noise_var[n_data], then 10 scalars {cfo used to mix, cfo after tracking, noise_variance,
+ * timing_offset_samples, estimated_snr_linear, pilot_phase_correction re/im, carrier_phase_correction re/im,
+ * snr_symbol_count}. */
+PU_API pu_status pu_ofdm_presynced_debug(pu_ofdm* h, const float* samples, size_t L, int training_symbols,
+                                         float cfo_hz, float cfo_phase, float* llr_out, size_t llr_cap,
+                                         float* records, size_t records_cap, int* n_data_symbols);
+
 #ifdef __cplusplus
 }
 #endif

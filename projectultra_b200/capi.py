@@ -230,3 +230,99 @@ def block_interleaver_perm(rows, cols):
     perm = np.zeros(rows * cols, np.uint32)
     check(lib().pu_block_interleaver_perm(C.c_size_t(rows), C.c_size_t(cols), _ptr(perm)))
     return perm
+
+
+class OfdmDemodulator:
+    """pu_ofdm: batched drop-in for ultra::OFDMDemodulator's presynced path (include/ultra/ofdm.hpp:58-127)."""
+    DBG_SCALARS = 10
+
+    def __init__(self, ctx, cfg):
+        self.ctx = ctx
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        check(lib().pu_ofdm_create(ctx._h, C.byref(cfg), C.byref(self._h)))
+        self.symbol_samples = lib().pu_ofdm_symbol_samples(self._h)
+        self.n_data = lib().pu_ofdm_data_carriers(self._h)
+        self.n_pilot = lib().pu_ofdm_pilot_carriers(self._h)
+        self.bits_per_symbol = lib().pu_ofdm_bits_per_symbol(self._h)
+
+    def close(self):
+        if self._h:
+            lib().pu_ofdm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def carrier_bins(self):
+        buf = (C.c_int32 * 128)()
+        n = lib().pu_ofdm_carrier_bins(self._h, buf, 128)
+        return np.array(buf[:n], dtype=np.int32)
+
+    def set_deinterleave(self, bits_per_symbol, total_bits=648):
+        check(lib().pu_ofdm_set_deinterleave(self._h, C.c_size_t(bits_per_symbol), C.c_size_t(total_bits)))
+
+    def n_llr(self, L, training=2):
+        return max(0, L // self.symbol_samples - training) * self.bits_per_symbol
+
+    def presynced_batch(self, samples, training=2, cfo_hz=None, cfo_phase=None, llr_stride=None, llr=None,
+                        snr_db=None, final_cfo=None, want_aux=True):
+        """samples [B, L] float32 (numpy => host, torch.cuda => device) -> (llr [B, llr_stride], snr_db, final_cfo)."""
+        tor = _is_torch(samples)
+        if tor:
+            import torch
+            assert samples.dtype == torch.float32 and samples.dim() == 2 and samples.is_contiguous()
+            B, L = samples.shape
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.float32)
+            if samples.ndim == 1:
+                samples = samples.reshape(1, -1)
+            B, L = samples.shape
+        if llr_stride is None:
+            llr_stride = self.n_llr(L, training) if llr is None else llr.shape[1]
+        if tor:
+            import torch
+            if llr is None:
+                llr = torch.zeros((B, llr_stride), dtype=torch.float32, device=samples.device)
+            if want_aux and snr_db is None:
+                snr_db = torch.empty(B, dtype=torch.float32, device=samples.device)
+            if want_aux and final_cfo is None:
+                final_cfo = torch.empty(B, dtype=torch.float32, device=samples.device)
+        else:
+            if llr is None:
+                llr = np.zeros((B, llr_stride), np.float32)
+            if want_aux and snr_db is None:
+                snr_db = np.zeros(B, np.float32)
+            if want_aux and final_cfo is None:
+                final_cfo = np.zeros(B, np.float32)
+            if cfo_hz is not None:
+                cfo_hz = np.ascontiguousarray(cfo_hz, dtype=np.float32)
+            if cfo_phase is not None:
+                cfo_phase = np.ascontiguousarray(cfo_phase, dtype=np.float32)
+        sp = _space(samples, llr, cfo_hz, cfo_phase, snr_db, final_cfo)
+        check(lib().pu_ofdm_presynced_batch(self._h, _ptr(samples), C.c_size_t(B), C.c_size_t(L), int(training),
+                                            _ptr(cfo_hz), _ptr(cfo_phase), _ptr(llr), C.c_size_t(llr_stride),
+                                            _ptr(snr_db), _ptr(final_cfo), sp, _stream(sp)))
+        return llr, snr_db, final_cfo
+
+    def presynced_debug(self, samples, training=2, cfo_hz=0.0, cfo_phase=0.0):
+        x = np.ascontiguousarray(samples, dtype=np.float32)
+        L = len(x)
+        nds = max(0, L // self.symbol_samples - training)
+        nd, nu = self.n_data, self.n_data + self.n_pilot
+        rec = 4 * nu + 3 * nd + self.DBG_SCALARS
+        records = np.zeros(max(nds, 1) * rec, np.float32)
+        cap = max(self.n_llr(L, training), 1)
+        llr = np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        check(lib().pu_ofdm_presynced_debug(self._h, _ptr(x), C.c_size_t(L), int(training), C.c_float(cfo_hz),
+                                            C.c_float(cfo_phase), _ptr(llr), C.c_size_t(cap), _ptr(records),
+                                            C.c_size_t(len(records)), C.byref(n)))
+        r = records[: nds * rec].reshape(nds, rec)
+        cplx = lambda a: np.ascontiguousarray(a).view(np.complex64)
+        return dict(n_sym=nds, carriers=self.carrier_bins(), llr=llr[: self.n_llr(L, training)],
+                    bins=cplx(r[:, : 2 * nu]), h=cplx(r[:, 2 * nu: 4 * nu]), eq=cplx(r[:, 4 * nu: 4 * nu + 2 * nd]),
+                    nv=r[:, 4 * nu + 2 * nd: 4 * nu + 3 * nd].copy(), scalars=r[:, 4 * nu + 3 * nd:].copy())

@@ -1,0 +1,887 @@
+// projectultra_b200/csrc/ofdm_demod.cu — batched presynced OFDM receive path for sm_100a and the pu_ofdm_*
+// entry points of the C ABI: baseband mix -> FFT -> LTS channel estimate -> pilot tracking -> interpolation ->
+// equaliser -> soft demapper, one launch, LLRs written once.
+//
+// Reference behaviour: OFDMDemodulator::processPresynced (src/ofdm/demodulator.cpp:854-985) after
+// reset() + setFrequencyOffset[WithPhase]() on a fresh object, i.e. the per-frame algorithm of SURVEY App. E:
+//   toBaseband            src/ofdm/channel_equalizer.cpp:19-57   (NCO mix over ALL samples, optional CFO rotator)
+//   extractSymbol + FFT   :59-71, src/dsp/fft.cpp:89-121         (drop CP, in-order radix-2 DIT)
+//   estimateChannelFromLTS :77-328                               (data H = last LTS symbol, pilot H = mean)
+//   updateChannelEstimate :330-595                               (pilot LS, phase lock, EMA, CFO / timing / noise trackers)
+//   interpolateChannel    :601-631
+//   equalize              :728-840                               (ZF for differential, MMSE + fade erasure for coherent)
+//   demodulateSymbol      src/ofdm/demodulator.cpp:199-356, soft_demap.hpp
+// The decision-directed tracker block (demodulator.cpp:362-434) is numerically dead (it reads
+// the reference symbol after it was overwritten, so every correction is exactly (1,+-0)); it is not executed here.
+//
+// Numerics: the FFT performs the reference's radix-2 butterflies in the reference's order (fused in registers
+// three stages at a time) with unfused fp32 multiplies/adds, so FFT bins, H and equalised symbols are bit-identical
+// to the reference; only libm calls (atan2f, sinf, cosf) differ at the ulp level.  Compiled with -fmad=false.
+//
+// Kernel shape: one frame per CTA of NFFT/8 threads; the frame's symbols are walked in order because in pilot
+// modes symbol s+1's mixer depends on the CFO tracked in symbol s.  Shared memory holds one padded FFT buffer,
+// the per-carrier state and the trackers.
+#include <cfloat>
+#include <memory>
+#include <new>
+
+#include "ofdm_plan.h"
+#include "pu_internal.h"
+
+namespace pu {
+
+constexpr int kMaxCarr = 64;
+constexpr int kDbgScalars = 10;
+
+struct OfdmDev {
+    int nfft, log2n, cp, sym_len, n_data, n_pilot, bps, mod;
+    float ce_margin, sample_rate;
+    const float2* twiddle;   // [nfft/2]
+    const float2* nco;       // [max_symbols * sym_len] (cos, sin)
+    int nco_len;
+    const int* data_bin;     // [n_data]
+    const int* pilot_bin;    // [n_pilot]
+    const float2* zc;        // [n_data] known LTS symbol on data carrier i
+    const float* pilot_sign; // [n_pilot]
+    const int* interp_lo;    // [n_data]
+    const int* interp_hi;
+    const float* interp_alpha;
+    const int* llr_perm;     // optional [perm_len]: output position of LLR index i (fused deinterleave), or NULL
+    int perm_len;
+};
+
+// ---- std::complex<float> arithmetic as GCC lowers it (no FMA, naive formulas) ----
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),
+                       __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
+__device__ __forceinline__ float2 cdivs(float2 a, float s) { return make_float2(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s)); }
+__device__ __forceinline__ float cnorm(float2 a) { return __fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)); }
+// complex / complex: libgcc __divsc3 evaluates the textbook formula in double when the hardware has doubles
+__device__ __forceinline__ float2 cdiv(float2 a, float2 b) {
+    const double aa = a.x, bb = a.y, cc = b.x, dd = b.y;
+    const double den = __dadd_rn(__dmul_rn(cc, cc), __dmul_rn(dd, dd));
+    const double x = __ddiv_rn(__dadd_rn(__dmul_rn(aa, cc), __dmul_rn(bb, dd)), den);
+    const double y = __ddiv_rn(__dsub_rn(__dmul_rn(bb, cc), __dmul_rn(aa, dd)), den);
+    return make_float2(static_cast<float>(x), static_cast<float>(y));
+}
+// std::abs(complex<float>) = hypotf: glibc evaluates sqrt(x*x + y*y) in double
+__device__ __forceinline__ float cabs_ref(float2 a) {
+    const double x = a.x, y = a.y;
+    return static_cast<float>(__dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y))));
+}
+__device__ __forceinline__ float clampf(float lo, float hi, float v) { return fmaxf(lo, fminf(hi, v)); }
+
+// soft_demap::clipLLR, soft_demap.hpp:22-29
+__device__ __forceinline__ float clip_llr(float llr) {
+    float c = clampf(-10.0f, 10.0f, llr);
+    if (fabsf(c) < 0.5f) c = (c >= 0.0f) ? 0.5f : -0.5f;
+    return c;
+}
+
+#define PADIDX(p) ((p) + ((p) >> 3))   // one float2 of padding per 8 keeps the strided passes off the same banks
+
+__device__ __forceinline__ void butterfly(float2& a, float2& b, float2 w) {
+    const float2 t = cmul(w, b);     // Complex t = w * data[i + k + half]      (fft.cpp:108)
+    b = csub(a, t);                  // data[i + k + half] = data[i + k] - t
+    a = cadd(a, t);                  // data[i + k]        = data[i + k] + t
+}
+
+// R consecutive radix-2 stages (global stages S0+1 .. S0+R) on the 2^R elements base + q*2^S0 held in registers.
+template <int R, int S0, int LOG2N>
+__device__ __forceinline__ void stages_in_regs(float2 (&v)[1 << R], int lo, const float2* __restrict__ tw) {
+#pragma unroll
+    for (int t = 1; t <= R; ++t) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int half = 1 << (t - 1);
+#pragma unroll
+        for (int pr = 0; pr < (1 << (R - 1)); ++pr) {
+            const int kq = pr & (half - 1);
+            const int a = ((pr >> (t - 1)) << t) | kq;
+            const int k = lo + (kq << S0);
+            const float2 w = __ldg(&tw[k << (LOG2N - S0 - t)]);
+            butterfly(v[a], v[a + half], w);
+        }
+    }
+}
+
+template <int R, int S0, int LOG2N>
+__device__ __forceinline__ void fft_pass_smem(float2* buf, int gid, const float2* __restrict__ tw) {
+    const int lo = gid & ((1 << S0) - 1);
+    const int base = ((gid >> S0) << (S0 + R)) | lo;
+    float2 v[1 << R];
+#pragma unroll
+    for (int q = 0; q < (1 << R); ++q) v[q] = buf[PADIDX(base + (q << S0))];
+    stages_in_regs<R, S0, LOG2N>(v, lo, tw);
+#pragma unroll
+    for (int q = 0; q < (1 << R); ++q) buf[PADIDX(base + (q << S0))] = v[q];
+}
+
+struct RxShared {
+    float2 Hd[kMaxCarr];      // channel_estimate at data carriers
+    float2 Hp[kMaxCarr];      // channel_estimate at pilot carriers
+    float2 Fd[kMaxCarr];      // FFT bins at data carriers
+    float2 Fp[kMaxCarr];      // FFT bins at pilot carriers
+    float2 hls[kMaxCarr];     // h_ls_all
+    float2 prevp[kMaxCarr];   // prev_pilot_phases
+    float2 preveq[kMaxCarr];  // dbpsk_prev_equalized
+    float2 eq[kMaxCarr];
+    float2 tmpc[kMaxCarr];
+    float tmpa[kMaxCarr], tmpb[kMaxCarr], tmpd[kMaxCarr];
+    float cnv[kMaxCarr];      // carrier_noise_var
+    int valid[kMaxCarr];
+    // trackers (demodulator_impl.hpp)
+    float cfo_hz, cfo_filt, rot_phase, noise_var, snr_lin, timing;
+    int snr_cnt, since_sync, have_prev, cpc_init, have_preveq;
+    float2 ppc, cpc;
+    float cfo_used;
+};
+
+template <int NFFT>
+__global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
+    OfdmDev d, const float* __restrict__ samples, size_t frame_stride, int n_symbols, int training,
+    const float* __restrict__ cfo_hz, const float* __restrict__ cfo_phase,
+    float* __restrict__ llr_out, size_t llr_stride, int llr_limit,
+    float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out, float* __restrict__ dbg) {
+    constexpr int LOG2N = (NFFT == 512) ? 9 : 10;
+    constexpr int T = NFFT / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);                       // [NFFT + NFFT/8]
+    float* theta = reinterpret_cast<float*>(buf + NFFT + NFFT / 8);          // [sym_len] rotator phases
+    RxShared& S = *reinterpret_cast<RxShared*>(theta + ((d.sym_len + 3) & ~3));
+    const int tid = threadIdx.x;
+    const size_t frame = blockIdx.x;
+    const float* x = samples + frame * frame_stride;
+    const int nd = d.n_data, np = d.n_pilot, nu = nd + np;
+    const bool differential = (d.mod == PU_MOD_DBPSK || d.mod == PU_MOD_DQPSK || d.mod == PU_MOD_D8PSK);
+    const float kPiF_dbl_2 = 0.0f;
+    (void)kPiF_dbl_2;
+
+    if (tid == 0) {
+        const float f = cfo_hz ? cfo_hz[frame] : 0.0f;
+        S.cfo_hz = f;
+        S.cfo_filt = f;
+        S.rot_phase = cfo_phase ? cfo_phase[frame] : 0.0f;
+        S.noise_var = 0.1f;
+        S.snr_lin = 1.0f;
+        S.timing = 0.0f;
+        S.snr_cnt = 0;
+        S.since_sync = 0;
+        S.have_prev = 0;
+        S.cpc_init = 0;
+        S.have_preveq = 0;
+        S.ppc = make_float2(1.0f, 0.0f);
+        S.cpc = make_float2(1.0f, 0.0f);
+    }
+    for (int i = tid; i < kMaxCarr; i += T) {
+        S.Hd[i] = make_float2(1.0f, 0.0f);
+        S.Hp[i] = make_float2(1.0f, 0.0f);
+        S.preveq[i] = make_float2(1.0f, 0.0f);   // differential reference (1,0): channel_equalizer.cpp:300, demodulator.cpp:251-255
+        S.tmpc[i] = make_float2(0.0f, 0.0f);     // h_sum_pilot accumulator during the LTS phase
+    }
+    __syncthreads();
+
+    int llr_pos = 0;   // LLRs emitted so far (same for all threads)
+    for (int s = 0; s < n_symbols; ++s) {
+        const bool is_train = s < training;
+        const float* xs = x + static_cast<size_t>(s) * d.sym_len;
+        const float2* nco = d.nco + static_cast<size_t>(s) * d.sym_len;
+        // ---------------- rotator phases (channel_equalizer.cpp:23,39-51): a per-sample float recurrence
+        const bool rot = fabsf(S.cfo_hz) > 0.01f;
+        if (rot && tid == 0) {
+            const float inc = static_cast<float>(__ddiv_rn(__dmul_rn(-2.0f * 3.14159265358979323846, (double)S.cfo_hz), (double)d.sample_rate));
+            float ph = S.rot_phase;
+            const float pi_hi = 3.14159274101257324f;   // smallest float > M_PI: (double)ph > M_PI  <=>  ph >= pi_hi
+            for (int i = 0; i < d.sym_len; ++i) {
+                theta[i] = ph;
+                ph = __fadd_rn(ph, inc);
+                if (ph >= pi_hi) ph = static_cast<float>((double)ph - 2.0f * 3.14159265358979323846);
+                else if (ph <= -pi_hi) ph = static_cast<float>((double)ph + 2.0f * 3.14159265358979323846);
+            }
+            S.rot_phase = ph;
+        }
+        if (tid == 0) S.cfo_used = S.cfo_hz;
+        __syncthreads();
+        const bool skip_fft = is_train && np == 0 && s != training - 1;   // data H uses the LAST LTS symbol only (:179-185)
+        if (!skip_fft) {
+            // ---------------- mix + stages 1..3: group g owns bit-reversed positions 8g..8g+7 = samples brev(8g+q)
+            {
+                const int g = tid;
+                const int r = __brev(static_cast<unsigned>(g)) >> (32 - (LOG2N - 3));
+                float2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int brq = ((q & 1) << 2) | (q & 2) | ((q >> 2) & 1);
+                    const int n = d.cp + (brq << (LOG2N - 3)) + r;
+                    const float xv = __ldg(&xs[n]);
+                    const float2 o = __ldg(&nco[n]);
+                    float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
+                    if (rot) {
+                        float sn, cs;
+                        sincosf(theta[n], &sn, &cs);
+                        z = cmul(z, make_float2(cs, sn));                               // mixed *= correction (:42)
+                    }
+                    v[q] = z;
+                }
+                stages_in_regs<3, 0, LOG2N>(v, 0, d.twiddle);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) buf[PADIDX(8 * g + q)] = v[q];
+            }
+            __syncthreads();
+            fft_pass_smem<3, 3, LOG2N>(buf, tid, d.twiddle);     // stages 4..6
+            __syncthreads();
+            if constexpr (NFFT == 512) {
+                fft_pass_smem<2, 6, LOG2N>(buf, tid, d.twiddle);          // stages 7..8: 128 groups of 4
+                fft_pass_smem<2, 6, LOG2N>(buf, tid + T, d.twiddle);
+            } else {
+                fft_pass_smem<3, 6, LOG2N>(buf, tid, d.twiddle);          // stages 7..9
+            }
+            __syncthreads();
+            // ---------------- last stage, only for the bins that are used
+            for (int u = tid; u < nu; u += T) {
+                const int bin = u < nd ? d.data_bin[u] : d.pilot_bin[u - nd];
+                const int k = bin & (NFFT / 2 - 1);
+                const float2 w = __ldg(&d.twiddle[k]);
+                const float2 a = buf[PADIDX(k)];
+                const float2 t = cmul(w, buf[PADIDX(k + NFFT / 2)]);
+                const float2 out = (bin < NFFT / 2) ? cadd(a, t) : csub(a, t);
+                if (u < nd) S.Fd[u] = out;
+                else S.Fp[u - nd] = out;
+            }
+        }
+        __syncthreads();
+
+        if (is_train) {
+            // ---------------- estimateChannelFromLTS (channel_equalizer.cpp:137-194)
+            if (!skip_fft) {
+                for (int i = tid; i < nd; i += T)
+                    if (s == training - 1) S.Hd[i] = cdiv(S.Fd[i], d.zc[i]);
+                for (int i = tid; i < np; i += T)   // rx / (+-1, 0) accumulated over the training symbols
+                    S.tmpc[i] = cadd(S.tmpc[i], make_float2(__fmul_rn(S.Fp[i].x, d.pilot_sign[i]), __fmul_rn(S.Fp[i].y, d.pilot_sign[i])));
+            }
+            if (s == training - 1) {
+                __syncthreads();
+                const float inv = __fdiv_rn(1.0f, static_cast<float>(training));
+                for (int i = tid; i < np; i += T) S.Hp[i] = cscale(inv, S.tmpc[i]);
+                for (int i = tid; i < nd; i += T) S.tmpa[i] = cabs_ref(S.Hd[i]);
+                __syncthreads();
+                if (tid == 0) {   // reporting-only SNR estimate (:208-225)
+                    float sum = 0.0f;
+                    for (int i = 0; i < nd; ++i) sum = __fadd_rn(sum, S.tmpa[i]);
+                    const float avg = __fdiv_rn(sum, static_cast<float>(nd));
+                    if (avg > 1e-6f && S.noise_var > 1e-10f)
+                        S.snr_lin = clampf(0.1f, 10000.0f, __fdiv_rn(__fmul_rn(avg, avg), S.noise_var));
+                    S.snr_cnt = training;   // :327
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ================= data symbol =================
+        if (np > 0) {
+            // ---------------- updateChannelEstimate (channel_equalizer.cpp:330-595)
+            const float alpha = (S.snr_cnt == 0) ? 1.0f : 0.9f;
+            for (int i = tid; i < np; i += T)
+                S.hls[i] = make_float2(__fmul_rn(S.Fp[i].x, d.pilot_sign[i]), __fmul_rn(S.Fp[i].y, d.pilot_sign[i]));
+            __syncthreads();
+            if (tid == 0 && !S.cpc_init) {   // carrier phase lock on the first data symbol (:348-357)
+                float2 sum = make_float2(0.0f, 0.0f);
+                for (int i = 0; i < np; ++i) sum = cadd(sum, S.hls[i]);
+                const float2 avg = cdivs(sum, static_cast<float>(np));
+                const float mag = cabs_ref(avg);
+                if (mag > 0.01f) {
+                    S.cpc = cdivs(cconj(avg), mag);
+                    S.cpc_init = 1;
+                }
+            }
+            __syncthreads();
+            const int have_prev = S.have_prev;
+            for (int i = tid; i < np; i += T) {
+                const float2 h = cmul(S.hls[i], S.cpc);   // :360-362
+                S.hls[i] = h;
+                const float nh = cnorm(h);
+                S.tmpa[i] = nh;
+                int v = 0;
+                float dn = 0.0f;
+                float2 unit = make_float2(0.0f, 0.0f);
+                int vu = 0;
+                if (have_prev) {
+                    const float2 p = S.prevp[i];
+                    const float npv = cnorm(p);
+                    if (npv > 1e-6f && nh > 1e-6f) {
+                        v = 1;
+                        dn = cnorm(csub(h, p));                        // temporal noise (:402-406)
+                        const float2 df = cmul(h, cconj(p));           // CFO phase step (:426-435)
+                        const float mag = cabs_ref(df);
+                        if (mag > 1e-6f) {
+                            unit = cdivs(df, mag);
+                            vu = 1;
+                        }
+                    }
+                }
+                S.tmpb[i] = dn;
+                S.valid[i] = v | (vu << 1);
+                S.tmpc[i] = unit;
+                const float2 hold = S.Hp[i];
+                S.Hp[i] = cadd(cscale(alpha, h), cscale(__fsub_rn(1.0f, alpha), hold));   // EMA (:410-411)
+                if (S.snr_cnt >= 3 && nh >= 1e-6f) S.tmpd[i] = atan2f(h.y, h.x);          // std::arg for the timing fit (:483)
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float sp_sum = 0.0f;
+                for (int i = 0; i < np; ++i) sp_sum = __fadd_rn(sp_sum, S.tmpa[i]);
+                const float signal_power = __fdiv_rn(sp_sum, static_cast<float>(np));
+                float noise_sum = 0.0f;
+                int noise_count = 0;
+                for (int i = 0; i < np; ++i)
+                    if (S.valid[i] & 1) { noise_sum = __fadd_rn(noise_sum, S.tmpb[i]); ++noise_count; }
+                if (noise_count == 0) { noise_sum = __fdiv_rn(signal_power, 31.6f); noise_count = 1; }   // :415-418
+                if (have_prev) {   // :421-467
+                    float2 ps = make_float2(0.0f, 0.0f);
+                    int vc = 0;
+                    for (int i = 0; i < np; ++i)
+                        if (S.valid[i] & 2) { ps = cadd(ps, S.tmpc[i]); ++vc; }
+                    if (vc > 0) {
+                        const float2 avg = cdivs(ps, static_cast<float>(vc));
+                        const float apd = atan2f(avg.y, avg.x);
+                        float sn, cs;
+                        sincosf(-apd, &sn, &cs);
+                        S.ppc = make_float2(cs, sn);
+                        const float sym_dur = __fdiv_rn(static_cast<float>(d.sym_len), d.sample_rate);
+                        const float residual = static_cast<float>(__ddiv_rn((double)apd, __dmul_rn(2.0f * 3.14159265358979323846, (double)sym_dur)));
+                        const float total = __fadd_rn(S.cfo_hz, residual);
+                        float a = 0.3f;
+                        if (S.since_sync < 10) {
+                            const float progress = __fdiv_rn(static_cast<float>(S.since_sync), 10.0f);
+                            a = __fadd_rn(__fmul_rn(0.9f, __fsub_rn(1.0f, progress)), __fmul_rn(0.3f, progress));
+                        }
+                        if (fabsf(residual) > 10.0f) a = fmaxf(a, 0.9f);
+                        S.since_sync++;
+                        S.cfo_filt = __fadd_rn(__fmul_rn(a, total), __fmul_rn(__fsub_rn(1.0f, a), S.cfo_filt));
+                        S.cfo_hz = clampf(-90.0f, 90.0f, S.cfo_filt);
+                    }
+                } else {
+                    S.ppc = make_float2(1.0f, 0.0f);   // :468-470
+                }
+                if (S.snr_cnt >= 3) {   // timing slope by least squares over the pilots (:473-509)
+                    float sk = 0.0f, sk2 = 0.0f, sph = 0.0f, skp = 0.0f;
+                    int cnt = 0;
+                    for (int i = 0; i < np; ++i) {
+                        if (S.tmpa[i] < 1e-6f) continue;
+                        int k = d.pilot_bin[i];
+                        if (k > NFFT / 2) k -= NFFT;
+                        const float ph = S.tmpd[i];
+                        sk = __fadd_rn(sk, static_cast<float>(k));
+                        sk2 = __fadd_rn(sk2, static_cast<float>(k * k));
+                        sph = __fadd_rn(sph, ph);
+                        skp = __fadd_rn(skp, __fmul_rn(static_cast<float>(k), ph));
+                        ++cnt;
+                    }
+                    if (cnt >= 3) {
+                        const float n = static_cast<float>(cnt);
+                        const float den = __fsub_rn(__fmul_rn(n, sk2), __fmul_rn(sk, sk));
+                        if (fabsf(den) > 1e-6f) {
+                            const float slope = __fdiv_rn(__fsub_rn(__fmul_rn(n, skp), __fmul_rn(sk, sph)), den);
+                            const float inst = static_cast<float>(__ddiv_rn((double)__fmul_rn(slope, static_cast<float>(NFFT)), 2.0f * 3.14159265358979323846));
+                            float tm = __fadd_rn(__fmul_rn(0.3f, inst), __fmul_rn(__fsub_rn(1.0f, 0.3f), S.timing));
+                            const float maxt = __fmul_rn(50.0f, __fdiv_rn(static_cast<float>(NFFT), 512.0f));
+                            S.timing = clampf(-maxt, maxt, tm);
+                        }
+                    }
+                }
+                S.have_prev = 1;
+                if (noise_count > 1 && noise_sum > 0.0f) {   // :584-592
+                    float nv = __fdiv_rn(noise_sum, static_cast<float>(noise_count - 1));
+                    if (nv < 1e-6f) nv = 1e-6f;
+                    S.noise_var = nv;
+                    const float inst = clampf(0.1f, 10000.0f, __fdiv_rn(signal_power, nv));
+                    S.snr_lin = __fadd_rn(__fmul_rn(0.3f, inst), __fmul_rn(__fsub_rn(1.0f, 0.3f), S.snr_lin));
+                }
+                S.snr_cnt++;
+            }
+            for (int i = tid; i < np; i += T) S.prevp[i] = S.hls[i];   // :512
+            __syncthreads();
+            // coherent timing fix, interpolation, timing restore (:514-567, :601-631)
+            const float timing = S.timing;
+            const bool fix = !differential && fabsf(timing) > 0.1f;
+            if (fix) {
+                for (int i = tid; i < np; i += T) {
+                    int k = d.pilot_bin[i];
+                    if (k > NFFT / 2) k -= NFFT;
+                    const float tp = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(2.0f * 3.14159265358979323846, (double)k), (double)timing), (double)static_cast<float>(NFFT)));
+                    float sn, cs;
+                    sincosf(-tp, &sn, &cs);                 // std::exp(Complex(0, -timing_phase))
+                    S.Hp[i] = cmul(S.Hp[i], make_float2(cs, sn));
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < nd; i += T) {
+                const int lo = d.interp_lo[i], hi = d.interp_hi[i];
+                if (lo >= 0 && hi >= 0) {
+                    const float2 H1 = S.Hp[lo], H2 = S.Hp[hi];
+                    const float2 pd = cmul(H2, cconj(H1));
+                    const float ph = fabsf(atan2f(pd.y, pd.x));
+                    const float a = d.interp_alpha[i];
+                    if (ph > 1.5708f) S.Hd[i] = (a < 0.5f) ? H1 : H2;
+                    else S.Hd[i] = cadd(cscale(__fsub_rn(1.0f, a), H1), cscale(a, H2));
+                } else if (lo >= 0) {
+                    S.Hd[i] = S.Hp[lo];
+                } else if (hi >= 0) {
+                    S.Hd[i] = S.Hp[hi];
+                }
+            }
+            if (fix) {
+                __syncthreads();
+                for (int u = tid; u < nu; u += T) {
+                    int k = u < nd ? d.data_bin[u] : d.pilot_bin[u - nd];
+                    if (k > NFFT / 2) k -= NFFT;
+                    const float tp = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(2.0f * 3.14159265358979323846, (double)k), (double)timing), (double)static_cast<float>(NFFT)));
+                    float sn, cs;
+                    sincosf(tp, &sn, &cs);
+                    if (u < nd) S.Hd[u] = cmul(S.Hd[u], make_float2(cs, sn));
+                    else S.Hp[u - nd] = cmul(S.Hp[u - nd], make_float2(cs, sn));
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---------------- equalize (channel_equalizer.cpp:728-840)
+        const float noise_var = S.noise_var;
+        if (differential) {
+            const float timing = S.timing;
+            const float2 ppc = S.ppc;
+            for (int i = tid; i < nd; i += T) {
+                const float2 rx = S.Fd[i], h = S.Hd[i];
+                const float hp = cnorm(h);
+                int k = d.data_bin[i];
+                if (k > NFFT / 2) k -= NFFT;
+                const float tp = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(2.0f * 3.14159265358979323846, (double)k), (double)timing), (double)static_cast<float>(NFFT)));
+                float2 tc = make_float2(1.0f, 0.0f);       // std::exp(Complex(0, 0)) == (1, 0)
+                if (tp != 0.0f) {
+                    float sn, cs;
+                    sincosf(tp, &sn, &cs);
+                    tc = make_float2(cs, sn);
+                }
+                float2 e;
+                float nv;
+                if (hp > 1e-6f) {
+                    e = cmul(cmul(cdivs(cmul(rx, cconj(h)), hp), ppc), tc);   // :761
+                    nv = __fdiv_rn(noise_var, hp);
+                } else {
+                    e = cmul(cmul(rx, ppc), tc);
+                    nv = 100.0f;
+                }
+                S.eq[i] = e;
+                S.cnv[i] = clampf(1e-6f, 100.0f, nv);
+            }
+        } else {
+            for (int i = tid; i < nd; i += T) {
+                const float2 rx = S.Fd[i], h = S.Hd[i];
+                const float hp = cnorm(h);
+                S.tmpa[i] = hp;
+                const float den = __fadd_rn(hp, noise_var);
+                if (den < 1e-10f) {
+                    S.eq[i] = make_float2(0.0f, 0.0f);
+                    S.cnv[i] = 100.0f;
+                } else {
+                    S.eq[i] = cdivs(cmul(cconj(h), rx), den);                                          // MMSE (:815)
+                    S.cnv[i] = clampf(1e-6f, 100.0f, __fdiv_rn(noise_var, __fadd_rn(hp, 1e-6f)));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {   // deep-fade erasure threshold (:823-830): ordered sum
+                float sum = 0.0f;
+                for (int i = 0; i < nd; ++i) sum = __fadd_rn(sum, S.tmpa[i]);
+                S.tmpb[0] = __fmul_rn(0.1f, __fdiv_rn(sum, static_cast<float>(nd)));
+            }
+            __syncthreads();
+            const float thr = S.tmpb[0];
+            for (int i = tid; i < nd; i += T)
+                if (S.tmpa[i] < thr) S.cnv[i] = 100.0f;
+        }
+        __syncthreads();
+
+        // ---------------- debug dump of this symbol's intermediates (tests only)
+        if (dbg) {
+            const int sd = s - training;
+            float* rec = dbg + (frame * static_cast<size_t>(n_symbols - training) + sd) * (4 * nu + 3 * nd + kDbgScalars);
+            for (int u = tid; u < nu; u += T) {
+                const float2 f = u < nd ? S.Fd[u] : S.Fp[u - nd];
+                const float2 h = u < nd ? S.Hd[u] : S.Hp[u - nd];
+                rec[2 * u] = f.x; rec[2 * u + 1] = f.y;
+                rec[2 * nu + 2 * u] = h.x; rec[2 * nu + 2 * u + 1] = h.y;
+            }
+            for (int i = tid; i < nd; i += T) {
+                rec[4 * nu + 2 * i] = S.eq[i].x; rec[4 * nu + 2 * i + 1] = S.eq[i].y;
+                rec[4 * nu + 2 * nd + i] = S.cnv[i];
+            }
+            if (tid == 0) {
+                float* sc = rec + 4 * nu + 3 * nd;
+                sc[0] = S.cfo_used; sc[1] = S.cfo_hz; sc[2] = S.noise_var; sc[3] = S.timing; sc[4] = S.snr_lin;
+                sc[5] = S.ppc.x; sc[6] = S.ppc.y; sc[7] = S.cpc.x; sc[8] = S.cpc.y; sc[9] = static_cast<float>(S.snr_cnt);
+            }
+        }
+
+        // ---------------- demodulateSymbol (demodulator.cpp:279-356) + soft_demap.hpp
+        float* out = llr_out + frame * llr_stride;
+        for (int i = tid; i < nd; i += T) {
+            const float2 sym = S.eq[i];
+            const float nv = __fmul_rn(S.cnv[i], d.ce_margin);
+            float l[8];
+            int nb = d.bps;
+            if (differential) {
+                const float2 prev = S.preveq[i];
+                const float2 df = cmul(sym, cconj(prev));
+                const float sp = __fmul_rn(cabs_ref(sym), cabs_ref(prev));
+                S.preveq[i] = sym;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) l[b] = 0.0f;
+                if (!(sp < 1e-6f)) {
+                    const float phase = atan2f(df.y, df.x);
+                    if (d.mod == PU_MOD_DBPSK) {              // soft_demap.hpp:173-187
+                        l[0] = clip_llr(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, sp), cosf(phase)), nv));
+                    } else if (d.mod == PU_MOD_DQPSK) {       // :192-213
+                        const float scale = __fdiv_rn(__fmul_rn(2.0f, sp), nv);
+                        const float pi = 3.14159265358979f;
+                        l[0] = clip_llr(__fmul_rn(scale, sinf(__fadd_rn(phase, pi / 4))));
+                        l[1] = clip_llr(__fmul_rn(scale, cosf(__fmul_rn(2.0f, phase))));
+                    } else {                                  // D8PSK :217-237
+                        const float conf = __fdiv_rn(sp, nv);
+                        l[0] = clip_llr(__fmul_rn(conf, sinf(phase)));
+                        l[1] = clip_llr(__fmul_rn(conf, sinf(__fmul_rn(2.0f, phase))));
+                        l[2] = clip_llr(__fmul_rn(conf, sinf(__fmul_rn(4.0f, phase))));
+                    }
+                }
+            } else {
+                const float I = sym.x, Q = sym.y;
+                switch (d.mod) {
+                    case PU_MOD_BPSK:      // :37-39
+                        l[0] = clip_llr(__fdiv_rn(__fmul_rn(-2.0f, I), nv));
+                        break;
+                    case PU_MOD_QAM16: {   // :49-64
+                        const float sc = __fdiv_rn(2.0f, nv);
+                        l[0] = clip_llr(__fmul_rn(-sc, I));
+                        l[1] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(I), 0.6324555320336759f)));
+                        l[2] = clip_llr(__fmul_rn(-sc, Q));
+                        l[3] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(Q), 0.6324555320336759f)));
+                        break;
+                    }
+                    case PU_MOD_QAM32: {   // :68-121 max-log over the 4(I) x 8(Q) grid; the 32 distances are shared by the 5 bits
+                        const float sc = __fdiv_rn(2.0f, nv);
+                        const float qs = 0.1961161351381840f;
+                        float d0[5], d1[5];
+#pragma unroll
+                        for (int b = 0; b < 5; ++b) { d0[b] = 1e10f; d1[b] = 1e10f; }
+#pragma unroll
+                        for (int qi = 0; qi < 8; ++qi) {
+                            const int qg = qi ^ (qi >> 1);   // Q_GRAY = {0,1,3,2,6,7,5,4}
+                            const float dq = __fsub_rn(Q, __fmul_rn(static_cast<float>(2 * qi - 7), qs));
+                            const float dq2 = __fmul_rn(dq, dq);
+#pragma unroll
+                            for (int ii = 0; ii < 4; ++ii) {
+                                const int ig = ii ^ (ii >> 1);   // I_GRAY = {0,1,3,2}
+                                const float di = __fsub_rn(I, __fmul_rn(static_cast<float>(2 * ii - 3), qs));
+                                const float dist = __fadd_rn(__fmul_rn(di, di), dq2);
+                                const int bits = (qg << 2) | ig;
+#pragma unroll
+                                for (int b = 0; b < 5; ++b) {
+                                    if (bits & (1 << (4 - b))) d1[b] = fminf(d1[b], dist);
+                                    else d0[b] = fminf(d0[b], dist);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int b = 0; b < 5; ++b) l[b] = clip_llr(__fmul_rn(sc, __fsub_rn(d1[b], d0[b])));
+                        break;
+                    }
+                    case PU_MOD_QAM64: {   // :124-141
+                        const float sc = __fdiv_rn(2.0f, nv);
+                        const float D4 = 0.6172134f, D2 = 0.3086067f;
+                        l[0] = clip_llr(__fmul_rn(-sc, I));
+                        l[1] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(I), D4)));
+                        l[2] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(__fsub_rn(fabsf(I), D4)), D2)));
+                        l[3] = clip_llr(__fmul_rn(-sc, Q));
+                        l[4] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(Q), D4)));
+                        l[5] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(__fsub_rn(fabsf(Q), D4)), D2)));
+                        break;
+                    }
+                    case PU_MOD_QAM256: {  // :144-163
+                        const float sc = __fdiv_rn(2.0f, nv);
+                        const float D8 = 0.5163978f, D4 = 0.2581989f, D2 = 0.1290994f;
+                        const float a1 = __fsub_rn(fabsf(I), D8), a2 = __fsub_rn(fabsf(a1), D4);
+                        const float b1 = __fsub_rn(fabsf(Q), D8), b2 = __fsub_rn(fabsf(b1), D4);
+                        l[0] = clip_llr(__fmul_rn(-sc, I));
+                        l[1] = clip_llr(__fmul_rn(sc, a1));
+                        l[2] = clip_llr(__fmul_rn(sc, a2));
+                        l[3] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(a2), D2)));
+                        l[4] = clip_llr(__fmul_rn(-sc, Q));
+                        l[5] = clip_llr(__fmul_rn(sc, b1));
+                        l[6] = clip_llr(__fmul_rn(sc, b2));
+                        l[7] = clip_llr(__fmul_rn(sc, __fsub_rn(fabsf(b2), D2)));
+                        break;
+                    }
+                    default: {             // QPSK :42-45
+                        const float sc = __fdiv_rn(__fmul_rn(-2.0f, 0.7071067811865476f), nv);
+                        l[0] = clip_llr(__fmul_rn(I, sc));
+                        l[1] = clip_llr(__fmul_rn(Q, sc));
+                        nb = 2;
+                    }
+                }
+            }
+            const int base = llr_pos + i * nb;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < nb) {
+                    const int pos = base + b;
+                    if (pos < llr_limit) {
+                        const int dst = (d.llr_perm && pos < d.perm_len) ? d.llr_perm[pos] : pos;
+                        out[dst] = l[b];
+                    }
+                }
+            }
+        }
+        llr_pos += nd * d.bps;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (snr_db_out) snr_db_out[frame] = 10.0f * log10f(S.snr_lin);   // getEstimatedSNR, demodulator.cpp:797-799
+        if (final_cfo_out) final_cfo_out[frame] = S.cfo_hz;              // getFrequencyOffset, :801-803
+    }
+}
+
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+    template <class T>
+    pu_status upload(const T* src, size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        PU_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+        if (n) PU_CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+        return PU_OK;
+    }
+};
+
+}  // namespace pu
+
+struct pu_ofdm {
+    pu_ctx* ctx = nullptr;
+    pu::OfdmPlan plan;
+    pu::OfdmDev dev{};
+    pu::DevMem d_tw, d_nco, d_dbin, d_pbin, d_zc, d_psign, d_ilo, d_ihi, d_ia, d_perm;
+    int max_symbols = 0;
+    size_t smem_bytes = 0;
+
+    pu_status ensure_nco(int n_symbols) {
+        if (n_symbols <= max_symbols) return PU_OK;
+        const int want = std::max(n_symbols, 32);
+        std::vector<pu::cfloat> t = plan.nco(static_cast<float>(plan.cfg.center_freq), static_cast<size_t>(want) * plan.sym_len);
+        pu_status s = d_nco.upload(t.data(), t.size());
+        if (s != PU_OK) return s;
+        dev.nco = static_cast<const float2*>(d_nco.p);
+        dev.nco_len = static_cast<int>(t.size());
+        max_symbols = want;
+        return PU_OK;
+    }
+};
+
+extern "C" {
+
+pu_status pu_ofdm_create(pu_ctx* ctx, const pu_modem_config* cfg, pu_ofdm** out) {
+    PU_REQUIRE(ctx && cfg && out, "pu_ofdm_create: NULL argument");
+    *out = nullptr;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    std::unique_ptr<pu_ofdm> h(new (std::nothrow) pu_ofdm());
+    if (!h) return PU_ERR_NOMEM;
+    h->ctx = ctx;
+    const char* why = "";
+    if (!pu::make_ofdm_plan(*cfg, &h->plan, &why)) {
+        pu::set_error("pu_ofdm_create: %s", why);
+        return PU_ERR_UNSUPPORTED;
+    }
+    const pu::OfdmPlan& p = h->plan;
+    std::vector<pu::cfloat> zc(p.n_data);
+    for (int i = 0; i < p.n_data; ++i) zc[i] = p.sync_seq[i % p.cfg.num_carriers];   // channel_equalizer.cpp:141
+    pu_status s;
+    if ((s = h->d_tw.upload(p.twiddle.data(), p.twiddle.size())) != PU_OK) return s;
+    if ((s = h->d_dbin.upload(p.data_bin.data(), p.data_bin.size())) != PU_OK) return s;
+    if ((s = h->d_pbin.upload(p.pilot_bin.data(), p.pilot_bin.size())) != PU_OK) return s;
+    if ((s = h->d_zc.upload(zc.data(), zc.size())) != PU_OK) return s;
+    if ((s = h->d_psign.upload(p.pilot_sign.data(), p.pilot_sign.size())) != PU_OK) return s;
+    if ((s = h->d_ilo.upload(p.interp_lo.data(), p.interp_lo.size())) != PU_OK) return s;
+    if ((s = h->d_ihi.upload(p.interp_hi.data(), p.interp_hi.size())) != PU_OK) return s;
+    if ((s = h->d_ia.upload(p.interp_alpha.data(), p.interp_alpha.size())) != PU_OK) return s;
+    pu::OfdmDev& d = h->dev;
+    d.nfft = p.nfft; d.log2n = p.log2n; d.cp = p.cp; d.sym_len = p.sym_len;
+    d.n_data = p.n_data; d.n_pilot = p.n_pilot; d.bps = p.bps; d.mod = static_cast<int>(p.cfg.modulation);
+    d.ce_margin = p.ce_margin;
+    d.sample_rate = static_cast<float>(p.cfg.sample_rate);
+    d.twiddle = static_cast<const float2*>(h->d_tw.p);
+    d.data_bin = static_cast<const int*>(h->d_dbin.p);
+    d.pilot_bin = static_cast<const int*>(h->d_pbin.p);
+    d.zc = static_cast<const float2*>(h->d_zc.p);
+    d.pilot_sign = static_cast<const float*>(h->d_psign.p);
+    d.interp_lo = static_cast<const int*>(h->d_ilo.p);
+    d.interp_hi = static_cast<const int*>(h->d_ihi.p);
+    d.interp_alpha = static_cast<const float*>(h->d_ia.p);
+    d.llr_perm = nullptr;
+    d.perm_len = 0;
+    h->smem_bytes = sizeof(float2) * (p.nfft + p.nfft / 8) + sizeof(float) * ((p.sym_len + 3) & ~3) + sizeof(pu::RxShared);
+    if ((s = h->ensure_nco(32)) != PU_OK) return s;
+    *out = h.release();
+    return PU_OK;
+}
+
+void pu_ofdm_destroy(pu_ofdm* h) {
+    if (!h) return;
+    cudaSetDevice(h->ctx->device);
+    delete h;
+}
+
+int pu_ofdm_symbol_samples(const pu_ofdm* h) { return h ? h->plan.sym_len : -1; }
+int pu_ofdm_data_carriers(const pu_ofdm* h) { return h ? h->plan.n_data : -1; }
+int pu_ofdm_pilot_carriers(const pu_ofdm* h) { return h ? h->plan.n_pilot : -1; }
+int pu_ofdm_bits_per_symbol(const pu_ofdm* h) { return h ? h->plan.n_data * h->plan.bps : -1; }
+
+int pu_ofdm_carrier_bins(const pu_ofdm* h, int32_t* bins, int cap) {
+    if (!h) return -1;
+    int n = 0;
+    for (int b : h->plan.data_bin) { if (n < cap) bins[n] = b; ++n; }
+    for (int b : h->plan.pilot_bin) { if (n < cap) bins[n] = b; ++n; }
+    return n;
+}
+
+pu_status pu_ofdm_set_deinterleave(pu_ofdm* h, size_t bits_per_symbol, size_t total_bits) {
+    PU_REQUIRE(h, "pu_ofdm_set_deinterleave: NULL handle");
+    PU_CUDA_TRY(cudaSetDevice(h->ctx->device));
+    if (bits_per_symbol == 0) {
+        h->dev.llr_perm = nullptr;
+        h->dev.perm_len = 0;
+        return PU_OK;
+    }
+    // ChannelInterleaver::deinterleave: output[inverse_permutation_[i]] = soft_bits[i] (ldpc_decoder.cpp:612-620)
+    std::vector<uint32_t> perm(total_bits), inv(total_bits);
+    pu_status s = pu_channel_interleaver_perm(bits_per_symbol, total_bits, perm.data(), inv.data(), nullptr);
+    if (s != PU_OK) return s;
+    std::vector<int> dst(inv.begin(), inv.end());
+    if ((s = h->d_perm.upload(dst.data(), dst.size())) != PU_OK) return s;
+    h->dev.llr_perm = static_cast<const int*>(h->d_perm.p);
+    h->dev.perm_len = static_cast<int>(total_bits);
+    return PU_OK;
+}
+
+static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_t L, int training,
+                             const float* d_cfo, const float* d_phase, float* d_llr, size_t llr_stride,
+                             float* d_snr, float* d_fcfo, float* d_dbg, cudaStream_t st) {
+    const pu::OfdmPlan& p = h->plan;
+    const int n_symbols = static_cast<int>(L / p.sym_len);
+    pu_status s = h->ensure_nco(n_symbols);
+    if (s != PU_OK) return s;
+    const int total_llr = std::max(0, n_symbols - training) * p.n_data * p.bps;
+    const int limit = static_cast<int>(std::min<size_t>(llr_stride, static_cast<size_t>(total_llr)));
+    const unsigned grid = static_cast<unsigned>(B);
+    if (p.nfft == 512) {
+        static bool attr512 = false;
+        if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
+        pu::ofdm_presynced_kernel<512><<<grid, 64, h->smem_bytes, st>>>(h->dev, d_samples, L, n_symbols, training, d_cfo, d_phase,
+                                                                     d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg);
+    } else {
+        static bool attr1024 = false;
+        if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
+        pu::ofdm_presynced_kernel<1024><<<grid, 128, h->smem_bytes, st>>>(h->dev, d_samples, L, n_symbols, training, d_cfo, d_phase,
+                                                                       d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg);
+    }
+    h->ctx->launches.fetch_add(1);
+    PU_CUDA_TRY(cudaGetLastError());
+    return PU_OK;
+}
+
+pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, int training_symbols,
+                                  const float* cfo_hz, const float* cfo_phase, float* llr_out, size_t llr_stride,
+                                  float* snr_db, float* final_cfo_hz, pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_ofdm_presynced_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && llr_out, "pu_ofdm_presynced_batch: NULL data pointer");
+    PU_REQUIRE(training_symbols >= 0, "pu_ofdm_presynced_batch: negative training_symbols");
+    const pu::OfdmPlan& p = h->plan;
+    PU_REQUIRE(L >= static_cast<size_t>(p.sym_len) * static_cast<size_t>(training_symbols),
+               "pu_ofdm_presynced_batch: frame shorter than its training symbols");
+    PU_REQUIRE(llr_stride > 0, "pu_ofdm_presynced_batch: llr_stride is zero");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    if (space == PU_MEM_DEVICE)
+        return launch_ofdm(h, samples, B, L, training_symbols, cfo_hz, cfo_phase, llr_out, llr_stride, snr_db, final_cfo_hz, nullptr, st);
+
+    const size_t slab = std::min<size_t>(B, 8192);
+    pu_status s;
+    const size_t in_floats = slab * (L + 2), out_floats = slab * (llr_stride + 2);
+    if ((s = ctx->d_in.reserve(in_floats * sizeof(float))) != PU_OK) return s;
+    if ((s = ctx->h_in.reserve(in_floats * sizeof(float))) != PU_OK) return s;
+    if ((s = ctx->d_out.reserve(out_floats * sizeof(float))) != PU_OK) return s;
+    if ((s = ctx->h_out.reserve(out_floats * sizeof(float))) != PU_OK) return s;
+    for (size_t off = 0; off < B; off += slab) {
+        const size_t nb = std::min(slab, B - off);
+        float* hin = static_cast<float*>(ctx->h_in.ptr);
+        std::memcpy(hin, samples + off * L, nb * L * sizeof(float));
+        float* hcfo = hin + slab * L;
+        float* hph = hcfo + slab;
+        for (size_t b = 0; b < nb; ++b) {
+            hcfo[b] = cfo_hz ? cfo_hz[off + b] : 0.0f;
+            hph[b] = cfo_phase ? cfo_phase[off + b] : 0.0f;
+        }
+        float* din = static_cast<float*>(ctx->d_in.ptr);
+        PU_CUDA_TRY(cudaMemcpyAsync(din, hin, in_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+        float* dout = static_cast<float*>(ctx->d_out.ptr);
+        PU_CUDA_TRY(cudaMemsetAsync(dout, 0, out_floats * sizeof(float), st));
+        s = launch_ofdm(h, din, nb, L, training_symbols, din + slab * L, din + slab * L + slab, dout, llr_stride,
+                        dout + slab * llr_stride, dout + slab * llr_stride + slab, nullptr, st);
+        if (s != PU_OK) return s;
+        float* hout = static_cast<float*>(ctx->h_out.ptr);
+        PU_CUDA_TRY(cudaMemcpyAsync(hout, dout, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+        PU_CUDA_TRY(cudaStreamSynchronize(st));
+        std::memcpy(llr_out + off * llr_stride, hout, nb * llr_stride * sizeof(float));
+        if (snr_db) std::memcpy(snr_db + off, hout + slab * llr_stride, nb * sizeof(float));
+        if (final_cfo_hz) std::memcpy(final_cfo_hz + off, hout + slab * llr_stride + slab, nb * sizeof(float));
+    }
+    return PU_OK;
+}
+
+pu_status pu_ofdm_presynced_debug(pu_ofdm* h, const float* samples, size_t L, int training_symbols, float cfo_hz,
+                                  float cfo_phase, float* llr_out, size_t llr_cap, float* records, size_t records_cap,
+                                  int* n_data_symbols) {
+    PU_REQUIRE(h && samples && llr_out && records, "pu_ofdm_presynced_debug: NULL argument");
+    const pu::OfdmPlan& p = h->plan;
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n_symbols = static_cast<int>(L / p.sym_len);
+    const int nds = std::max(0, n_symbols - training_symbols);
+    const int nu = p.n_data + p.n_pilot;
+    const size_t rec = static_cast<size_t>(4 * nu + 3 * p.n_data + pu::kDbgScalars);
+    PU_REQUIRE(records_cap >= rec * nds, "pu_ofdm_presynced_debug: records buffer too small");
+    if (n_data_symbols) *n_data_symbols = nds;
+    pu::DevMem dx, dl, dr, dc;
+    pu_status s;
+    if ((s = dx.upload(samples, L)) != PU_OK) return s;
+    std::vector<float> zero(llr_cap, 0.0f), zr(rec * std::max(nds, 1), 0.0f);
+    if ((s = dl.upload(zero.data(), llr_cap)) != PU_OK) return s;
+    if ((s = dr.upload(zr.data(), zr.size())) != PU_OK) return s;
+    const float cp[2] = {cfo_hz, cfo_phase};
+    if ((s = dc.upload(cp, 2)) != PU_OK) return s;
+    s = launch_ofdm(h, static_cast<const float*>(dx.p), 1, L, training_symbols, static_cast<const float*>(dc.p),
+                    static_cast<const float*>(dc.p) + 1, static_cast<float*>(dl.p), llr_cap, nullptr, nullptr,
+                    static_cast<float*>(dr.p), st);
+    if (s != PU_OK) return s;
+    PU_CUDA_TRY(cudaStreamSynchronize(st));
+    PU_CUDA_TRY(cudaMemcpy(llr_out, dl.p, llr_cap * sizeof(float), cudaMemcpyDeviceToHost));
+    PU_CUDA_TRY(cudaMemcpy(records, dr.p, rec * nds * sizeof(float), cudaMemcpyDeviceToHost));
+    return PU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+"""GPU parity tests of the CUDA presynced OFDM receive path (through the C ABI) against the oracle on the same
+channel outputs: FFT bins / channel estimate / equalised symbols bit-exact (same radix-2 rounding sequence),
+LLRs within the north-star tolerance 1e-4 relative (libm calls differ at the ulp level), for every modulation
+of both presets, AWGN and Watterson channels, CFO with initial phase, ragged frame lengths, host and device
+memory, and the fused deinterleaver."""
+import numpy as np
+import pytest
+
+import oracleapi as O
+import refapi as R
+from golden.make_golden import OFDM_CASES, awgn
+
+pytestmark = pytest.mark.gpu
+LLR_RTOL = 1e-4          # BASELINE.json north_star: "LLRs ... within a stated relative tolerance (1e-4 on fp32)"
+MODS = [R.DBPSK, R.DQPSK, R.D8PSK, R.BPSK, R.QPSK, R.QAM16, R.QAM32, R.QAM64, R.QAM256]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from projectultra_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def to_capi_cfg(cfg):
+    from projectultra_b200 import capi
+    return capi.ModemConfig.from_buffer_copy(bytes(cfg))
+
+
+def llr_mismatches(a, b, rtol=LLR_RTOL):
+    """Indices where |a-b| > rtol*max(|b|, 0.5) -- 0.5 is the smallest LLR magnitude clipLLR can emit, so the
+    bound is relative for every representable LLR and still meaningful for the exact-zero erasures."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.nonzero(np.abs(a - b) > rtol * np.maximum(np.abs(b), 0.5))[0]
+
+
+def make_frame(cfg, rate, nbytes, snr, seed, chan=None):
+    rng = np.random.default_rng(seed)
+    data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    tx = O.ofdm_tx(cfg, O.ldpc_encode(rate, data), 0)
+    if chan is None:
+        return awgn(tx, snr, rng), data
+    if not R.available():
+        pytest.skip("Watterson stimulus needs oracle/_ref")
+    return R.watterson(tx, snr, chan[0], chan[1], seed=42 + seed), data
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a).view(np.uint32)
+    b = np.ascontiguousarray(b).view(np.uint32)
+    return a.shape == b.shape and bool((a == b).all())
+
+
+@pytest.mark.parametrize("preset", ["m1", "m3"])
+@pytest.mark.parametrize("mod", MODS)
+def test_stage_parity(ctx, preset, mod):
+    from projectultra_b200 import capi
+    rate = R.R1_2 if preset == "m1" else R.R3_4
+    cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    for i, snr in enumerate((3.0, 14.0, 28.0)):
+        rx, _ = make_frame(cfg, rate, 40 if preset == "m1" else 60, snr, mod * 10 + i)
+        cfo, ph = (0.0, 0.0) if i != 2 else (6.5, -1.3)
+        ref = O.ofdm_presynced_stages(cfg, rx, 2, 2 if i == 2 else 1, cfo, ph)
+        got = dem.presynced_debug(rx, 2, cfo, ph)
+        assert got["n_sym"] == ref["n_sym"] and (got["carriers"] == ref["carriers"]).all()
+        if i != 2:   # without the CFO rotator (sinf/cosf of the rotator phase) everything up to H is exact
+            if cfg.use_pilots == 0:
+                assert same_bits(got["bins"], ref["bins"]), "FFT bins"
+                assert same_bits(got["h"], ref["h"]), "channel estimate"
+                assert same_bits(got["eq"], ref["eq"]), "equalised symbols"
+                assert same_bits(got["nv"], ref["nv"]), "carrier noise variance"
+            else:
+                assert same_bits(got["bins"][0], ref["bins"][0]), "FFT bins of the first data symbol"
+        assert np.allclose(got["bins"], ref["bins"], rtol=2e-5, atol=2e-4)
+        assert np.allclose(got["h"], ref["h"], rtol=2e-5, atol=2e-5)
+        assert np.allclose(got["scalars"], ref["scalars"], rtol=1e-4, atol=2e-5)
+        bad = llr_mismatches(got["llr"], ref["llr"])
+        assert len(bad) == 0, (snr, bad[:10], got["llr"][bad[:10]], ref["llr"][bad[:10]])
+
+
+@pytest.mark.parametrize("case", [c[0] for c in OFDM_CASES])
+def test_golden_frames(ctx, golden, case):
+    from projectultra_b200 import capi
+    g = golden["ofdm"]
+    cfg = R.ModemConfig.from_buffer_copy(bytes(g[case + "_cfg"]))
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    cm, cfo, ph = g[case + "_cfo"]
+    rx = g[case + "_rx"]
+    llr, snr, fc = dem.presynced_batch(rx[None, :], 2, np.array([cfo], np.float32), np.array([ph], np.float32))
+    want = g[case + "_llr"]
+    assert llr.shape[1] == len(want)
+    bad = llr_mismatches(llr[0], want)
+    assert len(bad) == 0, (bad[:10], llr[0][bad[:10]], want[bad[:10]])
+    assert abs(fc[0] - g[case + "_scalars"][-1, 1]) < 1e-3
+    dec = capi.LdpcDecoder(ctx, cfg.code_rate)
+    info, ok, it = dec.decode_batch(llr[:, :648].copy())
+    assert (info[0] == g[case + "_info"]).all() and [int(ok[0]), int(it[0])] == list(g[case + "_ok"])
+
+
+def test_batch_host_and_device_paths_agree(ctx):
+    import torch
+    from projectultra_b200 import capi
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    frames = np.stack([make_frame(cfg, R.R1_2, 40, snr, 300 + i)[0] for i, snr in enumerate(np.linspace(-4, 20, 48))])
+    ref, counts = O.ofdm_presynced_batch(cfg, frames, 660)
+    assert (counts == 660).all()
+    host_llr, host_snr, _ = dem.presynced_batch(frames)
+    dev_llr, dev_snr, _ = dem.presynced_batch(torch.from_numpy(frames).cuda())
+    torch.cuda.synchronize()
+    assert same_bits(host_llr, dev_llr.cpu().numpy())
+    bad = llr_mismatches(host_llr.ravel(), ref.ravel())
+    assert len(bad) == 0, bad[:10]
+    # truncated output: only the first codeword (llr_stride 648) as the Monte-Carlo tools consume it
+    l648, _, _ = dem.presynced_batch(frames, llr_stride=648)
+    assert same_bits(l648, host_llr[:, :648].copy())
+    # hard decisions after LDPC identical to the oracle's on every frame
+    dec = capi.LdpcDecoder(ctx, R.R1_2)
+    gi, gok, git = dec.decode_batch(l648)
+    ci, cok, cit = O.ldpc_decode_batch(R.R1_2, ref[:, :648].copy())
+    assert (gok == cok).all() and (gi[cok == 1] == ci[cok == 1]).all()
+
+
+def test_ragged_and_edge_lengths(ctx):
+    from projectultra_b200 import capi
+    cfg = R.config_m1(R.QPSK, R.R1_2)
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    rx, _ = make_frame(cfg, R.R1_2, 40, 18.0, 11)
+    S = cfg.symbol_samples
+    for L in (2 * S, 2 * S + 5, 3 * S, 3 * S + S - 1, 7 * S + 17, len(rx)):
+        ref = O.ofdm_presynced_stages(cfg, rx[:L], 2, 1)
+        n = dem.n_llr(L)
+        assert n == len(ref["llr"])
+        if n == 0:
+            llr, _, _ = dem.presynced_batch(rx[None, :L], llr_stride=8)
+            assert not llr.any()
+            continue
+        llr, _, _ = dem.presynced_batch(rx[None, :L])
+        assert len(llr_mismatches(llr[0], ref["llr"])) == 0
+    # zero signal: weak-signal / deep-fade branches
+    z = np.zeros(len(rx), np.float32)
+    for mod in (R.DQPSK, R.QAM16):
+        c2 = R.config_m1(mod, R.R1_2)
+        d2 = capi.OfdmDemodulator(ctx, to_capi_cfg(c2))
+        ref = O.ofdm_presynced_stages(c2, z, 2, 1)
+        llr, _, _ = d2.presynced_batch(z[None, :])
+        assert np.array_equal(np.nan_to_num(llr[0], nan=77.0), np.nan_to_num(ref["llr"], nan=77.0))
+
+
+def test_fused_deinterleave(ctx):
+    from projectultra_b200 import capi
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    rx, _ = make_frame(cfg, R.R1_2, 40, 6.0, 21)
+    plain, _, _ = dem.presynced_batch(rx[None, :], llr_stride=648)
+    dem.set_deinterleave(60, 648)
+    fused, _, _ = dem.presynced_batch(rx[None, :], llr_stride=648)
+    assert same_bits(fused[0], O.channel_interleave(60, plain[0], inverse=True))
+    dem.set_deinterleave(0)
+    again, _, _ = dem.presynced_batch(rx[None, :], llr_stride=648)
+    assert same_bits(again, plain)
+
+
+@pytest.mark.ref
+def test_watterson_channels(ctx):
+    from projectultra_b200 import capi
+    for (preset, mod, rate, nbytes, snr, chan) in (("m1", R.DQPSK, R.R1_2, 40, 15.0, (0.5, 10.0)),
+                                                   ("m1", R.QPSK, R.R1_2, 40, 15.0, (2.0, 1.0)),
+                                                   ("m3", R.QAM32, R.R3_4, 60, 25.0, (0.5, 0.1)),
+                                                   ("m3", R.QAM16, R.R3_4, 60, 18.0, (1.0, 0.5))):
+        cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+        dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+        frames = np.stack([make_frame(cfg, rate, nbytes, snr, 700 + i, chan)[0] for i in range(12)])
+        n = dem.n_llr(frames.shape[1])
+        ref, _ = O.ofdm_presynced_batch(cfg, frames, n)
+        llr, _, _ = dem.presynced_batch(frames)
+        bad = llr_mismatches(llr.ravel(), ref.ravel())
+        # pilot-mode feedback can flip a gate (SURVEY "Hard parts"); such frames are reported, not hidden
+        frames_bad = np.unique(bad // n)
+        assert len(frames_bad) <= 1, (preset, mod, frames_bad, len(bad))
+
+
+def test_unsupported_configs_fail_loudly(ctx):
+    from projectultra_b200 import capi
+    cfg = to_capi_cfg(R.config_m1(R.DQPSK, R.R1_2))
+    cfg.fft_size = 256
+    with pytest.raises(capi.PuError):
+        capi.OfdmDemodulator(ctx, cfg)
+    cfg = to_capi_cfg(R.config_m1(R.DQPSK, R.R1_2))
+    cfg.modulation = R.QAM8
+    with pytest.raises(capi.PuError):
+        capi.OfdmDemodulator(ctx, cfg)
