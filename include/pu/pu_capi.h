@@ -154,6 +154,12 @@ PU_API pu_status pu_ofdm_presynced_debug(pu_ofdm* h, const float* samples, size_
                                          float cfo_hz, float cfo_phase, float* llr_out, size_t llr_cap,
                                          float* records, size_t records_cap, int* n_data_symbols);
 
+/* ---------------------------------------------------------------- numerics pinning (tests)
+ * Evaluates the device restatements of the host libm routines the reference's path calls (csrc/ref_math.cuh):
+ * op 0 atan2f(a,b), 1 sinf(a), 2 cosf(a), 3 hypotf(a,b), 4 atanf(a).  ctx == NULL evaluates the same source on
+ * the HOST (so it can be compared with libm without a GPU); otherwise on the device.  Host pointers. */
+PU_API pu_status pu_refmath_eval(pu_ctx* ctx, int op, const float* a, const float* b, float* out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

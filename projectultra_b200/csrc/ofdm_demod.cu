@@ -16,7 +16,8 @@
 //
 // Numerics: the FFT performs the reference's radix-2 butterflies in the reference's order (fused in registers
 // three stages at a time) with unfused fp32 multiplies/adds, so FFT bins, H and equalised symbols are bit-identical
-// to the reference; only libm calls (atan2f, sinf, cosf) differ at the ulp level.  Compiled with -fmad=false.
+// to the reference; the libm calls on the path (atan2f, sinf, cosf, hypotf) are restated in ref_math.cuh so that
+// LLRs match to the last bit as well (up to the host libm's FMA/non-FMA variant).  Compiled with -fmad=false.
 //
 // Kernel shape: one frame per CTA of NFFT/8 threads; the frame's symbols are walked in order because in pilot
 // modes symbol s+1's mixer depends on the CFO tracked in symbol s.  Shared memory holds one padded FFT buffer,
@@ -27,6 +28,7 @@
 
 #include "ofdm_plan.h"
 #include "pu_internal.h"
+#include "ref_math.cuh"
 
 namespace pu {
 
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
                     if (rot) {
                         float sn, cs;
-                        sincosf(theta[n], &sn, &cs);
+                        refmath::sincosf_ref(theta[n], &sn, &cs);
                         z = cmul(z, make_float2(cs, sn));                               // mixed *= correction (:42)
                     }
                     v[q] = z;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                 S.tmpc[i] = unit;
                 const float2 hold = S.Hp[i];
                 S.Hp[i] = cadd(cscale(alpha, h), cscale(__fsub_rn(1.0f, alpha), hold));   // EMA (:410-411)
-                if (S.snr_cnt >= 3 && nh >= 1e-6f) S.tmpd[i] = atan2f(h.y, h.x);          // std::arg for the timing fit (:483)
+                if (S.snr_cnt >= 3 && nh >= 1e-6f) S.tmpd[i] = refmath::atan2f_ref(h.y, h.x);          // std::arg for the timing fit (:483)
             }
             __syncthreads();
             if (tid == 0) {
@@ -349,9 +351,9 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                         if (S.valid[i] & 2) { ps = cadd(ps, S.tmpc[i]); ++vc; }
                     if (vc > 0) {
                         const float2 avg = cdivs(ps, static_cast<float>(vc));
-                        const float apd = atan2f(avg.y, avg.x);
+                        const float apd = refmath::atan2f_ref(avg.y, avg.x);
                         float sn, cs;
-                        sincosf(-apd, &sn, &cs);
+                        refmath::sincosf_ref(-apd, &sn, &cs);
                         S.ppc = make_float2(cs, sn);
                         const float sym_dur = __fdiv_rn(static_cast<float>(d.sym_len), d.sample_rate);
                         const float residual = static_cast<float>(__ddiv_rn((double)apd, __dmul_rn(2.0f * 3.14159265358979323846, (double)sym_dur)));
@@ -416,7 +418,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     if (k > NFFT / 2) k -= NFFT;
                     const float tp = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(2.0f * 3.14159265358979323846, (double)k), (double)timing), (double)static_cast<float>(NFFT)));
                     float sn, cs;
-                    sincosf(-tp, &sn, &cs);                 // std::exp(Complex(0, -timing_phase))
+                    refmath::sincosf_ref(-tp, &sn, &cs);                 // std::exp(Complex(0, -timing_phase))
                     S.Hp[i] = cmul(S.Hp[i], make_float2(cs, sn));
                 }
                 __syncthreads();
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                 if (lo >= 0 && hi >= 0) {
                     const float2 H1 = S.Hp[lo], H2 = S.Hp[hi];
                     const float2 pd = cmul(H2, cconj(H1));
-                    const float ph = fabsf(atan2f(pd.y, pd.x));
+                    const float ph = fabsf(refmath::atan2f_ref(pd.y, pd.x));
                     const float a = d.interp_alpha[i];
                     if (ph > 1.5708f) S.Hd[i] = (a < 0.5f) ? H1 : H2;
                     else S.Hd[i] = cadd(cscale(__fsub_rn(1.0f, a), H1), cscale(a, H2));
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     if (k > NFFT / 2) k -= NFFT;
                     const float tp = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(2.0f * 3.14159265358979323846, (double)k), (double)timing), (double)static_cast<float>(NFFT)));
                     float sn, cs;
-                    sincosf(tp, &sn, &cs);
+                    refmath::sincosf_ref(tp, &sn, &cs);
                     if (u < nd) S.Hd[u] = cmul(S.Hd[u], make_float2(cs, sn));
                     else S.Hp[u - nd] = cmul(S.Hp[u - nd], make_float2(cs, sn));
                 }
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                 float2 tc = make_float2(1.0f, 0.0f);       // std::exp(Complex(0, 0)) == (1, 0)
                 if (tp != 0.0f) {
                     float sn, cs;
-                    sincosf(tp, &sn, &cs);
+                    refmath::sincosf_ref(tp, &sn, &cs);
                     tc = make_float2(cs, sn);
                 }
                 float2 e;
@@ -543,19 +545,19 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
 #pragma unroll
                 for (int b = 0; b < 3; ++b) l[b] = 0.0f;
                 if (!(sp < 1e-6f)) {
-                    const float phase = atan2f(df.y, df.x);
+                    const float phase = refmath::atan2f_ref(df.y, df.x);
                     if (d.mod == PU_MOD_DBPSK) {              // soft_demap.hpp:173-187
-                        l[0] = clip_llr(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, sp), cosf(phase)), nv));
+                        l[0] = clip_llr(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, sp), refmath::cosf_ref(phase)), nv));
                     } else if (d.mod == PU_MOD_DQPSK) {       // :192-213
                         const float scale = __fdiv_rn(__fmul_rn(2.0f, sp), nv);
                         const float pi = 3.14159265358979f;
-                        l[0] = clip_llr(__fmul_rn(scale, sinf(__fadd_rn(phase, pi / 4))));
-                        l[1] = clip_llr(__fmul_rn(scale, cosf(__fmul_rn(2.0f, phase))));
+                        l[0] = clip_llr(__fmul_rn(scale, refmath::sinf_ref(__fadd_rn(phase, pi / 4))));
+                        l[1] = clip_llr(__fmul_rn(scale, refmath::cosf_ref(__fmul_rn(2.0f, phase))));
                     } else {                                  // D8PSK :217-237
                         const float conf = __fdiv_rn(sp, nv);
-                        l[0] = clip_llr(__fmul_rn(conf, sinf(phase)));
-                        l[1] = clip_llr(__fmul_rn(conf, sinf(__fmul_rn(2.0f, phase))));
-                        l[2] = clip_llr(__fmul_rn(conf, sinf(__fmul_rn(4.0f, phase))));
+                        l[0] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(phase)));
+                        l[1] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(2.0f, phase))));
+                        l[2] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(4.0f, phase))));
                     }
                 }
             } else {
