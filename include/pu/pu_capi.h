@@ -154,6 +154,59 @@ PU_API pu_status pu_ofdm_presynced_debug(pu_ofdm* h, const float* samples, size_
                                          float cfo_hz, float cfo_phase, float* llr_out, size_t llr_cap,
                                          float* records, size_t records_cap, int* n_data_symbols);
 
+/* ---------------------------------------------------------------- OFDM transmitter (host; TX stimulus)
+ * OFDMModulator (include/ultra/ofdm.hpp:24-52; src/ofdm/modulator.cpp).  layout 0 = generateTrainingSymbols(2)
+ * + modulate(data, cfg->modulation) -- the presynced frame of tools/test_ofdm_chirp_pilots.cpp:183-191;
+ * layout 1 = generatePreamble() + modulate -- the Schmidl-Cox frame of tools/test_mode_snr.cpp:47-52.
+ * Writes *out_len samples (also when out is too small, so callers can size the buffer). */
+PU_API pu_status pu_ofdm_tx(const pu_modem_config* cfg, int layout, const uint8_t* data, size_t n_bytes,
+                            float* out, size_t out_cap, size_t* out_len);
+
+/* ---------------------------------------------------------------- channel simulator
+ * Replaces sim::WattersonChannel (src/sim/hf_channel.hpp:34-299) for batches of frames.  POD mirror of
+ * WattersonChannel::Config (:36-65) without the CFO injector fields (out of scope). */
+typedef struct {
+    float delay_spread_ms;      /* second path delay; effective delay is floor(ms*fs/1000)+1 samples (Q11) */
+    float doppler_spread_hz;
+    float path1_gain, path2_gain;
+    uint32_t sample_rate;
+    uint32_t fading_enabled, multipath_enabled, noise_enabled;
+} pu_channel_config;
+/* Derived constants of a config (delay d, IIR coefficient a, sqrt(1/a), (1-a)^(2^s), (1-a)^(l+1)): the numbers
+ * the CPU twin needs to regenerate a frame bit for bit.  Any output pointer may be NULL. */
+PU_API pu_status pu_channel_params(const pu_channel_config* cfg, int32_t* delay_samples, float* alpha,
+                                   float* noise_scale, float* apow2_5, float* apl_32);
+/* Noise standard deviation for one TX waveform (host): convention 0 = WattersonChannel::process, rms(input) *
+ * 10^(-snr/20) (hf_channel.hpp:110-119); convention 1 = the AWGN tools, sqrt(mean power / 10^(snr/10))
+ * (tools/test_mode_snr.cpp:58-61). */
+PU_API float pu_channel_noise_std(const float* tx, size_t L, float snr_db, int convention);
+/* rx[b] = channel(tx_pool[tx_index[b]]) for b < B: frames of L samples, per-frame noise_std and 64-bit seed.
+ * The random stream is the counter-based generator specified in csrc/pu_rng.cuh (NOT the reference's
+ * mt19937 stream): frame b is a pure function of (config, tx waveform, noise_std[b], seed[b]).
+ * tx_index == NULL uses waveform 0 for every frame. */
+PU_API pu_status pu_channel_apply_batch(pu_ctx* ctx, const pu_channel_config* cfg, const float* tx_pool,
+                                        size_t pool_stride, size_t pool_count, const uint32_t* tx_index,
+                                        const float* noise_std, const uint64_t* seed, size_t B, size_t L,
+                                        float* rx, pu_memspace space, void* stream);
+
+/* ---------------------------------------------------------------- receive + decode, error counting
+ * One call per batch of frames = the body of the reference's Monte-Carlo trial loop after the channel
+ * (tools/test_ofdm_chirp_pilots.cpp:225-260): processPresynced -> first 648 soft bits -> decodeSoft.
+ * LLRs never leave the device.  Frames that yield fewer than 648 soft bits are decoded with the missing
+ * LLRs as erasures (0), like LDPCDecoder::decodeSoft's zero padding (ldpc_decoder.cpp:160-166). */
+PU_API pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const float* samples, size_t B, size_t L,
+                                         int training_symbols, const float* cfo_hz, const float* cfo_phase,
+                                         uint8_t* info_bytes, size_t info_stride, uint8_t* ok, int32_t* iters,
+                                         pu_memspace space, void* stream);
+/* Frame-error rule of the tools (tools/test_mode_snr.cpp:98-104): success iff lastDecodeSuccess() and the first
+ * payload_bytes decoded bytes equal the payload.  DEVICE pointers.  counters[bin[b]][6] (uint64, atomically
+ * accumulated) = {frames, frame_errors, bit_errors, payload_bits, decode_failures, iteration_sum};
+ * tx_index selects the payload row, bin the counter row (NULL = row 0). */
+PU_API pu_status pu_count_errors(pu_ctx* ctx, const uint8_t* info_bytes, size_t info_stride, const uint8_t* ok,
+                                 const int32_t* iters, const uint8_t* payload_pool, size_t payload_stride,
+                                 const uint32_t* tx_index, const uint32_t* bin, size_t payload_bytes, size_t B,
+                                 uint64_t* counters, void* stream);
+
 /* ---------------------------------------------------------------- numerics pinning (tests)
  * Evaluates the device restatements of the host libm routines the reference's path calls (csrc/ref_math.cuh):
  * op 0 atan2f(a,b), 1 sinf(a), 2 cosf(a), 3 hypotf(a,b), 4 atanf(a).  ctx == NULL evaluates the same source on

@@ -89,3 +89,17 @@ double orc_time_ldpc_decode(int rate, int max_iter, const float* llr, size_t B, 
 }
 #endif
 #endif
+
+/* ---- channel twin (oracle/pu_oracle_channel.c); declared late to keep the header append-only ---- */
+#ifdef __cplusplus
+extern "C" {
+#endif
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+float orc_noise_normal(uint64_t seed, uint32_t n);
+void orc_fading_normals(uint64_t seed, uint32_t n, float z[4]);
+int orc_channel_apply(float delay_ms, float doppler_hz, float g1, float g2, uint32_t fs, int fading, int multipath,
+                      int noise, const float* x, size_t L, float noise_std, uint64_t seed, float* y);
+float orc_channel_noise_std(const float* tx, size_t L, float snr_db, int convention);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,160 @@
+/* oracle/pu_oracle_channel.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see pu_oracle.h).
+ *
+ * CPU twin of the batched channel simulator.  Two things are restated here:
+ *  (1) the REFERENCE's channel algorithm, sim::WattersonChannel (src/sim/hf_channel.hpp:67-168, 258-275):
+ *      d = floor(delay_ms*fs/1000) with an effective tap delay of d+1 samples (zero-filled deque of d+1 entries,
+ *      :73-78,142-146), a = 1 - exp(-2 pi f_d/fs) (:87-88), both fading taps start at (1,0) (:91-92), fading is
+ *      updated BEFORE use each sample (:125-127), only its magnitude multiplies the real signal (:135-136),
+ *      out = x g1 |f1| + x[n-d-1] g2 |f2| + sigma N(0,1) (:139-153);
+ *  (2) the simulator's own SPECIFICATION of the random stream and of the recurrence evaluation order, which
+ *      replaces the reference's implementation-defined mt19937 + std::normal_distribution stream (north_star:
+ *      "counter-based per-frame RNG, so any frame can be regenerated on the CPU").  The spec is written out in
+ *      DESIGN.md ("Channel RNG") and is implemented independently of projectultra_b200/csrc/pu_rng.cuh:
+ *        Philox4x32-10, key = seed (lo, hi), counter = (index, 0, stream, 0), stream 1 fading / 2 noise;
+ *        u = ((w >> 9) + 0.5) 2^-23; Box-Muller with the fixed ln / sin / cos polynomials below (IEEE ops only);
+ *        fading normals of sample n from index n; noise normal of sample n from index n>>2, word pair (n&3)>>1,
+ *        cosine branch for even n; the one-pole recurrence evaluated per 32-sample group as a Kogge-Stone scan.
+ * Output is bit-identical to the CUDA kernels (tests/test_channel_gpu.py); against the reference the channel is
+ * compared statistically. */
+#include "pu_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1,
+                 n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    memcpy(out, ctr, 16);
+    philox(out, key[0], key[1]);
+}
+
+static float uni(uint32_t w) { return ((float)(w >> 9) + 0.5f) * 1.1920928955078125e-07f; }
+
+static float ln_poly(float u) {
+    uint32_t b;
+    memcpy(&b, &u, 4);
+    int e = (int)(b >> 23) - 127;
+    uint32_t mb = (b & 0x007fffffu) | 0x3f800000u;
+    float m;
+    memcpy(&m, &mb, 4);
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    float f = m - 1.0f, z = f * f;
+    static const float co[9] = {7.0376836292e-2f, -1.1514610310e-1f, 1.1676998740e-1f, -1.2420140846e-1f,
+                                1.4249322787e-1f, -1.6668057665e-1f, 2.0000714765e-1f, -2.4999993993e-1f,
+                                3.3333331174e-1f};
+    float p = co[0];
+    for (int i = 1; i < 9; ++i) p = fmaf(p, f, co[i]);
+    float y = (f * z) * p;
+    y = fmaf(-0.5f, z, y);
+    float fe = (float)e, r = f + y;
+    r = fmaf(fe, -2.12194440e-4f, r);
+    r = fmaf(fe, 0.693359375f, r);
+    return r;
+}
+
+static void sincos2pi(float u, float* s_out, float* c_out) {
+    float t = u * 4.0f;
+    int k = (int)(t + 0.5f);
+    float x = (t - (float)k) * 1.57079632679489662f, x2 = x * x;
+    float ps = fmaf(fmaf(-1.9515295891e-4f, x2, 8.3321608736e-3f), x2, -1.6666654611e-1f);
+    float s = fmaf(x * x2, ps, x);
+    float pc = fmaf(fmaf(2.443315711809948e-5f, x2, -1.388731625493765e-3f), x2, 4.166664568298827e-2f);
+    float c = fmaf(x2 * x2, pc, fmaf(-0.5f, x2, 1.0f));
+    switch (k & 3) {
+        case 0: *s_out = s; *c_out = c; break;
+        case 1: *s_out = c; *c_out = -s; break;
+        case 2: *s_out = -s; *c_out = -c; break;
+        default: *s_out = -c; *c_out = s; break;
+    }
+}
+
+static void bm(uint32_t w0, uint32_t w1, float* zc, float* zs) {
+    float r = sqrtf(-2.0f * ln_poly(uni(w0)));
+    float s, c;
+    sincos2pi(uni(w1), &s, &c);
+    *zc = r * c;
+    *zs = r * s;
+}
+
+/* Gaussian primitives exposed for distribution tests */
+float orc_noise_normal(uint64_t seed, uint32_t n) {
+    uint32_t c[4] = {n >> 2, 0, 2, 0};
+    philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float zc, zs;
+    if (n & 2) bm(c[2], c[3], &zc, &zs);
+    else bm(c[0], c[1], &zc, &zs);
+    return (n & 1) ? zs : zc;
+}
+
+void orc_fading_normals(uint64_t seed, uint32_t n, float z[4]) {
+    uint32_t c[4] = {n, 0, 1, 0};
+    philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    bm(c[0], c[1], &z[0], &z[1]);
+    bm(c[2], c[3], &z[2], &z[3]);
+}
+
+/* one frame; returns 0 */
+int orc_channel_apply(float delay_ms, float doppler_hz, float g1, float g2, uint32_t fs, int fading, int multipath,
+                      int noise, const float* x, size_t L, float noise_std, uint64_t seed, float* y) {
+    size_t d = (size_t)(delay_ms * (float)fs / 1000.0f);
+    float nd = doppler_hz / (float)fs;
+    float alpha = (float)(1.0f - exp(-2.0f * 3.14159265358979323846 * nd));
+    float ns = alpha > 0.0f ? sqrtf(1.0f / alpha) : 0.0f;
+    float a = 1.0f - alpha, apow2[5], apl[32];
+    float v = a;
+    for (int s = 0; s < 5; ++s) { apow2[s] = v; v = v * v; }
+    v = a;
+    for (int l = 0; l < 32; ++l) { apl[l] = v; v = v * a; }
+    float carry[4] = {1.0f, 0.0f, 1.0f, 0.0f};
+    for (size_t base = 0; base < L; base += 32) {
+        float f[4][32];
+        if (fading) {
+            for (int l = 0; l < 32; ++l) {
+                float z[4] = {0, 0, 0, 0};
+                if (base + (size_t)l < L) orc_fading_normals(seed, (uint32_t)(base + (size_t)l), z);
+                for (int c = 0; c < 4; ++c) f[c][l] = alpha * (ns * z[c]);
+            }
+            for (int c = 0; c < 4; ++c) {
+                for (int s = 0; s < 5; ++s)
+                    for (int l = 31; l >= (1 << s); --l) f[c][l] = fmaf(apow2[s], f[c][l - (1 << s)], f[c][l]);
+                for (int l = 0; l < 32; ++l) f[c][l] = fmaf(apl[l], carry[c], f[c][l]);
+                carry[c] = f[c][31];
+            }
+        }
+        for (int l = 0; l < 32 && base + (size_t)l < L; ++l) {
+            size_t n = base + (size_t)l;
+            float m1 = 1.0f, m2 = 1.0f;
+            if (fading) {
+                m1 = sqrtf(fmaf(f[0][l], f[0][l], f[1][l] * f[1][l]));
+                m2 = sqrtf(fmaf(f[2][l], f[2][l], f[3][l] * f[3][l]));
+            }
+            float out;
+            if (multipath && d > 0) {
+                float xd = n >= d + 1 ? x[n - d - 1] : 0.0f;
+                out = fmaf(xd * g2, m2, (x[n] * g1) * m1);
+            } else {
+                out = x[n] * m1;
+            }
+            if (noise) out = fmaf(noise_std, orc_noise_normal(seed, (uint32_t)n), out);
+            y[n] = out;
+        }
+    }
+    return 0;
+}
+
+/* noise sigma conventions: 0 = WattersonChannel::process (hf_channel.hpp:110-119), 1 = AWGN tools (test_mode_snr.cpp:58-61) */
+float orc_channel_noise_std(const float* tx, size_t L, float snr_db, int convention) {
+    float acc = 0.0f;
+    for (size_t i = 0; i < L; ++i) acc += tx[i] * tx[i];
+    if (convention == 0) return sqrtf(acc / (float)L) * powf(10.0f, -snr_db / 20.0f);
+    return sqrtf((acc / (float)L) / powf(10.0f, snr_db / 10.0f));
+}

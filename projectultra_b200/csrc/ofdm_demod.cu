@@ -887,3 +887,5 @@ pu_status pu_ofdm_presynced_debug(pu_ofdm* h, const float* samples, size_t L, in
 }
 
 }  // extern "C"
+
+pu_ctx* pu_ofdm_context(pu_ofdm* h) { return h ? h->ctx : nullptr; }

@@ -1,0 +1,212 @@
+"""Host side of the batched Monte-Carlo link simulation: TX waveform pool, channel, receive+decode, error
+counters, sharding over ranks.  Everything heavy happens in libpu_b200.so through the C ABI (capi); torch is
+used for device memory, streams and the one collective (all-reduce of the counter table).
+
+Mirrors the reference's Monte-Carlo tools (tools/test_mode_snr.cpp:18-109, tools/test_ofdm_chirp_pilots.cpp:
+100-270): per trial  encode -> modulate -> channel -> processPresynced -> getSoftBits -> decodeSoft -> compare.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+
+COUNTER_NAMES = ("frames", "frame_errors", "bit_errors", "bits", "decode_failures", "iteration_sum")
+
+
+class ChannelConfig(C.Structure):
+    """pu_channel_config: POD mirror of sim::WattersonChannel::Config (src/sim/hf_channel.hpp:36-65)."""
+    _fields_ = [("delay_spread_ms", C.c_float), ("doppler_spread_hz", C.c_float), ("path1_gain", C.c_float),
+                ("path2_gain", C.c_float), ("sample_rate", C.c_uint32), ("fading_enabled", C.c_uint32),
+                ("multipath_enabled", C.c_uint32), ("noise_enabled", C.c_uint32)]
+
+
+def channel_preset(name):
+    """ccir:: presets of src/sim/hf_channel.hpp:305-381."""
+    table = {"awgn": (0.0, 0.0, 1.0, 0.0, 0, 0), "good": (0.5, 0.1, 0.707, 0.707, 1, 1),
+             "moderate": (1.0, 0.5, 0.707, 0.707, 1, 1), "poor": (2.0, 1.0, 0.707, 0.707, 1, 1),
+             "flutter": (0.5, 10.0, 0.707, 0.707, 1, 1)}
+    d, f, g1, g2, fad, mp = table[name]
+    return ChannelConfig(d, f, g1, g2, 48000, fad, mp, 1)
+
+
+def ofdm_tx(cfg, data, layout=0):
+    """pu_ofdm_tx: OFDMModulator training/preamble + modulate on the host."""
+    d = np.ascontiguousarray(data, dtype=np.uint8)
+    n = C.c_size_t(0)
+    capi.lib().pu_ofdm_tx(C.byref(cfg), int(layout), capi._ptr(d), C.c_size_t(len(d)), None, C.c_size_t(0), C.byref(n))
+    out = np.zeros(n.value, np.float32)
+    capi.check(capi.lib().pu_ofdm_tx(C.byref(cfg), int(layout), capi._ptr(d), C.c_size_t(len(d)), capi._ptr(out),
+                                     C.c_size_t(len(out)), C.byref(n)))
+    return out
+
+
+def channel_noise_std(tx, snr_db, convention=0):
+    f = capi.lib().pu_channel_noise_std
+    f.restype = C.c_float
+    x = np.ascontiguousarray(tx, dtype=np.float32)
+    return float(f(capi._ptr(x), C.c_size_t(len(x)), C.c_float(snr_db), int(convention)))
+
+
+def channel_apply(ctx, ch, tx_pool, tx_index, noise_std, seed, rx=None):
+    """pu_channel_apply_batch.  numpy => host staging, torch.cuda => device."""
+    tor = capi._is_torch(tx_pool)
+    P, L = tx_pool.shape
+    B = len(noise_std)
+    if rx is None:
+        if tor:
+            import torch
+            rx = torch.empty((B, L), dtype=torch.float32, device=tx_pool.device)
+        else:
+            rx = np.zeros((B, L), np.float32)
+    sp = capi._space(tx_pool, tx_index, noise_std, seed, rx)
+    capi.check(capi.lib().pu_channel_apply_batch(ctx._h, C.byref(ch), capi._ptr(tx_pool), C.c_size_t(L), C.c_size_t(P),
+                                                 capi._ptr(tx_index), capi._ptr(noise_std), capi._ptr(seed),
+                                                 C.c_size_t(B), C.c_size_t(L), capi._ptr(rx), sp, capi._stream(sp)))
+    return rx
+
+
+def receive_decode(ofdm, ldpc, samples, training=2, cfo_hz=None, cfo_phase=None, info=None, ok=None, iters=None):
+    """pu_receive_decode_batch: demodulate + LDPC decode; LLRs stay on the device."""
+    tor = capi._is_torch(samples)
+    B, L = samples.shape
+    kb = ldpc.info_bytes
+    if tor:
+        import torch
+        info = torch.empty((B, kb), dtype=torch.uint8, device=samples.device) if info is None else info
+        ok = torch.empty(B, dtype=torch.uint8, device=samples.device) if ok is None else ok
+        iters = torch.empty(B, dtype=torch.int32, device=samples.device) if iters is None else iters
+    else:
+        samples = np.ascontiguousarray(samples, dtype=np.float32)
+        info = np.zeros((B, kb), np.uint8) if info is None else info
+        ok = np.zeros(B, np.uint8) if ok is None else ok
+        iters = np.zeros(B, np.int32) if iters is None else iters
+    sp = capi._space(samples, info, ok, iters, cfo_hz, cfo_phase)
+    capi.check(capi.lib().pu_receive_decode_batch(ofdm._h, ldpc._h, capi._ptr(samples), C.c_size_t(B), C.c_size_t(L),
+                                                  int(training), capi._ptr(cfo_hz), capi._ptr(cfo_phase),
+                                                  capi._ptr(info), C.c_size_t(kb), capi._ptr(ok), capi._ptr(iters),
+                                                  sp, capi._stream(sp)))
+    return info, ok, iters
+
+
+def count_errors(ctx, info, ok, iters, payload_pool, tx_index, bins, payload_bytes, counters):
+    """pu_count_errors on device tensors; counters is a torch.int64 [n_bins, 6] tensor accumulated in place."""
+    import torch
+    B = info.shape[0]
+    capi.check(capi.lib().pu_count_errors(ctx._h, capi._ptr(info), C.c_size_t(info.stride(0)), capi._ptr(ok),
+                                          capi._ptr(iters), capi._ptr(payload_pool), C.c_size_t(payload_pool.stride(0)),
+                                          capi._ptr(tx_index), capi._ptr(bins), C.c_size_t(payload_bytes), C.c_size_t(B),
+                                          capi._ptr(counters), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return counters
+
+
+def wilson_interval(errors, n, z=1.96):
+    """Wilson score interval for an error rate (the Monte-Carlo confidence interval of the north star)."""
+    if n == 0:
+        return 0.0, 1.0
+    p = errors / n
+    den = 1 + z * z / n
+    mid = (p + z * z / (2 * n)) / den
+    half = z * math.sqrt(p * (1 - p) / n + z * z / (4 * n * n)) / den
+    return max(0.0, mid - half), min(1.0, mid + half)
+
+
+class LinkSim:
+    """One waveform mode x code rate x channel: owns the TX pool and runs sharded SNR sweeps on one GPU.
+
+    Frames are identified by (snr index, trial index); frame -> (tx waveform, seed) is a pure function, so any
+    frame can be regenerated, and ranks take disjoint trial ranges with no data exchange."""
+
+    def __init__(self, ctx, cfg, channel="awgn", payload_bytes=40, pool=64, snr_convention=None, pool_seed=12345,
+                 max_iter=50, device=None):
+        import torch
+        self.ctx, self.cfg = ctx, cfg
+        self.device = device or torch.device("cuda", ctx.device)
+        self.ch = channel_preset(channel) if isinstance(channel, str) else channel
+        self.channel_name = channel if isinstance(channel, str) else "custom"
+        # AWGN tools define SNR on mean frame power, WattersonChannel on input rms (same number, different rounding)
+        self.snr_convention = (1 if self.channel_name == "awgn" else 0) if snr_convention is None else snr_convention
+        self.ofdm = capi.OfdmDemodulator(ctx, cfg)
+        self.ldpc = capi.LdpcDecoder(ctx, cfg.code_rate, max_iter)
+        self.payload_bytes = payload_bytes
+        rng = np.random.default_rng(pool_seed)
+        self.payloads = rng.integers(0, 256, (pool, payload_bytes), dtype=np.uint8)
+        waves = [ofdm_tx(cfg, capi.ldpc_encode(cfg.code_rate, p), 0) for p in self.payloads]
+        self.L = len(waves[0])
+        self.tx_host = np.stack(waves)
+        self.tx_pool = torch.from_numpy(self.tx_host).to(self.device)
+        kb = self.ldpc.info_bytes
+        pad = np.zeros((pool, kb), np.uint8)
+        pad[:, :payload_bytes] = self.payloads
+        self.payload_pool = torch.from_numpy(pad).to(self.device)
+        self.pool = pool
+
+    def noise_std_table(self, snr_points):
+        return np.array([[channel_noise_std(self.tx_host[i], s, self.snr_convention) for i in range(self.pool)]
+                         for s in snr_points], dtype=np.float32)
+
+    @staticmethod
+    def frame_seed(snr_idx, trial, base_seed=0xB200):
+        return (np.uint64(base_seed) << np.uint64(40)) ^ (np.uint64(snr_idx) << np.uint64(32)) ^ np.uint64(trial)
+
+    def make_batch(self, snr_points, snr_idx, trials, base_seed=0xB200):
+        """Device descriptors of the frames (snr_idx[i], trials[i]): tx index, noise std, seed, counter bin."""
+        import torch
+        snr_idx = np.asarray(snr_idx, dtype=np.int64)
+        trials = np.asarray(trials, dtype=np.int64)
+        tx_index = (trials % self.pool).astype(np.uint32)
+        std = self.noise_std_table(snr_points)[snr_idx, tx_index].astype(np.float32)
+        seeds = ((np.uint64(base_seed) << np.uint64(40)) ^ (snr_idx.astype(np.uint64) << np.uint64(32))
+                 ^ trials.astype(np.uint64))
+        to = lambda a, dt: torch.from_numpy(a.view(dt) if a.dtype != dt else a).to(self.device)
+        return dict(tx_index=to(tx_index.view(np.int32), np.int32), noise_std=to(std, np.float32),
+                    seed=to(seeds.view(np.int64), np.int64), bins=to(snr_idx.astype(np.uint32).view(np.int32), np.int32),
+                    host=dict(tx_index=tx_index, noise_std=std, seed=seeds, snr_idx=snr_idx))
+
+    def run_batch(self, batch, counters, rx=None, keep=False):
+        """channel -> demod -> LDPC -> counters for one prepared batch (all on the current stream)."""
+        rx = channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rx)
+        info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
+        count_errors(self.ctx, info, ok, iters, self.payload_pool, batch["tx_index"], batch["bins"], self.payload_bytes,
+                     counters)
+        return (rx, info, ok, iters) if keep else None
+
+    def sweep(self, snr_points, trials_per_point, rank=0, world=1, batch_frames=1 << 15, base_seed=0xB200):
+        """FER/BER sweep; this rank takes trials t with t % world == rank.  Returns an int64 [n_snr, 6] device tensor
+        holding THIS rank's counters (all-reduce it with torch.distributed for the job total)."""
+        import torch
+        counters = torch.zeros((len(snr_points), 6), dtype=torch.int64, device=self.device)
+        mine = np.arange(rank, trials_per_point, world, dtype=np.int64)
+        si = np.repeat(np.arange(len(snr_points), dtype=np.int64), len(mine))
+        tr = np.tile(mine, len(snr_points))
+        for off in range(0, len(si), batch_frames):
+            b = self.make_batch(snr_points, si[off:off + batch_frames], tr[off:off + batch_frames], base_seed)
+            self.run_batch(b, counters)
+        return counters
+
+
+def shard_trials(trials_per_point, rank, world):
+    """Trial indices of this rank: t % world == rank (disjoint, exhaustive; no data-path collective)."""
+    return np.arange(rank, trials_per_point, world, dtype=np.int64)
+
+
+def allreduce_counters(counters):
+    """The path's only exchange step: sum the [n_snr, 6] int64 counter tables over all ranks (NCCL on GPUs, gloo in
+    the CPU tests).  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    return counters
+
+
+def summarize(counters, snr_points):
+    """Rows of {snr_db, frames, fer, ber, fer_ci, avg_iters} from a counter table (host)."""
+    c = counters.detach().cpu().numpy() if hasattr(counters, "detach") else np.asarray(counters)
+    rows = []
+    for s, r in zip(snr_points, c):
+        frames, ferr, berr, bits, dfail, its = (int(v) for v in r)
+        rows.append(dict(snr_db=float(s), frames=frames, fer=ferr / max(frames, 1), ber=berr / max(bits, 1),
+                         fer_ci=wilson_interval(ferr, frames), decode_fail=dfail / max(frames, 1),
+                         avg_iters=its / max(frames, 1)))
+    return rows
