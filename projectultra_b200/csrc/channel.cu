@@ -180,6 +180,7 @@ pu_status pu_channel_apply_batch(pu_ctx* ctx, const pu_channel_config* cfg, cons
     auto launch = [&](const float* d_pool, const uint32_t* d_idx, const float* d_std, const uint64_t* d_seed, size_t nb,
                       float* d_rx) -> pu_status {
         const unsigned blocks = static_cast<unsigned>((nb * 32 + 255) / 256);
+        (void)cudaGetLastError();
         if (awgn_only) pu::awgn_kernel<<<blocks, 256, 0, st>>>(d_pool, pool_stride, d_idx, d_std, d_seed, nb, static_cast<int>(L), d_rx);
         else pu::channel_kernel<<<blocks, 256, 0, st>>>(p, d_pool, pool_stride, d_idx, d_std, d_seed, nb, static_cast<int>(L), d_rx);
         ctx->launches.fetch_add(1);

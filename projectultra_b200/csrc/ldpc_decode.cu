@@ -164,6 +164,7 @@ struct DevArray {
 
 struct pu_ldpc {
     pu_ctx* ctx = nullptr;
+    int device = 0;   // copy of ctx->device: the handle may outlive its context
     int max_iter = 50;
     pu::LdpcCode code;
     pu::LdpcHostTables host;
@@ -201,6 +202,7 @@ struct pu_ldpc {
 static pu_status launch_decode(pu_ldpc* h, const float* d_llr, size_t llr_stride, size_t B, uint8_t* d_info,
                                size_t info_stride, uint8_t* d_ok, int32_t* d_iters, cudaStream_t st) {
     if (B == 0) return PU_OK;
+    (void)cudaGetLastError();   // drop stale non-sticky errors so the check below reports this launch only
     const size_t kMaxGrid = 1u << 30;
     for (size_t off = 0; off < B; off += kMaxGrid) {
         const size_t nb = std::min(kMaxGrid, B - off);
@@ -222,6 +224,7 @@ pu_status pu_ldpc_create(pu_ctx* ctx, int code_rate, int max_iter, pu_ldpc** out
     std::unique_ptr<pu_ldpc> h(new (std::nothrow) pu_ldpc());
     if (!h) return PU_ERR_NOMEM;
     h->ctx = ctx;
+    h->device = ctx->device;
     h->max_iter = max_iter < 0 ? 50 : max_iter;   // Impl::max_iterations default, ldpc_decoder.cpp:43
     pu_status s = h->load(code_rate);
     if (s != PU_OK) return s;
@@ -231,7 +234,7 @@ pu_status pu_ldpc_create(pu_ctx* ctx, int code_rate, int max_iter, pu_ldpc** out
 
 void pu_ldpc_destroy(pu_ldpc* h) {
     if (!h) return;
-    cudaSetDevice(h->ctx->device);
+    cudaSetDevice(h->device);
     delete h;
 }
 

@@ -55,6 +55,7 @@ pu_status pu_count_errors(pu_ctx* ctx, const uint8_t* info_bytes, size_t info_st
     if (B == 0) return PU_OK;
     PU_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    (void)cudaGetLastError();
     pu::count_errors_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(
         info_bytes, info_stride, ok, iters, payload_pool, payload_stride, tx_index, bin, static_cast<int>(payload_bytes), B,
         reinterpret_cast<unsigned long long*>(counters));

@@ -673,6 +673,7 @@ struct DevMem {
 
 struct pu_ofdm {
     pu_ctx* ctx = nullptr;
+    int device = 0;   // copy of ctx->device: the handle may outlive its context
     pu::OfdmPlan plan;
     pu::OfdmDev dev{};
     pu::DevMem d_tw, d_nco, d_dbin, d_pbin, d_zc, d_psign, d_ilo, d_ihi, d_ia, d_perm;
@@ -701,6 +702,7 @@ pu_status pu_ofdm_create(pu_ctx* ctx, const pu_modem_config* cfg, pu_ofdm** out)
     std::unique_ptr<pu_ofdm> h(new (std::nothrow) pu_ofdm());
     if (!h) return PU_ERR_NOMEM;
     h->ctx = ctx;
+    h->device = ctx->device;
     const char* why = "";
     if (!pu::make_ofdm_plan(*cfg, &h->plan, &why)) {
         pu::set_error("pu_ofdm_create: %s", why);
@@ -741,7 +743,7 @@ pu_status pu_ofdm_create(pu_ctx* ctx, const pu_modem_config* cfg, pu_ofdm** out)
 
 void pu_ofdm_destroy(pu_ofdm* h) {
     if (!h) return;
-    cudaSetDevice(h->ctx->device);
+    cudaSetDevice(h->device);
     delete h;
 }
 
@@ -787,6 +789,7 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
     const int total_llr = std::max(0, n_symbols - training) * p.n_data * p.bps;
     const int limit = static_cast<int>(std::min<size_t>(llr_stride, static_cast<size_t>(total_llr)));
     const unsigned grid = static_cast<unsigned>(B);
+    (void)cudaGetLastError();
     if (p.nfft == 512) {
         static bool attr512 = false;
         if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }

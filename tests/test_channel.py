@@ -61,7 +61,7 @@ def test_kernels_match_cpu_twin_bitwise():
     x = (rng.standard_normal((1, 64)) * 0.3).astype(np.float32)
     got = linksim.channel_apply(ctx, ch, x, np.zeros(1, np.uint32), np.ones(1, np.float32), np.array([7], np.uint64))
     assert (got[0].view(np.uint32) == CH.channel_apply(ch, x[0], 1.0, 7).view(np.uint32)).all()
-    ctx.close()
+    del ctx
 
 
 @pytest.mark.gpu
@@ -111,4 +111,4 @@ def test_statistics_match_reference_watterson():
             mg, mr = np.sqrt((g[:, sl] ** 2).mean()), np.sqrt((r[:, sl] ** 2).mean())
             assert abs(mg / mr - 1) < tol, (name, sl, mg, mr)
         assert abs(g[:, :5].mean() - 1.0) < 0.05     # starts at (1, 0), hf_channel.hpp:91-92
-    ctx.close()
+    del ctx

@@ -65,7 +65,7 @@ def test_frame_by_frame_parity(case):
     assert (counters.cpu().numpy() == want).all()
     fer = want[:, 1] / want[:, 0]
     assert fer[0] >= fer[-1]                      # waterfall runs the right way
-    ctx.close()
+    del ctx
 
 
 def test_sharding_invariance_and_waterfall():
@@ -83,7 +83,7 @@ def test_sharding_invariance_and_waterfall():
     # SURVEY §8d [probe]: M1 DQPSK R1/2 success 0 % @-4 dB, ~68 % @0 dB, 100 % @+4 dB (wideband mean-power SNR)
     assert rows[0]["fer"] > 0.9 and rows[-1]["fer"] < 0.02 and 0.1 < rows[2]["fer"] < 0.7
     assert all(r["frames"] == 300 for r in rows)
-    ctx.close()
+    del ctx
 
 
 def test_host_buffer_path_matches_device_path():
@@ -99,4 +99,4 @@ def test_host_buffer_path_matches_device_path():
     b = linksim.receive_decode(sim.ofdm, sim.ldpc, rx.cpu().numpy())
     for u, v in zip(a, b):
         assert (u.cpu().numpy() == v).all()
-    ctx.close()
+    del ctx

@@ -43,4 +43,4 @@ def test_llr_words_identical(preset):
     frac = same / total
     print(f"\n[{preset}] bit-identical LLR words: {same}/{total} = {frac:.6f}")
     assert frac >= 0.9999
-    ctx.close()
+    del ctx

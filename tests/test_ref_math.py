@@ -63,4 +63,4 @@ def test_device_matches_host(rm):
     y, x, t = inputs(400000, 2)
     for name, a, b in (("atan2f", y, x), ("atanf", y, None), ("hypotf", y, x), ("sinf", t, None), ("cosf", t, None)):
         assert (bits(rm.evaluate(name, a, b, ctx=ctx)) == bits(rm.evaluate(name, a, b))).all(), name
-    ctx.close()
+    del ctx
