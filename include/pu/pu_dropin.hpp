@@ -1,0 +1,476 @@
+// include/pu/pu_dropin.hpp — C++20 host classes that present ProjectUltra's own call surface over the C ABI of
+// libpu_b200.so (include/pu/pu_capi.h).  Header-only; link with -lpu_b200.
+//
+//   pu::LDPCEncoder / pu::LDPCDecoder        <->  ultra::LDPCEncoder / ultra::LDPCDecoder   include/ultra/fec.hpp:20-77
+//   pu::Interleaver / pu::ChannelInterleaver <->  ultra::Interleaver / ChannelInterleaver   include/ultra/fec.hpp:85-142
+//   pu::OFDMDemodulator                      <->  ultra::OFDMDemodulator (presynced path)   include/ultra/ofdm.hpp:58-127
+//   pu::OFDMModulator                        <->  ultra::OFDMModulator (host TX stimulus)   include/ultra/ofdm.hpp:24-52
+//   pu::OfdmChirpWaveform                    <->  ultra::OFDMChirpWaveform RX data path     src/waveform/ofdm_chirp_waveform.cpp:174-230
+//
+// Same method names, argument meaning, ownership (borrowed spans in, values out) and error behaviour as the
+// reference: no exceptions on the decode path, failure = lastDecodeSuccess()==false with best-effort
+// bytes, empty input -> {} and failure.  What differs: construction throws std::runtime_error when no sm_100 GPU /
+// library is usable (there is NO CPU fallback), and the parts of the reference classes outside the hot path
+// (Schmidl-Cox acquisition in OFDMDemodulator::process, chirp detection in IWaveform::detectSync) report
+// "not synchronised" instead of computing — they are SURVEY §8f "next" rows.
+//
+// Define PU_DROPIN_WITH_ULTRA before including this header (with the reference's include/ and src/ on the include
+// path) to use the reference's own types (ultra::ModemConfig, Modulation, CodeRate, Bytes, ...) and to make
+// pu::OfdmChirpWaveform derive from ultra::IWaveform, so reference drivers compile against either implementation.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pu/pu_capi.h"
+
+#ifdef PU_DROPIN_WITH_ULTRA
+#include "ultra/types.hpp"
+#include "waveform/waveform_interface.hpp"
+#endif
+
+namespace pu {
+
+#ifdef PU_DROPIN_WITH_ULTRA
+using ultra::ByteSpan;
+using ultra::Bytes;
+using ultra::CodeRate;
+using ultra::Complex;
+using ultra::ModemConfig;
+using ultra::Modulation;
+using ultra::SampleSpan;
+using ultra::Samples;
+using ultra::Symbol;
+#else
+// stand-alone mirrors of include/ultra/types.hpp:13-23,27-39,92-101,139-234 (receive-path fields only)
+using Complex = std::complex<float>;
+using Symbol = std::vector<Complex>;
+using Samples = std::vector<float>;
+using Bytes = std::vector<uint8_t>;
+using SampleSpan = std::span<const float>;
+using ByteSpan = std::span<const uint8_t>;
+enum class Modulation : uint8_t { DBPSK = 0, BPSK = 1, DQPSK = 2, QPSK = 3, D8PSK = 4, QAM8 = 5, QAM16 = 6, QAM32 = 7,
+                                  QAM64 = 8, QAM128 = 9, QAM256 = 10, AUTO = 255 };
+enum class CodeRate : uint8_t { R1_4 = 0, R1_3 = 1, R1_2 = 2, R2_3 = 3, R3_4 = 4, R5_6 = 5, R7_8 = 6, AUTO = 255 };
+enum class CyclicPrefixMode : uint8_t { SHORT = 0, MEDIUM = 1, LONG = 2 };
+struct ModemConfig {
+    uint32_t sample_rate = 48000, center_freq = 1500, fft_size = 512, num_carriers = 30;
+    CyclicPrefixMode cp_mode = CyclicPrefixMode::MEDIUM;
+    uint32_t symbol_guard = 4, pilot_spacing = 2;
+    bool use_pilots = true;
+    Modulation modulation = Modulation::QPSK;
+    CodeRate code_rate = CodeRate::R1_2;
+    bool adaptive_eq_enabled = false;
+    float output_scale = 40.0f, tx_cfo_hz = 0.0f;
+    uint32_t getCyclicPrefix() const {
+        const uint32_t base = cp_mode == CyclicPrefixMode::SHORT ? 32u : cp_mode == CyclicPrefixMode::LONG ? 64u : 48u;
+        return base * (fft_size / 512);
+    }
+    uint32_t getSymbolDuration() const { return fft_size + getCyclicPrefix() + symbol_guard; }
+};
+#endif
+
+namespace detail {
+
+[[noreturn]] inline void fail(const char* what, pu_status s) {
+    throw std::runtime_error(std::string(what) + ": " + pu_status_string(s) + ": " + pu_last_error());
+}
+
+// One context per process and device, created on first use and kept for the life of the process (the reference's
+// objects need no context; this keeps their constructors' signatures).
+inline pu_ctx* shared_context(int device = -1) {
+    static pu_ctx* ctx = nullptr;
+    static int dev = 0;
+    if (!ctx) {
+        if (device >= 0) dev = device;
+        const pu_status s = pu_init(dev, &ctx);
+        if (s != PU_OK) fail("pu_init", s);
+    }
+    return ctx;
+}
+
+inline pu_modem_config to_pod(const ModemConfig& c) {
+    pu_modem_config p{};
+    p.sample_rate = c.sample_rate;
+    p.center_freq = c.center_freq;
+    p.fft_size = c.fft_size;
+    p.num_carriers = c.num_carriers;
+    p.cp_mode = static_cast<uint32_t>(c.cp_mode);
+    p.symbol_guard = c.symbol_guard;
+    p.pilot_spacing = c.pilot_spacing;
+    p.use_pilots = c.use_pilots ? 1u : 0u;
+    p.modulation = static_cast<uint32_t>(c.modulation);
+    p.code_rate = static_cast<uint32_t>(c.code_rate);
+    p.output_scale = c.output_scale;
+    p.tx_cfo_hz = c.tx_cfo_hz;
+    return p;
+}
+
+}  // namespace detail
+
+// Selects the CUDA device used by every drop-in object of this process; call before constructing the first one.
+inline void use_device(int device) { (void)detail::shared_context(device); }
+
+// ------------------------------------------------------------------------------------------------ FEC
+class LDPCEncoder {   // ultra::LDPCEncoder, include/ultra/fec.hpp:20-41
+public:
+    explicit LDPCEncoder(CodeRate rate) : rate_(rate) {}
+    Bytes encode(ByteSpan data) {   // src/fec/ldpc_encoder.cpp:193-257
+        size_t n = 0;
+        Bytes out(getCodedSize(data.size()) + 81);
+        const pu_status s = pu_ldpc_encode(static_cast<int>(rate_), data.data(), data.size(), out.data(), out.size(), &n);
+        if (s != PU_OK) return {};
+        out.resize(n);
+        return out;
+    }
+    size_t getCodedSize(size_t input_size) const {   // ldpc_encoder.cpp:259-264: whole 648-bit blocks
+        static const int k_of[] = {162, 324, 324, 432, 486, 540, 324};
+        const size_t k = static_cast<size_t>(k_of[static_cast<unsigned>(rate_) < 7 ? static_cast<unsigned>(rate_) : 2]);
+        const size_t blocks = (input_size * 8 + k - 1) / k;
+        return (blocks * PU_LDPC_N + 7) / 8;
+    }
+    CodeRate getRate() const { return rate_; }
+    void setRate(CodeRate rate) { rate_ = rate; }
+
+private:
+    CodeRate rate_;
+};
+
+class LDPCDecoder {   // ultra::LDPCDecoder, include/ultra/fec.hpp:48-77
+public:
+    explicit LDPCDecoder(CodeRate rate) {
+        const pu_status s = pu_ldpc_create(detail::shared_context(), static_cast<int>(rate), -1, &h_);
+        if (s != PU_OK) detail::fail("pu_ldpc_create", s);
+    }
+    ~LDPCDecoder() { pu_ldpc_destroy(h_); }
+    LDPCDecoder(const LDPCDecoder&) = delete;
+    LDPCDecoder& operator=(const LDPCDecoder&) = delete;
+
+    Bytes decode(ByteSpan coded_data) {   // src/fec/ldpc_decoder.cpp:267-281
+        Bytes out(coded_data.size() + 128);
+        size_t n = 0;
+        if (pu_ldpc_decode_hard(h_, coded_data.data(), coded_data.size(), out.data(), out.size(), &n, &ok_, &iters_) != PU_OK) {
+            ok_ = 0;
+            return {};
+        }
+        out.resize(n);
+        return out;
+    }
+    Bytes decodeSoft(std::span<const float> llrs) {   // ldpc_decoder.cpp:283-428
+        Bytes out(llrs.size() / 8 + 128);
+        size_t n = 0;
+        if (pu_ldpc_decode_soft(h_, llrs.data(), llrs.size(), out.data(), out.size(), &n, &ok_, &iters_) != PU_OK) {
+            ok_ = 0;
+            return {};
+        }
+        out.resize(n);
+        return out;
+    }
+    bool lastDecodeSuccess() const { return ok_ != 0; }
+    int lastIterations() const { return iters_; }
+    void setRate(CodeRate rate) { (void)pu_ldpc_set_rate(h_, static_cast<int>(rate)); }
+    CodeRate getRate() const { return static_cast<CodeRate>(pu_ldpc_rate(h_)); }
+    void setMaxIterations(int max_iter) { (void)pu_ldpc_set_max_iterations(h_, max_iter); }
+    pu_ldpc* handle() const { return h_; }   // for the batched entry points
+
+private:
+    pu_ldpc* h_ = nullptr;
+    int ok_ = 0, iters_ = 0;
+};
+
+namespace detail {
+template <class T>
+inline std::vector<T> permute_fwd(const std::vector<uint32_t>& perm, std::span<const T> in) {
+    // out[perm[i]] = in[i]; inputs shorter than the table are zero-padded (ldpc_decoder.cpp:466-481, :587-600)
+    std::vector<T> out(perm.size(), T(0));
+    for (size_t i = 0; i < perm.size() && i < in.size(); ++i) out[perm[i]] = in[i];
+    return out;
+}
+inline Bytes permute_bits(const std::vector<uint32_t>& perm, ByteSpan data) {
+    // bit i of the input (MSB-first) goes to bit perm[i] of the output (ldpc_decoder.cpp:483-510, :622-672)
+    const size_t total = perm.size();
+    Bytes out((total + 7) / 8, 0);
+    for (size_t i = 0; i < total && i < data.size() * 8; ++i)
+        if ((data[i >> 3] >> (7 - (i & 7))) & 1) out[perm[i] >> 3] |= static_cast<uint8_t>(1u << (7 - (perm[i] & 7)));
+    return out;
+}
+}  // namespace detail
+
+class Interleaver {   // ultra::Interleaver, include/ultra/fec.hpp:85-107; ldpc_decoder.cpp:454-540
+public:
+    Interleaver(size_t rows, size_t cols) : rows_(rows), cols_(cols), perm_(rows * cols), inv_(rows * cols) {
+        pu_block_interleaver_perm(rows, cols, perm_.data());
+        for (size_t i = 0; i < perm_.size(); ++i) inv_[perm_[i]] = static_cast<uint32_t>(i);
+    }
+    Bytes interleave(ByteSpan data) { return detail::permute_bits(perm_, data); }
+    Bytes deinterleave(ByteSpan data) { return detail::permute_bits(inv_, data); }
+    std::vector<float> interleave(std::span<const float> s) { return detail::permute_fwd<float>(perm_, s); }
+    std::vector<float> deinterleave(std::span<const float> s) { return detail::permute_fwd<float>(inv_, s); }
+    size_t getPermutation(size_t i) const { return i < perm_.size() ? perm_[i] : 0; }
+    size_t getRows() const { return rows_; }
+    size_t getCols() const { return cols_; }
+
+private:
+    size_t rows_, cols_;
+    std::vector<uint32_t> perm_, inv_;
+};
+
+class ChannelInterleaver {   // ultra::ChannelInterleaver, include/ultra/fec.hpp:120-142; ldpc_decoder.cpp:547-672
+public:
+    explicit ChannelInterleaver(size_t bits_per_symbol, size_t total_bits = 648)
+        : bps_(bits_per_symbol), perm_(total_bits), inv_(total_bits) {
+        pu_channel_interleaver_perm(bits_per_symbol, total_bits, perm_.data(), inv_.data(), &step_);
+    }
+    std::vector<float> interleave(std::span<const float> s) { return detail::permute_fwd<float>(perm_, s); }
+    std::vector<float> deinterleave(std::span<const float> s) { return detail::permute_fwd<float>(inv_, s); }
+    Bytes interleave(ByteSpan d) { return detail::permute_bits(perm_, d); }
+    Bytes deinterleave(ByteSpan d) { return detail::permute_bits(inv_, d); }
+    size_t getSymbolSeparation() const { return bps_ ? step_ / bps_ : 0; }   // ldpc_decoder.cpp:583
+    size_t getStep() const { return step_; }
+
+private:
+    size_t bps_, step_ = 0;
+    std::vector<uint32_t> perm_, inv_;
+};
+
+// ------------------------------------------------------------------------------------------------ OFDM
+class OFDMModulator {   // ultra::OFDMModulator, include/ultra/ofdm.hpp:24-52 (host side: TX stimulus only)
+public:
+    explicit OFDMModulator(const ModemConfig& config) : cfg_(config) {}
+    // generateTrainingSymbols(2) followed by modulate(data, mod): the presynced frame (layout 0), or
+    // generatePreamble() followed by modulate (layout 1); modulator.cpp:348-580
+    Samples frame(ByteSpan data, Modulation mod, int layout = 0) {
+        pu_modem_config p = detail::to_pod(cfg_);
+        p.modulation = static_cast<uint32_t>(mod);
+        size_t n = 0;
+        pu_ofdm_tx(&p, layout, data.data(), data.size(), nullptr, 0, &n);
+        Samples out(n);
+        if (pu_ofdm_tx(&p, layout, data.data(), data.size(), out.data(), out.size(), &n) != PU_OK) return {};
+        return out;
+    }
+    Samples generateTrainingSymbols(int count = 2) {   // only the reference's default count is on the path
+        Samples f = frame(ByteSpan{}, cfg_.modulation, 0);
+        f.resize(std::min<size_t>(f.size(), static_cast<size_t>(count) * samplesPerSymbol()));
+        return f;
+    }
+    Samples modulate(ByteSpan data, Modulation mod) {   // data symbols that follow generateTrainingSymbols(2)
+        Samples f = frame(data, mod, 0);
+        const size_t skip = std::min<size_t>(f.size(), 2 * samplesPerSymbol());
+        return Samples(f.begin() + static_cast<std::ptrdiff_t>(skip), f.end());
+    }
+    size_t samplesPerSymbol() const { return cfg_.getSymbolDuration(); }
+
+private:
+    ModemConfig cfg_;
+};
+
+class OFDMDemodulator {   // ultra::OFDMDemodulator, include/ultra/ofdm.hpp:58-127
+public:
+    explicit OFDMDemodulator(const ModemConfig& config) : cfg_(config) {
+        const pu_modem_config p = detail::to_pod(config);
+        const pu_status s = pu_ofdm_create(detail::shared_context(), &p, &h_);
+        if (s != PU_OK) detail::fail("pu_ofdm_create", s);
+        sym_len_ = static_cast<size_t>(pu_ofdm_symbol_samples(h_));
+        bits_per_symbol_ = static_cast<size_t>(pu_ofdm_bits_per_symbol(h_));
+    }
+    ~OFDMDemodulator() { pu_ofdm_destroy(h_); }
+    OFDMDemodulator(const OFDMDemodulator&) = delete;
+    OFDMDemodulator& operator=(const OFDMDemodulator&) = delete;
+
+    // Schmidl-Cox acquisition (demodulator.cpp:462-743) is a SURVEY §8f "next" row: never reports a frame.
+    bool process(SampleSpan) { return false; }
+
+    // demodulator.cpp:854-985.  The frame is demodulated by the CUDA kernel from a fresh tracker state with the CFO
+    // and phase given to setFrequencyOffset[WithPhase]; like the reference, the soft-bit FIFO is replaced.
+    bool processPresynced(SampleSpan samples, int training_symbols = 2) {
+        if (samples.size() < sym_len_) return false;               // :865-867
+        soft_.clear();
+        if (!cfo_set_) return false;   // estimateCFOFromTraining (:920-925) is outside the path
+        const size_t n_sym = samples.size() / sym_len_;
+        const size_t n_data = n_sym > static_cast<size_t>(training_symbols) ? n_sym - static_cast<size_t>(training_symbols) : 0;
+        const size_t n_llr = n_data * bits_per_symbol_;
+        std::vector<float> llr(std::max<size_t>(n_llr, 1), 0.0f);
+        float snr_db = 0.0f, fcfo = cfo_hz_;
+        const pu_status s = pu_ofdm_presynced_batch(h_, samples.data(), 1, samples.size(), training_symbols, &cfo_hz_, &cfo_phase_,
+                                                    llr.data(), llr.size(), &snr_db, &fcfo, PU_MEM_HOST, nullptr);
+        if (s != PU_OK) return false;
+        llr.resize(n_llr);
+        soft_ = std::move(llr);
+        snr_db_ = snr_db;
+        cfo_hz_ = fcfo;            // getFrequencyOffset() reports the tracked value (:801-803)
+        synced_ = true;
+        return soft_.size() >= PU_LDPC_N;
+    }
+    std::vector<float> getSoftBits() {   // drains at most 648 per call (:766-791)
+        if (soft_.size() <= PU_LDPC_N) {
+            std::vector<float> out = std::move(soft_);
+            soft_.clear();
+            return out;
+        }
+        std::vector<float> out(soft_.begin(), soft_.begin() + PU_LDPC_N);
+        soft_.erase(soft_.begin(), soft_.begin() + PU_LDPC_N);
+        return out;
+    }
+    Bytes getData() {   // hard decisions of the FIFO, bit = (llr > 0) as the reference has it (:745-764)
+        Bytes data;
+        uint8_t byte = 0;
+        int cnt = 0;
+        for (float l : soft_) {
+            byte = static_cast<uint8_t>((byte << 1) | (l > 0 ? 1 : 0));
+            if (++cnt == 8) { data.push_back(byte); byte = 0; cnt = 0; }
+        }
+        soft_.clear();
+        return data;
+    }
+    float getEstimatedSNR() const { return snr_db_; }
+    float getFrequencyOffset() const { return cfo_hz_; }
+    void setFrequencyOffset(float cfo_hz) { cfo_hz_ = cfo_hz; cfo_phase_ = 0.0f; cfo_set_ = true; }                    // :805-814
+    void setFrequencyOffsetWithPhase(float cfo_hz, float phase) { cfo_hz_ = cfo_hz; cfo_phase_ = phase; cfo_set_ = true; }   // :816-825
+    Symbol getConstellationSymbols() const { return {}; }   // GUI scatter plot: not produced by the batch kernels
+    bool isSynced() const { return synced_; }
+    bool hasPendingData() const { return !soft_.empty(); }
+    size_t getLastSyncOffset() const { return 0; }
+    void setTimingOffset(int) {}
+    void reset() {   // :987-1017
+        soft_.clear();
+        cfo_hz_ = 0.0f;
+        cfo_phase_ = 0.0f;
+        cfo_set_ = false;
+        synced_ = false;
+        snr_db_ = 0.0f;
+    }
+    pu_ofdm* handle() const { return h_; }
+
+private:
+    ModemConfig cfg_;
+    pu_ofdm* h_ = nullptr;
+    size_t sym_len_ = 0, bits_per_symbol_ = 0;
+    std::vector<float> soft_;
+    float cfo_hz_ = 0.0f, cfo_phase_ = 0.0f, snr_db_ = 0.0f;
+    bool cfo_set_ = false, synced_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------ waveform plugin
+#ifdef PU_DROPIN_WITH_ULTRA
+#define PU_IWAVEFORM_BASE : public ultra::IWaveform
+#define PU_OVERRIDE override
+using ultra::SyncResult;
+using ultra::WaveformCapabilities;
+#else
+#define PU_IWAVEFORM_BASE
+#define PU_OVERRIDE
+struct SyncResult {   // src/waveform/waveform_interface.hpp:37-44
+    bool detected = false;
+    int start_sample = -1;
+    float correlation = 0.0f, cfo_hz = 0.0f, snr_estimate = 0.0f;
+    bool has_training = false;
+};
+struct WaveformCapabilities {   // :25-34
+    bool supports_cfo_correction = false, supports_doppler_correction = false, requires_pilots = false;
+    bool supports_differential = true;
+    float min_snr_db = 0.0f, max_snr_db = 30.0f, max_throughput_bps = 1000.0f, preamble_duration_ms = 500.0f;
+};
+#endif
+
+// The RX data path of ultra::OFDMChirpWaveform (src/waveform/ofdm_chirp_waveform.cpp): configure ->
+// setFrequencyOffset -> process(span starting at the first training symbol) -> getSoftBits.  The dual-chirp
+// detector (detectSync, chirp_sync.hpp:349-506) is a SURVEY §8f next-2 row: detectSync reports "not detected", and
+// callers with external (genie / chirp) timing call process() directly, as tools/test_ofdm_chirp_pilots.cpp does.
+class OfdmChirpWaveform PU_IWAVEFORM_BASE {
+public:
+    explicit OfdmChirpWaveform(const ModemConfig& cfg = ModemConfig{}) : cfg_(cfg) { rebuild(); }
+
+    std::string getName() const PU_OVERRIDE { return "OFDM-CHIRP"; }
+#ifdef PU_DROPIN_WITH_ULTRA
+    ultra::protocol::WaveformMode getMode() const override { return ultra::protocol::WaveformMode::OFDM_CHIRP; }
+#endif
+    WaveformCapabilities getCapabilities() const PU_OVERRIDE {   // ofdm_chirp_waveform.cpp:60-72
+        WaveformCapabilities c;
+        c.supports_cfo_correction = true;
+        c.supports_doppler_correction = true;
+        c.requires_pilots = cfg_.use_pilots;
+        c.supports_differential = true;
+        c.min_snr_db = 10.0f;
+        c.max_snr_db = 30.0f;
+        c.max_throughput_bps = 7200.0f;
+        c.preamble_duration_ms = 1200.0f;
+        return c;
+    }
+    void configure(Modulation mod, CodeRate rate) PU_OVERRIDE {   // :78-85
+        cfg_.modulation = mod;
+        cfg_.code_rate = rate;
+        rebuild();
+    }
+    void setFrequencyOffset(float cfo_hz) PU_OVERRIDE { cfo_hz_ = cfo_hz; demod_->setFrequencyOffset(cfo_hz); }   // :87-93
+    void setTxFrequencyOffset(float cfo_hz) PU_OVERRIDE { cfg_.tx_cfo_hz = cfo_hz; mod_ = std::make_unique<OFDMModulator>(cfg_); }
+    Modulation getModulation() const PU_OVERRIDE { return cfg_.modulation; }
+    CodeRate getCodeRate() const PU_OVERRIDE { return cfg_.code_rate; }
+    float getFrequencyOffset() const PU_OVERRIDE { return cfo_hz_; }
+
+    Samples generatePreamble() PU_OVERRIDE { return mod_->generateTrainingSymbols(2); }   // training part (chirp: next-2)
+    Samples modulate(const Bytes& encoded) PU_OVERRIDE { return mod_->modulate(ByteSpan(encoded.data(), encoded.size()), cfg_.modulation); }
+
+    bool detectSync(SampleSpan, SyncResult& result, float = 0.3f) PU_OVERRIDE {
+        result = SyncResult{};
+        return false;
+    }
+    bool process(SampleSpan samples) PU_OVERRIDE {   // :174-219: processPresynced on the span from the training start
+        demod_->setFrequencyOffsetWithPhase(cfo_hz_, 0.0f);
+        const bool ready = demod_->processPresynced(samples, 2);
+        soft_.clear();
+        while (demod_->hasPendingData()) {   // drain everything (:202-212)
+            std::vector<float> c = demod_->getSoftBits();
+            soft_.insert(soft_.end(), c.begin(), c.end());
+        }
+        synced_ = ready;
+        return ready;
+    }
+    std::vector<float> getSoftBits() PU_OVERRIDE { return std::move(soft_); }
+    void reset() PU_OVERRIDE {   // preserves the CFO, as the code does (:221-230)
+        soft_.clear();
+        synced_ = false;
+        demod_->reset();
+    }
+    bool isSynced() const PU_OVERRIDE { return synced_; }
+    bool hasData() const PU_OVERRIDE { return !soft_.empty(); }
+    float estimatedSNR() const PU_OVERRIDE { return demod_->getEstimatedSNR(); }
+    float estimatedCFO() const PU_OVERRIDE { return demod_->getFrequencyOffset(); }
+    std::vector<std::complex<float>> getConstellationSymbols() const PU_OVERRIDE { return {}; }
+    std::string getStatusString() const PU_OVERRIDE { return "OFDM-CHIRP (B200 batch path) " + std::to_string(cfg_.num_carriers) + " carriers"; }
+    int getCarrierCount() const PU_OVERRIDE { return static_cast<int>(cfg_.num_carriers); }
+    float getThroughput(CodeRate rate) const PU_OVERRIDE {
+        static const float rv[] = {0.25f, 1.0f / 3, 0.5f, 2.0f / 3, 0.75f, 5.0f / 6, 0.875f};
+        const unsigned r = static_cast<unsigned>(rate) < 7 ? static_cast<unsigned>(rate) : 2;
+        return static_cast<float>(pu_ofdm_bits_per_symbol(demod_->handle())) * rv[r] *
+               static_cast<float>(cfg_.sample_rate) / static_cast<float>(cfg_.getSymbolDuration());
+    }
+    int getSamplesPerSymbol() const PU_OVERRIDE { return static_cast<int>(cfg_.getSymbolDuration()); }
+    int getPreambleSamples() const PU_OVERRIDE { return 2 * getSamplesPerSymbol(); }
+    int getMinSamplesForFrame() const PU_OVERRIDE {   // 2 training symbols + the data symbols of one codeword
+        const int bps = pu_ofdm_bits_per_symbol(demod_->handle());
+        const int nsym = bps > 0 ? (PU_LDPC_N + bps - 1) / bps : 0;
+        return (2 + nsym) * getSamplesPerSymbol();
+    }
+
+private:
+    void rebuild() {
+        demod_ = std::make_unique<OFDMDemodulator>(cfg_);
+        mod_ = std::make_unique<OFDMModulator>(cfg_);
+    }
+    ModemConfig cfg_;
+    std::unique_ptr<OFDMDemodulator> demod_;
+    std::unique_ptr<OFDMModulator> mod_;
+    std::vector<float> soft_;
+    float cfo_hz_ = 0.0f;
+    bool synced_ = false;
+};
+
+#undef PU_IWAVEFORM_BASE
+#undef PU_OVERRIDE
+
+}  // namespace pu
