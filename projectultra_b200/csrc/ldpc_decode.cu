@@ -148,6 +148,158 @@ __global__ void __launch_bounds__(512) ldpc_flood_kernel(LdpcDevTables t, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Register-resident variant used for the five real code rates.  Thread p owns check slot p for the whole decode: its
+// variable indices, the messages it sent last iteration and its parity bit's LLR/message live in registers, so an
+// iteration reads only the totals of its info bits from shared memory and writes its new messages there.  Thread j
+// (+ r*T) owns information bit j: channel LLR and message slots in registers.  VR = info bits per thread,
+// DV = maximum variable degree.
+//
+// Exactness notes (all against ldpc_decoder.cpp:179-236):
+//  * channel LLRs are canonicalised on load (x + 0.0f turns -0 into +0).  A total that starts from a value that is
+//    not -0 can never become -0, and neither can v = total - c2v, so "v < 0" is exactly the sign bit and the sign
+//    product of a row is an XOR of raw bit patterns.  The sign of a zero never reaches a comparison or a magnitude
+//    in the reference, so this does not change any message, hard decision or iteration count.
+//  * |clamp(v, +-50)| = min(|v|, 50) and the clamp keeps the sign, so the clamped message itself is never formed.
+//  * the exclude-self minimum (:185-201) is (a_e == m1 ? m2 : m1): a unique minimum sees the second minimum, and on
+//    ties m2 == m1, which is what the reference's scan yields.
+//  * absent edges: variable-side slots point at a word holding +0.0f (x + 0 == x for x != -0); check-side edges of
+//    rows shorter than their warp's longest row read a total of +INF: no sign, and a magnitude of exactly the clamp
+//    limit, which cannot lower the first or second minimum of a row that has two real edges (every row does).
+template <int NE>
+__device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* __restrict__ c2v_col, int M, const int (&var)[kE],
+                                          float (&prev)[kE], float par_llr, float& pc, float lim, bool last, unsigned& syn_bits) {
+    const float ptot = __fadd_rn(par_llr, pc);        // total of the parity bit (:206-213)
+    const float vp = __fsub_rn(ptot, pc);             // its v2c before the clamp (:219-222)
+    unsigned px = __float_as_uint(ptot);              // XOR of the totals' sign bits = parity of the hard decisions
+    unsigned sx = __float_as_uint(vp);                // XOR of the messages' sign bits
+    const float ap = fminf(fabsf(vp), lim);
+    float m1 = ap, m2 = FLT_MAX;
+    float v[NE > 0 ? NE : 1], a[NE > 0 ? NE : 1];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const float te = tot[var[e]];
+        px ^= __float_as_uint(te);
+        v[e] = __fsub_rn(te, prev[e]);
+        sx ^= __float_as_uint(v[e]);
+        a[e] = fminf(fabsf(v[e]), lim);
+        m2 = fminf(m2, fmaxf(m1, a[e]));
+        m1 = fminf(m1, a[e]);
+    }
+    syn_bits = px;
+    if (!last) {
+        const unsigned sgn = sx & 0x80000000u;
+        const unsigned s1 = __float_as_uint(__fmul_rn(m1, 0.75f)) ^ sgn;   // (:200), pre-multiplied by the row's sign
+        const unsigned s2 = __float_as_uint(__fmul_rn(m2, 0.75f)) ^ sgn;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const unsigned mag = (a[e] == m1) ? s2 : s1;
+            const float msg = __uint_as_float(mag ^ (__float_as_uint(v[e]) & 0x80000000u));
+            prev[e] = msg;
+            c2v_col[e * M] = msg;
+        }
+        const unsigned mag = (ap == m1) ? s2 : s1;
+        pc = __uint_as_float(mag ^ (__float_as_uint(vp) & 0x80000000u));
+    }
+}
+
+template <int VR, int DV>
+__global__ void __launch_bounds__(512) ldpc_flood_reg_kernel(LdpcDevTables t, const float* __restrict__ llr, size_t llr_stride,
+                                                             uint8_t* __restrict__ info, size_t info_stride,
+                                                             uint8_t* __restrict__ ok, int32_t* __restrict__ iters, int max_iter) {
+    extern __shared__ float smem[];
+    const int K = t.k, M = t.m;
+    float* c2v = smem;                 // [kE][M], then the +0.0f word
+    float* tot = c2v + kE * M + 4;     // [K], then the +INF word
+    const int zero_slot = kE * M;
+    const int inf_slot = K;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const float* x = llr + static_cast<size_t>(blockIdx.x) * llr_stride;
+
+    const bool has_check = tid < M;
+    int ninfo = 0;
+    int var[kE];
+    float prev[kE];
+    float par_llr = 0.0f, pc = 0.0f;
+#pragma unroll
+    for (int e = 0; e < kE; ++e) { var[e] = inf_slot; prev[e] = 0.0f; }
+    if (has_check) {
+        ninfo = t.cn_ninfo[tid];
+#pragma unroll
+        for (int e = 0; e < kE; ++e)
+            if (e < ninfo) var[e] = t.cn_var[e * M + tid];
+        par_llr = __fadd_rn(x[K + t.cn_check[tid]], 0.0f);
+    }
+    const int nw = __reduce_max_sync(0xffffffffu, ninfo);   // longest row of this warp (slots are sorted by degree)
+    float lin[VR];
+    int slot[VR][DV];
+#pragma unroll
+    for (int r = 0; r < VR; ++r) {
+        const int j = tid + r * T;
+        lin[r] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < DV; ++d) slot[r][d] = zero_slot;
+        if (j < K) {
+            lin[r] = __fadd_rn(x[j], 0.0f);
+            tot[j] = lin[r];
+            const int deg = t.vn_deg[j];
+#pragma unroll
+            for (int d = 0; d < DV; ++d)
+                if (d < deg) slot[r][d] = t.vn_slot[d * K + j];
+        }
+    }
+    if (tid == 0) {
+        c2v[zero_slot] = 0.0f;
+        tot[inf_slot] = INFINITY;
+    }
+    __syncthreads();
+
+    float* c2v_col = c2v + tid;
+    int it = 0;
+    int converged = 0;
+    for (;; ++it) {
+        const bool last = (it == max_iter);
+        const float lim = (it == 0) ? INFINITY : 50.0f;   // iteration 0 consumes the raw channel LLRs (:169-173)
+        unsigned syn_bits = 0;
+        if (has_check) {
+            switch (nw) {
+                case 0: cn_update<0>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 1: cn_update<1>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 2: cn_update<2>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 3: cn_update<3>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 4: cn_update<4>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 5: cn_update<5>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+                default: cn_update<6>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+            }
+        }
+        const int any = __syncthreads_or(static_cast<int>(syn_bits >> 31));   // syndrome of iteration it-1's totals (:227-235)
+        if (it > 0 && !any) { converged = 1; --it; break; }
+        if (last) break;
+#pragma unroll
+        for (int r = 0; r < VR; ++r) {
+            const int j = tid + r * T;
+            float s = lin[r];
+#pragma unroll
+            for (int d = 0; d < DV; ++d) s = __fadd_rn(s, c2v[slot[r][d]]);   // ascending check order (:208-213)
+            if (j < K) tot[j] = s;
+        }
+        __syncthreads();
+    }
+
+    uint8_t* out = info + static_cast<size_t>(blockIdx.x) * info_stride;
+    const int nbytes = (K + 7) >> 3;
+    for (int b = tid; b < nbytes; b += T) {   // k information bits MSB-first, last byte left-justified (:242-256)
+        unsigned byte = 0;
+        int cnt = 0;
+        for (int j = b * 8; j < b * 8 + 8 && j < K; ++j, ++cnt) byte = (byte << 1) | (tot[j] < 0.0f ? 1u : 0u);
+        out[b] = static_cast<uint8_t>(byte << (8 - cnt));
+    }
+    if (tid == 0) {
+        if (ok) ok[blockIdx.x] = static_cast<uint8_t>(converged);
+        if (iters) iters[blockIdx.x] = it;
+    }
+}
+
 struct DevArray {
     void* p = nullptr;
     ~DevArray() { if (p) cudaFree(p); }
@@ -172,6 +324,8 @@ struct pu_ldpc {
     pu::LdpcDevTables dev{};
     int threads = 128;
     size_t smem_bytes = 0;
+    int reg_threads = 0, reg_vr = 0, reg_dv = 0;   // launch shape of the register-resident kernel (0: generic kernel)
+    size_t reg_smem = 0;
     int last_success = 0, last_iters = 0;
 
     pu_status load(int rate) {
@@ -195,6 +349,10 @@ struct pu_ldpc {
         const int per_round = host.m > 256 ? (host.m + 1) / 2 : host.m;
         threads = (per_round + 31) / 32 * 32;
         smem_bytes = sizeof(float) * (static_cast<size_t>(pu::kE + 2) * host.m + 2 * static_cast<size_t>(host.k));
+        reg_threads = (host.m + 31) / 32 * 32;
+        reg_vr = (host.k + reg_threads - 1) / reg_threads;
+        reg_dv = host.dv_max;
+        reg_smem = sizeof(float) * (static_cast<size_t>(pu::kE) * host.m + 4 + static_cast<size_t>(host.k) + 4);
         return PU_OK;
     }
 };
@@ -206,9 +364,26 @@ static pu_status launch_decode(pu_ldpc* h, const float* d_llr, size_t llr_stride
     const size_t kMaxGrid = 1u << 30;
     for (size_t off = 0; off < B; off += kMaxGrid) {
         const size_t nb = std::min(kMaxGrid, B - off);
-        pu::ldpc_flood_kernel<<<static_cast<unsigned>(nb), h->threads, h->smem_bytes, st>>>(
-            h->dev, d_llr + off * llr_stride, llr_stride, d_info + off * info_stride, info_stride,
-            d_ok ? d_ok + off : nullptr, d_iters ? d_iters + off : nullptr, h->max_iter);
+#define PU_LDPC_REG_CASE(VR, DV)                                                                                   \
+    if (!done && h->reg_vr <= (VR) && h->reg_dv <= (DV)) {                                                        \
+        pu::ldpc_flood_reg_kernel<VR, DV><<<static_cast<unsigned>(nb), h->reg_threads, h->reg_smem, st>>>(        \
+            h->dev, d_llr + off * llr_stride, llr_stride, d_info + off * info_stride, info_stride,                \
+            d_ok ? d_ok + off : nullptr, d_iters ? d_iters + off : nullptr, h->max_iter);                         \
+        done = true;                                                                                              \
+    }
+        bool done = false;
+        if (h->reg_threads <= 512) {
+            PU_LDPC_REG_CASE(1, 5)    // R1/2
+            PU_LDPC_REG_CASE(2, 3)    // R2/3
+            PU_LDPC_REG_CASE(3, 3)    // R3/4
+            PU_LDPC_REG_CASE(5, 3)    // R5/6
+            PU_LDPC_REG_CASE(1, 13)   // R1/4
+        }
+#undef PU_LDPC_REG_CASE
+        if (!done)
+            pu::ldpc_flood_kernel<<<static_cast<unsigned>(nb), h->threads, h->smem_bytes, st>>>(
+                h->dev, d_llr + off * llr_stride, llr_stride, d_info + off * info_stride, info_stride,
+                d_ok ? d_ok + off : nullptr, d_iters ? d_iters + off : nullptr, h->max_iter);
         h->ctx->launches.fetch_add(1);
     }
     PU_CUDA_TRY(cudaGetLastError());

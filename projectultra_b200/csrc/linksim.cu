@@ -16,6 +16,8 @@ extern "C" pu_status pu_ofdm_presynced_batch(pu_ofdm*, const float*, size_t, siz
 extern "C" pu_status pu_ldpc_decode_batch(pu_ldpc*, const float*, size_t, size_t, uint8_t*, size_t, uint8_t*, int32_t*,
                                           pu_memspace, void*);
 extern "C" int pu_ldpc_info_bits(const pu_ldpc*);
+extern "C" int pu_ofdm_symbol_samples(const pu_ofdm*);
+extern "C" int pu_ofdm_bits_per_symbol(const pu_ofdm*);
 pu_ctx* pu_ofdm_context(pu_ofdm* h);   // ofdm_demod.cu
 
 namespace pu {
@@ -85,48 +87,82 @@ pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const float* sam
                                          nullptr, PU_MEM_DEVICE, st)) != PU_OK) return s;
         return pu_ldpc_decode_batch(ldpc, d_llr, PU_LDPC_N, B, info_bytes, info_stride, ok, iters, PU_MEM_DEVICE, st);
     }
-    // host buffers: pinned staging in slabs; samples go up, only info bytes / flags come back
-    const size_t slab = std::min<size_t>(B, 16384);
-    const size_t in_floats = slab * (L + 2);
+    // Host buffers: a two-lane pipeline.  Each slab of frames goes H2D -> demod -> LDPC -> D2H on its lane's own
+    // stream, so the copy of slab i+1 overlaps the kernels and the read-back of slab i.  Samples that already live
+    // in pinned (page-locked) memory are DMA'd straight from the caller's buffer; pageable samples are staged through
+    // the lane's pinned buffer (that memcpy overlaps the other lane's GPU work).  Only info bytes / flags come back.
+    cudaPointerAttributes attr{};
+    const bool src_pinned = cudaPointerGetAttributes(&attr, samples) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    const size_t slab = std::min<size_t>(B, 4096);
     const size_t out_row = kb + 1 + sizeof(int32_t);
-    if ((s = ctx->d_in.reserve(in_floats * sizeof(float))) != PU_OK) return s;
-    if ((s = ctx->h_in.reserve(in_floats * sizeof(float))) != PU_OK) return s;
-    if ((s = ctx->d_aux.reserve(slab * PU_LDPC_N * sizeof(float))) != PU_OK) return s;
-    if ((s = ctx->d_out.reserve(slab * out_row + 64)) != PU_OK) return s;
-    if ((s = ctx->h_out.reserve(slab * out_row + 64)) != PU_OK) return s;
-    for (size_t off = 0; off < B; off += slab) {
-        const size_t nb = std::min(slab, B - off);
-        float* hin = static_cast<float*>(ctx->h_in.ptr);
-        std::memcpy(hin, samples + off * L, nb * L * sizeof(float));
-        float* hcfo = hin + slab * L;
-        float* hph = hcfo + slab;
-        for (size_t b = 0; b < nb; ++b) {
-            hcfo[b] = cfo_hz ? cfo_hz[off + b] : 0.0f;
-            hph[b] = cfo_phase ? cfo_phase[off + b] : 0.0f;
-        }
-        float* din = static_cast<float*>(ctx->d_in.ptr);
-        PU_CUDA_TRY(cudaMemcpyAsync(din, hin, nb * L * sizeof(float), cudaMemcpyHostToDevice, st));
-        PU_CUDA_TRY(cudaMemcpyAsync(din + slab * L, hcfo, 2 * slab * sizeof(float), cudaMemcpyHostToDevice, st));
-        float* d_llr = static_cast<float*>(ctx->d_aux.ptr);
-        PU_CUDA_TRY(cudaMemsetAsync(d_llr, 0, nb * PU_LDPC_N * sizeof(float), st));
-        if ((s = pu_ofdm_presynced_batch(ofdm, din, nb, L, training_symbols, din + slab * L, din + slab * L + slab, d_llr,
-                                         PU_LDPC_N, nullptr, nullptr, PU_MEM_DEVICE, st)) != PU_OK) return s;
-        uint8_t* d_info = static_cast<uint8_t*>(ctx->d_out.ptr);
-        int32_t* d_iters = reinterpret_cast<int32_t*>(d_info + ((slab * kb + 15) / 16) * 16);
-        uint8_t* d_ok = reinterpret_cast<uint8_t*>(d_iters + slab);
-        if ((s = pu_ldpc_decode_batch(ldpc, d_llr, PU_LDPC_N, nb, d_info, kb, d_ok, d_iters, PU_MEM_DEVICE, st)) != PU_OK) return s;
-        uint8_t* hout = static_cast<uint8_t*>(ctx->h_out.ptr);
-        const size_t total = static_cast<size_t>(reinterpret_cast<uint8_t*>(d_ok + slab) - d_info);
-        PU_CUDA_TRY(cudaMemcpyAsync(hout, d_info, total, cudaMemcpyDeviceToHost, st));
-        PU_CUDA_TRY(cudaStreamSynchronize(st));
-        const int32_t* h_iters = reinterpret_cast<const int32_t*>(hout + ((slab * kb + 15) / 16) * 16);
-        const uint8_t* h_ok = reinterpret_cast<const uint8_t*>(h_iters + slab);
-        for (size_t b = 0; b < nb; ++b) {
-            std::memcpy(info_bytes + (off + b) * info_stride, hout + b * kb, kb);
-            if (ok) ok[off + b] = h_ok[b];
-            if (iters) iters[off + b] = h_iters[b];
-        }
+    const size_t iters_off = ((slab * kb + 15) / 16) * 16;
+    const size_t out_bytes = iters_off + slab * sizeof(int32_t) + slab;
+    (void)out_row;
+    if (stream) {   // order the lanes after work already queued on the caller's stream
+        PU_CUDA_TRY(cudaEventRecord(ctx->pipe_ev, st));
+        for (auto& sl : ctx->pipe) PU_CUDA_TRY(cudaStreamWaitEvent(sl.stream, ctx->pipe_ev, 0));
     }
+    for (auto& sl : ctx->pipe) {
+        sl.nb = 0;
+        if ((s = sl.d_in.reserve(slab * (L + 2) * sizeof(float))) != PU_OK) return s;
+        if (!src_pinned && (s = sl.h_in.reserve(slab * L * sizeof(float))) != PU_OK) return s;
+        if ((s = sl.d_llr.reserve(slab * PU_LDPC_N * sizeof(float))) != PU_OK) return s;
+        if ((s = sl.d_out.reserve(out_bytes + 64)) != PU_OK) return s;
+        if ((s = sl.h_out.reserve(out_bytes + 64)) != PU_OK) return s;
+    }
+    const int n_sym = static_cast<int>(L / static_cast<size_t>(pu_ofdm_symbol_samples(ofdm)));
+    const bool short_frames = static_cast<size_t>(std::max(0, n_sym - training_symbols)) *
+                              static_cast<size_t>(pu_ofdm_bits_per_symbol(ofdm)) < PU_LDPC_N;
+    auto drain = [&](pu::PipeSlot& sl) -> pu_status {
+        if (sl.nb == 0) return PU_OK;
+        PU_CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        const uint8_t* hout = static_cast<const uint8_t*>(sl.h_out.ptr);
+        const int32_t* h_iters = reinterpret_cast<const int32_t*>(hout + iters_off);
+        const uint8_t* h_ok = reinterpret_cast<const uint8_t*>(h_iters + slab);
+        if (info_stride == kb) std::memcpy(info_bytes + sl.off * kb, hout, sl.nb * kb);
+        else for (size_t b = 0; b < sl.nb; ++b) std::memcpy(info_bytes + (sl.off + b) * info_stride, hout + b * kb, kb);
+        if (ok) std::memcpy(ok + sl.off, h_ok, sl.nb);
+        if (iters) std::memcpy(iters + sl.off, h_iters, sl.nb * sizeof(int32_t));
+        sl.nb = 0;
+        return PU_OK;
+    };
+    size_t lane = 0;
+    for (size_t off = 0; off < B; off += slab, lane ^= 1) {
+        pu::PipeSlot& sl = ctx->pipe[lane];
+        if ((s = drain(sl)) != PU_OK) return s;
+        const size_t nb = std::min(slab, B - off);
+        cudaStream_t ls = sl.stream;
+        float* din = static_cast<float*>(sl.d_in.ptr);
+        const float* src = samples + off * L;
+        if (!src_pinned) {
+            std::memcpy(sl.h_in.ptr, src, nb * L * sizeof(float));
+            src = static_cast<const float*>(sl.h_in.ptr);
+        }
+        PU_CUDA_TRY(cudaMemcpyAsync(din, src, nb * L * sizeof(float), cudaMemcpyHostToDevice, ls));
+        const float *d_cfo = nullptr, *d_ph = nullptr;
+        if (cfo_hz) {
+            PU_CUDA_TRY(cudaMemcpyAsync(din + slab * L, cfo_hz + off, nb * sizeof(float), cudaMemcpyHostToDevice, ls));
+            d_cfo = din + slab * L;
+        }
+        if (cfo_phase) {
+            PU_CUDA_TRY(cudaMemcpyAsync(din + slab * L + slab, cfo_phase + off, nb * sizeof(float), cudaMemcpyHostToDevice, ls));
+            d_ph = din + slab * L + slab;
+        }
+        float* d_llr = static_cast<float*>(sl.d_llr.ptr);
+        if (short_frames) PU_CUDA_TRY(cudaMemsetAsync(d_llr, 0, nb * PU_LDPC_N * sizeof(float), ls));   // missing LLRs = erasures
+        if ((s = pu_ofdm_presynced_batch(ofdm, din, nb, L, training_symbols, d_cfo, d_ph, d_llr, PU_LDPC_N, nullptr, nullptr,
+                                         PU_MEM_DEVICE, ls)) != PU_OK) return s;
+        uint8_t* d_info = static_cast<uint8_t*>(sl.d_out.ptr);
+        int32_t* d_iters = reinterpret_cast<int32_t*>(d_info + iters_off);
+        uint8_t* d_ok = reinterpret_cast<uint8_t*>(d_iters + slab);
+        if ((s = pu_ldpc_decode_batch(ldpc, d_llr, PU_LDPC_N, nb, d_info, kb, d_ok, d_iters, PU_MEM_DEVICE, ls)) != PU_OK) return s;
+        PU_CUDA_TRY(cudaMemcpyAsync(sl.h_out.ptr, d_info, out_bytes, cudaMemcpyDeviceToHost, ls));
+        sl.off = off;
+        sl.nb = nb;
+    }
+    if ((s = drain(ctx->pipe[lane])) != PU_OK) return s;
+    if ((s = drain(ctx->pipe[lane ^ 1])) != PU_OK) return s;
     return PU_OK;
 }
 

@@ -86,6 +86,17 @@ pu_status pu_init(int device, pu_ctx** out) {
         pu::set_error("pu_init: cudaStreamCreate failed: %s", cudaGetErrorString(e));
         return PU_ERR_CUDA;
     }
+    for (auto& sl : c->pipe) {
+        sl.h_in.pinned_host = true;
+        sl.h_out.pinned_host = true;
+        if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) sl.stream = nullptr;
+    }
+    if (cudaEventCreateWithFlags(&c->pipe_ev, cudaEventDisableTiming) != cudaSuccess) c->pipe_ev = nullptr;
+    if (!c->pipe[0].stream || !c->pipe[1].stream || !c->pipe_ev) {
+        pu::set_error("pu_init: could not create the pipeline streams");
+        pu_destroy(c);
+        return PU_ERR_CUDA;
+    }
     *out = c;
     return PU_OK;
 }
@@ -99,6 +110,12 @@ void pu_destroy(pu_ctx* c) {
     c->d_aux.release();
     c->h_in.release();
     c->h_out.release();
+    for (auto& sl : c->pipe) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        sl.d_in.release(); sl.d_llr.release(); sl.d_out.release(); sl.h_in.release(); sl.h_out.release();
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
     cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -44,6 +44,16 @@ struct Buffer {
 
 }  // namespace pu
 
+namespace pu {
+// One lane of the host-buffer pipeline (pu_receive_decode_batch with PU_MEM_HOST): its own stream and buffers, so
+// that the H2D copy of slab i+1 overlaps the kernels and the D2H copy of slab i.
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    Buffer d_in, d_llr, d_out, h_in, h_out;
+    size_t off = 0, nb = 0;   // slab in flight (nb == 0: idle)
+};
+}  // namespace pu
+
 struct pu_ctx {
     int device = 0;
     int sm_count = 0;
@@ -52,6 +62,8 @@ struct pu_ctx {
     std::atomic<uint64_t> launches{0};
     // staging for PU_MEM_HOST calls
     pu::Buffer d_in, d_out, d_aux, h_in, h_out;
+    pu::PipeSlot pipe[2];
+    cudaEvent_t pipe_ev = nullptr;
 };
 
 namespace pu {
