@@ -193,3 +193,45 @@ def test_unsupported_configs_fail_loudly(ctx):
     cfg.modulation = R.QAM8
     with pytest.raises(capi.PuError):
         capi.OfdmDemodulator(ctx, cfg)
+
+
+@pytest.mark.parametrize("preset", ["m1", "m3"])
+@pytest.mark.parametrize("mod", [R.DBPSK, R.DQPSK, R.D8PSK])
+def test_warp_fft_kernel_is_bit_identical(ctx, preset, mod):
+    """Differential no-pilot modes with setFrequencyOffset(0) run on the warp-FFT kernel (csrc/ofdm_diff.cu); with an
+    explicit (all-zero) CFO array the same frames run on the general kernel.  Both must give the same LLR words, and
+    the oracle's, for noisy, faded-to-nothing, silent and ragged frames and for 1..3 training symbols."""
+    from projectultra_b200 import capi
+    rate = R.R1_2 if preset == "m1" else R.R3_4
+    cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    nbytes = 40 if preset == "m1" else 60
+    frames = [make_frame(cfg, rate, nbytes, snr, 900 + mod * 50 + i)[0] for i, snr in enumerate(np.linspace(-8, 30, 36))]
+    frames.append(np.zeros_like(frames[0]))                     # silence: weak-signal gate on every carrier
+    frames.append(frames[3] * np.float32(1e-5))                  # very weak signal
+    frames.append(frames[5] * np.float32(37.0))                  # strong signal
+    frames = np.stack(frames).astype(np.float32)
+    B, L = frames.shape
+    S = cfg.symbol_samples
+    zeros = np.zeros(B, np.float32)
+    for training, Lcut in ((2, L), (2, L - S - 7), (2, 3 * S + 11), (2, 2 * S), (1, L), (3, L), (2, L - 1)):
+        x = np.ascontiguousarray(frames[:, :Lcut])
+        n = dem.n_llr(Lcut, training)
+        stride = max(n, 4)
+        fast, fsnr, fcfo = dem.presynced_batch(x, training, llr_stride=stride)
+        gen, gsnr, gcfo = dem.presynced_batch(x, training, zeros, zeros, llr_stride=stride)
+        assert same_bits(fast, gen), (training, Lcut)
+        assert same_bits(fsnr, gsnr) and same_bits(fcfo, gcfo)
+        if n and training == 2:
+            ref, counts = O.ofdm_presynced_batch(cfg, x, n)
+            assert (counts == n).all()
+            assert len(llr_mismatches(fast[:, :n].ravel(), ref.ravel())) == 0
+            same = (fast[:, :n].view(np.uint32) == ref.view(np.uint32)).mean()
+            assert same >= 0.9999, same
+    # fused deinterleave and truncated output go through the same kernel
+    bps = dem.bits_per_symbol
+    dem.set_deinterleave(bps, 648)
+    a, _, _ = dem.presynced_batch(frames, llr_stride=648)
+    b, _, _ = dem.presynced_batch(frames, 2, zeros, zeros, llr_stride=648)
+    dem.set_deinterleave(0)
+    assert same_bits(a, b)

@@ -14,7 +14,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $
 if [ "$SKIP_NCU" != "1" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_launch_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ofdm_presynced -s 3 -c 1 -f -o $OUT/prof_ofdm \
+ncu --set full --clock-control none --import-source on -k regex:ofdm_ -s 3 -c 1 -f -o $OUT/prof_ofdm \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_ofdm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ldpc_flood -s 3 -c 1 -f -o $OUT/prof_ldpc \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/ncu_ldpc.log 2>&1
