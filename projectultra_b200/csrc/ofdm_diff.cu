@@ -40,6 +40,81 @@ __device__ __forceinline__ void bfly(float2& a, float2& b, float2 w) {
 __device__ __forceinline__ float2 bfly_lo(float2 a, float2 b, float2 w) { return cadd(a, cmul(w, b)); }
 __device__ __forceinline__ float2 bfly_hi(float2 a, float2 b, float2 w) { return csub(a, cmul(w, b)); }
 
+// ---- soft demapping of one differential carrier -------------------------------------------------------------------
+// Exact path: soft_demap.hpp:173-237 with the host libm restatements of ref_math.cuh.
+__device__ __noinline__ void demap_exact(int mod, float2 sym, float2 prev, bool first, float nv, float (&l)[3]) {
+    l[0] = l[1] = l[2] = 0.0f;
+    const float2 df = cmul(sym, cconj(prev));
+    const float sp = __fmul_rn(cabs_ref(sym), first ? 1.0f : cabs_ref(prev));   // |(1,0)| == 1 exactly
+    if (sp < 1e-6f) return;                                                     // weak-signal gate (:178,199,224)
+    const float phase = refmath::atan2f_ref(df.y, df.x);
+    if (mod == PU_MOD_DBPSK) {              // :173-187
+        l[0] = clip_llr(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, sp), refmath::cosf_ref(phase)), nv));
+    } else if (mod == PU_MOD_DQPSK) {       // :192-213
+        const float scale = __fdiv_rn(__fmul_rn(2.0f, sp), nv);
+        const float pi = 3.14159265358979f;
+        l[0] = clip_llr(__fmul_rn(scale, refmath::sinf_ref(__fadd_rn(phase, pi / 4))));
+        l[1] = clip_llr(__fmul_rn(scale, refmath::cosf_ref(__fmul_rn(2.0f, phase))));
+    } else {                                // D8PSK :217-237
+        const float conf = __fdiv_rn(sp, nv);
+        l[0] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(phase)));
+        l[1] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(2.0f, phase))));
+        l[2] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(4.0f, phase))));
+    }
+}
+
+// Saturation filter.  With d = sym * conj(prev), |d| = |sym||prev| = sp, so the reference's LLRs are, in exact
+// arithmetic,  DBPSK 2 dx / nv;  DQPSK sqrt2 (dx+dy) / nv  and  2 (dx^2-dy^2) / (nv sp);  D8PSK dy / nv,
+// 2 dx dy / (nv sp), 4 dx dy (dx^2-dy^2) / (nv sp^3): no atan2/sin/cos needed to know them approximately.  The
+// reference evaluates scale * trig(k * atan2f(dy, dx) [+ pi/4]) in fp32; its absolute error is below
+// scale * (k * 5e-7 + 5e-7) (<= 1 ulp atan2f at |phase| <= pi, one rounding of the angle, <= 1 ulp sinf/cosf, k <= 4),
+// and the fp32 evaluation below is within 1e-6 relative.  So when every LLR of the carrier satisfies
+// |approx| >= 10.01 + 1e-5 * scale the reference's clipLLR returns exactly +-10 with the sign of the approximation,
+// and (sp_approx > 2e-6) rules out the weak-signal gate.  >= 99 % of carriers end here; the others
+// take the exact path.  Returns false when the exact path is required.
+__device__ __forceinline__ bool demap_saturated(int mod, float2 df, float nv, float (&l)[3]) {
+    const float dx = df.x, dy = df.y;
+    const float r2 = fmaf(dx, dx, dy * dy);
+    const float sp = sqrtf(r2);                       // approximate |sym||prev|
+    const float inv_nv = __frcp_rn(nv);
+    const float inv_sp = __frcp_rn(sp);
+    float a0, a1 = 1e30f, a2 = 1e30f, scale;
+    if (mod == PU_MOD_DBPSK) {
+        scale = 2.0f * sp * inv_nv;
+        a0 = 2.0f * dx * inv_nv;
+    } else if (mod == PU_MOD_DQPSK) {
+        scale = 2.0f * sp * inv_nv;
+        a0 = 1.41421356f * (dx + dy) * inv_nv;
+        a1 = 2.0f * (dx - dy) * (dx + dy) * inv_nv * inv_sp;
+    } else {
+        scale = sp * inv_nv;
+        const float sc = dx * dy * inv_nv * inv_sp;                  // conf * sin(phase) cos(phase)
+        a0 = dy * inv_nv;
+        a1 = 2.0f * sc;
+        a2 = 4.0f * sc * (dx - dy) * (dx + dy) * inv_sp * inv_sp;
+    }
+    const float thr = fmaf(scale, 1e-5f, 10.01f);
+    const bool ok = (sp > 2e-6f) && (fabsf(a0) >= thr) && (fabsf(a1) >= thr) && (fabsf(a2) >= thr) && (scale < 1e30f);
+    l[0] = copysignf(10.0f, a0);
+    l[1] = copysignf(10.0f, a1);
+    l[2] = copysignf(10.0f, a2);
+    return ok;
+}
+
+__device__ __forceinline__ void store_llrs(float* __restrict__ out, int base, int bps, const float (&l)[3], int llr_limit,
+                                           const int* __restrict__ perm, int perm_len) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        if (b < bps) {
+            const int pos = base + b;
+            if (pos < llr_limit) {
+                const int dst = (perm && pos < perm_len) ? perm[pos] : pos;
+                out[dst] = l[b];
+            }
+        }
+    }
+}
+
 template <int NFFT>
 struct DiffGeom {
     static constexpr int LOG2N = (NFFT == 512) ? 9 : 10;
@@ -63,10 +138,11 @@ __global__ void __launch_bounds__(kDiffWarps * 32) ofdm_diff_kernel(
     float2* F = fftbuf + kDiffWarps * G::BUF;                             // [n_symbols][nd] bins, then equalised symbols
     const int nd = d.n_data;
     float2* Hs = F + n_symbols * nd;                                      // [nd] channel estimate
-    float* eabs = reinterpret_cast<float*>(Hs + kMaxCarr);                // [n_symbols][nd] |equalised symbol|
+    float* eabs = reinterpret_cast<float*>(Hs + kMaxCarr);                // [n_symbols][nd] scratch: list of carriers for the exact demapper
     float* hp_s = eabs + n_symbols * nd;                                  // [nd] |H|^2
     float* nv_s = hp_s + kMaxCarr;                                        // [nd] carrier noise variance
     float* habs = nv_s + kMaxCarr;                                        // [nd] |H| (SNR report only)
+    int* slow_count = reinterpret_cast<int*>(habs + kMaxCarr);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t frame = blockIdx.x;
@@ -179,6 +255,8 @@ __global__ void __launch_bounds__(kDiffWarps * 32) ofdm_diff_kernel(
     // ---- equalize (:747-770): ZF with pilot_phase_correction == (1,0) and timing_offset == 0
     const int nds = n_symbols - training;
     const int items = nds > 0 ? nds * nd : 0;
+    int* slow_list = reinterpret_cast<int*>(eabs);       // [items] carriers that need the exact demapper
+    if (tid == 0) *slow_count = 0;
     for (int it = tid; it < items; it += blockDim.x) {
         const int sd = it / nd, i = it - sd * nd;
         float2* slot = F + (training + sd) * nd + i;
@@ -189,50 +267,33 @@ __global__ void __launch_bounds__(kDiffWarps * 32) ofdm_diff_kernel(
         if (hp > 1e-6f) e = cmul(cmul(cdivs(cmul(rx, cconj(h)), hp), one), one);   // :761
         else e = cmul(cmul(rx, one), one);
         *slot = e;
-        eabs[(training + sd) * nd + i] = cabs_ref(e);
     }
     __syncthreads();
 
-    // ---- demodulateSymbol (demodulator.cpp:279-316) + soft_demap.hpp
+    // ---- demodulateSymbol (demodulator.cpp:279-316) + soft_demap.hpp: saturation filter first, exact path for the rest
     float* out = llr_out + frame * llr_stride;
-    const int bps = d.bps;
+    const int bps = d.bps, mod = d.mod;
     for (int it = tid; it < items; it += blockDim.x) {
         const int sd = it / nd, i = it - sd * nd;
         const int s = training + sd;
         const float2 sym = F[s * nd + i];
         const float2 prev = sd > 0 ? F[(s - 1) * nd + i] : make_float2(1.0f, 0.0f);   // differential reference (1,0) (:251-255)
-        const float pabs = sd > 0 ? eabs[(s - 1) * nd + i] : 1.0f;
         const float nv = __fmul_rn(nv_s[i], d.ce_margin);
-        const float2 df = cmul(sym, cconj(prev));
-        const float sp = __fmul_rn(eabs[s * nd + i], pabs);
-        float l[3] = {0.0f, 0.0f, 0.0f};
-        if (!(sp < 1e-6f)) {
-            const float phase = refmath::atan2f_ref(df.y, df.x);
-            if (d.mod == PU_MOD_DBPSK) {              // soft_demap.hpp:173-187
-                l[0] = clip_llr(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, sp), refmath::cosf_ref(phase)), nv));
-            } else if (d.mod == PU_MOD_DQPSK) {       // :192-213
-                const float scale = __fdiv_rn(__fmul_rn(2.0f, sp), nv);
-                const float pi = 3.14159265358979f;
-                l[0] = clip_llr(__fmul_rn(scale, refmath::sinf_ref(__fadd_rn(phase, pi / 4))));
-                l[1] = clip_llr(__fmul_rn(scale, refmath::cosf_ref(__fmul_rn(2.0f, phase))));
-            } else {                                  // D8PSK :217-237
-                const float conf = __fdiv_rn(sp, nv);
-                l[0] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(phase)));
-                l[1] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(2.0f, phase))));
-                l[2] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(4.0f, phase))));
-            }
-        }
-        const int base = it * bps;
-#pragma unroll
-        for (int b = 0; b < 3; ++b) {
-            if (b < bps) {
-                const int pos = base + b;
-                if (pos < llr_limit) {
-                    const int dst = (d.llr_perm && pos < d.perm_len) ? d.llr_perm[pos] : pos;
-                    out[dst] = l[b];
-                }
-            }
-        }
+        float l[3];
+        if (demap_saturated(mod, cmul(sym, cconj(prev)), nv, l)) store_llrs(out, it * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
+        else slow_list[atomicAdd(slow_count, 1)] = it;
+    }
+    __syncthreads();
+    const int n_slow = *slow_count;
+    for (int k = tid; k < n_slow; k += blockDim.x) {     // dense: the first n_slow threads of the CTA
+        const int it = slow_list[k];
+        const int sd = it / nd, i = it - sd * nd;
+        const int s = training + sd;
+        const float2 sym = F[s * nd + i];
+        const float2 prev = sd > 0 ? F[(s - 1) * nd + i] : make_float2(1.0f, 0.0f);
+        float l[3];
+        demap_exact(mod, sym, prev, sd == 0, __fmul_rn(nv_s[i], d.ce_margin), l);
+        store_llrs(out, it * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
     }
     if (tid == 0) {
         if (snr_db_out) {   // reporting-only SNR estimate of estimateChannelFromLTS (:208-225), getEstimatedSNR (demodulator.cpp:797-799)
@@ -262,7 +323,7 @@ bool ofdm_diff_supported(const OfdmDev& d, int n_symbols, int training) {
 size_t ofdm_diff_smem(const OfdmDev& d, int n_symbols) {
     const size_t buf = d.nfft == 512 ? DiffGeom<512>::BUF : DiffGeom<1024>::BUF;
     return sizeof(float2) * (kDiffWarps * buf + static_cast<size_t>(n_symbols) * d.n_data + kMaxCarr) +
-           sizeof(float) * (static_cast<size_t>(n_symbols) * d.n_data + 3 * kMaxCarr);
+           sizeof(float) * (static_cast<size_t>(n_symbols) * d.n_data + 3 * kMaxCarr + 4);
 }
 
 cudaError_t ofdm_diff_launch(const OfdmDev& d, const float2* host_twiddle, const float* samples, size_t B, size_t frame_stride,
