@@ -37,4 +37,28 @@ struct LdpcHostTables {
 };
 LdpcHostTables make_ldpc_tables(const LdpcCode& code);
 
+// Bank-conflict-free layout for the register-resident decoder kernel (ldpc_flood_reg_kernel in ldpc_decode.cu).
+//   * thread p < m owns check slot p (checks sorted by descending info degree, 32 per warp);
+//   * information bit j lives in "variable slot" a(j) < kpad: its total is tot[a], its d-th incoming message
+//     (d = rank of the check among j's checks in ASCENDING CHECK ORDER, the accumulation order of
+//     ldpc_decoder.cpp:208-213) is msg[d * kpad + a];
+//   * a(j) and the order of the edges inside every check are chosen so that the 32 lanes of a warp touch 32
+//     different shared-memory banks (a mod 32) on every edge instruction: variables get banks by local search
+//     until no warp uses a bank more often than its longest row, then each warp's (check x bank) bipartite
+//     multigraph is edge-coloured (Koenig) with one colour per edge instruction.  conflicts = what is left over.
+struct LdpcLayout {
+    int k = 0, m = 0, threads = 0, kpad = 0, dv = 0, vr = 0;
+    int inf_slot = 0;      // tot[] word that holds +INF (absent check-side edges read it)
+    int scratch_slot = 0;  // msg[] word that absorbs the writes of absent edges
+    int tot_words = 0, msg_words = 0;
+    std::vector<uint8_t> cn_ninfo;    // [threads] info edges of slot p (0 for p >= m)
+    std::vector<uint16_t> cn_check;   // [threads] original check index of slot p
+    std::vector<uint16_t> cn_rd;      // [6][threads] tot[] index read by edge e of slot p
+    std::vector<uint16_t> cn_wr;      // [6][threads] msg[] index written by edge e of slot p
+    std::vector<uint16_t> var_slot;   // [k]    a(j)
+    std::vector<int16_t> slot_var;    // [kpad] j or -1
+    int conflicts = 0;                // extra shared-memory wavefronts per iteration that the layout could not remove
+};
+LdpcLayout make_ldpc_layout(const LdpcCode& code);
+
 }  // namespace pu

@@ -166,8 +166,18 @@ __global__ void __launch_bounds__(512) ldpc_flood_kernel(LdpcDevTables t, const 
 //  * absent edges: variable-side slots point at a word holding +0.0f (x + 0 == x for x != -0); check-side edges of
 //    rows shorter than their warp's longest row read a total of +INF: no sign, and a magnitude of exactly the clamp
 //    limit, which cannot lower the first or second minimum of a row that has two real edges (every row does).
+struct LdpcRegDev {   // device view of LdpcLayout (ldpc_code.h)
+    int k, m, kpad, inf_slot, msg_words, threads;
+    const uint8_t* cn_ninfo;
+    const uint16_t* cn_check;
+    const uint16_t* cn_rd;     // [kE][threads]
+    const uint16_t* cn_wr;     // [kE][threads]
+    const uint16_t* var_slot;  // [k]
+    const int16_t* slot_var;   // [kpad]
+};
+
 template <int NE>
-__device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* __restrict__ c2v_col, int M, const int (&var)[kE],
+__device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* __restrict__ msg, const int (&rd)[kE], const int (&wr)[kE],
                                           float (&prev)[kE], float par_llr, float& pc, float lim, bool last, unsigned& syn_bits) {
     const float ptot = __fadd_rn(par_llr, pc);        // total of the parity bit (:206-213)
     const float vp = __fsub_rn(ptot, pc);             // its v2c before the clamp (:219-222)
@@ -178,7 +188,7 @@ __device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* 
     float v[NE > 0 ? NE : 1], a[NE > 0 ? NE : 1];
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
-        const float te = tot[var[e]];
+        const float te = tot[rd[e]];
         px ^= __float_as_uint(te);
         v[e] = __fsub_rn(te, prev[e]);
         sx ^= __float_as_uint(v[e]);
@@ -194,67 +204,61 @@ __device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* 
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             const unsigned mag = (a[e] == m1) ? s2 : s1;
-            const float msg = __uint_as_float(mag ^ (__float_as_uint(v[e]) & 0x80000000u));
-            prev[e] = msg;
-            c2v_col[e * M] = msg;
+            const float out = __uint_as_float(mag ^ (__float_as_uint(v[e]) & 0x80000000u));
+            prev[e] = out;
+            msg[wr[e]] = out;
         }
         const unsigned mag = (ap == m1) ? s2 : s1;
         pc = __uint_as_float(mag ^ (__float_as_uint(vp) & 0x80000000u));
     }
 }
 
+// Shared memory: msg[d][a] = message from the d-th check (ascending check index) of the information bit in variable
+// slot a; tot[a] = its total.  The variable pass reads msg[d * kpad + a] with a = thread index: conflict-free by
+// construction.  The check pass gathers tot[a] and scatters msg[rank * kpad + a]; both hit bank a mod 32, and the
+// layout (ldpc_code.cpp: make_ldpc_layout) makes the 32 lanes of a warp use 32 different banks on every edge.
 template <int VR, int DV>
-__global__ void __launch_bounds__(512) ldpc_flood_reg_kernel(LdpcDevTables t, const float* __restrict__ llr, size_t llr_stride,
+__global__ void __launch_bounds__(512) ldpc_flood_reg_kernel(LdpcRegDev t, const float* __restrict__ llr, size_t llr_stride,
                                                              uint8_t* __restrict__ info, size_t info_stride,
                                                              uint8_t* __restrict__ ok, int32_t* __restrict__ iters, int max_iter) {
     extern __shared__ float smem[];
-    const int K = t.k, M = t.m;
-    float* c2v = smem;                 // [kE][M], then the +0.0f word
-    float* tot = c2v + kE * M + 4;     // [K], then the +INF word
-    const int zero_slot = kE * M;
-    const int inf_slot = K;
+    const int K = t.k, M = t.m, KP = t.kpad;
+    float* msg = smem;                       // [DV][KP] + scratch row
+    float* tot = smem + t.msg_words;         // [KP] + the +INF word
     const int tid = threadIdx.x, T = blockDim.x;
     const float* x = llr + static_cast<size_t>(blockIdx.x) * llr_stride;
 
     const bool has_check = tid < M;
     int ninfo = 0;
-    int var[kE];
+    int rd[kE], wr[kE];
     float prev[kE];
     float par_llr = 0.0f, pc = 0.0f;
 #pragma unroll
-    for (int e = 0; e < kE; ++e) { var[e] = inf_slot; prev[e] = 0.0f; }
+    for (int e = 0; e < kE; ++e) {
+        rd[e] = t.cn_rd[e * T + tid];
+        wr[e] = t.cn_wr[e * T + tid];
+        prev[e] = 0.0f;
+    }
     if (has_check) {
         ninfo = t.cn_ninfo[tid];
-#pragma unroll
-        for (int e = 0; e < kE; ++e)
-            if (e < ninfo) var[e] = t.cn_var[e * M + tid];
         par_llr = __fadd_rn(x[K + t.cn_check[tid]], 0.0f);
     }
     const int nw = __reduce_max_sync(0xffffffffu, ninfo);   // longest row of this warp (slots are sorted by degree)
     float lin[VR];
-    int slot[VR][DV];
 #pragma unroll
     for (int r = 0; r < VR; ++r) {
-        const int j = tid + r * T;
+        const int a = tid + r * T;
         lin[r] = 0.0f;
-#pragma unroll
-        for (int d = 0; d < DV; ++d) slot[r][d] = zero_slot;
-        if (j < K) {
-            lin[r] = __fadd_rn(x[j], 0.0f);
-            tot[j] = lin[r];
-            const int deg = t.vn_deg[j];
-#pragma unroll
-            for (int d = 0; d < DV; ++d)
-                if (d < deg) slot[r][d] = t.vn_slot[d * K + j];
+        if (a < KP) {
+            const int j = t.slot_var[a];
+            if (j >= 0) lin[r] = __fadd_rn(x[j], 0.0f);
+            tot[a] = lin[r];
         }
     }
-    if (tid == 0) {
-        c2v[zero_slot] = 0.0f;
-        tot[inf_slot] = INFINITY;
-    }
+    for (int i = tid; i < t.msg_words; i += T) msg[i] = 0.0f;   // absent variable-side edges stay +0 forever
+    if (tid == 0) tot[t.inf_slot] = INFINITY;
     __syncthreads();
 
-    float* c2v_col = c2v + tid;
     int it = 0;
     int converged = 0;
     for (;; ++it) {
@@ -263,13 +267,13 @@ __global__ void __launch_bounds__(512) ldpc_flood_reg_kernel(LdpcDevTables t, co
         unsigned syn_bits = 0;
         if (has_check) {
             switch (nw) {
-                case 0: cn_update<0>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 1: cn_update<1>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 2: cn_update<2>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 3: cn_update<3>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 4: cn_update<4>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 5: cn_update<5>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
-                default: cn_update<6>(tot, c2v_col, M, var, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 0: cn_update<0>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 1: cn_update<1>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 2: cn_update<2>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 3: cn_update<3>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 4: cn_update<4>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
+                case 5: cn_update<5>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
+                default: cn_update<6>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
             }
         }
         const int any = __syncthreads_or(static_cast<int>(syn_bits >> 31));   // syndrome of iteration it-1's totals (:227-235)
@@ -277,11 +281,13 @@ __global__ void __launch_bounds__(512) ldpc_flood_reg_kernel(LdpcDevTables t, co
         if (last) break;
 #pragma unroll
         for (int r = 0; r < VR; ++r) {
-            const int j = tid + r * T;
-            float s = lin[r];
+            const int a = tid + r * T;
+            if (a < KP) {
+                float s = lin[r];
 #pragma unroll
-            for (int d = 0; d < DV; ++d) s = __fadd_rn(s, c2v[slot[r][d]]);   // ascending check order (:208-213)
-            if (j < K) tot[j] = s;
+                for (int d = 0; d < DV; ++d) s = __fadd_rn(s, msg[d * KP + a]);   // ascending check order (:208-213)
+                tot[a] = s;
+            }
         }
         __syncthreads();
     }
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(512) ldpc_flood_reg_kernel(LdpcDevTables t, co
     for (int b = tid; b < nbytes; b += T) {   // k information bits MSB-first, last byte left-justified (:242-256)
         unsigned byte = 0;
         int cnt = 0;
-        for (int j = b * 8; j < b * 8 + 8 && j < K; ++j, ++cnt) byte = (byte << 1) | (tot[j] < 0.0f ? 1u : 0u);
+        for (int j = b * 8; j < b * 8 + 8 && j < K; ++j, ++cnt) byte = (byte << 1) | (tot[t.var_slot[j]] < 0.0f ? 1u : 0u);
         out[b] = static_cast<uint8_t>(byte << (8 - cnt));
     }
     if (tid == 0) {
@@ -321,6 +327,9 @@ struct pu_ldpc {
     pu::LdpcCode code;
     pu::LdpcHostTables host;
     pu::DevArray d_ninfo, d_check, d_var, d_deg, d_slot;
+    pu::LdpcLayout layout;
+    pu::DevArray r_ninfo, r_check, r_rd, r_wr, r_vslot, r_svar;
+    pu::LdpcRegDev reg{};
     pu::LdpcDevTables dev{};
     int threads = 128;
     size_t smem_bytes = 0;
@@ -349,10 +358,25 @@ struct pu_ldpc {
         const int per_round = host.m > 256 ? (host.m + 1) / 2 : host.m;
         threads = (per_round + 31) / 32 * 32;
         smem_bytes = sizeof(float) * (static_cast<size_t>(pu::kE + 2) * host.m + 2 * static_cast<size_t>(host.k));
-        reg_threads = (host.m + 31) / 32 * 32;
-        reg_vr = (host.k + reg_threads - 1) / reg_threads;
-        reg_dv = host.dv_max;
-        reg_smem = sizeof(float) * (static_cast<size_t>(pu::kE) * host.m + 4 + static_cast<size_t>(host.k) + 4);
+        layout = pu::make_ldpc_layout(code);
+        if ((s = r_ninfo.upload(layout.cn_ninfo)) != PU_OK) return s;
+        if ((s = r_check.upload(layout.cn_check)) != PU_OK) return s;
+        if ((s = r_rd.upload(layout.cn_rd)) != PU_OK) return s;
+        if ((s = r_wr.upload(layout.cn_wr)) != PU_OK) return s;
+        if ((s = r_vslot.upload(layout.var_slot)) != PU_OK) return s;
+        if ((s = r_svar.upload(layout.slot_var)) != PU_OK) return s;
+        reg.k = layout.k; reg.m = layout.m; reg.kpad = layout.kpad; reg.inf_slot = layout.inf_slot;
+        reg.msg_words = layout.msg_words; reg.threads = layout.threads;
+        reg.cn_ninfo = static_cast<const uint8_t*>(r_ninfo.p);
+        reg.cn_check = static_cast<const uint16_t*>(r_check.p);
+        reg.cn_rd = static_cast<const uint16_t*>(r_rd.p);
+        reg.cn_wr = static_cast<const uint16_t*>(r_wr.p);
+        reg.var_slot = static_cast<const uint16_t*>(r_vslot.p);
+        reg.slot_var = static_cast<const int16_t*>(r_svar.p);
+        reg_threads = layout.threads;
+        reg_vr = layout.vr;
+        reg_dv = layout.dv;
+        reg_smem = sizeof(float) * (static_cast<size_t>(layout.msg_words) + layout.tot_words);
         return PU_OK;
     }
 };
@@ -365,9 +389,9 @@ static pu_status launch_decode(pu_ldpc* h, const float* d_llr, size_t llr_stride
     for (size_t off = 0; off < B; off += kMaxGrid) {
         const size_t nb = std::min(kMaxGrid, B - off);
 #define PU_LDPC_REG_CASE(VR, DV)                                                                                   \
-    if (!done && h->reg_vr <= (VR) && h->reg_dv <= (DV)) {                                                        \
+    if (!done && h->reg_vr <= (VR) && h->reg_dv == (DV)) {                                                        \
         pu::ldpc_flood_reg_kernel<VR, DV><<<static_cast<unsigned>(nb), h->reg_threads, h->reg_smem, st>>>(        \
-            h->dev, d_llr + off * llr_stride, llr_stride, d_info + off * info_stride, info_stride,                \
+            h->reg, d_llr + off * llr_stride, llr_stride, d_info + off * info_stride, info_stride,                \
             d_ok ? d_ok + off : nullptr, d_iters ? d_iters + off : nullptr, h->max_iter);                         \
         done = true;                                                                                              \
     }
