@@ -1,0 +1,256 @@
+// tests/cpp/dropin_driver.cpp — TEST INFRASTRUCTURE.  One binary, both implementations: the reference's classes
+// (ultra::*, linked from oracle/_ref/libpu_ref.so) and the drop-in classes of include/pu/pu_dropin.hpp (pu::*, over
+// libpu_b200.so) are driven with the same inputs and must agree bit for bit.  The checks follow the reference's own
+// drivers for this surface: tests/test_multiblock_ldpc.cpp:104-317,441-488 (encode -> +-6 LLR -> decodeSoft for
+// 1/2/5 blocks x 5 rates, boundary bytes, 24/46/279-byte frames), tests/test_interleaver.cpp (round trips) and the RX
+// loop of tools/test_iwaveform.cpp:597-806 / tools/test_ofdm_chirp_pilots.cpp:183-260 with known timing.
+// Built here (needs the reference headers) by oracle/ref_build/Makefile into oracle/_ref/dropin_driver; run on the GPU
+// box by tests/test_dropin_cpp_gpu.py.
+#include <cstdio>
+#include <cstring>
+#include <random>
+
+#define PU_DROPIN_WITH_ULTRA
+#include "pu/pu_dropin.hpp"
+
+#include "ultra/fec.hpp"
+#include "ultra/logging.hpp"
+#include "ultra/ofdm.hpp"
+
+using namespace ultra;
+
+static int g_fail = 0, g_pass = 0;
+#define CHECK(cond, ...)                                   \
+    do {                                                   \
+        if (cond) { ++g_pass; }                            \
+        else { ++g_fail; std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } \
+    } while (0)
+
+static bool same_words(const std::vector<float>& a, const std::vector<float>& b) {
+    return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(float)) == 0);
+}
+
+static std::vector<float> hard_llrs(const Bytes& coded, float mag) {
+    std::vector<float> llr;
+    for (uint8_t byte : coded)
+        for (int b = 7; b >= 0; --b) llr.push_back(((byte >> b) & 1) ? -mag : mag);
+    return llr;
+}
+
+static void ldpc_section() {
+    const CodeRate rates[] = {CodeRate::R1_4, CodeRate::R1_2, CodeRate::R2_3, CodeRate::R3_4, CodeRate::R5_6};
+    const int ks[] = {162, 324, 432, 486, 540};
+    std::mt19937 rng(2024);
+    for (int r = 0; r < 5; ++r) {
+        LDPCEncoder ref_enc(rates[r]);
+        LDPCDecoder ref_dec(rates[r]);
+        pu::LDPCEncoder enc(rates[r]);
+        pu::LDPCDecoder dec(rates[r]);
+        CHECK(dec.getRate() == rates[r], "getRate");
+        for (int blocks : {1, 2, 5}) {
+            Bytes data(static_cast<size_t>(ks[r]) * blocks / 8);
+            for (auto& b : data) b = static_cast<uint8_t>(rng());
+            const Bytes c_ref = ref_enc.encode(data), c_pu = enc.encode(data);
+            CHECK(c_ref == c_pu, "encode rate %d blocks %d", r, blocks);
+            for (float mag : {6.0f, 10.0f, 1.5f}) {
+                const auto llr = hard_llrs(c_ref, mag);
+                const Bytes d_ref = ref_dec.decodeSoft(llr), d_pu = dec.decodeSoft(llr);
+                CHECK(d_ref == d_pu, "decodeSoft bytes rate %d blocks %d mag %.1f", r, blocks, mag);
+                CHECK(ref_dec.lastDecodeSuccess() == dec.lastDecodeSuccess(), "success flag rate %d blocks %d", r, blocks);
+                CHECK(ref_dec.lastIterations() == dec.lastIterations(), "iterations rate %d blocks %d: %d vs %d", r, blocks,
+                      ref_dec.lastIterations(), dec.lastIterations());
+                CHECK(dec.lastDecodeSuccess() && std::equal(data.begin(), data.end(), d_pu.begin()), "identity rate %d blocks %d", r, blocks);
+            }
+            // hard-decision entry point and a partial trailing block
+            const Bytes h_ref = ref_dec.decode(c_ref), h_pu = dec.decode(c_pu);
+            CHECK(h_ref == h_pu && ref_dec.lastDecodeSuccess() == dec.lastDecodeSuccess(), "decode(hard) rate %d blocks %d", r, blocks);
+            auto llr = hard_llrs(c_ref, 6.0f);
+            llr.resize(llr.size() - 100);
+            const Bytes p_ref = ref_dec.decodeSoft(llr), p_pu = dec.decodeSoft(llr);
+            CHECK(p_ref == p_pu && ref_dec.lastDecodeSuccess() == dec.lastDecodeSuccess() && ref_dec.lastIterations() == dec.lastIterations(),
+                  "partial block rate %d blocks %d", r, blocks);
+        }
+        // boundary byte patterns (test_multiblock_ldpc.cpp:233-317) and noisy / inverted / erased inputs
+        for (uint8_t fill : {uint8_t(0x00), uint8_t(0xFF), uint8_t(0xAA), uint8_t(0x55)}) {
+            Bytes data(static_cast<size_t>(ks[r]) * 2 / 8, fill);
+            const auto llr = hard_llrs(ref_enc.encode(data), 6.0f);
+            CHECK(ref_dec.decodeSoft(llr) == dec.decodeSoft(llr) && ref_dec.lastDecodeSuccess() == dec.lastDecodeSuccess(), "fill %02x rate %d", fill, r);
+        }
+        std::normal_distribution<float> noise(0.0f, 2.0f);
+        for (int t = 0; t < 40; ++t) {
+            Bytes data(static_cast<size_t>(ks[r]) / 8);
+            for (auto& b : data) b = static_cast<uint8_t>(rng());
+            auto llr = hard_llrs(ref_enc.encode(data), 4.0f);
+            for (auto& l : llr) l += noise(rng) * (0.5f + 0.05f * static_cast<float>(t));
+            if (t % 7 == 3) for (auto& l : llr) l = -l;                 // inverted LLRs must be rejected the same way
+            if (t % 5 == 1) for (size_t i = 0; i < llr.size(); i += 9) llr[i] = 0.0f;   // erasures
+            const Bytes a = ref_dec.decodeSoft(llr), b = dec.decodeSoft(llr);
+            CHECK(a == b && ref_dec.lastDecodeSuccess() == dec.lastDecodeSuccess() && ref_dec.lastIterations() == dec.lastIterations(),
+                  "noisy rate %d trial %d (iters %d vs %d)", r, t, ref_dec.lastIterations(), dec.lastIterations());
+        }
+        const Bytes e_ref = ref_dec.decodeSoft({}), e_pu = dec.decodeSoft({});
+        CHECK(e_ref.empty() && e_pu.empty() && !dec.lastDecodeSuccess() && !ref_dec.lastDecodeSuccess(), "empty input rate %d", r);
+        ref_dec.setMaxIterations(3);
+        dec.setMaxIterations(3);
+        auto llr = hard_llrs(ref_enc.encode(Bytes(static_cast<size_t>(ks[r]) / 8, 0x3C)), 1.0f);
+        for (size_t i = 0; i < llr.size(); i += 3) llr[i] = -llr[i];
+        CHECK(ref_dec.decodeSoft(llr) == dec.decodeSoft(llr) && ref_dec.lastIterations() == dec.lastIterations(), "max_iter 3 rate %d", r);
+    }
+    // frame sizes of test_multiblock_ldpc.cpp:441-488 at R1/4, and setRate
+    pu::LDPCDecoder dec(CodeRate::R1_2);
+    LDPCDecoder ref_dec(CodeRate::R1_2);
+    dec.setRate(CodeRate::R1_4);
+    ref_dec.setRate(CodeRate::R1_4);
+    LDPCEncoder ref_enc(CodeRate::R1_4);
+    for (size_t n : {size_t(24), size_t(46), size_t(279)}) {
+        Bytes data(n);
+        for (size_t i = 0; i < n; ++i) data[i] = static_cast<uint8_t>(i * 7 + 1);
+        const auto llr = hard_llrs(ref_enc.encode(data), 6.0f);
+        const Bytes a = ref_dec.decodeSoft(llr), b = dec.decodeSoft(llr);
+        CHECK(a == b && dec.lastDecodeSuccess() && std::equal(data.begin(), data.end(), b.begin()), "frame of %zu bytes", n);
+    }
+}
+
+static void interleaver_section() {
+    std::mt19937 rng(7);
+    for (size_t bps : {size_t(60), size_t(90), size_t(118), size_t(220)}) {
+        ChannelInterleaver ref(bps, 648);
+        pu::ChannelInterleaver mine(bps, 648);
+        std::vector<float> x(648);
+        for (auto& v : x) v = static_cast<float>(rng() % 2001) / 100.0f - 10.0f;
+        CHECK(same_words(ref.interleave(x), mine.interleave(x)), "ChannelInterleaver(%zu) interleave", bps);
+        CHECK(same_words(ref.deinterleave(x), mine.deinterleave(x)), "ChannelInterleaver(%zu) deinterleave", bps);
+        CHECK(same_words(mine.deinterleave(mine.interleave(x)), x), "ChannelInterleaver(%zu) round trip", bps);
+        Bytes d(81);
+        for (auto& b : d) b = static_cast<uint8_t>(rng());
+        CHECK(ref.interleave(d) == mine.interleave(d) && ref.deinterleave(d) == mine.deinterleave(d), "ChannelInterleaver(%zu) bytes", bps);
+        CHECK(ref.getSymbolSeparation() == mine.getSymbolSeparation(), "ChannelInterleaver(%zu) separation", bps);
+    }
+    Interleaver ref(6, 108);
+    pu::Interleaver mine(6, 108);
+    std::vector<float> x(648);
+    for (auto& v : x) v = static_cast<float>(rng() % 97);
+    CHECK(same_words(ref.interleave(x), mine.interleave(x)) && same_words(ref.deinterleave(x), mine.deinterleave(x)), "Interleaver(6,108) soft");
+    Bytes d(81);
+    for (auto& b : d) b = static_cast<uint8_t>(rng());
+    CHECK(ref.interleave(d) == mine.interleave(d) && ref.deinterleave(d) == mine.deinterleave(d), "Interleaver(6,108) bytes");
+}
+
+static Samples add_noise(const Samples& tx, float snr_db, uint32_t seed) {
+    double p = 0;
+    for (float s : tx) p += static_cast<double>(s) * s;
+    const float sigma = static_cast<float>(std::sqrt(p / tx.size() / std::pow(10.0, snr_db / 10.0)));
+    std::mt19937 rng(seed);
+    std::normal_distribution<float> n(0.0f, sigma);
+    Samples rx = tx;
+    for (auto& s : rx) s += n(rng);
+    return rx;
+}
+
+static std::vector<float> drain(OFDMDemodulator& d) {
+    std::vector<float> all;
+    while (d.hasPendingData()) {
+        auto c = d.getSoftBits();
+        all.insert(all.end(), c.begin(), c.end());
+    }
+    return all;
+}
+static std::vector<float> drain(pu::OFDMDemodulator& d) {
+    std::vector<float> all;
+    while (d.hasPendingData()) {
+        auto c = d.getSoftBits();
+        all.insert(all.end(), c.begin(), c.end());
+    }
+    return all;
+}
+
+static void ofdm_section() {
+    struct Case { const char* name; bool nvis; Modulation mod; CodeRate rate; bool pilots; uint32_t spacing; size_t payload; float snr; };
+    const Case cases[] = {{"M1 DQPSK R1/2", false, Modulation::DQPSK, CodeRate::R1_2, false, 2, 40, 6.0f},
+                          {"M1 D8PSK R1/2", false, Modulation::D8PSK, CodeRate::R1_2, false, 2, 40, 14.0f},
+                          {"M1 16QAM R1/2 pilots/2", false, Modulation::QAM16, CodeRate::R1_2, true, 2, 40, 22.0f},
+                          {"M3 32QAM R3/4 pilots/4", true, Modulation::QAM32, CodeRate::R3_4, true, 4, 60, 26.0f},
+                          {"M3 DQPSK R1/2", true, Modulation::DQPSK, CodeRate::R1_2, false, 2, 40, 8.0f}};
+    for (const Case& c : cases) {
+        ModemConfig cfg = c.nvis ? presets::nvis_mode() : ModemConfig{};
+        cfg.modulation = c.mod;
+        cfg.code_rate = c.rate;
+        cfg.use_pilots = c.pilots;
+        cfg.pilot_spacing = c.spacing;
+        LDPCEncoder enc(c.rate);
+        LDPCDecoder ref_dec(c.rate);
+        pu::LDPCDecoder dec(c.rate);
+        std::mt19937 rng(99);
+        for (int trial = 0; trial < 6; ++trial) {
+            Bytes payload(c.payload);
+            for (auto& b : payload) b = static_cast<uint8_t>(rng());
+            const Bytes coded = enc.encode(payload);
+            OFDMModulator mod(cfg);
+            Samples tx = mod.generateTrainingSymbols(2);
+            const Samples data = mod.modulate(coded, c.mod);
+            tx.insert(tx.end(), data.begin(), data.end());
+            const Samples rx = add_noise(tx, c.snr - 2.0f * static_cast<float>(trial % 3), 1000u + static_cast<uint32_t>(trial));
+
+            OFDMDemodulator ref(cfg);
+            ref.reset();
+            ref.setFrequencyOffset(0.0f);
+            const bool ref_ready = ref.processPresynced(SampleSpan(rx.data(), rx.size()), 2);
+            const float ref_snr = ref.getEstimatedSNR();
+            const auto ref_soft = drain(ref);
+
+            pu::OFDMDemodulator mine(cfg);
+            mine.reset();
+            mine.setFrequencyOffset(0.0f);
+            const bool ready = mine.processPresynced(SampleSpan(rx.data(), rx.size()), 2);
+            const float snr = mine.getEstimatedSNR();
+            const auto soft = drain(mine);
+            CHECK(ref_ready == ready, "%s trial %d ready flag", c.name, trial);
+            CHECK(ref_soft.size() == soft.size(), "%s trial %d soft-bit count %zu vs %zu", c.name, trial, ref_soft.size(), soft.size());
+            size_t diff = 0;
+            double worst = 0;
+            for (size_t i = 0; i < std::min(soft.size(), ref_soft.size()); ++i) {
+                if (std::memcmp(&soft[i], &ref_soft[i], 4) != 0) ++diff;
+                worst = std::max(worst, static_cast<double>(std::fabs(soft[i] - ref_soft[i])) / std::max(0.5, static_cast<double>(std::fabs(ref_soft[i]))));
+            }
+            CHECK(worst <= 1e-4, "%s trial %d LLR tolerance 1e-4 exceeded: %.3g", c.name, trial, worst);
+            CHECK(diff * 1000 <= soft.size(), "%s trial %d: %zu of %zu LLR words differ", c.name, trial, diff, soft.size());
+            CHECK(std::fabs(ref_snr - snr) <= 1e-3f * std::max(1.0f, std::fabs(ref_snr)), "%s trial %d SNR estimate %.4f vs %.4f", c.name, trial, ref_snr, snr);
+            if (ref_soft.size() >= 648 && soft.size() >= 648) {
+                const Bytes a = ref_dec.decodeSoft(std::span<const float>(ref_soft.data(), 648));
+                const Bytes b = dec.decodeSoft(std::span<const float>(soft.data(), 648));
+                CHECK(a == b && ref_dec.lastDecodeSuccess() == dec.lastDecodeSuccess() && ref_dec.lastIterations() == dec.lastIterations(),
+                      "%s trial %d decoded bytes / flags", c.name, trial);
+            }
+            // the IWaveform surface: configure -> setFrequencyOffset -> process -> getSoftBits (tools/test_iwaveform.cpp:597-806)
+            if (trial == 0) {
+                std::unique_ptr<IWaveform> wf = std::make_unique<pu::OfdmChirpWaveform>(cfg);
+                wf->configure(c.mod, c.rate);
+                wf->reset();
+                wf->setFrequencyOffset(0.0f);
+                const bool wready = wf->process(SampleSpan(rx.data(), rx.size()));
+                const auto wsoft = wf->getSoftBits();
+                CHECK(wready == ref_ready && same_words(wsoft, soft), "%s IWaveform::process/getSoftBits", c.name);
+                CHECK(wf->getSamplesPerSymbol() == static_cast<int>(cfg.getSymbolDuration()) && wf->getCarrierCount() == static_cast<int>(cfg.num_carriers),
+                      "%s IWaveform geometry", c.name);
+                SyncResult sr;
+                CHECK(!wf->detectSync(SampleSpan(rx.data(), rx.size()), sr) && !sr.detected, "%s detectSync reports not detected", c.name);
+            }
+        }
+    }
+}
+
+int main() {
+    setLogLevel(LogLevel::ERROR);
+    if (!std::freopen("/dev/null", "w", stderr)) return 2;   // the reference prints unconditionally on the hot path
+    try {
+        ldpc_section();
+        interleaver_section();
+        ofdm_section();
+    } catch (const std::exception& e) {
+        std::printf("EXCEPTION: %s\n", e.what());
+        return 2;
+    }
+    std::printf("dropin_driver: %d checks passed, %d failed\n", g_pass, g_fail);
+    std::printf(g_fail == 0 ? "ALL PASS\n" : "SOME FAILED\n");
+    return g_fail == 0 ? 0 : 1;
+}

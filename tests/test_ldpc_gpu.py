@@ -173,3 +173,38 @@ def test_device_memory_path_and_properties_at_full_size(ctx, rate):
     cpu = O.ldpc_decode_batch(rate, noisy[:P].cpu().numpy())
     assert_same((info[:P].cpu().numpy(), ok[:P].cpu().numpy(), it[:P].cpu().numpy()), cpu)
     assert 0 < int(ok[:P].sum()) < P or rate in (R.R3_4, R.R5_6)
+
+
+def oracle_decode_parallel(rate, llr):
+    """The oracle on all host cores (ctypes releases the GIL; the oracle's scratch is thread-local)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    O.ldpc_decode_batch(rate, llr[:1])          # builds the cached code on this thread first
+    n = max(1, min(len(os.sched_getaffinity(0)), 32))
+    parts = np.array_split(np.arange(len(llr)), n)
+    with ThreadPoolExecutor(n) as ex:
+        res = list(ex.map(lambda idx: O.ldpc_decode_batch(rate, llr[idx]), parts))
+    return tuple(np.concatenate([r[i] for r in res]) for i in range(3))
+
+
+@pytest.mark.parametrize("rate", RATES)
+def test_bitexact_large(ctx, rate):
+    """SURVEY test T3 at scale: 36k noisy codewords per rate (easy / waterfall / stress, vectorised generation) --
+    info bytes, ok flag and iteration count identical to the oracle, including the never-converging ones."""
+    from projectultra_b200 import capi
+    dec = capi.LdpcDecoder(ctx, rate)
+    rng = np.random.default_rng(4200 + rate)
+    k = R.RATE_K[rate]
+    cws = np.stack([np.unpackbits(O.ldpc_encode(rate, rng.integers(0, 256, k // 8, dtype=np.uint8)))[:648] for _ in range(32)])
+    per = 12000
+    sig = SIGMAS[rate]
+    seen_fail = seen_ok = 0
+    for sigma in (sig[0], sig[1], sig[3]):
+        bits = cws[rng.integers(0, 32, per)].astype(np.float32)
+        y = (1 - 2 * bits) + sigma * rng.standard_normal((per, 648)).astype(np.float32)
+        llr = np.clip(2 * y / sigma ** 2, -10, 10).astype(np.float32)
+        cpu = oracle_decode_parallel(rate, llr)
+        assert_same(dec.decode_batch(llr), cpu)
+        seen_ok += int(cpu[1].sum())
+        seen_fail += int((cpu[2] == 50).sum())
+    assert seen_ok > 0 and seen_fail > 0
