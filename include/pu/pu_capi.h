@@ -162,6 +162,59 @@ PU_API pu_status pu_ofdm_presynced_debug(pu_ofdm* h, const float* samples, size_
 PU_API pu_status pu_ofdm_tx(const pu_modem_config* cfg, int layout, const uint8_t* data, size_t n_bytes,
                             float* out, size_t out_cap, size_t* out_len);
 
+/* ---------------------------------------------------------------- single-carrier DPSK (externally timed)
+ * Replaces ultra::DPSKDemodulator (src/psk/dpsk.hpp:309-1059) on frames whose data start is known (genie timing, or
+ * the offset DPSKDemodulator::findPreamble returned -- Barker acquisition itself is SURVEY 8f next-2).
+ * POD mirror of ultra::DPSKConfig (dpsk.hpp:42-50); modulation follows enum DPSKModulation (:31-35):
+ * 0 DBPSK, 1 DQPSK, 2 D8PSK.  Pulse shaping (TX only) is on, as in the reference's default. */
+typedef struct {
+    float sample_rate;            /* 48000 */
+    float carrier_freq;           /* 1500 */
+    uint32_t samples_per_symbol;  /* 384 = 125 baud (tools/test_dpsk_snr.cpp:22), default 1536 */
+    uint32_t modulation;
+} pu_dpsk_config;
+typedef struct pu_dpsk pu_dpsk;
+PU_API pu_status pu_dpsk_create(pu_ctx* ctx, const pu_dpsk_config* cfg, pu_dpsk** out);   /* DPSKDemodulator ctor, :311-323 */
+PU_API void pu_dpsk_destroy(pu_dpsk* h);
+PU_API int pu_dpsk_bits_per_symbol(const pu_dpsk* h);
+/* B frames of L samples; data symbols start at sample data_start of every frame.
+ *   ref_mode 0: differential reference (1,0), a fresh / reset() demodulator (:881-886);
+ *   ref_mode 1: setReferenceSymbol on the symbol that ends at data_start (:889-892; what findPreamble does, :470-478);
+ *   est_cfo_hz[B] / phase_offset[B]: the members estimated_cfo_ / initial_phase_offset_ that findPreamble or
+ *   setReferenceWithTraining leave behind and demodulateSoft compensates (:857-865); NULL = 0.
+ * llr_out[b*llr_stride ...] = demodulateSoft() of the frame (:827-879), truncated to llr_stride floats. */
+PU_API pu_status pu_dpsk_demod_soft_batch(pu_dpsk* h, const float* samples, size_t B, size_t L, size_t data_start,
+                                          int ref_mode, const float* est_cfo_hz, const float* phase_offset,
+                                          float* llr_out, size_t llr_stride, pu_memspace space, void* stream);
+/* DPSKModulator (dpsk.hpp:102-307), host: layout 0 = generatePreamble() (Barker-13 x 3) + modulate(data), the frame of
+ * tools/test_dpsk_snr.cpp:47-52; 1 = generateReferenceSymbol() + modulate; 2 = modulate only.  *out_len is always set. */
+PU_API pu_status pu_dpsk_tx(const pu_dpsk_config* cfg, int layout, const uint8_t* data, size_t n_bytes, float* out,
+                            size_t out_cap, size_t* out_len);
+
+/* ---------------------------------------------------------------- multi-carrier DPSK (externally timed)
+ * Replaces ultra::MultiCarrierDPSKDemodulator (src/psk/multi_carrier_dpsk.hpp:258-701) on frames that start at the
+ * training sequence: [training_symbols][1 reference symbol][data symbols] -- what processGotChirp (:533-627) sees
+ * after an external chirp detection.  POD mirror of MultiCarrierDPSKConfig (:26-89). */
+typedef struct {
+    float sample_rate;            /* 48000 */
+    float freq_low, freq_high;    /* 500, 2500 */
+    uint32_t num_carriers;        /* 3..20 */
+    uint32_t samples_per_symbol;  /* 512 */
+    uint32_t bits_per_symbol;     /* 2 DQPSK, 1 DBPSK */
+    uint32_t training_symbols;    /* 8 */
+} pu_mcdpsk_config;
+typedef struct pu_mcdpsk pu_mcdpsk;
+PU_API pu_status pu_mcdpsk_create(pu_ctx* ctx, const pu_mcdpsk_config* cfg, pu_mcdpsk** out);
+PU_API void pu_mcdpsk_destroy(pu_mcdpsk* h);
+/* setReference (:424-435) + demodulateSoft (:437-472) per frame; residual_cfo_hz[B] (may be NULL) receives cfo_hz_
+ * after processTraining (:390-422) so the caller can apply the |cfo| > 5 Hz rejection of :591-598.  The CFO
+ * correction through the 127-tap Hilbert FIR (:633-658) only runs for |cfo| > 0.1 Hz and is not part of this path. */
+PU_API pu_status pu_mcdpsk_demod_soft_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, float* llr_out,
+                                            size_t llr_stride, float* residual_cfo_hz, pu_memspace space, void* stream);
+/* MultiCarrierDPSKModulator (:91-257), host: generateTrainingSequence + generateReferenceSymbol + modulate(data). */
+PU_API pu_status pu_mcdpsk_tx(const pu_mcdpsk_config* cfg, const uint8_t* data, size_t n_bytes, float* out, size_t out_cap,
+                              size_t* out_len);
+
 /* ---------------------------------------------------------------- channel simulator
  * Replaces sim::WattersonChannel (src/sim/hf_channel.hpp:34-299) for batches of frames.  POD mirror of
  * WattersonChannel::Config (:36-65) without the CFO injector fields (out of scope). */

@@ -103,3 +103,15 @@ float orc_channel_noise_std(const float* tx, size_t L, float snr_db, int convent
 #ifdef __cplusplus
 }
 #endif
+
+/* ---- single- and multi-carrier DPSK demodulators (oracle/pu_oracle_psk.c) ---- */
+#ifdef __cplusplus
+extern "C" {
+#endif
+long orc_dpsk_demod_soft(int mod, int sps, float fc, float fs, const float* x, size_t L, long data_start, int ref_mode,
+                         float est_cfo, float phase_off, float* llr, size_t cap);
+long orc_mcdpsk_demod_soft(int nc, int sps, int bits_per_symbol, float f_lo, float f_hi, float fs, const float* x, size_t L,
+                           int training_symbols, float* llr, size_t cap, float* residual_cfo);
+#ifdef __cplusplus
+}
+#endif

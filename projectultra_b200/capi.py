@@ -326,3 +326,136 @@ class OfdmDemodulator:
         return dict(n_sym=nds, carriers=self.carrier_bins(), llr=llr[: self.n_llr(L, training)],
                     bins=cplx(r[:, : 2 * nu]), h=cplx(r[:, 2 * nu: 4 * nu]), eq=cplx(r[:, 4 * nu: 4 * nu + 2 * nd]),
                     nv=r[:, 4 * nu + 2 * nd: 4 * nu + 3 * nd].copy(), scalars=r[:, 4 * nu + 3 * nd:].copy())
+
+
+# ------------------------------------------------------------------------------------------------ DPSK waveforms
+class DpskConfig(C.Structure):
+    """pu_dpsk_config: POD mirror of ultra::DPSKConfig (src/psk/dpsk.hpp:42-50).  modulation 0 DBPSK, 1 DQPSK, 2 D8PSK."""
+    _fields_ = [("sample_rate", C.c_float), ("carrier_freq", C.c_float), ("samples_per_symbol", C.c_uint32),
+                ("modulation", C.c_uint32)]
+
+
+class McDpskConfig(C.Structure):
+    """pu_mcdpsk_config: POD mirror of ultra::MultiCarrierDPSKConfig (src/psk/multi_carrier_dpsk.hpp:26-89)."""
+    _fields_ = [("sample_rate", C.c_float), ("freq_low", C.c_float), ("freq_high", C.c_float), ("num_carriers", C.c_uint32),
+                ("samples_per_symbol", C.c_uint32), ("bits_per_symbol", C.c_uint32), ("training_symbols", C.c_uint32)]
+
+
+def dpsk_config(mod=1, sps=384, fc=1500.0, fs=48000.0):
+    return DpskConfig(fs, fc, sps, mod)
+
+
+def mcdpsk_config(nc=8, bits=2, sps=512, f_lo=500.0, f_hi=2500.0, fs=48000.0, training=8):
+    return McDpskConfig(fs, f_lo, f_hi, nc, sps, bits, training)
+
+
+def _tx_call(fn, *args):
+    n = C.c_size_t(0)
+    fn(*args, None, C.c_size_t(0), C.byref(n))
+    out = np.zeros(n.value, np.float32)
+    check(fn(*args, _ptr(out), C.c_size_t(len(out)), C.byref(n)))
+    return out
+
+
+def dpsk_tx(cfg, data, layout=0):
+    """pu_dpsk_tx: DPSKModulator on the host (layout 0 Barker preamble + data, 1 reference symbol + data, 2 data only)."""
+    d = np.ascontiguousarray(data, dtype=np.uint8)
+    return _tx_call(lib().pu_dpsk_tx, C.byref(cfg), int(layout), _ptr(d), C.c_size_t(len(d)))
+
+
+def mcdpsk_tx(cfg, data):
+    """pu_mcdpsk_tx: training sequence + reference symbol + data (MultiCarrierDPSKModulator, host)."""
+    d = np.ascontiguousarray(data, dtype=np.uint8)
+    return _tx_call(lib().pu_mcdpsk_tx, C.byref(cfg), _ptr(d), C.c_size_t(len(d)))
+
+
+def _frames(samples):
+    if _is_torch(samples):
+        import torch
+        assert samples.dtype == torch.float32 and samples.dim() == 2 and samples.is_contiguous()
+        return samples
+    s = np.ascontiguousarray(samples, dtype=np.float32)
+    return s.reshape(1, -1) if s.ndim == 1 else s
+
+
+def _like(samples, shape, dtype_np, dtype_torch_name):
+    if _is_torch(samples):
+        import torch
+        return torch.zeros(shape, dtype=getattr(torch, dtype_torch_name), device=samples.device)
+    return np.zeros(shape, dtype_np)
+
+
+class DpskDemodulator:
+    """pu_dpsk: batched drop-in for ultra::DPSKDemodulator::demodulateSoft with external timing."""
+
+    def __init__(self, ctx, cfg):
+        self.ctx, self.cfg = ctx, cfg
+        self._h = C.c_void_p()
+        check(lib().pu_dpsk_create(ctx._h, C.byref(cfg), C.byref(self._h)))
+        self.bits_per_symbol = lib().pu_dpsk_bits_per_symbol(self._h)
+
+    def close(self):
+        if self._h:
+            lib().pu_dpsk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def n_llr(self, L, data_start):
+        return max(0, (L - data_start) // self.cfg.samples_per_symbol) * self.bits_per_symbol
+
+    def demod_soft_batch(self, samples, data_start, ref_mode=1, est_cfo=None, phase_off=None, llr_stride=None, llr=None):
+        x = _frames(samples)
+        B, L = x.shape
+        if llr_stride is None:
+            llr_stride = max(self.n_llr(L, data_start), 1) if llr is None else llr.shape[1]
+        if llr is None:
+            llr = _like(x, (B, llr_stride), np.float32, "float32")
+        if not _is_torch(x):
+            est_cfo = None if est_cfo is None else np.ascontiguousarray(est_cfo, dtype=np.float32)
+            phase_off = None if phase_off is None else np.ascontiguousarray(phase_off, dtype=np.float32)
+        sp = _space(x, llr, est_cfo, phase_off)
+        check(lib().pu_dpsk_demod_soft_batch(self._h, _ptr(x), C.c_size_t(B), C.c_size_t(L), C.c_size_t(data_start), int(ref_mode),
+                                             _ptr(est_cfo), _ptr(phase_off), _ptr(llr), C.c_size_t(llr_stride), sp, _stream(sp)))
+        return llr
+
+
+class McDpskDemodulator:
+    """pu_mcdpsk: batched drop-in for ultra::MultiCarrierDPSKDemodulator (setReference + demodulateSoft, external timing)."""
+
+    def __init__(self, ctx, cfg):
+        self.ctx, self.cfg = ctx, cfg
+        self._h = C.c_void_p()
+        check(lib().pu_mcdpsk_create(ctx._h, C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().pu_mcdpsk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def n_llr(self, L):
+        c = self.cfg
+        return max(0, L // c.samples_per_symbol - c.training_symbols - 1) * c.num_carriers * c.bits_per_symbol
+
+    def demod_soft_batch(self, samples, llr_stride=None, llr=None, want_cfo=True):
+        x = _frames(samples)
+        B, L = x.shape
+        if llr_stride is None:
+            llr_stride = max(self.n_llr(L), 1) if llr is None else llr.shape[1]
+        if llr is None:
+            llr = _like(x, (B, llr_stride), np.float32, "float32")
+        cfo = _like(x, (B,), np.float32, "float32") if want_cfo else None
+        sp = _space(x, llr, cfo)
+        check(lib().pu_mcdpsk_demod_soft_batch(self._h, _ptr(x), C.c_size_t(B), C.c_size_t(L), _ptr(llr), C.c_size_t(llr_stride),
+                                               _ptr(cfo), sp, _stream(sp)))
+        return llr, cfo

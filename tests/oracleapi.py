@@ -230,3 +230,27 @@ def time_ldpc_decode(rate, llr, max_iter=-1):
     t = lib().orc_time_ldpc_decode(rate, max_iter, _p(x, C.c_float), C.c_size_t(B), _p(out, C.c_uint8),
                                    C.c_size_t(kb), _p(ok, C.c_uint8), _p(it, C.c_int32))
     return t, out, ok, it
+
+
+# ---------------------------------------------------------------- DPSK (oracle/pu_oracle_psk.c)
+def dpsk_demod_soft(mod, sps, samples, data_start, ref_mode=0, est_cfo=0.0, phase_off=0.0, fc=1500.0, fs=48000.0):
+    x = _f32(samples)
+    out = np.zeros(4096, np.float32)
+    L = lib()
+    L.orc_dpsk_demod_soft.restype = C.c_long
+    n = L.orc_dpsk_demod_soft(mod, sps, C.c_float(fc), C.c_float(fs), _p(x, C.c_float), C.c_size_t(len(x)), C.c_long(data_start),
+                              ref_mode, C.c_float(est_cfo), C.c_float(phase_off), _p(out, C.c_float), C.c_size_t(len(out)))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy()
+
+
+def mcdpsk_demod_soft(nc, samples, sps=512, bits=2, f_lo=500.0, f_hi=2500.0, fs=48000.0, training=8):
+    x = _f32(samples)
+    out = np.zeros(8192, np.float32)
+    cfo = C.c_float(0)
+    L = lib()
+    L.orc_mcdpsk_demod_soft.restype = C.c_long
+    n = L.orc_mcdpsk_demod_soft(nc, sps, bits, C.c_float(f_lo), C.c_float(f_hi), C.c_float(fs), _p(x, C.c_float), C.c_size_t(len(x)),
+                                training, _p(out, C.c_float), C.c_size_t(len(out)), C.byref(cfo))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), cfo.value
