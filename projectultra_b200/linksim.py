@@ -115,11 +115,16 @@ def wilson_interval(errors, n, z=1.96):
 class LinkSim:
     """One waveform mode x code rate x channel: owns the TX pool and runs sharded SNR sweeps on one GPU.
 
+    cfg selects the waveform: capi.ModemConfig (OFDM, presynced frame = 2 LTS + data, tools/test_ofdm_chirp_pilots.cpp:
+    183-191), capi.DpskConfig (single-carrier DPSK, Barker preamble + data, tools/test_dpsk_snr.cpp:47-52, genie data
+    start) or capi.McDpskConfig (multi-carrier DPSK, training + reference + data, tools/test_mc_dpsk.cpp:180-196).
+    peak=0.5 applies the tools' peak normalisation (tools/test_mode_snr.cpp:54-56).
+
     Frames are identified by (snr index, trial index); frame -> (tx waveform, seed) is a pure function, so any
     frame can be regenerated, and ranks take disjoint trial ranges with no data exchange."""
 
     def __init__(self, ctx, cfg, channel="awgn", payload_bytes=40, pool=64, snr_convention=None, pool_seed=12345,
-                 max_iter=50, device=None):
+                 max_iter=50, device=None, code_rate=None, peak=None):
         import torch
         self.ctx, self.cfg = ctx, cfg
         self.device = device or torch.device("cuda", ctx.device)
@@ -127,12 +132,32 @@ class LinkSim:
         self.channel_name = channel if isinstance(channel, str) else "custom"
         # AWGN tools define SNR on mean frame power, WattersonChannel on input rms (same number, different rounding)
         self.snr_convention = (1 if self.channel_name == "awgn" else 0) if snr_convention is None else snr_convention
-        self.ofdm = capi.OfdmDemodulator(ctx, cfg)
-        self.ldpc = capi.LdpcDecoder(ctx, cfg.code_rate, max_iter)
+        if isinstance(cfg, capi.ModemConfig):
+            self.kind = "ofdm"
+            rate = cfg.code_rate if code_rate is None else code_rate
+            self.ofdm = self.demod = capi.OfdmDemodulator(ctx, cfg)
+            build = lambda coded: ofdm_tx(cfg, coded, 0)
+        elif isinstance(cfg, capi.DpskConfig):
+            self.kind = "dpsk"
+            rate = capi.R1_4 if code_rate is None else code_rate          # tools/test_dpsk_snr.cpp:28-29
+            self.demod = capi.DpskDemodulator(ctx, cfg)
+            self.data_start = 39 * cfg.samples_per_symbol                 # Barker-13 x 3 (dpsk.hpp:202-204)
+            build = lambda coded: capi.dpsk_tx(cfg, coded, 0)
+        elif isinstance(cfg, capi.McDpskConfig):
+            self.kind = "mcdpsk"
+            rate = capi.R1_2 if code_rate is None else code_rate
+            self.demod = capi.McDpskDemodulator(ctx, cfg)
+            build = lambda coded: capi.mcdpsk_tx(cfg, coded)
+        else:
+            raise TypeError("cfg must be a capi.ModemConfig, capi.DpskConfig or capi.McDpskConfig")
+        self.code_rate = rate
+        self.ldpc = capi.LdpcDecoder(ctx, rate, max_iter)
         self.payload_bytes = payload_bytes
         rng = np.random.default_rng(pool_seed)
         self.payloads = rng.integers(0, 256, (pool, payload_bytes), dtype=np.uint8)
-        waves = [ofdm_tx(cfg, capi.ldpc_encode(cfg.code_rate, p), 0) for p in self.payloads]
+        waves = [build(capi.ldpc_encode(rate, p)) for p in self.payloads]
+        if peak is not None:
+            waves = [(w * (np.float32(peak) / np.abs(w).max())).astype(np.float32) for w in waves]
         self.L = len(waves[0])
         self.tx_host = np.stack(waves)
         self.tx_pool = torch.from_numpy(self.tx_host).to(self.device)
@@ -141,6 +166,14 @@ class LinkSim:
         pad[:, :payload_bytes] = self.payloads
         self.payload_pool = torch.from_numpy(pad).to(self.device)
         self.pool = pool
+
+    def demod_llr(self, rx, llr=None):
+        """First 648 soft bits of every frame (device tensors), as the tools consume them."""
+        if self.kind == "ofdm":
+            return self.demod.presynced_batch(rx, 2, llr_stride=648, llr=llr, want_aux=False)[0]
+        if self.kind == "dpsk":
+            return self.demod.demod_soft_batch(rx, self.data_start, 1, llr_stride=648, llr=llr)
+        return self.demod.demod_soft_batch(rx, llr_stride=648, llr=llr, want_cfo=False)[0]
 
     def noise_std_table(self, snr_points):
         return np.array([[channel_noise_std(self.tx_host[i], s, self.snr_convention) for i in range(self.pool)]
@@ -167,7 +200,10 @@ class LinkSim:
     def run_batch(self, batch, counters, rx=None, keep=False):
         """channel -> demod -> LDPC -> counters for one prepared batch (all on the current stream)."""
         rx = channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rx)
-        info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
+        if self.kind == "ofdm":
+            info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
+        else:
+            info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))
         count_errors(self.ctx, info, ok, iters, self.payload_pool, batch["tx_index"], batch["bins"], self.payload_bytes,
                      counters)
         return (rx, info, ok, iters) if keep else None

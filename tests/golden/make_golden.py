@@ -131,11 +131,44 @@ def misc_vectors():
     np.savez_compressed(os.path.join(HERE, "misc_golden.npz"), **out)
 
 
+def psk_vectors():
+    """Short single- and multi-carrier DPSK frames (kept small: noise does not compress)."""
+    out = {}
+    for mod in (0, 1, 2):
+        rng = np.random.default_rng(5000 + mod)
+        sps = 192
+        data = rng.integers(0, 256, 6, dtype=np.uint8)
+        tx = R.dpsk_tx(mod, sps, data, 0)
+        tx = (tx * np.float32(0.5 / np.abs(tx).max())).astype(np.float32)
+        rx = awgn(tx, 4.0 + 3 * mod, rng)
+        rx = rx[30 * sps:]                      # keep 9 preamble symbols + data
+        start = 9 * sps
+        out[f"sc{mod}_data"] = data
+        out[f"sc{mod}_rx"] = rx
+        out[f"sc{mod}_llr_ref1"] = R.dpsk_demod_soft_ex(mod, sps, rx, start, 1)
+        out[f"sc{mod}_llr_ref0"] = R.dpsk_demod_soft_ex(mod, sps, rx, start, 0)
+        out[f"sc{mod}_llr_comp"] = R.dpsk_demod_soft_ex(mod, sps, rx, start, 1, 7.25, -0.6)
+        out[f"sc{mod}_tx_head"] = R.dpsk_tx(mod, sps, data, 0)[: 41 * sps]
+    for nc, bits in ((8, 2), (3, 2), (5, 1)):
+        rng = np.random.default_rng(6000 + nc)
+        data = rng.integers(0, 256, 12, dtype=np.uint8)
+        tx = R.mcdpsk_tx(nc, data, bits=bits)
+        rx = awgn(tx, 5.0, rng)
+        llr, cfo = R.mcdpsk_demod_soft(nc, rx, bits=bits)
+        out[f"mc{nc}_data"] = data
+        out[f"mc{nc}_rx"] = rx
+        out[f"mc{nc}_llr"] = llr
+        out[f"mc{nc}_cfo"] = np.array([cfo], np.float32)
+        out[f"mc{nc}_tx"] = tx
+    np.savez_compressed(os.path.join(HERE, "psk_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
     ldpc_vectors()
     ofdm_vectors()
     misc_vectors()
+    psk_vectors()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
