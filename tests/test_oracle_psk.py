@@ -56,3 +56,30 @@ def test_mc_dpsk_vs_reference(nc, bits):
         assert np.float32(gcfo) == np.float32(wcfo)
     z = np.zeros(12 * 512 + 100, np.float32)
     assert same_bits(O.mcdpsk_demod_soft(nc, z, bits=bits)[0], R.mcdpsk_demod_soft(nc, z, bits=bits)[0])
+
+
+@pytest.mark.parametrize("mod", [0, 1, 2])
+def test_sc_dpsk_golden(golden, mod):
+    g = golden["psk"]
+    rx, sps = g[f"sc{mod}_rx"], 192
+    assert same_bits(O.dpsk_demod_soft(mod, sps, rx, 9 * sps, 1), g[f"sc{mod}_llr_ref1"])
+    assert same_bits(O.dpsk_demod_soft(mod, sps, rx, 9 * sps, 0), g[f"sc{mod}_llr_ref0"])
+    assert same_bits(O.dpsk_demod_soft(mod, sps, rx, 9 * sps, 1, 7.25, -0.6), g[f"sc{mod}_llr_comp"])
+
+
+@pytest.mark.parametrize("nc,bits", [(8, 2), (3, 2), (5, 1)])
+def test_mc_dpsk_golden(golden, nc, bits):
+    g = golden["psk"]
+    llr, cfo = O.mcdpsk_demod_soft(nc, g[f"mc{nc}_rx"], bits=bits)
+    assert same_bits(llr, g[f"mc{nc}_llr"]) and np.float32(cfo) == g[f"mc{nc}_cfo"][0]
+
+
+def test_psk_tx_golden(golden):
+    from projectultra_b200 import build, capi
+    build.build()
+    g = golden["psk"]
+    for mod in (0, 1, 2):
+        tx = capi.dpsk_tx(capi.dpsk_config(mod, 192), g[f"sc{mod}_data"], 0)
+        assert same_bits(tx[: 41 * 192], g[f"sc{mod}_tx_head"])
+    for nc, bits in ((8, 2), (3, 2), (5, 1)):
+        assert same_bits(capi.mcdpsk_tx(capi.mcdpsk_config(nc, bits), g[f"mc{nc}_data"]), g[f"mc{nc}_tx"])

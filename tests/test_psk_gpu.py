@@ -116,3 +116,19 @@ def test_mc_dpsk_llrs_bit_identical(ctx, nc, bits):
     llr, _ = dem.demod_soft_batch(noisy(tx, 15.0, rng)[None, :], llr_stride=648)
     info, ok, it = dec.decode_batch(llr)
     assert ok[0] == 1 and (info[0, :40] == payload).all()
+
+
+def test_golden_frames(ctx, golden):
+    from projectultra_b200 import capi
+    g = golden["psk"]
+    for mod in (0, 1, 2):
+        dem = capi.DpskDemodulator(ctx, capi.dpsk_config(mod, 192))
+        rx = g[f"sc{mod}_rx"]
+        assert same_bits(dem.demod_soft_batch(rx, 9 * 192, 1)[0], g[f"sc{mod}_llr_ref1"])
+        assert same_bits(dem.demod_soft_batch(rx, 9 * 192, 0)[0], g[f"sc{mod}_llr_ref0"])
+        comp = dem.demod_soft_batch(rx, 9 * 192, 1, np.array([7.25], np.float32), np.array([-0.6], np.float32))[0]
+        assert same_bits(comp, g[f"sc{mod}_llr_comp"])
+    for nc, bits in ((8, 2), (3, 2), (5, 1)):
+        dem = capi.McDpskDemodulator(ctx, capi.mcdpsk_config(nc, bits))
+        llr, cfo = dem.demod_soft_batch(g[f"mc{nc}_rx"])
+        assert same_bits(llr[0], g[f"mc{nc}_llr"]) and cfo[0] == g[f"mc{nc}_cfo"][0]
