@@ -183,33 +183,50 @@ __device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* 
     const float vp = __fsub_rn(ptot, pc);             // its v2c before the clamp (:219-222)
     unsigned px = __float_as_uint(ptot);              // XOR of the totals' sign bits = parity of the hard decisions
     unsigned sx = __float_as_uint(vp);                // XOR of the messages' sign bits
-    const float ap = fminf(fabsf(vp), lim);
-    float m1 = ap, m2 = FLT_MAX;
-    float v[NE > 0 ? NE : 1], a[NE > 0 ? NE : 1];
+    // x[0] = parity edge, x[1..NE] = info edges: |clamp(v2c)|
+    float v[NE + 1], x[NE + 1];
+    v[0] = vp;
+    x[0] = fminf(fabsf(vp), lim);
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         const float te = tot[rd[e]];
         px ^= __float_as_uint(te);
-        v[e] = __fsub_rn(te, prev[e]);
-        sx ^= __float_as_uint(v[e]);
-        a[e] = fminf(fabsf(v[e]), lim);
-        m2 = fminf(m2, fmaxf(m1, a[e]));
-        m1 = fminf(m1, a[e]);
+        v[e + 1] = __fsub_rn(te, prev[e]);
+        sx ^= __float_as_uint(v[e + 1]);
+        x[e + 1] = fminf(fabsf(v[e + 1]), lim);
     }
     syn_bits = px;
     if (!last) {
-        const unsigned sgn = sx & 0x80000000u;
-        const unsigned s1 = __float_as_uint(__fmul_rn(m1, 0.75f)) ^ sgn;   // (:200), pre-multiplied by the row's sign
-        const unsigned s2 = __float_as_uint(__fmul_rn(m2, 0.75f)) ^ sgn;
+        // minimum over the OTHER edges of the row (:185-197) from prefix and suffix minima: 3(n-2) min operations for
+        // n edges, exact (a minimum does not depend on the order it is taken in)
+        float oth[NE + 1];
+        if (NE == 0) {
+            oth[0] = FLT_MAX;
+        } else {
+            float pre[NE + 1], suf[NE + 1];
+            pre[0] = x[0];
+#pragma unroll
+            for (int i = 1; i < NE; ++i) pre[i] = fminf(pre[i - 1], x[i]);
+            suf[NE] = x[NE];
+#pragma unroll
+            for (int i = NE - 1; i >= 1; --i) suf[i] = fminf(suf[i + 1], x[i]);
+            oth[0] = suf[1];
+            oth[NE] = pre[NE - 1];
+#pragma unroll
+            for (int i = 1; i < NE; ++i) oth[i] = fminf(pre[i - 1], suf[i + 1]);
+        }
+        // sign * min_abs * 0.75f (:200): the row's sign product is folded into the constant, the edge's own sign is
+        // XOR-ed back in (excluding an edge from a product of +-1 is the same as multiplying by it again)
+        const float k = __uint_as_float(0x3f400000u | (sx & 0x80000000u));   // +-0.75
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-            const unsigned mag = (a[e] == m1) ? s2 : s1;
-            const float out = __uint_as_float(mag ^ (__float_as_uint(v[e]) & 0x80000000u));
+            const float m = __fmul_rn(oth[e + 1], k);
+            const float out = __uint_as_float(__float_as_uint(m) ^ (__float_as_uint(v[e + 1]) & 0x80000000u));
             prev[e] = out;
             msg[wr[e]] = out;
         }
-        const unsigned mag = (ap == m1) ? s2 : s1;
-        pc = __uint_as_float(mag ^ (__float_as_uint(vp) & 0x80000000u));
+        const float m = __fmul_rn(oth[0], k);
+        pc = __uint_as_float(__float_as_uint(m) ^ (__float_as_uint(vp) & 0x80000000u));
     }
 }
 
@@ -217,8 +234,8 @@ __device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* 
 // slot a; tot[a] = its total.  The variable pass reads msg[d * kpad + a] with a = thread index: conflict-free by
 // construction.  The check pass gathers tot[a] and scatters msg[rank * kpad + a]; both hit bank a mod 32, and the
 // layout (ldpc_code.cpp: make_ldpc_layout) makes the 32 lanes of a warp use 32 different banks on every edge.
-template <int VR, int DV>
-__global__ void __launch_bounds__(512) ldpc_flood_reg_kernel(LdpcRegDev t, const float* __restrict__ llr, size_t llr_stride,
+template <int VR, int DV, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) ldpc_flood_reg_kernel(LdpcRegDev t, const float* __restrict__ llr, size_t llr_stride,
                                                              uint8_t* __restrict__ info, size_t info_stride,
                                                              uint8_t* __restrict__ ok, int32_t* __restrict__ iters, int max_iter) {
     extern __shared__ float smem[];
@@ -388,20 +405,20 @@ static pu_status launch_decode(pu_ldpc* h, const float* d_llr, size_t llr_stride
     const size_t kMaxGrid = 1u << 30;
     for (size_t off = 0; off < B; off += kMaxGrid) {
         const size_t nb = std::min(kMaxGrid, B - off);
-#define PU_LDPC_REG_CASE(VR, DV)                                                                                   \
-    if (!done && h->reg_vr <= (VR) && h->reg_dv == (DV)) {                                                        \
-        pu::ldpc_flood_reg_kernel<VR, DV><<<static_cast<unsigned>(nb), h->reg_threads, h->reg_smem, st>>>(        \
+#define PU_LDPC_REG_CASE(VR, DV, MAXT, MINB)                                                                       \
+    if (!done && h->reg_vr <= (VR) && h->reg_dv == (DV) && h->reg_threads <= (MAXT)) {                            \
+        pu::ldpc_flood_reg_kernel<VR, DV, MAXT, MINB><<<static_cast<unsigned>(nb), h->reg_threads, h->reg_smem, st>>>( \
             h->reg, d_llr + off * llr_stride, llr_stride, d_info + off * info_stride, info_stride,                \
             d_ok ? d_ok + off : nullptr, d_iters ? d_iters + off : nullptr, h->max_iter);                         \
         done = true;                                                                                              \
     }
         bool done = false;
         if (h->reg_threads <= 512) {
-            PU_LDPC_REG_CASE(1, 5)    // R1/2
-            PU_LDPC_REG_CASE(2, 3)    // R2/3
-            PU_LDPC_REG_CASE(3, 3)    // R3/4
-            PU_LDPC_REG_CASE(5, 3)    // R5/6
-            PU_LDPC_REG_CASE(1, 13)   // R1/4
+            PU_LDPC_REG_CASE(1, 5, 352, 3)     // R1/2: 324 checks, 3 CTAs of 11 warps per SM
+            PU_LDPC_REG_CASE(2, 3, 224, 4)     // R2/3: 216 checks
+            PU_LDPC_REG_CASE(3, 3, 192, 5)     // R3/4: 162 checks
+            PU_LDPC_REG_CASE(5, 3, 128, 6)     // R5/6: 108 checks
+            PU_LDPC_REG_CASE(1, 13, 512, 2)    // R1/4: 486 checks
         }
 #undef PU_LDPC_REG_CASE
         if (!done)
