@@ -257,6 +257,13 @@ class OfdmDemodulator:
         except Exception:
             pass
 
+    KERNELS = {0: "none", 1: "ofdm_presynced_kernel", 2: "ofdm_diff_kernel", 3: "ofdm_diff512_kernel"}
+
+    @property
+    def last_kernel(self):
+        """Name of the kernel the last launch on this handle used (pu_ofdm_last_kernel)."""
+        return self.KERNELS[lib().pu_ofdm_last_kernel(self._h)]
+
     def carrier_bins(self):
         buf = (C.c_int32 * 128)()
         n = lib().pu_ofdm_carrier_bins(self._h, buf, 128)

@@ -219,7 +219,17 @@ def test_warp_fft_kernel_is_bit_identical(ctx, preset, mod):
         n = dem.n_llr(Lcut, training)
         stride = max(n, 4)
         fast, fsnr, fcfo = dem.presynced_batch(x, training, llr_stride=stride)
+        fast_kernel = dem.last_kernel
         gen, gsnr, gcfo = dem.presynced_batch(x, training, zeros, zeros, llr_stride=stride)
+        assert dem.last_kernel == "ofdm_presynced_kernel"
+        if training != 2:
+            assert fast_kernel in ("ofdm_diff512_kernel", "ofdm_diff_kernel", "ofdm_presynced_kernel")
+        elif preset == "m1" and mod != R.DBPSK and Lcut % 4 == 0:
+            # 512-FFT frames with 16-byte aligned rows take the persistent TMA-staged packed-fp32 kernel (csrc/ofdm_diff512.cu);
+            # M1 DBPSK (25 symbols after the first LTS) does not fit its shared-memory budget and stays on the warp-FFT kernel
+            assert fast_kernel == "ofdm_diff512_kernel", (fast_kernel, training, Lcut)
+        else:
+            assert fast_kernel in ("ofdm_diff_kernel", "ofdm_presynced_kernel"), (fast_kernel, training, Lcut)
         assert same_bits(fast, gen), (training, Lcut)
         assert same_bits(fsnr, gsnr) and same_bits(fcfo, gcfo)
         if n and training == 2:

@@ -6,21 +6,26 @@ import csv, re, subprocess, sys
 from collections import defaultdict
 sass_csv, cubin, kname = sys.argv[1:4]
 minp = float(sys.argv[4]) if len(sys.argv) > 4 else 0.7
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+dis = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
 lines, cur, infn, off = [], None, False, 0
+chain, fresh = [], True
 for ln in dis.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
     if m:
         infn = kname in m.group(1); continue
     if not infn: continue
-    m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
+    m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
-        inl = re.search(r'inlined at "([^"]+)", line (\d+)', m.group(3))
-        cur = (m.group(1).split("/")[-1], int(m.group(2)), (inl.group(1).split("/")[-1], int(inl.group(2))) if inl else None)
+        # nvdisasm -gi prints the inline chain innermost first, outermost (the line in the kernel body) last
+        loc = (m.group(1).split("/")[-1], int(m.group(2)))
+        if fresh: chain, fresh = [], False
+        chain.append(loc)
+        cur = (chain[0][0], chain[0][1], chain[-1] if len(chain) > 1 else None)
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m:
         lines.append((int(m.group(1), 16), cur, m.group(2)))
+        fresh = True
 rows = list(csv.reader(open(sass_csv)))
 hdr = rows[1]
 iS, iI = hdr.index("# Samples"), hdr.index("Instructions Executed")
