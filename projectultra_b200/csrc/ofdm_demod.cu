@@ -612,7 +612,7 @@ cudaError_t ofdm_diff_launch(const OfdmDev& d, const float2* host_twiddle, const
                              int n_symbols, int training, float* llr, size_t llr_stride, int llr_limit, float* snr_db,
                              float* final_cfo, cudaStream_t st);
 // ofdm_diff512.cu
-bool ofdm_diff512_supported(const OfdmDev& d, int n_symbols, int training, const float* samples, size_t frame_stride);
+bool ofdm_diff512_supported(const OfdmDev& d, int n_symbols, int training, const float* samples, size_t frame_stride, size_t B);
 cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, const float* samples, size_t B, size_t frame_stride,
                                 int n_symbols, int training, float* llr, size_t llr_stride, int llr_limit, float* snr_db,
                                 float* final_cfo, int sm_count, cudaStream_t st);
@@ -636,7 +636,7 @@ struct pu_ofdm {
     int device = 0;   // copy of ctx->device: the handle may outlive its context
     pu::OfdmPlan plan;
     pu::OfdmDev dev{};
-    pu::DevMem d_tw, d_nco, d_nco2, d_dbin, d_pbin, d_zc, d_psign, d_ilo, d_ihi, d_ia, d_perm;
+    pu::DevMem d_tw, d_nco, d_dbin, d_pbin, d_zc, d_psign, d_ilo, d_ihi, d_ia, d_perm;
     int max_symbols = 0;
     int last_kernel = 0;
     size_t smem_bytes = 0;
@@ -649,21 +649,6 @@ struct pu_ofdm {
         if (s != PU_OK) return s;
         dev.nco = static_cast<const float2*>(d_nco.p);
         dev.nco_len = want * plan.sym_len;
-        dev.nco2 = nullptr;
-        if (plan.nfft == 512) {   // symbol-pair table of the packed kernel (ofdm_diff512.cu)
-            std::vector<float4> t2(static_cast<size_t>(want) * 512);
-            auto brev = [](unsigned v, int bits) { unsigned r = 0; for (int b = 0; b < bits; ++b) r |= ((v >> b) & 1u) << (bits - 1 - b); return r; };
-            for (int sy = 0; sy < want; ++sy)
-                for (unsigned q = 0; q < 16; ++q)
-                    for (unsigned l = 0; l < 32; ++l) {   // entry [q][lane] belongs to sample brev5(lane) + 32 brev4(q): the lane-linear order of pass A
-                        const size_t n = brev(l, 5) + 32 * brev(q, 4);
-                        const pu::cfloat a = t[static_cast<size_t>(sy) * plan.sym_len + plan.cp + n];
-                        const pu::cfloat b = t[static_cast<size_t>(sy + 1) * plan.sym_len + plan.cp + n];
-                        t2[static_cast<size_t>(sy) * 512 + q * 32 + l] = make_float4(a.real(), b.real(), -a.imag(), -b.imag());
-                    }
-            if ((s = d_nco2.upload(t2.data(), t2.size())) != PU_OK) return s;
-            dev.nco2 = static_cast<const float4*>(d_nco2.p);
-        }
         max_symbols = want;
         return PU_OK;
     }
@@ -709,7 +694,6 @@ pu_status pu_ofdm_create(pu_ctx* ctx, const pu_modem_config* cfg, pu_ofdm** out)
     d.interp_lo = static_cast<const int*>(h->d_ilo.p);
     d.interp_hi = static_cast<const int*>(h->d_ihi.p);
     d.interp_alpha = static_cast<const float*>(h->d_ia.p);
-    d.nco2 = nullptr;
     d.llr_perm = nullptr;
     d.perm_len = 0;
     h->smem_bytes = sizeof(float2) * (p.nfft + p.nfft / 8) + sizeof(float) * ((p.sym_len + 3) & ~3) + sizeof(pu::RxShared);
@@ -770,7 +754,7 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
     (void)cudaGetLastError();
     static const bool no_p512 = getenv("PU_OFDM_NO_PACKED512") != nullptr;   // A/B switch for tests and profiling
     if (!d_cfo && !d_phase && !d_dbg && !no_p512 && pu::ofdm_diff_supported(h->dev, n_symbols, training) &&
-        pu::ofdm_diff512_supported(h->dev, n_symbols, training, d_samples, L)) {
+        pu::ofdm_diff512_supported(h->dev, n_symbols, training, d_samples, L, B)) {
         // 512-FFT differential no-pilot mode: persistent TMA-staged packed-fp32 kernel (ofdm_diff512.cu)
         const cudaError_t e = pu::ofdm_diff512_launch(h->dev, reinterpret_cast<const float2*>(p.twiddle.data()), d_samples, B, L, n_symbols,
                                                       training, d_llr, llr_stride, limit, d_snr, d_fcfo, h->ctx->sm_count, st);

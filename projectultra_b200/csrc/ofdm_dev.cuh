@@ -26,7 +26,6 @@ struct OfdmDev {
     const float* interp_alpha;
     const int* llr_perm;     // optional [perm_len]: output position of LLR index i (fused deinterleave), or NULL
     int perm_len;
-    const float4* nco2;      // 512-FFT only, [max_symbols][16][32]: (cos_s, cos_s+1, -sin_s, -sin_s+1) of sample cp + brev5(lane) + 32 brev4(q) (ofdm_diff512.cu)
 };
 
 // ---- std::complex<float> arithmetic as GCC lowers it (no FMA, naive formulas) ----

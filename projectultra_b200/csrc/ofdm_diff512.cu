@@ -7,21 +7,29 @@
 // src/ofdm/soft_demap.hpp:173-237); every butterfly is still the reference's unfused (t = w*b, a+t, a-t) in the
 // reference's stage order, so bins / H / equalised symbols / LLRs stay bit-identical.  What changes is the machine
 // mapping, chosen from the r03 profile (ofdm_diff_kernel: 78 % issue-slot utilisation, 56 % of all instructions are
-// scalar FMUL/FADD of the butterflies, 28 % of stall samples wait on the first LDG of a symbol):
-//   * TWO SYMBOLS PER WARP, PACKED: each 64-bit register pair holds the same quantity of symbols s and s+1, and the
-//     butterflies are issued as sm_100 packed-fp32 instructions (FFMA2 / FADD2: two IEEE-rn fp32 operations per
-//     issue slot; same FP-pipe throughput as scalar, half the issue slots).  ptxas contracts `mul.rn.f32x2` +
-//     `add.rn.f32x2` into one FFMA2 even with --fmad=false (measured: tools/ubench/f32x2_bench.cu), which would
-//     break bit-exactness, so every product is written as fma(a, b, Z) with Z = (-0, -0) passed as a KERNEL ARGUMENT:
-//     a*b + (-0) is exactly RN(a*b) including the sign of a zero product, and ptxas cannot fold an unknown addend.
+// scalar FMUL/FADD of the butterflies, 28 % of stall samples wait on the first LDG of a symbol) and from the first
+// packed kernel (pairs of symbols of one frame per warp: half the instructions, but two CTA-wide barriers per frame
+// and a few-thread exact-demapper tail left the SM idle 75 % of the time):
+//   * A WARP OWNS TWO FRAMES and walks their symbols in order.  Each 64-bit register pair holds the same quantity of
+//     frame f and frame f+1, and the butterflies are issued as sm_100 packed-fp32 instructions (FFMA2 / FADD2: two
+//     IEEE-rn fp32 operations per issue slot).  ptxas contracts `mul.rn.f32x2` + `add.rn.f32x2` into one FFMA2 even
+//     with --fmad=false (measured: tools/ubench/f32x2_bench.cu), which would break bit-exactness, so every product
+//     is written as fma(a, b, Z) with Z = (-0, -0) passed as a KERNEL ARGUMENT: a*b + (-0) is exactly RN(a*b)
+//     including the sign of a zero product, and ptxas cannot fold an unknown addend.
+//   * NOTHING IS SHARED BETWEEN WARPS but the read-only NCO table: the lanes that end the FFT holding a used bin keep
+//     H, 1/nv and the previous equalised symbol of their carrier in registers and equalise + demap right there, so
+//     the kernel has no __syncthreads / named barrier at all after its prologue.
 //   * butterflies whose twiddle is tw[0] = (1, -0) skip the multiplication: (1, -0) * b == b for every finite b up
 //     to the sign of a zero component, and a zero whose sign could differ can only reach a bin when all 512 samples
 //     of the symbol are zero (any other zero is produced by a cancellation x - x = +0 in both evaluations); then the
 //     carrier is below the demapper's weak-signal gate (soft_demap.hpp:178,199,224) and its LLRs are 0 either way.
-//   * PERSISTENT CTAs (2 per SM) loop over frames; the samples of the next frame are staged into shared memory by
-//     cp.async.bulk (TMA, one copy per symbol, mbarrier complete_tx) while the current frame is computed, so no warp
-//     ever waits on HBM latency and sample loads are conflict-free LDS.
-//   * one 128-bit shared-memory transpose per element pair (re_s, re_s1, im_s, im_s1) between the two FFT passes.
+//   * PERSISTENT CTA per SM; every warp runs its own ring of cp.async.bulk (TMA) copies, one symbol of both frames
+//     per stage, mbarrier complete_tx, refilled as soon as pass A has taken the samples into registers: no warp
+//     waits on HBM latency and sample loads are conflict-free LDS.
+//   * the <= 2 % of carriers that fail the saturation filter are queued per warp (equalised symbol, predecessor,
+//     nv, destination) and the exact libm-restatement demapper runs on 32 queued carriers at a time with all lanes
+//     busy, instead of on one or two lanes per symbol.
+//   * one 128-bit shared-memory transpose per element (re_f, re_f1, im_f, im_f1) between the two FFT passes.
 // HBM traffic: every sample of the symbols that are used is read exactly once, LLRs are written once.
 #include <cfloat>
 
@@ -33,14 +41,14 @@ namespace pu {
 
 typedef unsigned long long u64;
 
-constexpr int kP512MaxWarps = 6;        // symbol pairs in flight per CTA (M1 DQPSK: 12 symbols = 6 pairs)
+constexpr int kP512MaxWarps = 12;       // frame pairs in flight per CTA (one warp each)
 constexpr int kP512MaxSym = 40;
 constexpr int kP512Buf = 512 + 32;      // float4 per warp: element p lives at p + (p >> 4)
 constexpr size_t kP512SmemMax = 227 * 1024;
 
 struct P512Tw { u64 re[8], im[8]; };    // pass-A twiddles tw[32 m] as broadcast pairs (w.x, w.x), (w.y, w.y)
 
-struct C2 { u64 re, im; };              // one complex quantity of symbols (s, s+1): re = (re_s, re_s1), im likewise
+struct C2 { u64 re, im; };              // one complex quantity of frames (f, f+1): re = (re_f, re_f1), im likewise
 
 __device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void upk(u64 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
@@ -97,84 +105,101 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-constexpr int kP512Carr = 32;           // data carriers per frame are < 32 (ofdm_diff512_supported)
-constexpr int kP512Groups = 2;          // frames in flight per CTA (each on its own W warps, named barrier and mbarriers)
+constexpr int kP512Queue = 64;          // per-warp queue of carriers waiting for the exact demapper (flushed 32 at a time)
+constexpr int kP512StageFloats = 1024;  // one ring stage: 512 samples (after the cyclic prefix) of frame f, then of frame f+1
 
 struct P512Smem {     // offsets (bytes) into dynamic shared memory, computed identically on host and device
-    size_t nco, tb, grp0, grp_stride;                       // CTA-wide: NCO slices, transpose buffers; then one block per group
-    size_t xs, F, Hs, slow, hp, nv, habs, misc;             // offsets inside a group block
+    size_t nco;                                              // CTA-wide: NCO slices of the processed symbols
+    size_t warp0, warp_stride;                               // then one block per warp:
+    size_t S, T, q_sym, q_prev, q_nv, q_frame, q_item, bars; //   offsets inside a warp block
     size_t total;
 };
-__host__ __device__ inline P512Smem p512_layout(int n_symbols, int first, int sym_len, int nd, int warps) {
+__host__ __device__ inline P512Smem p512_layout(int n_proc, int warps, int stages, bool half) {
     P512Smem L;
     size_t o = 0;
     auto take = [&o](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
-    const int npairs = (n_symbols - first + 1) / 2;
-    L.nco = take(static_cast<size_t>(npairs) * 512 * sizeof(float4));
-    L.tb = take(static_cast<size_t>(kP512Groups) * warps * kP512Buf * sizeof(float4));
-    L.grp0 = o;
+    L.nco = take(static_cast<size_t>(n_proc) * 512 * sizeof(float2));
+    L.warp0 = (o + 127) & ~size_t(127);
     o = 0;
-    L.xs = take(static_cast<size_t>(n_symbols - first) * 512 * sizeof(float));             // samples after the CP only
-    L.F = take(2 * static_cast<size_t>(n_symbols) * nd * sizeof(float2));     // [frame parity][symbol][carrier]
-    L.Hs = take(2 * kP512Carr * sizeof(float2));                               // [frame parity][carrier]
-    L.slow = take(static_cast<size_t>(n_symbols) * nd * sizeof(int));          // items (symbol, carrier) for the exact demapper
-    L.hp = take(2 * kP512Carr * sizeof(float));
-    L.nv = take(2 * kP512Carr * sizeof(float));
-    L.habs = take(2 * kP512Carr * sizeof(float));
-    L.misc = take(64);    // [0] full mbarrier, [8] empty mbarrier, [16] slow_count[2]
-    L.grp_stride = (o + 127) & ~size_t(127);
-    L.total = L.grp0 + kP512Groups * L.grp_stride;
+    L.S = take(static_cast<size_t>(stages) * kP512StageFloats * sizeof(float));
+    L.T = take(kP512Buf * (half ? sizeof(float2) : sizeof(float4)));
+    L.q_sym = take(kP512Queue * sizeof(float2));
+    L.q_prev = take(kP512Queue * sizeof(float2));
+    L.q_nv = take(kP512Queue * sizeof(float));
+    L.q_frame = take(kP512Queue * sizeof(unsigned));
+    L.q_item = take(kP512Queue * sizeof(int));
+    L.bars = take(static_cast<size_t>(stages) * sizeof(u64));
+    L.warp_stride = (o + 127) & ~size_t(127);
+    L.total = L.warp0 + static_cast<size_t>(warps) * L.warp_stride;
     return L;
 }
 
-__global__ void __launch_bounds__(kP512Groups * kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
+// D: ring depth of the per-warp sample staging.  HALF: transpose the real and imaginary halves one after the other through a
+// buffer of half the size (two more __syncwarp, twice the LDS/STS instructions, room for more warps per SM).
+template <int D, bool HALF>
+__global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
     OfdmDev d, P512Tw twa, u64 Z, const float* __restrict__ samples, size_t frame_stride, size_t B, int n_symbols, int training,
     float* __restrict__ llr_out, size_t llr_stride, int llr_limit, float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out) {
     constexpr int EPL = 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int W = (blockDim.x >> 5) / kP512Groups;               // warps per group
-    const int grp = (threadIdx.x >> 5) / W;                      // which of the CTA's frames-in-flight this thread works on
-    const int tid = threadIdx.x - grp * W * 32, lane = tid & 31, warp = tid >> 5, T = W * 32;
+    const int W = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nd = d.n_data;
     const int first = training > 0 ? training - 1 : 0;   // data H uses the LAST training symbol only (:179-185)
     const int n_proc = n_symbols - first;
-    const int npairs = (n_proc + 1) >> 1;
-    const P512Smem L = p512_layout(n_symbols, first, d.sym_len, nd, W);
-    float4* nco_s = reinterpret_cast<float4*>(smem_raw + L.nco);                       // [npairs][16][32]
-    float4* tb = reinterpret_cast<float4*>(smem_raw + L.tb) + (grp * W + warp) * kP512Buf;
-    unsigned char* gb = smem_raw + L.grp0 + grp * L.grp_stride;
-    float* xs = reinterpret_cast<float*>(gb + L.xs);
-    float2* F = reinterpret_cast<float2*>(gb + L.F);
-    float2* Hs = reinterpret_cast<float2*>(gb + L.Hs);
-    int* slow_item = reinterpret_cast<int*>(gb + L.slow);
-    float* hp_s = reinterpret_cast<float*>(gb + L.hp);
-    float* nv_s = reinterpret_cast<float*>(gb + L.nv);
-    float* habs = reinterpret_cast<float*>(gb + L.habs);
-    u64* full_bar = reinterpret_cast<u64*>(gb + L.misc);
-    u64* empty_bar = full_bar + 1;
-    int* slow_count = reinterpret_cast<int*>(full_bar + 2);
-    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(T) : "memory"); };
+    const P512Smem L = p512_layout(n_proc, W, D, HALF);
+    float2* nco_s = reinterpret_cast<float2*>(smem_raw + L.nco);                       // [n_proc][16][32] (cos, -sin)
+    unsigned char* wb = smem_raw + L.warp0 + warp * L.warp_stride;
+    float* S = reinterpret_cast<float*>(wb + L.S);
+    float4* tb = reinterpret_cast<float4*>(wb + L.T);
+    float2* q_sym = reinterpret_cast<float2*>(wb + L.q_sym);
+    float2* q_prev = reinterpret_cast<float2*>(wb + L.q_prev);
+    float* q_nv = reinterpret_cast<float*>(wb + L.q_nv);
+    unsigned* q_frame = reinterpret_cast<unsigned*>(wb + L.q_frame);
+    int* q_item = reinterpret_cast<int*>(wb + L.q_item);
+    u64* bars = reinterpret_cast<u64*>(wb + L.bars);
 
     const int c = lane & 15, b8 = lane >> 4;
     const int nlo = nd / 2, nhi = nd - nlo;
-    const uint32_t sym_bytes = 512 * sizeof(float);     // the samples after the cyclic prefix are all that is staged
+    const int rlane = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);   // brev5(lane)
+    const float zf = __uint_as_float(static_cast<unsigned>(Z));                        // -0.0f the compiler cannot see
 
-    if (tid == 0) {
-        mbar_init(full_bar, 1);
-        mbar_init(empty_bar, W);
-        slow_count[0] = slow_count[1] = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // NCO slices of the symbol pairs (loop invariant: resident in shared memory for the life of the CTA)
-    for (int i = threadIdx.x; i < npairs * 512; i += blockDim.x) nco_s[i] = __ldg(&d.nco2[static_cast<size_t>(first + 2 * (i >> 9)) * 512 + (i & 511)]);
-    __syncthreads();
-    const size_t frame0 = static_cast<size_t>(blockIdx.x) * kP512Groups + grp, frame_step = static_cast<size_t>(gridDim.x) * kP512Groups;
-    // stage the first frame of this group
-    if (warp == 0 && frame0 < B) {
-        if (lane == 0) mbar_expect_tx(full_bar, sym_bytes * n_proc);
-        __syncwarp();
-        const float* src = samples + frame0 * frame_stride + static_cast<size_t>(first) * d.sym_len + d.cp;
-        for (int sy = lane; sy < n_proc; sy += 32) bulk_g2s(xs + sy * 512, src + static_cast<size_t>(sy) * d.sym_len, sym_bytes, full_bar);
+    // NCO slices of the processed symbols (loop invariant: resident in shared memory for the life of the CTA); entry
+    // [sy][q][lane] belongs to sample cp + brev5(lane) + 32 brev4(q) of symbol first + sy: the lane-linear order of pass A
+    for (int i = threadIdx.x; i < n_proc * 512; i += blockDim.x) {
+        const int sy = i >> 9, q = (i >> 5) & 15, l = i & 31;
+        const int n = static_cast<int>(__brev(static_cast<unsigned>(l)) >> 27) + 32 * static_cast<int>(__brev(static_cast<unsigned>(q)) >> 28);
+        const float2 o = __ldg(&d.nco[static_cast<size_t>(first + sy) * d.sym_len + d.cp + n]);
+        nco_s[i] = make_float2(o.x, -o.y);
+    }
+    __syncthreads();      // the only CTA-wide barrier: from here on every warp is an independent pipeline
+
+    // ---- this warp's share of the batch: frame pairs gw, gw + GW, ...
+    const size_t n_pairs = (B + 1) >> 1;
+    const size_t gw = static_cast<size_t>(blockIdx.x) * W + warp, GW = static_cast<size_t>(gridDim.x) * W;
+    const size_t n_mine = gw < n_pairs ? (n_pairs - gw + GW - 1) / GW : 0;
+    const size_t total_steps = n_mine * n_proc;
+    const uint32_t sym_bytes = 512 * sizeof(float);
+
+    // producer cursor (lane 0 only uses it): step -> (pair, symbol)
+    size_t ip_pair = gw;
+    int ip_sym = 0;
+    auto issue = [&](int stage) {
+        const size_t f0 = 2 * ip_pair, f1 = (f0 + 1 < B) ? f0 + 1 : f0;     // odd tail: the upper half recomputes frame f (never stored)
+        const size_t so = static_cast<size_t>(first + ip_sym) * d.sym_len + d.cp;
+        mbar_expect_tx(&bars[stage], 2 * sym_bytes);
+        bulk_g2s(S + stage * kP512StageFloats, samples + f0 * frame_stride + so, sym_bytes, &bars[stage]);
+        bulk_g2s(S + stage * kP512StageFloats + 512, samples + f1 * frame_stride + so, sym_bytes, &bars[stage]);
+        if (++ip_sym == n_proc) { ip_sym = 0; ip_pair += GW; }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (static_cast<size_t>(i) < total_steps) issue(i);
     }
 
     // ---- per-lane twiddles of pass B as broadcast pairs (loop invariant).  Stage q pairs (j, j + 2^q); low outputs
@@ -192,54 +217,87 @@ __global__ void __launch_bounds__(kP512Groups * kP512MaxWarps * 32, 1) ofdm_diff
         const float2 a = __ldg(&d.twiddle[b8 ? (c + 240) : c]);
         wlast_re = pk(a.x, a.x); wlast_im = pk(a.y, a.y);
     }
-    const int rlane = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);   // brev5(lane)
+    // the carrier this lane ends the FFT with: bins 1..nhi on lanes (0, c), bins 512-nlo..511 on lanes (1, c)
+    int idx = -1;
+    if (b8 == 0) { if (c >= 1 && c <= nhi) idx = nlo + c - 1; }
+    else { const int cc = 16 - c; if (c >= 1 && cc <= nlo) idx = nlo - cc; }
+    const float2 zc = idx >= 0 ? __ldg(&d.zc[idx]) : make_float2(1.0f, 0.0f);
+    const int bps = d.bps, mod = d.mod;
+    const float2 one = make_float2(1.0f, 0.0f);
+    const unsigned lt_mask = (1u << lane) - 1u;
 
-    uint32_t it = 0;
-    for (size_t frame = frame0; frame < B; frame += frame_step, ++it) {
-        mbar_wait(full_bar, it & 1);
-        for (int pr = warp; pr < npairs; pr += W) {
-            const int s = first + 2 * pr;
-            const bool have2 = (s + 1) < n_symbols;
-            const float* x0 = xs + (s - first) * 512;
-            const float* x1 = have2 ? x0 + 512 : x0;            // odd tail: the upper half recomputes symbol s (never stored)
-            const float4* nc = nco_s + pr * 512 + lane;                   // [q][lane]: entry of sample brev5(lane) + 32 brev4(q)
-            // ---- pass A: lane g owns bit-reversed positions 16 g .. 16 g + 15 = samples brev5(g) + 32 brev4(q)
-            C2 v[EPL];
+    int qcount = 0;                                        // warp-uniform
+    auto flush = [&]() {                                   // exact demapper on the first min(qcount, 32) queued carriers
+        const int n = qcount < 32 ? qcount : 32;
+        if (lane < n) {
+            float l[3];
+            const int item = q_item[lane];
+            demap_exact(mod, q_sym[lane], q_prev[lane], false, q_nv[lane], l);   // |(1,0)| == 1 exactly, so `first` is not needed
+            store_llrs(llr_out + static_cast<size_t>(q_frame[lane]) * llr_stride, item * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
+        }
+        const int rem = qcount - n;
+        float2 ms = one, mp = one; float mn = 0.0f; unsigned mf = 0; int mi = 0;
+        if (lane < rem) { ms = q_sym[32 + lane]; mp = q_prev[32 + lane]; mn = q_nv[32 + lane]; mf = q_frame[32 + lane]; mi = q_item[32 + lane]; }
+        __syncwarp();
+        if (lane < rem) { q_sym[lane] = ms; q_prev[lane] = mp; q_nv[lane] = mn; q_frame[lane] = mf; q_item[lane] = mi; }
+        __syncwarp();
+        qcount = rem;
+    };
+
+    // per-frame state of this lane's carrier, [0] = frame f, [1] = frame f+1
+    float2 h[2] = {one, one}, prev[2] = {one, one};
+    float hp[2] = {1.0f, 1.0f}, nv[2] = {0.1f, 0.1f}, inv_nv[2] = {10.0f, 10.0f};
+
+    size_t pair = gw;
+    int sidx = 0, stage = 0;
+    uint32_t parity = 0;
+    for (size_t t = 0; t < total_steps; ++t) {
+        const size_t f0 = 2 * pair;
+        const bool have1 = f0 + 1 < B;
+        const int s = first + sidx;
+        mbar_wait(&bars[stage], parity);
+        const float* x0 = S + stage * kP512StageFloats;
+        const float* x1 = x0 + 512;
+        const float2* nc = nco_s + sidx * 512 + lane;                 // [q][lane]: entry of sample brev5(lane) + 32 brev4(q)
+        // ---- pass A: lane g owns bit-reversed positions 16 g .. 16 g + 15 = samples brev5(g) + 32 brev4(q)
+        C2 v[EPL];
 #pragma unroll
-            for (int q = 0; q < EPL; ++q) {
-                const int brq = static_cast<int>(__brev(static_cast<unsigned>(q)) >> 28);
-                const int n = rlane + 32 * brq;
-                const u64 xv = pk(x0[n], x1[n]);
-                const float4 o = nc[32 * q];                          // (cos_s, cos_s1, -sin_s, -sin_s1)
-                v[q].re = fma2(pk(o.x, o.y), xv, Z);                  // samples[i] * conj(osc) (channel_equalizer.cpp:36)
-                v[q].im = fma2(pk(o.z, o.w), xv, Z);
-            }
-            if (pr + W >= npairs) {       // this warp has taken its last samples of the frame out of shared memory
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty_bar);
-                const size_t next = frame + frame_step;
-                if (warp == 0 && next < B) {                          // refill the staging buffer for the next frame
-                    mbar_wait(empty_bar, it & 1);
-                    if (lane == 0) mbar_expect_tx(full_bar, sym_bytes * n_proc);
-                    __syncwarp();
-                    const float* src = samples + next * frame_stride + static_cast<size_t>(first) * d.sym_len + d.cp;
-                    for (int sy = lane; sy < n_proc; sy += 32)
-                        bulk_g2s(xs + sy * 512, src + static_cast<size_t>(sy) * d.sym_len, sym_bytes, full_bar);
-                }
-            }
+        for (int q = 0; q < EPL; ++q) {
+            const int brq = static_cast<int>(__brev(static_cast<unsigned>(q)) >> 28);
+            const int n = rlane + 32 * brq;
+            const float xa = x0[n], xb = x1[n];
+            const float2 o = nc[32 * q];                              // (cos, -sin)
+            v[q].re = pk(__fmaf_rn(o.x, xa, zf), __fmaf_rn(o.x, xb, zf));   // samples[i] * conj(osc) (channel_equalizer.cpp:36)
+            v[q].im = pk(__fmaf_rn(o.y, xa, zf), __fmaf_rn(o.y, xb, zf));
+        }
+        __syncwarp();                                                  // every lane has taken its samples out of the stage
+        if (lane == 0 && t + D < total_steps) issue(stage);           // refill it with the step D ahead
 #pragma unroll
-            for (int t = 1; t <= 4; ++t) {
-                const int half = 1 << (t - 1);
+        for (int tt = 1; tt <= 4; ++tt) {
+            const int half = 1 << (tt - 1);
 #pragma unroll
-                for (int p2 = 0; p2 < EPL / 2; ++p2) {
-                    const int kq = p2 & (half - 1);
-                    const int a = ((p2 >> (t - 1)) << t) | kq;
-                    const int m = kq << (4 - t);
-                    if (m == 0) bfly2_w0(v[a], v[a + half]);
-                    else bfly2(v[a], v[a + half], twa.re[m], twa.im[m], Z);
-                }
+            for (int p2 = 0; p2 < EPL / 2; ++p2) {
+                const int kq = p2 & (half - 1);
+                const int a = ((p2 >> (tt - 1)) << tt) | kq;
+                const int m = kq << (4 - tt);
+                if (m == 0) bfly2_w0(v[a], v[a + half]);
+                else bfly2(v[a], v[a + half], twa.re[m], twa.im[m], Z);
             }
+        }
+        if constexpr (HALF) {
+            u64* tb2 = reinterpret_cast<u64*>(tb);
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) tb2[17 * lane + q] = v[q].re;       // p = 16 lane + q at p + (p >> 4)
             __syncwarp();
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) v[j].re = tb2[c + 17 * j + 272 * b8];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < EPL; ++q) tb2[17 * lane + q] = v[q].im;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) v[j].im = tb2[c + 17 * j + 272 * b8];
+        } else {
 #pragma unroll
             for (int q = 0; q < EPL; ++q) {
                 float a0, a1, b0, b1;
@@ -253,140 +311,129 @@ __global__ void __launch_bounds__(kP512Groups * kP512MaxWarps * 32, 1) ofdm_diff
                 const float4 e = tb[c + 17 * j + 272 * b8];
                 v[j].re = pk(e.x, e.y); v[j].im = pk(e.z, e.w);
             }
+        }
+        __syncwarp();                                                  // the transpose buffer may be rewritten (next step / SNR scratch)
 #pragma unroll
-            for (int j = 0; j < EPL; j += 2) bfly2(v[j], v[j + 1], wl_re[0], wl_im[0], Z);
+        for (int j = 0; j < EPL; j += 2) bfly2(v[j], v[j + 1], wl_re[0], wl_im[0], Z);
 #pragma unroll
-            for (int q = 1; q < 4; ++q) {
-                const int step = 1 << (q + 1), h = 1 << q;
+        for (int q = 1; q < 4; ++q) {
+            const int step = 1 << (q + 1), hh = 1 << q;
 #pragma unroll
-                for (int j = 0; j < EPL; j += step) {
-                    v[j] = bfly2_lo(v[j], v[j + h], wl_re[q], wl_im[q], Z);
-                    v[j + step - 1] = bfly2_hi(v[j + step - 1 - h], v[j + step - 1], wh_re[q], wh_im[q], Z);
-                }
-            }
-            // stage 9 pairs lane (0,c) [A] with lane (1,c) [B]: bin c = A0 + w B0 on lane (0,c); bin 496+c = A15 - w B15 on lane (1,c)
-            const C2 send = b8 ? v[0] : v[EPL - 1];
-            C2 recv;
-            recv.re = __shfl_xor_sync(0xffffffffu, send.re, 16);
-            recv.im = __shfl_xor_sync(0xffffffffu, send.im, 16);
-            const C2 bin = b8 ? bfly2_hi(recv, v[EPL - 1], wlast_re, wlast_im, Z) : bfly2_lo(v[0], recv, wlast_re, wlast_im, Z);
-            int idx = -1;
-            if (b8 == 0) { if (c >= 1 && c <= nhi) idx = nlo + c - 1; }
-            else { const int cc = 16 - c; if (c >= 1 && cc <= nlo) idx = nlo - cc; }
-            float2* Fb = F + (it & 1) * n_symbols * nd;                 // bins of this frame (double-buffered by frame parity)
-            if (idx >= 0) {
-                float r0, r1, i0, i1;
-                upk(bin.re, r0, r1); upk(bin.im, i0, i1);
-                Fb[s * nd + idx] = make_float2(r0, i0);
-                if (have2) Fb[(s + 1) * nd + idx] = make_float2(r1, i1);
-                if (pr == 0) {
-                    // estimateChannelFromLTS for data carriers (channel_equalizer.cpp:141,179-185) + the per-carrier constants of
-                    // equalize, straight from the registers of the warp that transformed the last LTS symbol (s == training - 1)
-                    const float2 h = training > 0 ? cdiv(make_float2(r0, i0), __ldg(&d.zc[idx])) : make_float2(1.0f, 0.0f);
-                    const float hp = cnorm(h);
-                    const int o = (it & 1) * kP512Carr + idx;
-                    Hs[o] = h;
-                    hp_s[o] = hp;
-                    nv_s[o] = (hp > 1e-6f) ? clampf(1e-6f, 100.0f, __fdiv_rn(0.1f, hp)) : 100.0f;   // noise_variance stays 0.1 (:762-768)
-                    if (snr_db_out) habs[o] = cabs_ref(h);
-                }
+            for (int j = 0; j < EPL; j += step) {
+                v[j] = bfly2_lo(v[j], v[j + hh], wl_re[q], wl_im[q], Z);
+                v[j + step - 1] = bfly2_hi(v[j + step - 1 - hh], v[j + step - 1], wh_re[q], wh_im[q], Z);
             }
         }
-        group_sync();                                                  // B1: bins of all symbols + H are in shared memory
-        if (tid == 0) slow_count[(it + 1) & 1] = 0;                    // every reader of that counter (frame it - 1) is past B1
+        // stage 9 pairs lane (0,c) [A] with lane (1,c) [B]: bin c = A0 + w B0 on lane (0,c); bin 496+c = A15 - w B15 on lane (1,c)
+        const C2 send = b8 ? v[0] : v[EPL - 1];
+        C2 recv;
+        recv.re = __shfl_xor_sync(0xffffffffu, send.re, 16);
+        recv.im = __shfl_xor_sync(0xffffffffu, send.im, 16);
+        const C2 bin = b8 ? bfly2_hi(recv, v[EPL - 1], wlast_re, wlast_im, Z) : bfly2_lo(v[0], recv, wlast_re, wlast_im, Z);
+        float2 rx[2];
+        upk(bin.re, rx[0].x, rx[1].x); upk(bin.im, rx[0].y, rx[1].y);
 
-        // ---- equalize (:747-770, ZF with pilot_phase_correction == (1,0) and timing_offset == 0) + demodulateSymbol
-        //      (demodulator.cpp:279-316) + soft_demap.hpp, fused: lane = carrier, each warp walks a contiguous run of data symbols
-        //      and keeps the previous equalised symbol in registers (the run's first predecessor is re-equalised, not exchanged).
-        const float2* Fb = F + (it & 1) * n_symbols * nd;
-        const int nds = n_symbols - training;
-        float* out = llr_out + frame * llr_stride;
-        const int bps = d.bps, mod = d.mod;
-        int* scount = slow_count + (it & 1);
-        if (lane < nd && nds > 0) {
-            const int o = (it & 1) * kP512Carr + lane;
-            const float2 h = Hs[o];
-            const float hp = hp_s[o];
-            const float nv = __fmul_rn(nv_s[o], d.ce_margin);
-            const float inv_nv = __frcp_rn(nv);
-            const float2 one = make_float2(1.0f, 0.0f);
-            auto equalize = [&](int sd) {
-                const float2 rx = Fb[(training + sd) * nd + lane];
-                if (hp > 1e-6f) return cmul(cmul(cdivs(cmul(rx, cconj(h)), hp), one), one);   // :761
-                return cmul(cmul(rx, one), one);
-            };
-            const int ch = (nds + W - 1) / W;
-            const int sd0 = warp * ch, sd1 = min(nds, sd0 + ch);
-            float2 prev = make_float2(1.0f, 0.0f);                     // differential reference (1,0) (:251-255)
-            if (sd0 > 0 && sd0 < sd1) prev = equalize(sd0 - 1);
-            for (int sd = sd0; sd < sd1; ++sd) {
-                const float2 sym = equalize(sd);
-                const int item = sd * nd + lane;
-                float l[3];
-                if (demap_saturated_fast(mod, cmul(sym, cconj(prev)), inv_nv, l)) {
-                    store_llrs(out, item * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
-                } else {
-                    slow_item[atomicAdd(scount, 1)] = item;
-                }
-                prev = sym;
+        if (sidx == 0) {                                               // a new frame pair starts
+            prev[0] = prev[1] = one;                                   // differential reference (1,0) (demodulator.cpp:251-255)
+            if (training == 0) { h[0] = h[1] = one; }
+        }
+        if (s < training || (sidx == 0 && training == 0)) {
+            // estimateChannelFromLTS for data carriers (channel_equalizer.cpp:141,179-185) + the per-carrier constants of equalize,
+            // straight from the registers of the lane that holds the carrier's bin of the last LTS symbol (s == training - 1)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (s < training) h[j] = (idx >= 0) ? cdiv(rx[j], zc) : one;
+                hp[j] = cnorm(h[j]);
+                nv[j] = (hp[j] > 1e-6f) ? clampf(1e-6f, 100.0f, __fdiv_rn(0.1f, hp[j])) : 100.0f;   // noise_variance stays 0.1 (:762-768)
+                nv[j] = __fmul_rn(nv[j], d.ce_margin);
+                inv_nv[j] = __frcp_rn(nv[j]);
             }
-        }
-        group_sync();                                                  // B2: the list of carriers that need the exact demapper is complete
-        const int n_slow = *scount;
-        for (int k = tid; k < n_slow; k += T) {     // dense: the first n_slow threads of the group; re-equalises its two symbols
-            const int item = slow_item[k];
-            const int sd = item / nd, i = item - sd * nd;
-            const int o = (it & 1) * kP512Carr + i;
-            const float2 h = Hs[o];
-            const float hp = hp_s[o];
-            const float2 one = make_float2(1.0f, 0.0f);
-            auto equalize = [&](int sdx) {
-                const float2 rx = Fb[(training + sdx) * nd + i];
-                if (hp > 1e-6f) return cmul(cmul(cdivs(cmul(rx, cconj(h)), hp), one), one);
-                return cmul(cmul(rx, one), one);
-            };
-            const float2 sym = equalize(sd);
-            const float2 prev = sd > 0 ? equalize(sd - 1) : make_float2(1.0f, 0.0f);
-            float l[3];
-            demap_exact(mod, sym, prev, sd == 0, __fmul_rn(nv_s[o], d.ce_margin), l);
-            store_llrs(out, item * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
-        }
-        if (tid == 0) {
             if (snr_db_out) {   // reporting-only SNR estimate of estimateChannelFromLTS (:208-225), getEstimatedSNR (demodulator.cpp:797-799)
-                float snr_lin = 1.0f;
-                if (training > 0) {
-                    float sum = 0.0f;
-                    for (int i = 0; i < nd; ++i) sum = __fadd_rn(sum, habs[(it & 1) * kP512Carr + i]);
-                    const float avg = __fdiv_rn(sum, static_cast<float>(nd));
-                    if (avg > 1e-6f) snr_lin = clampf(0.1f, 10000.0f, __fdiv_rn(__fmul_rn(avg, avg), 0.1f));
+                float* sc = reinterpret_cast<float*>(tb);
+                if (idx >= 0) { sc[idx] = cabs_ref(h[0]); sc[32 + idx] = cabs_ref(h[1]); }
+                __syncwarp();
+                if (lane < 2 && (lane == 0 || have1)) {
+                    float snr_lin = 1.0f;
+                    if (training > 0) {
+                        float sum = 0.0f;
+                        for (int i = 0; i < nd; ++i) sum = __fadd_rn(sum, sc[32 * lane + i]);
+                        const float avg = __fdiv_rn(sum, static_cast<float>(nd));
+                        if (avg > 1e-6f) snr_lin = clampf(0.1f, 10000.0f, __fdiv_rn(__fmul_rn(avg, avg), 0.1f));
+                    }
+                    snr_db_out[f0 + lane] = 10.0f * log10f(snr_lin);
                 }
-                snr_db_out[frame] = 10.0f * log10f(snr_lin);
+                __syncwarp();
             }
-            if (final_cfo_out) final_cfo_out[frame] = 0.0f;
+            if (final_cfo_out && lane < 2 && (lane == 0 || have1)) final_cfo_out[f0 + lane] = 0.0f;
         }
-        // no barrier here: F / H are double-buffered by frame parity, the slow list is only appended to after the next B1
+        if (s >= training) {
+            // ---- equalize (:747-770, ZF with pilot_phase_correction == (1,0) and timing_offset == 0) + demodulateSymbol
+            //      (demodulator.cpp:279-316) + soft_demap.hpp on the lane that owns the carrier, for both frames
+            const int sd = s - training;
+            const int item = sd * nd + idx;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                bool need = false;
+                float2 sym = one;
+                if (idx >= 0 && (j == 0 || have1)) {
+                    sym = (hp[j] > 1e-6f) ? cmul(cmul(cdivs(cmul(rx[j], cconj(h[j])), hp[j]), one), one)    // :761
+                                          : cmul(cmul(rx[j], one), one);
+                    float l[3];
+                    if (demap_saturated_fast(mod, cmul(sym, cconj(prev[j])), inv_nv[j], l))
+                        store_llrs(llr_out + (f0 + j) * llr_stride, item * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
+                    else
+                        need = true;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, need);
+                if (m) {
+                    if (need) {
+                        const int pos = qcount + __popc(m & lt_mask);
+                        q_sym[pos] = sym; q_prev[pos] = prev[j]; q_nv[pos] = nv[j];
+                        q_frame[pos] = static_cast<unsigned>(f0 + j); q_item[pos] = item;
+                    }
+                    qcount += __popc(m);
+                    __syncwarp();
+                    if (qcount >= 32) flush();
+                }
+                prev[j] = sym;
+            }
+        }
+        if (++sidx == n_proc) { sidx = 0; pair += GW; }
+        if (++stage == D) { stage = 0; parity ^= 1u; }
     }
+    while (qcount > 0) flush();
 }
 
-static int p512_warps(int n_symbols, int training) {
-    const int first = training > 0 ? training - 1 : 0;
-    const int npairs = (n_symbols - first + 1) / 2;
-    return npairs < kP512MaxWarps ? npairs : kP512MaxWarps;
+// Warps per CTA: as many independent frame-pair pipelines as shared memory holds (NCO slices + one block per warp).
+static bool p512_half() {
+    static const int env = getenv("PU_P512_THALF") ? atoi(getenv("PU_P512_THALF")) : 1;
+    return env != 0;
+}
+static int p512_warps(int n_proc, int stages, bool half) {
+    static const int env = getenv("PU_P512_WARPS") ? atoi(getenv("PU_P512_WARPS")) : 0;
+    int w = kP512MaxWarps;
+    if (env > 0 && env < w) w = env;
+    while (w > 1 && p512_layout(n_proc, w, stages, half).total > kP512SmemMax) --w;
+    return w;
+}
+static int p512_stages() {
+    static const int env = getenv("PU_P512_STAGES") ? atoi(getenv("PU_P512_STAGES")) : 0;
+    return env == 3 ? 3 : 2;
 }
 
 // Returns true when the configuration / call is one this kernel covers (a superset of ofdm_diff_supported's
-// conditions: 512-FFT, 16-byte aligned rows so that the bulk copies are legal, the packed NCO table present).
-bool ofdm_diff512_supported(const OfdmDev& d, int n_symbols, int training, const float* samples, size_t frame_stride) {
+// conditions: 512-FFT, 16-byte aligned rows so that the bulk copies are legal).
+bool ofdm_diff512_supported(const OfdmDev& d, int n_symbols, int training, const float* samples, size_t frame_stride, size_t B) {
     const bool differential = d.mod == PU_MOD_DBPSK || d.mod == PU_MOD_DQPSK || d.mod == PU_MOD_D8PSK;
-    if (!differential || d.n_pilot != 0 || d.nfft != 512 || !d.nco2) return false;
+    if (!differential || d.n_pilot != 0 || d.nfft != 512 || !d.nco) return false;
     if (n_symbols > kP512MaxSym || n_symbols < 1 || training < 0 || training > n_symbols) return false;
     if ((d.sym_len & 3) || (d.cp & 3) || (frame_stride & 3) || (reinterpret_cast<uintptr_t>(samples) & 15)) return false;
+    if (B >= (size_t(1) << 32)) return false;                  // queued carriers carry their frame index as 32 bits
     const int first = training > 0 ? training - 1 : 0;
-    if (n_symbols - first < 1 || n_symbols - first > 32) return false;
+    if (n_symbols - first < 1) return false;
     const int nlo = d.n_data / 2, nhi = d.n_data - nlo;
     if (!(nlo < 16 && nhi < 16)) return false;
-    const P512Smem L = p512_layout(n_symbols, first, d.sym_len, d.n_data, p512_warps(n_symbols, training));
-    return L.total <= kP512SmemMax;
+    return p512_layout(n_symbols - first, 1, p512_stages(), p512_half()).total <= kP512SmemMax;
 }
 
 cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, const float* samples, size_t B, size_t frame_stride,
@@ -401,20 +448,26 @@ cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, co
         twa.im[m] = (static_cast<u64>(xi) << 32) | xi;
     }
     const int first = training > 0 ? training - 1 : 0;
-    const int warps = p512_warps(n_symbols, training);
-    const P512Smem L = p512_layout(n_symbols, first, d.sym_len, d.n_data, warps);
-    static size_t attr = 0;
-    if (L.total > attr) {
-        const cudaError_t e = cudaFuncSetAttribute(ofdm_diff512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kP512SmemMax));
-        if (e != cudaSuccess) return e;
-        attr = kP512SmemMax;
+    const int stages = p512_stages();
+    const bool half = p512_half();
+    const int warps = p512_warps(n_symbols - first, stages, half);
+    const P512Smem L = p512_layout(n_symbols - first, warps, stages, half);
+    using Kernel = void (*)(OfdmDev, P512Tw, u64, const float*, size_t, size_t, int, int, float*, size_t, int, float*, float*);
+    const Kernel kernels[4] = {ofdm_diff512_kernel<2, false>, ofdm_diff512_kernel<2, true>, ofdm_diff512_kernel<3, false>, ofdm_diff512_kernel<3, true>};
+    static bool attr = false;
+    if (!attr) {
+        for (const Kernel k : kernels) {
+            const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kP512SmemMax));
+            if (e != cudaSuccess) return e;
+        }
+        attr = true;
     }
     const size_t max_ctas = static_cast<size_t>(sm_count > 0 ? sm_count : 148);      // persistent: one CTA per SM
-    const size_t want_ctas = (B + kP512Groups - 1) / kP512Groups;
+    const size_t want_ctas = ((B + 1) / 2 + warps - 1) / warps;
     const unsigned grid = static_cast<unsigned>(want_ctas < max_ctas ? want_ctas : max_ctas);
     const u64 Z = 0x8000000080000000ull;    // (-0.0f, -0.0f): see the header comment
-    ofdm_diff512_kernel<<<grid, kP512Groups * warps * 32, L.total, st>>>(d, twa, Z, samples, frame_stride, B, n_symbols, training, llr, llr_stride, llr_limit,
-                                                          snr_db, final_cfo);
+    kernels[(stages == 3 ? 2 : 0) + (half ? 1 : 0)]<<<grid, warps * 32, L.total, st>>>(d, twa, Z, samples, frame_stride, B, n_symbols, training, llr,
+                                                                                     llr_stride, llr_limit, snr_db, final_cfo);
     return cudaGetLastError();
 }
 
