@@ -16,6 +16,7 @@
 // The syndrome of iteration t is evaluated by the check threads of iteration t+1 while they read the totals
 // anyway, and voted with one __syncthreads_or: two barriers per iteration.
 #include <cfloat>
+#include <cstdlib>
 #include <memory>
 #include <new>
 
@@ -160,9 +161,10 @@ __global__ void __launch_bounds__(512) ldpc_flood_kernel(LdpcDevTables t, const 
 //    not -0 can never become -0, and neither can v = total - c2v, so "v < 0" is exactly the sign bit and the sign
 //    product of a row is an XOR of raw bit patterns.  The sign of a zero never reaches a comparison or a magnitude
 //    in the reference, so this does not change any message, hard decision or iteration count.
-//  * |clamp(v, +-50)| = min(|v|, 50) and the clamp keeps the sign, so the clamped message itself is never formed.
-//  * the exclude-self minimum (:185-201) is (a_e == m1 ? m2 : m1): a unique minimum sees the second minimum, and on
-//    ties m2 == m1, which is what the reference's scan yields.
+//  * clamp(v, +-50) = sign(v) min(|v|, 50), and the message to edge e is 0.75 * (product of the other edges' signs) *
+//    (minimum of the other edges' magnitudes) (:185-201): both are FMNMX.XORSIGN combines (minxs below), so signs are
+//    never separated from magnitudes.  Ties between magnitudes need no care: every edge sees the minimum over the
+//    OTHER edges, which is what the reference's scan yields.
 //  * absent edges: variable-side slots point at a word holding +0.0f (x + 0 == x for x != -0); check-side edges of
 //    rows shorter than their warp's longest row read a total of +INF: no sign, and a magnitude of exactly the clamp
 //    limit, which cannot lower the first or second minimum of a row that has two real edges (every row does).
@@ -176,90 +178,123 @@ struct LdpcRegDev {   // device view of LdpcLayout (ldpc_code.h)
     const int16_t* slot_var;   // [kpad]
 };
 
+// sign(a) XOR sign(b) on min(|a|, |b|): one FMNMX.XORSIGN.  It is the min-sum combine of two messages (:185-197: the
+// sign product and the minimum magnitude of a row at once), and with b = +limit it is the symmetric clamp (:222).
+__device__ __forceinline__ float minxs(float a, float b) {
+    float d;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
 template <int NE>
 __device__ __forceinline__ void cn_update(const float* __restrict__ tot, float* __restrict__ msg, const int (&rd)[kE], const int (&wr)[kE],
                                           float (&prev)[kE], float par_llr, float& pc, float lim, bool last, unsigned& syn_bits) {
     const float ptot = __fadd_rn(par_llr, pc);        // total of the parity bit (:206-213)
     const float vp = __fsub_rn(ptot, pc);             // its v2c before the clamp (:219-222)
     unsigned px = __float_as_uint(ptot);              // XOR of the totals' sign bits = parity of the hard decisions
-    unsigned sx = __float_as_uint(vp);                // XOR of the messages' sign bits
-    // x[0] = parity edge, x[1..NE] = info edges: |clamp(v2c)|
-    float v[NE + 1], x[NE + 1];
-    v[0] = vp;
-    x[0] = fminf(fabsf(vp), lim);
+    // c[0] = parity edge, c[1..NE] = info edges: the clamped v2c messages, sign and magnitude together
+    float c[NE + 1];
+    c[0] = minxs(vp, lim);
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
         const float te = tot[rd[e]];
         px ^= __float_as_uint(te);
-        v[e + 1] = __fsub_rn(te, prev[e]);
-        sx ^= __float_as_uint(v[e + 1]);
-        x[e + 1] = fminf(fabsf(v[e + 1]), lim);
+        c[e + 1] = minxs(__fsub_rn(te, prev[e]), lim);
     }
     syn_bits = px;
     if (!last) {
-        // minimum over the OTHER edges of the row (:185-197) from prefix and suffix minima: 3(n-2) min operations for
-        // n edges, exact (a minimum does not depend on the order it is taken in)
+        // sign product and minimum magnitude over the OTHER edges of the row (:185-197) from prefix and suffix combines:
+        // 3(n-2) FMNMX.XORSIGN for n edges, exact (neither a minimum nor an XOR depends on the order it is taken in)
         float oth[NE + 1];
         if (NE == 0) {
             oth[0] = FLT_MAX;
         } else {
             float pre[NE + 1], suf[NE + 1];
-            pre[0] = x[0];
+            pre[0] = c[0];
 #pragma unroll
-            for (int i = 1; i < NE; ++i) pre[i] = fminf(pre[i - 1], x[i]);
-            suf[NE] = x[NE];
+            for (int i = 1; i < NE; ++i) pre[i] = minxs(pre[i - 1], c[i]);
+            suf[NE] = c[NE];
 #pragma unroll
-            for (int i = NE - 1; i >= 1; --i) suf[i] = fminf(suf[i + 1], x[i]);
+            for (int i = NE - 1; i >= 1; --i) suf[i] = minxs(suf[i + 1], c[i]);
             oth[0] = suf[1];
             oth[NE] = pre[NE - 1];
 #pragma unroll
-            for (int i = 1; i < NE; ++i) oth[i] = fminf(pre[i - 1], suf[i + 1]);
+            for (int i = 1; i < NE; ++i) oth[i] = minxs(pre[i - 1], suf[i + 1]);
         }
-        // sign * min_abs * 0.75f (:200): the row's sign product is folded into the constant, the edge's own sign is
-        // XOR-ed back in (excluding an edge from a product of +-1 is the same as multiplying by it again)
-        const float k = __uint_as_float(0x3f400000u | (sx & 0x80000000u));   // +-0.75
+        // sign * min_abs * 0.75f (:200)
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-            const float m = __fmul_rn(oth[e + 1], k);
-            const float out = __uint_as_float(__float_as_uint(m) ^ (__float_as_uint(v[e + 1]) & 0x80000000u));
+            const float out = __fmul_rn(oth[e + 1], 0.75f);
             prev[e] = out;
             msg[wr[e]] = out;
         }
-        const float m = __fmul_rn(oth[0], k);
-        pc = __uint_as_float(__float_as_uint(m) ^ (__float_as_uint(vp) & 0x80000000u));
+        pc = __fmul_rn(oth[0], 0.75f);
     }
 }
 
 // Shared memory: msg[d][a] = message from the d-th check (ascending check index) of the information bit in variable
-// slot a; tot[a] = its total.  The variable pass reads msg[d * kpad + a] with a = thread index: conflict-free by
-// construction.  The check pass gathers tot[a] and scatters msg[rank * kpad + a]; both hit bank a mod 32, and the
+// slot a; tot[a] = its total.  The variable pass reads msg[d * KP + a] with a = thread index: conflict-free by
+// construction.  The check pass gathers tot[a] and scatters msg[rank * KP + a]; both hit bank a mod 32, and the
 // layout (ldpc_code.cpp: make_ldpc_layout) makes the 32 lanes of a warp use 32 different banks on every edge.
-template <int VR, int DV, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) ldpc_flood_reg_kernel(LdpcRegDev t, const float* __restrict__ llr, size_t llr_stride,
-                                                             uint8_t* __restrict__ info, size_t info_stride,
-                                                             uint8_t* __restrict__ ok, int32_t* __restrict__ iters, int max_iter) {
+//
+// The whole iteration loop is specialised on NE = the longest row of the warp (check slots are sorted by degree, so
+// warps are nearly uniform): every warp runs its own copy of the loop, and all copies execute the same sequence of
+// CTA-wide barriers (barrier 0 counts arriving threads, not program counters).  KP, T and DV are compile-time, so every
+// shared-memory access of the variable pass is base + immediate.  Threads past the last check slot run a dummy row
+// (table defaults: reads of the +INF word, writes to the scratch words, a parity LLR of +0) whose total is never
+// negative, so there is no per-thread predicate in the loop.
+template <int NE, int VR, int DV, int T, int KP>
+__device__ __forceinline__ void decode_loop(float* __restrict__ msg, float* __restrict__ tot, const int (&rd)[kE], const int (&wr)[kE],
+                                            const float (&lin)[VR], float par_llr, int tid, int max_iter, int& it_out, int& converged) {
+    float prev[kE];
+#pragma unroll
+    for (int e = 0; e < kE; ++e) prev[e] = 0.0f;
+    float pc = 0.0f;
+    int it = 0;
+    converged = 0;
+    for (;; ++it) {
+        const bool last = (it == max_iter);
+        const float lim = (it == 0) ? INFINITY : 50.0f;   // iteration 0 consumes the raw channel LLRs (:169-173)
+        unsigned syn_bits = 0;
+        cn_update<NE>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits);
+        const int any = __syncthreads_or(static_cast<int>(syn_bits >> 31));   // syndrome of iteration it-1's totals (:227-235)
+        if (it > 0 && !any) { converged = 1; --it; break; }
+        if (last) break;
+#pragma unroll
+        for (int r = 0; r < VR; ++r) {
+            const int a = tid + r * T;
+            if ((r + 1) * T <= KP || a < KP) {
+                float s = lin[r];
+#pragma unroll
+                for (int d = 0; d < DV; ++d) s = __fadd_rn(s, msg[d * KP + a]);   // ascending check order (:208-213)
+                tot[a] = s;
+            }
+        }
+        __syncthreads();
+    }
+    it_out = it;
+}
+
+template <int VR, int DV, int T, int MINB, int KP>
+__global__ void __launch_bounds__(T, MINB) ldpc_flood_reg_kernel(LdpcRegDev t, const float* __restrict__ llr, size_t llr_stride,
+                                                          uint8_t* __restrict__ info, size_t info_stride,
+                                                          uint8_t* __restrict__ ok, int32_t* __restrict__ iters, int max_iter) {
     extern __shared__ float smem[];
-    const int K = t.k, M = t.m, KP = t.kpad;
+    constexpr int kMsgWords = DV * KP + 32;
+    const int K = t.k, M = t.m;
     float* msg = smem;                       // [DV][KP] + scratch row
-    float* tot = smem + t.msg_words;         // [KP] + the +INF word
-    const int tid = threadIdx.x, T = blockDim.x;
+    float* tot = smem + kMsgWords;           // [KP] + the +INF word
+    const int tid = threadIdx.x;
     const float* x = llr + static_cast<size_t>(blockIdx.x) * llr_stride;
 
-    const bool has_check = tid < M;
-    int ninfo = 0;
     int rd[kE], wr[kE];
-    float prev[kE];
-    float par_llr = 0.0f, pc = 0.0f;
 #pragma unroll
     for (int e = 0; e < kE; ++e) {
         rd[e] = t.cn_rd[e * T + tid];
         wr[e] = t.cn_wr[e * T + tid];
-        prev[e] = 0.0f;
     }
-    if (has_check) {
-        ninfo = t.cn_ninfo[tid];
-        par_llr = __fadd_rn(x[K + t.cn_check[tid]], 0.0f);
-    }
+    const int ninfo = t.cn_ninfo[tid];                       // 0 past the last check slot
+    const float par_llr = tid < M ? __fadd_rn(x[K + t.cn_check[tid]], 0.0f) : 0.0f;
     const int nw = __reduce_max_sync(0xffffffffu, ninfo);   // longest row of this warp (slots are sorted by degree)
     float lin[VR];
 #pragma unroll
@@ -272,42 +307,21 @@ __global__ void __launch_bounds__(MAXT, MINB) ldpc_flood_reg_kernel(LdpcRegDev t
             tot[a] = lin[r];
         }
     }
-    for (int i = tid; i < t.msg_words; i += T) msg[i] = 0.0f;   // absent variable-side edges stay +0 forever
-    if (tid == 0) tot[t.inf_slot] = INFINITY;
+    for (int i = tid; i < kMsgWords; i += T) msg[i] = 0.0f;   // absent variable-side edges stay +0 forever
+    if (tid == 0) tot[KP] = INFINITY;                          // LdpcLayout::inf_slot
     __syncthreads();
 
-    int it = 0;
-    int converged = 0;
-    for (;; ++it) {
-        const bool last = (it == max_iter);
-        const float lim = (it == 0) ? INFINITY : 50.0f;   // iteration 0 consumes the raw channel LLRs (:169-173)
-        unsigned syn_bits = 0;
-        if (has_check) {
-            switch (nw) {
-                case 0: cn_update<0>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 1: cn_update<1>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 2: cn_update<2>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 3: cn_update<3>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 4: cn_update<4>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
-                case 5: cn_update<5>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
-                default: cn_update<6>(tot, msg, rd, wr, prev, par_llr, pc, lim, last, syn_bits); break;
-            }
-        }
-        const int any = __syncthreads_or(static_cast<int>(syn_bits >> 31));   // syndrome of iteration it-1's totals (:227-235)
-        if (it > 0 && !any) { converged = 1; --it; break; }
-        if (last) break;
-#pragma unroll
-        for (int r = 0; r < VR; ++r) {
-            const int a = tid + r * T;
-            if (a < KP) {
-                float s = lin[r];
-#pragma unroll
-                for (int d = 0; d < DV; ++d) s = __fadd_rn(s, msg[d * KP + a]);   // ascending check order (:208-213)
-                tot[a] = s;
-            }
-        }
-        __syncthreads();
+    int it = 0, converged = 0;
+    switch (nw) {
+        case 0: decode_loop<0, VR, DV, T, KP>(msg, tot, rd, wr, lin, par_llr, tid, max_iter, it, converged); break;
+        case 1: decode_loop<1, VR, DV, T, KP>(msg, tot, rd, wr, lin, par_llr, tid, max_iter, it, converged); break;
+        case 2: decode_loop<2, VR, DV, T, KP>(msg, tot, rd, wr, lin, par_llr, tid, max_iter, it, converged); break;
+        case 3: decode_loop<3, VR, DV, T, KP>(msg, tot, rd, wr, lin, par_llr, tid, max_iter, it, converged); break;
+        case 4: decode_loop<4, VR, DV, T, KP>(msg, tot, rd, wr, lin, par_llr, tid, max_iter, it, converged); break;
+        case 5: decode_loop<5, VR, DV, T, KP>(msg, tot, rd, wr, lin, par_llr, tid, max_iter, it, converged); break;
+        default: decode_loop<6, VR, DV, T, KP>(msg, tot, rd, wr, lin, par_llr, tid, max_iter, it, converged); break;
     }
+    __syncthreads();   // every warp has left its loop: the totals are final
 
     uint8_t* out = info + static_cast<size_t>(blockIdx.x) * info_stride;
     const int nbytes = (K + 7) >> 3;
@@ -405,20 +419,21 @@ static pu_status launch_decode(pu_ldpc* h, const float* d_llr, size_t llr_stride
     const size_t kMaxGrid = 1u << 30;
     for (size_t off = 0; off < B; off += kMaxGrid) {
         const size_t nb = std::min(kMaxGrid, B - off);
-#define PU_LDPC_REG_CASE(VR, DV, MAXT, MINB)                                                                       \
-    if (!done && h->reg_vr <= (VR) && h->reg_dv == (DV) && h->reg_threads <= (MAXT)) {                            \
-        pu::ldpc_flood_reg_kernel<VR, DV, MAXT, MINB><<<static_cast<unsigned>(nb), h->reg_threads, h->reg_smem, st>>>( \
+#define PU_LDPC_REG_CASE(VR, DV, T, MINB, KP)                                                                        \
+    if (!done && h->reg_vr == (VR) && h->reg_dv == (DV) && h->reg_threads == (T) && h->layout.kpad == (KP)) {      \
+        pu::ldpc_flood_reg_kernel<VR, DV, T, MINB, KP><<<static_cast<unsigned>(nb), T, h->reg_smem, st>>>(           \
             h->reg, d_llr + off * llr_stride, llr_stride, d_info + off * info_stride, info_stride,                \
             d_ok ? d_ok + off : nullptr, d_iters ? d_iters + off : nullptr, h->max_iter);                         \
         done = true;                                                                                              \
     }
         bool done = false;
-        if (h->reg_threads <= 512) {
-            PU_LDPC_REG_CASE(1, 5, 352, 3)     // R1/2: 324 checks, 3 CTAs of 11 warps per SM
-            PU_LDPC_REG_CASE(2, 3, 224, 4)     // R2/3: 216 checks
-            PU_LDPC_REG_CASE(3, 3, 192, 5)     // R3/4: 162 checks
-            PU_LDPC_REG_CASE(5, 3, 128, 6)     // R5/6: 108 checks
-            PU_LDPC_REG_CASE(1, 13, 512, 2)    // R1/4: 486 checks
+        {
+            // the launch shapes of make_ldpc_layout for the five code rates (threads, variable slots, degrees are fixed by H)
+            PU_LDPC_REG_CASE(1, 5, 352, 3, 352)    // R1/2: 324 checks, 3 CTAs of 11 warps per SM
+            PU_LDPC_REG_CASE(2, 3, 224, 4, 448)    // R2/3: 216 checks
+            PU_LDPC_REG_CASE(3, 3, 192, 5, 512)    // R3/4: 162 checks
+            PU_LDPC_REG_CASE(5, 3, 128, 6, 576)    // R5/6: 108 checks
+            PU_LDPC_REG_CASE(1, 13, 512, 2, 192)   // R1/4: 486 checks
         }
 #undef PU_LDPC_REG_CASE
         if (!done)

@@ -23,25 +23,38 @@ pu_ctx* pu_ofdm_context(pu_ofdm* h);   // ofdm_demod.cu
 namespace pu {
 
 // counters[bin][6] = {frames, frame_errors, bit_errors, bits, decode_failures, iteration_sum}
-__global__ void count_errors_kernel(const uint8_t* __restrict__ info, size_t info_stride, const uint8_t* __restrict__ ok,
+// Bins below kSharedBins are accumulated in a per-CTA shared-memory table first (a sweep has tens of SNR points and
+// neighbouring frames belong to different points), so global memory sees one atomic per (CTA, bin, counter) instead of
+// five per frame on a few dozen addresses.
+constexpr int kSharedBins = 64;
+__global__ void __launch_bounds__(1024) count_errors_kernel(const uint8_t* __restrict__ info, size_t info_stride, const uint8_t* __restrict__ ok,
                                     const int32_t* __restrict__ iters, const uint8_t* __restrict__ payload_pool,
                                     size_t payload_stride, const uint32_t* __restrict__ tx_index,
                                     const uint32_t* __restrict__ bin, int payload_bytes, size_t B,
                                     unsigned long long* __restrict__ counters) {
+    __shared__ unsigned long long local[kSharedBins * 6];
+    for (int i = threadIdx.x; i < kSharedBins * 6; i += blockDim.x) local[i] = 0ull;
+    __syncthreads();
     const size_t b = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    if (b >= B) return;
-    const uint8_t* got = info + b * info_stride;
-    const uint8_t* want = payload_pool + static_cast<size_t>(tx_index ? tx_index[b] : 0) * payload_stride;
-    int bit_err = 0;
-    for (int i = 0; i < payload_bytes; ++i) bit_err += __popc(static_cast<unsigned>(got[i] ^ want[i]));
-    const int success = ok[b] && bit_err == 0;   // tools/test_mode_snr.cpp:98-104
-    unsigned long long* c = counters + static_cast<size_t>(bin ? bin[b] : 0) * 6;
-    atomicAdd(&c[0], 1ull);
-    if (!success) atomicAdd(&c[1], 1ull);
-    if (bit_err) atomicAdd(&c[2], static_cast<unsigned long long>(bit_err));
-    atomicAdd(&c[3], static_cast<unsigned long long>(payload_bytes) * 8ull);
-    if (!ok[b]) atomicAdd(&c[4], 1ull);
-    atomicAdd(&c[5], static_cast<unsigned long long>(iters ? iters[b] : 0));
+    if (b < B) {
+        const uint8_t* got = info + b * info_stride;
+        const uint8_t* want = payload_pool + static_cast<size_t>(tx_index ? tx_index[b] : 0) * payload_stride;
+        int bit_err = 0;
+        for (int i = 0; i < payload_bytes; ++i) bit_err += __popc(static_cast<unsigned>(got[i] ^ want[i]));
+        const int decoded = ok[b] != 0;
+        const int success = decoded && bit_err == 0;   // tools/test_mode_snr.cpp:98-104
+        const size_t bi = bin ? bin[b] : 0;
+        unsigned long long* c = bi < kSharedBins ? local + bi * 6 : counters + bi * 6;
+        atomicAdd(&c[0], 1ull);
+        if (!success) atomicAdd(&c[1], 1ull);
+        if (bit_err) atomicAdd(&c[2], static_cast<unsigned long long>(bit_err));
+        atomicAdd(&c[3], static_cast<unsigned long long>(payload_bytes) * 8ull);
+        if (!decoded) atomicAdd(&c[4], 1ull);
+        atomicAdd(&c[5], static_cast<unsigned long long>(iters ? iters[b] : 0));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSharedBins * 6; i += blockDim.x)
+        if (local[i]) atomicAdd(&counters[i], local[i]);
 }
 
 }  // namespace pu
@@ -58,7 +71,7 @@ pu_status pu_count_errors(pu_ctx* ctx, const uint8_t* info_bytes, size_t info_st
     PU_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     (void)cudaGetLastError();
-    pu::count_errors_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(
+    pu::count_errors_kernel<<<static_cast<unsigned>((B + 1023) / 1024), 1024, 0, st>>>(
         info_bytes, info_stride, ok, iters, payload_pool, payload_stride, tx_index, bin, static_cast<int>(payload_bytes), B,
         reinterpret_cast<unsigned long long*>(counters));
     ctx->launches.fetch_add(1);

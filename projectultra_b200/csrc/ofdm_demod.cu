@@ -828,8 +828,10 @@ pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_t B, si
         PU_CUDA_TRY(cudaMemcpyAsync(din, hin, in_floats * sizeof(float), cudaMemcpyHostToDevice, st));
         float* dout = static_cast<float*>(ctx->d_out.ptr);
         PU_CUDA_TRY(cudaMemsetAsync(dout, 0, out_floats * sizeof(float), st));
-        s = launch_ofdm(h, din, nb, L, training_symbols, din + slab * L, din + slab * L + slab, dout, llr_stride,
-                        dout + slab * llr_stride, dout + slab * llr_stride + slab, nullptr, st);
+        // without caller-supplied CFO / phase the launch sees NULL arrays and may take the differential fast kernels
+        const bool has_cfo = cfo_hz || cfo_phase;
+        s = launch_ofdm(h, din, nb, L, training_symbols, has_cfo ? din + slab * L : nullptr, has_cfo ? din + slab * L + slab : nullptr, dout,
+                        llr_stride, dout + slab * llr_stride, dout + slab * llr_stride + slab, nullptr, st);
         if (s != PU_OK) return s;
         float* hout = static_cast<float*>(ctx->h_out.ptr);
         PU_CUDA_TRY(cudaMemcpyAsync(hout, dout, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -42,6 +42,7 @@ namespace pu {
 typedef unsigned long long u64;
 
 constexpr int kP512MaxWarps = 12;       // frame pairs in flight per CTA (one warp each)
+constexpr int kP512MaxWarpsInplace = 16; // ... of the in-place-transpose variant
 constexpr int kP512MaxSym = 40;
 constexpr int kP512Buf = 512 + 32;      // float4 per warp: element p lives at p + (p >> 4)
 constexpr size_t kP512SmemMax = 227 * 1024;
@@ -110,19 +111,25 @@ constexpr int kP512StageFloats = 1024;  // one ring stage: 512 samples (after th
 
 struct P512Smem {     // offsets (bytes) into dynamic shared memory, computed identically on host and device
     size_t nco;                                              // CTA-wide: NCO slices of the processed symbols
+    size_t tws;                                              // CTA-wide: pass-B twiddles per lane as (re, re, im, im) (TWS variants)
     size_t warp0, warp_stride;                               // then one block per warp:
     size_t S, T, q_sym, q_prev, q_nv, q_frame, q_item, bars; //   offsets inside a warp block
+    size_t stage_floats;                                     // distance between ring stages
     size_t total;
 };
-__host__ __device__ inline P512Smem p512_layout(int n_proc, int warps, int stages, bool half) {
+// inplace: the transpose between the FFT passes reuses the ring stage whose samples were just taken (plus 256 bytes of
+// padding behind it) instead of a buffer of its own, so a warp needs 10.5 KB and sixteen warps fit next to the NCO table.
+__host__ __device__ inline P512Smem p512_layout(int n_proc, int warps, int stages, bool half, bool inplace) {
     P512Smem L;
     size_t o = 0;
     auto take = [&o](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~size_t(15); return at; };
     L.nco = take(static_cast<size_t>(n_proc) * 512 * sizeof(float2));
+    L.tws = take(inplace ? 9 * 32 * sizeof(float4) : 0);
     L.warp0 = (o + 127) & ~size_t(127);
     o = 0;
-    L.S = take(static_cast<size_t>(stages) * kP512StageFloats * sizeof(float));
-    L.T = take(kP512Buf * (half ? sizeof(float2) : sizeof(float4)));
+    L.stage_floats = inplace ? (kP512Buf * sizeof(float2)) / sizeof(float) : kP512StageFloats;
+    L.S = take(static_cast<size_t>(stages) * L.stage_floats * sizeof(float));
+    L.T = inplace ? L.S : take(kP512Buf * (half ? sizeof(float2) : sizeof(float4)));
     L.q_sym = take(kP512Queue * sizeof(float2));
     L.q_prev = take(kP512Queue * sizeof(float2));
     L.q_nv = take(kP512Queue * sizeof(float));
@@ -136,8 +143,10 @@ __host__ __device__ inline P512Smem p512_layout(int n_proc, int warps, int stage
 
 // D: ring depth of the per-warp sample staging.  HALF: transpose the real and imaginary halves one after the other through a
 // buffer of half the size (two more __syncwarp, twice the LDS/STS instructions, room for more warps per SM).
-template <int D, bool HALF>
-__global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
+// INPLACE (needs HALF): see p512_layout; the pass-B twiddles then come from shared memory instead of 36 registers, which
+// brings the kernel under the 128 registers that 16 resident warps leave per thread.
+template <int D, bool HALF, bool INPLACE, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) ofdm_diff512_kernel(
     OfdmDev d, P512Tw twa, u64 Z, const float* __restrict__ samples, size_t frame_stride, size_t B, int n_symbols, int training,
     float* __restrict__ llr_out, size_t llr_stride, int llr_limit, float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out) {
     constexpr int EPL = 16;
@@ -146,11 +155,14 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
     const int nd = d.n_data;
     const int first = training > 0 ? training - 1 : 0;   // data H uses the LAST training symbol only (:179-185)
     const int n_proc = n_symbols - first;
-    const P512Smem L = p512_layout(n_proc, W, D, HALF);
+    static_assert(!INPLACE || HALF, "the in-place transpose moves one 8-byte half at a time");
+    const P512Smem L = p512_layout(n_proc, W, D, HALF, INPLACE);
+    const int SS = static_cast<int>(L.stage_floats);
     float2* nco_s = reinterpret_cast<float2*>(smem_raw + L.nco);                       // [n_proc][16][32] (cos, -sin)
     unsigned char* wb = smem_raw + L.warp0 + warp * L.warp_stride;
     float* S = reinterpret_cast<float*>(wb + L.S);
-    float4* tb = reinterpret_cast<float4*>(wb + L.T);
+    float4* tb = reinterpret_cast<float4*>(wb + L.T);                                   // INPLACE: re-pointed at the current stage every step
+    float4* tws = reinterpret_cast<float4*>(smem_raw + L.tws);
     float2* q_sym = reinterpret_cast<float2*>(wb + L.q_sym);
     float2* q_prev = reinterpret_cast<float2*>(wb + L.q_prev);
     float* q_nv = reinterpret_cast<float*>(wb + L.q_nv);
@@ -189,11 +201,13 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
     size_t ip_pair = gw;
     int ip_sym = 0;
     auto issue = [&](int stage) {
+        // INPLACE: the stage was last written through the generic proxy (transpose); order that before the bulk copy's writes
+        if constexpr (INPLACE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const size_t f0 = 2 * ip_pair, f1 = (f0 + 1 < B) ? f0 + 1 : f0;     // odd tail: the upper half recomputes frame f (never stored)
         const size_t so = static_cast<size_t>(first + ip_sym) * d.sym_len + d.cp;
         mbar_expect_tx(&bars[stage], 2 * sym_bytes);
-        bulk_g2s(S + stage * kP512StageFloats, samples + f0 * frame_stride + so, sym_bytes, &bars[stage]);
-        bulk_g2s(S + stage * kP512StageFloats + 512, samples + f1 * frame_stride + so, sym_bytes, &bars[stage]);
+        bulk_g2s(S + stage * SS, samples + f0 * frame_stride + so, sym_bytes, &bars[stage]);
+        bulk_g2s(S + stage * SS + 512, samples + f1 * frame_stride + so, sym_bytes, &bars[stage]);
         if (++ip_sym == n_proc) { ip_sym = 0; ip_pair += GW; }
     };
     if (lane == 0) {
@@ -217,6 +231,32 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
         const float2 a = __ldg(&d.twiddle[b8 ? (c + 240) : c]);
         wlast_re = pk(a.x, a.x); wlast_im = pk(a.y, a.y);
     }
+    if constexpr (INPLACE) {      // the same pairs, parked in shared memory by warp 0: [0..3] low, [4..7] high, [8] last stage
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float x0, x1, y0, y1;
+                upk(wl_re[q], x0, x1); upk(wl_im[q], y0, y1);
+                tws[q * 32 + lane] = make_float4(x0, x1, y0, y1);
+                upk(wh_re[q], x0, x1); upk(wh_im[q], y0, y1);
+                tws[(4 + q) * 32 + lane] = make_float4(x0, x1, y0, y1);
+            }
+            float x0, x1, y0, y1;
+            upk(wlast_re, x0, x1); upk(wlast_im, y0, y1);
+            tws[8 * 32 + lane] = make_float4(x0, x1, y0, y1);
+        }
+    }
+    if constexpr (INPLACE) __syncthreads();   // (prologue) the twiddle table is visible to every warp
+    auto tw_get = [&](int i, u64& re, u64& im) {     // i as in the shared table; the register copy is dead code under INPLACE
+        if constexpr (INPLACE) {
+            const float4 e = tws[i * 32 + lane];
+            re = pk(e.x, e.y); im = pk(e.z, e.w);
+        } else {
+            if (i < 4) { re = wl_re[i]; im = wl_im[i]; }
+            else if (i < 8) { re = wh_re[i - 4]; im = wh_im[i - 4]; }
+            else { re = wlast_re; im = wlast_im; }
+        }
+    };
     // the carrier this lane ends the FFT with: bins 1..nhi on lanes (0, c), bins 512-nlo..511 on lanes (1, c)
     int idx = -1;
     if (b8 == 0) { if (c >= 1 && c <= nhi) idx = nlo + c - 1; }
@@ -256,7 +296,8 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
         const bool have1 = f0 + 1 < B;
         const int s = first + sidx;
         mbar_wait(&bars[stage], parity);
-        const float* x0 = S + stage * kP512StageFloats;
+        const float* x0 = S + stage * SS;
+        if constexpr (INPLACE) tb = reinterpret_cast<float4*>(S + stage * SS);
         const float* x1 = x0 + 512;
         const float2* nc = nco_s + sidx * 512 + lane;                 // [q][lane]: entry of sample brev5(lane) + 32 brev4(q)
         // ---- pass A: lane g owns bit-reversed positions 16 g .. 16 g + 15 = samples brev5(g) + 32 brev4(q)
@@ -271,7 +312,10 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
             v[q].im = pk(__fmaf_rn(o.y, xa, zf), __fmaf_rn(o.y, xb, zf));
         }
         __syncwarp();                                                  // every lane has taken its samples out of the stage
-        if (lane == 0 && t + D < total_steps) issue(stage);           // refill it with the step D ahead
+        // refill it with the step D ahead -- at once when the stage is only a staging buffer; INPLACE: after the transposes
+        // (and after the SNR scratch of a training step) have finished with it
+        const bool snr_step = snr_db_out && (s < training || (sidx == 0 && training == 0));
+        if (!INPLACE && lane == 0 && t + D < total_steps) issue(stage);
 #pragma unroll
         for (int tt = 1; tt <= 4; ++tt) {
             const int half = 1 << (tt - 1);
@@ -313,15 +357,23 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
             }
         }
         __syncwarp();                                                  // the transpose buffer may be rewritten (next step / SNR scratch)
+        if (INPLACE && !snr_step && lane == 0 && t + D < total_steps) issue(stage);
+        {
+            u64 wr, wi;
+            tw_get(0, wr, wi);
 #pragma unroll
-        for (int j = 0; j < EPL; j += 2) bfly2(v[j], v[j + 1], wl_re[0], wl_im[0], Z);
+            for (int j = 0; j < EPL; j += 2) bfly2(v[j], v[j + 1], wr, wi, Z);
+        }
 #pragma unroll
         for (int q = 1; q < 4; ++q) {
             const int step = 1 << (q + 1), hh = 1 << q;
+            u64 lr, li, hr, hi;
+            tw_get(q, lr, li);
+            tw_get(4 + q, hr, hi);
 #pragma unroll
             for (int j = 0; j < EPL; j += step) {
-                v[j] = bfly2_lo(v[j], v[j + hh], wl_re[q], wl_im[q], Z);
-                v[j + step - 1] = bfly2_hi(v[j + step - 1 - hh], v[j + step - 1], wh_re[q], wh_im[q], Z);
+                v[j] = bfly2_lo(v[j], v[j + hh], lr, li, Z);
+                v[j + step - 1] = bfly2_hi(v[j + step - 1 - hh], v[j + step - 1], hr, hi, Z);
             }
         }
         // stage 9 pairs lane (0,c) [A] with lane (1,c) [B]: bin c = A0 + w B0 on lane (0,c); bin 496+c = A15 - w B15 on lane (1,c)
@@ -329,7 +381,9 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
         C2 recv;
         recv.re = __shfl_xor_sync(0xffffffffu, send.re, 16);
         recv.im = __shfl_xor_sync(0xffffffffu, send.im, 16);
-        const C2 bin = b8 ? bfly2_hi(recv, v[EPL - 1], wlast_re, wlast_im, Z) : bfly2_lo(v[0], recv, wlast_re, wlast_im, Z);
+        u64 wlr, wli;
+        tw_get(8, wlr, wli);
+        const C2 bin = b8 ? bfly2_hi(recv, v[EPL - 1], wlr, wli, Z) : bfly2_lo(v[0], recv, wlr, wli, Z);
         float2 rx[2];
         upk(bin.re, rx[0].x, rx[1].x); upk(bin.im, rx[0].y, rx[1].y);
 
@@ -366,6 +420,7 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
             }
             if (final_cfo_out && lane < 2 && (lane == 0 || have1)) final_cfo_out[f0 + lane] = 0.0f;
         }
+        if (INPLACE && snr_step && lane == 0 && t + D < total_steps) issue(stage);
         if (s >= training) {
             // ---- equalize (:747-770, ZF with pilot_phase_correction == (1,0) and timing_offset == 0) + demodulateSymbol
             //      (demodulator.cpp:279-316) + soft_demap.hpp on the lane that owns the carrier, for both frames
@@ -404,21 +459,25 @@ __global__ void __launch_bounds__(kP512MaxWarps * 32, 1) ofdm_diff512_kernel(
     while (qcount > 0) flush();
 }
 
+// Variant switches (read once; defaults = the fastest measured, profiles/r04_ofdm512_variants.txt and later):
+//   PU_P512_INPLACE (default 0)  in-place transpose + shared-memory twiddles, up to 16 warps (<= 128 registers); measured
+//                                0.56 ms against 0.54 ms for 12 warps with a transpose buffer of their own (r05): not occupancy-bound
+//   PU_P512_THALF   (default 1)  half-size transpose buffer            PU_P512_STAGES (2|3)  ring depth
+//   PU_P512_WARPS                upper bound on warps per CTA
+static int p512_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+static bool p512_inplace() { static const int env = p512_env("PU_P512_INPLACE", 0); return env != 0; }
+static bool p512_half() { static const int env = p512_env("PU_P512_THALF", 1); return env != 0 || p512_inplace(); }
+static int p512_stages() { static const int env = p512_env("PU_P512_STAGES", 0); return (env == 3 && !p512_inplace()) ? 3 : 2; }
 // Warps per CTA: as many independent frame-pair pipelines as shared memory holds (NCO slices + one block per warp).
-static bool p512_half() {
-    static const int env = getenv("PU_P512_THALF") ? atoi(getenv("PU_P512_THALF")) : 1;
-    return env != 0;
-}
-static int p512_warps(int n_proc, int stages, bool half) {
-    static const int env = getenv("PU_P512_WARPS") ? atoi(getenv("PU_P512_WARPS")) : 0;
-    int w = kP512MaxWarps;
+static int p512_warps(int n_proc, int stages, bool half, bool inplace) {
+    static const int env = p512_env("PU_P512_WARPS", 0);
+    int w = inplace ? kP512MaxWarpsInplace : kP512MaxWarps;
     if (env > 0 && env < w) w = env;
-    while (w > 1 && p512_layout(n_proc, w, stages, half).total > kP512SmemMax) --w;
+    while (w > 1 && p512_layout(n_proc, w, stages, half, inplace).total > kP512SmemMax) --w;
     return w;
-}
-static int p512_stages() {
-    static const int env = getenv("PU_P512_STAGES") ? atoi(getenv("PU_P512_STAGES")) : 0;
-    return env == 3 ? 3 : 2;
 }
 
 // Returns true when the configuration / call is one this kernel covers (a superset of ofdm_diff_supported's
@@ -433,7 +492,7 @@ bool ofdm_diff512_supported(const OfdmDev& d, int n_symbols, int training, const
     if (n_symbols - first < 1) return false;
     const int nlo = d.n_data / 2, nhi = d.n_data - nlo;
     if (!(nlo < 16 && nhi < 16)) return false;
-    return p512_layout(n_symbols - first, 1, p512_stages(), p512_half()).total <= kP512SmemMax;
+    return p512_layout(n_symbols - first, 1, p512_stages(), p512_half(), p512_inplace()).total <= kP512SmemMax;
 }
 
 cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, const float* samples, size_t B, size_t frame_stride,
@@ -449,11 +508,13 @@ cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, co
     }
     const int first = training > 0 ? training - 1 : 0;
     const int stages = p512_stages();
-    const bool half = p512_half();
-    const int warps = p512_warps(n_symbols - first, stages, half);
-    const P512Smem L = p512_layout(n_symbols - first, warps, stages, half);
+    const bool half = p512_half(), inplace = p512_inplace();
+    const int warps = p512_warps(n_symbols - first, stages, half, inplace);
+    const P512Smem L = p512_layout(n_symbols - first, warps, stages, half, inplace);
     using Kernel = void (*)(OfdmDev, P512Tw, u64, const float*, size_t, size_t, int, int, float*, size_t, int, float*, float*);
-    const Kernel kernels[4] = {ofdm_diff512_kernel<2, false>, ofdm_diff512_kernel<2, true>, ofdm_diff512_kernel<3, false>, ofdm_diff512_kernel<3, true>};
+    const Kernel kernels[5] = {ofdm_diff512_kernel<2, false, false, kP512MaxWarps>, ofdm_diff512_kernel<2, true, false, kP512MaxWarps>,
+                               ofdm_diff512_kernel<3, false, false, kP512MaxWarps>, ofdm_diff512_kernel<3, true, false, kP512MaxWarps>,
+                               ofdm_diff512_kernel<2, true, true, kP512MaxWarpsInplace>};
     static bool attr = false;
     if (!attr) {
         for (const Kernel k : kernels) {
@@ -466,7 +527,7 @@ cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, co
     const size_t want_ctas = ((B + 1) / 2 + warps - 1) / warps;
     const unsigned grid = static_cast<unsigned>(want_ctas < max_ctas ? want_ctas : max_ctas);
     const u64 Z = 0x8000000080000000ull;    // (-0.0f, -0.0f): see the header comment
-    kernels[(stages == 3 ? 2 : 0) + (half ? 1 : 0)]<<<grid, warps * 32, L.total, st>>>(d, twa, Z, samples, frame_stride, B, n_symbols, training, llr,
+    kernels[inplace ? 4 : (stages == 3 ? 2 : 0) + (half ? 1 : 0)]<<<grid, warps * 32, L.total, st>>>(d, twa, Z, samples, frame_stride, B, n_symbols, training, llr,
                                                                                      llr_stride, llr_limit, snr_db, final_cfo);
     return cudaGetLastError();
 }

@@ -138,3 +138,38 @@ def test_psk_waveforms_frame_by_frame_parity(case):
     assert c[:, 0].tolist() == [trials] * len(snrs)
     assert c[0, 1] >= c[-1, 1] and c[-1, 1] < trials        # the waterfall runs the right way and the top point decodes
     del ctx
+
+
+def test_count_errors_matches_numpy_for_many_bins():
+    """pu_count_errors: the frame-error rule of tools/test_mode_snr.cpp:98-104 over random decoder outputs, with more
+    bins than the kernel's shared-memory table holds (bins >= 64 go straight to global memory) and ragged batch sizes."""
+    import torch
+    from projectultra_b200 import capi, linksim
+    ctx = capi.Context(0)
+    rng = np.random.default_rng(7)
+    for B, n_bins in ((1, 1), (1000, 13), (5003, 100), (70000, 64)):
+        nbytes, kb, pool = 40, 41, 8
+        payloads = rng.integers(0, 256, (pool, nbytes), dtype=np.uint8)
+        tx = rng.integers(0, pool, B).astype(np.uint32)
+        info = np.zeros((B, kb), np.uint8)
+        info[:, :nbytes] = payloads[tx]
+        bad = rng.random(B) < 0.3
+        info[bad, rng.integers(0, nbytes)] ^= rng.integers(1, 256, int(bad.sum()), dtype=np.uint8)
+        ok = (rng.random(B) < 0.8).astype(np.uint8)
+        iters = rng.integers(0, 51, B).astype(np.int32)
+        bins = rng.integers(0, n_bins, B).astype(np.uint32)
+        want = np.zeros((n_bins, 6), np.int64)
+        biterr = np.unpackbits(info[:, :nbytes] ^ payloads[tx], axis=1).sum(axis=1)
+        np.add.at(want[:, 0], bins, 1)
+        np.add.at(want[:, 1], bins, ((ok == 0) | (biterr > 0)).astype(np.int64))
+        np.add.at(want[:, 2], bins, biterr)
+        np.add.at(want[:, 3], bins, nbytes * 8)
+        np.add.at(want[:, 4], bins, (ok == 0).astype(np.int64))
+        np.add.at(want[:, 5], bins, iters)
+        t = lambda a: torch.from_numpy(a).cuda()
+        counters = torch.zeros((n_bins, 6), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            linksim.count_errors(ctx, t(info), t(ok), t(iters), t(payloads), t(tx), t(bins), nbytes, counters)
+        torch.cuda.synchronize()
+        assert (counters.cpu().numpy() == 2 * want).all(), (B, n_bins)
+    del ctx
