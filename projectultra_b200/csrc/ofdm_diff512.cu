@@ -113,7 +113,7 @@ struct P512Smem {     // offsets (bytes) into dynamic shared memory, computed id
     size_t nco;                                              // CTA-wide: NCO slices of the processed symbols
     size_t tws;                                              // CTA-wide: pass-B twiddles per lane as (re, re, im, im) (TWS variants)
     size_t warp0, warp_stride;                               // then one block per warp:
-    size_t S, T, q_sym, q_prev, q_nv, q_frame, q_item, bars; //   offsets inside a warp block
+    size_t S, T, q_rx, q_rxp, q_h, q_frame, q_item, bars; //   offsets inside a warp block
     size_t stage_floats;                                     // distance between ring stages
     size_t total;
 };
@@ -130,9 +130,9 @@ __host__ __device__ inline P512Smem p512_layout(int n_proc, int warps, int stage
     L.stage_floats = inplace ? (kP512Buf * sizeof(float2)) / sizeof(float) : kP512StageFloats;
     L.S = take(static_cast<size_t>(stages) * L.stage_floats * sizeof(float));
     L.T = inplace ? L.S : take(kP512Buf * (half ? sizeof(float2) : sizeof(float4)));
-    L.q_sym = take(kP512Queue * sizeof(float2));
-    L.q_prev = take(kP512Queue * sizeof(float2));
-    L.q_nv = take(kP512Queue * sizeof(float));
+    L.q_rx = take(kP512Queue * sizeof(float2));
+    L.q_rxp = take(kP512Queue * sizeof(float2));
+    L.q_h = take(kP512Queue * sizeof(float2));
     L.q_frame = take(kP512Queue * sizeof(unsigned));
     L.q_item = take(kP512Queue * sizeof(int));
     L.bars = take(static_cast<size_t>(stages) * sizeof(u64));
@@ -163,9 +163,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ofdm_diff512_kernel(
     float* S = reinterpret_cast<float*>(wb + L.S);
     float4* tb = reinterpret_cast<float4*>(wb + L.T);                                   // INPLACE: re-pointed at the current stage every step
     float4* tws = reinterpret_cast<float4*>(smem_raw + L.tws);
-    float2* q_sym = reinterpret_cast<float2*>(wb + L.q_sym);
-    float2* q_prev = reinterpret_cast<float2*>(wb + L.q_prev);
-    float* q_nv = reinterpret_cast<float*>(wb + L.q_nv);
+    float2* q_rx = reinterpret_cast<float2*>(wb + L.q_rx);       // queued carriers: FFT bin of the symbol,
+    float2* q_rxp = reinterpret_cast<float2*>(wb + L.q_rxp);     //   bin of the preceding symbol,
+    float2* q_h = reinterpret_cast<float2*>(wb + L.q_h);         //   channel estimate of the carrier
     unsigned* q_frame = reinterpret_cast<unsigned*>(wb + L.q_frame);
     int* q_item = reinterpret_cast<int*>(wb + L.q_item);
     u64* bars = reinterpret_cast<u64*>(wb + L.bars);
@@ -267,26 +267,45 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ofdm_diff512_kernel(
     const unsigned lt_mask = (1u << lane) - 1u;
 
     int qcount = 0;                                        // warp-uniform
-    auto flush = [&]() {                                   // exact demapper on the first min(qcount, 32) queued carriers
+    // Exact path for the first min(qcount, 32) queued carriers: equalize (:747-770, ZF with pilot_phase_correction == (1,0)
+    // and timing_offset == 0) of the symbol and of its predecessor from their raw bins, then the libm-restatement demapper.
+    auto flush = [&]() {
         const int n = qcount < 32 ? qcount : 32;
         if (lane < n) {
             float l[3];
-            const int item = q_item[lane];
-            demap_exact(mod, q_sym[lane], q_prev[lane], false, q_nv[lane], l);   // |(1,0)| == 1 exactly, so `first` is not needed
+            const int qi = q_item[lane];
+            const int item = qi & 0x3fffffff;
+            const bool first = (qi >> 30) != 0;
+            const float2 hh = q_h[lane];
+            const float hq = cnorm(hh);
+            float nq = (hq > 1e-6f) ? clampf(1e-6f, 100.0f, __fdiv_rn(0.1f, hq)) : 100.0f;   // noise_variance stays 0.1 (:762-768)
+            nq = __fmul_rn(nq, d.ce_margin);
+            auto eq = [&](float2 r) {
+                return (hq > 1e-6f) ? cmul(cmul(cdivs(cmul(r, cconj(hh)), hq), one), one)    // :761
+                                    : cmul(cmul(r, one), one);
+            };
+            const float2 sym = eq(q_rx[lane]);
+            const float2 prv = first ? one : eq(q_rxp[lane]);            // differential reference (1,0) (demodulator.cpp:251-255)
+            demap_exact(mod, sym, prv, false, nq, l);                    // |(1,0)| == 1 exactly, so `first` is not needed there
             store_llrs(llr_out + static_cast<size_t>(q_frame[lane]) * llr_stride, item * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
         }
         const int rem = qcount - n;
-        float2 ms = one, mp = one; float mn = 0.0f; unsigned mf = 0; int mi = 0;
-        if (lane < rem) { ms = q_sym[32 + lane]; mp = q_prev[32 + lane]; mn = q_nv[32 + lane]; mf = q_frame[32 + lane]; mi = q_item[32 + lane]; }
+        float2 ms = one, mp = one, mh = one; unsigned mf = 0; int mi = 0;
+        if (lane < rem) { ms = q_rx[32 + lane]; mp = q_rxp[32 + lane]; mh = q_h[32 + lane]; mf = q_frame[32 + lane]; mi = q_item[32 + lane]; }
         __syncwarp();
-        if (lane < rem) { q_sym[lane] = ms; q_prev[lane] = mp; q_nv[lane] = mn; q_frame[lane] = mf; q_item[lane] = mi; }
+        if (lane < rem) { q_rx[lane] = ms; q_rxp[lane] = mp; q_h[lane] = mh; q_frame[lane] = mf; q_item[lane] = mi; }
         __syncwarp();
         qcount = rem;
     };
 
-    // per-frame state of this lane's carrier, [0] = frame f, [1] = frame f+1
-    float2 h[2] = {one, one}, prev[2] = {one, one};
-    float hp[2] = {1.0f, 1.0f}, nv[2] = {0.1f, 0.1f}, inv_nv[2] = {10.0f, 10.0f};
+    // per-frame state of this lane's carrier, [0] = frame f, [1] = frame f+1.  rxp holds the FFT bin of the previous symbol
+    // (the channel estimate itself before the first data symbol, so that bin * conj(rxp) / |h|^2 is the equalised symbol
+    // times the conjugate of the reference (1,0)); ihp = 1/|h|^2 (0 when the carrier is not equalised, which sends it to
+    // the exact path).
+    float2 h[2] = {one, one};
+    float inv_nv[2] = {10.0f, 10.0f};
+    C2 rxp = {pk(1.0f, 1.0f), pk(0.0f, 0.0f)};
+    u64 ihp = pk(1.0f, 1.0f);
 
     size_t pair = gw;
     int sidx = 0, stage = 0;
@@ -387,21 +406,23 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ofdm_diff512_kernel(
         float2 rx[2];
         upk(bin.re, rx[0].x, rx[1].x); upk(bin.im, rx[0].y, rx[1].y);
 
-        if (sidx == 0) {                                               // a new frame pair starts
-            prev[0] = prev[1] = one;                                   // differential reference (1,0) (demodulator.cpp:251-255)
-            if (training == 0) { h[0] = h[1] = one; }
-        }
+        if (sidx == 0 && training == 0) { h[0] = h[1] = one; }        // a new frame pair starts without training symbols
         if (s < training || (sidx == 0 && training == 0)) {
             // estimateChannelFromLTS for data carriers (channel_equalizer.cpp:141,179-185) + the per-carrier constants of equalize,
             // straight from the registers of the lane that holds the carrier's bin of the last LTS symbol (s == training - 1)
+            float ih[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 if (s < training) h[j] = (idx >= 0) ? cdiv(rx[j], zc) : one;
-                hp[j] = cnorm(h[j]);
-                nv[j] = (hp[j] > 1e-6f) ? clampf(1e-6f, 100.0f, __fdiv_rn(0.1f, hp[j])) : 100.0f;   // noise_variance stays 0.1 (:762-768)
-                nv[j] = __fmul_rn(nv[j], d.ce_margin);
-                inv_nv[j] = __frcp_rn(nv[j]);
+                const float hq = cnorm(h[j]);
+                float nq = (hq > 1e-6f) ? clampf(1e-6f, 100.0f, __fdiv_rn(0.1f, hq)) : 100.0f;   // noise_variance stays 0.1 (:762-768)
+                nq = __fmul_rn(nq, d.ce_margin);
+                inv_nv[j] = __frcp_rn(nq);
+                ih[j] = (hq > 1e-6f) ? __frcp_rn(hq) : 0.0f;
             }
+            ihp = pk(ih[0], ih[1]);
+            rxp.re = pk(h[0].x, h[1].x);
+            rxp.im = pk(h[0].y, h[1].y);
             if (snr_db_out) {   // reporting-only SNR estimate of estimateChannelFromLTS (:208-225), getEstimatedSNR (demodulator.cpp:797-799)
                 float* sc = reinterpret_cast<float*>(tb);
                 if (idx >= 0) { sc[idx] = cabs_ref(h[0]); sc[32 + idx] = cabs_ref(h[1]); }
@@ -422,19 +443,26 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ofdm_diff512_kernel(
         }
         if (INPLACE && snr_step && lane == 0 && t + D < total_steps) issue(stage);
         if (s >= training) {
-            // ---- equalize (:747-770, ZF with pilot_phase_correction == (1,0) and timing_offset == 0) + demodulateSymbol
-            //      (demodulator.cpp:279-316) + soft_demap.hpp on the lane that owns the carrier, for both frames
+            // ---- equalize (:747-770) + demodulateSymbol (demodulator.cpp:279-316) + soft_demap.hpp on the lane that owns the
+            //      carrier, for both frames.  The equalised symbols themselves are only formed on the exact path (flush):
+            //      sym * conj(prev) = bin * conj(previous bin) / |h|^2 up to rounding, and the saturation filter only needs
+            //      that product to a few ulp (its margin is 4e-5 relative + 0.01 absolute), so it reads the raw bins.
             const int sd = s - training;
             const int item = sd * nd + idx;
+            C2 e;
+            e.re = fma2(bin.re, rxp.re, fma2(bin.im, rxp.im, Z));
+            e.im = sub2(fma2(bin.im, rxp.re, Z), fma2(bin.re, rxp.im, Z));
+            e.re = fma2(e.re, ihp, Z);
+            e.im = fma2(e.im, ihp, Z);
+            float2 dd[2], rp[2];
+            upk(e.re, dd[0].x, dd[1].x); upk(e.im, dd[0].y, dd[1].y);
+            upk(rxp.re, rp[0].x, rp[1].x); upk(rxp.im, rp[0].y, rp[1].y);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 bool need = false;
-                float2 sym = one;
                 if (idx >= 0 && (j == 0 || have1)) {
-                    sym = (hp[j] > 1e-6f) ? cmul(cmul(cdivs(cmul(rx[j], cconj(h[j])), hp[j]), one), one)    // :761
-                                          : cmul(cmul(rx[j], one), one);
                     float l[3];
-                    if (demap_saturated_fast(mod, cmul(sym, cconj(prev[j])), inv_nv[j], l))
+                    if (demap_saturated_fast(mod, dd[j], inv_nv[j], l, 4e-5f))
                         store_llrs(llr_out + (f0 + j) * llr_stride, item * bps, bps, l, llr_limit, d.llr_perm, d.perm_len);
                     else
                         need = true;
@@ -443,15 +471,15 @@ __global__ void __launch_bounds__(MAXW * 32, 1) ofdm_diff512_kernel(
                 if (m) {
                     if (need) {
                         const int pos = qcount + __popc(m & lt_mask);
-                        q_sym[pos] = sym; q_prev[pos] = prev[j]; q_nv[pos] = nv[j];
-                        q_frame[pos] = static_cast<unsigned>(f0 + j); q_item[pos] = item;
+                        q_rx[pos] = rx[j]; q_rxp[pos] = rp[j]; q_h[pos] = h[j];
+                        q_frame[pos] = static_cast<unsigned>(f0 + j); q_item[pos] = item | (sd == 0 ? (1 << 30) : 0);
                     }
                     qcount += __popc(m);
                     __syncwarp();
                     if (qcount >= 32) flush();
                 }
-                prev[j] = sym;
             }
+            rxp = bin;
         }
         if (++sidx == n_proc) { sidx = 0; pair += GW; }
         if (++stage == D) { stage = 0; parity ^= 1u; }

@@ -83,7 +83,10 @@ __device__ __forceinline__ void store_llrs(float* __restrict__ out, int base, in
 // Same filter with the per-carrier 1/nv hoisted by the caller and MUFU.RSQ instead of IEEE sqrt + reciprocal: the extra
 // relative error (<= 2^-22 of the rsqrt, a few roundings) stays far inside the 1e-5 * scale + 0.01 margin derived above.
 // The weak-signal gate is tested on r2 = sp^2 (> 4e-12) so that a flushed rsqrt input cannot pass it.
-__device__ __forceinline__ bool demap_saturated_fast(int mod, float2 df, float inv_nv, float (&l)[3]) {
+// rel_margin: callers that feed an approximation of sym * conj(prev) (ofdm_diff512.cu forms it from the raw FFT bins,
+// bin * conj(previous bin) / |h|^2: <= 10 ulp away from the reference's fp32 value relative to |d|, which moves the
+// LLR laws by <= 8 * 1.2e-6 * scale for the k = 4 term) widen the relative part of the margin accordingly.
+__device__ __forceinline__ bool demap_saturated_fast(int mod, float2 df, float inv_nv, float (&l)[3], float rel_margin = 1e-5f) {
     const float dx = df.x, dy = df.y;
     const float r2 = fmaf(dx, dx, dy * dy);
     float inv_sp;
@@ -104,7 +107,7 @@ __device__ __forceinline__ bool demap_saturated_fast(int mod, float2 df, float i
         a1 = 2.0f * sc;
         a2 = 4.0f * sc * (dx - dy) * (dx + dy) * inv_sp * inv_sp;
     }
-    const float thr = fmaf(scale, 1e-5f, 10.01f);
+    const float thr = fmaf(scale, rel_margin, 10.01f);
     const bool ok = (r2 > 4e-12f) && (r2 < 1e30f) && (fabsf(a0) >= thr) && (fabsf(a1) >= thr) && (fabsf(a2) >= thr) && (scale < 1e30f);
     l[0] = copysignf(10.0f, a0);
     l[1] = copysignf(10.0f, a1);

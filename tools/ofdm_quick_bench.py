@@ -16,10 +16,16 @@ ctx = capi.Context(0)
 if mode == "m1":
     cfg = capi.ModemConfig(48000, 1500, 512, 30, 1, 4, 2, 0, capi.DQPSK, capi.R1_2, 40.0, 0.0)
     snrs = [float(s) for s in range(-4, 9)]
-else:
-    cfg = capi.nvis_config(capi.QAM32, capi.R3_4) if hasattr(capi, "nvis_config") else None
+    rate = capi.R1_2
+elif mode == "m1qam16":       # M1 coherent, pilots/2 (tools/test_mode_snr.cpp:30)
+    cfg = capi.ModemConfig(48000, 1500, 512, 30, 1, 4, 2, 1, capi.QAM16, capi.R1_2, 40.0, 0.0)
+    snrs = [float(s) for s in range(4, 17)]
+    rate = capi.R1_2
+else:                          # M3: presets::nvis_mode() 1024-FFT 59 carriers CP 96, 32QAM R3/4 pilots/4 (config 3)
+    cfg = capi.ModemConfig(48000, 1500, 1024, 59, 1, 0, 4, 1, capi.QAM32, capi.R3_4, 40.0, 0.0)
     snrs = [float(s) for s in range(6, 19)]
-sim = linksim.LinkSim(ctx, cfg, "awgn", payload_bytes=40 if mode == "m1" else 60, pool=64)
+    rate = capi.R3_4
+sim = linksim.LinkSim(ctx, cfg, os.environ.get("QB_CHANNEL", "awgn"), payload_bytes=40 if mode.startswith("m1") else 60, pool=64, code_rate=rate)
 n = len(snrs)
 B = fpp * n
 trials = np.repeat(np.arange(fpp, dtype=np.int64), n)
