@@ -91,6 +91,8 @@ struct RxShared {
     int snr_cnt, since_sync, have_prev, cpc_init, have_preveq;
     float2 ppc, cpc;
     float cfo_used;
+    int rot_fail[4];          // first broken link of each warp in the rotator-phase chain
+    float rot_next;
 };
 
 template <int NFFT>
@@ -143,18 +145,43 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
         const float* xs = x + static_cast<size_t>(s) * d.sym_len;
         const float2* nco = d.nco + static_cast<size_t>(s) * d.sym_len;
         // ---------------- rotator phases (channel_equalizer.cpp:23,39-51): a per-sample float recurrence
+        //   theta[i] = ph;  ph = wrap(fl(ph + inc)).
+        // Run T samples at a time: while ph stays in one binade every step adds the same number of ulps, so the next T
+        // values are bits(ph) + t * (bits(step(ph)) - bits(ph)); thread t checks its own link step(c_t) == c_{t+1} bit for
+        // bit, and the chain is accepted up to the first broken link (binade change, zero crossing, +-pi wrap), where the
+        // true successor computed by that thread restarts it.  Every accepted value is thus the reference's value by
+        // induction, at ~sym_len / T rounds instead of sym_len dependent additions on one thread.
         const bool rot = fabsf(S.cfo_hz) > 0.01f;
-        if (rot && tid == 0) {
+        if (rot) {
             const float inc = static_cast<float>(__ddiv_rn(__dmul_rn(-2.0f * 3.14159265358979323846, (double)S.cfo_hz), (double)d.sample_rate));
-            float ph = S.rot_phase;
             const float pi_hi = 3.14159274101257324f;   // smallest float > M_PI: (double)ph > M_PI  <=>  ph >= pi_hi
-            for (int i = 0; i < d.sym_len; ++i) {
-                theta[i] = ph;
+            auto step = [&](float ph) {
                 ph = __fadd_rn(ph, inc);
                 if (ph >= pi_hi) ph = static_cast<float>((double)ph - 2.0f * 3.14159265358979323846);
                 else if (ph <= -pi_hi) ph = static_cast<float>((double)ph + 2.0f * 3.14159265358979323846);
+                return ph;
+            };
+            float ph = S.rot_phase;
+            for (int i = 0; i < d.sym_len;) {
+                const unsigned b0 = __float_as_uint(ph);
+                const unsigned delta = __float_as_uint(step(ph)) - b0;
+                const float cand = __uint_as_float(b0 + static_cast<unsigned>(tid) * delta);
+                const float nxt = step(cand);
+                const bool broken = __float_as_uint(nxt) != b0 + static_cast<unsigned>(tid + 1) * delta;
+                const unsigned bal = __ballot_sync(0xffffffffu, broken);
+                if ((tid & 31) == 0) S.rot_fail[tid >> 5] = bal ? (tid + __ffs(bal) - 1) : T;
+                __syncthreads();
+                int f = T;
+#pragma unroll
+                for (int w = 0; w < T / 32; ++w) f = min(f, S.rot_fail[w]);
+                const int nvalid = min(f < T ? f + 1 : T, d.sym_len - i);    // c_0 .. c_f are the reference's values
+                if (tid < nvalid) theta[i + tid] = cand;
+                if (tid == nvalid - 1) S.rot_next = nxt;                      // true successor of the last accepted value
+                __syncthreads();
+                ph = S.rot_next;
+                i += nvalid;
             }
-            S.rot_phase = ph;
+            if (tid == 0) S.rot_phase = ph;
         }
         if (tid == 0) S.cfo_used = S.cfo_hz;
         __syncthreads();
