@@ -131,7 +131,8 @@ PU_API int pu_ofdm_pilot_carriers(const pu_ofdm* h);
 PU_API int pu_ofdm_bits_per_symbol(const pu_ofdm* h);  /* OFDMModulator::bitsPerSymbol, modulator.cpp:342-346 */
 /* Diagnostic (no reference counterpart): which kernel the last pu_ofdm_presynced_batch / pu_receive_decode_batch launch on
  * this handle used: 0 = none yet, 1 = general presynced kernel (ofdm_demod.cu), 2 = warp-FFT kernel for differential
- * no-pilot modes (ofdm_diff.cu), 3 = persistent TMA-staged packed-fp32 512-FFT kernel (ofdm_diff512.cu). */
+ * no-pilot modes (ofdm_diff.cu), 3 = persistent TMA-staged packed-fp32 512-FFT kernel (ofdm_diff512.cu), 4 = general presynced
+ * kernel in its one-frame-per-warp form (ofdm_demod.cu, WARPG). */
 PU_API int pu_ofdm_last_kernel(const pu_ofdm* h);
 /* FFT bins of the used carriers, data carriers first then pilots (setupCarriers, demodulator.cpp:45-67) */
 PU_API int pu_ofdm_carrier_bins(const pu_ofdm* h, int32_t* bins, int cap);

@@ -257,7 +257,8 @@ class OfdmDemodulator:
         except Exception:
             pass
 
-    KERNELS = {0: "none", 1: "ofdm_presynced_kernel", 2: "ofdm_diff_kernel", 3: "ofdm_diff512_kernel"}
+    KERNELS = {0: "none", 1: "ofdm_presynced_kernel", 2: "ofdm_diff_kernel", 3: "ofdm_diff512_kernel",
+               4: "ofdm_presynced_warp_kernel"}
 
     @property
     def last_kernel(self):

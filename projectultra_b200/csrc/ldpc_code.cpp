@@ -331,7 +331,7 @@ LdpcLayout make_ldpc_layout(const LdpcCode& code) {
     }
 
     L.inf_slot = L.kpad;
-    L.tot_words = L.kpad + 4;
+    L.tot_words = L.kpad + 32;    // + one +INF word per bank
     L.scratch_slot = L.dv * L.kpad;
     L.msg_words = L.dv * L.kpad + 32;
     L.cn_ninfo.assign(L.threads, 0);
@@ -363,10 +363,31 @@ LdpcLayout make_ldpc_layout(const LdpcCode& code) {
             L.cn_rd[static_cast<size_t>(e_slot) * L.threads + p] = static_cast<uint16_t>(a);
             L.cn_wr[static_cast<size_t>(e_slot) * L.threads + p] = static_cast<uint16_t>(rank[chk][e_row] * L.kpad + a);
         };
-        for (const Ref& r : placed) emit(r.p, r.e_row, col.colour[r.id]);
+        std::vector<char> real(static_cast<size_t>(kMaxInfoEdgesPerCheck) * 32, 0);
+        std::vector<unsigned> used(kMaxInfoEdgesPerCheck, 0u);       // banks touched by the real edges of instruction slot e
+        auto emit_real = [&](int p, int e_row, int e_slot) {
+            emit(p, e_row, e_slot);
+            real[static_cast<size_t>(e_slot) * 32 + (p - p0)] = 1;
+            used[e_slot] |= 1u << (L.cn_rd[static_cast<size_t>(e_slot) * L.threads + p] & 31);
+        };
+        for (const Ref& r : placed) emit_real(r.p, r.e_row, col.colour[r.id]);
         for (const Ref& r : deferred) {
-            emit(r.p, r.e_row, col.add_conflicting(r.p - p0));
+            emit_real(r.p, r.e_row, col.add_conflicting(r.p - p0));
             ++L.conflicts;
+        }
+        // absent edges (rows shorter than the warp's longest, lanes past the last check) read a +INF word and write a
+        // scratch word in a bank that no real edge of the same instruction uses; all of them share one address, so
+        // they add no shared-memory wavefront
+        for (int e = 0; e < ne_w[w] && e < kMaxInfoEdgesPerCheck; ++e) {
+            int fb = -1;
+            for (int b = 0; b < 32; ++b)
+                if (!(used[e] & (1u << b))) { fb = b; break; }
+            if (fb < 0) continue;
+            for (int lane = 0; lane < 32 && p0 + lane < L.threads; ++lane) {
+                if (real[static_cast<size_t>(e) * 32 + lane]) continue;
+                L.cn_rd[static_cast<size_t>(e) * L.threads + p0 + lane] = static_cast<uint16_t>(L.inf_slot + fb);
+                L.cn_wr[static_cast<size_t>(e) * L.threads + p0 + lane] = static_cast<uint16_t>(L.scratch_slot + fb);
+            }
         }
     }
     for (int p = 0; p < m; ++p) {

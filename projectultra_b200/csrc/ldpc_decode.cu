@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(T, MINB) ldpc_flood_reg_kernel(LdpcRegDev t, c
         }
     }
     for (int i = tid; i < kMsgWords; i += T) msg[i] = 0.0f;   // absent variable-side edges stay +0 forever
-    if (tid == 0) tot[KP] = INFINITY;                          // LdpcLayout::inf_slot
+    if (tid < 32) tot[KP + tid] = INFINITY;                    // LdpcLayout::inf_slot: one +INF word per bank
     __syncthreads();
 
     int it = 0, converged = 0;

@@ -73,6 +73,22 @@ __device__ __forceinline__ void fft_pass_smem(float2* buf, int gid, const float2
     for (int q = 0; q < (1 << R); ++q) buf[PADIDX(base + (q << S0))] = v[q];
 }
 
+// ---- warp-granular variant (WARPG): one warp walks one frame; the FFT is the two-pass register FFT of ofdm_diff.cu
+//      (pass A: N/32 elements per lane, log2(N/32) stages; one padded shared-memory transpose; pass B pruned to the
+//      bins within +-CW of DC), every butterfly still the reference's unfused (t = w*b, a+t, a-t) in stage order.
+template <int NFFT>
+struct WgGeom {
+    static constexpr int LOG2N = (NFFT == 512) ? 9 : 10;
+    static constexpr int EPL = NFFT / 32;                    // elements per lane
+    static constexpr int LA = (NFFT == 512) ? 4 : 5;         // stages of pass A = in-lane stages of pass B
+    static constexpr int CW = (NFFT == 512) ? 16 : 32;       // pass B: p = c + CW*j (+256*b8 for N = 512)
+    static constexpr int PADSH = (NFFT == 512) ? 4 : 5;      // one float2 of padding per 2^PADSH
+    static constexpr int BUF = NFFT + (NFFT >> PADSH);       // float2 per warp
+};
+struct WgTw { float2 a[16]; };                               // pass-A twiddles tw[32 m] (N = 512) / tw[32 m] (N = 1024: tw[(N/32) m])
+__device__ __forceinline__ float2 wg_lo(float2 a, float2 b, float2 w) { return cadd(a, cmul(w, b)); }
+__device__ __forceinline__ float2 wg_hi(float2 a, float2 b, float2 w) { return csub(a, cmul(w, b)); }
+
 struct RxShared {
     float2 Hd[kMaxCarr];      // channel_estimate at data carriers
     float2 Hp[kMaxCarr];      // channel_estimate at pilot carriers
@@ -95,25 +111,51 @@ struct RxShared {
     float rot_next;
 };
 
-template <int NFFT>
-__global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
-    OfdmDev d, const float* __restrict__ samples, size_t frame_stride, int n_symbols, int training,
+// WARPG = false: one frame per CTA of NFFT/8 threads (debug dumps, carrier layouts the warp FFT does not cover).
+// WARPG = true:  one frame per WARP, blockDim.x / 32 frames per CTA, no CTA-wide barrier anywhere: the serial tracker
+//                sections and the HBM latency of a frame's next symbol only stall that frame's warp.
+#define PU_GSYNC() do { if constexpr (WARPG) __syncwarp(); else __syncthreads(); } while (0)
+template <int NFFT, bool WARPG>
+__global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, WARPG ? 5 : 1) ofdm_presynced_kernel(
+    OfdmDev d, WgTw twa, const float* __restrict__ samples, size_t frame_stride, size_t B, int n_symbols, int training,
     const float* __restrict__ cfo_hz, const float* __restrict__ cfo_phase,
     float* __restrict__ llr_out, size_t llr_stride, int llr_limit,
-    float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out, float* __restrict__ dbg) {
+    float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out, float* __restrict__ dbg, unsigned group_bytes) {
     constexpr int LOG2N = (NFFT == 512) ? 9 : 10;
-    constexpr int T = NFFT / 8;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* buf = reinterpret_cast<float2*>(smem_raw);                       // [NFFT + NFFT/8]
-    float* theta = reinterpret_cast<float*>(buf + NFFT + NFFT / 8);          // [sym_len] rotator phases
-    RxShared& S = *reinterpret_cast<RxShared*>(theta + ((d.sym_len + 3) & ~3));
-    const int tid = threadIdx.x;
-    const size_t frame = blockIdx.x;
+    constexpr int T = WARPG ? 32 : NFFT / 8;
+    using G = WgGeom<NFFT>;
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int tid = WARPG ? static_cast<int>(threadIdx.x & 31) : static_cast<int>(threadIdx.x);
+    const int wig = WARPG ? static_cast<int>(threadIdx.x >> 5) : 0;
+    const size_t frame = WARPG ? static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + wig : blockIdx.x;
+    if (WARPG && frame >= B) return;     // whole warps leave; no CTA-wide barrier follows
+    unsigned char* smem_raw = smem_all + static_cast<size_t>(wig) * group_bytes;
+    // CTA mode: [NFFT + NFFT/8] FFT buffer, then [sym_len] rotator phases.  Warp mode: [BUF] transpose buffer (its first
+    // NFFT entries double as the buffer of rotated samples), then the [2 CW] bins around DC; phases stay in registers.
+    float2* buf = reinterpret_cast<float2*>(smem_raw);
+    float* theta = reinterpret_cast<float*>(buf + NFFT + NFFT / 8);
+    float2* binbuf = buf + G::BUF;
+    RxShared& S = WARPG ? *reinterpret_cast<RxShared*>(binbuf + 2 * G::CW)
+                        : *reinterpret_cast<RxShared*>(theta + ((d.sym_len + 3) & ~3));
     const float* x = samples + frame * frame_stride;
     const int nd = d.n_data, np = d.n_pilot, nu = nd + np;
     const bool differential = (d.mod == PU_MOD_DBPSK || d.mod == PU_MOD_DQPSK || d.mod == PU_MOD_D8PSK);
-    const float kPiF_dbl_2 = 0.0f;
-    (void)kPiF_dbl_2;
+
+    // warp FFT: per-lane twiddles of pass B (loop invariant)
+    const int lane = tid;
+    const int wc = lane & (G::CW - 1);
+    const int wb8 = (NFFT == 512) ? (lane >> 4) : 0;
+    const int rlane = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);
+    float2 wl[G::LA], wh[G::LA], wlast = make_float2(0.0f, 0.0f);
+    if constexpr (WARPG) {
+#pragma unroll
+        for (int q = 0; q < G::LA; ++q) {
+            const int sh = LOG2N - (G::LA + 1 + q);
+            wl[q] = __ldg(&d.twiddle[wc << sh]);
+            wh[q] = __ldg(&d.twiddle[(wc + G::CW * ((1 << q) - 1)) << sh]);
+        }
+        if (NFFT == 512) wlast = __ldg(&d.twiddle[wb8 ? (wc + 240) : wc]);
+    }
 
     if (tid == 0) {
         const float f = cfo_hz ? cfo_hz[frame] : 0.0f;
@@ -137,7 +179,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
         S.preveq[i] = make_float2(1.0f, 0.0f);   // differential reference (1,0): channel_equalizer.cpp:300, demodulator.cpp:251-255
         S.tmpc[i] = make_float2(0.0f, 0.0f);     // h_sum_pilot accumulator during the LTS phase
     }
-    __syncthreads();
+    PU_GSYNC();
 
     int llr_pos = 0;   // LLRs emitted so far (same for all threads)
     for (int s = 0; s < n_symbols; ++s) {
@@ -152,87 +194,201 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
         // true successor computed by that thread restarts it.  Every accepted value is thus the reference's value by
         // induction, at ~sym_len / T rounds instead of sym_len dependent additions on one thread.
         const bool rot = fabsf(S.cfo_hz) > 0.01f;
-        if (rot) {
-            const float inc = static_cast<float>(__ddiv_rn(__dmul_rn(-2.0f * 3.14159265358979323846, (double)S.cfo_hz), (double)d.sample_rate));
+        const float rot_inc = static_cast<float>(__ddiv_rn(__dmul_rn(-2.0f * 3.14159265358979323846, (double)S.cfo_hz), (double)d.sample_rate));
+        auto rot_step = [&](float ph) {
             const float pi_hi = 3.14159274101257324f;   // smallest float > M_PI: (double)ph > M_PI  <=>  ph >= pi_hi
-            auto step = [&](float ph) {
-                ph = __fadd_rn(ph, inc);
-                if (ph >= pi_hi) ph = static_cast<float>((double)ph - 2.0f * 3.14159265358979323846);
-                else if (ph <= -pi_hi) ph = static_cast<float>((double)ph + 2.0f * 3.14159265358979323846);
-                return ph;
-            };
+            ph = __fadd_rn(ph, rot_inc);
+            if (ph >= pi_hi) ph = static_cast<float>((double)ph - 2.0f * 3.14159265358979323846);
+            else if (ph <= -pi_hi) ph = static_cast<float>((double)ph + 2.0f * 3.14159265358979323846);
+            return ph;
+        };
+        if (!WARPG && rot) {
             float ph = S.rot_phase;
             for (int i = 0; i < d.sym_len;) {
                 const unsigned b0 = __float_as_uint(ph);
-                const unsigned delta = __float_as_uint(step(ph)) - b0;
+                const unsigned delta = __float_as_uint(rot_step(ph)) - b0;
                 const float cand = __uint_as_float(b0 + static_cast<unsigned>(tid) * delta);
-                const float nxt = step(cand);
+                const float nxt = rot_step(cand);
                 const bool broken = __float_as_uint(nxt) != b0 + static_cast<unsigned>(tid + 1) * delta;
                 const unsigned bal = __ballot_sync(0xffffffffu, broken);
                 if ((tid & 31) == 0) S.rot_fail[tid >> 5] = bal ? (tid + __ffs(bal) - 1) : T;
-                __syncthreads();
+                PU_GSYNC();
                 int f = T;
 #pragma unroll
                 for (int w = 0; w < T / 32; ++w) f = min(f, S.rot_fail[w]);
                 const int nvalid = min(f < T ? f + 1 : T, d.sym_len - i);    // c_0 .. c_f are the reference's values
                 if (tid < nvalid) theta[i + tid] = cand;
                 if (tid == nvalid - 1) S.rot_next = nxt;                      // true successor of the last accepted value
-                __syncthreads();
+                PU_GSYNC();
                 ph = S.rot_next;
                 i += nvalid;
             }
             if (tid == 0) S.rot_phase = ph;
         }
         if (tid == 0) S.cfo_used = S.cfo_hz;
-        __syncthreads();
+        PU_GSYNC();
         const bool skip_fft = is_train && np == 0 && s != training - 1;   // data H uses the LAST LTS symbol only (:179-185)
-        if (!skip_fft) {
-            // ---------------- mix + stages 1..3: group g owns bit-reversed positions 8g..8g+7 = samples brev(8g+q)
-            {
-                const int g = tid;
-                const int r = __brev(static_cast<unsigned>(g)) >> (32 - (LOG2N - 3));
-                float2 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int brq = ((q & 1) << 2) | (q & 2) | ((q >> 2) & 1);
-                    const int n = d.cp + (brq << (LOG2N - 3)) + r;
-                    const float xv = __ldg(&xs[n]);
-                    const float2 o = __ldg(&nco[n]);
-                    float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
-                    if (rot) {
-                        float sn, cs;
-                        refmath::sincosf_ref(theta[n], &sn, &cs);
-                        z = cmul(z, make_float2(cs, sn));                               // mixed *= correction (:42)
+        if constexpr (WARPG) {
+            constexpr int EPL = G::EPL, LA = G::LA, CW = G::CW;
+            float2* zbuf = buf;                                   // [NFFT] rotated samples in natural order (rot only)
+            if (rot) {
+                // ---------------- rotator (channel_equalizer.cpp:23,39-51): the per-sample recurrence walked 32 samples at a
+                //   time with the bit-for-bit link check described above; lane t of a window holds the phase of sample
+                //   base + t and mixes that sample itself, so the phases never leave registers.
+                float ph = S.rot_phase;
+                auto window = [&](int len) {                      // phases of the next len (<= 32) samples; advances ph
+                    float mine = 0.0f;
+                    int done = 0;
+                    while (done < len) {
+                        const unsigned b0 = __float_as_uint(ph);
+                        const unsigned delta = __float_as_uint(rot_step(ph)) - b0;
+                        const int t = lane - done;
+                        const float cand = __uint_as_float(b0 + static_cast<unsigned>(t) * delta);
+                        const float nxt = rot_step(cand);
+                        const bool inside = t >= 0 && lane < len;
+                        const bool broken = inside && __float_as_uint(nxt) != b0 + static_cast<unsigned>(t + 1) * delta;
+                        const unsigned bal = __ballot_sync(0xffffffffu, broken);
+                        const int last = bal ? (__ffs(bal) - 1) : (len - 1);      // lane of the last accepted value
+                        if (inside && lane <= last) mine = cand;
+                        ph = __shfl_sync(0xffffffffu, nxt, last);                  // its true successor restarts the chain
+                        done = last + 1;
                     }
-                    v[q] = z;
+                    return mine;
+                };
+                for (int i = 0; i < d.cp; i += 32) (void)window(min(32, d.cp - i));
+                for (int m = 0; m < NFFT / 32; ++m) {
+                    const float th = window(32);
+                    if (!skip_fft) {
+                        const int n = d.cp + 32 * m + lane;
+                        const float xv = __ldg(&xs[n]);
+                        const float2 o = __ldg(&nco[n]);
+                        float sn, cs;
+                        refmath::sincosf_ref(th, &sn, &cs);
+                        const float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
+                        zbuf[32 * m + lane] = cmul(z, make_float2(cs, sn));                       // mixed *= correction (:42)
+                    }
                 }
-                stages_in_regs<3, 0, LOG2N>(v, 0, d.twiddle);
+                for (int i = d.cp + NFFT; i < d.sym_len; i += 32) (void)window(min(32, d.sym_len - i));
+                if (lane == 0) S.rot_phase = ph;
+                __syncwarp();
+            }
+            if (!skip_fft) {
+                // ---------------- pass A: lane g owns bit-reversed positions EPL g .. EPL g + EPL-1 = samples brev5(g) + 32 brev(q)
+                float2 v[EPL];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) buf[PADIDX(8 * g + q)] = v[q];
+                for (int q = 0; q < EPL; ++q) {
+                    const int brq = static_cast<int>(__brev(static_cast<unsigned>(q)) >> (32 - LA));
+                    const int n = rlane + 32 * brq;
+                    if (rot) {
+                        v[q] = zbuf[n];
+                    } else {
+                        const float xv = __ldg(&xs[d.cp + n]);
+                        const float2 o = __ldg(&nco[d.cp + n]);
+                        v[q] = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));               // samples[i] * conj(osc) (:36)
+                    }
+                }
+#pragma unroll
+                for (int t = 1; t <= LA; ++t) {
+                    const int half = 1 << (t - 1);
+#pragma unroll
+                    for (int pr = 0; pr < EPL / 2; ++pr) {
+                        const int kq = pr & (half - 1);
+                        const int a = ((pr >> (t - 1)) << t) | kq;
+                        butterfly(v[a], v[a + half], twa.a[kq << (LA - t)]);
+                    }
+                }
+                __syncwarp();                                       // zbuf has been read by every lane
+#pragma unroll
+                for (int q = 0; q < EPL; ++q) {
+                    const int p = EPL * lane + q;
+                    buf[p + (p >> G::PADSH)] = v[q];
+                }
+                __syncwarp();
+                // ---------------- pass B: lane (b8, c) owns p = c + CW j (+ 256 b8); pruned to the outputs at j = 0 and j = EPL-1
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    const int p = wc + CW * j + 256 * wb8;
+                    v[j] = buf[p + (p >> G::PADSH)];
+                }
+#pragma unroll
+                for (int j = 0; j < EPL; j += 2) butterfly(v[j], v[j + 1], wl[0]);
+#pragma unroll
+                for (int q = 1; q < LA; ++q) {
+                    const int step = 1 << (q + 1), hh = 1 << q;
+#pragma unroll
+                    for (int j = 0; j < EPL; j += step) {
+                        v[j] = wg_lo(v[j], v[j + hh], wl[q]);
+                        v[j + step - 1] = wg_hi(v[j + step - 1 - hh], v[j + step - 1], wh[q]);
+                    }
+                }
+                if (NFFT == 512) {
+                    // stage 9 pairs lane (0,c) with lane (1,c): bin c = A0 + w B0 on lane (0,c); bin 496 + c = A15 - w B15 on lane (1,c)
+                    const float2 send = wb8 ? v[0] : v[EPL - 1];
+                    float2 recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+                    binbuf[lane] = wb8 ? wg_hi(recv, v[EPL - 1], wlast) : wg_lo(v[0], recv, wlast);
+                } else {
+                    binbuf[wc] = v[0];                              // bin c
+                    binbuf[CW + wc] = v[EPL - 1];                   // bin N - CW + c
+                }
+                __syncwarp();
+                for (int u = tid; u < nu; u += T) {
+                    const int bin = u < nd ? d.data_bin[u] : d.pilot_bin[u - nd];
+                    const float2 out = binbuf[bin < NFFT / 2 ? bin : bin - NFFT + 2 * CW];
+                    if (u < nd) S.Fd[u] = out;
+                    else S.Fp[u - nd] = out;
+                }
             }
-            __syncthreads();
-            fft_pass_smem<3, 3, LOG2N>(buf, tid, d.twiddle);     // stages 4..6
-            __syncthreads();
-            if constexpr (NFFT == 512) {
-                fft_pass_smem<2, 6, LOG2N>(buf, tid, d.twiddle);          // stages 7..8: 128 groups of 4
-                fft_pass_smem<2, 6, LOG2N>(buf, tid + T, d.twiddle);
-            } else {
-                fft_pass_smem<3, 6, LOG2N>(buf, tid, d.twiddle);          // stages 7..9
-            }
-            __syncthreads();
-            // ---------------- last stage, only for the bins that are used
-            for (int u = tid; u < nu; u += T) {
-                const int bin = u < nd ? d.data_bin[u] : d.pilot_bin[u - nd];
-                const int k = bin & (NFFT / 2 - 1);
-                const float2 w = __ldg(&d.twiddle[k]);
-                const float2 a = buf[PADIDX(k)];
-                const float2 t = cmul(w, buf[PADIDX(k + NFFT / 2)]);
-                const float2 out = (bin < NFFT / 2) ? cadd(a, t) : csub(a, t);
-                if (u < nd) S.Fd[u] = out;
-                else S.Fp[u - nd] = out;
+        } else {
+            if (!skip_fft) {
+                // ---------------- mix + stages 1..3: group g owns bit-reversed positions 8g..8g+7 = samples brev(8g+q)
+                {
+                    const int g = tid;
+                    const int r = __brev(static_cast<unsigned>(g)) >> (32 - (LOG2N - 3));
+                    float2 v[8];
+    #pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int brq = ((q & 1) << 2) | (q & 2) | ((q >> 2) & 1);
+                        const int n = d.cp + (brq << (LOG2N - 3)) + r;
+                        const float xv = __ldg(&xs[n]);
+                        const float2 o = __ldg(&nco[n]);
+                        float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
+                        if (rot) {
+                            float sn, cs;
+                            refmath::sincosf_ref(theta[n], &sn, &cs);
+                            z = cmul(z, make_float2(cs, sn));                               // mixed *= correction (:42)
+                        }
+                        v[q] = z;
+                    }
+                    stages_in_regs<3, 0, LOG2N>(v, 0, d.twiddle);
+    #pragma unroll
+                    for (int q = 0; q < 8; ++q) buf[PADIDX(8 * g + q)] = v[q];
+                }
+                PU_GSYNC();
+                fft_pass_smem<3, 3, LOG2N>(buf, tid, d.twiddle);     // stages 4..6
+                PU_GSYNC();
+                if constexpr (NFFT == 512) {
+                    fft_pass_smem<2, 6, LOG2N>(buf, tid, d.twiddle);          // stages 7..8: 128 groups of 4
+                    fft_pass_smem<2, 6, LOG2N>(buf, tid + T, d.twiddle);
+                } else {
+                    fft_pass_smem<3, 6, LOG2N>(buf, tid, d.twiddle);          // stages 7..9
+                }
+                PU_GSYNC();
+                // ---------------- last stage, only for the bins that are used
+                for (int u = tid; u < nu; u += T) {
+                    const int bin = u < nd ? d.data_bin[u] : d.pilot_bin[u - nd];
+                    const int k = bin & (NFFT / 2 - 1);
+                    const float2 w = __ldg(&d.twiddle[k]);
+                    const float2 a = buf[PADIDX(k)];
+                    const float2 t = cmul(w, buf[PADIDX(k + NFFT / 2)]);
+                    const float2 out = (bin < NFFT / 2) ? cadd(a, t) : csub(a, t);
+                    if (u < nd) S.Fd[u] = out;
+                    else S.Fp[u - nd] = out;
+                }
             }
         }
-        __syncthreads();
+        PU_GSYNC();
 
         if (is_train) {
             // ---------------- estimateChannelFromLTS (channel_equalizer.cpp:137-194)
@@ -243,11 +399,11 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     S.tmpc[i] = cadd(S.tmpc[i], make_float2(__fmul_rn(S.Fp[i].x, d.pilot_sign[i]), __fmul_rn(S.Fp[i].y, d.pilot_sign[i])));
             }
             if (s == training - 1) {
-                __syncthreads();
+                PU_GSYNC();
                 const float inv = __fdiv_rn(1.0f, static_cast<float>(training));
                 for (int i = tid; i < np; i += T) S.Hp[i] = cscale(inv, S.tmpc[i]);
                 for (int i = tid; i < nd; i += T) S.tmpa[i] = cabs_ref(S.Hd[i]);
-                __syncthreads();
+                PU_GSYNC();
                 if (tid == 0) {   // reporting-only SNR estimate (:208-225)
                     float sum = 0.0f;
                     for (int i = 0; i < nd; ++i) sum = __fadd_rn(sum, S.tmpa[i]);
@@ -257,7 +413,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     S.snr_cnt = training;   // :327
                 }
             }
-            __syncthreads();
+            PU_GSYNC();
             continue;
         }
 
@@ -267,7 +423,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
             const float alpha = (S.snr_cnt == 0) ? 1.0f : 0.9f;
             for (int i = tid; i < np; i += T)
                 S.hls[i] = make_float2(__fmul_rn(S.Fp[i].x, d.pilot_sign[i]), __fmul_rn(S.Fp[i].y, d.pilot_sign[i]));
-            __syncthreads();
+            PU_GSYNC();
             if (tid == 0 && !S.cpc_init) {   // carrier phase lock on the first data symbol (:348-357)
                 float2 sum = make_float2(0.0f, 0.0f);
                 for (int i = 0; i < np; ++i) sum = cadd(sum, S.hls[i]);
@@ -278,7 +434,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     S.cpc_init = 1;
                 }
             }
-            __syncthreads();
+            PU_GSYNC();
             const int have_prev = S.have_prev;
             for (int i = tid; i < np; i += T) {
                 const float2 h = cmul(S.hls[i], S.cpc);   // :360-362
@@ -310,7 +466,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                 S.Hp[i] = cadd(cscale(alpha, h), cscale(__fsub_rn(1.0f, alpha), hold));   // EMA (:410-411)
                 if (S.snr_cnt >= 3 && nh >= 1e-6f) S.tmpd[i] = refmath::atan2f_ref(h.y, h.x);          // std::arg for the timing fit (:483)
             }
-            __syncthreads();
+            PU_GSYNC();
             if (tid == 0) {
                 float sp_sum = 0.0f;
                 for (int i = 0; i < np; ++i) sp_sum = __fadd_rn(sp_sum, S.tmpa[i]);
@@ -384,7 +540,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                 S.snr_cnt++;
             }
             for (int i = tid; i < np; i += T) S.prevp[i] = S.hls[i];   // :512
-            __syncthreads();
+            PU_GSYNC();
             // coherent timing fix, interpolation, timing restore (:514-567, :601-631)
             const float timing = S.timing;
             const bool fix = !differential && fabsf(timing) > 0.1f;
@@ -397,7 +553,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     refmath::sincosf_ref(-tp, &sn, &cs);                 // std::exp(Complex(0, -timing_phase))
                     S.Hp[i] = cmul(S.Hp[i], make_float2(cs, sn));
                 }
-                __syncthreads();
+                PU_GSYNC();
             }
             for (int i = tid; i < nd; i += T) {
                 const int lo = d.interp_lo[i], hi = d.interp_hi[i];
@@ -415,7 +571,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                 }
             }
             if (fix) {
-                __syncthreads();
+                PU_GSYNC();
                 for (int u = tid; u < nu; u += T) {
                     int k = u < nd ? d.data_bin[u] : d.pilot_bin[u - nd];
                     if (k > NFFT / 2) k -= NFFT;
@@ -426,7 +582,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     else S.Hp[u - nd] = cmul(S.Hp[u - nd], make_float2(cs, sn));
                 }
             }
-            __syncthreads();
+            PU_GSYNC();
         }
 
         // ---------------- equalize (channel_equalizer.cpp:728-840)
@@ -472,18 +628,18 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
                     S.cnv[i] = clampf(1e-6f, 100.0f, __fdiv_rn(noise_var, __fadd_rn(hp, 1e-6f)));
                 }
             }
-            __syncthreads();
+            PU_GSYNC();
             if (tid == 0) {   // deep-fade erasure threshold (:823-830): ordered sum
                 float sum = 0.0f;
                 for (int i = 0; i < nd; ++i) sum = __fadd_rn(sum, S.tmpa[i]);
                 S.tmpb[0] = __fmul_rn(0.1f, __fdiv_rn(sum, static_cast<float>(nd)));
             }
-            __syncthreads();
+            PU_GSYNC();
             const float thr = S.tmpb[0];
             for (int i = tid; i < nd; i += T)
                 if (S.tmpa[i] < thr) S.cnv[i] = 100.0f;
         }
-        __syncthreads();
+        PU_GSYNC();
 
         // ---------------- debug dump of this symbol's intermediates (tests only)
         if (dbg) {
@@ -625,7 +781,7 @@ __global__ void __launch_bounds__(NFFT / 8) ofdm_presynced_kernel(
             }
         }
         llr_pos += nd * d.bps;
-        __syncthreads();
+        PU_GSYNC();
     }
     if (tid == 0) {
         if (snr_db_out) snr_db_out[frame] = 10.0f * log10f(S.snr_lin);   // getEstimatedSNR, demodulator.cpp:797-799
@@ -800,16 +956,49 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         PU_CUDA_TRY(e);
         return PU_OK;
     }
+    pu::WgTw twa;
+    for (int m = 0; m < 16; ++m) {
+        const pu::cfloat w = (32 * m < p.nfft / 2) ? p.twiddle[32 * m] : pu::cfloat(0.0f, 0.0f);
+        twa.a[m] = make_float2(w.real(), w.imag());
+    }
+    // Warp-granular variant (one frame per warp): needs every used bin within +-CW of DC (the pruned pass B of the warp FFT)
+    static const bool no_warpg = getenv("PU_OFDM_NO_WARPG") != nullptr;   // A/B switch for tests and profiling
+    const int cw = p.nfft == 512 ? 16 : 32;
+    bool near_dc = true;
+    for (int b : p.data_bin) near_dc = near_dc && ((b >= 1 && b < cw) || b > p.nfft - cw);
+    for (int b : p.pilot_bin) near_dc = near_dc && ((b >= 1 && b < cw) || b > p.nfft - cw);
+    if (!d_dbg && !no_warpg && near_dc) {
+        const int warps = p.nfft == 512 ? 4 : 3;
+        const size_t buf_f2 = static_cast<size_t>(p.nfft + (p.nfft >> (p.nfft == 512 ? 4 : 5)) + 2 * cw);
+        const unsigned group = static_cast<unsigned>((buf_f2 * sizeof(float2) + sizeof(pu::RxShared) + 15) & ~size_t(15));
+        const unsigned wgrid = static_cast<unsigned>((B + warps - 1) / warps);
+        static bool attrw = false;
+        if (!attrw) {
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+            attrw = true;
+        }
+        if (p.nfft == 512)
+            pu::ofdm_presynced_kernel<512, true><<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(
+                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group);
+        else
+            pu::ofdm_presynced_kernel<1024, true><<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(
+                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group);
+        h->last_kernel = 4;
+        h->ctx->launches.fetch_add(1);
+        PU_CUDA_TRY(cudaGetLastError());
+        return PU_OK;
+    }
     if (p.nfft == 512) {
         static bool attr512 = false;
-        if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
-        pu::ofdm_presynced_kernel<512><<<grid, 64, h->smem_bytes, st>>>(h->dev, d_samples, L, n_symbols, training, d_cfo, d_phase,
-                                                                     d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg);
+        if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
+        pu::ofdm_presynced_kernel<512, false><<<grid, 64, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
+                                                                            d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u);
     } else {
         static bool attr1024 = false;
-        if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
-        pu::ofdm_presynced_kernel<1024><<<grid, 128, h->smem_bytes, st>>>(h->dev, d_samples, L, n_symbols, training, d_cfo, d_phase,
-                                                                       d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg);
+        if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
+        pu::ofdm_presynced_kernel<1024, false><<<grid, 128, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
+                                                                              d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u);
     }
     h->last_kernel = 1;
     h->ctx->launches.fetch_add(1);

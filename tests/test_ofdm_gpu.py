@@ -221,7 +221,7 @@ def test_warp_fft_kernel_is_bit_identical(ctx, preset, mod):
         fast, fsnr, fcfo = dem.presynced_batch(x, training, llr_stride=stride)
         fast_kernel = dem.last_kernel
         gen, gsnr, gcfo = dem.presynced_batch(x, training, zeros, zeros, llr_stride=stride)
-        assert dem.last_kernel == "ofdm_presynced_kernel"
+        assert dem.last_kernel in ("ofdm_presynced_kernel", "ofdm_presynced_warp_kernel")
         if training != 2:
             assert fast_kernel in ("ofdm_diff512_kernel", "ofdm_diff_kernel", "ofdm_presynced_kernel")
         elif preset == "m1" and mod != R.DBPSK and Lcut % 4 == 0:
@@ -248,3 +248,39 @@ def test_warp_fft_kernel_is_bit_identical(ctx, preset, mod):
     b, _, _ = dem.presynced_batch(frames, 2, zeros, zeros, llr_stride=648)
     dem.set_deinterleave(0)
     assert same_bits(a, b)
+
+
+@pytest.mark.parametrize("preset", ["m1", "m3"])
+@pytest.mark.parametrize("mod", MODS)
+def test_warp_granular_kernel_matches_cta_kernel(ctx, preset, mod):
+    """The batch entry point runs the general presynced path one frame per warp (ofdm_demod.cu, WARPG: warp FFT, rotator phases
+    in registers, no CTA barrier); the debug entry point runs the same path one frame per CTA.  Every LLR word, the SNR
+    report and the tracked CFO must agree bit for bit -- with and without pilots, with zero and non-zero CFO (rotator on
+    from the first symbol), with tracked CFO (rotator switching on mid-frame), for ragged batches and lengths."""
+    from projectultra_b200 import capi
+    rate = R.R1_2 if preset == "m1" else R.R3_4
+    cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    nbytes = 40 if preset == "m1" else 60
+    frames = [make_frame(cfg, rate, nbytes, snr, 7000 + mod * 40 + i)[0] for i, snr in enumerate(np.linspace(0, 32, 9))]
+    frames.append(np.zeros_like(frames[0]))
+    frames.append(frames[2] * np.float32(1e-4))
+    frames = np.stack(frames).astype(np.float32)
+    B, L = frames.shape
+    S = cfg.symbol_samples
+    rng = np.random.default_rng(mod)
+    for cfo, ph, Lcut, training in ((np.zeros(B, np.float32), np.zeros(B, np.float32), L, 2),
+                                    (rng.uniform(-25, 25, B).astype(np.float32), rng.uniform(-3, 3, B).astype(np.float32), L, 2),
+                                    (rng.uniform(-0.02, 0.02, B).astype(np.float32), np.zeros(B, np.float32), L - S - 5, 2),
+                                    (rng.uniform(-60, 60, B).astype(np.float32), rng.uniform(-3, 3, B).astype(np.float32), L, 1)):
+        x = np.ascontiguousarray(frames[:, :Lcut])
+        n = dem.n_llr(Lcut, training)
+        if n == 0:
+            continue
+        llr, snr, fc = dem.presynced_batch(x, training, cfo, ph)
+        assert dem.last_kernel == "ofdm_presynced_warp_kernel"
+        for b in range(B):
+            dbg = dem.presynced_debug(x[b], training, float(cfo[b]), float(ph[b]))
+            assert same_bits(llr[b, :n], dbg["llr"][:n]), (b, float(cfo[b]), Lcut, training)
+            if dbg["n_sym"]:
+                assert same_bits(fc[b:b + 1], dbg["scalars"][-1, 1:2]), (b, "tracked CFO")
