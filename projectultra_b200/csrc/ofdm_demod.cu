@@ -34,6 +34,16 @@
 
 namespace pu {
 
+// Out-of-line copies of the libm restatements: the kernel calls them from 16 places, and inlining every copy made the
+// warp-granular kernel 14 000 instructions long -- with each warp in a different phase of its frame the instruction
+// cache thrashed (r11: 4.4 "no instruction" stall cycles per issued instruction).
+namespace nl {
+static __device__ __noinline__ float atan2f_ref(float y, float x) { return refmath::atan2f_ref(y, x); }
+static __device__ __noinline__ float sinf_ref(float x) { return refmath::sinf_ref(x); }
+static __device__ __noinline__ float cosf_ref(float x) { return refmath::cosf_ref(x); }
+static __device__ __noinline__ void sincosf_ref(float x, float* s, float* c) { *s = refmath::sinf_ref(x); *c = refmath::cosf_ref(x); }
+}  // namespace nl
+
 #define PADIDX(p) ((p) + ((p) >> 3))   // one float2 of padding per 8 keeps the strided passes off the same banks
 
 __device__ __forceinline__ void butterfly(float2& a, float2& b, float2 w) {
@@ -186,6 +196,13 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
         const bool is_train = s < training;
         const float* xs = x + static_cast<size_t>(s) * d.sym_len;
         const float2* nco = d.nco + static_cast<size_t>(s) * d.sym_len;
+        if constexpr (WARPG) {
+            // the warp waits on nothing but its own loads: pull the NEXT symbol's samples into L2 while this one is processed
+            if (s + 1 < n_symbols) {
+                const char* nx = reinterpret_cast<const char*>(xs + d.sym_len);
+                for (int off = tid * 128; off < d.sym_len * 4; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
+            }
+        }
         // ---------------- rotator phases (channel_equalizer.cpp:23,39-51): a per-sample float recurrence
         //   theta[i] = ph;  ph = wrap(fl(ph + inc)).
         // Run T samples at a time: while ph stays in one binade every step adds the same number of ulps, so the next T
@@ -263,7 +280,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                         const float xv = __ldg(&xs[n]);
                         const float2 o = __ldg(&nco[n]);
                         float sn, cs;
-                        refmath::sincosf_ref(th, &sn, &cs);
+                        nl::sincosf_ref(th, &sn, &cs);
                         const float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
                         zbuf[32 * m + lane] = cmul(z, make_float2(cs, sn));                       // mixed *= correction (:42)
                     }
@@ -356,7 +373,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                         float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
                         if (rot) {
                             float sn, cs;
-                            refmath::sincosf_ref(theta[n], &sn, &cs);
+                            nl::sincosf_ref(theta[n], &sn, &cs);
                             z = cmul(z, make_float2(cs, sn));                               // mixed *= correction (:42)
                         }
                         v[q] = z;
@@ -464,7 +481,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                 S.tmpc[i] = unit;
                 const float2 hold = S.Hp[i];
                 S.Hp[i] = cadd(cscale(alpha, h), cscale(__fsub_rn(1.0f, alpha), hold));   // EMA (:410-411)
-                if (S.snr_cnt >= 3 && nh >= 1e-6f) S.tmpd[i] = refmath::atan2f_ref(h.y, h.x);          // std::arg for the timing fit (:483)
+                if (S.snr_cnt >= 3 && nh >= 1e-6f) S.tmpd[i] = nl::atan2f_ref(h.y, h.x);          // std::arg for the timing fit (:483)
             }
             PU_GSYNC();
             if (tid == 0) {
@@ -483,9 +500,9 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                         if (S.valid[i] & 2) { ps = cadd(ps, S.tmpc[i]); ++vc; }
                     if (vc > 0) {
                         const float2 avg = cdivs(ps, static_cast<float>(vc));
-                        const float apd = refmath::atan2f_ref(avg.y, avg.x);
+                        const float apd = nl::atan2f_ref(avg.y, avg.x);
                         float sn, cs;
-                        refmath::sincosf_ref(-apd, &sn, &cs);
+                        nl::sincosf_ref(-apd, &sn, &cs);
                         S.ppc = make_float2(cs, sn);
                         const float sym_dur = __fdiv_rn(static_cast<float>(d.sym_len), d.sample_rate);
                         const float residual = static_cast<float>(__ddiv_rn((double)apd, __dmul_rn(2.0f * 3.14159265358979323846, (double)sym_dur)));
@@ -550,7 +567,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                     if (k > NFFT / 2) k -= NFFT;
                     const float tp = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(2.0f * 3.14159265358979323846, (double)k), (double)timing), (double)static_cast<float>(NFFT)));
                     float sn, cs;
-                    refmath::sincosf_ref(-tp, &sn, &cs);                 // std::exp(Complex(0, -timing_phase))
+                    nl::sincosf_ref(-tp, &sn, &cs);                 // std::exp(Complex(0, -timing_phase))
                     S.Hp[i] = cmul(S.Hp[i], make_float2(cs, sn));
                 }
                 PU_GSYNC();
@@ -560,7 +577,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                 if (lo >= 0 && hi >= 0) {
                     const float2 H1 = S.Hp[lo], H2 = S.Hp[hi];
                     const float2 pd = cmul(H2, cconj(H1));
-                    const float ph = fabsf(refmath::atan2f_ref(pd.y, pd.x));
+                    const float ph = fabsf(nl::atan2f_ref(pd.y, pd.x));
                     const float a = d.interp_alpha[i];
                     if (ph > 1.5708f) S.Hd[i] = (a < 0.5f) ? H1 : H2;
                     else S.Hd[i] = cadd(cscale(__fsub_rn(1.0f, a), H1), cscale(a, H2));
@@ -577,7 +594,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                     if (k > NFFT / 2) k -= NFFT;
                     const float tp = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(2.0f * 3.14159265358979323846, (double)k), (double)timing), (double)static_cast<float>(NFFT)));
                     float sn, cs;
-                    refmath::sincosf_ref(tp, &sn, &cs);
+                    nl::sincosf_ref(tp, &sn, &cs);
                     if (u < nd) S.Hd[u] = cmul(S.Hd[u], make_float2(cs, sn));
                     else S.Hp[u - nd] = cmul(S.Hp[u - nd], make_float2(cs, sn));
                 }
@@ -599,7 +616,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                 float2 tc = make_float2(1.0f, 0.0f);       // std::exp(Complex(0, 0)) == (1, 0)
                 if (tp != 0.0f) {
                     float sn, cs;
-                    refmath::sincosf_ref(tp, &sn, &cs);
+                    nl::sincosf_ref(tp, &sn, &cs);
                     tc = make_float2(cs, sn);
                 }
                 float2 e;
@@ -677,19 +694,19 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
 #pragma unroll
                 for (int b = 0; b < 3; ++b) l[b] = 0.0f;
                 if (!(sp < 1e-6f)) {
-                    const float phase = refmath::atan2f_ref(df.y, df.x);
+                    const float phase = nl::atan2f_ref(df.y, df.x);
                     if (d.mod == PU_MOD_DBPSK) {              // soft_demap.hpp:173-187
-                        l[0] = clip_llr(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, sp), refmath::cosf_ref(phase)), nv));
+                        l[0] = clip_llr(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, sp), nl::cosf_ref(phase)), nv));
                     } else if (d.mod == PU_MOD_DQPSK) {       // :192-213
                         const float scale = __fdiv_rn(__fmul_rn(2.0f, sp), nv);
                         const float pi = 3.14159265358979f;
-                        l[0] = clip_llr(__fmul_rn(scale, refmath::sinf_ref(__fadd_rn(phase, pi / 4))));
-                        l[1] = clip_llr(__fmul_rn(scale, refmath::cosf_ref(__fmul_rn(2.0f, phase))));
+                        l[0] = clip_llr(__fmul_rn(scale, nl::sinf_ref(__fadd_rn(phase, pi / 4))));
+                        l[1] = clip_llr(__fmul_rn(scale, nl::cosf_ref(__fmul_rn(2.0f, phase))));
                     } else {                                  // D8PSK :217-237
                         const float conf = __fdiv_rn(sp, nv);
-                        l[0] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(phase)));
-                        l[1] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(2.0f, phase))));
-                        l[2] = clip_llr(__fmul_rn(conf, refmath::sinf_ref(__fmul_rn(4.0f, phase))));
+                        l[0] = clip_llr(__fmul_rn(conf, nl::sinf_ref(phase)));
+                        l[1] = clip_llr(__fmul_rn(conf, nl::sinf_ref(__fmul_rn(2.0f, phase))));
+                        l[2] = clip_llr(__fmul_rn(conf, nl::sinf_ref(__fmul_rn(4.0f, phase))));
                     }
                 }
             } else {
