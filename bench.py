@@ -318,8 +318,8 @@ def run_ours(args):
                                % (B * FRAME_SAMPLES * 4 / 1e6)),
                 "info_bits_per_s": value * INFO_BITS, "gpu_launches": int(launches),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (FRAME_SAMPLES + 2) * 4,
-                        "d2h_bytes_per_step": B * (sim.ldpc.info_bytes + 5), "steps": e2e_steps,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * (FRAME_SAMPLES + 2) * 4,
+                        "d2h_bytes_per_step": world * B * (sim.ldpc.info_bytes + 5), "steps": e2e_steps,
                         "api": "pu_receive_decode_batch(PU_MEM_HOST)", "matches_device_path": e2e_matches},
                 "roofline": {"kernel": demod_kernel, "bound": "hbm", "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,

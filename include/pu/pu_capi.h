@@ -150,6 +150,28 @@ PU_API pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_
                                          const float* cfo_hz, const float* cfo_phase, float* llr_out,
                                          size_t llr_stride, float* snr_db, float* final_cfo_hz,
                                          pu_memspace space, void* stream);
+/* ---------------------------------------------------------------- OFDM acquisition (Schmidl-Cox path)
+ * Replaces the SEARCHING state of ultra::OFDMDemodulator::process (src/ofdm/demodulator.cpp:474-600) with
+ * Impl::hasMinimumEnergy / measureSchmidlCoxCorrelation / estimateCoarseCFO / refineLTSTiming
+ * (src/ofdm/ofdm_sync.cpp:20-50,118-163,230-261,386-461) for B frames at once.  Row b of samples[B][L] is what a caller
+ * would feed to process() in `chunk`-sample pieces (tools/test_mode_snr.cpp:65-70: 960); the search is replayed call
+ * by call, so the result is the reference's for that chunking.  sync_info[B][4] = {synchronised (0/1),
+ * getLastSyncOffset(), samples consumed up to the first data symbol, process() calls until sync};
+ * coarse_cfo_hz[B] = the Schmidl-Cox CFO estimate.  sync_threshold <= 0 selects ModemConfig's default 0.80
+ * (include/ultra/types.hpp:188).  PU_ERR_UNSUPPORTED for L > 40000 (the reference would trim its buffer). */
+PU_API pu_status pu_ofdm_acquire_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, size_t chunk,
+                                       float sync_threshold, int32_t* sync_info, float* coarse_cfo_hz,
+                                       pu_memspace space, void* stream);
+/* ultra::OFDMDemodulator::process + getSoftBits (include/ultra/ofdm.hpp:58-127) on whole frames: acquisition as above,
+ * then the SYNCED state (demodulator.cpp:665-690: per-symbol toBaseband / FFT / updateChannelEstimate / equalize /
+ * demodulateSymbol with the coarse CFO, no LTS channel estimate) over every complete symbol after the preamble.
+ * llr_out[B][llr_stride] (caller-zeroed rows; frames without sync stay untouched), n_llr[B] = soft bits available
+ * (capped at llr_stride; < 648 is what the reference's tools count as a lost frame); sync_info / coarse_cfo_hz /
+ * snr_db may be NULL. */
+PU_API pu_status pu_ofdm_process_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, size_t chunk,
+                                       float sync_threshold, float* llr_out, size_t llr_stride, int32_t* n_llr,
+                                       int32_t* sync_info, float* coarse_cfo_hz, float* snr_db,
+                                       pu_memspace space, void* stream);
 /* One frame on HOST memory with per-symbol intermediates for stage-by-stage parity tests.  records holds, per
  * data symbol: bins[n_used] (re,im), channel_estimate[n_used] (re,im), equalized[n_data] (re,im),
  * carrier_noise_var[n_data], then 10 scalars {cfo used to mix, cfo after tracking, noise_variance,

@@ -327,6 +327,35 @@ long ref_ofdm_process(const ref_modem_config* c, const float* samples, size_t L,
     return (long)soft.size();
 }
 
+// Same call sequence, also reporting what acquisition decided: getLastSyncOffset() and getFrequencyOffset() (the
+// Schmidl-Cox coarse CFO; no tracker changes it in the no-pilot differential modes) -- for the GPU acquisition tests.
+long ref_ofdm_process_info(const ref_modem_config* c, const float* samples, size_t L, size_t chunk,
+                           float* llr_out, size_t cap, int* synced, long* sync_offset, float* cfo_hz) {
+    init_once();
+    StderrSilencer quiet;
+    ModemConfig cfg = to_cfg(c);
+    OFDMDemodulator d(cfg);
+    bool ever = false;
+    long off = -1;
+    float cfo = 0.0f;
+    for (size_t i = 0; i < L; i += chunk) {
+        size_t len = std::min(chunk, L - i);
+        d.process(SampleSpan(samples + i, len));
+        if (!ever && d.isSynced()) {
+            ever = true;
+            off = (long)d.getLastSyncOffset();
+            cfo = d.getFrequencyOffset();
+        }
+    }
+    std::vector<float> soft = d.getSoftBits();
+    if (synced) *synced = ever ? 1 : 0;
+    if (sync_offset) *sync_offset = off;
+    if (cfo_hz) *cfo_hz = cfo;
+    if (soft.size() > cap) return -(long)soft.size();
+    std::memcpy(llr_out, soft.data(), soft.size() * sizeof(float));
+    return (long)soft.size();
+}
+
 // ---------------------------------------------------------------- Watterson channel
 // sim::WattersonChannel(cfg, seed).process (src/sim/hf_channel.hpp:67-168).  Used for statistical
 // comparison only (its mt19937+normal_distribution stream is replaced by a counter RNG in the product).

@@ -316,6 +316,58 @@ class OfdmDemodulator:
                                             _ptr(snr_db), _ptr(final_cfo), sp, _stream(sp)))
         return llr, snr_db, final_cfo
 
+    def acquire_batch(self, samples, chunk=960, sync_threshold=0.0):
+        """pu_ofdm_acquire_batch: samples [B, L] (numpy or torch.cuda) -> (sync_info [B, 4] int32 = {synced, sync offset,
+        samples consumed before the first data symbol, process() calls}, coarse_cfo_hz [B])."""
+        tor = _is_torch(samples)
+        if tor:
+            import torch
+            assert samples.dtype == torch.float32 and samples.dim() == 2 and samples.is_contiguous()
+            B, L = samples.shape
+            info = torch.zeros((B, 4), dtype=torch.int32, device=samples.device)
+            cfo = torch.zeros(B, dtype=torch.float32, device=samples.device)
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.float32)
+            if samples.ndim == 1:
+                samples = samples.reshape(1, -1)
+            B, L = samples.shape
+            info = np.zeros((B, 4), np.int32)
+            cfo = np.zeros(B, np.float32)
+        sp = _space(samples, info, cfo)
+        check(lib().pu_ofdm_acquire_batch(self._h, _ptr(samples), C.c_size_t(B), C.c_size_t(L), C.c_size_t(chunk),
+                                          C.c_float(sync_threshold), _ptr(info), _ptr(cfo), sp, _stream(sp)))
+        return info, cfo
+
+    def process_batch(self, samples, chunk=960, llr_stride=648, sync_threshold=0.0):
+        """pu_ofdm_process_batch: OFDMDemodulator::process fed in chunk-sample pieces + getSoftBits() for every row of
+        samples [B, L] -> (llr [B, llr_stride], n_llr [B], sync_info [B, 4], coarse_cfo_hz [B], snr_db [B])."""
+        tor = _is_torch(samples)
+        if tor:
+            import torch
+            assert samples.dtype == torch.float32 and samples.dim() == 2 and samples.is_contiguous()
+            B, L = samples.shape
+            dev = samples.device
+            llr = torch.zeros((B, llr_stride), dtype=torch.float32, device=dev)
+            n = torch.zeros(B, dtype=torch.int32, device=dev)
+            info = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+            cfo = torch.zeros(B, dtype=torch.float32, device=dev)
+            snr = torch.zeros(B, dtype=torch.float32, device=dev)
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.float32)
+            if samples.ndim == 1:
+                samples = samples.reshape(1, -1)
+            B, L = samples.shape
+            llr = np.zeros((B, llr_stride), np.float32)
+            n = np.zeros(B, np.int32)
+            info = np.zeros((B, 4), np.int32)
+            cfo = np.zeros(B, np.float32)
+            snr = np.zeros(B, np.float32)
+        sp = _space(samples, llr, n, info, cfo, snr)
+        check(lib().pu_ofdm_process_batch(self._h, _ptr(samples), C.c_size_t(B), C.c_size_t(L), C.c_size_t(chunk),
+                                          C.c_float(sync_threshold), _ptr(llr), C.c_size_t(llr_stride), _ptr(n), _ptr(info),
+                                          _ptr(cfo), _ptr(snr), sp, _stream(sp)))
+        return llr, n, info, cfo, snr
+
     def presynced_debug(self, samples, training=2, cfo_hz=0.0, cfo_phase=0.0):
         x = np.ascontiguousarray(samples, dtype=np.float32)
         L = len(x)

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
     OfdmDev d, WgTw twa, const float* __restrict__ samples, size_t frame_stride, size_t B, int n_symbols, int training,
     const float* __restrict__ cfo_hz, const float* __restrict__ cfo_phase,
     float* __restrict__ llr_out, size_t llr_stride, int llr_limit,
-    float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out, float* __restrict__ dbg, unsigned group_bytes) {
+    float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out, float* __restrict__ dbg, unsigned group_bytes,
+    const int* __restrict__ frame_start, const int* __restrict__ frame_nsym) {
     constexpr int LOG2N = (NFFT == 512) ? 9 : 10;
     constexpr int T = WARPG ? 32 : NFFT / 8;
     using G = WgGeom<NFFT>;
@@ -147,7 +148,10 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
     float2* binbuf = buf + G::BUF;
     RxShared& S = WARPG ? *reinterpret_cast<RxShared*>(binbuf + 2 * G::CW)
                         : *reinterpret_cast<RxShared*>(theta + ((d.sym_len + 3) & ~3));
-    const float* x = samples + frame * frame_stride;
+    // optional per-frame window (acquired frames, pu_ofdm_process_batch): the symbols start frame_start[frame] samples into the
+    // row and there are frame_nsym[frame] of them; the NCO restarts there (mixer.reset(), demodulator.cpp:583)
+    const float* x = samples + frame * frame_stride + (frame_start ? frame_start[frame] : 0);
+    if (frame_nsym) n_symbols = min(n_symbols, max(frame_nsym[frame], 0));
     const int nd = d.n_data, np = d.n_pilot, nu = nd + np;
     const bool differential = (d.mod == PU_MOD_DBPSK || d.mod == PU_MOD_DQPSK || d.mod == PU_MOD_D8PSK);
 
@@ -817,6 +821,31 @@ cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, co
                                 int n_symbols, int training, float* llr, size_t llr_stride, int llr_limit, float* snr_db,
                                 float* final_cfo, int sm_count, cudaStream_t st);
 
+// ofdm_acquire.cu
+struct AcqDev {
+    int nfft, log2n, cp, sym_len;
+    float sample_rate, sync_threshold;
+    const float2* twiddle;
+    const float* lts_i;
+    const float* lts_q;
+    float lts_energy_ref;
+    float lts_threshold;
+};
+cudaError_t ofdm_acquire_launch(const AcqDev& a, const float* samples, size_t B, size_t frame_stride, int L, int chunk, int4* out_int,
+                                float* out_cfo, cudaStream_t st);
+
+// frame windows of acquired frames: data symbols start at data_start and run to the end of the row
+__global__ void acquire_windows_kernel(const int4* __restrict__ acq, size_t B, int L, int sym_len, int llr_per_symbol, int llr_stride,
+                                       int* __restrict__ start, int* __restrict__ nsym, int* __restrict__ n_llr) {
+    const size_t b = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (b >= B) return;
+    const int4 a = acq[b];
+    const int n = a.x ? max(0, (L - a.z) / sym_len) : 0;
+    start[b] = a.x ? a.z : 0;
+    nsym[b] = n;
+    if (n_llr) n_llr[b] = min(n * llr_per_symbol, llr_stride);
+}
+
 struct DevMem {
     void* p = nullptr;
     ~DevMem() { if (p) cudaFree(p); }
@@ -837,6 +866,62 @@ struct pu_ofdm {
     pu::OfdmPlan plan;
     pu::OfdmDev dev{};
     pu::DevMem d_tw, d_nco, d_dbin, d_pbin, d_zc, d_psign, d_ilo, d_ihi, d_ia, d_perm;
+    pu::DevMem d_lts_i, d_lts_q;          // LTS passband templates of refineLTSTiming (built on first use)
+    pu::AcqDev acq{};
+    bool acq_ready = false;
+
+    // generateSequences (src/ofdm/demodulator.cpp:99-132): LTS in the frequency domain -> inverse FFT -> cyclic prefix ->
+    // passband templates; energy_ref as refineLTSTiming accumulates it (ofdm_sync.cpp:405-411)
+    pu_status ensure_acquire() {
+        if (acq_ready) return PU_OK;
+        const pu::OfdmPlan& p = plan;
+        std::vector<pu::cfloat> f(p.nfft, pu::cfloat(0, 0));
+        for (size_t i = 0; i < p.data_bin.size(); ++i) f[p.data_bin[i]] = p.sync_seq[i % p.sync_seq.size()];
+        for (size_t i = 0; i < p.pilot_bin.size(); ++i) f[p.pilot_bin[i]] = pu::cfloat(p.pilot_sign[i], 0.0f);
+        const size_t n = f.size();
+        for (size_t i = 0, rev = 0; i + 1 < n; ++i) {          // fft_impl(inverse), src/dsp/fft.cpp:89-121
+            if (i < rev) std::swap(f[i], f[rev]);
+            size_t bit = n >> 1;
+            while (bit <= rev) { rev -= bit; bit >>= 1; }
+            rev += bit;
+        }
+        for (size_t span = 2; span <= n; span <<= 1) {
+            const size_t half = span >> 1, stride = n / span;
+            for (size_t blk = 0; blk < n; blk += span)
+                for (size_t k = 0; k < half; ++k) {
+                    const pu::cfloat t = std::conj(p.twiddle[k * stride]) * f[blk + k + half];
+                    f[blk + k + half] = f[blk + k] - t;
+                    f[blk + k] = f[blk + k] + t;
+                }
+        }
+        const float scale = 1.0f / static_cast<float>(n);
+        for (auto& v : f) v *= scale;
+        const int P = p.nfft + p.cp;
+        std::vector<pu::cfloat> osc = p.nco(static_cast<float>(p.cfg.center_freq), static_cast<size_t>(P) + 1);
+        std::vector<float> li(P), lq(P);
+        for (int i = 0; i < P; ++i) {
+            const pu::cfloat bb = i < p.cp ? f[p.nfft - p.cp + i] : f[i - p.cp];
+            const pu::cfloat mixed = bb * osc[i];
+            li[i] = mixed.real();
+            lq[i] = mixed.imag();
+        }
+        float e = 0.0f;
+        for (int i = 0; i < P; ++i) { e += li[i] * li[i]; e += lq[i] * lq[i]; }
+        e *= 0.5f;
+        pu_status st;
+        if ((st = d_lts_i.upload(li.data(), li.size())) != PU_OK) return st;
+        if ((st = d_lts_q.upload(lq.data(), lq.size())) != PU_OK) return st;
+        acq.nfft = p.nfft; acq.log2n = p.log2n; acq.cp = p.cp; acq.sym_len = p.sym_len;
+        acq.sample_rate = static_cast<float>(p.cfg.sample_rate);
+        acq.sync_threshold = 0.80f;                              // ModemConfig::sync_threshold default, include/ultra/types.hpp:188
+        acq.twiddle = static_cast<const float2*>(d_tw.p);
+        acq.lts_i = static_cast<const float*>(d_lts_i.p);
+        acq.lts_q = static_cast<const float*>(d_lts_q.p);
+        acq.lts_energy_ref = e;
+        acq.lts_threshold = p.nfft >= 1024 ? 0.05f : 0.35f;      // ofdm_sync.cpp:451
+        acq_ready = true;
+        return PU_OK;
+    }
     int max_symbols = 0;
     int last_kernel = 0;
     size_t smem_bytes = 0;
@@ -943,7 +1028,8 @@ pu_status pu_ofdm_set_deinterleave(pu_ofdm* h, size_t bits_per_symbol, size_t to
 
 static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_t L, int training,
                              const float* d_cfo, const float* d_phase, float* d_llr, size_t llr_stride,
-                             float* d_snr, float* d_fcfo, float* d_dbg, cudaStream_t st) {
+                             float* d_snr, float* d_fcfo, float* d_dbg, cudaStream_t st,
+                             const int* d_fstart = nullptr, const int* d_fnsym = nullptr) {
     const pu::OfdmPlan& p = h->plan;
     const int n_symbols = static_cast<int>(L / p.sym_len);
     pu_status s = h->ensure_nco(n_symbols);
@@ -953,7 +1039,7 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
     const unsigned grid = static_cast<unsigned>(B);
     (void)cudaGetLastError();
     static const bool no_p512 = getenv("PU_OFDM_NO_PACKED512") != nullptr;   // A/B switch for tests and profiling
-    if (!d_cfo && !d_phase && !d_dbg && !no_p512 && pu::ofdm_diff_supported(h->dev, n_symbols, training) &&
+    if (!d_fstart && !d_fnsym && !d_cfo && !d_phase && !d_dbg && !no_p512 && pu::ofdm_diff_supported(h->dev, n_symbols, training) &&
         pu::ofdm_diff512_supported(h->dev, n_symbols, training, d_samples, L, B)) {
         // 512-FFT differential no-pilot mode: persistent TMA-staged packed-fp32 kernel (ofdm_diff512.cu)
         const cudaError_t e = pu::ofdm_diff512_launch(h->dev, reinterpret_cast<const float2*>(p.twiddle.data()), d_samples, B, L, n_symbols,
@@ -963,7 +1049,7 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         PU_CUDA_TRY(e);
         return PU_OK;
     }
-    if (!d_cfo && !d_phase && !d_dbg && pu::ofdm_diff_supported(h->dev, n_symbols, training)) {
+    if (!d_fstart && !d_fnsym && !d_cfo && !d_phase && !d_dbg && pu::ofdm_diff_supported(h->dev, n_symbols, training)) {
         // differential no-pilot mode with setFrequencyOffset(0): symbols are independent -> warp-FFT kernel (ofdm_diff.cu)
         static_assert(sizeof(pu::cfloat) == sizeof(float2), "twiddle layout");
         const cudaError_t e = pu::ofdm_diff_launch(h->dev, reinterpret_cast<const float2*>(p.twiddle.data()), d_samples, B, L, n_symbols,
@@ -997,10 +1083,10 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         }
         if (p.nfft == 512)
             pu::ofdm_presynced_kernel<512, true><<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(
-                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group);
+                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym);
         else
             pu::ofdm_presynced_kernel<1024, true><<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(
-                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group);
+                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym);
         h->last_kernel = 4;
         h->ctx->launches.fetch_add(1);
         PU_CUDA_TRY(cudaGetLastError());
@@ -1010,12 +1096,12 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         static bool attr512 = false;
         if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
         pu::ofdm_presynced_kernel<512, false><<<grid, 64, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
-                                                                            d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u);
+                                                                            d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym);
     } else {
         static bool attr1024 = false;
         if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
         pu::ofdm_presynced_kernel<1024, false><<<grid, 128, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
-                                                                              d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u);
+                                                                              d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym);
     }
     h->last_kernel = 1;
     h->ctx->launches.fetch_add(1);
@@ -1072,6 +1158,105 @@ pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_t B, si
         std::memcpy(llr_out + off * llr_stride, hout, nb * llr_stride * sizeof(float));
         if (snr_db) std::memcpy(snr_db + off, hout + slab * llr_stride, nb * sizeof(float));
         if (final_cfo_hz) std::memcpy(final_cfo_hz + off, hout + slab * llr_stride + slab, nb * sizeof(float));
+    }
+    return PU_OK;
+}
+
+pu_status pu_ofdm_acquire_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, size_t chunk, float sync_threshold,
+                                int32_t* sync_info, float* coarse_cfo_hz, pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_ofdm_acquire_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && sync_info && coarse_cfo_hz, "pu_ofdm_acquire_batch: NULL data pointer");
+    PU_REQUIRE(chunk > 0, "pu_ofdm_acquire_batch: chunk is zero");
+    if (L > 40000) {   // 2 * OVERLAP_SAMPLES: beyond it the reference trims its buffer between calls (demodulator.cpp:593-597)
+        pu::set_error("pu_ofdm_acquire_batch: frames longer than 40000 samples are not supported");
+        return PU_ERR_UNSUPPORTED;
+    }
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    pu_status s = h->ensure_acquire();
+    if (s != PU_OK) return s;
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    pu::AcqDev a = h->acq;
+    if (sync_threshold > 0.0f) a.sync_threshold = sync_threshold;
+    (void)cudaGetLastError();
+    if (space == PU_MEM_DEVICE) {
+        PU_CUDA_TRY(pu::ofdm_acquire_launch(a, samples, B, L, static_cast<int>(L), static_cast<int>(std::min<size_t>(chunk, L)),
+                                            reinterpret_cast<int4*>(sync_info), coarse_cfo_hz, st));
+        ctx->launches.fetch_add(1);
+        return PU_OK;
+    }
+    pu::DevMem dx, di, dc;
+    if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
+    std::vector<int32_t> zi(B * 4, 0);
+    std::vector<float> zc(B, 0.0f);
+    if ((s = di.upload(zi.data(), zi.size())) != PU_OK) return s;
+    if ((s = dc.upload(zc.data(), zc.size())) != PU_OK) return s;
+    PU_CUDA_TRY(pu::ofdm_acquire_launch(a, static_cast<const float*>(dx.p), B, L, static_cast<int>(L), static_cast<int>(std::min<size_t>(chunk, L)),
+                                        static_cast<int4*>(di.p), static_cast<float*>(dc.p), st));
+    ctx->launches.fetch_add(1);
+    PU_CUDA_TRY(cudaStreamSynchronize(st));
+    PU_CUDA_TRY(cudaMemcpy(sync_info, di.p, B * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    PU_CUDA_TRY(cudaMemcpy(coarse_cfo_hz, dc.p, B * sizeof(float), cudaMemcpyDeviceToHost));
+    return PU_OK;
+}
+
+pu_status pu_ofdm_process_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, size_t chunk, float sync_threshold,
+                                float* llr_out, size_t llr_stride, int32_t* n_llr, int32_t* sync_info, float* coarse_cfo_hz,
+                                float* snr_db, pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_ofdm_process_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && llr_out && n_llr, "pu_ofdm_process_batch: NULL data pointer");
+    PU_REQUIRE(llr_stride > 0, "pu_ofdm_process_batch: llr_stride is zero");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    const pu::OfdmPlan& p = h->plan;
+    // device scratch: samples / llr (host callers), acquisition results, frame windows
+    pu::DevMem dx, dl, dn, dsn, dacq, dcfo, dstart, dnsym;
+    pu_status s;
+    const float* d_x = samples;
+    float* d_llr = llr_out;
+    int32_t* d_n = n_llr;
+    float* d_snr = snr_db;
+    std::vector<float> zl;
+    if (space == PU_MEM_HOST) {
+        if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
+        zl.assign(B * llr_stride, 0.0f);
+        if ((s = dl.upload(zl.data(), zl.size())) != PU_OK) return s;
+        std::vector<int32_t> zn(B, 0);
+        if ((s = dn.upload(zn.data(), zn.size())) != PU_OK) return s;
+        if ((s = dsn.upload(zl.data(), B)) != PU_OK) return s;
+        d_x = static_cast<const float*>(dx.p); d_llr = static_cast<float*>(dl.p); d_n = static_cast<int32_t*>(dn.p);
+        d_snr = snr_db ? static_cast<float*>(dsn.p) : nullptr;
+    }
+    std::vector<int32_t> zi(B * 4, 0);
+    if ((s = dacq.upload(zi.data(), zi.size())) != PU_OK) return s;
+    if ((s = dcfo.upload(zi.data(), B)) != PU_OK) return s;
+    if ((s = dstart.upload(zi.data(), B)) != PU_OK) return s;
+    if ((s = dnsym.upload(zi.data(), B)) != PU_OK) return s;
+    s = pu_ofdm_acquire_batch(h, d_x, B, L, chunk, sync_threshold, static_cast<int32_t*>(dacq.p), static_cast<float*>(dcfo.p),
+                              PU_MEM_DEVICE, st);
+    if (s != PU_OK) return s;
+    pu::acquire_windows_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(
+        static_cast<const int4*>(dacq.p), B, static_cast<int>(L), p.sym_len, p.n_data * p.bps, static_cast<int>(llr_stride),
+        static_cast<int*>(dstart.p), static_cast<int*>(dnsym.p), d_n);
+    ctx->launches.fetch_add(1);
+    // SYNCED state (demodulator.cpp:665-690): no LTS channel estimate, mixer restarted at the first data symbol, CFO = the
+    // Schmidl-Cox estimate with zero rotator phase -- the presynced path with zero training symbols on the frame's window
+    s = launch_ofdm(h, d_x, B, L, 0, static_cast<const float*>(dcfo.p), nullptr, d_llr, llr_stride, d_snr, nullptr, nullptr, st,
+                    static_cast<const int*>(dstart.p), static_cast<const int*>(dnsym.p));
+    if (s != PU_OK) return s;
+    PU_CUDA_TRY(cudaStreamSynchronize(st));   // the scratch buffers above are freed on return
+    if (space == PU_MEM_HOST) {
+        PU_CUDA_TRY(cudaMemcpy(llr_out, d_llr, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
+        PU_CUDA_TRY(cudaMemcpy(n_llr, d_n, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (snr_db) PU_CUDA_TRY(cudaMemcpy(snr_db, d_snr, B * sizeof(float), cudaMemcpyDeviceToHost));
+        if (sync_info) PU_CUDA_TRY(cudaMemcpy(sync_info, dacq.p, B * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (coarse_cfo_hz) PU_CUDA_TRY(cudaMemcpy(coarse_cfo_hz, dcfo.p, B * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        if (sync_info) PU_CUDA_TRY(cudaMemcpy(sync_info, dacq.p, B * 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+        if (coarse_cfo_hz) PU_CUDA_TRY(cudaMemcpy(coarse_cfo_hz, dcfo.p, B * sizeof(float), cudaMemcpyDeviceToDevice));
     }
     return PU_OK;
 }

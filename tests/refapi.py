@@ -80,6 +80,7 @@ def lib():
         L.ref_ofdm_tx.restype = C.c_long
         L.ref_ofdm_presynced.restype = C.c_long
         L.ref_ofdm_process.restype = C.c_long
+        L.ref_ofdm_process_info.restype = C.c_long
         L.ref_ofdm_presynced_stages.restype = C.c_long
         L.ref_dpsk_modulate.restype = C.c_long
         L.ref_dpsk_demod_soft.restype = C.c_long
@@ -240,6 +241,17 @@ def ofdm_process(cfg, samples, chunk=960):
                                _p(out, C.c_float), C.c_size_t(len(out)), C.byref(synced), C.byref(snr))
     assert n >= 0
     return out[:n].copy(), bool(synced.value), snr.value
+
+
+def ofdm_process_info(cfg, samples, chunk=960):
+    """OFDMDemodulator::process in `chunk`-sample pieces + getSoftBits(): (llr, synced, sync_offset, coarse_cfo)."""
+    x = _f32(samples)
+    out = np.zeros(2048, np.float32)
+    synced, off, cfo = C.c_int(0), C.c_long(0), C.c_float(0)
+    n = lib().ref_ofdm_process_info(C.byref(cfg), _p(x, C.c_float), C.c_size_t(len(x)), C.c_size_t(chunk),
+                                    _p(out, C.c_float), C.c_size_t(len(out)), C.byref(synced), C.byref(off), C.byref(cfo))
+    assert n >= 0
+    return out[:n].copy(), bool(synced.value), int(off.value), float(cfo.value)
 
 
 def ofdm_presynced_stages(cfg, samples, training=2, cfo_mode=1, cfo_hz=0.0, cfo_phase=0.0, max_sym=64):
