@@ -282,8 +282,32 @@ public:
     OFDMDemodulator(const OFDMDemodulator&) = delete;
     OFDMDemodulator& operator=(const OFDMDemodulator&) = delete;
 
-    // Schmidl-Cox acquisition (demodulator.cpp:462-743) is a SURVEY §8f "next" row: never reports a frame.
-    bool process(SampleSpan) { return false; }
+    // demodulator.cpp:459-743.  Samples accumulate on the host; every call hands the whole buffer to
+    // pu_ofdm_process_batch, which replays the reference's sequence of process() calls for the chunk size of the FIRST call
+    // (the reference's outcome depends on the chunking; callers feed equal chunks, tools/test_mode_snr.cpp:65-70), so the
+    // synchronisation decision, the coarse CFO and the soft bits are the reference's.  Returns true once a codeword's
+    // worth of soft bits (648) is available, like the reference.  Not replayed: the mid-frame preamble re-check and the
+    // idle / timeout resets of the SYNCED state (:604-662,692-735), which need idle calls.
+    bool process(SampleSpan samples) {
+        if (rx_.empty()) chunk_ = std::max<size_t>(samples.size(), 1);
+        rx_.insert(rx_.end(), samples.begin(), samples.end());
+        if (rx_.size() > 40000) return false;                      // beyond 2 * OVERLAP_SAMPLES the reference trims its buffer
+        const size_t cap = (rx_.size() / sym_len_ + 1) * bits_per_symbol_;
+        std::vector<float> llr(std::max<size_t>(cap, 1), 0.0f);
+        int32_t n = 0, info[4] = {0, 0, 0, 0};
+        float cfo = 0.0f, snr_db = 0.0f;
+        const pu_status s = pu_ofdm_process_batch(h_, rx_.data(), 1, rx_.size(), chunk_, 0.0f, llr.data(), llr.size(), &n, info, &cfo,
+                                                  &snr_db, PU_MEM_HOST, nullptr);
+        if (s != PU_OK) return false;
+        synced_ = info[0] != 0;
+        if (!synced_) return false;
+        last_sync_offset_ = static_cast<size_t>(info[1]);
+        cfo_hz_ = cfo;
+        snr_db_ = snr_db;
+        llr.resize(static_cast<size_t>(n));
+        soft_ = std::move(llr);
+        return soft_.size() >= PU_LDPC_N;
+    }
 
     // demodulator.cpp:854-985.  The frame is demodulated by the CUDA kernel from a fresh tracker state with the CFO
     // and phase given to setFrequencyOffset[WithPhase]; like the reference, the soft-bit FIFO is replaced.
@@ -334,10 +358,12 @@ public:
     Symbol getConstellationSymbols() const { return {}; }   // GUI scatter plot: not produced by the batch kernels
     bool isSynced() const { return synced_; }
     bool hasPendingData() const { return !soft_.empty(); }
-    size_t getLastSyncOffset() const { return 0; }
+    size_t getLastSyncOffset() const { return last_sync_offset_; }
     void setTimingOffset(int) {}
     void reset() {   // :987-1017
         soft_.clear();
+        rx_.clear();
+        last_sync_offset_ = 0;
         cfo_hz_ = 0.0f;
         cfo_phase_ = 0.0f;
         cfo_set_ = false;
@@ -351,6 +377,8 @@ private:
     pu_ofdm* h_ = nullptr;
     size_t sym_len_ = 0, bits_per_symbol_ = 0;
     std::vector<float> soft_;
+    std::vector<float> rx_;        // samples handed to process() so far
+    size_t chunk_ = 960, last_sync_offset_ = 0;
     float cfo_hz_ = 0.0f, cfo_phase_ = 0.0f, snr_db_ = 0.0f;
     bool cfo_set_ = false, synced_ = false;
 };

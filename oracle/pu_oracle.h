@@ -75,6 +75,10 @@ typedef struct {   /* optional per-stage dumps, same layout as ref_ofdm_presynce
 long orc_ofdm_presynced(const orc_modem_config* c, const float* samples, size_t L, int training,
                         int cfo_mode, float cfo_hz, float cfo_phase, float* llr_out, size_t cap,
                         float* snr_db, float* final_cfo, orc_stage_dump* dump);
+/* OFDMDemodulator::process fed in chunk-sample pieces + the soft bits of every complete data symbol (Schmidl-Cox path,
+ * demodulator.cpp:459-760, ofdm_sync.cpp).  info[4] = {synchronised, sync offset, samples consumed, calls}. */
+long orc_ofdm_process(const orc_modem_config* c, const float* samples, size_t L, size_t chunk, float sync_threshold,
+                      float* llr_out, size_t cap, int32_t* info, float* coarse_cfo);
 int orc_ofdm_presynced_batch(const orc_modem_config* c, const float* samples, size_t B, size_t L, int training,
                              int cfo_mode, const float* cfo_hz, const float* cfo_phase,
                              float* llr_out, size_t stride, int32_t* counts);

@@ -897,3 +897,182 @@ double orc_time_presynced_decode(const orc_modem_config* c, const float* samples
     free(llr);
     return (double)(b2.tv_sec - a.tv_sec) + 1e-9 * (double)(b2.tv_nsec - a.tv_nsec);
 }
+
+/* ------------------------------------------------------------------ Schmidl-Cox acquisition
+ * TEST INFRASTRUCTURE.  OFDMDemodulator::process fed in `chunk`-sample pieces, then getSoftBits():
+ *   SEARCHING state            src/ofdm/demodulator.cpp:474-600
+ *   hasMinimumEnergy           src/ofdm/ofdm_sync.cpp:20-50
+ *   toAnalytic                 :56-84
+ *   measureSchmidlCoxCorrelation :118-163
+ *   estimateCoarseCFO          :230-261
+ *   refineLTSTiming            :386-461
+ *   LTS passband templates     src/ofdm/demodulator.cpp:99-132
+ *   SYNCED state               src/ofdm/demodulator.cpp:665-690 (= the presynced symbol loop without training symbols)
+ * Restricted to L <= 2 * OVERLAP_SAMPLES (40000): beyond it the reference trims its buffer between calls.
+ * Pinned against the compiled reference by tests/test_oracle_ofdm.py::test_process_path_matches_reference. */
+typedef struct {
+    modem_t* m;
+    const float* x; /* the frame */
+    size_t size;    /* rx_buffer.size() at the current call */
+    float noise_floor;
+    float* lts_i; float* lts_q; int lts_len;
+} acq_t;
+
+static void acq_analytic(const modem_t* m, const float* s, size_t len, cf* out) { /* toAnalytic, ofdm_sync.cpp:56-84 (len == fft size) */
+    for (size_t i = 0; i < len; ++i) out[i] = MKC(s[i], 0);
+    fft_inplace(out, len, m->tw, 0);
+    for (size_t i = 1; i < len / 2; ++i) out[i] = cscale(2.0f, out[i]);
+    for (size_t i = len / 2 + 1; i < len; ++i) out[i] = MKC(0, 0);
+    fft_inplace(out, len, m->tw, 1);
+}
+
+static int acq_min_energy(acq_t* a, size_t offset, size_t window) { /* ofdm_sync.cpp:20-50 */
+    if (offset + window > a->size) return 0;
+    float sum_sq = 0;
+    size_t count = 0;
+    for (size_t i = 0; i < window; i += 16) { float s = a->x[offset + i]; sum_sq += s * s; ++count; }
+    float energy = sum_sq / (float)count;
+    if (a->noise_floor < 1e-20f) a->noise_floor = energy * 0.1f;
+    if (energy < a->noise_floor) a->noise_floor = energy;
+    else if (energy < a->noise_floor * 3.0f) a->noise_floor = (1.0f - 0.01f) * a->noise_floor + 0.01f * energy;
+    return energy >= a->noise_floor * 4.0f;
+}
+
+static float acq_sc_corr(acq_t* a, size_t offset) { /* measureSchmidlCoxCorrelation, ofdm_sync.cpp:118-163 */
+    const modem_t* m = a->m;
+    size_t fft_len = (size_t)m->nfft, half = fft_len / 2, cp = (size_t)m->cp;
+    if (offset + cp + fft_len > a->size) return 0.0f;
+    const float* w = a->x + offset + cp;
+    float dc_sum = 0.0f;
+    for (size_t i = 0; i < fft_len; ++i) dc_sum += w[i];
+    float dc = dc_sum / (float)fft_len;
+    static _Thread_local float tmp[MAX_FFT];
+    static _Thread_local cf an[MAX_FFT];
+    for (size_t i = 0; i < fft_len; ++i) tmp[i] = w[i] - dc;
+    acq_analytic(m, tmp, fft_len, an);
+    cf P = MKC(0, 0);
+    float R1 = 0.0f, R2 = 0.0f;
+    for (size_t i = 0; i < half; ++i) {
+        P = P + conjf(an[i]) * an[i + half];
+        R1 += cnorm(an[i]);
+        R2 += cnorm(an[i + half]);
+    }
+    float normalization = sqrtf(R1 * R2);
+    if (normalization < 1e-10f) return 0.0f;
+    return cabsf(P) / normalization;
+}
+
+static float acq_coarse_cfo(acq_t* a, size_t sync_offset) { /* estimateCoarseCFO, ofdm_sync.cpp:230-261 */
+    const modem_t* m = a->m;
+    size_t fft_len = (size_t)m->nfft, half = fft_len / 2, start = sync_offset + (size_t)m->cp;
+    if (start + fft_len > a->size) return 0.0f;
+    static _Thread_local cf an[MAX_FFT];
+    acq_analytic(m, a->x + start, fft_len, an);
+    cf P = MKC(0, 0);
+    for (size_t i = 0; i < half; ++i) P = P + conjf(an[i]) * an[i + half];
+    float phase = atan2f(cimagf(P), crealf(P));
+    float cfo = (float)((double)(phase * (float)m->c.sample_rate) / (M_PI * (double)fft_len));
+    float max_cfo = (float)(m->c.sample_rate / (uint32_t)fft_len);
+    if (cfo > max_cfo) cfo = max_cfo;
+    if (cfo < -max_cfo) cfo = -max_cfo;
+    return cfo;
+}
+
+static long acq_refine_lts(acq_t* a, size_t coarse_sts) { /* refineLTSTiming, ofdm_sync.cpp:386-461; -1 == SIZE_MAX */
+    const modem_t* m = a->m;
+    size_t P = (size_t)(m->nfft + m->cp), coarse_lts = coarse_sts + 4 * P;
+    int back = (int)(3 * P), fwd = (int)(P / 2);
+    if (coarse_lts < (size_t)back || coarse_lts + (size_t)fwd + (size_t)a->lts_len > a->size) return (long)coarse_lts;
+    float energy_ref = 0.0f;
+    for (int i = 0; i < a->lts_len; ++i) { energy_ref += a->lts_i[i] * a->lts_i[i]; energy_ref += a->lts_q[i] * a->lts_q[i]; }
+    energy_ref *= 0.5f;
+    float best = 0.0f;
+    size_t best_off = coarse_lts;
+    for (int delta = -back; delta <= fwd; ++delta) {
+        size_t off = coarse_lts + (size_t)(long)delta;
+        float ci = 0.0f, cq = 0.0f, er = 0.0f;
+        for (int i = 0; i < a->lts_len; ++i) {
+            float r = a->x[off + (size_t)i];
+            ci += r * a->lts_i[i];
+            cq += r * a->lts_q[i];
+            er += r * r;
+        }
+        float mag = sqrtf(ci * ci + cq * cq), norm = sqrtf(er * energy_ref);
+        float corr = (norm > 1e-6f) ? mag / norm : 0.0f;
+        if (corr > best) { best = corr; best_off = off; }
+    }
+    float thr = (m->nfft >= 1024) ? 0.05f : 0.35f;
+    return best < thr ? -1 : (long)best_off;
+}
+
+/* info[4] = {synchronised, last_sync_offset, samples consumed before the first data symbol, process() calls until sync} */
+long orc_ofdm_process(const orc_modem_config* c, const float* samples, size_t L, size_t chunk, float sync_threshold,
+                      float* llr_out, size_t cap, int32_t* info, float* coarse_cfo) {
+    modem_t m;
+    if (modem_init(&m, c)) return -1;
+    if (L > 40000 || chunk == 0) { modem_free(&m); return -3; }
+    if (sync_threshold <= 0.0f) sync_threshold = 0.80f; /* ModemConfig::sync_threshold, types.hpp:188 */
+    /* generateSequences, demodulator.cpp:99-132 */
+    int P = m.nfft + m.cp;
+    static _Thread_local cf lf[MAX_FFT];
+    for (int i = 0; i < m.nfft; ++i) lf[i] = MKC(0, 0);
+    for (int i = 0; i < m.n_data; ++i) lf[m.data_idx[i]] = m.sync_seq[(size_t)i % c->num_carriers];
+    for (int i = 0; i < m.n_pilot; ++i) lf[m.pilot_idx[i]] = m.pilot_seq[i];
+    fft_inplace(lf, (size_t)m.nfft, m.tw, 1);
+    float* li = (float*)malloc(sizeof(float) * (size_t)P * 2);
+    float* lq = li + P;
+    nco_t osc;
+    nco_init(&osc, (float)c->center_freq, (float)c->sample_rate);
+    for (int i = 0; i < P; ++i) {
+        cf bb = i < m.cp ? lf[m.nfft - m.cp + i] : lf[i - m.cp];
+        cf mixed = bb * nco_next(&osc);
+        li[i] = crealf(mixed);
+        lq[i] = cimagf(mixed);
+    }
+    acq_t a = {&m, samples, 0, 0.0f, li, lq, P};
+    size_t total = 6 * (size_t)P, window = 2 * (size_t)P;
+    int found = 0, calls = 0;
+    size_t sync_offset = 0, data_start = 0;
+    float cfo = 0.0f;
+    for (size_t size = chunk < L ? chunk : L;; size = size + chunk < L ? size + chunk : L) {
+        ++calls;
+        a.size = size;
+        if (size >= 4000) { /* MIN_SEARCH_SAMPLES */
+            size_t search_end = size > total + window ? size - total - window : 0, peak_pos = 0;
+            int hit = 0;
+            for (size_t i = 0; i < search_end; i += 8) {
+                if (!acq_min_energy(&a, i, window)) { i += window / 2 - 8; continue; }
+                float corr = acq_sc_corr(&a, i);
+                if (corr > sync_threshold) {
+                    size_t plateau = 0;
+                    float peak = corr;
+                    peak_pos = i;
+                    for (size_t j = 0; j <= 300 && i + j + total < size; j += 8) {
+                        float r = acq_sc_corr(&a, i + j);
+                        if (r >= 0.90f) plateau++;
+                        if (r > peak) { peak = r; peak_pos = i + j; }
+                    }
+                    if (plateau >= 15) { hit = 1; break; }
+                }
+            }
+            if (hit) {
+                float coarse = acq_coarse_cfo(&a, peak_pos);
+                long refined = acq_refine_lts(&a, peak_pos);
+                if (refined >= 0) {
+                    found = 1;
+                    sync_offset = peak_pos;
+                    cfo = coarse;
+                    data_start = (size_t)refined + 2 * (size_t)P;
+                    break;
+                }
+            }
+        }
+        if (size >= L) break;
+    }
+    free(li);
+    modem_free(&m);
+    if (info) { info[0] = found; info[1] = (int32_t)sync_offset; info[2] = (int32_t)data_start; info[3] = calls; }
+    if (coarse_cfo) *coarse_cfo = cfo;
+    if (!found || data_start >= L) return 0;
+    return orc_ofdm_presynced(c, samples + data_start, L - data_start, 0, 1, cfo, 0.0f, llr_out, cap, NULL, NULL, NULL);
+}

@@ -239,6 +239,67 @@ static void ofdm_section() {
     }
 }
 
+// The reference's own Monte-Carlo loop for this path, tools/test_mode_snr.cpp:40-105, run side by side: frame =
+// generatePreamble() + modulate(), peak-normalised to 0.5, AWGN, fed to process() in 960-sample chunks, one getSoftBits().
+static void process_section() {
+    struct Case { const char* name; bool nvis; Modulation mod; CodeRate rate; size_t payload; };
+    const Case cases[] = {{"M1 DQPSK R1/2 process()", false, Modulation::DQPSK, CodeRate::R1_2, 40},
+                          {"M3 DQPSK R3/4 process()", true, Modulation::DQPSK, CodeRate::R3_4, 60}};
+    for (const Case& c : cases) {
+        ModemConfig cfg = c.nvis ? presets::nvis_mode() : ModemConfig{};
+        cfg.modulation = c.mod;
+        cfg.code_rate = c.rate;
+        cfg.use_pilots = false;
+        LDPCEncoder enc(c.rate);
+        LDPCDecoder ref_dec(c.rate);
+        pu::LDPCDecoder dec(c.rate);
+        std::mt19937 rng(12345);
+        const float snrs[] = {30.0f, 25.0f, 21.0f, 12.0f};
+        for (int trial = 0; trial < 4; ++trial) {
+            Bytes payload(c.payload);
+            for (auto& b : payload) b = static_cast<uint8_t>(rng() & 0xFF);
+            const Bytes coded = enc.encode(payload);
+            OFDMModulator mod(cfg);
+            Samples tx = mod.generatePreamble();
+            const Samples data = mod.modulate(coded, c.mod);
+            tx.insert(tx.end(), data.begin(), data.end());
+            float peak = 0.0f;
+            for (float v : tx) peak = std::max(peak, std::fabs(v));
+            if (peak > 0.0f) for (float& v : tx) v *= 0.5f / peak;
+            const Samples rx = add_noise(tx, snrs[trial], 2000u + static_cast<uint32_t>(trial));
+
+            OFDMDemodulator ref(cfg);
+            pu::OFDMDemodulator mine(cfg);
+            bool ref_ready = false, ready = false;
+            for (size_t i = 0; i < rx.size(); i += 960) {
+                const size_t len = std::min<size_t>(960, rx.size() - i);
+                ref_ready = ref.process(SampleSpan(rx.data() + i, len));
+                ready = mine.process(SampleSpan(rx.data() + i, len));
+            }
+            CHECK(ref_ready == ready, "%s trial %d ready flag %d vs %d", c.name, trial, (int)ref_ready, (int)ready);
+            CHECK(ref.isSynced() == mine.isSynced(), "%s trial %d isSynced", c.name, trial);
+            if (ref.isSynced() && mine.isSynced()) {
+                CHECK(ref.getLastSyncOffset() == mine.getLastSyncOffset(), "%s trial %d sync offset %zu vs %zu", c.name, trial,
+                      ref.getLastSyncOffset(), mine.getLastSyncOffset());
+                const float a = ref.getFrequencyOffset(), b = mine.getFrequencyOffset();
+                CHECK(std::memcmp(&a, &b, 4) == 0, "%s trial %d coarse CFO %.9g vs %.9g", c.name, trial, a, b);
+            }
+            const auto ref_soft = ref.getSoftBits();
+            const auto soft = mine.getSoftBits();
+            CHECK(ref_soft.size() == soft.size(), "%s trial %d soft-bit count %zu vs %zu", c.name, trial, ref_soft.size(), soft.size());
+            double worst = 0;
+            for (size_t i = 0; i < std::min(soft.size(), ref_soft.size()); ++i)
+                worst = std::max(worst, static_cast<double>(std::fabs(soft[i] - ref_soft[i])) / std::max(0.5, static_cast<double>(std::fabs(ref_soft[i]))));
+            CHECK(worst <= 1e-4, "%s trial %d LLR tolerance 1e-4 exceeded: %.3g", c.name, trial, worst);
+            if (ref_soft.size() >= 648 && soft.size() >= 648) {
+                const Bytes a = ref_dec.decodeSoft(std::span<const float>(ref_soft.data(), 648));
+                const Bytes b = dec.decodeSoft(std::span<const float>(soft.data(), 648));
+                CHECK(a == b && ref_dec.lastDecodeSuccess() == dec.lastDecodeSuccess(), "%s trial %d decoded bytes / flags", c.name, trial);
+            }
+        }
+    }
+}
+
 int main() {
     setLogLevel(LogLevel::ERROR);
     if (!std::freopen("/dev/null", "w", stderr)) return 2;   // the reference prints unconditionally on the hot path
@@ -246,6 +307,7 @@ int main() {
         ldpc_section();
         interleaver_section();
         ofdm_section();
+        process_section();
     } catch (const std::exception& e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

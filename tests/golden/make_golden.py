@@ -163,12 +163,38 @@ def psk_vectors():
     np.savez_compressed(os.path.join(HERE, "psk_golden.npz"), **out)
 
 
+ACQ_CASES = [("m1", R.DQPSK, R.R1_2, 40, 25.0), ("m1", R.DQPSK, R.R1_2, 40, 19.0), ("m1", R.D8PSK, R.R1_2, 40, 28.0),
+             ("m1", R.DQPSK, R.R1_2, 40, 9.0), ("m3", R.DQPSK, R.R3_4, 60, 24.0)]
+
+
+def acquire_vectors():
+    """Schmidl-Cox path (SURVEY 8f next-1): OFDMDemodulator::process fed in 960-sample chunks (tools/test_mode_snr.cpp:65-70)
+    and in one piece, then getSoftBits(); frames = generatePreamble() + modulate() over AWGN on mean frame power."""
+    rng = np.random.default_rng(20261018)
+    out = {}
+    for i, (preset, mod, rate, nbytes, snr) in enumerate(ACQ_CASES):
+        cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+        data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        tx = R.ofdm_tx(cfg, R.ldpc_encode(rate, data), 1)
+        rx = awgn(tx, snr, rng)
+        out[f"a{i}_cfg"] = np.frombuffer(bytes(cfg), np.uint8)
+        out[f"a{i}_rx"] = rx
+        for chunk in (960, len(rx)):
+            llr, synced, off, cfo = R.ofdm_process_info(cfg, rx, chunk)
+            tag = f"a{i}_c{0 if chunk == 960 else 1}"
+            out[tag + "_llr"] = llr
+            out[tag + "_info"] = np.array([int(synced), off], np.int64)
+            out[tag + "_cfo"] = np.array([cfo], np.float32)
+    np.savez_compressed(os.path.join(HERE, "acquire_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
     ldpc_vectors()
     ofdm_vectors()
     misc_vectors()
     psk_vectors()
+    acquire_vectors()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

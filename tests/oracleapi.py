@@ -36,7 +36,7 @@ def lib():
         if not os.path.exists(ORACLE_SO):
             build()
         L = C.CDLL(ORACLE_SO)
-        for f in ("orc_ldpc_encode", "orc_ldpc_decode_soft", "orc_ofdm_tx", "orc_ofdm_presynced"):
+        for f in ("orc_ldpc_encode", "orc_ldpc_decode_soft", "orc_ofdm_tx", "orc_ofdm_presynced", "orc_ofdm_process"):
             getattr(L, f).restype = C.c_long
         L.orc_channel_interleaver_step.restype = C.c_size_t
         L.orc_time_presynced_decode.restype = C.c_double
@@ -164,6 +164,20 @@ def ofdm_presynced(cfg, samples, training=2, cfo_mode=1, cfo_hz=0.0, cfo_phase=0
                                  C.byref(snr), C.byref(fc), None)
     assert n >= 0, n
     return out[:n].copy(), snr.value, fc.value
+
+
+def ofdm_process(cfg, samples, chunk=960, sync_threshold=0.0):
+    """OFDMDemodulator::process in chunk-sample pieces + getSoftBits() (first <= 648 soft bits):
+    (llr, synced, sync_offset, coarse_cfo, data_start, calls)."""
+    x = _f32(samples)
+    cap = 16384
+    out = np.zeros(cap, np.float32)
+    info = np.zeros(4, np.int32)
+    cfo = C.c_float(0)
+    n = lib().orc_ofdm_process(C.byref(cfg), _p(x, C.c_float), C.c_size_t(len(x)), C.c_size_t(chunk), C.c_float(sync_threshold),
+                               _p(out, C.c_float), C.c_size_t(cap), _p(info, C.c_int32), C.byref(cfo))
+    assert n >= 0, n
+    return out[:min(n, 648)].copy(), bool(info[0]), int(info[1]), float(cfo.value), int(info[2]), int(info[3])
 
 
 def ofdm_presynced_stages(cfg, samples, training=2, cfo_mode=1, cfo_hz=0.0, cfo_phase=0.0, max_sym=64):

@@ -61,6 +61,50 @@ def test_process_path_matches_reference(preset, mod):
     del ctx
 
 
+def test_golden_and_oracle_acquisition(golden):
+    """The same path against the committed reference vectors (tests/golden/acquire_golden.npz) and against the plain-C oracle
+    (oracle/pu_oracle_ofdm.c: orc_ofdm_process) on a batch that mixes synchronising and non-synchronising frames and carries
+    leading silence, so that the energy gate, the noise-floor tracker and later process() calls are exercised."""
+    from golden.make_golden import ACQ_CASES
+    from projectultra_b200 import capi
+    ctx = capi.Context(0)
+    g = golden["acquire"]
+    for i in range(len(ACQ_CASES)):
+        cfg = R.ModemConfig.from_buffer_copy(bytes(g[f"a{i}_cfg"]))
+        dem = capi.OfdmDemodulator(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)))
+        rx = g[f"a{i}_rx"]
+        for ci, chunk in enumerate((960, len(rx))):
+            llr, n, info, cfo, _ = dem.process_batch(rx[None, :], chunk=chunk)
+            want_sync, want_off = (int(v) for v in g[f"a{i}_c{ci}_info"])
+            assert int(info[0, 0]) == want_sync, (i, chunk)
+            if want_sync:
+                want = g[f"a{i}_c{ci}_llr"]
+                assert int(info[0, 1]) == want_off and cfo.view(np.uint32)[0] == g[f"a{i}_c{ci}_cfo"].view(np.uint32)[0]
+                assert int(n[0]) == len(want) and np.allclose(llr[0, :len(want)], want, rtol=1e-4, atol=1e-6), (i, chunk)
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    dem = capi.OfdmDemodulator(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)))
+    L = 10124 + 3000
+    frames = []
+    for i, (snr, lead) in enumerate(((30.0, 0), (26.0, 1000), (22.0, 2999), (19.0, 1777), (16.0, 500), (13.0, 0), (6.0, 2000), (24.0, 8))):
+        f = sc_frame(cfg, R.R1_2, 40, snr, 4000 + i, lead=lead, tail=3000 - lead)
+        frames.append(f + np.random.default_rng(i).normal(0, 1e-3, len(f)).astype(np.float32))
+    x = np.stack(frames)
+    assert x.shape[1] == L
+    for chunk in (960, 1500):
+        llr, n, info, cfo, _ = dem.process_batch(x, chunk=chunk)
+        n_sync = 0
+        for b in range(len(x)):
+            ol, osync, ooff, ocfo, ods, ocalls = O.ofdm_process(cfg, x[b], chunk)
+            assert bool(info[b, 0]) == osync, (b, chunk, info[b])
+            if osync:
+                n_sync += 1
+                assert (int(info[b, 1]), int(info[b, 2]), int(info[b, 3])) == (ooff, ods, ocalls), (b, chunk, info[b], ooff, ods, ocalls)
+                assert np.float32(cfo[b]).view(np.uint32) == np.float32(ocfo).view(np.uint32)
+                assert int(n[b]) == len(ol) and np.allclose(llr[b, :len(ol)], ol, rtol=1e-4, atol=1e-6), (b, chunk)
+        assert n_sync >= 3
+    del ctx
+
+
 def test_acquire_device_and_host_paths_agree():
     import torch
     from projectultra_b200 import capi

@@ -87,3 +87,51 @@ def test_vs_reference_sc_preamble_tx():
         cfg = R.config_m1(mod, R.R1_2)
         cw = R.ldpc_encode(R.R1_2, np.arange(40, dtype=np.uint8))
         assert same_bits(R.ofdm_tx(cfg, cw, 1), O.ofdm_tx(cfg, cw, 1))
+
+
+def _same_words(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    b = np.ascontiguousarray(b, np.float32).view(np.uint32)
+    return a.shape == b.shape and bool((a == b).all())
+
+
+def test_golden_acquisition(golden):
+    """SURVEY §8f next-1: the oracle's restatement of OFDMDemodulator::process (Schmidl-Cox search, coarse CFO, LTS timing,
+    SYNCED symbol loop) against vectors produced by the unmodified reference fed in 960-sample chunks and in one piece."""
+    from golden.make_golden import ACQ_CASES
+    g = golden["acquire"]
+    for i in range(len(ACQ_CASES)):
+        cfg = R.ModemConfig.from_buffer_copy(bytes(g[f"a{i}_cfg"]))
+        rx = g[f"a{i}_rx"]
+        for ci, chunk in enumerate((960, len(rx))):
+            llr, synced, off, cfo, data_start, calls = O.ofdm_process(cfg, rx, chunk)
+            want_sync, want_off = (int(v) for v in g[f"a{i}_c{ci}_info"])
+            assert int(synced) == want_sync, (i, chunk)
+            if not want_sync:
+                assert len(llr) == 0
+                continue
+            assert off == want_off, (i, chunk, off, want_off)
+            assert _same_words(np.float32(cfo), g[f"a{i}_c{ci}_cfo"][0]), (i, chunk, cfo)
+            assert _same_words(llr, g[f"a{i}_c{ci}_llr"]), (i, chunk)
+
+
+@pytest.mark.parametrize("preset,mod", [("m1", R.DQPSK), ("m1", R.D8PSK), ("m3", R.DQPSK)])
+def test_process_path_matches_reference(preset, mod):
+    """Same restatement against the compiled reference itself on fresh frames across the synchronisation threshold."""
+    if not R.available():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    rate = R.R1_2 if preset == "m1" else R.R3_4
+    cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    rng = np.random.default_rng(31 + mod)
+    n_sync = 0
+    for snr in (30.0, 24.0, 20.0, 17.0, 15.0, 11.0):
+        data = rng.integers(0, 256, 40 if preset == "m1" else 60, dtype=np.uint8)
+        rx = awgn(O.ofdm_tx(cfg, O.ldpc_encode(rate, data), 1), snr, rng)
+        for chunk in (960, 2500):
+            rl, rs, roff, rcfo = R.ofdm_process_info(cfg, rx, chunk)
+            ol, osync, ooff, ocfo, _, _ = O.ofdm_process(cfg, rx, chunk)
+            assert rs == osync, (snr, chunk)
+            if rs:
+                n_sync += 1
+                assert roff == ooff and _same_words(np.float32(rcfo), np.float32(ocfo)) and _same_words(rl, ol), (snr, chunk)
+    assert n_sync >= 4
