@@ -103,9 +103,16 @@ __device__ void analytic_smem(float2* buf, const float* __restrict__ x, float dc
 }
 
 // measureSchmidlCoxCorrelation(offset) over a buffer of `size` samples (ofdm_sync.cpp:118-163); uniform result.
+// The value depends on the samples only (the buffer size enters through the bound check), and every call of process()
+// searches again from offset 0: probes are memoised per offset (all probe offsets are multiples of 8) for the life of
+// the frame, which removes ~3/4 of the FFTs of a frame that synchronises late or never.
+constexpr int kAcqMaxProbes = 40000 / 8 + 1;
 template <int NFFT>
-__device__ float sc_correlation(const AcqDev& a, float2* buf, AcqShared& S, const float* __restrict__ x, int size, int offset) {
+__device__ float sc_correlation(const AcqDev& a, float2* buf, AcqShared& S, float* __restrict__ memo, const float* __restrict__ x, int size,
+                                int offset) {
     if (offset + a.cp + NFFT > size) return 0.0f;
+    const float cached = memo[offset >> 3];
+    if (cached >= 0.0f) return cached;              // uniform: written below by thread 0 between two barriers
     const float* w = x + offset + a.cp;
     const int tid = threadIdx.x;
     if (tid == 0) {                                   // ordered DC sum (:131-135)
@@ -132,7 +139,8 @@ __device__ float sc_correlation(const AcqDev& a, float2* buf, AcqShared& S, cons
     __syncthreads();
     const float norm = __fsqrt_rn(__fmul_rn(S.R1, S.R2));
     const float corr = (norm < 1e-10f) ? 0.0f : __fdiv_rn(cabs_ref(S.P), norm);
-    __syncthreads();                                  // S.* may be rewritten by the next probe
+    if (tid == 0) memo[offset >> 3] = corr;
+    __syncthreads();                                  // S.* may be rewritten by the next probe; the memo entry is visible
     return corr;
 }
 
@@ -142,7 +150,10 @@ __global__ void __launch_bounds__(kAcqThreads) ofdm_acquire_kernel(AcqDev a, con
                                                                    int L, int chunk, int4* __restrict__ out_int, float* __restrict__ out_cfo) {
     __shared__ float2 buf[NFFT];
     __shared__ AcqShared S;
+    __shared__ float memo[kAcqMaxProbes];               // Schmidl-Cox correlation per probe offset / 8, < 0 = not computed yet
     const int tid = threadIdx.x;
+    for (int i = tid; i < kAcqMaxProbes; i += blockDim.x) memo[i] = -1.0f;
+    __syncthreads();
     const float* x = samples + static_cast<size_t>(blockIdx.x) * frame_stride;
     const int P = NFFT + a.cp;                          // preamble_symbol_len
     const int total = 6 * P, window = 2 * P;            // preamble_total_len, correlation_window (demodulator.cpp:466-468)
@@ -183,14 +194,14 @@ __global__ void __launch_bounds__(kAcqThreads) ofdm_acquire_kernel(AcqDev a, con
                     __syncthreads();
                 }
                 if (!enough) { i += window / 2 - kSearchStep; continue; }
-                const float corr = sc_correlation<NFFT>(a, buf, S, x, size, i);
+                const float corr = sc_correlation<NFFT>(a, buf, S, memo, x, size, i);
                 if (corr > a.sync_threshold) {
                     // ---- plateau search (demodulator.cpp:504-531)
                     int plateau = 0;
                     float peak = corr;
                     peak_pos = i;
                     for (int j = 0; j <= kPlateauWindow && i + j + total < size; j += 8) {
-                        const float r = sc_correlation<NFFT>(a, buf, S, x, size, i + j);
+                        const float r = sc_correlation<NFFT>(a, buf, S, memo, x, size, i + j);
                         if (r >= kPlateauThreshold) ++plateau;
                         if (r > peak) { peak = r; peak_pos = i + j; }
                     }

@@ -124,7 +124,7 @@ class LinkSim:
     frame can be regenerated, and ranks take disjoint trial ranges with no data exchange."""
 
     def __init__(self, ctx, cfg, channel="awgn", payload_bytes=40, pool=64, snr_convention=None, pool_seed=12345,
-                 max_iter=50, device=None, code_rate=None, peak=None):
+                 max_iter=50, device=None, code_rate=None, peak=None, layout="presynced", chunk=960):
         import torch
         self.ctx, self.cfg = ctx, cfg
         self.device = device or torch.device("cuda", ctx.device)
@@ -136,7 +136,11 @@ class LinkSim:
             self.kind = "ofdm"
             rate = cfg.code_rate if code_rate is None else code_rate
             self.ofdm = self.demod = capi.OfdmDemodulator(ctx, cfg)
-            build = lambda coded: ofdm_tx(cfg, coded, 0)
+            # layout "presynced": 2 LTS + data, genie timing (tools/test_ofdm_chirp_pilots.cpp); layout "sc": generatePreamble()
+            # + data fed to process() in `chunk`-sample pieces, i.e. with Schmidl-Cox acquisition (tools/test_mode_snr.cpp:40-105)
+            assert layout in ("presynced", "sc")
+            self.layout, self.chunk = layout, chunk
+            build = lambda coded: ofdm_tx(cfg, coded, 1 if layout == "sc" else 0)
         elif isinstance(cfg, capi.DpskConfig):
             self.kind = "dpsk"
             rate = capi.R1_4 if code_rate is None else code_rate          # tools/test_dpsk_snr.cpp:28-29
@@ -169,6 +173,10 @@ class LinkSim:
 
     def demod_llr(self, rx, llr=None):
         """First 648 soft bits of every frame (device tensors), as the tools consume them."""
+        if self.kind == "ofdm" and self.layout == "sc":
+            out = self.demod.process_batch(rx, chunk=self.chunk, llr_stride=648)
+            self.last_n_llr, self.last_sync = out[1], out[2]
+            return out[0]
         if self.kind == "ofdm":
             return self.demod.presynced_batch(rx, 2, llr_stride=648, llr=llr, want_aux=False)[0]
         if self.kind == "dpsk":
@@ -200,7 +208,12 @@ class LinkSim:
     def run_batch(self, batch, counters, rx=None, keep=False):
         """channel -> demod -> LDPC -> counters for one prepared batch (all on the current stream)."""
         rx = channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rx)
-        if self.kind == "ofdm":
+        if self.kind == "ofdm" and self.layout == "sc":
+            # no sync or fewer than 648 soft bits is a lost frame (tools/test_mode_snr.cpp:72-77): the decoder's verdict on
+            # the zero-filled row is overridden
+            info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))
+            ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
+        elif self.kind == "ofdm":
             info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
         else:
             info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))

@@ -173,3 +173,40 @@ def test_count_errors_matches_numpy_for_many_bins():
         torch.cuda.synchronize()
         assert (counters.cpu().numpy() == 2 * want).all(), (B, n_bins)
     del ctx
+
+
+def test_linksim_config1_with_acquisition():
+    """BASELINE config 1 as tools/test_mode_snr.cpp runs it: frame = generatePreamble() + modulate(), peak-normalised to 0.5,
+    AWGN on mean frame power, process() in 960-sample chunks (Schmidl-Cox acquisition), getSoftBits, decodeSoft, frame-error
+    rule -- every frame's sync decision, soft-bit count, ok flag, iteration count and bytes against the oracle on the
+    identical channel outputs."""
+    import torch
+    from projectultra_b200 import capi, linksim
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    ctx = capi.Context(0)
+    sim = linksim.LinkSim(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)), "awgn", payload_bytes=40, pool=4, peak=0.5, layout="sc")
+    assert sim.L == 10124
+    snrs = [12.0, 16.0, 18.0, 21.0, 25.0]
+    trials = 6
+    si = np.repeat(np.arange(len(snrs)), trials)
+    tr = np.tile(np.arange(trials), len(snrs))
+    batch = sim.make_batch(snrs, si, tr)
+    counters = torch.zeros((len(snrs), 6), dtype=torch.int64, device="cuda")
+    rx, info, ok, iters = sim.run_batch(batch, counters, keep=True)
+    torch.cuda.synchronize()
+    rx_h = rx.cpu().numpy()
+    n_llr = sim.last_n_llr.cpu().numpy()
+    sync = sim.last_sync.cpu().numpy()
+    ok_h, info_h, it_h = ok.cpu().numpy(), info.cpu().numpy(), iters.cpu().numpy()
+    for b in range(len(rx_h)):
+        ol, osync, ooff, ocfo, ods, ocalls = O.ofdm_process(cfg, rx_h[b], 960)
+        assert bool(sync[b, 0]) == osync and int(n_llr[b]) == len(ol), (b, sync[b], n_llr[b], len(ol))
+        if len(ol) >= 648:
+            ci, cok, cit = O.ldpc_decode_batch(R.R1_2, ol[None, :648].copy())
+            assert ok_h[b] == cok[0] and it_h[b] == cit[0] and (info_h[b] == ci[0]).all(), b
+        else:
+            assert ok_h[b] == 0
+    c = counters.cpu().numpy()
+    assert c[:, 0].tolist() == [trials] * len(snrs)
+    assert c[0, 1] == trials and c[-1, 1] == 0      # the reference's acquisition threshold sits between 12 and 25 dB
+    del ctx
