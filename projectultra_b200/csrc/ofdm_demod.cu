@@ -125,7 +125,9 @@ struct RxShared {
 // WARPG = true:  one frame per WARP, blockDim.x / 32 frames per CTA, no CTA-wide barrier anywhere: the serial tracker
 //                sections and the HBM latency of a frame's next symbol only stall that frame's warp.
 #define PU_GSYNC() do { if constexpr (WARPG) __syncwarp(); else __syncthreads(); } while (0)
-template <int NFFT, bool WARPG>
+// FAM: 0 = modulation family decided at run time, 1 = differential (DBPSK/DQPSK/D8PSK), 2 = coherent: the warp form is
+// compiled once per family so that each instance carries only its own equaliser and demappers (instruction-cache footprint).
+template <int NFFT, bool WARPG, int FAM>
 __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, WARPG ? 5 : 1) ofdm_presynced_kernel(
     OfdmDev d, WgTw twa, const float* __restrict__ samples, size_t frame_stride, size_t B, int n_symbols, int training,
     const float* __restrict__ cfo_hz, const float* __restrict__ cfo_phase,
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
     const float* x = samples + frame * frame_stride + (frame_start ? frame_start[frame] : 0);
     if (frame_nsym) n_symbols = min(n_symbols, max(frame_nsym[frame], 0));
     const int nd = d.n_data, np = d.n_pilot, nu = nd + np;
-    const bool differential = (d.mod == PU_MOD_DBPSK || d.mod == PU_MOD_DQPSK || d.mod == PU_MOD_D8PSK);
+    const bool differential = FAM == 1 ? true : FAM == 2 ? false : (d.mod == PU_MOD_DBPSK || d.mod == PU_MOD_DQPSK || d.mod == PU_MOD_D8PSK);
 
     // warp FFT: per-lane twiddles of pass B (loop invariant)
     const int lane = tid;
@@ -1075,18 +1077,21 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         const size_t buf_f2 = static_cast<size_t>(p.nfft + (p.nfft >> (p.nfft == 512 ? 4 : 5)) + 2 * cw);
         const unsigned group = static_cast<unsigned>((buf_f2 * sizeof(float2) + sizeof(pu::RxShared) + 15) & ~size_t(15));
         const unsigned wgrid = static_cast<unsigned>((B + warps - 1) / warps);
+        const bool diff = pu::is_differential(p.cfg.modulation);
+        using WK = void (*)(pu::OfdmDev, pu::WgTw, const float*, size_t, size_t, int, int, const float*, const float*, float*, size_t, int,
+                            float*, float*, float*, unsigned, const int*, const int*);
+        const WK wk = p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1> : pu::ofdm_presynced_kernel<512, true, 2>)
+                                    : (diff ? pu::ofdm_presynced_kernel<1024, true, 1> : pu::ofdm_presynced_kernel<1024, true, 2>);
         static bool attrw = false;
         if (!attrw) {
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
             attrw = true;
         }
-        if (p.nfft == 512)
-            pu::ofdm_presynced_kernel<512, true><<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(
-                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym);
-        else
-            pu::ofdm_presynced_kernel<1024, true><<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(
-                h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr, llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym);
+        wk<<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr,
+                                                                           llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym);
         h->last_kernel = 4;
         h->ctx->launches.fetch_add(1);
         PU_CUDA_TRY(cudaGetLastError());
@@ -1094,13 +1099,13 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
     }
     if (p.nfft == 512) {
         static bool attr512 = false;
-        if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
-        pu::ofdm_presynced_kernel<512, false><<<grid, 64, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
+        if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
+        pu::ofdm_presynced_kernel<512, false, 0><<<grid, 64, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
                                                                             d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym);
     } else {
         static bool attr1024 = false;
-        if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
-        pu::ofdm_presynced_kernel<1024, false><<<grid, 128, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
+        if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
+        pu::ofdm_presynced_kernel<1024, false, 0><<<grid, 128, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
                                                                               d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym);
     }
     h->last_kernel = 1;
