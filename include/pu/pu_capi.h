@@ -150,6 +150,17 @@ PU_API pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_
                                          const float* cfo_hz, const float* cfo_phase, float* llr_out,
                                          size_t llr_stride, float* snr_db, float* final_cfo_hz,
                                          pu_memspace space, void* stream);
+/* ---------------------------------------------------------------- batched transmitter
+ * LDPCEncoder::encode (src/fec/ldpc_encoder.cpp:193-257, one 648-bit block, payload zero-padded to k bits) followed by
+ * OFDMModulator::generateTrainingSymbols(2) (layout 0) or generatePreamble() (layout 1) + modulate()
+ * (src/ofdm/modulator.cpp:348-580) for B payloads at once; peak > 0 rescales every frame to that peak amplitude as the
+ * tools do (tools/test_mode_snr.cpp:52-56).  `code` supplies the code rate (its tables double as the encoder's).
+ * out[B][out_stride] receives *frame_len samples per row; call with B = 0 to query *frame_len.  Waveforms are
+ * bit-identical to pu_ldpc_encode + pu_ofdm_tx. */
+PU_API pu_status pu_ofdm_tx_batch(pu_ofdm* h, const pu_ldpc* code, const uint8_t* payload, size_t payload_stride,
+                                  size_t payload_bytes, size_t B, int layout, float peak, float* out, size_t out_stride,
+                                  size_t* frame_len, pu_memspace space, void* stream);
+
 /* ---------------------------------------------------------------- OFDM acquisition (Schmidl-Cox path)
  * Replaces the SEARCHING state of ultra::OFDMDemodulator::process (src/ofdm/demodulator.cpp:474-600) with
  * Impl::hasMinimumEnergy / measureSchmidlCoxCorrelation / estimateCoarseCFO / refineLTSTiming
@@ -260,6 +271,10 @@ PU_API pu_status pu_channel_params(const pu_channel_config* cfg, int32_t* delay_
  * 10^(-snr/20) (hf_channel.hpp:110-119); convention 1 = the AWGN tools, sqrt(mean power / 10^(snr/10))
  * (tools/test_mode_snr.cpp:58-61). */
 PU_API float pu_channel_noise_std(const float* tx, size_t L, float snr_db, int convention);
+/* The same for every row of tx[B][tx_stride] on the DEVICE (frames produced by pu_ofdm_tx_batch): snr_factor[b] =
+ * powf(10, snr_db/10) (convention 1) or powf(10, -snr_db/20) (convention 0), evaluated by the caller on the host. */
+PU_API pu_status pu_channel_noise_std_batch(pu_ctx* ctx, const float* tx, size_t tx_stride, size_t L, size_t B,
+                                            const float* snr_factor, int convention, float* noise_std, void* stream);
 /* rx[b] = channel(tx_pool[tx_index[b]]) for b < B: frames of L samples, per-frame noise_std and 64-bit seed.
  * The random stream is the counter-based generator specified in csrc/pu_rng.cuh (NOT the reference's
  * mt19937 stream): frame b is a pure function of (config, tx waveform, noise_std[b], seed[b]).

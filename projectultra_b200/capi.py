@@ -316,6 +316,36 @@ class OfdmDemodulator:
                                             _ptr(snr_db), _ptr(final_cfo), sp, _stream(sp)))
         return llr, snr_db, final_cfo
 
+    def tx_frame_len(self, ldpc, layout=0):
+        n = C.c_size_t(0)
+        check(lib().pu_ofdm_tx_batch(self._h, ldpc._h, None, C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), int(layout), C.c_float(0.0),
+                                     None, C.c_size_t(0), C.byref(n), 0, None))
+        return int(n.value)
+
+    def tx_batch(self, ldpc, payload, layout=0, peak=0.0, out=None):
+        """pu_ofdm_tx_batch: payload [B, payload_bytes] uint8 (numpy or torch.cuda) -> frames [B, L] float32: LDPC encode (the
+        rate of `ldpc`) + training symbols / Schmidl-Cox preamble + modulate, optionally rescaled to `peak`."""
+        tor = _is_torch(payload)
+        B, nbytes = payload.shape
+        L = self.tx_frame_len(ldpc, layout)
+        if tor:
+            import torch
+            assert payload.dtype == torch.uint8 and payload.dim() == 2
+            stride = payload.stride(0)
+            if out is None:
+                out = torch.empty((B, L), dtype=torch.float32, device=payload.device)
+        else:
+            payload = np.ascontiguousarray(payload, dtype=np.uint8)
+            stride = payload.shape[1]
+            if out is None:
+                out = np.zeros((B, L), np.float32)
+        n = C.c_size_t(0)
+        sp = _space(payload, out)
+        ostride = out.stride(0) if tor else out.shape[1]
+        check(lib().pu_ofdm_tx_batch(self._h, ldpc._h, _ptr(payload), C.c_size_t(stride), C.c_size_t(nbytes), C.c_size_t(B), int(layout),
+                                     C.c_float(peak), _ptr(out), C.c_size_t(ostride), C.byref(n), sp, _stream(sp)))
+        return out
+
     def acquire_batch(self, samples, chunk=960, sync_threshold=0.0):
         """pu_ofdm_acquire_batch: samples [B, L] (numpy or torch.cuda) -> (sync_info [B, 4] int32 = {synced, sync offset,
         samples consumed before the first data symbol, process() calls}, coarse_cfo_hz [B])."""

@@ -139,6 +139,23 @@ static ChannelParams make_params(const pu_channel_config& c) {
 
 }  // namespace pu
 
+namespace pu {
+// pu_channel_noise_std for every row of tx[B][stride] (device): the ordered fp32 power sum of the reference's tools
+// (tools/test_mode_snr.cpp:58-61) / of WattersonChannel::process (hf_channel.hpp:110-119), one thread per frame.  The
+// SNR-dependent factor -- powf(10, snr/10) (convention 1) or powf(10, -snr/20) (convention 0) -- is evaluated on the host
+// per SNR point and gathered per frame, so no device pow enters the noise level.
+__global__ void noise_std_kernel(const float* __restrict__ tx, size_t stride, int L, size_t B, const float* __restrict__ factor, int convention,
+                                 float* __restrict__ out) {
+    const size_t b = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (b >= B) return;
+    const float* w = tx + b * stride;
+    float acc = 0.0f;
+    for (int i = 0; i < L; ++i) acc = __fadd_rn(acc, __fmul_rn(w[i], w[i]));
+    const float mean = __fdiv_rn(acc, static_cast<float>(L));
+    out[b] = convention == 0 ? __fmul_rn(__fsqrt_rn(mean), factor[b]) : __fsqrt_rn(__fdiv_rn(mean, factor[b]));
+}
+}  // namespace pu
+
 extern "C" {
 
 pu_status pu_channel_params(const pu_channel_config* cfg, int32_t* delay_samples, float* alpha, float* noise_scale,
@@ -150,6 +167,20 @@ pu_status pu_channel_params(const pu_channel_config* cfg, int32_t* delay_samples
     if (noise_scale) *noise_scale = p.noise_scale;
     if (apow2_5) std::memcpy(apow2_5, p.apow2, sizeof(p.apow2));
     if (apl_32) std::memcpy(apl_32, p.apl, sizeof(p.apl));
+    return PU_OK;
+}
+
+pu_status pu_channel_noise_std_batch(pu_ctx* ctx, const float* tx, size_t tx_stride, size_t L, size_t B, const float* snr_factor,
+                                     int convention, float* noise_std, void* stream) {
+    PU_REQUIRE(ctx, "pu_channel_noise_std_batch: NULL context");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(tx && snr_factor && noise_std && tx_stride >= L && L > 0, "pu_channel_noise_std_batch: bad argument");
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    (void)cudaGetLastError();
+    pu::noise_std_kernel<<<static_cast<unsigned>((B + 63) / 64), 64, 0, st>>>(tx, tx_stride, static_cast<int>(L), B, snr_factor, convention, noise_std);
+    ctx->launches.fetch_add(1);
+    PU_CUDA_TRY(cudaGetLastError());
     return PU_OK;
 }
 

@@ -446,6 +446,12 @@ static pu_status launch_decode(pu_ldpc* h, const float* d_llr, size_t llr_stride
     return PU_OK;
 }
 
+// device tables of the systematic encoder (ofdm_tx_gpu.cu): the decoder's check tables in slot order
+void pu_ldpc_encoder_view(const pu_ldpc* h, int* k, int* m, const uint8_t** cn_ninfo, const uint16_t** cn_check, const uint16_t** cn_var) {
+    *k = h->dev.k; *m = h->dev.m;
+    *cn_ninfo = h->dev.cn_ninfo; *cn_check = h->dev.cn_check; *cn_var = h->dev.cn_var;
+}
+
 extern "C" {
 
 pu_status pu_ldpc_create(pu_ctx* ctx, int code_rate, int max_iter, pu_ldpc** out) {

@@ -836,6 +836,29 @@ struct AcqDev {
 cudaError_t ofdm_acquire_launch(const AcqDev& a, const float* samples, size_t B, size_t frame_stride, int L, int chunk, int4* out_int,
                                 float* out_cfo, cudaStream_t st);
 
+// ofdm_tx_gpu.cu
+struct TxDev {
+    int nfft, cp, sym_len, guard, n_data, n_pilot, bps, differential;
+    int k, m;
+    int pre_len, n_sym, frame_len;
+    int osc_start;
+    float scale;
+    const uint8_t* cn_ninfo;
+    const uint16_t* cn_check;
+    const uint16_t* cn_var;
+    const int* data_bin;
+    const int* pilot_bin;
+    const float* pilot_sign;
+    const float2* twiddle;
+    const float2* osc;
+    const float* preamble;
+    const float2* points;
+};
+cudaError_t ofdm_tx_launch(const TxDev& t, const uint8_t* payload, size_t payload_stride, int payload_bytes, size_t B, float peak, float* out,
+                           size_t out_stride, cudaStream_t st);
+std::vector<float> ofdm_modulate_frame(const OfdmPlan& p, int layout, const uint8_t* data, size_t n_bytes);   // ofdm_tx.cpp
+cfloat ofdm_constellation_point(uint32_t bits, uint32_t mod);
+
 // frame windows of acquired frames: data symbols start at data_start and run to the end of the row
 __global__ void acquire_windows_kernel(const int4* __restrict__ acq, size_t B, int L, int sym_len, int llr_per_symbol, int llr_stride,
                                        int* __restrict__ start, int* __restrict__ nsym, int* __restrict__ n_llr) {
@@ -862,6 +885,8 @@ struct DevMem {
 
 }  // namespace pu
 
+void pu_ldpc_encoder_view(const pu_ldpc* h, int* k, int* m, const uint8_t** cn_ninfo, const uint16_t** cn_check, const uint16_t** cn_var);   // ldpc_decode.cu
+
 struct pu_ofdm {
     pu_ctx* ctx = nullptr;
     int device = 0;   // copy of ctx->device: the handle may outlive its context
@@ -869,6 +894,9 @@ struct pu_ofdm {
     pu::OfdmDev dev{};
     pu::DevMem d_tw, d_nco, d_dbin, d_pbin, d_zc, d_psign, d_ilo, d_ihi, d_ia, d_perm;
     pu::DevMem d_lts_i, d_lts_q;          // LTS passband templates of refineLTSTiming (built on first use)
+    pu::DevMem d_tx_osc, d_tx_pre[2], d_tx_points;   // transmitter tables (built on first use; preamble per layout)
+    int tx_pre_len[2] = {-1, -1};
+    size_t tx_osc_len = 0;
     pu::AcqDev acq{};
     bool acq_ready = false;
 
@@ -1164,6 +1192,75 @@ pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_t B, si
         if (snr_db) std::memcpy(snr_db + off, hout + slab * llr_stride, nb * sizeof(float));
         if (final_cfo_hz) std::memcpy(final_cfo_hz + off, hout + slab * llr_stride + slab, nb * sizeof(float));
     }
+    return PU_OK;
+}
+
+pu_status pu_ofdm_tx_batch(pu_ofdm* h, const pu_ldpc* code, const uint8_t* payload, size_t payload_stride, size_t payload_bytes, size_t B,
+                           int layout, float peak, float* out, size_t out_stride, size_t* frame_len, pu_memspace space, void* stream) {
+    PU_REQUIRE(h && code && frame_len, "pu_ofdm_tx_batch: NULL argument");
+    PU_REQUIRE(layout == 0 || layout == 1, "pu_ofdm_tx_batch: layout must be 0 (training) or 1 (Schmidl-Cox preamble)");
+    const pu::OfdmPlan& p = h->plan;
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    pu::TxDev t{};
+    pu_ldpc_encoder_view(code, &t.k, &t.m, &t.cn_ninfo, &t.cn_check, &t.cn_var);
+    PU_REQUIRE(payload_bytes * 8 <= static_cast<size_t>(t.k) && payload_bytes <= payload_stride, "pu_ofdm_tx_batch: payload longer than one codeword's information bits");
+    pu_status s;
+    if (h->tx_pre_len[layout] < 0) {                 // generateTrainingSymbols / generatePreamble: payload independent
+        std::vector<float> pre = pu::ofdm_modulate_frame(p, layout, nullptr, 0);
+        if ((s = h->d_tx_pre[layout].upload(pre.data(), pre.size())) != PU_OK) return s;
+        h->tx_pre_len[layout] = static_cast<int>(pre.size());
+    }
+    if (!h->d_tx_points.p) {
+        const uint32_t mod = p.cfg.modulation;
+        std::vector<pu::cfloat> pts(static_cast<size_t>(1) << p.bps);
+        for (uint32_t v = 0; v < pts.size(); ++v) {
+            if (mod == PU_MOD_DBPSK) pts[v] = (v & 1) ? pu::cfloat(-1, 0) : pu::cfloat(1, 0);
+            else if (mod == PU_MOD_DQPSK) { static const pu::cfloat st4[4] = {{1, 0}, {0, 1}, {-1, 0}, {0, -1}}; pts[v] = st4[v & 3]; }
+            else if (mod == PU_MOD_D8PSK) {
+                const float pi = 3.14159265358979f;
+                const float ang = static_cast<float>(v & 7) * (pi / 4.0f) + pi / 8.0f;
+                pts[v] = pu::cfloat(std::cos(ang), std::sin(ang));
+            } else pts[v] = pu::ofdm_constellation_point(v, mod);
+        }
+        if ((s = h->d_tx_points.upload(pts.data(), pts.size())) != PU_OK) return s;
+    }
+    const int per_sym = p.n_data * p.bps;
+    t.n_sym = (PU_LDPC_N + per_sym - 1) / per_sym;
+    t.pre_len = h->tx_pre_len[layout];
+    t.frame_len = t.pre_len + t.n_sym * p.sym_len;
+    *frame_len = static_cast<size_t>(t.frame_len);
+    if (B == 0 || !out) return PU_OK;                // length query
+    PU_REQUIRE(payload && out_stride >= static_cast<size_t>(t.frame_len), "pu_ofdm_tx_batch: output rows shorter than a frame");
+    t.osc_start = layout == 0 ? t.pre_len : 2 * (p.nfft + p.cp);
+    if (h->tx_osc_len < static_cast<size_t>(t.frame_len)) {
+        std::vector<pu::cfloat> osc = p.nco(static_cast<float>(p.cfg.center_freq) + p.cfg.tx_cfo_hz, static_cast<size_t>(t.frame_len) + 1);
+        if ((s = h->d_tx_osc.upload(osc.data(), static_cast<size_t>(t.frame_len))) != PU_OK) return s;
+        h->tx_osc_len = static_cast<size_t>(t.frame_len);
+    }
+    t.nfft = p.nfft; t.cp = p.cp; t.sym_len = p.sym_len; t.guard = static_cast<int>(p.cfg.symbol_guard);
+    t.n_data = p.n_data; t.n_pilot = p.n_pilot; t.bps = p.bps; t.differential = pu::is_differential(p.cfg.modulation) ? 1 : 0;
+    t.scale = p.cfg.output_scale;
+    t.data_bin = static_cast<const int*>(h->d_dbin.p); t.pilot_bin = static_cast<const int*>(h->d_pbin.p);
+    t.pilot_sign = static_cast<const float*>(h->d_psign.p); t.twiddle = static_cast<const float2*>(h->d_tw.p);
+    t.osc = static_cast<const float2*>(h->d_tx_osc.p); t.preamble = static_cast<const float*>(h->d_tx_pre[layout].p);
+    t.points = static_cast<const float2*>(h->d_tx_points.p);
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    (void)cudaGetLastError();
+    if (space == PU_MEM_DEVICE) {
+        PU_CUDA_TRY(pu::ofdm_tx_launch(t, payload, payload_stride, static_cast<int>(payload_bytes), B, peak, out, out_stride, st));
+        ctx->launches.fetch_add(1);
+        return PU_OK;
+    }
+    pu::DevMem dp, dout;
+    if ((s = dp.upload(payload, B * payload_stride)) != PU_OK) return s;
+    std::vector<float> z(B * out_stride, 0.0f);
+    if ((s = dout.upload(z.data(), z.size())) != PU_OK) return s;
+    PU_CUDA_TRY(pu::ofdm_tx_launch(t, static_cast<const uint8_t*>(dp.p), payload_stride, static_cast<int>(payload_bytes), B, peak,
+                                   static_cast<float*>(dout.p), out_stride, st));
+    ctx->launches.fetch_add(1);
+    PU_CUDA_TRY(cudaStreamSynchronize(st));
+    PU_CUDA_TRY(cudaMemcpy(out, dout.p, B * out_stride * sizeof(float), cudaMemcpyDeviceToHost));
     return PU_OK;
 }
 

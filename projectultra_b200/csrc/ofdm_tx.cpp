@@ -105,6 +105,8 @@ struct Transmitter {
 
 }  // namespace
 
+cfloat ofdm_constellation_point(uint32_t bits, uint32_t mod) { return constellation_point(bits, mod); }   // tables of ofdm_tx_gpu.cu
+
 std::vector<float> ofdm_modulate_frame(const OfdmPlan& p, int layout, const uint8_t* data, size_t n_bytes) {
     const uint32_t mod = p.cfg.modulation;
     const int bpc = p.bps;

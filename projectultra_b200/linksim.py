@@ -124,7 +124,7 @@ class LinkSim:
     frame can be regenerated, and ranks take disjoint trial ranges with no data exchange."""
 
     def __init__(self, ctx, cfg, channel="awgn", payload_bytes=40, pool=64, snr_convention=None, pool_seed=12345,
-                 max_iter=50, device=None, code_rate=None, peak=None, layout="presynced", chunk=960):
+                 max_iter=50, device=None, code_rate=None, peak=None, layout="presynced", chunk=960, fresh_payload=False):
         import torch
         self.ctx, self.cfg = ctx, cfg
         self.device = device or torch.device("cuda", ctx.device)
@@ -156,6 +156,11 @@ class LinkSim:
             raise TypeError("cfg must be a capi.ModemConfig, capi.DpskConfig or capi.McDpskConfig")
         self.code_rate = rate
         self.ldpc = capi.LdpcDecoder(ctx, rate, max_iter)
+        # fresh_payload: every frame carries its own random payload, encoded and modulated on the GPU (pu_ofdm_tx_batch), as the
+        # reference's tools do per trial (tools/test_mode_snr.cpp:44-56), instead of indexing a host-built pool of waveforms
+        self.fresh_payload = bool(fresh_payload)
+        self.peak = peak
+        assert not self.fresh_payload or self.kind == "ofdm", "the GPU transmitter covers the OFDM waveforms"
         self.payload_bytes = payload_bytes
         rng = np.random.default_rng(pool_seed)
         self.payloads = rng.integers(0, 256, (pool, payload_bytes), dtype=np.uint8)
@@ -205,8 +210,43 @@ class LinkSim:
                     seed=to(seeds.view(np.int64), np.int64), bins=to(snr_idx.astype(np.uint32).view(np.int32), np.int32),
                     host=dict(tx_index=tx_index, noise_std=std, seed=seeds, snr_idx=snr_idx))
 
-    def run_batch(self, batch, counters, rx=None, keep=False):
+    def fresh_frames(self, batch, snr_points):
+        """Payloads drawn on the device (torch Philox stream keyed by the batch's first frame seed), pu_ofdm_tx_batch, and the
+        per-frame noise level of the tools' SNR convention.  Returns (payload [B, kb] uint8 zero-padded, tx [B, L], noise_std [B])."""
+        import torch
+        B = batch["seed"].shape[0]
+        g = torch.Generator(device=self.device)
+        g.manual_seed(int(batch["host"]["seed"][0]) & 0x7FFFFFFFFFFFFFFF)
+        kb = self.ldpc.info_bytes
+        payload = torch.zeros((B, kb), dtype=torch.uint8, device=self.device)
+        payload[:, :self.payload_bytes] = torch.randint(0, 256, (B, self.payload_bytes), dtype=torch.uint8, device=self.device, generator=g)
+        tx = self.demod.tx_batch(self.ldpc, payload[:, :self.payload_bytes], layout=1 if self.layout == "sc" else 0,
+                                 peak=float(self.peak) if self.peak else 0.0)
+        snr = np.asarray(snr_points, np.float32)
+        fac = (np.power(np.float32(10.0), -snr / np.float32(20.0)) if self.snr_convention == 0
+               else np.power(np.float32(10.0), snr / np.float32(10.0))).astype(np.float32)
+        factor = torch.from_numpy(fac[batch["host"]["snr_idx"]]).to(self.device)
+        std = torch.empty(B, dtype=torch.float32, device=self.device)
+        capi.check(capi.lib().pu_channel_noise_std_batch(self.ctx._h, capi._ptr(tx), C.c_size_t(tx.stride(0)), C.c_size_t(tx.shape[1]),
+                                                         C.c_size_t(B), capi._ptr(factor), int(self.snr_convention), capi._ptr(std),
+                                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return payload, tx, std
+
+    def run_batch(self, batch, counters, rx=None, keep=False, snr_points=None):
         """channel -> demod -> LDPC -> counters for one prepared batch (all on the current stream)."""
+        if self.fresh_payload:
+            import torch
+            assert snr_points is not None, "fresh-payload batches need the SNR table to set each frame's noise level"
+            payload, tx, std = self.fresh_frames(batch, snr_points)
+            idx = torch.arange(tx.shape[0], dtype=torch.int32, device=self.device)
+            rx = channel_apply(self.ctx, self.ch, tx, idx, std, batch["seed"], rx)
+            info, ok, iters = (self.ldpc.decode_batch(self.demod_llr(rx)) if self.layout == "sc"
+                               else receive_decode(self.ofdm, self.ldpc, rx))
+            if self.layout == "sc":
+                ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
+            count_errors(self.ctx, info, ok, iters, payload, idx, batch["bins"], self.payload_bytes, counters)
+            self.last_payload, self.last_tx, self.last_std = payload, tx, std
+            return (rx, info, ok, iters) if keep else None
         rx = channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rx)
         if self.kind == "ofdm" and self.layout == "sc":
             # no sync or fewer than 648 soft bits is a lost frame (tools/test_mode_snr.cpp:72-77): the decoder's verdict on
@@ -231,7 +271,7 @@ class LinkSim:
         tr = np.tile(mine, len(snr_points))
         for off in range(0, len(si), batch_frames):
             b = self.make_batch(snr_points, si[off:off + batch_frames], tr[off:off + batch_frames], base_seed)
-            self.run_batch(b, counters)
+            self.run_batch(b, counters, snr_points=snr_points)
         return counters
 
 

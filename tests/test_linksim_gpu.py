@@ -210,3 +210,54 @@ def test_linksim_config1_with_acquisition():
     assert c[:, 0].tolist() == [trials] * len(snrs)
     assert c[0, 1] == trials and c[-1, 1] == 0      # the reference's acquisition threshold sits between 12 and 25 dB
     del ctx
+
+
+@pytest.mark.parametrize("layout", ["presynced", "sc"])
+def test_linksim_fresh_payload_gpu_transmitter(layout):
+    """Every frame carries its own payload, LDPC-encoded and modulated on the GPU: the transmitted
+    waveforms are the host/oracle transmitter's bit for bit, the noise level follows the tools' convention, the channel
+    output regenerates on the CPU, and every frame's decode result matches the oracle on the identical channel output."""
+    import torch
+    from projectultra_b200 import capi, linksim
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    ctx = capi.Context(0)
+    sim = linksim.LinkSim(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)), "awgn", payload_bytes=40, pool=2,
+                          peak=0.5 if layout == "sc" else None, layout=layout, fresh_payload=True)
+    snrs = [0.0, 3.0, 24.0] if layout == "presynced" else [14.0, 20.0, 26.0]
+    trials = 5
+    si = np.repeat(np.arange(len(snrs)), trials)
+    tr = np.tile(np.arange(trials), len(snrs))
+    batch = sim.make_batch(snrs, si, tr)
+    counters = torch.zeros((len(snrs), 6), dtype=torch.int64, device="cuda")
+    rx, info, ok, iters = sim.run_batch(batch, counters, keep=True, snr_points=snrs)
+    torch.cuda.synchronize()
+    payload = sim.last_payload.cpu().numpy()
+    tx, std, rx_h = sim.last_tx.cpu().numpy(), sim.last_std.cpu().numpy(), rx.cpu().numpy()
+    assert len(np.unique(payload[:, :40], axis=0)) == len(payload), "payloads must differ from frame to frame"
+    h = batch["host"]
+    for b in range(len(tx)):
+        w = O.ofdm_tx(cfg, O.ldpc_encode(R.R1_2, payload[b, :40]), 1 if layout == "sc" else 0)
+        if layout == "sc":
+            w = (w * (np.float32(0.5) / np.abs(w).max())).astype(np.float32)
+        assert (w.view(np.uint32) == tx[b].view(np.uint32)).all(), b
+        assert abs(std[b] - CH.noise_std(w, snrs[si[b]], 1)) <= 2e-7 * std[b], (b, std[b])
+        twin = CH.channel_apply(sim.ch, w, std[b], h["seed"][b])
+        assert (twin.view(np.uint32) == rx_h[b].view(np.uint32)).all(), b
+    if layout == "presynced":
+        llr, _ = O.ofdm_presynced_batch(cfg, rx_h, 648)
+        cinfo, cok, cit = O.ldpc_decode_batch(R.R1_2, llr)
+    else:
+        llr = np.zeros((len(rx_h), 648), np.float32)
+        got = np.zeros(len(rx_h), bool)
+        for b in range(len(rx_h)):
+            ol = O.ofdm_process(cfg, rx_h[b], 960)[0]
+            got[b] = len(ol) >= 648
+            llr[b, :len(ol)] = ol
+        cinfo, cok, cit = O.ldpc_decode_batch(R.R1_2, llr)
+        cok = cok * got
+    assert (ok.cpu().numpy() == cok).all() and (iters.cpu().numpy() == cit).all() and (info.cpu().numpy() == cinfo).all()
+    c = counters.cpu().numpy()
+    want_err = [(1 - ((cok == 1) & (cinfo[:, :40] == payload[:, :40]).all(axis=1))[si == k]).sum() for k in range(len(snrs))]
+    assert c[:, 0].tolist() == [trials] * len(snrs) and c[:, 1].tolist() == want_err
+    assert c[-1, 1] == 0
+    del ctx
