@@ -187,3 +187,188 @@ long orc_mcdpsk_demod_soft(int nc, int sps, int bits_per_symbol, float f_lo, flo
     }
     return n;
 }
+
+/* ------------------------------------------------------------------ Barker-13 acquisition of the single-carrier DPSK waveform
+ * TEST INFRASTRUCTURE (DPSK half).  DPSKDemodulator::findPreamble (src/psk/dpsk.hpp:338-481) with
+ * computeDifferentialScore (:489-546), estimateCFOTolerant (:550-593), estimateInitialPhaseOffset (:659-704) and
+ * refineTimingWithMatchedFilter (:708-771), in the reference's order of floating-point operations. */
+#define BK_SYMS 39   /* BARKER_LEN * REPEATS */
+#define BK_DIFFS 38
+static const int BARKER13[13] = {1, 1, 1, 1, 1, -1, -1, 1, 1, -1, 1, -1, 1};
+
+typedef struct { const float* x; size_t L; int sps; const float* ccos; const float* csin; float fc, fs; int pattern[BK_DIFFS]; } bk_t;
+
+static float bk_score(const bk_t* b, int start, float min_energy) {   /* computeDifferentialScore, :489-546 */
+    float sr[BK_SYMS], si[BK_SYMS], total_energy = 0;
+    for (int s = 0; s < BK_SYMS; ++s) {
+        dpsk_correlate(b->x + start + s * b->sps, b->sps, b->ccos, b->csin, &sr[s], &si[s]);
+        total_energy += sr[s] * sr[s] + si[s] * si[s];
+    }
+    if (total_energy < min_energy * BK_SYMS) return 0;
+    float cr = 0, ci = 0, magnitude_sum = 0;
+    for (int i = 0; i < BK_DIFFS; ++i) {
+        float dr, di;
+        cmulf(sr[i + 1], si[i + 1], sr[i], -si[i], &dr, &di);
+        const float magnitude = hypotf(dr, di);
+        if (magnitude < 1e-10f) continue;
+        const float nr = dr / magnitude, ni = di / magnitude;
+        float er, ei;
+        cmulf(nr, ni, (float)b->pattern[i], -0.0f, &er, &ei);   /* diff_norm * std::conj(Complex(expected, 0)) */
+        cr += er;
+        ci += ei;
+        magnitude_sum += magnitude;
+    }
+    if (magnitude_sum < 1e-10f) return 0;
+    return hypotf(cr, ci) / BK_DIFFS;
+}
+
+static float bk_cfo_tolerant(const bk_t* b, int start) {   /* estimateCFOTolerant, :550-593 */
+    float dr[BK_DIFFS], di[BK_DIFFS];
+    int nd = 0;
+    float pr = 0, pi = 0;
+    for (int s = 0; s <= BK_DIFFS; ++s) {
+        float cr, ci;
+        dpsk_correlate(b->x + start + s * b->sps, b->sps, b->ccos, b->csin, &cr, &ci);
+        if (s > 0 && hypotf(pr, pi) > 0.01f && hypotf(cr, ci) > 0.01f) {
+            float xr, xi;
+            cmulf(cr, ci, pr, -pi, &xr, &xi);
+            const float m = hypotf(xr, xi);
+            dr[nd] = xr / m;
+            di[nd] = xi / m;
+            ++nd;
+        }
+        pr = cr;
+        pi = ci;
+    }
+    if (nd < 10) return 0;
+    float cr = 0, ci = 0;
+    for (int i = 0; i < nd && i < BK_DIFFS; ++i) {
+        float er, ei;
+        cmulf(dr[i], di[i], (float)b->pattern[i], -0.0f, &er, &ei);
+        cr += er;
+        ci += ei;
+    }
+    const float phase_offset = atan2f(ci, cr);
+    const float symbol_duration = (float)b->sps / b->fs;
+    const float cfo_hz = (float)(phase_offset / (2.0f * ORC_PI * symbol_duration));
+    return -cfo_hz;
+}
+
+static int bk_refine_mf(const bk_t* b, int coarse) {   /* refineTimingWithMatchedFilter(cfo_hz = 0), :708-771 */
+    const int n = 6 * b->sps;
+    float* tmpl = (float*)malloc(sizeof(float) * (size_t)n);
+    const float adj = b->fc + 0.0f;
+    const float carrier_inc = (float)(2.0f * ORC_PI * adj / b->fs);
+    float phase = 0.0f, symbol_phase = 0.0f;
+    int k = 0;
+    for (int s = 0; s < 6; ++s) {
+        if (BARKER13[s] < 0) symbol_phase = (float)(symbol_phase + ORC_PI);
+        for (int i = 0; i < b->sps; ++i) {
+            tmpl[k++] = cosf(phase + symbol_phase);
+            phase += carrier_inc;
+            if (phase > 2.0f * ORC_PI) phase = (float)(phase - 2.0f * ORC_PI);
+        }
+    }
+    float template_energy = 0;
+    for (int j = 0; j < n; ++j) template_energy += tmpl[j] * tmpl[j];
+    int fine_start = coarse - b->sps > 0 ? coarse - b->sps : 0;
+    int fine_end = (int)b->L - n < coarse + b->sps ? (int)b->L - n : coarse + b->sps;
+    float best_corr = -1;
+    int best = coarse;
+    for (int i = fine_start; i <= fine_end; ++i) {
+        float corr = 0, sig = 0;
+        for (int j = 0; j < n; ++j) {
+            corr += b->x[i + j] * tmpl[j];
+            sig += b->x[i + j] * b->x[i + j];
+        }
+        const float norm = sqrtf(sig * template_energy);
+        if (norm < 1e-10f) continue;
+        const float nc = fabsf(corr) / norm;
+        if (nc > best_corr) { best_corr = nc; best = i; }
+    }
+    free(tmpl);
+    return best;
+}
+
+static float bk_initial_phase(const bk_t* b, int start, float est_cfo) {   /* estimateInitialPhaseOffset, :659-704 */
+    float errs[16];
+    int ne = 0;
+    float pr = 0, pi = 0;
+    for (int s = 0; s <= 10 && s < BK_DIFFS; ++s) {
+        const int offset = start + s * b->sps;
+        if (offset + b->sps > (int)b->L) break;
+        float cr, ci;
+        dpsk_correlate(b->x + offset, b->sps, b->ccos, b->csin, &cr, &ci);
+        if (s > 0 && hypotf(pr, pi) > 0.01f && hypotf(cr, ci) > 0.01f) {
+            float dr, di;
+            cmulf(cr, ci, pr, -pi, &dr, &di);
+            float measured = atan2f(di, dr);
+            const float expected = b->pattern[s - 1] > 0 ? 0.0f : (float)ORC_PI;
+            const float cfo_phase = (float)(2.0f * ORC_PI * est_cfo * b->sps / b->fs);
+            measured -= cfo_phase;
+            float error = measured - expected;
+            while (error > ORC_PI) error = (float)(error - 2.0f * ORC_PI);
+            while (error < -ORC_PI) error = (float)(error + 2.0f * ORC_PI);
+            errs[ne++] = error;
+        }
+        pr = cr;
+        pi = ci;
+    }
+    if (ne == 0) return 0.0f;
+    float sum = 0;
+    for (int i = 0; i < ne; ++i) sum += errs[i];
+    return sum / (float)ne;
+}
+
+/* Returns data_start (> 0) or -1; *est_cfo / *phase_off = the members findPreamble leaves behind (0 when it fails early). */
+long orc_dpsk_find_preamble(int sps, float fc, float fs, const float* x, size_t L, float* est_cfo, float* phase_off) {
+    *est_cfo = 0.0f;
+    *phase_off = 0.0f;
+    if (sps <= 0) return -1;
+    const int preamble_samples = BK_SYMS * sps;
+    if ((int)L < preamble_samples + preamble_samples / 2) return -1;
+    float energy = 0;
+    const size_t check = L < (size_t)(preamble_samples * 2) ? L : (size_t)(preamble_samples * 2);
+    for (size_t i = 0; i < check; ++i) energy += x[i] * x[i];
+    const float rms = sqrtf(energy / (float)check);
+    if (rms < 0.01f) return -1;
+    float* ccos = (float*)malloc(sizeof(float) * (size_t)sps * 2);
+    float* csin = ccos + sps;
+    const float carrier_inc = (float)(2.0f * ORC_PI * fc / fs);        /* :315 */
+    for (int i = 0; i < sps; ++i) {
+        const float phase = carrier_inc * (float)i;
+        csin[i] = sinf(phase);
+        ccos[i] = cosf(phase);
+    }
+    bk_t b = {x, L, sps, ccos, csin, fc, fs, {0}};
+    for (int s = 1; s < BK_SYMS; ++s) b.pattern[s - 1] = BARKER13[s % 13];
+    const int limit = preamble_samples * 4;
+    const int max_search = (int)L - preamble_samples < limit ? (int)L - preamble_samples : limit;
+    float best_score = 0, sum_scores = 0;
+    int best_offset = -1, num_scores = 0;
+    for (int start = 0; start < max_search; start += sps) {
+        const float score = bk_score(&b, start, 0.001f);
+        sum_scores += score;
+        num_scores++;
+        if (score > best_score) { best_score = score; best_offset = start; }
+    }
+    const float global_avg = num_scores > 0 ? sum_scores / (float)num_scores : 0;
+    if (best_offset >= 0 && best_score > 0.80f * 0.7f) {
+        const int fine_start = best_offset - sps > 0 ? best_offset - sps : 0;
+        const int fine_end = max_search < best_offset + sps ? max_search : best_offset + sps;
+        for (int start = fine_start; start < fine_end; ++start) {
+            const float score = bk_score(&b, start, 0.001f);
+            if (score > best_score) { best_score = score; best_offset = start; }
+        }
+    }
+    long result = -1;
+    if (!(best_score < 0.80f) && !(global_avg > 0 && best_score < global_avg * 1.3f)) {
+        const float cfo = bk_cfo_tolerant(&b, best_offset);
+        *est_cfo = cfo;
+        if (fabsf(cfo) < 0.5f) best_offset = bk_refine_mf(&b, best_offset);
+        *phase_off = bk_initial_phase(&b, best_offset, cfo);
+        result = (long)best_offset + preamble_samples;
+    }
+    free(ccos);
+    return result;
+}

@@ -100,6 +100,22 @@ long ref_dpsk_demod_soft_ex(int mod, int sps, float fc, float fs, const float* x
     return static_cast<long>(soft.size());
 }
 
+// The receive sequence of tools/test_dpsk_snr.cpp:66-73: findPreamble on the whole frame, then demodulateSoft on the span
+// that starts at the returned data start.  Returns the number of soft bits (0 when no preamble was found).
+long ref_dpsk_receive(int mod, int sps, float fc, float fs, const float* x, size_t L, long* data_start, float* est_cfo,
+                      float* phase_off, float* llr, size_t cap) {
+    Quiet q;
+    DPSKDemodulator d(sc_cfg(mod, sps, fc, fs));
+    const int ds = d.findPreamble(SampleSpan(x, L));
+    *data_start = ds;
+    *est_cfo = d.estimated_cfo_;
+    *phase_off = d.initial_phase_offset_;
+    if (!(ds > 0 && ds < (int)L)) return 0;
+    std::vector<float> soft = d.demodulateSoft(SampleSpan(x + ds, L - ds));
+    for (size_t i = 0; i < soft.size() && i < cap; ++i) llr[i] = soft[i];
+    return static_cast<long>(soft.size());
+}
+
 // MultiCarrierDPSKModulator: generateTrainingSequence() + generateReferenceSymbol() + modulate(data) (no chirp: the
 // frame as processGotChirp sees it after an external chirp detection).
 long ref_mcdpsk_tx(int nc, int sps, int bits, float f_lo, float f_hi, float fs, int training, const uint8_t* data, size_t len,

@@ -258,6 +258,24 @@ def dpsk_demod_soft(mod, sps, samples, data_start, ref_mode=0, est_cfo=0.0, phas
     return out[:n].copy()
 
 
+def dpsk_find_preamble(sps, samples, fc=1500.0, fs=48000.0):
+    """DPSKDemodulator::findPreamble -> (data_start or -1, est_cfo, phase_offset)."""
+    x = _f32(samples)
+    L = lib()
+    L.orc_dpsk_find_preamble.restype = C.c_long
+    cfo, ph = C.c_float(0), C.c_float(0)
+    ds = L.orc_dpsk_find_preamble(sps, C.c_float(fc), C.c_float(fs), _p(x, C.c_float), C.c_size_t(len(x)), C.byref(cfo), C.byref(ph))
+    return int(ds), float(cfo.value), float(ph.value)
+
+
+def dpsk_receive(mod, sps, samples, fc=1500.0, fs=48000.0):
+    """findPreamble + demodulateSoft (tools/test_dpsk_snr.cpp:66-73) -> (llr, data_start, est_cfo, phase_offset)."""
+    ds, cfo, ph = dpsk_find_preamble(sps, samples, fc, fs)
+    if not (0 < ds < len(samples)):
+        return np.zeros(0, np.float32), ds, cfo, ph
+    return dpsk_demod_soft(mod, sps, samples, ds, 1, cfo, ph, fc, fs), ds, cfo, ph
+
+
 def mcdpsk_demod_soft(nc, samples, sps=512, bits=2, f_lo=500.0, f_hi=2500.0, fs=48000.0, training=8):
     x = _f32(samples)
     out = np.zeros(8192, np.float32)

@@ -310,6 +310,19 @@ def dpsk_demod_soft(mod_order, sps, samples, data_start=-1):
     return out[:n].copy(), found.value
 
 
+def dpsk_receive(mod, sps, samples, fc=1500.0, fs=48000.0):
+    """tools/test_dpsk_snr.cpp:66-73: findPreamble + demodulateSoft -> (llr, data_start, est_cfo, phase_offset)."""
+    x = _f32(samples)
+    out = np.zeros(4096, np.float32)
+    L = lib()
+    L.ref_dpsk_receive.restype = C.c_long
+    ds, cfo, ph = C.c_long(0), C.c_float(0), C.c_float(0)
+    n = L.ref_dpsk_receive(mod, sps, C.c_float(fc), C.c_float(fs), _p(x, C.c_float), C.c_size_t(len(x)), C.byref(ds), C.byref(cfo),
+                           C.byref(ph), _p(out, C.c_float), C.c_size_t(len(out)))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), int(ds.value), float(cfo.value), float(ph.value)
+
+
 def time_presynced_decode(cfg, samples, rate):
     x = _f32(samples)
     B, L = x.shape
