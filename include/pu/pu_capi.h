@@ -226,6 +226,15 @@ PU_API pu_status pu_dpsk_demod_soft_batch(pu_dpsk* h, const float* samples, size
                                           float* llr_out, size_t llr_stride, pu_memspace space, void* stream);
 /* DPSKModulator (dpsk.hpp:102-307), host: layout 0 = generatePreamble() (Barker-13 x 3) + modulate(data), the frame of
  * tools/test_dpsk_snr.cpp:47-52; 1 = generateReferenceSymbol() + modulate; 2 = modulate only.  *out_len is always set. */
+/* DPSKDemodulator::findPreamble (Barker-13 x 3 acquisition, dpsk.hpp:338-481, with computeDifferentialScore,
+ * estimateCFOTolerant, refineTimingWithMatchedFilter and estimateInitialPhaseOffset) followed, when llr_out is not NULL, by
+ * demodulateSoft on the span that starts at the returned data start -- the receive sequence of tools/test_dpsk_snr.cpp:66-73
+ * for B frames.  data_start[B] = findPreamble's return value (-1: no preamble), est_cfo_hz[B] / phase_offset[B] = the members it
+ * leaves behind, n_llr[B] = soft bits written to llr_out[b*llr_stride ...] (capped at llr_stride; rows are not cleared).
+ * PU_ERR_UNSUPPORTED for samples_per_symbol > 512. */
+PU_API pu_status pu_dpsk_receive_batch(pu_dpsk* h, const float* samples, size_t B, size_t L, float* llr_out, size_t llr_stride,
+                                       int32_t* n_llr, int32_t* data_start, float* est_cfo_hz, float* phase_offset,
+                                       pu_memspace space, void* stream);
 PU_API pu_status pu_dpsk_tx(const pu_dpsk_config* cfg, int layout, const uint8_t* data, size_t n_bytes, float* out,
                             size_t out_cap, size_t* out_len);
 

@@ -498,6 +498,35 @@ class DpskDemodulator:
     def n_llr(self, L, data_start):
         return max(0, (L - data_start) // self.cfg.samples_per_symbol) * self.bits_per_symbol
 
+    def receive_batch(self, samples, llr_stride=648, want_llr=True):
+        """pu_dpsk_receive_batch: findPreamble + demodulateSoft (tools/test_dpsk_snr.cpp:66-73) for every row of samples [B, L]
+        -> (llr [B, llr_stride], n_llr [B], data_start [B], est_cfo_hz [B], phase_offset [B])."""
+        tor = _is_torch(samples)
+        if tor:
+            import torch
+            assert samples.dtype == torch.float32 and samples.dim() == 2 and samples.is_contiguous()
+            B, L = samples.shape
+            dev = samples.device
+            llr = torch.zeros((B, llr_stride), dtype=torch.float32, device=dev) if want_llr else None
+            n = torch.zeros(B, dtype=torch.int32, device=dev)
+            ds = torch.zeros(B, dtype=torch.int32, device=dev)
+            cfo = torch.zeros(B, dtype=torch.float32, device=dev)
+            ph = torch.zeros(B, dtype=torch.float32, device=dev)
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.float32)
+            if samples.ndim == 1:
+                samples = samples.reshape(1, -1)
+            B, L = samples.shape
+            llr = np.zeros((B, llr_stride), np.float32) if want_llr else None
+            n = np.zeros(B, np.int32)
+            ds = np.zeros(B, np.int32)
+            cfo = np.zeros(B, np.float32)
+            ph = np.zeros(B, np.float32)
+        sp = _space(samples, n, ds, cfo, ph)
+        check(lib().pu_dpsk_receive_batch(self._h, _ptr(samples), C.c_size_t(B), C.c_size_t(L), _ptr(llr), C.c_size_t(llr_stride), _ptr(n),
+                                          _ptr(ds), _ptr(cfo), _ptr(ph), sp, _stream(sp)))
+        return llr, n, ds, cfo, ph
+
     def demod_soft_batch(self, samples, data_start, ref_mode=1, est_cfo=None, phase_off=None, llr_stride=None, llr=None):
         x = _frames(samples)
         B, L = x.shape

@@ -40,7 +40,8 @@ constexpr int kPskChunk = 32;
 __global__ void __launch_bounds__(kPskThreads) dpsk_correlate_kernel(const float* __restrict__ samples, size_t frame_stride,
                                                                      long first_start, int sps, int n_corr,
                                                                      const float* __restrict__ ccos, const float* __restrict__ csin,
-                                                                     float2* __restrict__ corr) {
+                                                                     float2* __restrict__ corr, const int* __restrict__ frame_start,
+                                                                     int has_ref, int L) {
     extern __shared__ float sm[];
     float* tcos = sm;                       // [sps]
     float* tsin = sm + sps;                 // [sps]
@@ -52,6 +53,14 @@ __global__ void __launch_bounds__(kPskThreads) dpsk_correlate_kernel(const float
     }
     __syncthreads();
     const size_t frame = blockIdx.y;
+    // per-frame data start (acquired frames): symbols from frame_start[frame] (minus the reference symbol) to the end of the row
+    const int n_all = n_corr;
+    if (frame_start) {
+        const int st = frame_start[frame];
+        if (!(st > 0 && st < L)) return;                            // no preamble found: no symbols (tools/test_dpsk_snr.cpp:69)
+        first_start = static_cast<long>(st) - has_ref * sps;
+        n_corr = min(n_corr, (L - st) / sps + has_ref);
+    }
     const float* x = samples + frame * frame_stride + first_start;
     const int s0 = (blockIdx.x * (kPskThreads / 32) + warp) * 32;   // first symbol of this warp
     if (s0 >= n_corr) return;
@@ -74,7 +83,7 @@ __global__ void __launch_bounds__(kPskThreads) dpsk_correlate_kernel(const float
             Q = __fsub_rn(Q, __fmul_rn(xv, tsin[c0 + i]));
         }
     }
-    if (s < n_corr) corr[frame * n_corr + s] = make_float2(__fdiv_rn(I, static_cast<float>(sps)), __fdiv_rn(Q, static_cast<float>(sps)));
+    if (s < n_corr) corr[frame * n_all + s] = make_float2(__fdiv_rn(I, static_cast<float>(sps)), __fdiv_rn(Q, static_cast<float>(sps)));
 }
 
 __device__ __forceinline__ float wrap_0_2pi(float phase) {   // while (phase < 0) phase += 2 pi; while (phase >= 2 pi) phase -= 2 pi
@@ -86,11 +95,18 @@ __device__ __forceinline__ float wrap_0_2pi(float phase) {   // while (phase < 0
 
 __global__ void dpsk_llr_kernel(const float2* __restrict__ corr, int n_corr, int has_ref, int n_sym, int mod, int sps, float sample_rate,
                                 const float* __restrict__ est_cfo, const float* __restrict__ phase_off, size_t B,
-                                float* __restrict__ llr, size_t llr_stride) {
+                                float* __restrict__ llr, size_t llr_stride, const int* __restrict__ frame_start, int L,
+                                int* __restrict__ n_llr) {
     const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
     if (g >= B * static_cast<size_t>(n_sym)) return;
     const size_t frame = g / n_sym;
     const int s = static_cast<int>(g - frame * n_sym);
+    if (frame_start) {
+        const int st = frame_start[frame];
+        const int mine = (st > 0 && st < L) ? (L - st) / sps : 0;
+        if (s == 0 && n_llr) n_llr[frame] = static_cast<int>(min(static_cast<size_t>(mine) * (mod + 1), llr_stride));
+        if (s >= mine) return;
+    }
     const float2* c = corr + frame * n_corr + has_ref;
     const float2 cur = c[s];
     const float2 prev = (s > 0 || has_ref) ? c[s - 1] : make_float2(1.0f, 0.0f);   // prev_symbol_ (:840, :889-892)
@@ -122,6 +138,234 @@ __global__ void dpsk_llr_kernel(const float2* __restrict__ corr, int n_corr, int
     for (int b = 0; b < bps; ++b) {
         const size_t pos = static_cast<size_t>(s) * bps + b;
         if (pos < llr_stride) out[pos] = l[b];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- Barker-13 acquisition
+// DPSKDemodulator::findPreamble (src/psk/dpsk.hpp:338-481) for B frames, one frame per CTA (DPSK half):
+// energy gate, coarse search at one-symbol steps, fine search at one-sample steps around the best coarse position
+// (computeDifferentialScore :489-546), threshold + global-outlier tests, estimateCFOTolerant (:550-593),
+// refineTimingWithMatchedFilter (:708-771, only when |cfo| < 0.5 Hz), estimateInitialPhaseOffset (:659-704).
+// Every ordered sum of the reference is an ordered sum here (one thread per sum); what is parallel is what the reference
+// computes independently: the symbol correlations at different offsets, the scores of different start positions, the
+// matched-filter candidates.  The symbol correlation at sample offset o is shared by every start r = o - s * sps, so the fine
+// search evaluates 40 * sps correlations once (shared memory) instead of 2 * sps * 39.
+constexpr int kBkSyms = 39, kBkDiffs = 38, kBkThreads = 512;
+__constant__ int kBarker13[13] = {1, 1, 1, 1, 1, -1, -1, 1, 1, -1, 1, -1, 1};
+__device__ __forceinline__ int bk_pattern(int i) { return kBarker13[(i + 1) % 13]; }   // expected_pattern[i] = BARKER13[(i + 1) % 13]
+
+// correlateSymbol (:777-787) of the sps samples at x
+__device__ __forceinline__ float2 bk_correlate(const float* __restrict__ x, int sps, const float* tcos, const float* tsin) {
+    float I = 0.0f, Q = 0.0f;
+    for (int i = 0; i < sps; ++i) {
+        const float v = x[i];
+        I = __fadd_rn(I, __fmul_rn(v, tcos[i]));
+        Q = __fsub_rn(Q, __fmul_rn(v, tsin[i]));
+    }
+    return make_float2(__fdiv_rn(I, static_cast<float>(sps)), __fdiv_rn(Q, static_cast<float>(sps)));
+}
+
+// computeDifferentialScore from the symbol correlations c[0], c[stride], ... (:496-545)
+__device__ float bk_score(const float2* c, int stride) {
+    float total_energy = 0.0f;
+    for (int s = 0; s < kBkSyms; ++s) total_energy = __fadd_rn(total_energy, cnorm(c[s * stride]));
+    if (total_energy < __fmul_rn(0.001f, static_cast<float>(kBkSyms))) return 0.0f;
+    float2 sum = make_float2(0.0f, 0.0f);
+    float magnitude_sum = 0.0f;
+    for (int i = 0; i < kBkDiffs; ++i) {
+        const float2 diff = cmul(c[(i + 1) * stride], cconj(c[i * stride]));
+        const float magnitude = cabs_ref(diff);
+        if (magnitude < 1e-10f) continue;
+        const float2 dn = make_float2(__fdiv_rn(diff.x, magnitude), __fdiv_rn(diff.y, magnitude));
+        sum = cadd(sum, cmul(dn, make_float2(static_cast<float>(bk_pattern(i)), -0.0f)));   // diff_norm * conj(Complex(expected, 0))
+        magnitude_sum = __fadd_rn(magnitude_sum, magnitude);
+    }
+    if (magnitude_sum < 1e-10f) return 0.0f;
+    return __fdiv_rn(cabs_ref(sum), static_cast<float>(kBkDiffs));
+}
+
+struct BkShared {
+    float scores[kBkThreads * 2];   // coarse (<= 4 * 39) then fine (<= 2 * sps) scores
+    float2 c0[4 * kBkSyms + kBkSyms + 4];
+    float best_score, global_avg, cfo, rms;
+    int best_offset, fine_start, fine_end, result;
+    float red_c[kBkThreads / 32];
+    int red_i[kBkThreads / 32];
+    float2 ph[12];
+};
+
+__global__ void __launch_bounds__(kBkThreads) dpsk_find_preamble_kernel(const float* __restrict__ samples, size_t frame_stride, int L, int sps,
+                                                                        float fs, const float* __restrict__ ccos, const float* __restrict__ csin,
+                                                                        const float* __restrict__ mf_template, float mf_energy,
+                                                                        int* __restrict__ out_start, float* __restrict__ out_cfo,
+                                                                        float* __restrict__ out_phase) {
+    extern __shared__ __align__(16) unsigned char bk_smem[];
+    float* tcos = reinterpret_cast<float*>(bk_smem);                 // [sps]
+    float* tsin = tcos + sps;                                        // [sps]
+    float2* C = reinterpret_cast<float2*>(tsin + sps);               // [40 * sps] fine correlations; later the matched-filter template
+    __shared__ BkShared S;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const float* x = samples + static_cast<size_t>(blockIdx.x) * frame_stride;
+    const int preamble = kBkSyms * sps;
+    for (int i = tid; i < sps; i += T) { tcos[i] = __ldg(&ccos[i]); tsin[i] = __ldg(&csin[i]); }
+    if (tid == 0) { S.result = -1; S.cfo = 0.0f; S.best_offset = -1; S.best_score = 0.0f; }
+    __syncthreads();
+    bool alive = L >= preamble + preamble / 2;                        // :354-355
+    const int max_search = min(L - preamble, preamble * 4);           // :393
+    const int n_starts = alive ? (max_search + sps - 1) / sps : 0;    // coarse positions 0, sps, ... < max_search
+    // ---- energy gate (:359-368, thread 0) next to the coarse symbol correlations (all other warps)
+    if (alive) {
+        if (tid == 0) {
+            const int check = min(L, preamble * 2);
+            float energy = 0.0f;
+            for (int i = 0; i < check; ++i) energy = __fadd_rn(energy, __fmul_rn(x[i], x[i]));
+            S.rms = __fsqrt_rn(__fdiv_rn(energy, static_cast<float>(check)));
+        } else if (tid >= 32) {
+            for (int m = tid - 32; m < n_starts + kBkDiffs; m += T - 32) S.c0[m] = bk_correlate(x + m * sps, sps, tcos, tsin);
+        }
+    }
+    __syncthreads();
+    alive = alive && !(S.rms < 0.01f);
+    if (alive) {
+        for (int m = tid; m < n_starts; m += T) S.scores[m] = bk_score(S.c0 + m, 1);
+        __syncthreads();
+        if (tid == 0) {                                               // :403-414, in order
+            float best = 0.0f, sum = 0.0f;
+            int bo = -1;
+            for (int m = 0; m < n_starts; ++m) {
+                const float sc = S.scores[m];
+                sum = __fadd_rn(sum, sc);
+                if (sc > best) { best = sc; bo = m * sps; }
+            }
+            S.best_score = best;
+            S.best_offset = bo;
+            S.global_avg = n_starts > 0 ? __fdiv_rn(sum, static_cast<float>(n_starts)) : 0.0f;
+            S.fine_start = max(0, bo - sps);
+            S.fine_end = min(max_search, bo + sps);
+        }
+        __syncthreads();
+        const bool fine = S.best_offset >= 0 && S.best_score > __fmul_rn(0.80f, 0.7f);   // :417
+        if (fine) {
+            const int f0 = S.fine_start, n_fine = S.fine_end - S.fine_start;
+            const int n_off = n_fine + kBkDiffs * sps;
+            for (int o = tid; o < n_off; o += T) C[o] = bk_correlate(x + f0 + o, sps, tcos, tsin);
+            __syncthreads();
+            for (int r = tid; r < n_fine; r += T) S.scores[r] = bk_score(C + r, sps);
+            __syncthreads();
+            if (tid == 0) {                                           // :421-428, in order
+                float best = S.best_score;
+                int bo = S.best_offset;
+                for (int r = 0; r < n_fine; ++r)
+                    if (S.scores[r] > best) { best = S.scores[r]; bo = f0 + r; }
+                S.best_score = best;
+                S.best_offset = bo;
+            }
+            __syncthreads();
+        }
+        alive = fine && !(S.best_score < 0.80f) && !(S.global_avg > 0.0f && S.best_score < __fmul_rn(S.global_avg, 1.3f));   // :434-448
+    }
+    if (alive) {
+        // ---- estimateCFOTolerant(best_offset) from the correlations the fine search left in C (:550-593)
+        if (tid == 0) {
+            const float2* c = C + (S.best_offset - S.fine_start);
+            float2 corr = make_float2(0.0f, 0.0f);
+            int nd = 0;
+            float2 prev = make_float2(0.0f, 0.0f);
+            for (int s = 0; s <= kBkDiffs; ++s) {
+                const float2 cur = c[s * sps];
+                if (s > 0 && cabs_ref(prev) > 0.01f && cabs_ref(cur) > 0.01f) {
+                    float2 d = cmul(cur, cconj(prev));
+                    const float m = cabs_ref(d);
+                    d = make_float2(__fdiv_rn(d.x, m), __fdiv_rn(d.y, m));
+                    // diffs are compacted and paired with expected_pattern[position in the list] (:575-579)
+                    corr = cadd(corr, cmul(d, make_float2(static_cast<float>(bk_pattern(nd)), -0.0f)));
+                    ++nd;
+                }
+                prev = cur;
+            }
+            float cfo = 0.0f;
+            if (nd >= 10) {
+                const float phase_offset = refmath::atan2f_ref(corr.y, corr.x);
+                const float symbol_duration = __fdiv_rn(static_cast<float>(sps), fs);
+                cfo = -static_cast<float>(__ddiv_rn(static_cast<double>(phase_offset),
+                                                    __dmul_rn(2.0f * 3.14159265358979323846, static_cast<double>(symbol_duration))));
+            }
+            S.cfo = cfo;
+        }
+        __syncthreads();
+        // ---- refineTimingWithMatchedFilter(best_offset, cfo_hz = 0) when |cfo| < 0.5 (:457-461, :708-771)
+        if (fabsf(S.cfo) < 0.5f) {
+            const int n = 6 * sps;
+            float* tm = reinterpret_cast<float*>(C);
+            for (int j = tid; j < n; j += T) tm[j] = __ldg(&mf_template[j]);
+            __syncthreads();
+            const int coarse = S.best_offset;
+            const int fs2 = max(0, coarse - sps), fe2 = min(L - n, coarse + sps);
+            float bc = -1.0f;
+            int bi = coarse;
+            for (int i = fs2 + tid; i <= fe2; i += T) {
+                const float* r = x + i;
+                float corr = 0.0f, sig = 0.0f;
+                for (int j = 0; j < n; ++j) {
+                    const float v = r[j];
+                    corr = __fadd_rn(corr, __fmul_rn(v, tm[j]));
+                    sig = __fadd_rn(sig, __fmul_rn(v, v));
+                }
+                const float norm = __fsqrt_rn(__fmul_rn(sig, mf_energy));
+                if (norm < 1e-10f) continue;
+                const float nc = __fdiv_rn(fabsf(corr), norm);
+                if (nc > bc) { bc = nc; bi = i; }
+            }
+            // first maximum in ascending i: larger value wins, equal value -> smaller index; threads without a candidate hold -1
+            for (int o = 16; o > 0; o >>= 1) {
+                const float oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oc > bc || (oc == bc && oc >= 0.0f && oi < bi)) { bc = oc; bi = oi; }
+            }
+            if ((tid & 31) == 0) { S.red_c[tid >> 5] = bc; S.red_i[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < T / 32; ++w)
+                    if (S.red_c[w] > bc || (S.red_c[w] == bc && bc >= 0.0f && S.red_i[w] < bi)) { bc = S.red_c[w]; bi = S.red_i[w]; }
+                S.best_offset = bc >= 0.0f ? bi : coarse;
+            }
+            __syncthreads();
+        }
+        // ---- estimateInitialPhaseOffset(best_offset) (:659-704): 11 symbol correlations at the final position
+        const int bo = S.best_offset;
+        if (tid < 11 && bo + tid * sps + sps <= L) S.ph[tid] = bk_correlate(x + bo + tid * sps, sps, tcos, tsin);
+        __syncthreads();
+        if (tid == 0) {
+            const double two_pi = 2.0f * 3.14159265358979323846, pi = 3.14159265358979323846;
+            float sum = 0.0f;
+            int ne = 0;
+            float2 prev = make_float2(0.0f, 0.0f);
+            for (int s = 0; s <= 10 && s < kBkDiffs; ++s) {
+                if (bo + s * sps + sps > L) break;
+                const float2 cur = S.ph[s];
+                if (s > 0 && cabs_ref(prev) > 0.01f && cabs_ref(cur) > 0.01f) {
+                    const float2 d = cmul(cur, cconj(prev));
+                    float measured = refmath::atan2f_ref(d.y, d.x);
+                    const float expected = bk_pattern(s - 1) > 0 ? 0.0f : static_cast<float>(pi);
+                    const float cfo_phase = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(two_pi, static_cast<double>(S.cfo)), static_cast<double>(sps)),
+                                                                         static_cast<double>(fs)));
+                    measured = __fsub_rn(measured, cfo_phase);
+                    float error = __fsub_rn(measured, expected);
+                    while (static_cast<double>(error) > pi) error = static_cast<float>(__dsub_rn(static_cast<double>(error), two_pi));
+                    while (static_cast<double>(error) < -pi) error = static_cast<float>(__dadd_rn(static_cast<double>(error), two_pi));
+                    sum = __fadd_rn(sum, error);   // the reference sums the list afterwards, in the same order
+                    ++ne;
+                }
+                prev = cur;
+            }
+            out_phase[blockIdx.x] = ne ? __fdiv_rn(sum, static_cast<float>(ne)) : 0.0f;
+            out_cfo[blockIdx.x] = S.cfo;
+            out_start[blockIdx.x] = bo + preamble;
+        }
+    } else if (tid == 0) {
+        out_start[blockIdx.x] = -1;
+        out_cfo[blockIdx.x] = 0.0f;
+        out_phase[blockIdx.x] = 0.0f;
     }
 }
 
@@ -232,6 +476,8 @@ struct pu_dpsk {
     int device = 0;
     pu_dpsk_config cfg{};
     pu::PskDevMem d_cos, d_sin;
+    pu::PskDevMem d_mf;        // matched-filter template of refineTimingWithMatchedFilter (cfo 0), 6 symbols
+    float mf_energy = 0.0f;
     pu::Buffer corr;
 };
 
@@ -303,7 +549,90 @@ pu_status pu_dpsk_create(pu_ctx* ctx, const pu_dpsk_config* cfg, pu_dpsk** out) 
     pu_status s;
     if ((s = h->d_cos.upload(cs.data(), cs.size())) != PU_OK) return s;
     if ((s = h->d_sin.upload(sn.data(), sn.size())) != PU_OK) return s;
+    {   // refineTimingWithMatchedFilter's template for cfo_hz = 0 (dpsk.hpp:712-735)
+        static const int barker[6] = {1, 1, 1, 1, 1, -1};
+        std::vector<float> tm;
+        tm.reserve(static_cast<size_t>(6) * n);
+        const float adjusted = cfg->carrier_freq + 0.0f;
+        const float carrier_inc = static_cast<float>(2.0f * 3.14159265358979323846 * adjusted / cfg->sample_rate);
+        float phase = 0.0f, symbol_phase = 0.0f;
+        for (int sy = 0; sy < 6; ++sy) {
+            if (barker[sy] < 0) symbol_phase = static_cast<float>(symbol_phase + 3.14159265358979323846);
+            for (int i = 0; i < n; ++i) {
+                tm.push_back(std::cos(phase + symbol_phase));
+                phase += carrier_inc;
+                if (phase > 2.0f * 3.14159265358979323846) phase = static_cast<float>(phase - 2.0f * 3.14159265358979323846);
+            }
+        }
+        float e = 0.0f;
+        for (float t : tm) e += t * t;
+        h->mf_energy = e;
+        if ((s = h->d_mf.upload(tm.data(), tm.size())) != PU_OK) return s;
+    }
     *out = h.release();
+    return PU_OK;
+}
+
+static pu_status dpsk_launch(pu_dpsk* h, const float* d_samples, size_t B, size_t L, size_t data_start, int ref_mode,
+                             const float* d_cfo, const float* d_poff, float* d_llr, size_t llr_stride, cudaStream_t st,
+                             const int* d_fstart, int* d_nllr);
+
+static pu_status dpsk_find_launch(pu_dpsk* h, const float* d_samples, size_t B, size_t L, int* d_start, float* d_cfo, float* d_phase,
+                                  cudaStream_t st) {
+    const int sps = static_cast<int>(h->cfg.samples_per_symbol);
+    if (sps > 512) {
+        pu::set_error("pu_dpsk_find_preamble_batch: samples_per_symbol > 512 is not supported (shared-memory budget of the fine search)");
+        return PU_ERR_UNSUPPORTED;
+    }
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(sps) + 2 * 40 * static_cast<size_t>(sps));
+    (void)cudaGetLastError();
+    cudaFuncSetAttribute(pu::dpsk_find_preamble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    pu::dpsk_find_preamble_kernel<<<static_cast<unsigned>(B), pu::kBkThreads, smem, st>>>(
+        d_samples, L, static_cast<int>(L), sps, h->cfg.sample_rate, static_cast<const float*>(h->d_cos.p), static_cast<const float*>(h->d_sin.p),
+        static_cast<const float*>(h->d_mf.p), h->mf_energy, d_start, d_cfo, d_phase);
+    h->ctx->launches.fetch_add(1);
+    PU_CUDA_TRY(cudaGetLastError());
+    return PU_OK;
+}
+
+pu_status pu_dpsk_receive_batch(pu_dpsk* h, const float* samples, size_t B, size_t L, float* llr_out, size_t llr_stride, int32_t* n_llr,
+                                int32_t* data_start, float* est_cfo_hz, float* phase_offset, pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_dpsk_receive_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && data_start && est_cfo_hz && phase_offset, "pu_dpsk_receive_batch: NULL data pointer");
+    PU_REQUIRE(L < (1u << 30), "pu_dpsk_receive_batch: frame too long");
+    PU_REQUIRE(!llr_out || (llr_stride > 0 && n_llr), "pu_dpsk_receive_batch: llr_out needs llr_stride and n_llr");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    const int sps = static_cast<int>(h->cfg.samples_per_symbol);
+    pu_status s;
+    if (space == PU_MEM_DEVICE) {
+        if ((s = dpsk_find_launch(h, samples, B, L, data_start, est_cfo_hz, phase_offset, st)) != PU_OK) return s;
+        if (!llr_out || L <= static_cast<size_t>(39) * sps) return PU_OK;
+        return dpsk_launch(h, samples, B, L, static_cast<size_t>(39) * sps, 1, est_cfo_hz, phase_offset, llr_out, llr_stride, st, data_start, n_llr);
+    }
+    pu::PskDevMem dx, dst, dc, dp, dl, dn;
+    std::vector<float> zf(std::max<size_t>(B * std::max<size_t>(llr_stride, 1), B), 0.0f);
+    std::vector<int32_t> zi(B, 0);
+    if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
+    if ((s = dst.upload(zi.data(), B)) != PU_OK) return s;
+    if ((s = dc.upload(zf.data(), B)) != PU_OK) return s;
+    if ((s = dp.upload(zf.data(), B)) != PU_OK) return s;
+    if ((s = dn.upload(zi.data(), B)) != PU_OK) return s;
+    if (llr_out && (s = dl.upload(zf.data(), B * llr_stride)) != PU_OK) return s;
+    s = pu_dpsk_receive_batch(h, static_cast<const float*>(dx.p), B, L, llr_out ? static_cast<float*>(dl.p) : nullptr, llr_stride,
+                              static_cast<int32_t*>(dn.p), static_cast<int32_t*>(dst.p), static_cast<float*>(dc.p), static_cast<float*>(dp.p),
+                              PU_MEM_DEVICE, st);
+    if (s != PU_OK) return s;
+    PU_CUDA_TRY(cudaStreamSynchronize(st));
+    PU_CUDA_TRY(cudaMemcpy(data_start, dst.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    PU_CUDA_TRY(cudaMemcpy(est_cfo_hz, dc.p, B * sizeof(float), cudaMemcpyDeviceToHost));
+    PU_CUDA_TRY(cudaMemcpy(phase_offset, dp.p, B * sizeof(float), cudaMemcpyDeviceToHost));
+    if (llr_out) {
+        PU_CUDA_TRY(cudaMemcpy(llr_out, dl.p, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
+        PU_CUDA_TRY(cudaMemcpy(n_llr, dn.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
     return PU_OK;
 }
 
@@ -317,8 +646,10 @@ void pu_dpsk_destroy(pu_dpsk* h) {
 int pu_dpsk_bits_per_symbol(const pu_dpsk* h) { return h ? static_cast<int>(h->cfg.modulation) + 1 : -1; }
 
 static pu_status dpsk_launch(pu_dpsk* h, const float* d_samples, size_t B, size_t L, size_t data_start, int ref_mode,
-                             const float* d_cfo, const float* d_poff, float* d_llr, size_t llr_stride, cudaStream_t st) {
+                             const float* d_cfo, const float* d_poff, float* d_llr, size_t llr_stride, cudaStream_t st,
+                             const int* d_fstart, int* d_nllr) {
     const int sps = static_cast<int>(h->cfg.samples_per_symbol);
+    // with per-frame starts data_start is the smallest possible start (one preamble), which bounds the symbol count
     const int has_ref = (ref_mode == 1 && data_start >= static_cast<size_t>(sps)) ? 1 : 0;
     const int n_sym = static_cast<int>((L - data_start) / sps);
     if (n_sym == 0) return PU_OK;
@@ -335,12 +666,14 @@ static pu_status dpsk_launch(pu_dpsk* h, const float* d_samples, size_t B, size_
         const dim3 grid(static_cast<unsigned>((n_corr + pu::kPskThreads - 1) / pu::kPskThreads), static_cast<unsigned>(nb));
         pu::dpsk_correlate_kernel<<<grid, pu::kPskThreads, smem, st>>>(d_samples + off * L, L, static_cast<long>(data_start) - has_ref * sps, sps,
                                                                      n_corr, static_cast<const float*>(h->d_cos.p),
-                                                                     static_cast<const float*>(h->d_sin.p), corr + off * n_corr);
+                                                                     static_cast<const float*>(h->d_sin.p), corr + off * n_corr,
+                                                                     d_fstart ? d_fstart + off : nullptr, has_ref, static_cast<int>(L));
         h->ctx->launches.fetch_add(1);
     }
     const size_t total = B * static_cast<size_t>(n_sym);
     pu::dpsk_llr_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, st>>>(corr, n_corr, has_ref, n_sym, static_cast<int>(h->cfg.modulation),
-                                                                                  sps, h->cfg.sample_rate, d_cfo, d_poff, B, d_llr, llr_stride);
+                                                                                  sps, h->cfg.sample_rate, d_cfo, d_poff, B, d_llr, llr_stride, d_fstart,
+                                                                                  static_cast<int>(L), d_nllr);
     h->ctx->launches.fetch_add(1);
     PU_CUDA_TRY(cudaGetLastError());
     return PU_OK;
@@ -358,10 +691,10 @@ pu_status pu_dpsk_demod_soft_batch(pu_dpsk* h, const float* samples, size_t B, s
     pu_ctx* ctx = h->ctx;
     PU_CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = pu::pick_stream(ctx, stream, space);
-    if (space == PU_MEM_DEVICE) return dpsk_launch(h, samples, B, L, data_start, ref_mode, est_cfo_hz, phase_offset, llr_out, llr_stride, st);
+    if (space == PU_MEM_DEVICE) return dpsk_launch(h, samples, B, L, data_start, ref_mode, est_cfo_hz, phase_offset, llr_out, llr_stride, st, nullptr, nullptr);
     return psk_host_call(ctx, st, samples, B, L, est_cfo_hz, phase_offset, llr_out, llr_stride, nullptr,
                          [&](const float* din, size_t nb, const float* c, const float* p, float* dout, float*) {
-                             return dpsk_launch(h, din, nb, L, data_start, ref_mode, c, p, dout, llr_stride, st);
+                             return dpsk_launch(h, din, nb, L, data_start, ref_mode, c, p, dout, llr_stride, st, nullptr, nullptr);
                          });
 }
 

@@ -188,6 +188,29 @@ def acquire_vectors():
     np.savez_compressed(os.path.join(HERE, "acquire_golden.npz"), **out)
 
 
+def dpsk_acquire_vectors():
+    """Barker acquisition (DPSK half): the receive sequence of tools/test_dpsk_snr.cpp:66-73 on two D8PSK
+    frames (98k samples each), one found at 0 dB behind 300 samples of noise, one lost at -25 dB."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from projectultra_b200 import capi
+    rng = np.random.default_rng(20261019)
+    out = {}
+    cfg = capi.dpsk_config(2, 384)
+    for i, (snr, lead) in enumerate(((0.0, 300), (-25.0, 0))):
+        data = rng.integers(0, 256, 20, dtype=np.uint8)
+        tx = R.dpsk_tx(2, 384, R.ldpc_encode(R.R1_4, data), 0)
+        tx = (tx * (np.float32(0.5) / np.abs(tx).max())).astype(np.float32)
+        w = np.concatenate([np.zeros(lead, np.float32), tx])
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        rx = (w + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(w))).astype(np.float32)
+        llr, ds, cfo, ph = R.dpsk_receive(2, 384, rx)
+        out[f"d{i}_rx"] = rx
+        out[f"d{i}_llr"] = llr
+        out[f"d{i}_info"] = np.array([ds], np.int64)
+        out[f"d{i}_cfo_phase"] = np.array([cfo, ph], np.float32)
+    np.savez_compressed(os.path.join(HERE, "dpsk_acquire_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
     ldpc_vectors()
@@ -195,6 +218,7 @@ if __name__ == "__main__":
     misc_vectors()
     psk_vectors()
     acquire_vectors()
+    dpsk_acquire_vectors()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

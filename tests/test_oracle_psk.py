@@ -83,3 +83,40 @@ def test_psk_tx_golden(golden):
         assert same_bits(tx[: 41 * 192], g[f"sc{mod}_tx_head"])
     for nc, bits in ((8, 2), (3, 2), (5, 1)):
         assert same_bits(capi.mcdpsk_tx(capi.mcdpsk_config(nc, bits), g[f"mc{nc}_data"]), g[f"mc{nc}_tx"])
+
+
+def _words(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_golden_dpsk_acquisition(golden):
+    """SURVEY §8f next-2 (DPSK half): the oracle's DPSKDemodulator::findPreamble + demodulateSoft restatement against
+    vectors produced by the unmodified reference (tools/test_dpsk_snr.cpp:66-73 receive sequence)."""
+    g = golden["dpsk_acquire"]
+    for i in range(2):
+        llr, ds, cfo, ph = O.dpsk_receive(2, 384, g[f"d{i}_rx"])
+        assert ds == int(g[f"d{i}_info"][0])
+        assert (_words(np.array([cfo, ph], np.float32)) == _words(g[f"d{i}_cfo_phase"])).all()
+        want = g[f"d{i}_llr"]
+        assert len(llr) == len(want) and (_words(llr) == _words(want)).all()
+
+
+@pytest.mark.parametrize("mod", [0, 1, 2])
+def test_dpsk_acquisition_matches_reference(mod):
+    if not R.available():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    rng = np.random.default_rng(40 + mod)
+    found = 0
+    for snr, lead in ((12.0, 0), (2.0, 411), (-5.0, 64), (-11.0, 700), (-18.0, 250), (-30.0, 0)):
+        data = rng.integers(0, 256, 20, dtype=np.uint8)
+        tx = R.dpsk_tx(mod, 384, R.ldpc_encode(R.R1_4, data), 0)
+        tx = (tx * (np.float32(0.5) / np.abs(tx).max())).astype(np.float32)
+        w = np.concatenate([np.zeros(lead, np.float32), tx])
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        rx = (w + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(w))).astype(np.float32)
+        rl, rds, rcfo, rph = R.dpsk_receive(mod, 384, rx)
+        ol, ods, ocfo, oph = O.dpsk_receive(mod, 384, rx)
+        assert rds == ods and (_words(np.array([rcfo, rph], np.float32)) == _words(np.array([ocfo, oph], np.float32))).all(), (snr, lead)
+        assert len(rl) == len(ol) and (_words(rl) == _words(ol)).all(), (snr, lead)
+        found += rds > 0
+    assert found >= 3
