@@ -124,7 +124,8 @@ class LinkSim:
     frame can be regenerated, and ranks take disjoint trial ranges with no data exchange."""
 
     def __init__(self, ctx, cfg, channel="awgn", payload_bytes=40, pool=64, snr_convention=None, pool_seed=12345,
-                 max_iter=50, device=None, code_rate=None, peak=None, layout="presynced", chunk=960, fresh_payload=False):
+                 max_iter=50, device=None, code_rate=None, peak=None, layout="presynced", chunk=960, fresh_payload=False,
+                 acquire=False):
         import torch
         self.ctx, self.cfg = ctx, cfg
         self.device = device or torch.device("cuda", ctx.device)
@@ -158,6 +159,10 @@ class LinkSim:
         self.ldpc = capi.LdpcDecoder(ctx, rate, max_iter)
         # fresh_payload: every frame carries its own random payload, encoded and modulated on the GPU (pu_ofdm_tx_batch), as the
         # reference's tools do per trial (tools/test_mode_snr.cpp:44-56), instead of indexing a host-built pool of waveforms
+        # acquire (single-carrier DPSK): Barker acquisition by findPreamble instead of genie timing, i.e. the receive sequence of
+        # tools/test_dpsk_snr.cpp:66-73; a frame without preamble or with fewer than 648 soft bits is lost
+        self.acquire = bool(acquire)
+        assert not self.acquire or self.kind == "dpsk", "acquire=True is the DPSK Barker path; OFDM uses layout='sc'"
         self.fresh_payload = bool(fresh_payload)
         self.peak = peak
         assert not self.fresh_payload or self.kind == "ofdm", "the GPU transmitter covers the OFDM waveforms"
@@ -184,6 +189,10 @@ class LinkSim:
             return out[0]
         if self.kind == "ofdm":
             return self.demod.presynced_batch(rx, 2, llr_stride=648, llr=llr, want_aux=False)[0]
+        if self.kind == "dpsk" and self.acquire:
+            out = self.demod.receive_batch(rx, llr_stride=648)
+            self.last_n_llr, self.last_sync = out[1], out[2]
+            return out[0]
         if self.kind == "dpsk":
             return self.demod.demod_soft_batch(rx, self.data_start, 1, llr_stride=648, llr=llr)
         return self.demod.demod_soft_batch(rx, llr_stride=648, llr=llr, want_cfo=False)[0]
@@ -257,6 +266,8 @@ class LinkSim:
             info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
         else:
             info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))
+            if self.kind == "dpsk" and self.acquire:
+                ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
         count_errors(self.ctx, info, ok, iters, self.payload_pool, batch["tx_index"], batch["bins"], self.payload_bytes,
                      counters)
         return (rx, info, ok, iters) if keep else None

@@ -261,3 +261,35 @@ def test_linksim_fresh_payload_gpu_transmitter(layout):
     assert c[:, 0].tolist() == [trials] * len(snrs) and c[:, 1].tolist() == want_err
     assert c[-1, 1] == 0
     del ctx
+
+
+def test_linksim_config4_with_barker_acquisition():
+    """BASELINE config 4 as tools/test_dpsk_snr.cpp runs it: Barker preamble + data, peak-normalised, findPreamble on the whole
+    frame, demodulateSoft from the returned data start, decodeSoft, frame-error rule -- over the Watterson 'poor' channel, every
+    frame's data start, soft bits, ok flag, iteration count and bytes against the oracle on the identical channel outputs."""
+    import torch
+    from projectultra_b200 import capi, linksim
+    ctx = capi.Context(0)
+    sim = linksim.LinkSim(ctx, capi.dpsk_config(1, 384), "poor", payload_bytes=20, pool=3, code_rate=capi.R1_4, peak=0.5, acquire=True)
+    snrs = [-14.0, -4.0, 6.0, 16.0]
+    trials = 4
+    si = np.repeat(np.arange(len(snrs)), trials)
+    tr = np.tile(np.arange(trials), len(snrs))
+    batch = sim.make_batch(snrs, si, tr)
+    counters = torch.zeros((len(snrs), 6), dtype=torch.int64, device="cuda")
+    rx, info, ok, iters = sim.run_batch(batch, counters, keep=True)
+    torch.cuda.synchronize()
+    rx_h = rx.cpu().numpy()
+    n_llr, ds = sim.last_n_llr.cpu().numpy(), sim.last_sync.cpu().numpy()
+    ok_h, info_h, it_h = ok.cpu().numpy(), info.cpu().numpy(), iters.cpu().numpy()
+    for b in range(len(rx_h)):
+        ol, ods, ocfo, oph = O.dpsk_receive(1, 384, rx_h[b])
+        assert int(ds[b]) == ods and int(n_llr[b]) == min(len(ol), 648), (b, ds[b], ods)
+        if len(ol) >= 648:
+            ci, cok, cit = O.ldpc_decode_batch(R.R1_4, ol[None, :648].copy())
+            assert ok_h[b] == cok[0] and it_h[b] == cit[0] and (info_h[b] == ci[0]).all(), b
+        else:
+            assert ok_h[b] == 0
+    c = counters.cpu().numpy()
+    assert c[:, 0].tolist() == [trials] * len(snrs) and c[0, 1] >= c[-1, 1]
+    del ctx
