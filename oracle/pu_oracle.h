@@ -79,6 +79,11 @@ long orc_ofdm_presynced(const orc_modem_config* c, const float* samples, size_t 
  * demodulator.cpp:459-760, ofdm_sync.cpp).  info[4] = {synchronised, sync offset, samples consumed, calls}. */
 long orc_ofdm_process(const orc_modem_config* c, const float* samples, size_t L, size_t chunk, float sync_threshold,
                       float* llr_out, size_t cap, int32_t* info, float* coarse_cfo);
+/* sync::ChirpSync (src/sync/chirp_sync.hpp) as OFDMChirpWaveform configures it, and the waveform's receive glue */
+long orc_chirp_generate(float fs, float tx_cfo, float* out, size_t cap);
+int orc_chirp_detect_dual(float fs, const float* x, size_t L, float threshold, int32_t* info, float* f);
+long orc_ofdm_chirp_receive(const orc_modem_config* c, const float* x, size_t L, float threshold, int32_t* info, float* cfo_out,
+                            float* llr_out, size_t cap);
 int orc_ofdm_presynced_batch(const orc_modem_config* c, const float* samples, size_t B, size_t L, int training,
                              int cfo_mode, const float* cfo_hz, const float* cfo_phase,
                              float* llr_out, size_t stride, int32_t* counts);

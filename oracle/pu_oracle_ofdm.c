@@ -1076,3 +1076,164 @@ long orc_ofdm_process(const orc_modem_config* c, const float* samples, size_t L,
     if (!found || data_start >= L) return 0;
     return orc_ofdm_presynced(c, samples + data_start, L - data_start, 0, 1, cfo, 0.0f, llr_out, cap, NULL, NULL, NULL);
 }
+
+/* ------------------------------------------------------------------ dual-chirp synchronisation (chirp half)
+ * TEST INFRASTRUCTURE.  sync::ChirpSync (src/sync/chirp_sync.hpp) with the configuration OFDMChirpWaveform gives it
+ * (src/waveform/ofdm_chirp_waveform.cpp:39-49: 300 -> 2700 Hz, 500 ms, 100 ms gaps, dual chirp):
+ *   generate                          :58-108     generateTemplate                  :706-735
+ *   detectDualChirp                   :349-506    detectChirpTemplate               :560-629
+ *   computeComplexTemplateCorrelation :639-662
+ * and the receive glue of OFDMChirpWaveform::detectSync / process (ofdm_chirp_waveform.cpp:129-199) as driven by
+ * tools/test_iwaveform.cpp:127-160. */
+typedef struct { float fs, f_start, f_end, duration_ms, gap_ms, amplitude; size_t n, gap; float *up_s, *up_c, *dn_s, *dn_c; float up_e, dn_e; } chirp_t;
+
+static void chirp_init(chirp_t* c, float fs) {
+    c->fs = fs; c->f_start = 300.0f; c->f_end = 2700.0f; c->duration_ms = 500.0f; c->gap_ms = 100.0f; c->amplitude = 0.5f;
+    c->n = (size_t)(c->fs * c->duration_ms / 1000.0f);
+    c->gap = (size_t)(c->fs * c->gap_ms / 1000.0f);
+    c->up_s = (float*)malloc(sizeof(float) * c->n * 4);
+    c->up_c = c->up_s + c->n; c->dn_s = c->up_c + c->n; c->dn_c = c->dn_s + c->n;
+    const float T = c->duration_ms / 1000.0f, k = (c->f_end - c->f_start) / T;
+    c->up_e = 0.0f;
+    for (size_t i = 0; i < c->n; ++i) {   /* generateTemplate, :706-735 */
+        const float t = (float)i / c->fs;
+        const float phase = (float)(2.0f * M_PI * (c->f_start * t + 0.5f * k * t * t));
+        c->up_s[i] = sinf(phase);
+        c->up_c[i] = cosf(phase);
+        c->up_e += c->up_s[i] * c->up_s[i];
+    }
+    c->dn_e = 0.0f;
+    for (size_t i = 0; i < c->n; ++i) {
+        const float t = (float)i / c->fs;
+        const float phase = (float)(2.0f * M_PI * (c->f_end * t - 0.5f * k * t * t));
+        c->dn_s[i] = sinf(phase);
+        c->dn_c[i] = cosf(phase);
+        c->dn_e += c->dn_s[i] * c->dn_s[i];
+    }
+}
+static void chirp_free(chirp_t* c) { free(c->up_s); }
+
+long orc_chirp_generate(float fs, float tx_cfo, float* out, size_t cap) {   /* ChirpSync::generate, :58-108 */
+    chirp_t c;
+    chirp_init(&c, fs);
+    const size_t total = 2 * c.n + 2 * c.gap;
+    if (total > cap) { chirp_free(&c); return -(long)total; }
+    memset(out, 0, sizeof(float) * total);
+    const float T = c.duration_ms / 1000.0f, k = (c.f_end - c.f_start) / T;
+    const float fu = c.f_start + tx_cfo, fd = c.f_end + tx_cfo;
+    for (size_t i = 0; i < c.n; ++i) {
+        const float t = (float)i / c.fs;
+        const float phase = (float)(2.0f * M_PI * (fu * t + 0.5f * k * t * t));
+        out[i] = c.amplitude * sinf(phase);
+    }
+    for (size_t i = 0; i < c.n; ++i) {
+        const float t = (float)i / c.fs;
+        const float phase = (float)(2.0f * M_PI * (fd * t - 0.5f * k * t * t));
+        out[c.n + c.gap + i] = c.amplitude * sinf(phase);
+    }
+    chirp_free(&c);
+    return (long)total;
+}
+
+static float chirp_corr(const float* x, size_t L, size_t off, const float* ts, const float* tc, size_t n, float te) {   /* :639-662 */
+    if (off + n > L) return 0.0f;
+    float ci = 0.0f, cq = 0.0f, se = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        const float s = x[off + i];
+        ci += s * tc[i];
+        cq += s * ts[i];
+        se += s * s;
+    }
+    const float denom = sqrtf(se * te);
+    if (denom < 1e-10f) return 0.0f;
+    return sqrtf(ci * ci + cq * cq) / denom;
+}
+
+static int chirp_detect_template(const float* x, size_t L, const float* ts, const float* tc, size_t n, float te, float threshold,
+                                 float* corr_out) {   /* detectChirpTemplate, :560-629 */
+    *corr_out = 0.0f;
+    if (L < n) return -1;
+    const size_t search_len = L - n;
+    float best = 0.0f;
+    int pos_best = -1;
+    for (size_t pos = 0; pos < search_len; pos += 48) {
+        const float c = chirp_corr(x, L, pos, ts, tc, n, te);
+        if (c > best) { best = c; pos_best = (int)pos; }
+    }
+    *corr_out = best;
+    if (pos_best < 0 || best < threshold * 0.3f) return -1;
+    const int fine_start = pos_best - 48 > 0 ? pos_best - 48 : 0;
+    const int fine_end = (int)search_len < pos_best + 48 ? (int)search_len : pos_best + 48;
+    for (int pos = fine_start; pos <= fine_end; ++pos) {
+        const float c = chirp_corr(x, L, (size_t)pos, ts, tc, n, te);
+        if (c > best) { best = c; pos_best = pos; }
+    }
+    if (pos_best > 0 && pos_best < (int)search_len - 1) {
+        const float c0 = chirp_corr(x, L, (size_t)(pos_best - 1), ts, tc, n, te), c1 = best;
+        const float c2 = chirp_corr(x, L, (size_t)(pos_best + 1), ts, tc, n, te);
+        const float denom = 2.0f * (c0 - 2.0f * c1 + c2);
+        if (fabsf(denom) > 1e-10f) {
+            float delta = (c0 - c2) / denom;
+            delta = fmaxf(-1.0f, fminf(1.0f, delta));
+            pos_best = (int)roundf((float)pos_best + delta);
+        }
+    }
+    *corr_out = best;
+    return best >= threshold ? pos_best : -1;
+}
+
+/* info[3] = {success, up_chirp_start, down_chirp_start}; f[3] = {cfo_hz, up_correlation, down_correlation} */
+int orc_chirp_detect_dual(float fs, const float* x, size_t L, float threshold, int32_t* info, float* f) {   /* :349-506 */
+    chirp_t c;
+    chirp_init(&c, fs);
+    info[0] = 0; info[1] = 0; info[2] = 0;
+    f[0] = 0.0f; f[1] = 0.0f; f[2] = 0.0f;
+    do {
+        if (L < 2 * c.n + c.gap) break;
+        float up_corr;
+        const int up_pos = chirp_detect_template(x, L, c.up_s, c.up_c, c.n, c.up_e, threshold, &up_corr);
+        f[1] = up_corr;
+        if (up_pos < 0) break;
+        const size_t ds = (size_t)up_pos + c.n / 2, expected = (size_t)up_pos + c.n + c.gap, margin = 2 * c.n;
+        size_t de = L < expected + margin ? L : expected + margin;
+        if (ds >= L) break;
+        if (de <= ds + c.n) de = L < ds + 2 * c.n ? L : ds + 2 * c.n;
+        float dn_corr;
+        const int rel = chirp_detect_template(x + ds, de - ds, c.dn_s, c.dn_c, c.n, c.dn_e, threshold, &dn_corr);
+        if (rel < 0) break;
+        const int down_pos = rel + (int)ds;
+        f[2] = dn_corr;
+        const float T = c.duration_ms / 1000.0f, chirp_rate = (c.f_end - c.f_start) / T, cfo_to_samples = c.fs / chirp_rate;
+        const int expected_gap = (int)(c.n + c.gap), actual_gap = down_pos - up_pos;
+        const float gap_error = (float)(actual_gap - expected_gap);
+        f[0] = gap_error / (2.0f * cfo_to_samples);
+        if (fabsf(f[0]) > 100.0f) break;
+        const float up_corr_s = f[0] * cfo_to_samples, dn_corr_s = -f[0] * cfo_to_samples;
+        info[1] = (int)roundf((float)up_pos + up_corr_s);
+        info[2] = (int)roundf((float)down_pos + dn_corr_s);
+        info[0] = 1;
+    } while (0);
+    chirp_free(&c);
+    return 0;
+}
+
+/* info[4] = {success, up_chirp_start, down_chirp_start, start_sample (training start) or -1} */
+long orc_ofdm_chirp_receive(const orc_modem_config* c, const float* x, size_t L, float threshold, int32_t* info, float* cfo_out,
+                            float* llr_out, size_t cap) {
+    float f[3];
+    orc_chirp_detect_dual((float)c->sample_rate, x, L, threshold, info, f);
+    info[3] = -1;
+    *cfo_out = f[0];
+    if (!info[0]) return 0;
+    const size_t chirp_samples = (size_t)((float)c->sample_rate * 500.0f / 1000.0f);
+    const size_t gap_samples = (size_t)((float)c->sample_rate * 100.0f / 1000.0f);   /* config_.sample_rate * 100.0f / 1000.0f */
+    const int start = (int)((size_t)info[2] + chirp_samples + gap_samples);
+    info[3] = start;
+    if (start < 0 || (size_t)start >= L) return 0;
+    const float cfo = f[0];
+    float ph = (float)(-2.0f * M_PI * cfo * (float)(size_t)start / (float)c->sample_rate);
+    while (ph > M_PI) ph = (float)(ph - 2.0f * M_PI);
+    while (ph < -M_PI) ph = (float)(ph + 2.0f * M_PI);
+    const long n = orc_ofdm_presynced(c, x + start, L - (size_t)start, 2, 2, cfo, ph, llr_out, cap, NULL, NULL, NULL);
+    return n >= 648 ? n : 0;   /* process() only collects soft bits when processPresynced reports a codeword */
+}

@@ -37,6 +37,7 @@
 #include "ofdm/soft_demap.hpp"
 #include "sim/hf_channel.hpp"
 #include "psk/dpsk.hpp"
+#include "sync/chirp_sync.hpp"
 
 using namespace ultra;
 
@@ -354,6 +355,87 @@ long ref_ofdm_process_info(const ref_modem_config* c, const float* samples, size
     if (soft.size() > cap) return -(long)soft.size();
     std::memcpy(llr_out, soft.data(), soft.size() * sizeof(float));
     return (long)soft.size();
+}
+
+// ---------------------------------------------------------------- dual-chirp synchronisation (src/sync/chirp_sync.hpp)
+static sync::ChirpConfig chirp_cfg(float fs, float tx_cfo) {   // OFDMChirpWaveform::getChirpConfig, ofdm_chirp_waveform.cpp:39-49
+    sync::ChirpConfig c;
+    c.sample_rate = fs;
+    c.f_start = 300.0f;
+    c.f_end = 2700.0f;
+    c.duration_ms = 500.0f;
+    c.gap_ms = 100.0f;
+    c.use_dual_chirp = true;
+    c.tx_cfo_hz = tx_cfo;
+    return c;
+}
+// ChirpSync::generate(): [up chirp][gap][down chirp][gap]
+long ref_chirp_generate(float fs, float tx_cfo, float* out, size_t cap) {
+    init_once();
+    StderrSilencer quiet;
+    sync::ChirpSync cs(chirp_cfg(fs, tx_cfo));
+    Samples s = cs.generate();
+    if (s.size() > cap) return -(long)s.size();
+    std::memcpy(out, s.data(), s.size() * sizeof(float));
+    return (long)s.size();
+}
+// ChirpSync::detectDualChirp: info = {success, up_chirp_start, down_chirp_start}, f = {cfo_hz, up_correlation, down_correlation}
+int ref_chirp_detect_dual(float fs, const float* x, size_t L, float threshold, int32_t* info, float* f) {
+    init_once();
+    StderrSilencer quiet;
+    fflush(stdout);
+    int saved = dup(1), nul = open("/dev/null", O_WRONLY);   // detectDualChirp printf()s on stdout
+    if (nul >= 0) { dup2(nul, 1); close(nul); }
+    sync::ChirpSync cs(chirp_cfg(fs, 0.0f));
+    auto r = cs.detectDualChirp(SampleSpan(x, L), threshold);
+    fflush(stdout);
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+    info[0] = r.success ? 1 : 0; info[1] = r.up_chirp_start; info[2] = r.down_chirp_start;
+    f[0] = r.cfo_hz; f[1] = r.up_correlation; f[2] = r.down_correlation;
+    return 0;
+}
+// The receive sequence of tools/test_iwaveform.cpp:127-160 on an OFDM_CHIRP frame, with the glue of
+// OFDMChirpWaveform::detectSync / process (ofdm_chirp_waveform.cpp:129-199) applied to the reference's own ChirpSync and
+// OFDMDemodulator objects (the waveform class itself pulls the protocol layer into the build):
+//   detectDualChirp -> start_sample = down_chirp_start + chirp + gap -> setFrequencyOffsetWithPhase(cfo, accumulated phase)
+//   -> processPresynced(span from start_sample, 2) -> all soft bits.
+long ref_ofdm_chirp_receive(const ref_modem_config* c, const float* x, size_t L, float threshold, int32_t* info, float* cfo_out,
+                            float* llr_out, size_t cap) {
+    init_once();
+    StderrSilencer quiet;
+    fflush(stdout);
+    int saved = dup(1), nul = open("/dev/null", O_WRONLY);
+    if (nul >= 0) { dup2(nul, 1); close(nul); }
+    ModemConfig cfg = to_cfg(c);
+    sync::ChirpSync cs(chirp_cfg((float)cfg.sample_rate, 0.0f));
+    auto r = cs.detectDualChirp(SampleSpan(x, L), threshold);
+    fflush(stdout);
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+    info[0] = r.success ? 1 : 0; info[1] = r.up_chirp_start; info[2] = r.down_chirp_start; info[3] = -1;
+    *cfo_out = r.cfo_hz;
+    if (!r.success) return 0;
+    size_t chirp_samples = cs.getChirpSamples();
+    size_t gap_samples = static_cast<size_t>(cfg.sample_rate * 100.0f / 1000.0f);
+    int start_sample = r.down_chirp_start + chirp_samples + gap_samples;
+    info[3] = start_sample;
+    if (start_sample < 0 || (size_t)start_sample >= L) return 0;            // tools/test_iwaveform.cpp:145-148
+    size_t training_start_sample = (size_t)start_sample;
+    float cfo_hz = r.cfo_hz;                                                  // waveform.setFrequencyOffset(sync_result.cfo_hz)
+    float initial_phase_rad = -2.0f * M_PI * cfo_hz * training_start_sample / cfg.sample_rate;
+    while (initial_phase_rad > M_PI) initial_phase_rad -= 2.0f * M_PI;
+    while (initial_phase_rad < -M_PI) initial_phase_rad += 2.0f * M_PI;
+    OFDMDemodulator d(cfg);
+    d.setFrequencyOffsetWithPhase(cfo_hz, initial_phase_rad);
+    bool ready = d.processPresynced(SampleSpan(x + start_sample, L - start_sample), 2);
+    size_t n = 0;
+    if (ready) {
+        while (d.hasPendingData()) {
+            auto chunk = d.getSoftBits();
+            if (chunk.empty()) break;
+            for (float v : chunk) { if (n < cap) llr_out[n] = v; ++n; }
+        }
+    }
+    return (long)n;
 }
 
 // ---------------------------------------------------------------- Watterson channel

@@ -180,6 +180,29 @@ def ofdm_process(cfg, samples, chunk=960, sync_threshold=0.0):
     return out[:min(n, 648)].copy(), bool(info[0]), int(info[1]), float(cfo.value), int(info[2]), int(info[3])
 
 
+def chirp_generate(fs=48000.0, tx_cfo=0.0):
+    out = np.zeros(80000, np.float32)
+    L = lib()
+    L.orc_chirp_generate.restype = C.c_long
+    n = L.orc_chirp_generate(C.c_float(fs), C.c_float(tx_cfo), _p(out, C.c_float), C.c_size_t(len(out)))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def ofdm_chirp_receive(cfg, samples, threshold=0.15):
+    """(llr, info[4] = {success, up start, down start, training start}, cfo) -- see orc_ofdm_chirp_receive."""
+    x = _f32(samples)
+    out = np.zeros(8192, np.float32)
+    info = np.zeros(4, np.int32)
+    cfo = C.c_float(0)
+    L = lib()
+    L.orc_ofdm_chirp_receive.restype = C.c_long
+    n = L.orc_ofdm_chirp_receive(C.byref(cfg), _p(x, C.c_float), C.c_size_t(len(x)), C.c_float(threshold), _p(info, C.c_int32),
+                                 C.byref(cfo), _p(out, C.c_float), C.c_size_t(len(out)))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), info, float(cfo.value)
+
+
 def ofdm_presynced_stages(cfg, samples, training=2, cfo_mode=1, cfo_hz=0.0, cfo_phase=0.0, max_sym=64):
     x = _f32(samples)
     nd, npil = cfg.n_data, cfg.n_pilots

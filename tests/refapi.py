@@ -323,6 +323,29 @@ def dpsk_receive(mod, sps, samples, fc=1500.0, fs=48000.0):
     return out[:n].copy(), int(ds.value), float(cfo.value), float(ph.value)
 
 
+def chirp_generate(fs=48000.0, tx_cfo=0.0):
+    out = np.zeros(80000, np.float32)
+    L = lib()
+    L.ref_chirp_generate.restype = C.c_long
+    n = L.ref_chirp_generate(C.c_float(fs), C.c_float(tx_cfo), _p(out, C.c_float), C.c_size_t(len(out)))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def ofdm_chirp_receive(cfg, samples, threshold=0.15):
+    """tools/test_iwaveform.cpp:127-160 on an OFDM_CHIRP frame: (llr, info[4] = {success, up start, down start, training start}, cfo)."""
+    x = _f32(samples)
+    out = np.zeros(8192, np.float32)
+    info = np.zeros(4, np.int32)
+    cfo = C.c_float(0)
+    L = lib()
+    L.ref_ofdm_chirp_receive.restype = C.c_long
+    n = L.ref_ofdm_chirp_receive(C.byref(cfg), _p(x, C.c_float), C.c_size_t(len(x)), C.c_float(threshold), _p(info, C.c_int32),
+                                 C.byref(cfo), _p(out, C.c_float), C.c_size_t(len(out)))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), info, float(cfo.value)
+
+
 def time_presynced_decode(cfg, samples, rate):
     x = _f32(samples)
     B, L = x.shape
