@@ -150,6 +150,20 @@ PU_API pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_
                                          const float* cfo_hz, const float* cfo_phase, float* llr_out,
                                          size_t llr_stride, float* snr_db, float* final_cfo_hz,
                                          pu_memspace space, void* stream);
+/* ---------------------------------------------------------------- dual-chirp synchronisation
+ * sync::ChirpSync::detectDualChirp (src/sync/chirp_sync.hpp:349-506, configured as OFDMChirpWaveform::getChirpConfig,
+ * src/waveform/ofdm_chirp_waveform.cpp:39-49) and the receive sequence of tools/test_iwaveform.cpp:127-160 on OFDM_CHIRP
+ * frames: IWaveform::detectSync -> setFrequencyOffset(cfo) -> process(span from start_sample) -> getSoftBits, for B frames.
+ *   sync_info[B][4]   = {detected, up_chirp_start, down_chirp_start, SyncResult::start_sample (training start) or -1}
+ *   sync_values[B][4] = {cfo_hz, up correlation, down correlation, initial CFO-rotator phase}
+ *   llr_out[B][llr_stride] (may be NULL: detection only), n_llr[B] = soft bits available (0 unless a codeword's worth, as
+ *   OFDMChirpWaveform::process only collects them then); threshold <= 0 selects the callers' 0.15. */
+PU_API pu_status pu_ofdm_chirp_receive_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, float threshold,
+                                             float* llr_out, size_t llr_stride, int32_t* n_llr, int32_t* sync_info,
+                                             float* sync_values, float* snr_db, pu_memspace space, void* stream);
+/* sync::ChirpSync::generate (chirp_sync.hpp:58-108), host side: [up chirp][gap][down chirp][gap]; out == NULL queries the length */
+PU_API pu_status pu_chirp_generate(float sample_rate, float tx_cfo_hz, float* out, size_t out_cap, size_t* out_len);
+
 /* ---------------------------------------------------------------- batched transmitter
  * LDPCEncoder::encode (src/fec/ldpc_encoder.cpp:193-257, one 648-bit block, payload zero-padded to k bits) followed by
  * OFDMModulator::generateTrainingSymbols(2) (layout 0) or generatePreamble() (layout 1) + modulate()

@@ -1186,7 +1186,7 @@ static int chirp_detect_template(const float* x, size_t L, const float* ts, cons
 int orc_chirp_detect_dual(float fs, const float* x, size_t L, float threshold, int32_t* info, float* f) {   /* :349-506 */
     chirp_t c;
     chirp_init(&c, fs);
-    info[0] = 0; info[1] = 0; info[2] = 0;
+    info[0] = 0; info[1] = -1; info[2] = -1;   /* DualChirpResult defaults, chirp_sync.hpp:317-324 */
     f[0] = 0.0f; f[1] = 0.0f; f[2] = 0.0f;
     do {
         if (L < 2 * c.n + c.gap) break;

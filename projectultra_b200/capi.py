@@ -208,6 +208,15 @@ class LdpcDecoder:
         return out[:n.value].copy(), bool(ok.value), it.value
 
 
+def chirp_generate(sample_rate=48000.0, tx_cfo_hz=0.0):
+    """ChirpSync::generate (host): [up chirp][gap][down chirp][gap]."""
+    n = C.c_size_t(0)
+    check(lib().pu_chirp_generate(C.c_float(sample_rate), C.c_float(tx_cfo_hz), None, C.c_size_t(0), C.byref(n)))
+    out = np.zeros(n.value, np.float32)
+    check(lib().pu_chirp_generate(C.c_float(sample_rate), C.c_float(tx_cfo_hz), _ptr(out), C.c_size_t(len(out)), C.byref(n)))
+    return out
+
+
 def ldpc_encode(rate, data):
     """LDPCEncoder::encode (host)."""
     d = np.ascontiguousarray(np.frombuffer(bytes(data), np.uint8) if isinstance(data, (bytes, bytearray)) else data,
@@ -345,6 +354,35 @@ class OfdmDemodulator:
         check(lib().pu_ofdm_tx_batch(self._h, ldpc._h, _ptr(payload), C.c_size_t(stride), C.c_size_t(nbytes), C.c_size_t(B), int(layout),
                                      C.c_float(peak), _ptr(out), C.c_size_t(ostride), C.byref(n), sp, _stream(sp)))
         return out
+
+    def chirp_receive_batch(self, samples, threshold=0.15, llr_stride=648, want_llr=True):
+        """pu_ofdm_chirp_receive_batch: dual-chirp detectSync + setFrequencyOffset + process + getSoftBits for every row of
+        samples [B, L] -> (llr [B, llr_stride], n_llr [B], sync_info [B, 4] int32, sync_values [B, 4] float32, snr_db [B])."""
+        tor = _is_torch(samples)
+        if tor:
+            import torch
+            assert samples.dtype == torch.float32 and samples.dim() == 2 and samples.is_contiguous()
+            B, L = samples.shape
+            dev = samples.device
+            llr = torch.zeros((B, llr_stride), dtype=torch.float32, device=dev) if want_llr else None
+            n = torch.zeros(B, dtype=torch.int32, device=dev)
+            info = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+            val = torch.zeros((B, 4), dtype=torch.float32, device=dev)
+            snr = torch.zeros(B, dtype=torch.float32, device=dev)
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.float32)
+            if samples.ndim == 1:
+                samples = samples.reshape(1, -1)
+            B, L = samples.shape
+            llr = np.zeros((B, llr_stride), np.float32) if want_llr else None
+            n = np.zeros(B, np.int32)
+            info = np.zeros((B, 4), np.int32)
+            val = np.zeros((B, 4), np.float32)
+            snr = np.zeros(B, np.float32)
+        sp = _space(samples, n, info, val, snr)
+        check(lib().pu_ofdm_chirp_receive_batch(self._h, _ptr(samples), C.c_size_t(B), C.c_size_t(L), C.c_float(threshold), _ptr(llr),
+                                                C.c_size_t(llr_stride), _ptr(n), _ptr(info), _ptr(val), _ptr(snr), sp, _stream(sp)))
+        return llr, n, info, val, snr
 
     def acquire_batch(self, samples, chunk=960, sync_threshold=0.0):
         """pu_ofdm_acquire_batch: samples [B, L] (numpy or torch.cuda) -> (sync_info [B, 4] int32 = {synced, sync offset,

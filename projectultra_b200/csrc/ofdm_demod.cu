@@ -836,6 +836,17 @@ struct AcqDev {
 cudaError_t ofdm_acquire_launch(const AcqDev& a, const float* samples, size_t B, size_t frame_stride, int L, int chunk, int4* out_int,
                                 float* out_cfo, cudaStream_t st);
 
+// chirp_sync.cu
+struct ChirpDev {
+    int n, gap;
+    float fs, cfo_to_samples;
+    const float* up_s; const float* up_c; const float* dn_s; const float* dn_c;
+    float up_e, dn_e;
+};
+cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t B, size_t frame_stride, int L, float threshold, int sym_len,
+                                int4* out_info, float4* out_f, int* frame_start, int* frame_nsym, float* cfo_out, float* phase_out,
+                                int* n_llr, int llr_per_symbol, int llr_stride, cudaStream_t st);
+
 // ofdm_tx_gpu.cu
 struct TxDev {
     int nfft, cp, sym_len, guard, n_data, n_pilot, bps, differential;
@@ -894,6 +905,45 @@ struct pu_ofdm {
     pu::OfdmDev dev{};
     pu::DevMem d_tw, d_nco, d_dbin, d_pbin, d_zc, d_psign, d_ilo, d_ihi, d_ia, d_perm;
     pu::DevMem d_lts_i, d_lts_q;          // LTS passband templates of refineLTSTiming (built on first use)
+    pu::DevMem d_chirp;                   // dual-chirp templates: up sin, up cos, down sin, down cos (built on first use)
+    pu::ChirpDev chirp{};
+    bool chirp_ready = false;
+
+    // sync::ChirpSync::generateTemplate (src/sync/chirp_sync.hpp:706-735) with OFDMChirpWaveform::getChirpConfig
+    // (src/waveform/ofdm_chirp_waveform.cpp:39-49): 300 -> 2700 Hz in 500 ms, 100 ms gaps
+    pu_status ensure_chirp() {
+        if (chirp_ready) return PU_OK;
+        const float fs = static_cast<float>(plan.cfg.sample_rate), f_start = 300.0f, f_end = 2700.0f, duration_ms = 500.0f, gap_ms = 100.0f;
+        const size_t n = static_cast<size_t>(fs * duration_ms / 1000.0f);
+        const float T = duration_ms / 1000.0f, k = (f_end - f_start) / T;
+        std::vector<float> t(4 * n);
+        float ue = 0.0f, de = 0.0f;
+        for (size_t i = 0; i < n; ++i) {
+            const float tt = static_cast<float>(i) / fs;
+            const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (f_start * tt + 0.5f * k * tt * tt));
+            t[i] = std::sin(phase);
+            t[n + i] = std::cos(phase);
+            ue += t[i] * t[i];
+        }
+        for (size_t i = 0; i < n; ++i) {
+            const float tt = static_cast<float>(i) / fs;
+            const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (f_end * tt - 0.5f * k * tt * tt));
+            t[2 * n + i] = std::sin(phase);
+            t[3 * n + i] = std::cos(phase);
+            de += t[2 * n + i] * t[2 * n + i];
+        }
+        pu_status st = d_chirp.upload(t.data(), t.size());
+        if (st != PU_OK) return st;
+        const float* b = static_cast<const float*>(d_chirp.p);
+        chirp.n = static_cast<int>(n);
+        chirp.gap = static_cast<int>(static_cast<size_t>(fs * gap_ms / 1000.0f));
+        chirp.fs = fs;
+        chirp.cfo_to_samples = fs / ((f_end - f_start) / T);
+        chirp.up_s = b; chirp.up_c = b + n; chirp.dn_s = b + 2 * n; chirp.dn_c = b + 3 * n;
+        chirp.up_e = ue; chirp.dn_e = de;
+        chirp_ready = true;
+        return PU_OK;
+    }
     pu::DevMem d_tx_osc, d_tx_pre[2], d_tx_points;   // transmitter tables (built on first use; preamble per layout)
     int tx_pre_len[2] = {-1, -1};
     size_t tx_osc_len = 0;
@@ -1191,6 +1241,96 @@ pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_t B, si
         std::memcpy(llr_out + off * llr_stride, hout, nb * llr_stride * sizeof(float));
         if (snr_db) std::memcpy(snr_db + off, hout + slab * llr_stride, nb * sizeof(float));
         if (final_cfo_hz) std::memcpy(final_cfo_hz + off, hout + slab * llr_stride + slab, nb * sizeof(float));
+    }
+    return PU_OK;
+}
+
+pu_status pu_ofdm_chirp_receive_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, float threshold, float* llr_out,
+                                      size_t llr_stride, int32_t* n_llr, int32_t* sync_info, float* sync_values, float* snr_db,
+                                      pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_ofdm_chirp_receive_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && sync_info && sync_values, "pu_ofdm_chirp_receive_batch: NULL data pointer");
+    PU_REQUIRE(!llr_out || (n_llr && llr_stride > 0), "pu_ofdm_chirp_receive_batch: llr_out needs n_llr and llr_stride");
+    PU_REQUIRE(L < (1u << 30), "pu_ofdm_chirp_receive_batch: frame too long");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    pu_status s = h->ensure_chirp();
+    if (s != PU_OK) return s;
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    const pu::OfdmPlan& p = h->plan;
+    if (threshold <= 0.0f) threshold = 0.15f;        // the callers' value, tools/test_iwaveform.cpp:133
+    pu::DevMem dx, dl, dn, dsn, dinfo, dval, dstart, dnsym, dcfo, dph;
+    const float* d_x = samples;
+    float* d_llr = llr_out;
+    int32_t* d_n = n_llr;
+    float* d_snr = snr_db;
+    int32_t* d_info = sync_info;
+    float* d_val = sync_values;
+    std::vector<int32_t> zi(B * 4, 0);
+    if (space == PU_MEM_HOST) {
+        if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
+        if ((s = dinfo.upload(zi.data(), B * 4)) != PU_OK) return s;
+        if ((s = dval.upload(zi.data(), B * 4)) != PU_OK) return s;
+        d_x = static_cast<const float*>(dx.p); d_info = static_cast<int32_t*>(dinfo.p); d_val = static_cast<float*>(dval.p);
+        if (llr_out) {
+            std::vector<float> zl(B * llr_stride, 0.0f);
+            if ((s = dl.upload(zl.data(), zl.size())) != PU_OK) return s;
+            if ((s = dn.upload(zi.data(), B)) != PU_OK) return s;
+            if ((s = dsn.upload(zi.data(), B)) != PU_OK) return s;
+            d_llr = static_cast<float*>(dl.p); d_n = static_cast<int32_t*>(dn.p); d_snr = snr_db ? static_cast<float*>(dsn.p) : nullptr;
+        }
+    }
+    if ((s = dstart.upload(zi.data(), B)) != PU_OK) return s;
+    if ((s = dnsym.upload(zi.data(), B)) != PU_OK) return s;
+    if ((s = dcfo.upload(zi.data(), B)) != PU_OK) return s;
+    if ((s = dph.upload(zi.data(), B)) != PU_OK) return s;
+    (void)cudaGetLastError();
+    PU_CUDA_TRY(pu::chirp_detect_launch(h->chirp, d_x, B, L, static_cast<int>(L), threshold, p.sym_len, reinterpret_cast<int4*>(d_info),
+                                        reinterpret_cast<float4*>(d_val), static_cast<int*>(dstart.p), static_cast<int*>(dnsym.p),
+                                        static_cast<float*>(dcfo.p), static_cast<float*>(dph.p), llr_out ? d_n : nullptr, p.n_data * p.bps,
+                                        static_cast<int>(llr_stride), st));
+    ctx->launches.fetch_add(1);
+    if (llr_out) {
+        // OFDMChirpWaveform::process (:170-199): setFrequencyOffsetWithPhase(cfo, accumulated phase); processPresynced(span, 2)
+        s = launch_ofdm(h, d_x, B, L, 2, static_cast<const float*>(dcfo.p), static_cast<const float*>(dph.p), d_llr, llr_stride, d_snr, nullptr,
+                        nullptr, st, static_cast<const int*>(dstart.p), static_cast<const int*>(dnsym.p));
+        if (s != PU_OK) return s;
+    }
+    PU_CUDA_TRY(cudaStreamSynchronize(st));           // the scratch buffers above are freed on return
+    if (space == PU_MEM_HOST) {
+        PU_CUDA_TRY(cudaMemcpy(sync_info, d_info, B * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        PU_CUDA_TRY(cudaMemcpy(sync_values, d_val, B * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (llr_out) {
+            PU_CUDA_TRY(cudaMemcpy(llr_out, d_llr, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
+            PU_CUDA_TRY(cudaMemcpy(n_llr, d_n, B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            if (snr_db) PU_CUDA_TRY(cudaMemcpy(snr_db, d_snr, B * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+    }
+    return PU_OK;
+}
+
+pu_status pu_chirp_generate(float sample_rate, float tx_cfo_hz, float* out, size_t out_cap, size_t* out_len) {
+    PU_REQUIRE(out_len && sample_rate > 0, "pu_chirp_generate: bad argument");
+    // sync::ChirpSync::generate (src/sync/chirp_sync.hpp:58-108), host side: [up chirp][gap][down chirp][gap]
+    const float f_start = 300.0f, f_end = 2700.0f, duration_ms = 500.0f, gap_ms = 100.0f, amplitude = 0.5f;
+    const size_t n = static_cast<size_t>(sample_rate * duration_ms / 1000.0f), gap = static_cast<size_t>(sample_rate * gap_ms / 1000.0f);
+    const size_t total = 2 * n + 2 * gap;
+    *out_len = total;
+    if (!out) return PU_OK;
+    PU_REQUIRE(out_cap >= total, "pu_chirp_generate: output buffer too small");
+    std::fill(out, out + total, 0.0f);
+    const float T = duration_ms / 1000.0f, k = (f_end - f_start) / T;
+    const float fu = f_start + tx_cfo_hz, fd = f_end + tx_cfo_hz;
+    for (size_t i = 0; i < n; ++i) {
+        const float t = static_cast<float>(i) / sample_rate;
+        const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (fu * t + 0.5f * k * t * t));
+        out[i] = amplitude * std::sin(phase);
+    }
+    for (size_t i = 0; i < n; ++i) {
+        const float t = static_cast<float>(i) / sample_rate;
+        const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (fd * t - 0.5f * k * t * t));
+        out[n + gap + i] = amplitude * std::sin(phase);
     }
     return PU_OK;
 }

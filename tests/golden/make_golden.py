@@ -211,6 +211,28 @@ def dpsk_acquire_vectors():
     np.savez_compressed(os.path.join(HERE, "dpsk_acquire_golden.npz"), **out)
 
 
+def chirp_vectors():
+    """Dual-chirp sync (chirp half): tools/test_iwaveform.cpp:127-160 receive sequence on two OFDM_CHIRP frames
+    (M1 DQPSK R1/2): +12.5 Hz TX CFO at 15 dB behind 1 200 samples of noise, and 0 Hz at -6 dB."""
+    rng = np.random.default_rng(20261020)
+    out = {}
+    for i, (snr, lead, tx_cfo) in enumerate(((15.0, 1200, 12.5), (-6.0, 300, 0.0))):
+        cfg = R.config_m1(R.DQPSK, R.R1_2)
+        cfg.tx_cfo_hz = tx_cfo
+        data = rng.integers(0, 256, 40, dtype=np.uint8)
+        body = R.ofdm_tx(cfg, R.ldpc_encode(R.R1_2, data), 0)
+        w = np.concatenate([np.zeros(lead, np.float32), R.chirp_generate(48000.0, tx_cfo), body, np.zeros(600, np.float32)])
+        p = float(np.mean(body.astype(np.float64) ** 2))
+        rx = (w + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(w))).astype(np.float32)
+        base = R.config_m1(R.DQPSK, R.R1_2)
+        llr, info, cfo = R.ofdm_chirp_receive(base, rx)
+        out[f"c{i}_rx"] = rx
+        out[f"c{i}_llr"] = llr
+        out[f"c{i}_info"] = info.astype(np.int64)
+        out[f"c{i}_cfo"] = np.array([cfo], np.float32)
+    np.savez_compressed(os.path.join(HERE, "chirp_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
     ldpc_vectors()
@@ -219,6 +241,7 @@ if __name__ == "__main__":
     psk_vectors()
     acquire_vectors()
     dpsk_acquire_vectors()
+    chirp_vectors()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,75 @@
+"""SURVEY §8f next-2 (chirp half): dual-chirp synchronisation of the OFDM_CHIRP waveform on the GPU -- the receive sequence
+of tools/test_iwaveform.cpp:127-160 (IWaveform::detectSync -> setFrequencyOffset -> process -> getSoftBits) -- against the
+plain-C oracle (oracle/pu_oracle_ofdm.c: orc_ofdm_chirp_receive, pinned to the compiled reference) and, when present, the compiled
+reference.  Detection flag, chirp positions, training start: identical integers; CFO: identical bits; LLRs within 1e-4."""
+import numpy as np
+import pytest
+
+import refapi as R
+import oracleapi as O
+
+pytestmark = pytest.mark.gpu
+
+
+def frame(cfg, rate, nbytes, snr, seed, lead, tail, tx_cfo=0.0):
+    from projectultra_b200 import capi
+    rng = np.random.default_rng(seed)
+    data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    body = O.ofdm_tx(cfg, O.ldpc_encode(rate, data), 0)                 # generateTrainingSymbols(2) + modulate()
+    chirp = capi.chirp_generate(48000.0, tx_cfo)
+    w = np.concatenate([np.zeros(lead, np.float32), chirp, body, np.zeros(tail, np.float32)])
+    if snr is None:
+        return w
+    p = float(np.mean(body.astype(np.float64) ** 2))
+    return (w + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(w))).astype(np.float32)
+
+
+def test_chirp_generate_matches_oracle():
+    from projectultra_b200 import capi
+    for cfo in (0.0, 12.5, -30.0):
+        a, b = capi.chirp_generate(48000.0, cfo), O.chirp_generate(48000.0, cfo)
+        assert a.shape == b.shape and (a.view(np.uint32) == b.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("preset,mod", [("m1", R.DQPSK), ("m1", R.QAM16), ("m3", R.DQPSK)])
+def test_chirp_receive_matches_oracle(preset, mod):
+    import torch
+    from projectultra_b200 import capi
+    rate = R.R1_2
+    ctx = capi.Context(0)
+    total = 57600 + 16000
+    frames, cfgs = [], []
+    cases = [(25.0, 0, 0.0), (12.0, 3000, 0.0), (4.0, 777, 0.0), (-4.0, 5000, 0.0), (-12.0, 100, 0.0), (20.0, 1200, 12.5), (15.0, 40, -30.0), (None, 2500, 0.0)]
+    for i, (snr, lead, tx_cfo) in enumerate(cases):
+        cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+        cfg.tx_cfo_hz = tx_cfo
+        body_len = len(O.ofdm_tx(cfg, O.ldpc_encode(rate, np.zeros(40, np.uint8)), 0))
+        frames.append(frame(cfg, rate, 40, snr, 800 + 13 * i + mod, lead, total - 57600 - body_len - lead, tx_cfo))
+        cfgs.append(cfg)
+    frames.append(np.random.default_rng(5).normal(0, 0.1, total).astype(np.float32))     # noise only
+    frames.append(np.zeros(total, np.float32))                                            # silence
+    cfgs += [cfgs[0], cfgs[0]]
+    x = np.stack(frames)
+    base = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    dem = capi.OfdmDemodulator(ctx, capi.ModemConfig.from_buffer_copy(bytes(base)))
+    llr, n, info, val, snr_db = dem.chirp_receive_batch(x, llr_stride=700)
+    found = 0
+    for b in range(len(x)):
+        ol, oi, ocfo = O.ofdm_chirp_receive(base, x[b])
+        assert (info[b] == oi).all(), (b, info[b], oi)
+        assert np.float32(val[b, 0]).view(np.uint32) == np.float32(ocfo).view(np.uint32), (b, val[b, 0], ocfo)
+        want = ol[:700]
+        assert int(n[b]) == len(want), (b, n[b], len(ol))
+        if len(want):
+            found += 1
+            bad = np.flatnonzero(~np.isclose(llr[b, :len(want)], want, rtol=1e-4, atol=1e-6))
+            assert len(bad) == 0, (b, bad[:8], llr[b, bad[:8]], want[bad[:8]])
+        if R.available() and b in (0, 5):
+            rl, ri, rcfo = R.ofdm_chirp_receive(base, x[b])
+            assert (ri == oi).all() and np.float32(rcfo).view(np.uint32) == np.float32(ocfo).view(np.uint32)
+    assert found >= 5
+    d = dem.chirp_receive_batch(torch.from_numpy(x).cuda(), llr_stride=700)
+    torch.cuda.synchronize()
+    assert (d[2].cpu().numpy() == info).all() and (d[1].cpu().numpy() == n).all()
+    assert (d[0].cpu().numpy().view(np.uint32) == llr.view(np.uint32)).all()
+    del ctx

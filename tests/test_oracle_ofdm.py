@@ -135,3 +135,36 @@ def test_process_path_matches_reference(preset, mod):
                 n_sync += 1
                 assert roff == ooff and _same_words(np.float32(rcfo), np.float32(ocfo)) and _same_words(rl, ol), (snr, chunk)
     assert n_sync >= 4
+
+
+def test_golden_chirp_sync(golden):
+    """SURVEY §8f next-2 (chirp half): the oracle's sync::ChirpSync::detectDualChirp + OFDMChirpWaveform receive glue against
+    vectors produced by the unmodified reference (tools/test_iwaveform.cpp:127-160 sequence), with and without TX CFO."""
+    g = golden["chirp"]
+    base = R.config_m1(R.DQPSK, R.R1_2)
+    for i in range(2):
+        llr, info, cfo = O.ofdm_chirp_receive(base, g[f"c{i}_rx"])
+        assert (info.astype(np.int64) == g[f"c{i}_info"]).all(), (i, info, g[f"c{i}_info"])
+        assert _same_words(np.float32(cfo), g[f"c{i}_cfo"][0])
+        assert _same_words(llr, g[f"c{i}_llr"]), i
+
+
+def test_chirp_sync_matches_reference():
+    if not R.available():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    assert _same_words(O.chirp_generate(48000.0, 7.5), R.chirp_generate(48000.0, 7.5))
+    rng = np.random.default_rng(77)
+    base = R.config_m1(R.DQPSK, R.R1_2)
+    found = 0
+    for snr, lead, tx_cfo in ((20.0, 0, 0.0), (8.0, 2100, -20.0), (0.0, 640, 5.0), (-9.0, 3000, 0.0), (-25.0, 10, 0.0)):
+        cfg = R.config_m1(R.DQPSK, R.R1_2)
+        cfg.tx_cfo_hz = tx_cfo
+        body = O.ofdm_tx(cfg, O.ldpc_encode(R.R1_2, rng.integers(0, 256, 40, dtype=np.uint8)), 0)
+        w = np.concatenate([np.zeros(lead, np.float32), O.chirp_generate(48000.0, tx_cfo), body, np.zeros(900, np.float32)])
+        p = float(np.mean(body.astype(np.float64) ** 2))
+        rx = (w + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(w))).astype(np.float32)
+        rl, ri, rc = R.ofdm_chirp_receive(base, rx)
+        ol, oi, oc = O.ofdm_chirp_receive(base, rx)
+        assert (ri == oi).all() and _same_words(np.float32(rc), np.float32(oc)) and _same_words(rl, ol), (snr, lead, tx_cfo, ri, oi)
+        found += int(oi[0])
+    assert found >= 3
