@@ -440,15 +440,43 @@ public:
     CodeRate getCodeRate() const PU_OVERRIDE { return cfg_.code_rate; }
     float getFrequencyOffset() const PU_OVERRIDE { return cfo_hz_; }
 
-    Samples generatePreamble() PU_OVERRIDE { return mod_->generateTrainingSymbols(2); }   // training part (chirp: next-2)
+    Samples generatePreamble() PU_OVERRIDE {   // [CHIRP][TRAINING_SYMBOLS] (:104-118)
+        size_t n = 0;
+        pu_chirp_generate(static_cast<float>(cfg_.sample_rate), cfg_.tx_cfo_hz, nullptr, 0, &n);
+        Samples pre(n);
+        pu_chirp_generate(static_cast<float>(cfg_.sample_rate), cfg_.tx_cfo_hz, pre.data(), pre.size(), &n);
+        const Samples training = mod_->generateTrainingSymbols(2);
+        pre.insert(pre.end(), training.begin(), training.end());
+        return pre;
+    }
     Samples modulate(const Bytes& encoded) PU_OVERRIDE { return mod_->modulate(ByteSpan(encoded.data(), encoded.size()), cfg_.modulation); }
 
-    bool detectSync(SampleSpan, SyncResult& result, float = 0.3f) PU_OVERRIDE {
+    bool detectSync(SampleSpan samples, SyncResult& result, float threshold = 0.3f) PU_OVERRIDE {   // :129-172: dual-chirp detection
         result = SyncResult{};
-        return false;
+        int32_t info[4] = {0, -1, -1, -1};
+        float val[4] = {0, 0, 0, 0};
+        if (samples.empty() ||
+            pu_ofdm_chirp_receive_batch(demod_->handle(), samples.data(), 1, samples.size(), threshold, nullptr, 0, nullptr, info, val, nullptr,
+                                        PU_MEM_HOST, nullptr) != PU_OK)
+            return false;
+        result.detected = info[0] != 0;
+        result.correlation = std::max(val[1], val[2]);
+        result.cfo_hz = val[0];
+        result.has_training = true;
+        if (result.detected) {
+            synced_ = true;
+            result.start_sample = info[3];
+            training_start_sample_ = static_cast<size_t>(info[3]);
+        }
+        return result.detected;
     }
     bool process(SampleSpan samples) PU_OVERRIDE {   // :174-219: processPresynced on the span from the training start
-        demod_->setFrequencyOffsetWithPhase(cfo_hz_, 0.0f);
+        // CFO rotator phase accumulated since sample 0 of the audio, wrapped to [-pi, pi] (:177-181)
+        constexpr double kPi = 3.14159265358979323846;
+        float initial_phase_rad = static_cast<float>(-2.0f * kPi * cfo_hz_ * training_start_sample_ / cfg_.sample_rate);
+        while (initial_phase_rad > kPi) initial_phase_rad = static_cast<float>(initial_phase_rad - 2.0f * kPi);
+        while (initial_phase_rad < -kPi) initial_phase_rad = static_cast<float>(initial_phase_rad + 2.0f * kPi);
+        demod_->setFrequencyOffsetWithPhase(cfo_hz_, initial_phase_rad);
         const bool ready = demod_->processPresynced(samples, 2);
         soft_.clear();
         while (demod_->hasPendingData()) {   // drain everything (:202-212)
@@ -495,6 +523,7 @@ private:
     std::unique_ptr<OFDMModulator> mod_;
     std::vector<float> soft_;
     float cfo_hz_ = 0.0f;
+    size_t training_start_sample_ = 0;   // SyncResult::start_sample of the last detection (0 before any: phase 0)
     bool synced_ = false;
 };
 

@@ -9,8 +9,11 @@
 #include <cstdio>
 #include <cstring>
 #include <random>
+#include <fcntl.h>
+#include <unistd.h>
 
 #define PU_DROPIN_WITH_ULTRA
+#include "sync/chirp_sync.hpp"
 #include "pu/pu_dropin.hpp"
 
 #include "ultra/fec.hpp"
@@ -300,6 +303,76 @@ static void process_section() {
     }
 }
 
+// tools/test_iwaveform.cpp:127-160 on OFDM_CHIRP frames: IWaveform::detectSync -> setFrequencyOffset -> process -> getSoftBits
+// through pu::OfdmChirpWaveform, against the reference's ChirpSync + OFDMDemodulator driven with the glue of
+// OFDMChirpWaveform::detectSync / process (src/waveform/ofdm_chirp_waveform.cpp:129-199).
+static void chirp_section() {
+    ModemConfig cfg{};
+    cfg.modulation = Modulation::DQPSK;
+    cfg.code_rate = CodeRate::R1_2;
+    cfg.use_pilots = false;
+    sync::ChirpConfig cc;
+    cc.sample_rate = static_cast<float>(cfg.sample_rate);
+    cc.f_start = 300.0f; cc.f_end = 2700.0f; cc.duration_ms = 500.0f; cc.gap_ms = 100.0f; cc.use_dual_chirp = true;
+    sync::ChirpSync chirp(cc);
+    LDPCEncoder enc(cfg.code_rate);
+    std::mt19937 rng(4242);
+    const float snrs[] = {20.0f, 6.0f, -4.0f};
+    for (int trial = 0; trial < 3; ++trial) {
+        Bytes payload(40);
+        for (auto& b : payload) b = static_cast<uint8_t>(rng() & 0xFF);
+        std::unique_ptr<IWaveform> wf = std::make_unique<pu::OfdmChirpWaveform>(cfg);
+        wf->configure(cfg.modulation, cfg.code_rate);
+        Samples tx(static_cast<size_t>(500 + 700 * trial), 0.0f);
+        const Samples pre = wf->generatePreamble();
+        const Samples ref_chirp = chirp.generate();
+        CHECK(pre.size() > ref_chirp.size() && std::memcmp(pre.data(), ref_chirp.data(), ref_chirp.size() * sizeof(float)) == 0,
+              "chirp trial %d generatePreamble chirp part", trial);
+        tx.insert(tx.end(), pre.begin(), pre.end());
+        const Samples data = wf->modulate(enc.encode(payload));
+        tx.insert(tx.end(), data.begin(), data.end());
+        tx.insert(tx.end(), 800, 0.0f);
+        const Samples rx = add_noise(tx, snrs[trial], 3000u + static_cast<uint32_t>(trial));
+        const SampleSpan audio(rx.data(), rx.size());
+
+        // reference side
+        std::fflush(stdout);                                        // detectDualChirp printf()s: park stdout on /dev/null for the call
+        const int saved = dup(1), nul = open("/dev/null", O_WRONLY);
+        if (nul >= 0) { dup2(nul, 1); close(nul); }
+        auto r = chirp.detectDualChirp(audio, 0.15f);
+        std::fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+        std::vector<float> ref_soft;
+        int ref_start = -1;
+        if (r.success) {
+            ref_start = r.down_chirp_start + static_cast<int>(chirp.getChirpSamples()) + static_cast<int>(cfg.sample_rate * 100.0f / 1000.0f);
+            float ph = -2.0f * M_PI * r.cfo_hz * static_cast<size_t>(ref_start) / cfg.sample_rate;
+            while (ph > M_PI) ph -= 2.0f * M_PI;
+            while (ph < -M_PI) ph += 2.0f * M_PI;
+            OFDMDemodulator d(cfg);
+            d.setFrequencyOffsetWithPhase(r.cfo_hz, ph);
+            if (d.processPresynced(SampleSpan(rx.data() + ref_start, rx.size() - ref_start), 2)) ref_soft = drain(d);
+        }
+        // drop-in side
+        wf->reset();
+        SyncResult sr;
+        const bool found = wf->detectSync(audio, sr, 0.15f);
+        CHECK(found == r.success, "chirp trial %d detected %d vs %d", trial, (int)found, (int)r.success);
+        if (found && r.success) {
+            CHECK(sr.start_sample == ref_start, "chirp trial %d start_sample %d vs %d", trial, sr.start_sample, ref_start);
+            CHECK(std::memcmp(&sr.cfo_hz, &r.cfo_hz, 4) == 0, "chirp trial %d cfo %.6f vs %.6f", trial, sr.cfo_hz, r.cfo_hz);
+            wf->setFrequencyOffset(sr.cfo_hz);
+            const bool ready = wf->process(SampleSpan(rx.data() + sr.start_sample, rx.size() - sr.start_sample));
+            const auto soft = wf->getSoftBits();
+            CHECK(ready == !ref_soft.empty() && soft.size() == ref_soft.size(), "chirp trial %d soft-bit count %zu vs %zu", trial, soft.size(), ref_soft.size());
+            double worst = 0;
+            for (size_t i = 0; i < std::min(soft.size(), ref_soft.size()); ++i)
+                worst = std::max(worst, static_cast<double>(std::fabs(soft[i] - ref_soft[i])) / std::max(0.5, static_cast<double>(std::fabs(ref_soft[i]))));
+            CHECK(worst <= 1e-4, "chirp trial %d LLR tolerance 1e-4 exceeded: %.3g", trial, worst);
+        }
+    }
+}
+
 int main() {
     setLogLevel(LogLevel::ERROR);
     if (!std::freopen("/dev/null", "w", stderr)) return 2;   // the reference prints unconditionally on the hot path
@@ -308,6 +381,7 @@ int main() {
         interleaver_section();
         ofdm_section();
         process_section();
+        chirp_section();
     } catch (const std::exception& e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

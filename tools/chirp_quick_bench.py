@@ -1,0 +1,35 @@
+"""Timing of the dual-chirp receive path: OFDM_CHIRP frames (57 600-sample dual chirp + M1 DQPSK R1/2 body)
+over AWGN: detectDualChirp + processPresynced for B frames.  python tools/chirp_quick_bench.py [B]"""
+import os, sys, time
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import refapi as R, oracleapi as O
+from projectultra_b200 import capi
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+ctx = capi.Context(0)
+cfg = R.config_m1(R.DQPSK, R.R1_2)
+dem = capi.OfdmDemodulator(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)))
+rng = np.random.default_rng(1)
+chirp = capi.chirp_generate()
+pool = [np.concatenate([np.zeros(500, np.float32), chirp, O.ofdm_tx(cfg, O.ldpc_encode(R.R1_2, rng.integers(0, 256, 40, dtype=np.uint8)), 0),
+                        np.zeros(500, np.float32)]) for _ in range(8)]
+L = len(pool[0])
+for snr in (15.0, -5.0):
+    tx = torch.from_numpy(np.stack([pool[i % 8] for i in range(B)])).cuda()
+    g = torch.Generator(device="cuda"); g.manual_seed(int(snr) + 50)
+    x = (tx + torch.randn(tx.shape, device="cuda", generator=g) * float(np.sqrt(0.02 / 10 ** (snr / 10)))).contiguous()
+    del tx
+    dem.chirp_receive_batch(x); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); out = dem.chirp_receive_batch(x); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print("snr=%5.1f detectDualChirp+process B=%d L=%d ms=%.1f  %.1f kframes/s  detected=%.3f" % (
+        snr, B, L, ms, B / ms, out[2][:, 0].float().mean().item()), flush=True)
+    if R.available():
+        xs = x[:2].cpu().numpy()
+        t0 = time.perf_counter()
+        for f in xs: R.ofdm_chirp_receive(cfg, f)
+        print("   reference CPU (1 core): %.1f ms/frame" % ((time.perf_counter() - t0) / len(xs) * 1e3), flush=True)
+    del x
