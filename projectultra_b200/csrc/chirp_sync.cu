@@ -45,6 +45,53 @@ __device__ float chirp_corr(const float* __restrict__ x, int Lw, int off, const 
     return __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ci, ci), __fmul_rn(cq, cq))), denom);
 }
 
+// Coarse search of detectChirpTemplate (:575-582) for the 32 consecutive coarse positions p0, p0 + 48, ... of one warp, staged through
+// shared memory.  Lanes sit 48 samples apart, so reading x[p0 + 48 l + i] with all lanes at the same tap i would put 16 lanes on each
+// of two banks (and, from global memory, 32 cache lines per instruction: what the first version of this kernel did).  The sums stay
+// ordered per lane, but nothing requires the lanes to be at the SAME tap: lane l runs s_l = 15 l mod 32 taps behind, which moves its
+// sample read to bank (l + t) mod 32 and its template reads to bank (t - 15 l) mod 32 -- all different across the warp.
+constexpr int kChirpTile = 512;                                      // taps per staged tile
+constexpr int kChirpXs = 48 * 31 + kChirpTile + 32;                  // samples per tile: all 32 windows, skew included
+struct ChirpWarpBuf { float xs[kChirpXs]; float tc[kChirpTile + 32]; float ts[kChirpTile + 32]; };
+
+__device__ float chirp_corr_coarse_warp(ChirpWarpBuf& W, const float* __restrict__ x, int Lw, int p0, const float* __restrict__ ts,
+                                        const float* __restrict__ tc, int n, float te) {
+    const int lane = threadIdx.x & 31;
+    const int skew = (15 * lane) & 31;
+    float ci = 0.0f, cq = 0.0f, se = 0.0f;
+    for (int t0 = 0; t0 < n + 32; t0 += kChirpTile) {
+        __syncwarp();
+        const int xbase = p0 + t0 - 32;                              // tile = x[xbase .. xbase + kChirpXs), taps [t0 - 32, t0 + kChirpTile)
+        for (int j = lane; j < kChirpXs; j += 32) {
+            const int idx = xbase + j;
+            W.xs[j] = (idx >= 0 && idx < Lw) ? x[idx] : 0.0f;
+        }
+        for (int j = lane; j < kChirpTile + 32; j += 32) {
+            const int i = t0 - 32 + j;
+            const bool in = i >= 0 && i < n;
+            W.tc[j] = in ? __ldg(&tc[i]) : 0.0f;
+            W.ts[j] = in ? __ldg(&ts[i]) : 0.0f;
+        }
+        __syncwarp();
+        const int xo = 48 * lane + 32 - skew - t0, to = 32 - skew - t0;
+        // this lane's steps inside the tile: tap i = t - skew must lie in [0, n)
+        const int t_lo = max(t0, skew), t_hi = min(t0 + kChirpTile, n + skew);
+        const float* px = W.xs + xo;
+        const float* pc = W.tc + to;
+        const float* ps = W.ts + to;
+#pragma unroll 4
+        for (int t = t_lo; t < t_hi; ++t) {
+            const float sv = px[t];
+            ci = __fadd_rn(ci, __fmul_rn(sv, pc[t]));
+            cq = __fadd_rn(cq, __fmul_rn(sv, ps[t]));
+            se = __fadd_rn(se, __fmul_rn(sv, sv));
+        }
+    }
+    const float denom = __fsqrt_rn(__fmul_rn(se, te));
+    if (denom < 1e-10f) return 0.0f;
+    return __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ci, ci), __fmul_rn(cq, cq))), denom);
+}
+
 // CTA-wide "first maximum": every thread holds its best (c, p) over an ascending subset (c > running best, strict); the result is
 // the maximum value at its smallest position, seeded with (seed_c, seed_p).
 __device__ void chirp_reduce(ChirpShared& S, float c, int p, float seed_c, int seed_p) {
@@ -76,7 +123,7 @@ __device__ void chirp_reduce(ChirpShared& S, float c, int p, float seed_c, int s
 }
 
 // detectChirpTemplate (:560-629) on the window x[0 .. Lw): returns the position or -1, *corr_out = best correlation seen
-__device__ int chirp_detect_template(ChirpShared& S, const float* __restrict__ x, int Lw, const float* ts, const float* tc, int n, float te,
+__device__ int chirp_detect_template(ChirpShared& S, ChirpWarpBuf* WB, const float* __restrict__ x, int Lw, const float* ts, const float* tc, int n, float te,
                                      float threshold, float* corr_out) {
     const int tid = threadIdx.x;
     *corr_out = 0.0f;
@@ -85,9 +132,14 @@ __device__ int chirp_detect_template(ChirpShared& S, const float* __restrict__ x
     // coarse search, step 48
     float bc = 0.0f;
     int bp = -1;
-    for (int pos = tid * 48; pos < search_len; pos += kChirpThreads * 48) {
-        const float c = chirp_corr(x, Lw, pos, ts, tc, n, te);
-        if (c > bc) { bc = c; bp = pos; }
+    {
+        const int n_pos = (search_len + 47) / 48;                    // positions 0, 48, ... < search_len
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int g = warp; g * 32 < n_pos; g += kChirpThreads / 32) {   // 32 consecutive positions per warp and round, ascending
+            const float c = chirp_corr_coarse_warp(WB[warp], x, Lw, g * 32 * 48, ts, tc, n, te);
+            const int m = g * 32 + lane;
+            if (m < n_pos && c > bc) { bc = c; bp = m * 48; }
+        }
     }
     chirp_reduce(S, bp >= 0 ? bc : -1.0f, bp, 0.0f, -1);
     float best = S.best_c;
@@ -134,20 +186,22 @@ __global__ void __launch_bounds__(kChirpThreads) chirp_detect_kernel(ChirpDev c,
                                                                      float* __restrict__ phase_out, int* __restrict__ n_llr,
                                                                      int llr_per_symbol, int llr_stride) {
     __shared__ ChirpShared S;
+    extern __shared__ __align__(16) unsigned char chirp_smem[];
+    ChirpWarpBuf* WB = reinterpret_cast<ChirpWarpBuf*>(chirp_smem);   // one staging buffer per warp
     const int tid = threadIdx.x;
     const float* x = samples + static_cast<size_t>(blockIdx.x) * frame_stride;
     int success = 0, up_start = -1, down_start = -1, start = -1;   // DualChirpResult defaults (chirp_sync.hpp:317-324)
     float cfo = 0.0f, up_corr = 0.0f, dn_corr = 0.0f, phase = 0.0f;
     do {
         if (L < 2 * c.n + c.gap) break;                                                       // :368-372
-        const int up_pos = chirp_detect_template(S, x, L, c.up_s, c.up_c, c.n, c.up_e, threshold, &up_corr);
+        const int up_pos = chirp_detect_template(S, WB, x, L, c.up_s, c.up_c, c.n, c.up_e, threshold, &up_corr);
         if (up_pos < 0) break;
         const int ds = up_pos + c.n / 2, expected = up_pos + c.n + c.gap, margin = 2 * c.n;      // :423-435
         int de = min(L, expected + margin);
         if (ds >= L) break;
         if (de <= ds + c.n) de = min(L, ds + 2 * c.n);
         float dc;
-        const int rel = chirp_detect_template(S, x + ds, de - ds, c.dn_s, c.dn_c, c.n, c.dn_e, threshold, &dc);
+        const int rel = chirp_detect_template(S, WB, x + ds, de - ds, c.dn_s, c.dn_c, c.n, c.dn_e, threshold, &dc);
         if (rel < 0) break;
         const int down_pos = rel + ds;
         dn_corr = dc;
@@ -189,7 +243,9 @@ cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t 
                                 int4* out_info, float4* out_f, int* frame_start, int* frame_nsym, float* cfo_out, float* phase_out,
                                 int* n_llr, int llr_per_symbol, int llr_stride, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
-    chirp_detect_kernel<<<static_cast<unsigned>(B), kChirpThreads, 0, st>>>(c, samples, frame_stride, L, threshold, sym_len, out_info, out_f,
+    const size_t smem = sizeof(ChirpWarpBuf) * (kChirpThreads / 32);
+    cudaFuncSetAttribute(chirp_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    chirp_detect_kernel<<<static_cast<unsigned>(B), kChirpThreads, smem, st>>>(c, samples, frame_stride, L, threshold, sym_len, out_info, out_f,
                                                                            frame_start, frame_nsym, cfo_out, phase_out, n_llr,
                                                                            llr_per_symbol, llr_stride);
     return cudaGetLastError();

@@ -128,12 +128,12 @@ struct RxShared {
 // FAM: 0 = modulation family decided at run time, 1 = differential (DBPSK/DQPSK/D8PSK), 2 = coherent: the warp form is
 // compiled once per family so that each instance carries only its own equaliser and demappers (instruction-cache footprint).
 template <int NFFT, bool WARPG, int FAM>
-__global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, WARPG ? 5 : 1) ofdm_presynced_kernel(
+__global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kernel(
     OfdmDev d, WgTw twa, const float* __restrict__ samples, size_t frame_stride, size_t B, int n_symbols, int training,
     const float* __restrict__ cfo_hz, const float* __restrict__ cfo_phase,
     float* __restrict__ llr_out, size_t llr_stride, int llr_limit,
     float* __restrict__ snr_db_out, float* __restrict__ final_cfo_out, float* __restrict__ dbg, unsigned group_bytes,
-    const int* __restrict__ frame_start, const int* __restrict__ frame_nsym) {
+    const int* __restrict__ frame_start, const int* __restrict__ frame_nsym, int phase_sync) {
     constexpr int LOG2N = (NFFT == 512) ? 9 : 10;
     constexpr int T = WARPG ? 32 : NFFT / 8;
     using G = WgGeom<NFFT>;
@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
     const int tid = WARPG ? static_cast<int>(threadIdx.x & 31) : static_cast<int>(threadIdx.x);
     const int wig = WARPG ? static_cast<int>(threadIdx.x >> 5) : 0;
     const size_t frame = WARPG ? static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + wig : blockIdx.x;
-    if (WARPG && frame >= B) return;     // whole warps leave; no CTA-wide barrier follows
+    // phase_sync (warp form): all warps of the CTA meet at a barrier at the top of every symbol, so that they walk the same part of
+    // this long kernel at the same time and share its instruction-cache lines; frames past the batch then idle instead of leaving
+    const bool no_frame = WARPG && frame >= B;
+    if (no_frame && !phase_sync) return;
+    const int n_symbols_cta = n_symbols;
     unsigned char* smem_raw = smem_all + static_cast<size_t>(wig) * group_bytes;
     // CTA mode: [NFFT + NFFT/8] FFT buffer, then [sym_len] rotator phases.  Warp mode: [BUF] transpose buffer (its first
     // NFFT entries double as the buffer of rotated samples), then the [2 CW] bins around DC; phases stay in registers.
@@ -152,8 +156,9 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
                         : *reinterpret_cast<RxShared*>(theta + ((d.sym_len + 3) & ~3));
     // optional per-frame window (acquired frames, pu_ofdm_process_batch): the symbols start frame_start[frame] samples into the
     // row and there are frame_nsym[frame] of them; the NCO restarts there (mixer.reset(), demodulator.cpp:583)
-    const float* x = samples + frame * frame_stride + (frame_start ? frame_start[frame] : 0);
-    if (frame_nsym) n_symbols = min(n_symbols, max(frame_nsym[frame], 0));
+    const float* x = samples + (no_frame ? 0 : frame * frame_stride + (frame_start ? frame_start[frame] : 0));
+    if (frame_nsym && !no_frame) n_symbols = min(n_symbols, max(frame_nsym[frame], 0));
+    if (no_frame) n_symbols = 0;
     const int nd = d.n_data, np = d.n_pilot, nu = nd + np;
     const bool differential = FAM == 1 ? true : FAM == 2 ? false : (d.mod == PU_MOD_DBPSK || d.mod == PU_MOD_DQPSK || d.mod == PU_MOD_D8PSK);
 
@@ -174,10 +179,10 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
     }
 
     if (tid == 0) {
-        const float f = cfo_hz ? cfo_hz[frame] : 0.0f;
+        const float f = (cfo_hz && !no_frame) ? cfo_hz[frame] : 0.0f;
         S.cfo_hz = f;
         S.cfo_filt = f;
-        S.rot_phase = cfo_phase ? cfo_phase[frame] : 0.0f;
+        S.rot_phase = (cfo_phase && !no_frame) ? cfo_phase[frame] : 0.0f;
         S.noise_var = 0.1f;
         S.snr_lin = 1.0f;
         S.timing = 0.0f;
@@ -198,7 +203,11 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
     PU_GSYNC();
 
     int llr_pos = 0;   // LLRs emitted so far (same for all threads)
-    for (int s = 0; s < n_symbols; ++s) {
+    for (int s = 0; s < (WARPG && phase_sync ? n_symbols_cta : n_symbols); ++s) {
+        if (WARPG && phase_sync) {
+            __syncthreads();
+            if (s >= n_symbols) continue;
+        }
         const bool is_train = s < training;
         const float* xs = x + static_cast<size_t>(s) * d.sym_len;
         const float2* nco = d.nco + static_cast<size_t>(s) * d.sym_len;
@@ -806,7 +815,7 @@ __global__ void __launch_bounds__(WARPG ? (NFFT == 512 ? 128 : 96) : NFFT / 8, W
         llr_pos += nd * d.bps;
         PU_GSYNC();
     }
-    if (tid == 0) {
+    if (tid == 0 && !no_frame) {
         if (snr_db_out) snr_db_out[frame] = 10.0f * log10f(S.snr_lin);   // getEstimatedSNR, demodulator.cpp:797-799
         if (final_cfo_out) final_cfo_out[frame] = S.cfo_hz;              // getFrequencyOffset, :801-803
     }
@@ -1151,25 +1160,28 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
     for (int b : p.data_bin) near_dc = near_dc && ((b >= 1 && b < cw) || b > p.nfft - cw);
     for (int b : p.pilot_bin) near_dc = near_dc && ((b >= 1 && b < cw) || b > p.nfft - cw);
     if (!d_dbg && !no_warpg && near_dc) {
-        const int warps = p.nfft == 512 ? 4 : 3;
+        // one CTA per SM with as many frames as shared memory holds, warps re-aligned at every symbol (default; r29: M3 32QAM 3.16 ->
+        // 2.49 ms, M1 16QAM 7.19 -> 6.08 ms per 53k frames); PU_OFDM_WARPG_SYNC=0 selects small CTAs without the barrier
+        static const bool wsync = !(getenv("PU_OFDM_WARPG_SYNC") != nullptr && atoi(getenv("PU_OFDM_WARPG_SYNC")) == 0);
+        const int warps = wsync ? (p.nfft == 512 ? 16 : 14) : (p.nfft == 512 ? 4 : 3);
         const size_t buf_f2 = static_cast<size_t>(p.nfft + (p.nfft >> (p.nfft == 512 ? 4 : 5)) + 2 * cw);
         const unsigned group = static_cast<unsigned>((buf_f2 * sizeof(float2) + sizeof(pu::RxShared) + 15) & ~size_t(15));
         const unsigned wgrid = static_cast<unsigned>((B + warps - 1) / warps);
         const bool diff = pu::is_differential(p.cfg.modulation);
         using WK = void (*)(pu::OfdmDev, pu::WgTw, const float*, size_t, size_t, int, int, const float*, const float*, float*, size_t, int,
-                            float*, float*, float*, unsigned, const int*, const int*);
+                            float*, float*, float*, unsigned, const int*, const int*, int);
         const WK wk = p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1> : pu::ofdm_presynced_kernel<512, true, 2>)
                                     : (diff ? pu::ofdm_presynced_kernel<1024, true, 1> : pu::ofdm_presynced_kernel<1024, true, 2>);
         static bool attrw = false;
         if (!attrw) {
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
             attrw = true;
         }
         wk<<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr,
-                                                                           llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym);
+                                                                           llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym, wsync ? 1 : 0);
         h->last_kernel = 4;
         h->ctx->launches.fetch_add(1);
         PU_CUDA_TRY(cudaGetLastError());
@@ -1179,12 +1191,12 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         static bool attr512 = false;
         if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
         pu::ofdm_presynced_kernel<512, false, 0><<<grid, 64, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
-                                                                            d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym);
+                                                                            d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym, 0);
     } else {
         static bool attr1024 = false;
         if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
         pu::ofdm_presynced_kernel<1024, false, 0><<<grid, 128, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
-                                                                              d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym);
+                                                                              d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym, 0);
     }
     h->last_kernel = 1;
     h->ctx->launches.fetch_add(1);
