@@ -7,6 +7,8 @@ python tools/ldpc_quick_bench.py 1048576 > $OUT/ldpc_config2.log 2>&1
 for m in m1 m3 m1qam16; do python tools/ofdm_quick_bench.py 4096 $m > $OUT/demod_$m.log 2>&1; done
 QB_CHANNEL=good python tools/ofdm_quick_bench.py 4096 m3 > $OUT/demod_m3_good.log 2>&1
 python tools/acquire_quick_bench.py 8192 > $OUT/acquire.log 2>&1
+python tools/dpsk_acquire_quick_bench.py 2048 > $OUT/dpsk_acquire.log 2>&1
+python tools/chirp_quick_bench.py 2048 > $OUT/chirp.log 2>&1
 python - > $OUT/tx.log 2>&1 <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -32,6 +34,8 @@ echo; echo "### Config 2: LDPC alone, 1 048 576 codewords (tools/ldpc_quick_benc
 echo; echo "### Demodulator kernels, 53 248 frames (tools/ofdm_quick_bench.py: m1 = headline, m3 = config 3, m1qam16 = pilots/2)"; echo '```'
 for f in demod_m1 demod_m3 demod_m3_good demod_m1qam16; do tail -1 $OUT/$f.log | sed 's/^ *//'; done; echo '```'
 echo; echo "### Acquisition (config 1 as literally specified), 8 192 frames of 10 124 samples (tools/acquire_quick_bench.py)"; echo '```'; cat $OUT/acquire.log; echo '```'
+echo; echo "### DPSK Barker acquisition (config 4 as literally specified), 2 048 frames of 139 392 samples (tools/dpsk_acquire_quick_bench.py)"; echo '```'; cat $OUT/dpsk_acquire.log; echo '```'
+echo; echo "### Dual-chirp synchronisation + presynced demodulation of OFDM_CHIRP frames (tools/chirp_quick_bench.py)"; echo '```'; cat $OUT/chirp.log; echo '```'
 echo; echo "### Transmitter (pu_ofdm_tx_batch)"; echo '```'; cat $OUT/tx.log; echo '```'
 } > $OUT/workloads.md
 cat $OUT/workloads.md | tail -40
