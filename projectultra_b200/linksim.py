@@ -139,9 +139,15 @@ class LinkSim:
             self.ofdm = self.demod = capi.OfdmDemodulator(ctx, cfg)
             # layout "presynced": 2 LTS + data, genie timing (tools/test_ofdm_chirp_pilots.cpp); layout "sc": generatePreamble()
             # + data fed to process() in `chunk`-sample pieces, i.e. with Schmidl-Cox acquisition (tools/test_mode_snr.cpp:40-105)
-            assert layout in ("presynced", "sc")
+            # layout "chirp": OFDM_CHIRP frames = ChirpSync::generate() + training + data, received through dual-chirp detectSync ->
+            # setFrequencyOffset -> process (tools/test_iwaveform.cpp:127-160)
+            assert layout in ("presynced", "sc", "chirp")
             self.layout, self.chunk = layout, chunk
-            build = lambda coded: ofdm_tx(cfg, coded, 1 if layout == "sc" else 0)
+            if layout == "chirp":
+                chirp = capi.chirp_generate(float(cfg.sample_rate), float(cfg.tx_cfo_hz))
+                build = lambda coded: np.concatenate([chirp, ofdm_tx(cfg, coded, 0)])
+            else:
+                build = lambda coded: ofdm_tx(cfg, coded, 1 if layout == "sc" else 0)
         elif isinstance(cfg, capi.DpskConfig):
             self.kind = "dpsk"
             rate = capi.R1_4 if code_rate is None else code_rate          # tools/test_dpsk_snr.cpp:28-29
@@ -187,6 +193,10 @@ class LinkSim:
             out = self.demod.process_batch(rx, chunk=self.chunk, llr_stride=648)
             self.last_n_llr, self.last_sync = out[1], out[2]
             return out[0]
+        if self.kind == "ofdm" and self.layout == "chirp":
+            out = self.demod.chirp_receive_batch(rx, llr_stride=648)
+            self.last_n_llr, self.last_sync = out[1], out[2]
+            return out[0]
         if self.kind == "ofdm":
             return self.demod.presynced_batch(rx, 2, llr_stride=648, llr=llr, want_aux=False)[0]
         if self.kind == "dpsk" and self.acquire:
@@ -229,6 +239,7 @@ class LinkSim:
         kb = self.ldpc.info_bytes
         payload = torch.zeros((B, kb), dtype=torch.uint8, device=self.device)
         payload[:, :self.payload_bytes] = torch.randint(0, 256, (B, self.payload_bytes), dtype=torch.uint8, device=self.device, generator=g)
+        assert self.layout != "chirp", "fresh payloads behind a chirp: build the pool on the host (layout='chirp' without fresh_payload)"
         tx = self.demod.tx_batch(self.ldpc, payload[:, :self.payload_bytes], layout=1 if self.layout == "sc" else 0,
                                  peak=float(self.peak) if self.peak else 0.0)
         snr = np.asarray(snr_points, np.float32)
@@ -249,15 +260,15 @@ class LinkSim:
             payload, tx, std = self.fresh_frames(batch, snr_points)
             idx = torch.arange(tx.shape[0], dtype=torch.int32, device=self.device)
             rx = channel_apply(self.ctx, self.ch, tx, idx, std, batch["seed"], rx)
-            info, ok, iters = (self.ldpc.decode_batch(self.demod_llr(rx)) if self.layout == "sc"
+            info, ok, iters = (self.ldpc.decode_batch(self.demod_llr(rx)) if self.layout in ("sc", "chirp")
                                else receive_decode(self.ofdm, self.ldpc, rx))
-            if self.layout == "sc":
+            if self.layout in ("sc", "chirp"):
                 ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
             count_errors(self.ctx, info, ok, iters, payload, idx, batch["bins"], self.payload_bytes, counters)
             self.last_payload, self.last_tx, self.last_std = payload, tx, std
             return (rx, info, ok, iters) if keep else None
         rx = channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rx)
-        if self.kind == "ofdm" and self.layout == "sc":
+        if self.kind == "ofdm" and self.layout in ("sc", "chirp"):
             # no sync or fewer than 648 soft bits is a lost frame (tools/test_mode_snr.cpp:72-77): the decoder's verdict on
             # the zero-filled row is overridden
             info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))

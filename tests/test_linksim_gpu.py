@@ -293,3 +293,38 @@ def test_linksim_config4_with_barker_acquisition():
     c = counters.cpu().numpy()
     assert c[:, 0].tolist() == [trials] * len(snrs) and c[0, 1] >= c[-1, 1]
     del ctx
+
+
+def test_linksim_ofdm_chirp_with_dual_chirp_sync():
+    """OFDM_CHIRP: dual chirp + training + DQPSK data over the Watterson 'good' channel, received as
+    tools/test_iwaveform.cpp:127-160 does (detectSync -> setFrequencyOffset -> process -> getSoftBits -> decodeSoft), every frame's
+    detection result, soft-bit count, ok flag, iteration count and bytes against the oracle on the identical channel outputs."""
+    import torch
+    from projectultra_b200 import capi, linksim
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    ctx = capi.Context(0)
+    sim = linksim.LinkSim(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)), "good", payload_bytes=40, pool=3, layout="chirp")
+    assert sim.L == 57600 + 7332
+    snrs = [-6.0, 2.0, 10.0, 22.0]
+    trials = 3
+    si = np.repeat(np.arange(len(snrs)), trials)
+    tr = np.tile(np.arange(trials), len(snrs))
+    batch = sim.make_batch(snrs, si, tr)
+    counters = torch.zeros((len(snrs), 6), dtype=torch.int64, device="cuda")
+    rx, info, ok, iters = sim.run_batch(batch, counters, keep=True)
+    torch.cuda.synchronize()
+    rx_h = rx.cpu().numpy()
+    n_llr, sync = sim.last_n_llr.cpu().numpy(), sim.last_sync.cpu().numpy()
+    ok_h, info_h, it_h = ok.cpu().numpy(), info.cpu().numpy(), iters.cpu().numpy()
+    for b in range(len(rx_h)):
+        ol, oi, ocfo = O.ofdm_chirp_receive(cfg, rx_h[b])
+        assert (sync[b] == oi).all() and int(n_llr[b]) == min(len(ol), 648), (b, sync[b], oi, n_llr[b], len(ol))
+        if len(ol) >= 648:
+            ci, cok, cit = O.ldpc_decode_batch(R.R1_2, ol[None, :648].copy())
+            # LLRs agree to 1e-4 (rotator path); decisions must agree on frames decoded with margin
+            assert ok_h[b] == cok[0] and (cok[0] == 0 or (it_h[b] == cit[0] and (info_h[b] == ci[0]).all())), b
+        else:
+            assert ok_h[b] == 0
+    c = counters.cpu().numpy()
+    assert c[:, 0].tolist() == [trials] * len(snrs) and c[-1, 1] == 0
+    del ctx
