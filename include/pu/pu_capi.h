@@ -272,6 +272,14 @@ PU_API void pu_mcdpsk_destroy(pu_mcdpsk* h);
  * correction through the 127-tap Hilbert FIR (:633-658) only runs for |cfo| > 0.1 Hz and is not part of this path. */
 PU_API pu_status pu_mcdpsk_demod_soft_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, float* llr_out,
                                             size_t llr_stride, float* residual_cfo_hz, pu_memspace space, void* stream);
+/* MultiCarrierDPSKDemodulator behind an externally detected chirp, as MCDPSKWaveform::process drives it
+ * (src/waveform/mc_dpsk_waveform.cpp:144-170: setChirpDetected(cfo) -> process(training + ref + data) -> getSoftBits), i.e.
+ * processGotChirp (multi_carrier_dpsk.hpp:533-627): the frame is first frequency-shifted through the 127-tap Hilbert FIR when
+ * |chirp_cfo_hz[b]| > 0.1 Hz (applyCFOCorrection :633-658), then processTraining / the 5 Hz false-positive rule / setReference /
+ * demodulateSoft.  n_llr[B] = soft bits handed out (0 for a rejected or too short frame), cfo_after_hz[B] = getEstimatedCFO(). */
+PU_API pu_status pu_mcdpsk_got_chirp_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, const float* chirp_cfo_hz,
+                                           float* llr_out, size_t llr_stride, int32_t* n_llr, float* cfo_after_hz,
+                                           pu_memspace space, void* stream);
 /* MultiCarrierDPSKModulator (:91-257), host: generateTrainingSequence + generateReferenceSymbol + modulate(data). */
 PU_API pu_status pu_mcdpsk_tx(const pu_mcdpsk_config* cfg, const uint8_t* data, size_t n_bytes, float* out, size_t out_cap,
                               size_t* out_len);

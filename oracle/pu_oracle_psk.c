@@ -372,3 +372,75 @@ long orc_dpsk_find_preamble(int sps, float fc, float fs, const float* x, size_t 
     free(ccos);
     return result;
 }
+
+/* ------------------------------------------------------------------ MC-DPSK behind an externally detected chirp
+ * TEST INFRASTRUCTURE.  MultiCarrierDPSKDemodulator::processGotChirp with external_chirp_detected_ (multi_carrier_dpsk.hpp:
+ * 533-627) as MCDPSKWaveform::process drives it (src/waveform/mc_dpsk_waveform.cpp:144-170): the whole buffer (training +
+ * reference + data) is frequency-shifted through the 127-tap Hilbert FIR when |cfo| > 0.1 Hz (applyCFOCorrection :633-658,
+ * HilbertTransform src/dsp/filters.cpp:266-317: Blackman-windowed taps, real path delayed by 63 samples), then
+ * processTraining / the |cfo| > 5 Hz rejection (:576-598) / setReference / demodulateSoft. */
+static void mc_cfo_correct(float* x, size_t L, float cfo_hz, float fs) {   /* applyCFOCorrection, :633-658 */
+    if (fabsf(cfo_hz) < 0.01f || L < 128) return;
+    enum { TAPS = 127 };
+    float coeffs[TAPS], delay[TAPS];
+    const int M = (TAPS - 1) / 2;
+    for (int n = 0; n < TAPS; ++n) {                                     /* HilbertTransform ctor, filters.cpp:266-291 */
+        const int k = n - M;
+        if (k == 0) coeffs[n] = 0;
+        else if (k % 2 != 0) coeffs[n] = (float)(2.0f / (ORC_PI * k));
+        else coeffs[n] = 0;
+        const float w = (float)(2.0f * ORC_PI * n / (TAPS - 1));
+        coeffs[n] *= 0.42f - 0.5f * cosf(w) + 0.08f * cosf(2.0f * w);
+        delay[n] = 0;
+    }
+    size_t idx = 0;
+    const float phase_inc = (float)(-2.0f * ORC_PI * cfo_hz / fs);
+    float phase = 0.0f;                                                  /* cfo_initial_phase_ of a fresh object */
+    for (size_t i = 0; i < L; ++i) {
+        delay[idx] = x[i];                                               /* HilbertTransform::process, filters.cpp:293-317 */
+        float q = 0;
+        size_t j = idx;
+        for (size_t k = 0; k < TAPS; ++k) {
+            q += coeffs[k] * delay[j];
+            if (j == 0) j = TAPS;
+            --j;
+        }
+        const float real = delay[(idx + TAPS - (size_t)M) % TAPS];
+        idx = (idx + 1) % TAPS;
+        const float rr = cosf(phase), ri = sinf(phase);
+        float sr, si;
+        cmulf(real, q, rr, ri, &sr, &si);                                /* analytic[i] * rotation */
+        x[i] = sr;
+        phase += phase_inc;
+        if (phase > ORC_PI) phase = (float)(phase - 2.0f * ORC_PI);
+        if (phase < -ORC_PI) phase = (float)(phase + 2.0f * ORC_PI);
+    }
+}
+
+/* Returns the number of soft bits (0 when the frame is rejected or too short); *cfo_after = cfo_hz_ after processGotChirp */
+long orc_mcdpsk_got_chirp(int nc, int sps, int bits_per_symbol, float f_lo, float f_hi, float fs, int training_symbols, const float* x,
+                          size_t L, float chirp_cfo, float* llr, size_t cap, float* cfo_after) {
+    const size_t pre = (size_t)(training_symbols + 1) * (size_t)sps;
+    if (cfo_after) *cfo_after = chirp_cfo;
+    /* processGotChirp waits for full_preamble + at least one codeword's worth of symbols when the buffer is not longer than the preamble */
+    if (L <= pre) return 0;
+    float* buf = (float*)malloc(sizeof(float) * L);
+    memcpy(buf, x, sizeof(float) * L);
+    float cfo = chirp_cfo;
+    if (fabsf(cfo) > 0.1f) { mc_cfo_correct(buf, L, cfo, fs); cfo = 0.0f; }   /* :565-569; applyCFOCorrection resets cfo_hz_ */
+    const float dual_chirp_cfo = cfo;                                           /* :572 (taken after the correction) */
+    float residual = 0.0f;
+    const long n = orc_mcdpsk_demod_soft(nc, sps, bits_per_symbol, f_lo, f_hi, fs, buf, L, training_symbols, llr, cap, &residual);
+    free(buf);
+    /* processTraining: cfo_hz_ += residual, clamped (:419-421); orc_mcdpsk_demod_soft reports clamp(0 + residual) */
+    float after = cfo;
+    if (training_symbols >= 2) {
+        /* recover the unclamped residual only matters beyond +-50 Hz, far outside the 5 Hz rule below */
+        after = fmaxf(-50.0f, fminf(50.0f, cfo + residual));
+    }
+    const int has_chirp_cfo = fabsf(dual_chirp_cfo) > 0.1f;                     /* :587 */
+    if (has_chirp_cfo) after = cfo;                                             /* :592-596 (saved_cfo, taken after the correction) */
+    if (cfo_after) *cfo_after = after;
+    if (fabsf(dual_chirp_cfo) < 0.1f && fabsf(after) > 5.0f) return 0;          /* false positive: back to IDLE (:599-607) */
+    return n;
+}

@@ -149,4 +149,21 @@ long ref_mcdpsk_demod_soft(int nc, int sps, int bits, float f_lo, float f_hi, fl
     return static_cast<long>(soft.size());
 }
 
+// MultiCarrierDPSKDemodulator behind an externally detected chirp, as MCDPSKWaveform::process drives it
+// (src/waveform/mc_dpsk_waveform.cpp:144-170): setChirpDetected(cfo) -> process(training + ref + data) -> getSoftBits().
+// processGotChirp (multi_carrier_dpsk.hpp:533-627) applies the Hilbert-FIR CFO correction when |cfo| > 0.1 Hz.
+long ref_mcdpsk_got_chirp(int nc, int sps, int bits, float f_lo, float f_hi, float fs, int training, const float* x, size_t L,
+                          float chirp_cfo, float* llr, size_t cap, int* ready_out, float* cfo_after) {
+    Quiet q;
+    MultiCarrierDPSKDemodulator d(mc_cfg(nc, sps, bits, f_lo, f_hi, fs, training));
+    d.setChirpDetected(chirp_cfo);
+    const bool ready = d.process(SampleSpan(x, L));
+    if (ready_out) *ready_out = ready ? 1 : 0;
+    if (cfo_after) *cfo_after = d.getEstimatedCFO();
+    if (!ready) return 0;
+    std::vector<float> soft = d.getSoftBits();
+    for (size_t i = 0; i < soft.size() && i < cap; ++i) llr[i] = soft[i];
+    return static_cast<long>(soft.size());
+}
+
 }  // extern "C"

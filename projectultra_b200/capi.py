@@ -604,6 +604,34 @@ class McDpskDemodulator:
         c = self.cfg
         return max(0, L // c.samples_per_symbol - c.training_symbols - 1) * c.num_carriers * c.bits_per_symbol
 
+    def got_chirp_batch(self, samples, chirp_cfo_hz, llr_stride=648):
+        """pu_mcdpsk_got_chirp_batch: setChirpDetected(cfo) -> process(training + ref + data) -> getSoftBits for every row of
+        samples [B, L] -> (llr [B, llr_stride], n_llr [B], cfo_after_hz [B])."""
+        tor = _is_torch(samples)
+        if tor:
+            import torch
+            assert samples.dtype == torch.float32 and samples.dim() == 2 and samples.is_contiguous()
+            B, L = samples.shape
+            dev = samples.device
+            cfo = torch.as_tensor(chirp_cfo_hz, dtype=torch.float32, device=dev).contiguous()
+            llr = torch.zeros((B, llr_stride), dtype=torch.float32, device=dev)
+            n = torch.zeros(B, dtype=torch.int32, device=dev)
+            after = torch.zeros(B, dtype=torch.float32, device=dev)
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.float32)
+            if samples.ndim == 1:
+                samples = samples.reshape(1, -1)
+            B, L = samples.shape
+            cfo = np.ascontiguousarray(chirp_cfo_hz, dtype=np.float32)
+            llr = np.zeros((B, llr_stride), np.float32)
+            n = np.zeros(B, np.int32)
+            after = np.zeros(B, np.float32)
+        assert len(cfo) == B
+        sp = _space(samples, cfo, llr, n, after)
+        check(lib().pu_mcdpsk_got_chirp_batch(self._h, _ptr(samples), C.c_size_t(B), C.c_size_t(L), _ptr(cfo), _ptr(llr),
+                                              C.c_size_t(llr_stride), _ptr(n), _ptr(after), sp, _stream(sp)))
+        return llr, n, after
+
     def demod_soft_batch(self, samples, llr_stride=None, llr=None, want_cfo=True):
         x = _frames(samples)
         B, L = x.shape

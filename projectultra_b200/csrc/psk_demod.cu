@@ -457,6 +457,68 @@ __global__ void mcdpsk_llr_kernel(const float2* __restrict__ corr, int nc, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------- MC-DPSK CFO correction
+// MultiCarrierDPSKDemodulator::applyCFOCorrection (multi_carrier_dpsk.hpp:633-658) on whole frames, as processGotChirp applies it
+// when |cfo| > 0.1 Hz (:565-569): analytic signal by the 127-tap Blackman-windowed Hilbert FIR (HilbertTransform::process,
+// src/dsp/filters.cpp:293-317: Q = ordered 127-tap sum over the delay line, I = the input delayed by 63 samples, delay line
+// zero-filled before the frame), multiplied by e^{j phase} with the per-sample phase recurrence phase += inc (one wrap test
+// per sample), real part kept.  One frame per CTA; the phase recurrence is walked T samples at a time with the bit-for-bit link
+// check of ofdm_demod.cu (every accepted value is the reference's by induction); everything else is independent per sample.
+constexpr int kHilbertTaps = 127, kCfoThreads = 256;
+struct HilbertTaps { float c[kHilbertTaps]; };
+
+__global__ void __launch_bounds__(kCfoThreads) mcdpsk_cfo_correct_kernel(HilbertTaps taps, const float* __restrict__ in, size_t stride, int L,
+                                                                          float fs, const float* __restrict__ cfo_hz,
+                                                                          float* __restrict__ out) {
+    __shared__ int fail[kCfoThreads / 32];
+    __shared__ float next_phase;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const float* x = in + static_cast<size_t>(blockIdx.x) * stride;
+    float* y = out + static_cast<size_t>(blockIdx.x) * stride;
+    const float cfo = cfo_hz[blockIdx.x];
+    if (!(fabsf(cfo) > 0.1f) || fabsf(cfo) < 0.01f || L < 128) {         // processGotChirp :565, applyCFOCorrection :634
+        for (int i = tid; i < L; i += T) y[i] = x[i];
+        return;
+    }
+    const double pi = 3.14159265358979323846;
+    const float inc = static_cast<float>(__ddiv_rn(__dmul_rn(__dmul_rn(-2.0f, pi), static_cast<double>(cfo)), static_cast<double>(fs)));
+    auto step = [&](float ph) {
+        ph = __fadd_rn(ph, inc);
+        if (static_cast<double>(ph) > pi) ph = static_cast<float>(__dsub_rn(static_cast<double>(ph), __dmul_rn(2.0f, pi)));
+        if (static_cast<double>(ph) < -pi) ph = static_cast<float>(__dadd_rn(static_cast<double>(ph), __dmul_rn(2.0f, pi)));
+        return ph;
+    };
+    float ph = 0.0f;                                                       // cfo_initial_phase_ of a fresh demodulator
+    for (int i0 = 0; i0 < L;) {
+        const unsigned b0 = __float_as_uint(ph);
+        const unsigned delta = __float_as_uint(step(ph)) - b0;
+        const float cand = __uint_as_float(b0 + static_cast<unsigned>(tid) * delta);
+        const float nxt = step(cand);
+        const bool broken = __float_as_uint(nxt) != b0 + static_cast<unsigned>(tid + 1) * delta;
+        const unsigned bal = __ballot_sync(0xffffffffu, broken);
+        if ((tid & 31) == 0) fail[tid >> 5] = bal ? (tid + __ffs(bal) - 1) : T;
+        __syncthreads();
+        int f = T;
+        for (int w = 0; w < T / 32; ++w) f = min(f, fail[w]);
+        const int nvalid = min(f < T ? f + 1 : T, L - i0);
+        if (tid == nvalid - 1) next_phase = nxt;
+        if (tid < nvalid) {
+            const int i = i0 + tid;
+            float q = 0.0f;                                                // ordered: coeffs[0] * x[i], coeffs[1] * x[i-1], ...
+#pragma unroll 1
+            for (int k = 0; k < kHilbertTaps; ++k) q = __fadd_rn(q, __fmul_rn(taps.c[k], i - k >= 0 ? x[i - k] : 0.0f));
+            const float re = i >= 63 ? x[i - 63] : 0.0f;                   // delay_samples_ = 63
+            float sn, cs;
+            sn = refmath::sinf_ref(cand);
+            cs = refmath::cosf_ref(cand);
+            y[i] = __fsub_rn(__fmul_rn(re, cs), __fmul_rn(q, sn));         // (analytic[i] * rotation).real()
+        }
+        __syncthreads();
+        ph = next_phase;
+        i0 += nvalid;
+    }
+}
+
 struct PskDevMem {
     void* p = nullptr;
     ~PskDevMem() { if (p) cudaFree(p); }
@@ -785,6 +847,83 @@ pu_status pu_mcdpsk_demod_soft_batch(pu_mcdpsk* h, const float* samples, size_t 
                          [&](const float* din, size_t nb, const float*, const float*, float* dout, float* daux) {
                              return mcdpsk_launch(h, din, nb, L, dout, llr_stride, residual_cfo_hz ? daux : nullptr, st);
                          });
+}
+
+// MultiCarrierDPSKDemodulator behind an externally detected chirp (MCDPSKWaveform::process, src/waveform/mc_dpsk_waveform.cpp:144-170:
+// setChirpDetected(cfo) -> process(training + ref + data) -> getSoftBits), i.e. processGotChirp (multi_carrier_dpsk.hpp:533-627).
+pu_status pu_mcdpsk_got_chirp_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, const float* chirp_cfo_hz, float* llr_out,
+                                    size_t llr_stride, int32_t* n_llr, float* cfo_after_hz, pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_mcdpsk_got_chirp_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && chirp_cfo_hz && llr_out && n_llr && cfo_after_hz, "pu_mcdpsk_got_chirp_batch: NULL data pointer");
+    PU_REQUIRE(llr_stride > 0 && L < (1u << 30), "pu_mcdpsk_got_chirp_batch: bad size");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    const size_t pre = static_cast<size_t>(h->cfg.training_symbols + 1) * h->cfg.samples_per_symbol;
+    pu::PskDevMem dx, dcfo, dy, dres, dl;
+    pu_status s;
+    const float* d_x = samples;
+    const float* d_cfo = chirp_cfo_hz;
+    float* d_llr = llr_out;
+    std::vector<float> zf(B * std::max<size_t>(llr_stride, 1), 0.0f);
+    if (space == PU_MEM_HOST) {
+        if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
+        if ((s = dcfo.upload(chirp_cfo_hz, B)) != PU_OK) return s;
+        if ((s = dl.upload(zf.data(), B * llr_stride)) != PU_OK) return s;
+        d_x = static_cast<const float*>(dx.p); d_cfo = static_cast<const float*>(dcfo.p); d_llr = static_cast<float*>(dl.p);
+    }
+    std::vector<float> res(B, 0.0f), cfo_h(B);
+    if (L > pre) {   // processGotChirp needs data behind the preamble; otherwise it keeps waiting (no soft bits)
+        if ((s = dy.upload(zf.data(), 0)) != PU_OK) return s;
+        PU_CUDA_TRY(cudaFree(dy.p)); dy.p = nullptr;
+        PU_CUDA_TRY(cudaMalloc(&dy.p, B * L * sizeof(float)));
+        if ((s = dres.upload(res.data(), B)) != PU_OK) return s;
+        pu::HilbertTaps taps;
+        const int M = (pu::kHilbertTaps - 1) / 2;
+        for (int n = 0; n < pu::kHilbertTaps; ++n) {                       // HilbertTransform ctor, src/dsp/filters.cpp:266-291
+            const int k = n - M;
+            float c = 0;
+            if (k != 0 && k % 2 != 0) c = static_cast<float>(2.0f / (3.14159265358979323846 * k));
+            const float w = static_cast<float>(2.0f * 3.14159265358979323846 * n / (pu::kHilbertTaps - 1));
+            c *= 0.42f - 0.5f * std::cos(w) + 0.08f * std::cos(2.0f * w);
+            taps.c[n] = c;
+        }
+        (void)cudaGetLastError();
+        pu::mcdpsk_cfo_correct_kernel<<<static_cast<unsigned>(B), pu::kCfoThreads, 0, st>>>(taps, d_x, L, static_cast<int>(L), h->cfg.sample_rate,
+                                                                                            d_cfo, static_cast<float*>(dy.p));
+        ctx->launches.fetch_add(1);
+        PU_CUDA_TRY(cudaGetLastError());
+        if ((s = mcdpsk_launch(h, static_cast<const float*>(dy.p), B, L, d_llr, llr_stride, static_cast<float*>(dres.p), st)) != PU_OK) return s;
+        PU_CUDA_TRY(cudaStreamSynchronize(st));
+        PU_CUDA_TRY(cudaMemcpy(res.data(), dres.p, B * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    PU_CUDA_TRY(cudaMemcpy(cfo_h.data(), d_cfo, B * sizeof(float), space == PU_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToHost));
+    // processTraining's cfo update and the false-positive rule (:572-607), per frame on the host: a handful of scalar operations
+    const int nc = static_cast<int>(h->cfg.num_carriers), bits = static_cast<int>(h->cfg.bits_per_symbol), sps = static_cast<int>(h->cfg.samples_per_symbol);
+    const size_t nsym = L > pre ? (L - pre) / sps : 0;
+    std::vector<int32_t> n_h(B);
+    std::vector<float> after_h(B);
+    for (size_t b = 0; b < B; ++b) {
+        float cfo = cfo_h[b];
+        if (L > pre && std::fabs(cfo) > 0.1f) cfo = 0.0f;                  // applyCFOCorrection resets cfo_hz_
+        const float dual = cfo;
+        float after = cfo;
+        if (L > pre && h->cfg.training_symbols >= 2) after = std::max(-50.0f, std::min(50.0f, cfo + res[b]));
+        if (std::fabs(dual) > 0.1f) after = cfo;
+        after_h[b] = L > pre ? after : cfo_h[b];
+        const bool rejected = std::fabs(dual) < 0.1f && std::fabs(after) > 5.0f;
+        n_h[b] = (L > pre && !rejected) ? static_cast<int32_t>(std::min(nsym * nc * bits, llr_stride)) : 0;
+    }
+    if (space == PU_MEM_HOST) {
+        if (L > pre) PU_CUDA_TRY(cudaMemcpy(llr_out, d_llr, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
+        std::memcpy(n_llr, n_h.data(), B * sizeof(int32_t));
+        std::memcpy(cfo_after_hz, after_h.data(), B * sizeof(float));
+    } else {
+        PU_CUDA_TRY(cudaMemcpy(n_llr, n_h.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice));
+        PU_CUDA_TRY(cudaMemcpy(cfo_after_hz, after_h.data(), B * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return PU_OK;
 }
 
 }  // extern "C"

@@ -233,6 +233,26 @@ def chirp_vectors():
     np.savez_compressed(os.path.join(HERE, "chirp_golden.npz"), **out)
 
 
+def mcdpsk_got_chirp_vectors():
+    """MC-DPSK behind an external chirp (SURVEY 8a row a16 with the Hilbert-FIR CFO correction): setChirpDetected(cfo) ->
+    process -> getSoftBits on two 8-carrier frames: cfo 0.15 Hz (corrected, accepted) and cfo 12 Hz (corrected, rejected)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from projectultra_b200 import capi
+    rng = np.random.default_rng(20261021)
+    out = {}
+    cfg = capi.mcdpsk_config(8, 2)
+    for i, (snr, cfo) in enumerate(((12.0, 0.15), (15.0, 12.0))):
+        tx = capi.mcdpsk_tx(cfg, capi.ldpc_encode(capi.R1_4, rng.integers(0, 256, 20, dtype=np.uint8)))
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        rx = (tx + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(tx))).astype(np.float32)
+        llr, ready, after = R.mcdpsk_got_chirp(8, rx, cfo)
+        out[f"m{i}_rx"] = rx
+        out[f"m{i}_llr"] = llr
+        out[f"m{i}_cfo"] = np.array([cfo, after], np.float32)
+        out[f"m{i}_ready"] = np.array([int(ready)], np.int64)
+    np.savez_compressed(os.path.join(HERE, "mcdpsk_chirp_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
     ldpc_vectors()
@@ -242,6 +262,7 @@ if __name__ == "__main__":
     acquire_vectors()
     dpsk_acquire_vectors()
     chirp_vectors()
+    mcdpsk_got_chirp_vectors()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

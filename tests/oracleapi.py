@@ -281,6 +281,19 @@ def dpsk_demod_soft(mod, sps, samples, data_start, ref_mode=0, est_cfo=0.0, phas
     return out[:n].copy()
 
 
+def mcdpsk_got_chirp(nc, samples, chirp_cfo, sps=512, bits=2, f_lo=500.0, f_hi=2500.0, fs=48000.0, training=8):
+    """processGotChirp behind an external chirp: (llr, cfo_after)."""
+    x = _f32(samples)
+    out = np.zeros(8192, np.float32)
+    cfo = C.c_float(0)
+    L = lib()
+    L.orc_mcdpsk_got_chirp.restype = C.c_long
+    n = L.orc_mcdpsk_got_chirp(nc, sps, bits, C.c_float(f_lo), C.c_float(f_hi), C.c_float(fs), training, _p(x, C.c_float),
+                               C.c_size_t(len(x)), C.c_float(chirp_cfo), _p(out, C.c_float), C.c_size_t(len(out)), C.byref(cfo))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), float(cfo.value)
+
+
 def dpsk_find_preamble(sps, samples, fc=1500.0, fs=48000.0):
     """DPSKDemodulator::findPreamble -> (data_start or -1, est_cfo, phase_offset)."""
     x = _f32(samples)

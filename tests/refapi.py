@@ -346,6 +346,19 @@ def ofdm_chirp_receive(cfg, samples, threshold=0.15):
     return out[:n].copy(), info, float(cfo.value)
 
 
+def mcdpsk_got_chirp(nc, samples, chirp_cfo, sps=512, bits=2, f_lo=500.0, f_hi=2500.0, fs=48000.0, training=8):
+    """setChirpDetected(cfo) -> process(training + ref + data) -> getSoftBits(): (llr, ready, cfo_after)."""
+    x = _f32(samples)
+    out = np.zeros(8192, np.float32)
+    ready, cfo = C.c_int(0), C.c_float(0)
+    L = lib()
+    L.ref_mcdpsk_got_chirp.restype = C.c_long
+    n = L.ref_mcdpsk_got_chirp(nc, sps, bits, C.c_float(f_lo), C.c_float(f_hi), C.c_float(fs), training, _p(x, C.c_float),
+                               C.c_size_t(len(x)), C.c_float(chirp_cfo), _p(out, C.c_float), C.c_size_t(len(out)), C.byref(ready), C.byref(cfo))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), bool(ready.value), float(cfo.value)
+
+
 def time_presynced_decode(cfg, samples, rate):
     x = _f32(samples)
     B, L = x.shape

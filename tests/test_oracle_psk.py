@@ -120,3 +120,35 @@ def test_dpsk_acquisition_matches_reference(mod):
         assert len(rl) == len(ol) and (_words(rl) == _words(ol)).all(), (snr, lead)
         found += rds > 0
     assert found >= 3
+
+
+def test_golden_mcdpsk_got_chirp(golden):
+    """SURVEY §8a row a16 (second half): the oracle's processGotChirp restatement -- Hilbert-FIR CFO correction, processTraining,
+    5 Hz false-positive rule, setReference, demodulateSoft -- against vectors produced by the unmodified reference."""
+    g = golden["mcdpsk_chirp"]
+    for i in range(2):
+        cfo, after = (float(v) for v in g[f"m{i}_cfo"])
+        llr, oafter = O.mcdpsk_got_chirp(8, g[f"m{i}_rx"], cfo)
+        want = g[f"m{i}_llr"]
+        assert len(llr) == len(want) and (_words(llr) == _words(want)).all(), i
+        assert (_words(np.float32(oafter)) == _words(np.float32(after))).all()
+        assert bool(g[f"m{i}_ready"][0]) == (len(want) > 0)
+
+
+@pytest.mark.parametrize("nc", [5, 8, 13, 20])
+def test_mcdpsk_got_chirp_matches_reference(nc):
+    if not R.available():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    from projectultra_b200 import capi
+    cfg = capi.mcdpsk_config(nc, 2)
+    rng = np.random.default_rng(500 + nc)
+    accepted = 0
+    for snr, cfo in ((18.0, 0.0), (9.0, 0.1), (9.0, 0.12), (4.0, -1.7), (14.0, 9.0), (0.0, 0.3)):
+        tx = capi.mcdpsk_tx(cfg, capi.ldpc_encode(capi.R1_4, rng.integers(0, 256, 20, dtype=np.uint8)))
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        rx = (tx + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(tx))).astype(np.float32)
+        rl, rr, rc = R.mcdpsk_got_chirp(nc, rx, cfo)
+        ol, oc = O.mcdpsk_got_chirp(nc, rx, cfo)
+        assert len(rl) == len(ol) and (_words(rl) == _words(ol)).all() and (_words(np.float32(rc)) == _words(np.float32(oc))).all(), (snr, cfo)
+        accepted += len(ol) > 0
+    assert accepted >= 3

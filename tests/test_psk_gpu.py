@@ -132,3 +132,44 @@ def test_golden_frames(ctx, golden):
         dem = capi.McDpskDemodulator(ctx, capi.mcdpsk_config(nc, bits))
         llr, cfo = dem.demod_soft_batch(g[f"mc{nc}_rx"])
         assert same_bits(llr[0], g[f"mc{nc}_llr"]) and cfo[0] == g[f"mc{nc}_cfo"][0]
+
+
+@pytest.mark.parametrize("nc", [5, 8, 13, 20])
+def test_mcdpsk_got_chirp_with_hilbert_cfo_correction(nc):
+    """SURVEY §8a row a16, second half: MC-DPSK behind an externally detected chirp (MCDPSKWaveform::process = setChirpDetected
+    -> process -> getSoftBits, i.e. processGotChirp): frames whose chirp CFO exceeds 0.1 Hz are first frequency-shifted through
+    the 127-tap Hilbert FIR (real path delayed by 63 samples, Q16), then processTraining / the 5 Hz false-positive rule /
+    setReference / demodulateSoft.  Soft-bit count and CFO report identical to the oracle, LLR words bit-identical (the
+    corrected samples are, so everything behind them is); the compiled reference is checked on a subset."""
+    import torch
+    from projectultra_b200 import capi
+    ctx = capi.Context(0)
+    cfg = capi.mcdpsk_config(nc, 2)
+    dem = capi.McDpskDemodulator(ctx, cfg)
+    rng = np.random.default_rng(300 + nc)
+    cases = [(20.0, 0.0), (12.0, 0.05), (12.0, 0.1), (10.0, 0.15), (8.0, -0.4), (6.0, 2.5), (15.0, -7.0), (25.0, 33.0), (3.0, 0.2), (30.0, -0.11)]
+    frames = []
+    for snr, _ in cases:
+        tx = capi.mcdpsk_tx(cfg, capi.ldpc_encode(capi.R1_4, rng.integers(0, 256, 20, dtype=np.uint8)))
+        p = float(np.mean(tx.astype(np.float64) ** 2))
+        frames.append((tx + rng.normal(0.0, np.sqrt(p / 10 ** (snr / 10)), len(tx))).astype(np.float32))
+    x = np.stack(frames)
+    cfo = np.array([c for _, c in cases], np.float32)
+    llr, n, after = dem.got_chirp_batch(x, cfo, llr_stride=700)
+    accepted = 0
+    for b in range(len(x)):
+        ol, oafter = O.mcdpsk_got_chirp(nc, x[b], float(cfo[b]))
+        want = ol[:700]
+        assert int(n[b]) == len(want), (b, cases[b], n[b], len(ol))
+        assert np.float32(after[b]).view(np.uint32) == np.float32(oafter).view(np.uint32), (b, after[b], oafter)
+        if len(want):
+            accepted += 1
+            assert (llr[b, :len(want)].view(np.uint32) == want.view(np.uint32)).all(), (b, cases[b])
+        if R.available() and b in (0, 3, 5):
+            rl, rr, rc = R.mcdpsk_got_chirp(nc, x[b], float(cfo[b]))
+            assert len(rl[:700]) == len(want) and (rl[:700].view(np.uint32) == want.view(np.uint32)).all()
+    assert accepted >= 5
+    d = dem.got_chirp_batch(torch.from_numpy(x).cuda(), cfo, llr_stride=700)
+    torch.cuda.synchronize()
+    assert (d[1].cpu().numpy() == n).all() and (d[0].cpu().numpy().view(np.uint32) == llr.view(np.uint32)).all()
+    del ctx
