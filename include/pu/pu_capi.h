@@ -280,6 +280,17 @@ PU_API pu_status pu_mcdpsk_demod_soft_batch(pu_mcdpsk* h, const float* samples, 
 PU_API pu_status pu_mcdpsk_got_chirp_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, const float* chirp_cfo_hz,
                                            float* llr_out, size_t llr_stride, int32_t* n_llr, float* cfo_after_hz,
                                            pu_memspace space, void* stream);
+/* The IWaveform receive sequence of tools/test_iwaveform.cpp:127-160 on MC-DPSK frames [up chirp][gap][down chirp][gap][training]
+ * [reference][data], for B frames: MCDPSKWaveform::detectSync (src/waveform/mc_dpsk_waveform.cpp:100-142: ChirpSync::detectDualChirp,
+ * start_sample = up_chirp_start + 2 chirps + 2 gaps) -> setFrequencyOffset(cfo) (:71-76) -> process(span from start_sample)
+ * (:144-170, i.e. pu_mcdpsk_got_chirp_batch on the located span) -> getSoftBits.
+ *   sync_info[B][4]   = {detected, up_chirp_start, down_chirp_start, SyncResult::start_sample (training start) or -1}
+ *   sync_values[B][4] = {cfo_hz, up correlation, down correlation, 0}
+ *   n_llr[B] = soft bits handed out (0: no chirp, start beyond the buffer, too short, or rejected by the 5 Hz rule); entries of
+ *   llr_out[b] beyond n_llr[b] are unspecified; cfo_after_hz[B] = estimatedCFO(); threshold <= 0 selects the callers' 0.15. */
+PU_API pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, float threshold,
+                                               float* llr_out, size_t llr_stride, int32_t* n_llr, int32_t* sync_info,
+                                               float* sync_values, float* cfo_after_hz, pu_memspace space, void* stream);
 /* MultiCarrierDPSKModulator (:91-257), host: generateTrainingSequence + generateReferenceSymbol + modulate(data). */
 PU_API pu_status pu_mcdpsk_tx(const pu_mcdpsk_config* cfg, const uint8_t* data, size_t n_bytes, float* out, size_t out_cap,
                               size_t* out_len);

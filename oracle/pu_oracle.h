@@ -121,6 +121,8 @@ extern "C" {
 long orc_dpsk_find_preamble(int sps, float fc, float fs, const float* x, size_t L, float* est_cfo, float* phase_off);
 long orc_mcdpsk_got_chirp(int nc, int sps, int bits_per_symbol, float f_lo, float f_hi, float fs, int training_symbols, const float* x,
                           size_t L, float chirp_cfo, float* llr, size_t cap, float* cfo_after);
+long orc_mcdpsk_chirp_receive(int nc, int sps, int bits_per_symbol, float f_lo, float f_hi, float fs, int training_symbols, const float* x,
+                              size_t L, float threshold, int32_t* info, float* f, float* llr, size_t cap, float* cfo_after);
 long orc_dpsk_demod_soft(int mod, int sps, float fc, float fs, const float* x, size_t L, long data_start, int ref_mode,
                          float est_cfo, float phase_off, float* llr, size_t cap);
 long orc_mcdpsk_demod_soft(int nc, int sps, int bits_per_symbol, float f_lo, float f_hi, float fs, const float* x, size_t L,

@@ -444,3 +444,22 @@ long orc_mcdpsk_got_chirp(int nc, int sps, int bits_per_symbol, float f_lo, floa
     if (fabsf(dual_chirp_cfo) < 0.1f && fabsf(after) > 5.0f) return 0;          /* false positive: back to IDLE (:599-607) */
     return n;
 }
+
+/* The IWaveform receive sequence (tools/test_iwaveform.cpp:127-160) on an MC-DPSK frame: MCDPSKWaveform::detectSync
+ * (src/waveform/mc_dpsk_waveform.cpp:100-142: detectDualChirp, start_sample = up_chirp_start + 2 chirps + 2 gaps),
+ * setFrequencyOffset(cfo) (:71-76) and process (:144-170: setChirpDetected(cfo) -> process(span) -> getSoftBits).
+ * info[4] = {success, up_chirp_start, down_chirp_start, start_sample or -1}; f[3] = {cfo_hz, up corr, down corr}. */
+long orc_mcdpsk_chirp_receive(int nc, int sps, int bits_per_symbol, float f_lo, float f_hi, float fs, int training_symbols, const float* x,
+                              size_t L, float threshold, int32_t* info, float* f, float* llr, size_t cap, float* cfo_after) {
+    orc_chirp_detect_dual(fs, x, L, threshold, info, f);     /* MultiCarrierDPSKConfig::getChirpConfig (:78-88) == the OFDM_CHIRP chirp */
+    info[3] = -1;
+    if (cfo_after) *cfo_after = f[0];
+    if (!info[0]) return 0;
+    const size_t chirp_samples = (size_t)(fs * 500.0f / 1000.0f);
+    const size_t gap_samples = (size_t)(fs * 100.0f / 1000.0f);
+    const int start = (int)((size_t)info[1] + 2 * chirp_samples + 2 * gap_samples);
+    info[3] = start;
+    if ((size_t)start >= L) return 0;                        /* test_iwaveform.cpp:143: int compared as size_t */
+    return orc_mcdpsk_got_chirp(nc, sps, bits_per_symbol, f_lo, f_hi, fs, training_symbols, x + start, L - (size_t)start, f[0], llr, cap,
+                                cfo_after);
+}

@@ -166,4 +166,40 @@ long ref_mcdpsk_got_chirp(int nc, int sps, int bits, float f_lo, float f_hi, flo
     return static_cast<long>(soft.size());
 }
 
+// The IWaveform receive sequence (tools/test_iwaveform.cpp:127-160) on an MC-DPSK frame [chirp pair][training][ref][data], with the
+// glue of MCDPSKWaveform::detectSync / setFrequencyOffset / process (src/waveform/mc_dpsk_waveform.cpp:100-170) applied to the
+// reference's own ChirpSync and MultiCarrierDPSKDemodulator objects (the waveform class itself pulls the protocol layer in):
+//   detectDualChirp -> start_sample = up_chirp_start + 2 chirps + 2 gaps -> setChirpDetected(cfo) -> process(span) -> getSoftBits.
+// info = {success, up_chirp_start, down_chirp_start, start_sample or -1}, f = {cfo_hz, up correlation, down correlation}.
+long ref_mcdpsk_chirp_receive(int nc, int sps, int bits, float f_lo, float f_hi, float fs, int training, const float* x, size_t L,
+                              float threshold, int32_t* info, float* f, float* llr, size_t cap, float* cfo_after) {
+    Quiet q;
+    fflush(stdout);
+    int saved = dup(1), nul = open("/dev/null", O_WRONLY);   // detectDualChirp printf()s on stdout
+    if (nul >= 0) { dup2(nul, 1); close(nul); }
+    MultiCarrierDPSKConfig cfg = mc_cfg(nc, sps, bits, f_lo, f_hi, fs, training);
+    sync::ChirpSync cs(cfg.getChirpConfig());
+    auto r = cs.detectDualChirp(SampleSpan(x, L), threshold);
+    fflush(stdout);
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+    info[0] = r.success ? 1 : 0; info[1] = r.up_chirp_start; info[2] = r.down_chirp_start; info[3] = -1;
+    f[0] = r.cfo_hz; f[1] = r.up_correlation; f[2] = r.down_correlation;
+    if (cfo_after) *cfo_after = r.cfo_hz;
+    if (!r.success) return 0;
+    size_t chirp_samples = cs.getChirpSamples();
+    size_t gap_samples = static_cast<size_t>(cfg.sample_rate * cfg.getChirpConfig().gap_ms / 1000.0f);
+    int start_sample = r.up_chirp_start + 2 * chirp_samples + 2 * gap_samples;      // use_dual_chirp
+    info[3] = start_sample;
+    if (start_sample >= L) return 0;                                                 // test_iwaveform.cpp:143 (int vs size_t, as there)
+    MultiCarrierDPSKDemodulator d(cfg);
+    d.setCFO(r.cfo_hz);                                                              // MCDPSKWaveform::setFrequencyOffset
+    d.setChirpDetected(r.cfo_hz);
+    const bool ready = d.process(SampleSpan(x + start_sample, L - start_sample));
+    if (cfo_after) *cfo_after = d.getEstimatedCFO();
+    if (!ready) return 0;
+    std::vector<float> soft = d.getSoftBits();
+    for (size_t i = 0; i < soft.size() && i < cap; ++i) llr[i] = soft[i];
+    return static_cast<long>(soft.size());
+}
+
 }  // extern "C"

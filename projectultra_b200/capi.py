@@ -632,6 +632,21 @@ class McDpskDemodulator:
                                               C.c_size_t(llr_stride), _ptr(n), _ptr(after), sp, _stream(sp)))
         return llr, n, after
 
+    def chirp_receive_batch(self, samples, threshold=0.15, llr_stride=648):
+        """pu_mcdpsk_chirp_receive_batch: dual-chirp detectSync + setFrequencyOffset + process + getSoftBits for every row of samples
+        [B, L] -> (llr [B, llr_stride], n_llr [B], sync_info [B, 4], sync_values [B, 4], cfo_after_hz [B])."""
+        x = _frames(samples)
+        B, L = x.shape
+        llr = _like(x, (B, llr_stride), np.float32, "float32")
+        n = _like(x, (B,), np.int32, "int32")
+        info = _like(x, (B, 4), np.int32, "int32")
+        val = _like(x, (B, 4), np.float32, "float32")
+        after = _like(x, (B,), np.float32, "float32")
+        sp = _space(x, llr, n, info, val, after)
+        check(lib().pu_mcdpsk_chirp_receive_batch(self._h, _ptr(x), C.c_size_t(B), C.c_size_t(L), C.c_float(threshold), _ptr(llr),
+                                                  C.c_size_t(llr_stride), _ptr(n), _ptr(info), _ptr(val), _ptr(after), sp, _stream(sp)))
+        return llr, n, info, val, after
+
     def demod_soft_batch(self, samples, llr_stride=None, llr=None, want_cfo=True):
         x = _frames(samples)
         B, L = x.shape

@@ -8,17 +8,12 @@
 // thread); what runs in parallel are the search positions, which the reference evaluates independently.  The first-maximum
 // rule of the reference's ascending scans is kept by the reductions (larger value wins, equal value -> smaller position).
 #include <cfloat>
+#include <cmath>
+#include <vector>
 
 #include "pu_internal.h"
 
 namespace pu {
-
-struct ChirpDev {
-    int n, gap;                        // chirp samples (24 000), gap samples (4 800)
-    float fs, cfo_to_samples;          // sample rate; sample_rate / chirp_rate
-    const float* up_s; const float* up_c; const float* dn_s; const float* dn_c;   // templates (generateTemplate, :706-735)
-    float up_e, dn_e;                  // template energies
-};
 
 constexpr int kChirpThreads = 256;
 struct ChirpShared {
@@ -249,6 +244,34 @@ cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t 
                                                                            frame_start, frame_nsym, cfo_out, phase_out, n_llr,
                                                                            llr_per_symbol, llr_stride);
     return cudaGetLastError();
+}
+
+void chirp_templates_host(float fs, std::vector<float>& t, ChirpDev& c) {
+    const float f_start = 300.0f, f_end = 2700.0f, duration_ms = 500.0f, gap_ms = 100.0f;
+    const size_t n = static_cast<size_t>(fs * duration_ms / 1000.0f);
+    const float T = duration_ms / 1000.0f, k = (f_end - f_start) / T;
+    t.assign(4 * n, 0.0f);
+    float ue = 0.0f, de = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        const float tt = static_cast<float>(i) / fs;
+        const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (f_start * tt + 0.5f * k * tt * tt));
+        t[i] = std::sin(phase);
+        t[n + i] = std::cos(phase);
+        ue += t[i] * t[i];
+    }
+    for (size_t i = 0; i < n; ++i) {
+        const float tt = static_cast<float>(i) / fs;
+        const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (f_end * tt - 0.5f * k * tt * tt));
+        t[2 * n + i] = std::sin(phase);
+        t[3 * n + i] = std::cos(phase);
+        de += t[2 * n + i] * t[2 * n + i];
+    }
+    c.n = static_cast<int>(n);
+    c.gap = static_cast<int>(static_cast<size_t>(fs * gap_ms / 1000.0f));
+    c.fs = fs;
+    c.cfo_to_samples = fs / ((f_end - f_start) / T);
+    c.up_e = ue; c.dn_e = de;
+    c.up_s = c.up_c = c.dn_s = c.dn_c = nullptr;
 }
 
 }  // namespace pu

@@ -845,17 +845,6 @@ struct AcqDev {
 cudaError_t ofdm_acquire_launch(const AcqDev& a, const float* samples, size_t B, size_t frame_stride, int L, int chunk, int4* out_int,
                                 float* out_cfo, cudaStream_t st);
 
-// chirp_sync.cu
-struct ChirpDev {
-    int n, gap;
-    float fs, cfo_to_samples;
-    const float* up_s; const float* up_c; const float* dn_s; const float* dn_c;
-    float up_e, dn_e;
-};
-cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t B, size_t frame_stride, int L, float threshold, int sym_len,
-                                int4* out_info, float4* out_f, int* frame_start, int* frame_nsym, float* cfo_out, float* phase_out,
-                                int* n_llr, int llr_per_symbol, int llr_stride, cudaStream_t st);
-
 // ofdm_tx_gpu.cu
 struct TxDev {
     int nfft, cp, sym_len, guard, n_data, n_pilot, bps, differential;
@@ -922,34 +911,11 @@ struct pu_ofdm {
     // (src/waveform/ofdm_chirp_waveform.cpp:39-49): 300 -> 2700 Hz in 500 ms, 100 ms gaps
     pu_status ensure_chirp() {
         if (chirp_ready) return PU_OK;
-        const float fs = static_cast<float>(plan.cfg.sample_rate), f_start = 300.0f, f_end = 2700.0f, duration_ms = 500.0f, gap_ms = 100.0f;
-        const size_t n = static_cast<size_t>(fs * duration_ms / 1000.0f);
-        const float T = duration_ms / 1000.0f, k = (f_end - f_start) / T;
-        std::vector<float> t(4 * n);
-        float ue = 0.0f, de = 0.0f;
-        for (size_t i = 0; i < n; ++i) {
-            const float tt = static_cast<float>(i) / fs;
-            const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (f_start * tt + 0.5f * k * tt * tt));
-            t[i] = std::sin(phase);
-            t[n + i] = std::cos(phase);
-            ue += t[i] * t[i];
-        }
-        for (size_t i = 0; i < n; ++i) {
-            const float tt = static_cast<float>(i) / fs;
-            const float phase = static_cast<float>(2.0f * 3.14159265358979323846 * (f_end * tt - 0.5f * k * tt * tt));
-            t[2 * n + i] = std::sin(phase);
-            t[3 * n + i] = std::cos(phase);
-            de += t[2 * n + i] * t[2 * n + i];
-        }
+        std::vector<float> t;
+        pu::chirp_templates_host(static_cast<float>(plan.cfg.sample_rate), t, chirp);
         pu_status st = d_chirp.upload(t.data(), t.size());
         if (st != PU_OK) return st;
-        const float* b = static_cast<const float*>(d_chirp.p);
-        chirp.n = static_cast<int>(n);
-        chirp.gap = static_cast<int>(static_cast<size_t>(fs * gap_ms / 1000.0f));
-        chirp.fs = fs;
-        chirp.cfo_to_samples = fs / ((f_end - f_start) / T);
-        chirp.up_s = b; chirp.up_c = b + n; chirp.dn_s = b + 2 * n; chirp.dn_c = b + 3 * n;
-        chirp.up_e = ue; chirp.dn_e = de;
+        pu::chirp_dev_bind(chirp, static_cast<const float*>(d_chirp.p));
         chirp_ready = true;
         return PU_OK;
     }

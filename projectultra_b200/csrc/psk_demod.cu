@@ -469,12 +469,19 @@ struct HilbertTaps { float c[kHilbertTaps]; };
 
 __global__ void __launch_bounds__(kCfoThreads) mcdpsk_cfo_correct_kernel(HilbertTaps taps, const float* __restrict__ in, size_t stride, int L,
                                                                           float fs, const float* __restrict__ cfo_hz,
-                                                                          float* __restrict__ out) {
+                                                                          float* __restrict__ out, const int* __restrict__ frame_start) {
     __shared__ int fail[kCfoThreads / 32];
     __shared__ float next_phase;
     const int tid = threadIdx.x, T = blockDim.x;
-    const float* x = in + static_cast<size_t>(blockIdx.x) * stride;
+    // optional per-frame window (frames located by the chirp): the span [start, row end) is moved to the front of the output row
+    // and the rest of the row is cleared; start < 0 or beyond the row = no frame
+    const int Lrow = L;
+    int start = frame_start ? frame_start[blockIdx.x] : 0;
+    if (start < 0 || start > Lrow) start = Lrow;
+    const float* x = in + static_cast<size_t>(blockIdx.x) * stride + start;
     float* y = out + static_cast<size_t>(blockIdx.x) * stride;
+    L = Lrow - start;
+    for (int i = L + tid; i < Lrow; i += T) y[i] = 0.0f;
     const float cfo = cfo_hz[blockIdx.x];
     if (!(fabsf(cfo) > 0.1f) || fabsf(cfo) < 0.01f || L < 128) {         // processGotChirp :565, applyCFOCorrection :634
         for (int i = tid; i < L; i += T) y[i] = x[i];
@@ -549,6 +556,9 @@ struct pu_mcdpsk {
     pu_mcdpsk_config cfg{};
     pu::PskDevMem d_mixer, d_expected;
     pu::Buffer corr;
+    pu::PskDevMem d_chirp;     // dual-chirp templates (built on first use)
+    pu::ChirpDev chirp{};
+    bool chirp_ready = false;
 };
 
 // Shared host-staging helper: samples (+ up to two per-frame float arrays) up, `out_floats` per frame (+ one per-frame
@@ -851,32 +861,21 @@ pu_status pu_mcdpsk_demod_soft_batch(pu_mcdpsk* h, const float* samples, size_t 
 
 // MultiCarrierDPSKDemodulator behind an externally detected chirp (MCDPSKWaveform::process, src/waveform/mc_dpsk_waveform.cpp:144-170:
 // setChirpDetected(cfo) -> process(training + ref + data) -> getSoftBits), i.e. processGotChirp (multi_carrier_dpsk.hpp:533-627).
-pu_status pu_mcdpsk_got_chirp_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, const float* chirp_cfo_hz, float* llr_out,
-                                    size_t llr_stride, int32_t* n_llr, float* cfo_after_hz, pu_memspace space, void* stream) {
-    PU_REQUIRE(h, "pu_mcdpsk_got_chirp_batch: NULL handle");
-    if (B == 0) return PU_OK;
-    PU_REQUIRE(samples && chirp_cfo_hz && llr_out && n_llr && cfo_after_hz, "pu_mcdpsk_got_chirp_batch: NULL data pointer");
-    PU_REQUIRE(llr_stride > 0 && L < (1u << 30), "pu_mcdpsk_got_chirp_batch: bad size");
+static pu_status mcdpsk_got_chirp(pu_mcdpsk* h, const float* d_x, size_t B, size_t L, const float* d_cfo, const int* d_start,
+                                  const std::vector<int>* h_start, float* d_llr, size_t llr_stride, std::vector<int32_t>& n_h,
+                                  std::vector<float>& after_h, cudaStream_t st) {
     pu_ctx* ctx = h->ctx;
-    PU_CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = pu::pick_stream(ctx, stream, space);
     const size_t pre = static_cast<size_t>(h->cfg.training_symbols + 1) * h->cfg.samples_per_symbol;
-    pu::PskDevMem dx, dcfo, dy, dres, dl;
+    pu::PskDevMem dy, dres;
     pu_status s;
-    const float* d_x = samples;
-    const float* d_cfo = chirp_cfo_hz;
-    float* d_llr = llr_out;
-    std::vector<float> zf(B * std::max<size_t>(llr_stride, 1), 0.0f);
-    if (space == PU_MEM_HOST) {
-        if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
-        if ((s = dcfo.upload(chirp_cfo_hz, B)) != PU_OK) return s;
-        if ((s = dl.upload(zf.data(), B * llr_stride)) != PU_OK) return s;
-        d_x = static_cast<const float*>(dx.p); d_cfo = static_cast<const float*>(dcfo.p); d_llr = static_cast<float*>(dl.p);
-    }
     std::vector<float> res(B, 0.0f), cfo_h(B);
-    if (L > pre) {   // processGotChirp needs data behind the preamble; otherwise it keeps waiting (no soft bits)
-        if ((s = dy.upload(zf.data(), 0)) != PU_OK) return s;
-        PU_CUDA_TRY(cudaFree(dy.p)); dy.p = nullptr;
+    size_t Lmax = 0;                                     // longest per-frame span
+    std::vector<size_t> Lb(B, L);
+    for (size_t b = 0; b < B; ++b) {
+        if (h_start) { const int st0 = (*h_start)[b]; Lb[b] = (st0 >= 0 && static_cast<size_t>(st0) <= L) ? L - static_cast<size_t>(st0) : 0; }
+        Lmax = std::max(Lmax, Lb[b]);
+    }
+    if (Lmax > pre) {   // processGotChirp needs data behind the preamble; otherwise it keeps waiting (no soft bits)
         PU_CUDA_TRY(cudaMalloc(&dy.p, B * L * sizeof(float)));
         if ((s = dres.upload(res.data(), B)) != PU_OK) return s;
         pu::HilbertTaps taps;
@@ -891,37 +890,138 @@ pu_status pu_mcdpsk_got_chirp_batch(pu_mcdpsk* h, const float* samples, size_t B
         }
         (void)cudaGetLastError();
         pu::mcdpsk_cfo_correct_kernel<<<static_cast<unsigned>(B), pu::kCfoThreads, 0, st>>>(taps, d_x, L, static_cast<int>(L), h->cfg.sample_rate,
-                                                                                            d_cfo, static_cast<float*>(dy.p));
+                                                                                            d_cfo, static_cast<float*>(dy.p), d_start);
         ctx->launches.fetch_add(1);
         PU_CUDA_TRY(cudaGetLastError());
         if ((s = mcdpsk_launch(h, static_cast<const float*>(dy.p), B, L, d_llr, llr_stride, static_cast<float*>(dres.p), st)) != PU_OK) return s;
         PU_CUDA_TRY(cudaStreamSynchronize(st));
         PU_CUDA_TRY(cudaMemcpy(res.data(), dres.p, B * sizeof(float), cudaMemcpyDeviceToHost));
     }
-    PU_CUDA_TRY(cudaMemcpy(cfo_h.data(), d_cfo, B * sizeof(float), space == PU_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToHost));
+    PU_CUDA_TRY(cudaMemcpy(cfo_h.data(), d_cfo, B * sizeof(float), cudaMemcpyDeviceToHost));
     // processTraining's cfo update and the false-positive rule (:572-607), per frame on the host: a handful of scalar operations
     const int nc = static_cast<int>(h->cfg.num_carriers), bits = static_cast<int>(h->cfg.bits_per_symbol), sps = static_cast<int>(h->cfg.samples_per_symbol);
-    const size_t nsym = L > pre ? (L - pre) / sps : 0;
-    std::vector<int32_t> n_h(B);
-    std::vector<float> after_h(B);
+    n_h.assign(B, 0);
+    after_h.assign(B, 0.0f);
     for (size_t b = 0; b < B; ++b) {
+        const bool live = Lb[b] > pre;
         float cfo = cfo_h[b];
-        if (L > pre && std::fabs(cfo) > 0.1f) cfo = 0.0f;                  // applyCFOCorrection resets cfo_hz_
+        if (live && std::fabs(cfo) > 0.1f) cfo = 0.0f;                     // applyCFOCorrection resets cfo_hz_
         const float dual = cfo;
         float after = cfo;
-        if (L > pre && h->cfg.training_symbols >= 2) after = std::max(-50.0f, std::min(50.0f, cfo + res[b]));
+        if (live && h->cfg.training_symbols >= 2) after = std::max(-50.0f, std::min(50.0f, cfo + res[b]));
         if (std::fabs(dual) > 0.1f) after = cfo;
-        after_h[b] = L > pre ? after : cfo_h[b];
+        after_h[b] = live ? after : cfo_h[b];
         const bool rejected = std::fabs(dual) < 0.1f && std::fabs(after) > 5.0f;
-        n_h[b] = (L > pre && !rejected) ? static_cast<int32_t>(std::min(nsym * nc * bits, llr_stride)) : 0;
+        const size_t nsym = live ? (Lb[b] - pre) / sps : 0;
+        n_h[b] = (live && !rejected) ? static_cast<int32_t>(std::min(nsym * nc * bits, llr_stride)) : 0;
     }
+    return PU_OK;
+}
+
+pu_status pu_mcdpsk_got_chirp_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, const float* chirp_cfo_hz, float* llr_out,
+                                    size_t llr_stride, int32_t* n_llr, float* cfo_after_hz, pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_mcdpsk_got_chirp_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && chirp_cfo_hz && llr_out && n_llr && cfo_after_hz, "pu_mcdpsk_got_chirp_batch: NULL data pointer");
+    PU_REQUIRE(llr_stride > 0 && L < (1u << 30), "pu_mcdpsk_got_chirp_batch: bad size");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    pu::PskDevMem dx, dcfo, dl;
+    pu_status s;
+    const float* d_x = samples;
+    const float* d_cfo = chirp_cfo_hz;
+    float* d_llr = llr_out;
     if (space == PU_MEM_HOST) {
-        if (L > pre) PU_CUDA_TRY(cudaMemcpy(llr_out, d_llr, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<float> zf(B * llr_stride, 0.0f);
+        if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
+        if ((s = dcfo.upload(chirp_cfo_hz, B)) != PU_OK) return s;
+        if ((s = dl.upload(zf.data(), zf.size())) != PU_OK) return s;
+        d_x = static_cast<const float*>(dx.p); d_cfo = static_cast<const float*>(dcfo.p); d_llr = static_cast<float*>(dl.p);
+    }
+    std::vector<int32_t> n_h;
+    std::vector<float> after_h;
+    if ((s = mcdpsk_got_chirp(h, d_x, B, L, d_cfo, nullptr, nullptr, d_llr, llr_stride, n_h, after_h, st)) != PU_OK) return s;
+    if (space == PU_MEM_HOST) {
+        PU_CUDA_TRY(cudaMemcpy(llr_out, d_llr, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
         std::memcpy(n_llr, n_h.data(), B * sizeof(int32_t));
         std::memcpy(cfo_after_hz, after_h.data(), B * sizeof(float));
     } else {
         PU_CUDA_TRY(cudaMemcpy(n_llr, n_h.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice));
         PU_CUDA_TRY(cudaMemcpy(cfo_after_hz, after_h.data(), B * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return PU_OK;
+}
+
+// The IWaveform receive sequence (tools/test_iwaveform.cpp:127-160) on MC-DPSK frames [chirp pair][training][ref][data]:
+// MCDPSKWaveform::detectSync (src/waveform/mc_dpsk_waveform.cpp:100-142) -> setFrequencyOffset(cfo) (:71-76) -> process (:144-170).
+pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, float threshold, float* llr_out,
+                                        size_t llr_stride, int32_t* n_llr, int32_t* sync_info, float* sync_values, float* cfo_after_hz,
+                                        pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_mcdpsk_chirp_receive_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && llr_out && n_llr && sync_info && sync_values && cfo_after_hz, "pu_mcdpsk_chirp_receive_batch: NULL data pointer");
+    PU_REQUIRE(llr_stride > 0 && L < (1u << 30), "pu_mcdpsk_chirp_receive_batch: bad size");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    pu_status s;
+    if (!h->chirp_ready) {
+        std::vector<float> t;
+        pu::chirp_templates_host(h->cfg.sample_rate, t, h->chirp);
+        if ((s = h->d_chirp.upload(t.data(), t.size())) != PU_OK) return s;
+        pu::chirp_dev_bind(h->chirp, static_cast<const float*>(h->d_chirp.p));
+        h->chirp_ready = true;
+    }
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    if (threshold <= 0.0f) threshold = 0.15f;        // the callers' value, tools/test_iwaveform.cpp:133
+    pu::PskDevMem dx, dl, dinfo, dval, dcfo, dstart;
+    const float* d_x = samples;
+    float* d_llr = llr_out;
+    std::vector<int32_t> info_h(B * 4, 0);
+    std::vector<float> val_h(B * 4, 0.0f);
+    if (space == PU_MEM_HOST) {
+        std::vector<float> zf(B * llr_stride, 0.0f);
+        if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
+        if ((s = dl.upload(zf.data(), zf.size())) != PU_OK) return s;
+        d_x = static_cast<const float*>(dx.p); d_llr = static_cast<float*>(dl.p);
+    }
+    if ((s = dinfo.upload(info_h.data(), info_h.size())) != PU_OK) return s;
+    if ((s = dval.upload(val_h.data(), val_h.size())) != PU_OK) return s;
+    if ((s = dcfo.upload(val_h.data(), B)) != PU_OK) return s;
+    (void)cudaGetLastError();
+    PU_CUDA_TRY(pu::chirp_detect_launch(h->chirp, d_x, B, L, static_cast<int>(L), threshold, static_cast<int>(h->cfg.samples_per_symbol),
+                                        static_cast<int4*>(dinfo.p), static_cast<float4*>(dval.p), nullptr, nullptr, static_cast<float*>(dcfo.p),
+                                        nullptr, nullptr, 0, 0, st));
+    ctx->launches.fetch_add(1);
+    PU_CUDA_TRY(cudaStreamSynchronize(st));
+    PU_CUDA_TRY(cudaMemcpy(info_h.data(), dinfo.p, info_h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    PU_CUDA_TRY(cudaMemcpy(val_h.data(), dval.p, val_h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    // MCDPSKWaveform::detectSync (:117-134): the training sequence starts two chirps and two gaps behind the up chirp (the kernel's own
+    // start_sample is the OFDM_CHIRP rule); tools/test_iwaveform.cpp:143 drops frames whose start lies at or beyond the end
+    std::vector<int> start_h(B, -1);
+    for (size_t b = 0; b < B; ++b) {
+        int start = -1;
+        if (info_h[4 * b]) start = static_cast<int>(static_cast<size_t>(info_h[4 * b + 1]) + 2 * static_cast<size_t>(h->chirp.n) + 2 * static_cast<size_t>(h->chirp.gap));
+        info_h[4 * b + 3] = start;
+        val_h[4 * b + 3] = 0.0f;                       // no rotator phase on this path (the CFO is removed by the Hilbert-FIR shift)
+        start_h[b] = (start >= 0 && static_cast<size_t>(start) < L) ? start : -1;
+    }
+    if ((s = dstart.upload(start_h.data(), B)) != PU_OK) return s;
+    std::vector<int32_t> n_h;
+    std::vector<float> after_h;
+    if ((s = mcdpsk_got_chirp(h, d_x, B, L, static_cast<const float*>(dcfo.p), static_cast<const int*>(dstart.p), &start_h, d_llr, llr_stride,
+                              n_h, after_h, st)) != PU_OK) return s;
+    if (space == PU_MEM_HOST) {
+        PU_CUDA_TRY(cudaMemcpy(llr_out, d_llr, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
+        std::memcpy(n_llr, n_h.data(), B * sizeof(int32_t));
+        std::memcpy(cfo_after_hz, after_h.data(), B * sizeof(float));
+        std::memcpy(sync_info, info_h.data(), info_h.size() * sizeof(int32_t));
+        std::memcpy(sync_values, val_h.data(), val_h.size() * sizeof(float));
+    } else {
+        PU_CUDA_TRY(cudaMemcpy(n_llr, n_h.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice));
+        PU_CUDA_TRY(cudaMemcpy(cfo_after_hz, after_h.data(), B * sizeof(float), cudaMemcpyHostToDevice));
+        PU_CUDA_TRY(cudaMemcpy(sync_info, info_h.data(), info_h.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        PU_CUDA_TRY(cudaMemcpy(sync_values, val_h.data(), val_h.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     return PU_OK;
 }

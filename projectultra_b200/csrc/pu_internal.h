@@ -74,3 +74,23 @@ inline cudaStream_t pick_stream(pu_ctx* ctx, void* stream, pu_memspace space = P
     return ctx->stream;
 }
 }  // namespace pu
+
+// chirp_sync.cu: dual-chirp synchronisation shared by the OFDM_CHIRP and MC-DPSK receive entry points
+namespace pu {
+struct ChirpDev {
+    int n, gap;                        // chirp samples (24 000), gap samples (4 800)
+    float fs, cfo_to_samples;          // sample rate; sample_rate / chirp_rate
+    const float* up_s; const float* up_c; const float* dn_s; const float* dn_c;   // templates (generateTemplate, chirp_sync.hpp:706-735)
+    float up_e, dn_e;                  // template energies
+};
+// templates of the 300 -> 2700 Hz, 500 ms chirp pair with 100 ms gaps (OFDMChirpWaveform::getChirpConfig, ofdm_chirp_waveform.cpp:39-49 ==
+// MultiCarrierDPSKConfig::getChirpConfig, multi_carrier_dpsk.hpp:78-88): host table of 4 n floats {up sin, up cos, down sin, down cos};
+// the caller uploads it and chirp_dev_bind points the descriptor at the device copy
+void chirp_templates_host(float fs, std::vector<float>& table, ChirpDev& c);
+inline void chirp_dev_bind(ChirpDev& c, const float* dev_table) {
+    c.up_s = dev_table; c.up_c = dev_table + c.n; c.dn_s = dev_table + 2 * static_cast<size_t>(c.n); c.dn_c = dev_table + 3 * static_cast<size_t>(c.n);
+}
+cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t B, size_t frame_stride, int L, float threshold, int sym_len,
+                                int4* out_info, float4* out_f, int* frame_start, int* frame_nsym, float* cfo_out, float* phase_out,
+                                int* n_llr, int llr_per_symbol, int llr_stride, cudaStream_t st);
+}  // namespace pu

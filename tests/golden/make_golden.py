@@ -250,6 +250,18 @@ def mcdpsk_got_chirp_vectors():
         out[f"m{i}_llr"] = llr
         out[f"m{i}_cfo"] = np.array([cfo, after], np.float32)
         out[f"m{i}_ready"] = np.array([int(ready)], np.int64)
+    # the whole IWaveform sequence behind the dual chirp (MCDPSKWaveform detectSync -> setFrequencyOffset -> process): 10 dB with
+    # +6.5 Hz CFO behind 800 samples of noise, and 4 dB without CFO
+    sys.path.insert(0, os.path.dirname(HERE))
+    from mcframes import mcdpsk_chirp_frame
+    for i, (snr, lead, cfo) in enumerate(((10.0, 800, 6.5), (4.0, 0, 0.0))):
+        rx = mcdpsk_chirp_frame(cfg, rng, snr, lead, cfo)
+        llr, info, f, after = R.mcdpsk_chirp_receive(8, rx)
+        out[f"r{i}_rx"] = rx
+        out[f"r{i}_llr"] = llr
+        out[f"r{i}_info"] = info.astype(np.int64)
+        out[f"r{i}_f"] = f
+        out[f"r{i}_after"] = np.array([after], np.float32)
     np.savez_compressed(os.path.join(HERE, "mcdpsk_chirp_golden.npz"), **out)
 
 

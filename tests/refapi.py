@@ -359,6 +359,22 @@ def mcdpsk_got_chirp(nc, samples, chirp_cfo, sps=512, bits=2, f_lo=500.0, f_hi=2
     return out[:n].copy(), bool(ready.value), float(cfo.value)
 
 
+def mcdpsk_chirp_receive(nc, samples, threshold=0.15, sps=512, bits=2, f_lo=500.0, f_hi=2500.0, fs=48000.0, training=8):
+    """MCDPSKWaveform detectSync -> setFrequencyOffset -> process -> getSoftBits: (llr, info[4], f[3] = {cfo, up corr, down corr}, cfo_after)."""
+    x = _f32(samples)
+    out = np.zeros(8192, np.float32)
+    info = np.zeros(4, np.int32)
+    f = np.zeros(3, np.float32)
+    after = C.c_float(0)
+    L = lib()
+    L.ref_mcdpsk_chirp_receive.restype = C.c_long
+    n = L.ref_mcdpsk_chirp_receive(nc, sps, bits, C.c_float(f_lo), C.c_float(f_hi), C.c_float(fs), training, _p(x, C.c_float),
+                                   C.c_size_t(len(x)), C.c_float(threshold), _p(info, C.c_int32), _p(f, C.c_float), _p(out, C.c_float),
+                                   C.c_size_t(len(out)), C.byref(after))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), info, f, float(after.value)
+
+
 def time_presynced_decode(cfg, samples, rate):
     x = _f32(samples)
     B, L = x.shape

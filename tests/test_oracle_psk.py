@@ -152,3 +152,35 @@ def test_mcdpsk_got_chirp_matches_reference(nc):
         assert len(rl) == len(ol) and (_words(rl) == _words(ol)).all() and (_words(np.float32(rc)) == _words(np.float32(oc))).all(), (snr, cfo)
         accepted += len(ol) > 0
     assert accepted >= 3
+
+
+def test_golden_mcdpsk_chirp_receive(golden):
+    """SURVEY §8f next-2 on MC-DPSK: the oracle's MCDPSKWaveform receive sequence (detectDualChirp -> training start two chirps and
+    two gaps behind the up chirp -> setChirpDetected(cfo) -> process -> getSoftBits) against vectors from the unmodified reference."""
+    g = golden["mcdpsk_chirp"]
+    for i in range(2):
+        llr, info, f, after = O.mcdpsk_chirp_receive(8, g[f"r{i}_rx"])
+        want = g[f"r{i}_llr"]
+        assert (info == g[f"r{i}_info"]).all(), i
+        assert (_words(f) == _words(g[f"r{i}_f"])).all() and (_words(np.float32(after)) == _words(g[f"r{i}_after"][0])).all(), i
+        assert len(llr) == len(want) and (_words(llr) == _words(want)).all(), i
+
+
+@pytest.mark.parametrize("nc", [5, 8, 20])
+def test_mcdpsk_chirp_receive_matches_reference(nc):
+    if not R.available():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    from projectultra_b200 import capi
+    from mcframes import mcdpsk_chirp_frame
+    cfg = capi.mcdpsk_config(nc, 2)
+    rng = np.random.default_rng(700 + nc)
+    got = 0
+    for snr, lead, cfo, total in ((14.0, 500, 0.0, None), (6.0, 0, 7.3, None), (10.0, 1234, -22.0, None), (-14.0, 100, 0.0, None),
+                                  (12.0, 300, 3.0, 60000), (12.0, 0, 0.0, 57600 + 9 * 512)):
+        rx = mcdpsk_chirp_frame(cfg, rng, snr, lead, cfo, total)
+        rl, ri, rf, ra = R.mcdpsk_chirp_receive(nc, rx)
+        ol, oi, of, oa = O.mcdpsk_chirp_receive(nc, rx)
+        assert (ri == oi).all() and (_words(rf) == _words(of)).all() and (_words(np.float32(ra)) == _words(np.float32(oa))).all(), (snr, lead, cfo)
+        assert len(rl) == len(ol) and (_words(rl) == _words(ol)).all(), (snr, lead, cfo)
+        got += len(ol) > 0
+    assert got >= 2      # the 5 Hz false-positive rule rejects some of the CFO-free frames at 20 carriers

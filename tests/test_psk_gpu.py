@@ -173,3 +173,63 @@ def test_mcdpsk_got_chirp_with_hilbert_cfo_correction(nc):
     torch.cuda.synchronize()
     assert (d[1].cpu().numpy() == n).all() and (d[0].cpu().numpy().view(np.uint32) == llr.view(np.uint32)).all()
     del ctx
+
+
+@pytest.mark.parametrize("nc", [5, 8, 20])
+def test_mcdpsk_chirp_receive_matches_oracle(nc):
+    """SURVEY §8f next-2 on MC-DPSK: the whole IWaveform receive sequence of tools/test_iwaveform.cpp:127-160 behind the dual chirp
+    (MCDPSKWaveform detectSync -> setFrequencyOffset -> process -> getSoftBits) for a ragged batch: detection flags, chirp positions,
+    training start, CFO and correlation words, soft-bit count, CFO report and LLR words identical to the oracle (and to the compiled
+    reference on a subset); covers CFO-shifted frames (Hilbert-FIR correction of the located span), a missed chirp, a frame cut
+    inside its data and one cut right behind the preamble."""
+    import torch
+    from projectultra_b200 import capi
+    from mcframes import mcdpsk_chirp_frame
+    ctx = capi.Context(0)
+    cfg = capi.mcdpsk_config(nc, 2)
+    dem = capi.McDpskDemodulator(ctx, cfg)
+    rng = np.random.default_rng(900 + nc)
+    nsym = 9 + -(-648 // (2 * nc))
+    total = 1500 + 57600 + nsym * 512 + 300
+    cases = [(14.0, 500, 0.0, None), (6.0, 0, 7.3, None), (10.0, 1234, -22.0, None), (-14.0, 100, 0.0, None), (12.0, 300, 3.0, 60000 + 4096),
+             (12.0, 0, 0.0, 57600 + 9 * 512), (9.0, 1500, -0.3, None), (20.0, 77, 0.08, None)]
+    frames = []
+    for snr, lead, cfo, cut in cases:
+        f = mcdpsk_chirp_frame(cfg, rng, snr, lead, cfo, total)
+        if cut is not None:       # a receiver buffer that ends early: the rest of the row is silence
+            f = f.copy()
+            f[cut:] = 0.0
+        frames.append(f)
+    x = np.stack(frames)
+    llr, n, info, val, after = dem.chirp_receive_batch(x, llr_stride=700)
+    detected = accepted = 0
+    for b in range(len(x)):
+        ol, oi, of, oa = O.mcdpsk_chirp_receive(nc, x[b])
+        assert (info[b] == oi).all(), (b, cases[b], info[b], oi)
+        assert (val[b, :3].view(np.uint32) == of.view(np.uint32)).all(), (b, val[b], of)
+        want = ol[:700]
+        assert int(n[b]) == len(want), (b, cases[b], n[b], len(ol))
+        assert np.float32(after[b]).view(np.uint32) == np.float32(oa).view(np.uint32), (b, after[b], oa)
+        detected += int(oi[0])
+        if len(want):
+            accepted += 1
+            assert (llr[b, :len(want)].view(np.uint32) == want.view(np.uint32)).all(), (b, cases[b])
+        if R.available() and b in (1, 3, 4):
+            rl, ri, rf, ra = R.mcdpsk_chirp_receive(nc, x[b])
+            assert (ri == oi).all() and len(rl[:700]) == len(want) and (rl[:700].view(np.uint32) == want.view(np.uint32)).all()
+    assert detected >= 6 and accepted >= 3
+    # buffers that end right behind the chirp pair: training start at or beyond the end (test_iwaveform.cpp:143) or no data behind the
+    # preamble (processGotChirp keeps waiting) -> no soft bits, CFO report = the chirp's
+    xs = np.ascontiguousarray(x[:, :58000])
+    ls, ns, infos, vals, afters = dem.chirp_receive_batch(xs, llr_stride=700)
+    for b in range(len(xs)):
+        ol, oi, of, oa = O.mcdpsk_chirp_receive(nc, xs[b])
+        assert (infos[b] == oi).all() and int(ns[b]) == len(ol) == 0, (b, infos[b], oi, ns[b], len(ol))
+        assert np.float32(afters[b]).view(np.uint32) == np.float32(oa).view(np.uint32), (b, afters[b], oa)
+    d = dem.chirp_receive_batch(torch.from_numpy(x).cuda(), llr_stride=700)
+    torch.cuda.synchronize()
+    assert (d[1].cpu().numpy() == n).all() and (d[2].cpu().numpy() == info).all()
+    for b in range(len(x)):
+        k = int(n[b])
+        assert (d[0][b, :k].cpu().numpy().view(np.uint32) == llr[b, :k].view(np.uint32)).all()
+    del ctx
