@@ -286,6 +286,7 @@ PU_API pu_status pu_mcdpsk_got_chirp_batch(pu_mcdpsk* h, const float* samples, s
  * (:144-170, i.e. pu_mcdpsk_got_chirp_batch on the located span) -> getSoftBits.
  *   sync_info[B][4]   = {detected, up_chirp_start, down_chirp_start, SyncResult::start_sample (training start) or -1}
  *   sync_values[B][4] = {cfo_hz, up correlation, down correlation, 0}
+ *   llr_out[B][llr_stride] (may be NULL: detection only, i.e. IWaveform::detectSync; n_llr and cfo_after_hz are then unused),
  *   n_llr[B] = soft bits handed out (0: no chirp, start beyond the buffer, too short, or rejected by the 5 Hz rule); entries of
  *   llr_out[b] beyond n_llr[b] are unspecified; cfo_after_hz[B] = estimatedCFO(); threshold <= 0 selects the callers' 0.15. */
 PU_API pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* samples, size_t B, size_t L, float threshold,

@@ -5,14 +5,14 @@
 //   pu::Interleaver / pu::ChannelInterleaver <->  ultra::Interleaver / ChannelInterleaver   include/ultra/fec.hpp:85-142
 //   pu::OFDMDemodulator                      <->  ultra::OFDMDemodulator (presynced path)   include/ultra/ofdm.hpp:58-127
 //   pu::OFDMModulator                        <->  ultra::OFDMModulator (host TX stimulus)   include/ultra/ofdm.hpp:24-52
-//   pu::OfdmChirpWaveform                    <->  ultra::OFDMChirpWaveform RX data path     src/waveform/ofdm_chirp_waveform.cpp:174-230
+//   pu::OfdmChirpWaveform                    <->  ultra::OFDMChirpWaveform                  src/waveform/ofdm_chirp_waveform.cpp:129-230
+//   pu::McDpskWaveform                       <->  ultra::MCDPSKWaveform                     src/waveform/mc_dpsk_waveform.cpp:33-265
 //
 // Same method names, argument meaning, ownership (borrowed spans in, values out) and error behaviour as the
 // reference: no exceptions on the decode path, failure = lastDecodeSuccess()==false with best-effort
 // bytes, empty input -> {} and failure.  What differs: construction throws std::runtime_error when no sm_100 GPU /
-// library is usable (there is NO CPU fallback), and the parts of the reference classes outside the hot path
-// (Schmidl-Cox acquisition in OFDMDemodulator::process, chirp detection in IWaveform::detectSync) report
-// "not synchronised" instead of computing — they are SURVEY §8f "next" rows.
+// library is usable (there is NO CPU fallback).  Acquisition (Schmidl-Cox in OFDMDemodulator::process, the dual chirp in
+// IWaveform::detectSync) runs on the GPU as well.
 //
 // Define PU_DROPIN_WITH_ULTRA before including this header (with the reference's include/ and src/ on the include
 // path) to use the reference's own types (ultra::ModemConfig, Modulation, CodeRate, Bytes, ...) and to make
@@ -406,9 +406,8 @@ struct WaveformCapabilities {   // :25-34
 #endif
 
 // The RX data path of ultra::OFDMChirpWaveform (src/waveform/ofdm_chirp_waveform.cpp): configure ->
-// setFrequencyOffset -> process(span starting at the first training symbol) -> getSoftBits.  The dual-chirp
-// detector (detectSync, chirp_sync.hpp:349-506) is a SURVEY §8f next-2 row: detectSync reports "not detected", and
-// callers with external (genie / chirp) timing call process() directly, as tools/test_ofdm_chirp_pilots.cpp does.
+// detectSync (dual-chirp detector, chirp_sync.hpp:349-506) -> setFrequencyOffset -> process(span starting at the first training
+// symbol) -> getSoftBits; callers with external (genie) timing call process() directly, as tools/test_ofdm_chirp_pilots.cpp does.
 class OfdmChirpWaveform PU_IWAVEFORM_BASE {
 public:
     explicit OfdmChirpWaveform(const ModemConfig& cfg = ModemConfig{}) : cfg_(cfg) { rebuild(); }
@@ -524,6 +523,178 @@ private:
     std::vector<float> soft_;
     float cfo_hz_ = 0.0f;
     size_t training_start_sample_ = 0;   // SyncResult::start_sample of the last detection (0 before any: phase 0)
+    bool synced_ = false;
+};
+
+// ultra::MCDPSKWaveform (src/waveform/mc_dpsk_waveform.cpp): [chirp pair][training][reference][data].  detectSync = dual-chirp
+// detection with the training start two chirps and two gaps behind the up chirp (:100-142); process = setChirpDetected(cfo) ->
+// MultiCarrierDPSKDemodulator::process -> getSoftBits (:144-170), i.e. Hilbert-FIR CFO correction + processGotChirp.
+struct McDpskConfig {   // receive-path fields of ultra::MultiCarrierDPSKConfig (src/psk/multi_carrier_dpsk.hpp:26-51)
+    float sample_rate = 48000.0f;
+    int num_carriers = 8;
+    float freq_low = 500.0f, freq_high = 2500.0f;
+    int samples_per_symbol = 512, bits_per_symbol = 2, training_symbols = 8;
+    float tx_cfo_hz = 0.0f;
+};
+class McDpskWaveform PU_IWAVEFORM_BASE {
+public:
+    explicit McDpskWaveform(const McDpskConfig& cfg = McDpskConfig{}) : cfg_(cfg), ctx_(detail::shared_context()) { rebuild(); }
+    ~McDpskWaveform() {
+        if (h_) pu_mcdpsk_destroy(h_);
+    }
+    McDpskWaveform(const McDpskWaveform&) = delete;
+    McDpskWaveform& operator=(const McDpskWaveform&) = delete;
+
+    std::string getName() const PU_OVERRIDE { return "MC-DPSK"; }
+#ifdef PU_DROPIN_WITH_ULTRA
+    ultra::protocol::WaveformMode getMode() const override { return ultra::protocol::WaveformMode::MC_DPSK; }
+#endif
+    WaveformCapabilities getCapabilities() const PU_OVERRIDE {   // mc_dpsk_waveform.cpp:33-44
+        WaveformCapabilities c;
+        c.supports_cfo_correction = true;
+        c.supports_doppler_correction = true;
+        c.requires_pilots = false;
+        c.supports_differential = true;
+        c.min_snr_db = -3.0f;
+        c.max_snr_db = 15.0f;
+        c.max_throughput_bps = getThroughput(CodeRate::R1_4);
+        c.preamble_duration_ms = 500.0f * 2 + 100.0f * 2;
+        return c;
+    }
+    void configure(Modulation mod, CodeRate rate) PU_OVERRIDE {   // :46-69
+        modulation_ = mod;
+        code_rate_ = rate;
+        if (mod != Modulation::DQPSK && mod != Modulation::DBPSK && mod != Modulation::D8PSK) modulation_ = Modulation::DQPSK;
+        cfg_.bits_per_symbol = mod == Modulation::DBPSK ? 1 : mod == Modulation::D8PSK ? 3 : 2;
+        rebuild();
+    }
+    void setFrequencyOffset(float cfo_hz) PU_OVERRIDE { cfo_hz_ = cfo_hz; }                                   // :71-76
+    void setTxFrequencyOffset(float cfo_hz) PU_OVERRIDE { cfg_.tx_cfo_hz = cfo_hz; }                          // :78-84
+    Modulation getModulation() const PU_OVERRIDE { return modulation_; }
+    CodeRate getCodeRate() const PU_OVERRIDE { return code_rate_; }
+    float getFrequencyOffset() const PU_OVERRIDE { return cfo_hz_; }
+
+    Samples generatePreamble() PU_OVERRIDE {   // chirp pair + training + reference (multi_carrier_dpsk.hpp:104-115)
+        size_t n = 0;
+        pu_chirp_generate(cfg_.sample_rate, cfg_.tx_cfo_hz, nullptr, 0, &n);
+        Samples pre(n);
+        pu_chirp_generate(cfg_.sample_rate, cfg_.tx_cfo_hz, pre.data(), pre.size(), &n);
+        const Samples head = tx(Bytes{});
+        pre.insert(pre.end(), head.begin(), head.end());
+        return pre;
+    }
+    Samples modulate(const Bytes& encoded) PU_OVERRIDE {   // data symbols behind the reference symbol (:176-243)
+        Samples all = tx(encoded);
+        const size_t pre = static_cast<size_t>(cfg_.training_symbols + 1) * cfg_.samples_per_symbol;
+        return all.size() > pre ? Samples(all.begin() + pre, all.end()) : Samples{};
+    }
+
+    bool detectSync(SampleSpan samples, SyncResult& result, float threshold = 0.3f) PU_OVERRIDE {   // :100-142
+        result = SyncResult{};
+        int32_t info[4] = {0, -1, -1, -1};
+        float val[4] = {0, 0, 0, 0};
+        if (!h_ || samples.empty() ||
+            pu_mcdpsk_chirp_receive_batch(h_, samples.data(), 1, samples.size(), threshold, nullptr, 0, nullptr, info, val, nullptr, PU_MEM_HOST,
+                                          nullptr) != PU_OK)
+            return false;
+        result.detected = info[0] != 0;
+        result.start_sample = info[1];
+        result.correlation = std::max(val[1], val[2]);
+        result.cfo_hz = val[0];
+        result.has_training = true;
+        if (result.detected) {
+            synced_ = true;
+            last_cfo_ = val[0];
+            result.start_sample = info[3];
+        }
+        return result.detected;
+    }
+    bool process(SampleSpan samples) PU_OVERRIDE {   // :144-170
+        soft_.clear();
+        if (!h_ || samples.empty()) return false;
+        const size_t nsym = samples.size() / static_cast<size_t>(cfg_.samples_per_symbol);
+        const size_t stride = std::max<size_t>(1, nsym * static_cast<size_t>(cfg_.num_carriers * cfg_.bits_per_symbol));
+        std::vector<float> llr(stride);
+        int32_t n = 0;
+        float after = cfo_hz_;
+        if (pu_mcdpsk_got_chirp_batch(h_, samples.data(), 1, samples.size(), &cfo_hz_, llr.data(), stride, &n, &after, PU_MEM_HOST, nullptr) != PU_OK)
+            return false;
+        demod_cfo_ = after;
+        if (n <= 0) return false;
+        llr.resize(static_cast<size_t>(n));
+        soft_ = std::move(llr);
+        synced_ = true;
+        return true;
+    }
+    std::vector<float> getSoftBits() PU_OVERRIDE { return std::move(soft_); }
+    void reset() PU_OVERRIDE {   // keeps the CFO (:176-184)
+        soft_.clear();
+        synced_ = false;
+    }
+    bool isSynced() const PU_OVERRIDE { return synced_; }
+    bool hasData() const PU_OVERRIDE { return !soft_.empty(); }
+    float estimatedSNR() const PU_OVERRIDE { return 0.0f; }
+    float estimatedCFO() const PU_OVERRIDE { return demod_cfo_; }
+    std::vector<std::complex<float>> getConstellationSymbols() const PU_OVERRIDE { return {}; }
+    std::string getStatusString() const PU_OVERRIDE {
+        return "MC-DPSK " + std::to_string(cfg_.num_carriers) + " carriers @ " + std::to_string(static_cast<int>(getThroughput(code_rate_))) + " bps";
+    }
+    int getCarrierCount() const PU_OVERRIDE { return cfg_.num_carriers; }
+    float getThroughput(CodeRate rate) const PU_OVERRIDE {   // :220-236
+        const float raw_bps = cfg_.sample_rate / cfg_.samples_per_symbol * cfg_.num_carriers * cfg_.bits_per_symbol;
+        float code_ratio = 0.25f;
+        switch (rate) {
+            case CodeRate::R1_4: code_ratio = 0.25f; break;
+            case CodeRate::R1_3: code_ratio = 0.333f; break;
+            case CodeRate::R1_2: code_ratio = 0.5f; break;
+            case CodeRate::R2_3: code_ratio = 0.667f; break;
+            case CodeRate::R3_4: code_ratio = 0.75f; break;
+            case CodeRate::R5_6: code_ratio = 0.833f; break;
+            default: break;
+        }
+        return raw_bps * code_ratio;
+    }
+    int getSamplesPerSymbol() const PU_OVERRIDE { return cfg_.samples_per_symbol; }
+    int getPreambleSamples() const PU_OVERRIDE {   // ChirpSync::getTotalSamples (:238-247)
+        const size_t chirp = static_cast<size_t>(cfg_.sample_rate * 500.0f / 1000.0f), gap = static_cast<size_t>(cfg_.sample_rate * 100.0f / 1000.0f);
+        return static_cast<int>(2 * chirp + 2 * gap);
+    }
+    int getMinSamplesForFrame() const PU_OVERRIDE {   // :254-265
+        const int bits = cfg_.num_carriers * cfg_.bits_per_symbol;
+        return (cfg_.training_symbols + 1 + (PU_LDPC_N + bits - 1) / bits) * cfg_.samples_per_symbol;
+    }
+
+private:
+    pu_mcdpsk_config pod() const {
+        pu_mcdpsk_config c{};
+        c.sample_rate = cfg_.sample_rate;
+        c.freq_low = cfg_.freq_low; c.freq_high = cfg_.freq_high;
+        c.num_carriers = static_cast<uint32_t>(cfg_.num_carriers);
+        c.samples_per_symbol = static_cast<uint32_t>(cfg_.samples_per_symbol);
+        c.bits_per_symbol = static_cast<uint32_t>(cfg_.bits_per_symbol);
+        c.training_symbols = static_cast<uint32_t>(cfg_.training_symbols);
+        return c;
+    }
+    void rebuild() {   // D8PSK over MC-DPSK (3 bits per carrier) is not on the batched path: the waveform then reports "no data"
+        if (h_) { pu_mcdpsk_destroy(h_); h_ = nullptr; }
+        const pu_mcdpsk_config c = pod();
+        pu_mcdpsk_create(ctx_, &c, &h_);
+    }
+    Samples tx(const Bytes& data) const {
+        const pu_mcdpsk_config c = pod();
+        size_t n = 0;
+        (void)pu_mcdpsk_tx(&c, data.data(), data.size(), nullptr, 0, &n);   // length query
+        Samples out(n);
+        if (pu_mcdpsk_tx(&c, data.data(), data.size(), out.data(), out.size(), &n) != PU_OK) return {};
+        return out;
+    }
+    McDpskConfig cfg_;
+    pu_ctx* ctx_;
+    pu_mcdpsk* h_ = nullptr;
+    Modulation modulation_ = Modulation::DQPSK;
+    CodeRate code_rate_ = CodeRate::R1_4;
+    std::vector<float> soft_;
+    float cfo_hz_ = 0.0f, last_cfo_ = 0.0f, demod_cfo_ = 0.0f;
     bool synced_ = false;
 };
 

@@ -960,8 +960,9 @@ pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* samples, size
                                         pu_memspace space, void* stream) {
     PU_REQUIRE(h, "pu_mcdpsk_chirp_receive_batch: NULL handle");
     if (B == 0) return PU_OK;
-    PU_REQUIRE(samples && llr_out && n_llr && sync_info && sync_values && cfo_after_hz, "pu_mcdpsk_chirp_receive_batch: NULL data pointer");
-    PU_REQUIRE(llr_stride > 0 && L < (1u << 30), "pu_mcdpsk_chirp_receive_batch: bad size");
+    PU_REQUIRE(samples && sync_info && sync_values, "pu_mcdpsk_chirp_receive_batch: NULL data pointer");
+    PU_REQUIRE(!llr_out || (n_llr && cfo_after_hz && llr_stride > 0), "pu_mcdpsk_chirp_receive_batch: llr_out needs n_llr, cfo_after_hz and llr_stride");
+    PU_REQUIRE(L < (1u << 30), "pu_mcdpsk_chirp_receive_batch: frame too long");
     pu_ctx* ctx = h->ctx;
     PU_CUDA_TRY(cudaSetDevice(ctx->device));
     pu_status s;
@@ -980,10 +981,13 @@ pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* samples, size
     std::vector<int32_t> info_h(B * 4, 0);
     std::vector<float> val_h(B * 4, 0.0f);
     if (space == PU_MEM_HOST) {
-        std::vector<float> zf(B * llr_stride, 0.0f);
         if ((s = dx.upload(samples, B * L)) != PU_OK) return s;
-        if ((s = dl.upload(zf.data(), zf.size())) != PU_OK) return s;
-        d_x = static_cast<const float*>(dx.p); d_llr = static_cast<float*>(dl.p);
+        d_x = static_cast<const float*>(dx.p);
+        if (llr_out) {
+            std::vector<float> zf(B * llr_stride, 0.0f);
+            if ((s = dl.upload(zf.data(), zf.size())) != PU_OK) return s;
+            d_llr = static_cast<float*>(dl.p);
+        }
     }
     if ((s = dinfo.upload(info_h.data(), info_h.size())) != PU_OK) return s;
     if ((s = dval.upload(val_h.data(), val_h.size())) != PU_OK) return s;
@@ -1006,6 +1010,14 @@ pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* samples, size
         val_h[4 * b + 3] = 0.0f;                       // no rotator phase on this path (the CFO is removed by the Hilbert-FIR shift)
         start_h[b] = (start >= 0 && static_cast<size_t>(start) < L) ? start : -1;
     }
+    if (space == PU_MEM_HOST) {
+        std::memcpy(sync_info, info_h.data(), info_h.size() * sizeof(int32_t));
+        std::memcpy(sync_values, val_h.data(), val_h.size() * sizeof(float));
+    } else {
+        PU_CUDA_TRY(cudaMemcpy(sync_info, info_h.data(), info_h.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        PU_CUDA_TRY(cudaMemcpy(sync_values, val_h.data(), val_h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (!llr_out) return PU_OK;                        // detection only (IWaveform::detectSync)
     if ((s = dstart.upload(start_h.data(), B)) != PU_OK) return s;
     std::vector<int32_t> n_h;
     std::vector<float> after_h;
@@ -1015,13 +1027,9 @@ pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* samples, size
         PU_CUDA_TRY(cudaMemcpy(llr_out, d_llr, B * llr_stride * sizeof(float), cudaMemcpyDeviceToHost));
         std::memcpy(n_llr, n_h.data(), B * sizeof(int32_t));
         std::memcpy(cfo_after_hz, after_h.data(), B * sizeof(float));
-        std::memcpy(sync_info, info_h.data(), info_h.size() * sizeof(int32_t));
-        std::memcpy(sync_values, val_h.data(), val_h.size() * sizeof(float));
     } else {
         PU_CUDA_TRY(cudaMemcpy(n_llr, n_h.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice));
         PU_CUDA_TRY(cudaMemcpy(cfo_after_hz, after_h.data(), B * sizeof(float), cudaMemcpyHostToDevice));
-        PU_CUDA_TRY(cudaMemcpy(sync_info, info_h.data(), info_h.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        PU_CUDA_TRY(cudaMemcpy(sync_values, val_h.data(), val_h.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     return PU_OK;
 }

@@ -14,6 +14,7 @@
 
 #define PU_DROPIN_WITH_ULTRA
 #include "sync/chirp_sync.hpp"
+#include "psk/multi_carrier_dpsk.hpp"
 #include "pu/pu_dropin.hpp"
 
 #include "ultra/fec.hpp"
@@ -373,6 +374,81 @@ static void chirp_section() {
     }
 }
 
+// tools/test_iwaveform.cpp:127-160 on MC-DPSK frames through pu::McDpskWaveform (IWaveform::generatePreamble / modulate / detectSync ->
+// setFrequencyOffset -> process -> getSoftBits), against the reference's MultiCarrierDPSKModulator / ChirpSync /
+// MultiCarrierDPSKDemodulator driven with the glue of MCDPSKWaveform (src/waveform/mc_dpsk_waveform.cpp:86-170).
+static void mcdpsk_section() {
+    const int carriers[] = {8, 5, 13};
+    const float snrs[] = {15.0f, 6.0f, 10.0f};
+    LDPCEncoder enc(CodeRate::R1_4);
+    std::mt19937 rng(777);
+    for (int trial = 0; trial < 3; ++trial) {
+        MultiCarrierDPSKConfig rc;
+        rc.num_carriers = carriers[trial];
+        pu::McDpskConfig pc;
+        pc.num_carriers = carriers[trial];
+        std::unique_ptr<IWaveform> wf = std::make_unique<pu::McDpskWaveform>(pc);
+        wf->configure(Modulation::DQPSK, CodeRate::R1_4);
+        Bytes payload(20);
+        for (auto& b : payload) b = static_cast<uint8_t>(rng() & 0xFF);
+        const Bytes coded = enc.encode(payload);
+        // transmitter: the drop-in's waveform must equal the reference modulator's sample for sample
+        MultiCarrierDPSKModulator mod(rc);
+        const Samples ref_pre = mod.generatePreamble();
+        const Samples ref_data = mod.modulate(coded);
+        const Samples pre = wf->generatePreamble();
+        const Samples data = wf->modulate(coded);
+        CHECK(pre.size() == ref_pre.size() && std::memcmp(pre.data(), ref_pre.data(), pre.size() * sizeof(float)) == 0, "mcdpsk trial %d generatePreamble", trial);
+        CHECK(data.size() == ref_data.size() && std::memcmp(data.data(), ref_data.data(), data.size() * sizeof(float)) == 0, "mcdpsk trial %d modulate", trial);
+        CHECK(wf->getPreambleSamples() == 57600 && wf->getSamplesPerSymbol() == 512 && wf->getCarrierCount() == carriers[trial] &&
+                  wf->getMinSamplesForFrame() == (9 + (648 + 2 * carriers[trial] - 1) / (2 * carriers[trial])) * 512,
+              "mcdpsk trial %d geometry", trial);
+        Samples tx(static_cast<size_t>(300 + 450 * trial), 0.0f);
+        tx.insert(tx.end(), ref_pre.begin(), ref_pre.end());
+        tx.insert(tx.end(), ref_data.begin(), ref_data.end());
+        tx.insert(tx.end(), 500, 0.0f);
+        const Samples rx = add_noise(tx, snrs[trial], 5000u + static_cast<uint32_t>(trial));
+        const SampleSpan audio(rx.data(), rx.size());
+
+        // reference side
+        sync::ChirpSync chirp(rc.getChirpConfig());
+        std::fflush(stdout);
+        const int saved = dup(1), nul = open("/dev/null", O_WRONLY);
+        if (nul >= 0) { dup2(nul, 1); close(nul); }
+        auto r = chirp.detectDualChirp(audio, 0.15f);
+        std::fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+        std::vector<float> ref_soft;
+        int ref_start = -1;
+        float ref_cfo_after = r.cfo_hz;
+        if (r.success) {
+            size_t chirp_samples = chirp.getChirpSamples();
+            size_t gap_samples = static_cast<size_t>(rc.sample_rate * rc.getChirpConfig().gap_ms / 1000.0f);
+            ref_start = r.up_chirp_start + 2 * chirp_samples + 2 * gap_samples;
+            MultiCarrierDPSKDemodulator d(rc);
+            d.setCFO(r.cfo_hz);
+            d.setChirpDetected(r.cfo_hz);
+            if (d.process(SampleSpan(rx.data() + ref_start, rx.size() - ref_start))) ref_soft = d.getSoftBits();
+            ref_cfo_after = d.getEstimatedCFO();
+        }
+        // drop-in side
+        wf->reset();
+        SyncResult sr;
+        const bool found = wf->detectSync(audio, sr, 0.15f);
+        CHECK(found == r.success, "mcdpsk trial %d detected %d vs %d", trial, (int)found, (int)r.success);
+        if (found && r.success) {
+            CHECK(sr.start_sample == ref_start, "mcdpsk trial %d start_sample %d vs %d", trial, sr.start_sample, ref_start);
+            CHECK(std::memcmp(&sr.cfo_hz, &r.cfo_hz, 4) == 0, "mcdpsk trial %d cfo %.6f vs %.6f", trial, sr.cfo_hz, r.cfo_hz);
+            wf->setFrequencyOffset(sr.cfo_hz);
+            const bool ready = wf->process(SampleSpan(rx.data() + sr.start_sample, rx.size() - sr.start_sample));
+            const auto soft = wf->getSoftBits();
+            CHECK(ready == !ref_soft.empty() && same_words(soft, ref_soft), "mcdpsk trial %d soft bits (%zu vs %zu)", trial, soft.size(), ref_soft.size());
+            const float after = wf->estimatedCFO();
+            CHECK(std::memcmp(&after, &ref_cfo_after, 4) == 0, "mcdpsk trial %d estimatedCFO %.6f vs %.6f", trial, after, ref_cfo_after);
+        }
+    }
+}
+
 int main() {
     setLogLevel(LogLevel::ERROR);
     if (!std::freopen("/dev/null", "w", stderr)) return 2;   // the reference prints unconditionally on the hot path
@@ -382,6 +458,7 @@ int main() {
         ofdm_section();
         process_section();
         chirp_section();
+        mcdpsk_section();
     } catch (const std::exception& e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

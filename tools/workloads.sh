@@ -9,6 +9,7 @@ QB_CHANNEL=good python tools/ofdm_quick_bench.py 4096 m3 > $OUT/demod_m3_good.lo
 python tools/acquire_quick_bench.py 8192 > $OUT/acquire.log 2>&1
 python tools/dpsk_acquire_quick_bench.py 2048 > $OUT/dpsk_acquire.log 2>&1
 python tools/chirp_quick_bench.py 2048 > $OUT/chirp.log 2>&1
+python tools/chirp_quick_bench.py 2048 mcdpsk > $OUT/chirp_mcdpsk.log 2>&1
 python - > $OUT/tx.log 2>&1 <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -36,6 +37,7 @@ for f in demod_m1 demod_m3 demod_m3_good demod_m1qam16; do tail -1 $OUT/$f.log |
 echo; echo "### Acquisition (config 1 as literally specified), 8 192 frames of 10 124 samples (tools/acquire_quick_bench.py)"; echo '```'; cat $OUT/acquire.log; echo '```'
 echo; echo "### DPSK Barker acquisition (config 4 as literally specified), 2 048 frames of 139 392 samples (tools/dpsk_acquire_quick_bench.py)"; echo '```'; cat $OUT/dpsk_acquire.log; echo '```'
 echo; echo "### Dual-chirp synchronisation + presynced demodulation of OFDM_CHIRP frames (tools/chirp_quick_bench.py)"; echo '```'; cat $OUT/chirp.log; echo '```'
+echo; echo "### Dual-chirp synchronisation + Hilbert-FIR correction + processGotChirp of MC-DPSK frames (tools/chirp_quick_bench.py B mcdpsk)"; echo '```'; cat $OUT/chirp_mcdpsk.log; echo '```'
 echo; echo "### Transmitter (pu_ofdm_tx_batch)"; echo '```'; cat $OUT/tx.log; echo '```'
 } > $OUT/workloads.md
 cat $OUT/workloads.md | tail -40
