@@ -336,6 +336,23 @@ PU_API pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const flo
                                          int training_symbols, const float* cfo_hz, const float* cfo_phase,
                                          uint8_t* info_bytes, size_t info_stride, uint8_t* ok, int32_t* iters,
                                          pu_memspace space, void* stream);
+/* ---------------------------------------------------------------- protocol-v2 multi-codeword frames
+ * RxPipeline::decodeFrame(soft_bits, num_codewords) (src/gui/modem/rx_pipeline.cpp:348-445) for B frames, all codewords at the
+ * decoder handle's rate (the rule of :356-365): decode CW0 (v2::decodeSingleCodeword, src/protocol/frame_v2.cpp:1134-1156) ->
+ * parseHeader (:1175-1230: magic 0x554C, control/data layout, CRC-16) -> expected = TOTAL_CW -> "waiting" when num_codewords <
+ * expected -> decode CW1+ -> success iff all decoded -> CodewordStatus::reassemble (:952-982,1023-1044: CW1+ lose their 0xD5/index
+ * prefix).  llr[B][num_codewords][648]; frame_out[B][frame_cap] (bytes beyond frame_cap are dropped), frame_len[B] = size of
+ * RxFrameResult::frame_data (0 unless success); info[B][5] = {success, frame_type, codewords_ok, codewords_failed, expected
+ * codewords (0 = CW0 failed or header invalid)}.  One launch of the LDPC kernel over all B*num_codewords codewords + one assembly
+ * kernel.  A data header with TOTAL_CW = 0 is undefined in the reference (out-of-bounds write); here: success, empty frame. */
+PU_API pu_status pu_frame_decode_batch(pu_ctx* ctx, pu_ldpc* dec, const float* llr, size_t B, size_t num_codewords,
+                                       uint8_t* frame_out, size_t frame_cap, int32_t* frame_len, int32_t* info,
+                                       pu_memspace space, void* stream);
+/* v2::encodeFrameWithLDPC(frame_data, rate) (frame_v2.cpp:1079-1127), host: out = n_codewords x 81 bytes; out == NULL queries
+ * the codeword count. */
+PU_API pu_status pu_frame_encode(int code_rate, const uint8_t* frame, size_t n_bytes, uint8_t* out, size_t out_cap,
+                                 size_t* n_codewords);
+
 /* Frame-error rule of the tools (tools/test_mode_snr.cpp:98-104): success iff lastDecodeSuccess() and the first
  * payload_bytes decoded bytes equal the payload.  DEVICE pointers.  counters[bin[b]][6] (uint64, atomically
  * accumulated) = {frames, frame_errors, bit_errors, payload_bits, decode_failures, iteration_sum};

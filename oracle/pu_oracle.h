@@ -53,6 +53,12 @@ long orc_ldpc_decode_soft(int rate, int max_iter, const float* llr, size_t n, ui
 int orc_ldpc_decode_batch(int rate, int max_iter, const float* llr, size_t B, uint8_t* out, size_t out_stride,
                           uint8_t* ok, int32_t* iters);
 
+/* ---- protocol-v2 codeword framing (src/protocol/frame_v2.cpp; RxPipeline::decodeFrame, src/gui/modem/rx_pipeline.cpp:348-445) ---- */
+uint16_t orc_frame_crc16(const uint8_t* data, size_t len);
+size_t orc_frame_bytes_per_codeword(int rate);
+long orc_frame_encode(int rate, const uint8_t* frame, size_t len, uint8_t* out, size_t cap);
+long orc_frame_decode(int rate, const float* soft, size_t n_soft, int num_codewords, uint8_t* out, size_t cap, int32_t* info);
+
 /* ---- interleavers (ldpc_decoder.cpp:454-620) ---- */
 size_t orc_channel_interleaver_step(size_t bits_per_symbol, size_t total);
 int orc_channel_interleave(size_t bps, size_t total, const float* in, size_t n, float* out, int inverse);

@@ -378,3 +378,111 @@ int orc_block_interleave(size_t rows, size_t cols, const float* in, size_t n, fl
     }
     return (int)n;
 }
+
+/* ------------------------------------------------------------------ protocol-v2 codeword framing
+ * src/protocol/frame_v2.hpp:139-155,212-217,551-566 (constants, isControlFrame, bytes per codeword), frame_v2.cpp:111-124 (CRC-16/CCITT,
+ * init 0xFFFF, poly 0x1021), :952-982 (reassembleCodewords), :1023-1044 (CodewordStatus::reassemble), :1079-1127 (encodeFrameWithLDPC),
+ * :1134-1156 (decodeSingleCodeword), :1175-1230 (parseHeader), and RxPipeline::decodeFrame (src/gui/modem/rx_pipeline.cpp:348-445). */
+uint16_t orc_frame_crc16(const uint8_t* data, size_t len) {
+    uint16_t crc = 0xFFFF;
+    for (size_t i = 0; i < len; i++) {
+        crc ^= (uint16_t)((uint16_t)data[i] << 8);
+        for (int j = 0; j < 8; j++) crc = (crc & 0x8000) ? (uint16_t)((crc << 1) ^ 0x1021) : (uint16_t)(crc << 1);
+    }
+    return crc;
+}
+
+size_t orc_frame_bytes_per_codeword(int rate) {   /* getInfoBitsForRate / 8, rounded down */
+    switch (rate) {
+        case 0: return 162 / 8;
+        case 1: return 216 / 8;
+        case 2: return 324 / 8;
+        case 3: return 432 / 8;
+        case 4: return 486 / 8;
+        case 5: return 540 / 8;
+        default: return 162 / 8;
+    }
+}
+
+/* encodeFrameWithLDPC: CW0 = the first bytes_per_cw frame bytes, CW1+ = {0xD5, index, payload}, zero-padded; returns the codeword count */
+long orc_frame_encode(int rate, const uint8_t* frame, size_t len, uint8_t* out, size_t cap) {
+    const size_t bpc = orc_frame_bytes_per_codeword(rate), pay = bpc - 2;
+    uint8_t chunk[80];
+    size_t off = 0, ncw = 0, offset = bpc;
+    memset(chunk, 0, sizeof chunk);
+    memcpy(chunk, frame, len < bpc ? len : bpc);
+    for (;;) {
+        if (off + 81 > cap) return -1;
+        if (orc_ldpc_encode(rate, chunk, bpc, out + off, 81) != 81) return -1;
+        off += 81;
+        ncw++;
+        if (offset >= len) break;
+        memset(chunk, 0, sizeof chunk);
+        chunk[0] = 0xD5;
+        chunk[1] = (uint8_t)ncw;
+        const size_t remaining = len - offset;
+        memcpy(chunk + 2, frame + offset, remaining < pay ? remaining : pay);
+        offset += pay;
+    }
+    return (long)ncw;
+}
+
+/* parseHeader: returns 1 when valid; total_cw / payload_len / is_control / type as HeaderInfo */
+static int frame_parse_header(const uint8_t* d, int* type, int* is_control, int* total_cw, int* payload_len) {
+    if (((d[0] << 8) | d[1]) != 0x554C) return 0;
+    *type = d[2];
+    *is_control = d[2] == 0x10 || d[2] == 0x11 || d[2] == 0x16 || d[2] == 0x17 || d[2] == 0x20 || d[2] == 0x21 || d[2] == 0x40;
+    if (*is_control) {
+        if (((d[18] << 8) | d[19]) != orc_frame_crc16(d, 18)) return 0;
+        *total_cw = 1;
+        *payload_len = 0;
+    } else {
+        *total_cw = d[12];
+        *payload_len = (d[13] << 8) | d[14];
+        if (((d[15] << 8) | d[16]) != orc_frame_crc16(d, 15)) return 0;
+    }
+    return 1;
+}
+
+/* RxPipeline::decodeFrame: info[5] = {success, frame_type, codewords_ok, codewords_failed, expected}; returns the frame_data size */
+long orc_frame_decode(int rate, const float* soft, size_t n_soft, int num_codewords, uint8_t* out, size_t cap, int32_t* info) {
+    const size_t bpc = orc_frame_bytes_per_codeword(rate);
+    const orc_ldpc_code* c = cached_code(rate);
+    uint8_t cw[256][72];
+    uint8_t buf[96];
+    int ok, it;
+    info[0] = info[1] = info[2] = info[3] = info[4] = 0;
+    if (n_soft < ORC_LDPC_N) return 0;
+    orc_ldpc_decode_block(c, 50, soft, ORC_LDPC_N, buf, &ok, &it, NULL);
+    if (!ok || (size_t)((c->k + 7) / 8) < bpc) { info[3]++; return 0; }     /* decodeSingleCodeword */
+    memcpy(cw[0], buf, bpc);
+    info[2]++;
+    int type = 0, is_control = 0, expected = 0, payload_len = 0;
+    if (!frame_parse_header(cw[0], &type, &is_control, &expected, &payload_len)) return 0;
+    info[1] = type;
+    info[4] = expected;
+    if (num_codewords < expected) return 0;
+    int all = 1;
+    for (int i = 1; i < expected; i++) {
+        orc_ldpc_decode_block(c, 50, soft + (size_t)i * ORC_LDPC_N, ORC_LDPC_N, buf, &ok, &it, NULL);
+        if (ok) { memcpy(cw[i], buf, bpc); info[2]++; }
+        else { info[3]++; all = 0; }
+    }
+    if (!all) return 0;      /* allSuccess over `expected` entries: expected == 0 leaves CW0 only... see below */
+    info[0] = 1;
+    /* CodewordStatus::reassemble: decoded.empty() (expected == 0) -> {}; otherwise header + payload + CRC bytes */
+    if (expected == 0) return 0;
+    const size_t expected_size = is_control ? 20 : (size_t)(17 + payload_len + 2);
+    size_t n = 0;
+    for (int i = 0; i < expected && n < expected_size; i++) {
+        const size_t remaining = expected_size - n;
+        const uint8_t* src = cw[i];
+        size_t avail = bpc;
+        if (i > 0 && cw[i][0] == 0xD5) { src = cw[i] + 2; avail = bpc - 2; }   /* marker + index skipped; else legacy fallback */
+        const size_t take = remaining < avail ? remaining : avail;
+        if (n + take > cap) return -1;
+        memcpy(out + n, src, take);
+        n += take;
+    }
+    return (long)n;
+}

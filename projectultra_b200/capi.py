@@ -159,6 +159,29 @@ class LdpcDecoder:
             out.append([buf[e] for e in range(d)])
         return out
 
+    def frame_decode_batch(self, llr, num_codewords, frame_cap=None):
+        """pu_frame_decode_batch: RxPipeline::decodeFrame for every row of llr [B, num_codewords * 648] at this decoder's rate ->
+        (frames [B, frame_cap] uint8, frame_len [B], info [B, 5] = {success, frame_type, codewords ok, codewords failed, expected})."""
+        tor = _is_torch(llr)
+        if tor:
+            import torch
+            assert llr.dtype == torch.float32 and llr.dim() == 2 and llr.is_contiguous()
+        else:
+            llr = np.ascontiguousarray(llr, dtype=np.float32)
+            if llr.ndim == 1:
+                llr = llr.reshape(1, -1)
+        B = llr.shape[0]
+        assert llr.shape[1] == num_codewords * 648
+        if frame_cap is None:
+            frame_cap = num_codewords * ((lib().pu_ldpc_info_bits(self._h) + 7) // 8)
+        frames = _like(llr, (B, frame_cap), np.uint8, "uint8")
+        flen = _like(llr, (B,), np.int32, "int32")
+        info = _like(llr, (B, 5), np.int32, "int32")
+        sp = _space(llr, frames, flen, info)
+        check(lib().pu_frame_decode_batch(self.ctx._h, self._h, _ptr(llr), C.c_size_t(B), C.c_size_t(num_codewords), _ptr(frames),
+                                          C.c_size_t(frame_cap), _ptr(flen), _ptr(info), sp, _stream(sp)))
+        return frames, flen, info
+
     def decode_batch(self, llr, info=None, ok=None, iters=None):
         """llr: [B, >=648] float32 (numpy => host, torch.cuda => device).  Returns (info_bytes, ok, iters)."""
         if _is_torch(llr):
@@ -225,6 +248,16 @@ def ldpc_encode(rate, data):
     n = C.c_size_t(0)
     check(lib().pu_ldpc_encode(int(rate), _ptr(d), C.c_size_t(len(d)), _ptr(out), C.c_size_t(len(out)), C.byref(n)))
     return out[:n.value].copy()
+
+
+def frame_encode(rate, frame):
+    """pu_frame_encode: v2::encodeFrameWithLDPC(frame, rate) (host) -> uint8 [n_codewords, 81]."""
+    f = np.ascontiguousarray(np.frombuffer(bytes(frame), np.uint8) if isinstance(frame, (bytes, bytearray)) else frame, dtype=np.uint8)
+    n = C.c_size_t(0)
+    check(lib().pu_frame_encode(int(rate), _ptr(f), C.c_size_t(len(f)), None, C.c_size_t(0), C.byref(n)))
+    out = np.zeros((n.value, 81), np.uint8)
+    check(lib().pu_frame_encode(int(rate), _ptr(f), C.c_size_t(len(f)), _ptr(out), C.c_size_t(out.size), C.byref(n)))
+    return out
 
 
 def channel_interleaver_perm(bps, total=648):

@@ -265,6 +265,34 @@ def mcdpsk_got_chirp_vectors():
     np.savez_compressed(os.path.join(HERE, "mcdpsk_chirp_golden.npz"), **out)
 
 
+def frame_vectors():
+    """Protocol-v2 multi-codeword frames (SURVEY 8f next-4): DataFrame::serialize -> encodeFrameWithLDPC -> +-6 LLRs with sign flips ->
+    RxPipeline::decodeFrame, for a 1-codeword control frame, 2- and 5-codeword data frames (clean / a failing CW0 / a failing later
+    codeword / too few codewords)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import v2frames as V
+    rng = np.random.default_rng(20261022)
+    out = {}
+    cases = [(R.R1_4, None, 0.0, 0, None), (R.R1_4, 30, 0.02, 0, None), (R.R1_2, 150, 0.0, 0, None), (R.R1_2, 150, 0.13, 0, None),
+             (R.R3_4, 200, 0.01, 1, None), (R.R5_6, 64, 0.0, 0, None), (R.R1_2, 150, 0.2, 0, 2)]
+    for i, (rate, plen, flip, drop, only_cw) in enumerate(cases):
+        fr = R.control_frame_serialize() if plen is None else R.data_frame_serialize(rate, rng.integers(0, 256, plen, dtype=np.uint8))
+        cws = R.frame_encode(rate, fr)
+        llr = V.codeword_llrs(cws[:len(cws) - drop], rng, flip if only_cw is None else 0.0)
+        if only_cw is not None:      # CW0 decodes, a later codeword does not
+            llr[only_cw * 648:(only_cw + 1) * 648] = V.codeword_llrs(cws[only_cw:only_cw + 1], rng, flip)
+        frame, info = R.frame_decode(rate, llr, len(cws) - drop)
+        out[f"f{i}_rate"] = np.array([rate], np.int64)
+        out[f"f{i}_frame"] = fr
+        out[f"f{i}_codewords"] = cws
+        out[f"f{i}_llr"] = llr.astype(np.float16).astype(np.float32)     # +-6 exactly representable: keeps the file small
+        out[f"f{i}_ncw"] = np.array([len(cws) - drop], np.int64)
+        out[f"f{i}_info"] = info.astype(np.int64)
+        out[f"f{i}_out"] = frame
+    out["count"] = np.array([len(cases)], np.int64)
+    np.savez_compressed(os.path.join(HERE, "frame_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
     ldpc_vectors()
@@ -275,6 +303,7 @@ if __name__ == "__main__":
     dpsk_acquire_vectors()
     chirp_vectors()
     mcdpsk_got_chirp_vectors()
+    frame_vectors()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

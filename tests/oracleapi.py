@@ -338,3 +338,30 @@ def mcdpsk_demod_soft(nc, samples, sps=512, bits=2, f_lo=500.0, f_hi=2500.0, fs=
                                 training, _p(out, C.c_float), C.c_size_t(len(out)), C.byref(cfo))
     assert 0 <= n <= len(out), n
     return out[:n].copy(), cfo.value
+
+
+def frame_encode(rate, frame):
+    """v2::encodeFrameWithLDPC(frame, rate) -> uint8 [ncw, 81]."""
+    f = np.ascontiguousarray(frame, np.uint8)
+    out = np.zeros(256 * 81, np.uint8)
+    L = lib()
+    L.orc_frame_encode.restype = C.c_long
+    n = L.orc_frame_encode(int(rate), _p(f, C.c_uint8), C.c_size_t(len(f)), _p(out, C.c_uint8), C.c_size_t(len(out)))
+    assert n > 0, n
+    return out[:n * 81].reshape(n, 81).copy()
+
+
+def frame_decode(rate, soft, num_codewords=None):
+    """RxPipeline::decodeFrame(soft_bits, num_codewords) -> (frame bytes, info[5] = {success, type, cw ok, cw failed, expected})."""
+    x = _f32(soft).reshape(-1)
+    if num_codewords is None:
+        num_codewords = len(x) // 648
+    assert len(x) >= num_codewords * 648
+    out = np.zeros(8192, np.uint8)
+    info = np.zeros(5, np.int32)
+    L = lib()
+    L.orc_frame_decode.restype = C.c_long
+    n = L.orc_frame_decode(int(rate), _p(x, C.c_float), C.c_size_t(len(x)), int(num_codewords), _p(out, C.c_uint8), C.c_size_t(len(out)),
+                             _p(info, C.c_int32))
+    assert 0 <= n <= len(out), n
+    return out[:n].copy(), info

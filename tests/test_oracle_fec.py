@@ -138,3 +138,66 @@ def test_vs_reference_random(rate):
     assert (a[0] == b[0]).all() and a[1:] == b[1:]
     a, b = R.ldpc_decode_soft(rate, mb[:77], max_iter=7), O.ldpc_decode_soft(rate, mb[:77], max_iter=7)
     assert (a[0] == b[0]).all() and a[1:] == b[1:]
+
+
+# ---------------------------------------------------------------- protocol-v2 multi-codeword frames
+def test_golden_v2_frames(golden):
+    """encodeFrameWithLDPC and RxPipeline::decodeFrame restated in the oracle, against vectors produced by the unmodified reference."""
+    g = golden["frame"]
+    n = int(g["count"][0])
+    for i in range(n):
+        rate = int(g[f"f{i}_rate"][0])
+        cws = O.frame_encode(rate, g[f"f{i}_frame"])
+        assert cws.shape == g[f"f{i}_codewords"].shape and (cws == g[f"f{i}_codewords"]).all(), i
+        out, info = O.frame_decode(rate, g[f"f{i}_llr"], int(g[f"f{i}_ncw"][0]))
+        assert (info == g[f"f{i}_info"]).all() and len(out) == len(g[f"f{i}_out"]) and (out == g[f"f{i}_out"]).all(), (i, info)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("rate", RATES)
+def test_v2_frames_vs_reference(rate):
+    if not R.available():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    import v2frames as V
+    rng = np.random.default_rng(77 + rate)
+    seen = set()
+    for plen in (0, 1, 5, 40, 200, 700):
+        fr = R.data_frame_serialize(rate, rng.integers(0, 256, plen, dtype=np.uint8))
+        mine = V.data_frame(fr[17:17 + plen], rate, seq=7, src_hash=int.from_bytes(bytes(fr[6:9]), "big"), dst_hash=int.from_bytes(bytes(fr[9:12]), "big"))
+        assert len(mine) == len(fr) and (mine == fr).all(), plen          # the GPU tests' frame builder == DataFrame::serialize
+        rc, oc = R.frame_encode(rate, fr), O.frame_encode(rate, fr)
+        assert rc.shape == oc.shape and (rc == oc).all() and len(rc) == V.codewords_for(plen, rate), plen
+        for flip in (0.0, 0.03, 0.12):
+            l = V.codeword_llrs(rc, rng, flip)
+            (rf, ri), (of, oi) = R.frame_decode(rate, l), O.frame_decode(rate, l)
+            assert (ri == oi).all() and len(rf) == len(of) and (rf == of).all(), (plen, flip, ri, oi)
+            seen.add((int(ri[0]), int(ri[3]) > 0, int(ri[4]) > 0))
+            if flip == 0.0:
+                assert ri[0] == 1 and (rf == fr).all()
+        if len(rc) > 1:                                                    # fewer codewords than TOTAL_CW: waiting
+            l = V.codeword_llrs(rc[:-1], rng)
+            (rf, ri), (of, oi) = R.frame_decode(rate, l), O.frame_decode(rate, l)
+            assert (ri == oi).all() and ri[0] == 0 and ri[4] == len(rc) and len(rf) == len(of) == 0
+    assert (1, False, True) in seen and any(not s[0] for s in seen)
+    # control frame, corrupted control CRC, corrupted header CRC, wrong magic, CW1 without its 0xD5 marker (legacy fallback)
+    c = R.control_frame_serialize()
+    assert (V.control_frame(src_hash=int.from_bytes(bytes(c[6:9]), "big"), dst_hash=int.from_bytes(bytes(c[9:12]), "big"),
+                            seq=int.from_bytes(bytes(c[4:6]), "big"), payload=bytes(c[12:18]), flags=int(c[3])) == c).all()
+    fr = V.data_frame(rng.integers(0, 256, 90, dtype=np.uint8), rate)
+    bad_h, bad_m, bad_c = fr.copy(), fr.copy(), c.copy()
+    bad_h[16] ^= 0x40
+    bad_m[1] = 0x4D
+    bad_c[19] ^= 1
+    for f in (c, bad_c, bad_h, bad_m):
+        l = V.codeword_llrs(O.frame_encode(rate, f), rng)
+        (rf, ri), (of, oi) = R.frame_decode(rate, l), O.frame_decode(rate, l)
+        assert (ri == oi).all() and len(rf) == len(of) and (rf == of).all(), (ri, oi)
+    cws = O.frame_encode(rate, fr)
+    bpc = V.BYTES_PER_CW[rate]
+    legacy = np.zeros(bpc, np.uint8)
+    legacy[:] = rng.integers(0, 256, bpc, dtype=np.uint8)
+    legacy[0] = 0x11
+    cws[1] = O.ldpc_encode(rate, legacy)
+    l = V.codeword_llrs(cws, rng)
+    (rf, ri), (of, oi) = R.frame_decode(rate, l), O.frame_decode(rate, l)
+    assert (ri == oi).all() and ri[0] == 1 and len(rf) == len(of) and (rf == of).all()
