@@ -76,6 +76,8 @@ PU_API void pu_destroy(pu_ctx* ctx);
 PU_API int pu_device_sm_count(const pu_ctx* ctx);
 PU_API pu_status pu_synchronize(pu_ctx* ctx, void* stream);
 PU_API uint64_t pu_kernel_launches(const pu_ctx* ctx);  /* kernels launched through this context so far */
+/* bytes copied host->device / device->host by pu_receive_decode_batch(PU_MEM_HOST) through this context so far */
+PU_API void pu_transfer_bytes(const pu_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 /* ---------------------------------------------------------------- LDPC decoder
  * Replaces ultra::LDPCDecoder (include/ultra/fec.hpp:48-77; src/fec/ldpc_decoder.cpp). */

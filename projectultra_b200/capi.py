@@ -106,6 +106,13 @@ class Context:
     def kernel_launches(self):
         return int(lib().pu_kernel_launches(self._h))
 
+    @property
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes moved so far by pu_receive_decode_batch(PU_MEM_HOST) through this context."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        lib().pu_transfer_bytes(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def synchronize(self):
         check(lib().pu_synchronize(self._h, None))
 

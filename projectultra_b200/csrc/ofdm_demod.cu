@@ -1516,3 +1516,22 @@ pu_status pu_ofdm_presynced_debug(pu_ofdm* h, const float* samples, size_t L, in
 }  // extern "C"
 
 pu_ctx* pu_ofdm_context(pu_ofdm* h) { return h ? h->ctx : nullptr; }
+
+// Which samples of a presynced frame the demodulation kernel reads when a zero-CFO call takes the ofdm_diff512 path (launch_ofdm):
+// symbols [first, n_symbols), samples [cp, cp + nfft) of each.  The host-buffer pipeline (linksim.cu) copies only those.  Returns
+// false when the call would take another kernel (which may read anything).
+bool pu_ofdm_diff512_window(pu_ofdm* h, const float* d_samples, size_t B, size_t L, int training, int* first, int* n_symbols, int* sym_len,
+                            int* cp, int* nfft) {
+    if (!h || getenv("PU_OFDM_NO_PACKED512")) return false;
+    const pu::OfdmPlan& p = h->plan;
+    const int ns = static_cast<int>(L / p.sym_len);
+    if (ns < 1 || static_cast<size_t>(ns) * p.sym_len != L) return false;
+    if (h->ensure_nco(ns) != PU_OK) return false;
+    if (!pu::ofdm_diff_supported(h->dev, ns, training) || !pu::ofdm_diff512_supported(h->dev, ns, training, d_samples, L, B)) return false;
+    *first = training > 0 ? training - 1 : 0;
+    *n_symbols = ns;
+    *sym_len = p.sym_len;
+    *cp = h->dev.cp;
+    *nfft = p.nfft;
+    return true;
+}

@@ -130,4 +130,9 @@ pu_status pu_synchronize(pu_ctx* c, void* stream) {
 
 uint64_t pu_kernel_launches(const pu_ctx* c) { return c ? c->launches.load() : 0; }
 
+void pu_transfer_bytes(const pu_ctx* c, uint64_t* h2d, uint64_t* d2h) {
+    if (h2d) *h2d = c ? c->h2d_bytes.load() : 0;
+    if (d2h) *d2h = c ? c->d2h_bytes.load() : 0;
+}
+
 }  // extern "C"

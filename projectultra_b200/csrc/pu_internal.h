@@ -60,6 +60,7 @@ struct pu_ctx {
     int cc_major = 0, cc_minor = 0;
     cudaStream_t stream = nullptr;  // context-owned stream used when the caller passes NULL
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};   // bytes moved by the host-buffer pipeline (pu_receive_decode_batch, PU_MEM_HOST)
     // staging for PU_MEM_HOST calls
     pu::Buffer d_in, d_out, d_aux, h_in, h_out;
     pu::PipeSlot pipe[2];

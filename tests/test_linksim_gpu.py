@@ -99,6 +99,30 @@ def test_host_buffer_path_matches_device_path():
     b = linksim.receive_decode(sim.ofdm, sim.ldpc, rx.cpu().numpy())
     for u, v in zip(a, b):
         assert (u.cpu().numpy() == v).all()
+    # pinned host buffers are DMA'd in place, and for zero-CFO 512-FFT differential frames only the FFT windows of the symbols behind
+    # the first training symbol cross PCIe (12 x 512 of 7 332 samples): poison everything else -- results must not change
+    B, L = rx.shape
+    pinned = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+    pinned.copy_(rx)
+    t0 = ctx.transfer_bytes
+    c = linksim.receive_decode(sim.ofdm, sim.ldpc, pinned.numpy())
+    t1 = ctx.transfer_bytes
+    for u, v in zip(a, c):
+        assert (u.cpu().numpy() == v).all()
+    assert t1[0] - t0[0] == B * 12 * 512 * 4 and t1[1] > t0[1]
+    poisoned = pinned.clone().view(B, 13, 564)
+    poisoned[:, 0, :] = float("nan")
+    poisoned[:, :, :48] = float("nan")
+    poisoned[:, :, 560:] = float("nan")
+    pp = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+    pp.copy_(poisoned.view(B, L))
+    d = linksim.receive_decode(sim.ofdm, sim.ldpc, pp.numpy())
+    for u, v in zip(a, d):
+        assert (u.cpu().numpy() == v).all()
+    # a call with a CFO takes the general kernel and copies whole frames
+    t0 = ctx.transfer_bytes
+    linksim.receive_decode(sim.ofdm, sim.ldpc, pinned.numpy(), cfo_hz=np.full(B, 0.5, np.float32))
+    assert ctx.transfer_bytes[0] - t0[0] >= B * L * 4
     del ctx
 
 

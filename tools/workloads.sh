@@ -10,6 +10,7 @@ python tools/acquire_quick_bench.py 8192 > $OUT/acquire.log 2>&1
 python tools/dpsk_acquire_quick_bench.py 2048 > $OUT/dpsk_acquire.log 2>&1
 python tools/chirp_quick_bench.py 2048 > $OUT/chirp.log 2>&1
 python tools/chirp_quick_bench.py 2048 mcdpsk > $OUT/chirp_mcdpsk.log 2>&1
+python tools/frame_quick_bench.py 65536 > $OUT/frames.log 2>&1
 python - > $OUT/tx.log 2>&1 <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())
@@ -38,6 +39,7 @@ echo; echo "### Acquisition (config 1 as literally specified), 8 192 frames of 1
 echo; echo "### DPSK Barker acquisition (config 4 as literally specified), 2 048 frames of 139 392 samples (tools/dpsk_acquire_quick_bench.py)"; echo '```'; cat $OUT/dpsk_acquire.log; echo '```'
 echo; echo "### Dual-chirp synchronisation + presynced demodulation of OFDM_CHIRP frames (tools/chirp_quick_bench.py)"; echo '```'; cat $OUT/chirp.log; echo '```'
 echo; echo "### Dual-chirp synchronisation + Hilbert-FIR correction + processGotChirp of MC-DPSK frames (tools/chirp_quick_bench.py B mcdpsk)"; echo '```'; cat $OUT/chirp_mcdpsk.log; echo '```'
+echo; echo "### Protocol-v2 multi-codeword frames: RxPipeline::decodeFrame for 65 536 five-codeword R1/2 frames (tools/frame_quick_bench.py)"; echo '```'; cat $OUT/frames.log; echo '```'
 echo; echo "### Transmitter (pu_ofdm_tx_batch)"; echo '```'; cat $OUT/tx.log; echo '```'
 } > $OUT/workloads.md
 cat $OUT/workloads.md | tail -40
