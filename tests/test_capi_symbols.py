@@ -56,6 +56,18 @@ def test_host_encoder_matches_oracle(capi, rate):
         assert (capi.ldpc_encode(rate, data) == O.ldpc_encode(rate, data)).all()
 
 
+@pytest.mark.parametrize("rate", [0, 1, 2, 3, 4, 5, 6])
+def test_host_frame_encoder_matches_oracle(capi, rate):
+    """pu_frame_encode == v2::encodeFrameWithLDPC (the oracle's restatement is pinned to the reference in test_oracle_fec.py);
+    R1/3 and R7/8 take the table's 27 / 20 bytes per codeword with the decoder's R1/2 fallback dimensions."""
+    import v2frames as V
+    rng = np.random.default_rng(60 + rate)
+    for plen in (0, 1, 21, 100, 333):
+        fr = V.data_frame(rng.integers(0, 256, plen, dtype=np.uint8), min(rate, 5))
+        a, b = capi.frame_encode(rate, fr), O.frame_encode(rate, fr)
+        assert a.shape == b.shape and (a == b).all(), (rate, plen)
+
+
 def test_host_interleaver_tables_match_oracle(capi):
     x = np.arange(648, dtype=np.float32)
     for bps in (30, 60, 90, 118, 220, 708):
