@@ -153,12 +153,22 @@ class LinkSim:
             rate = capi.R1_4 if code_rate is None else code_rate          # tools/test_dpsk_snr.cpp:28-29
             self.demod = capi.DpskDemodulator(ctx, cfg)
             self.data_start = 39 * cfg.samples_per_symbol                 # Barker-13 x 3 (dpsk.hpp:202-204)
+            self.layout = "presynced"
             build = lambda coded: capi.dpsk_tx(cfg, coded, 0)
         elif isinstance(cfg, capi.McDpskConfig):
             self.kind = "mcdpsk"
             rate = capi.R1_2 if code_rate is None else code_rate
             self.demod = capi.McDpskDemodulator(ctx, cfg)
-            build = lambda coded: capi.mcdpsk_tx(cfg, coded)
+            # layout "chirp": MC-DPSK frames as transmitted = ChirpSync::generate() + training + reference + data, received through
+            # MCDPSKWaveform's detectSync -> setFrequencyOffset -> process (tools/test_iwaveform.cpp:127-160); a frame without chirp
+            # or with fewer than 648 soft bits is lost
+            assert layout in ("presynced", "chirp")
+            self.layout = layout
+            if layout == "chirp":
+                chirp = capi.chirp_generate(float(cfg.sample_rate), 0.0)
+                build = lambda coded: np.concatenate([chirp, capi.mcdpsk_tx(cfg, coded)])
+            else:
+                build = lambda coded: capi.mcdpsk_tx(cfg, coded)
         else:
             raise TypeError("cfg must be a capi.ModemConfig, capi.DpskConfig or capi.McDpskConfig")
         self.code_rate = rate
@@ -205,6 +215,10 @@ class LinkSim:
             return out[0]
         if self.kind == "dpsk":
             return self.demod.demod_soft_batch(rx, self.data_start, 1, llr_stride=648, llr=llr)
+        if self.kind == "mcdpsk" and self.layout == "chirp":
+            out = self.demod.chirp_receive_batch(rx, llr_stride=648)
+            self.last_n_llr, self.last_sync, self.last_cfo = out[1], out[2], out[4]
+            return out[0]
         return self.demod.demod_soft_batch(rx, llr_stride=648, llr=llr, want_cfo=False)[0]
 
     def noise_std_table(self, snr_points):
@@ -277,7 +291,7 @@ class LinkSim:
             info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
         else:
             info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))
-            if self.kind == "dpsk" and self.acquire:
+            if (self.kind == "dpsk" and self.acquire) or (self.kind == "mcdpsk" and self.layout == "chirp"):
                 ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
         count_errors(self.ctx, info, ok, iters, self.payload_pool, batch["tx_index"], batch["bins"], self.payload_bytes,
                      counters)

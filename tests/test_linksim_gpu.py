@@ -356,3 +356,45 @@ def test_linksim_ofdm_chirp_with_dual_chirp_sync(chan):
     # interference), so only the AWGN run is required to be error free at 22 dB; the fading run checks parity frame by frame
     assert chan != "awgn" or c[-1, 1] == 0
     del ctx
+
+
+@pytest.mark.parametrize("case", [(8, "awgn", (-8.0, 0.0, 6.0, 14.0)), (13, "good", (-4.0, 4.0, 12.0, 20.0))])
+def test_linksim_mcdpsk_behind_dual_chirp(case):
+    """MC-DPSK as transmitted: dual chirp + training + reference + DQPSK data, R1/4, received as
+    tools/test_iwaveform.cpp:127-160 does through MCDPSKWaveform (detectSync -> setFrequencyOffset -> process -> getSoftBits ->
+    decodeSoft): every frame's sync result, soft-bit count, ok flag, iteration count and bytes identical to the oracle on the
+    identical channel outputs (LLR words are bit-identical on this path, so the decoder's results are too)."""
+    import torch
+    from projectultra_b200 import capi, linksim
+    nc, chan, snrs = case
+    ctx = capi.Context(0)
+    cfg = capi.mcdpsk_config(nc, 2)
+    sim = linksim.LinkSim(ctx, cfg, chan, payload_bytes=20, pool=3, code_rate=capi.R1_4, layout="chirp")
+    nsym = 9 + -(-648 // (2 * nc))
+    assert sim.L == 57600 + nsym * 512
+    trials = 3
+    si = np.repeat(np.arange(len(snrs)), trials)
+    tr = np.tile(np.arange(trials), len(snrs))
+    batch = sim.make_batch(list(snrs), si, tr)
+    counters = torch.zeros((len(snrs), 6), dtype=torch.int64, device="cuda")
+    rx, info, ok, iters = sim.run_batch(batch, counters, keep=True)
+    torch.cuda.synchronize()
+    rx_h = rx.cpu().numpy()
+    n_llr, sync, cfo = sim.last_n_llr.cpu().numpy(), sim.last_sync.cpu().numpy(), sim.last_cfo.cpu().numpy()
+    ok_h, info_h, it_h = ok.cpu().numpy(), info.cpu().numpy(), iters.cpu().numpy()
+    decoded = 0
+    for b in range(len(rx_h)):
+        ol, oi, of, oa = O.mcdpsk_chirp_receive(nc, rx_h[b])
+        assert (sync[b] == oi).all() and int(n_llr[b]) == min(len(ol), 648), (b, sync[b], oi, n_llr[b], len(ol))
+        assert np.float32(cfo[b]).view(np.uint32) == np.float32(oa).view(np.uint32), (b, cfo[b], oa)
+        if len(ol) >= 648:
+            ci, cok, cit = O.ldpc_decode_batch(R.R1_4, ol[None, :648].copy())
+            assert ok_h[b] == cok[0] and it_h[b] == cit[0] and (info_h[b] == ci[0]).all(), b
+            decoded += int(cok[0])
+        else:
+            assert ok_h[b] == 0
+    c = counters.cpu().numpy()
+    # frame-by-frame parity is the point; over the fading channel the 5 Hz false-positive rule and deep fades cost frames
+    assert c[:, 0].tolist() == [trials] * len(snrs) and decoded >= (trials if chan == "awgn" else 1)
+    assert chan != "awgn" or c[-1, 1] == 0
+    del ctx
