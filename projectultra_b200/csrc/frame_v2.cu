@@ -105,11 +105,6 @@ __global__ void __launch_bounds__(128) frame_assemble_kernel(const uint8_t* __re
     }
 }
 
-struct FrameDevMem {
-    void* p = nullptr;
-    ~FrameDevMem() { if (p) cudaFree(p); }
-};
-
 }  // namespace pu
 
 extern "C" {
@@ -124,31 +119,35 @@ pu_status pu_frame_decode_batch(pu_ctx* ctx, pu_ldpc* dec, const float* llr, siz
     cudaStream_t st = pu::pick_stream(ctx, stream, space);
     const int rate = pu_ldpc_rate(dec), kbytes = (pu_ldpc_info_bits(dec) + 7) / 8, bpc = pu::frame_bytes_per_codeword(rate);
     const size_t ncw = B * num_codewords;
-    pu::FrameDevMem dl, dbytes, dok, dit, dout, dlen, dinfo;
+    // grow-only scratch on the context (the calling convention is one thread per context, as for the reference's objects)
+    pu_status s;
     const float* d_llr = llr;
     uint8_t* d_out = frame_out;
     int32_t* d_len = frame_len;
     int32_t* d_info = info;
+    const size_t out_off_len = ((B * frame_cap + 15) / 16) * 16, out_off_info = out_off_len + B * sizeof(int32_t);
     if (space == PU_MEM_HOST) {
-        PU_CUDA_TRY(cudaMalloc(&dl.p, ncw * PU_LDPC_N * sizeof(float)));
-        PU_CUDA_TRY(cudaMalloc(&dout.p, B * frame_cap));
-        PU_CUDA_TRY(cudaMalloc(&dlen.p, B * sizeof(int32_t)));
-        PU_CUDA_TRY(cudaMalloc(&dinfo.p, B * 5 * sizeof(int32_t)));
-        PU_CUDA_TRY(cudaMemcpyAsync(dl.p, llr, ncw * PU_LDPC_N * sizeof(float), cudaMemcpyHostToDevice, st));
-        PU_CUDA_TRY(cudaMemsetAsync(dout.p, 0, B * frame_cap, st));
-        d_llr = static_cast<const float*>(dl.p); d_out = static_cast<uint8_t*>(dout.p);
-        d_len = static_cast<int32_t*>(dlen.p); d_info = static_cast<int32_t*>(dinfo.p);
+        if ((s = ctx->f_llr.reserve(ncw * PU_LDPC_N * sizeof(float))) != PU_OK) return s;
+        if ((s = ctx->f_out.reserve(out_off_info + B * 5 * sizeof(int32_t))) != PU_OK) return s;
+        PU_CUDA_TRY(cudaMemcpyAsync(ctx->f_llr.ptr, llr, ncw * PU_LDPC_N * sizeof(float), cudaMemcpyHostToDevice, st));
+        PU_CUDA_TRY(cudaMemsetAsync(ctx->f_out.ptr, 0, B * frame_cap, st));
+        d_llr = static_cast<const float*>(ctx->f_llr.ptr);
+        d_out = static_cast<uint8_t*>(ctx->f_out.ptr);
+        d_len = reinterpret_cast<int32_t*>(d_out + out_off_len);
+        d_info = reinterpret_cast<int32_t*>(d_out + out_off_info);
     }
-    PU_CUDA_TRY(cudaMalloc(&dbytes.p, ncw * static_cast<size_t>(kbytes)));
-    PU_CUDA_TRY(cudaMalloc(&dok.p, ncw));
-    PU_CUDA_TRY(cudaMalloc(&dit.p, ncw * sizeof(int32_t)));
-    pu_status s = pu_ldpc_decode_batch(dec, d_llr, PU_LDPC_N, ncw, static_cast<uint8_t*>(dbytes.p), static_cast<size_t>(kbytes),
-                                       static_cast<uint8_t*>(dok.p), static_cast<int32_t*>(dit.p), PU_MEM_DEVICE, st);
+    if ((s = ctx->f_bytes.reserve(ncw * static_cast<size_t>(kbytes))) != PU_OK) return s;
+    if ((s = ctx->f_ok.reserve(ncw)) != PU_OK) return s;
+    if ((s = ctx->f_iters.reserve(ncw * sizeof(int32_t))) != PU_OK) return s;
+    uint8_t* d_bytes = static_cast<uint8_t*>(ctx->f_bytes.ptr);
+    uint8_t* d_ok = static_cast<uint8_t*>(ctx->f_ok.ptr);
+    s = pu_ldpc_decode_batch(dec, d_llr, PU_LDPC_N, ncw, d_bytes, static_cast<size_t>(kbytes), d_ok, static_cast<int32_t*>(ctx->f_iters.ptr),
+                             PU_MEM_DEVICE, st);
     if (s != PU_OK) return s;
     const int warps = 4;
     (void)cudaGetLastError();
     pu::frame_assemble_kernel<<<static_cast<unsigned>((B + warps - 1) / warps), warps * 32, 0, st>>>(
-        static_cast<const uint8_t*>(dbytes.p), static_cast<size_t>(kbytes), static_cast<const uint8_t*>(dok.p), static_cast<int>(B),
+        d_bytes, static_cast<size_t>(kbytes), d_ok, static_cast<int>(B),
         static_cast<int>(num_codewords), bpc, kbytes, d_out, frame_cap, d_len, d_info);
     ctx->launches.fetch_add(1);
     PU_CUDA_TRY(cudaGetLastError());
@@ -157,7 +156,7 @@ pu_status pu_frame_decode_batch(pu_ctx* ctx, pu_ldpc* dec, const float* llr, siz
         PU_CUDA_TRY(cudaMemcpyAsync(frame_len, d_len, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PU_CUDA_TRY(cudaMemcpyAsync(info, d_info, B * 5 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
-    PU_CUDA_TRY(cudaStreamSynchronize(st));           // the scratch buffers above are freed on return
+    PU_CUDA_TRY(cudaStreamSynchronize(st));           // results are complete on return (the scratch is reused by the next call)
     return PU_OK;
 }
 

@@ -110,6 +110,7 @@ void pu_destroy(pu_ctx* c) {
     c->d_aux.release();
     c->h_in.release();
     c->h_out.release();
+    c->f_llr.release(); c->f_bytes.release(); c->f_ok.release(); c->f_iters.release(); c->f_out.release();
     for (auto& sl : c->pipe) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         sl.d_in.release(); sl.d_llr.release(); sl.d_out.release(); sl.h_in.release(); sl.h_out.release();

@@ -63,6 +63,7 @@ struct pu_ctx {
     std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};   // bytes moved by the host-buffer pipeline (pu_receive_decode_batch, PU_MEM_HOST)
     // staging for PU_MEM_HOST calls
     pu::Buffer d_in, d_out, d_aux, h_in, h_out;
+    pu::Buffer f_llr, f_bytes, f_ok, f_iters, f_out;   // scratch of pu_frame_decode_batch (grow-only, reused across calls)
     pu::PipeSlot pipe[2];
     cudaEvent_t pipe_ev = nullptr;
 };
