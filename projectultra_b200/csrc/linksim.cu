@@ -153,16 +153,26 @@ pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const float* sam
         cudaStream_t ls = sl.stream;
         float* din = static_cast<float*>(sl.d_in.ptr);
         const float* src = samples + off * L;
-        if (!src_pinned) {
-            std::memcpy(sl.h_in.ptr, src, nb * L * sizeof(float));
-            src = static_cast<const float*>(sl.h_in.ptr);
-        }
         // Zero-CFO 512-FFT differential frames go to the ofdm_diff512 kernel, which reads only the FFT windows of the symbols behind
         // the first training symbol: one strided (3-D) DMA moves exactly those (M1: 12 x 512 of 7 332 samples = 84 % of the frame);
         // the cyclic prefixes, guards and the first LTS symbol never cross PCIe.  Anything else is copied whole.
         int w_first = 0, w_nsym = 0, w_sym = 0, w_cp = 0, w_nfft = 0;
-        if (windowed_ok && !cfo_hz && !cfo_phase &&
-            pu_ofdm_diff512_window(ofdm, din, nb, L, training_symbols, &w_first, &w_nsym, &w_sym, &w_cp, &w_nfft)) {
+        const bool windowed = windowed_ok && !cfo_hz && !cfo_phase &&
+                              pu_ofdm_diff512_window(ofdm, din, nb, L, training_symbols, &w_first, &w_nsym, &w_sym, &w_cp, &w_nfft);
+        if (!src_pinned) {   // pageable source: stage through the lane's pinned buffer (only the windows, when windowed)
+            float* stage = static_cast<float*>(sl.h_in.ptr);
+            if (windowed) {
+                for (size_t b = 0; b < nb; ++b)
+                    for (int sy = w_first; sy < w_nsym; ++sy) {
+                        const size_t o = b * L + static_cast<size_t>(sy) * w_sym + w_cp;
+                        std::memcpy(stage + o, src + o, static_cast<size_t>(w_nfft) * sizeof(float));
+                    }
+            } else {
+                std::memcpy(stage, src, nb * L * sizeof(float));
+            }
+            src = stage;
+        }
+        if (windowed) {
             cudaMemcpy3DParms c3{};
             c3.srcPtr = make_cudaPitchedPtr(const_cast<float*>(src), static_cast<size_t>(w_sym) * sizeof(float), static_cast<size_t>(w_sym) * sizeof(float), static_cast<size_t>(w_nsym));
             c3.dstPtr = make_cudaPitchedPtr(din, static_cast<size_t>(w_sym) * sizeof(float), static_cast<size_t>(w_sym) * sizeof(float), static_cast<size_t>(w_nsym));
