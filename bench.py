@@ -135,7 +135,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -151,33 +151,48 @@ class ClockSampler:
             self.p = None
 
     def stop(self, gpus):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
-            return out
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.close()
+        self.p = None
+        return self.window(None, None, gpus)
+
+    def window(self, t0, t1, gpus):
+        """Median SM clock / throttle reasons of the samples taken between wall-clock times t0 and t1 (None = all)."""
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.f is not None and not self.f.closed:
+            self.f.flush()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        with open(self.path) as f:
-            for ln in f:
-                c = [v.strip() for v in ln.split(",")]
-                if len(c) < 9:
-                    continue
-                try:
-                    if int(c[0]) >= gpus:
+        try:
+            lines = open(self.path).read().splitlines()
+        except OSError:
+            return out
+        for ln in lines:
+            c = [v.strip() for v in ln.split(",")]
+            if len(c) < 10:
+                continue
+            try:
+                if t0 is not None:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t0 or ts > t1:
                         continue
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
-                    power.append(float(c[3]))
-                except ValueError:
+                if int(c[1]) >= gpus:
                     continue
-                for n, v in zip(names, c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                sm.append(float(c[2]))
+                mx.append(float(c[3]))
+                power.append(float(c[4]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[6:10]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
         if sm:
             sm.sort()
             out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
@@ -186,6 +201,87 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ this repo's arm
+# BASELINE.json configs behind --workload.  "m1" is the headline the metric is quoted on (the driver's default run); the others
+# are the same contract on configs 2-4 so that their numbers come from this file and not from ad-hoc tools.
+WORKLOADS = {
+    "m1": dict(kind="ofdm", cfg=(48000, 1500, 512, 30, 1, 4, 2, 0, "DQPSK", "R1_2", 40.0, 0.0), rate="R1_2", payload=40,
+               channel="awgn", snr=[float(s) for s in range(-4, 9)], info_bits=324,
+               name="M1 OFDM 512-FFT DQPSK R1/2 presynced (2 LTS + 11 data symbols, 7332 samples/frame), AWGN sweep -4..8 dB"),
+    "m3": dict(kind="ofdm", cfg=(48000, 1500, 1024, 59, 1, 0, 4, 1, "QAM32", "R3_4", 40.0, 0.0), rate="R3_4", payload=60,
+               channel="good", snr=[float(s) for s in range(8, 21)], info_bits=486,
+               name="config 3: M3 OFDM 1024-FFT NVIS 32QAM R3/4 pilots/4 presynced, Watterson 'good' channel seeds, sweep 8..20 dB"),
+    "dpsk": dict(kind="dpsk", rate="R1_4", payload=20, channel="poor", snr=[float(s) for s in range(-11, 18, 2)], info_bits=162,
+                 name="config 4: single-carrier DQPSK 125 baud R1/4 (Barker preamble, genie data start), Watterson 'poor' channel, "
+                      "FER-vs-SNR sweep -11..17 dB"),
+}
+
+
+class Timer:
+    """CUDA-event stopwatch on torch's current stream (the stream every C-ABI call of this file launches on)."""
+
+    def __init__(self, torch):
+        self.t = torch
+        self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        self.b.record()
+
+    def ms(self):
+        self.t.cuda.synchronize()
+        return self.a.elapsed_time(self.b)
+
+
+def measured_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback of B200_PROFILING.md"
+
+
+def traffic_of(kernel):
+    """Per-frame DRAM bytes of `kernel` from the committed ncu --set full capture (profiles/traffic.json: dram__bytes_read.sum +
+    dram__bytes_write.sum of one launch / frames of that launch).  A constant of the last profiled build, not of this run."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None, None
+    with open(tpath) as f:
+        tj = json.load(f)
+    e = tj.get("kernels", {}).get(kernel)
+    return (e["dram_bytes_per_unit"], e.get("source")) if e else (None, None)
+
+
+def bind_near_cpus(local):
+    """One process per GPU, bound to the CPUs NVML reports next to that GPU (the end-to-end leg streams GBs of pinned host memory
+    per step and first-touch places those pages on the allocating thread's NUMA node).  When every GPU reports the same CPU set
+    (virtualised hosts: the driver's 8-GPU box shows 0-31 / NUMA 0 for all) split that set evenly between the local ranks instead,
+    so the ranks' staging threads at least do not share cores."""
+    before = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        n_local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        sets = []
+        for g in range(max(n_local, local + 1)):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g), (ncpu + 63) // 64)
+            sets.append(frozenset(c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1) & frozenset(before))
+        near = sets[local]
+        if near and n_local > 1 and all(x == near for x in sets[:n_local]):
+            cpus = sorted(near)
+            per = max(1, len(cpus) // n_local)
+            near = frozenset(cpus[local * per:(local + 1) * per]) or near
+        if near:
+            os.sched_setaffinity(0, near)
+    except Exception:   # noqa: BLE001  (no NVML / restricted container: keep the inherited affinity)
+        pass
+    return before
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -200,57 +296,54 @@ def run_ours(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # one process per GPU, bound to the CPUs next to that GPU: the end-to-end leg streams 1.5 GB of pinned host memory per
-    # step and per GPU, and first-touch places those pages on the NUMA node of the thread that allocates them
-    cpus_before = os.sched_getaffinity(0)
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        ncpu = os.cpu_count() or 1
-        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local), (ncpu + 63) // 64)
-        near = {c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1} & set(cpus_before)
-        if near:
-            os.sched_setaffinity(0, near)
-    except Exception:   # noqa: BLE001  (no NVML / restricted container: keep the inherited affinity)
-        pass
+    cpus_before = bind_near_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = capi.Context(local)
-    cfg = capi.ModemConfig(48000, 1500, 512, 30, 1, 4, 2, 0, capi.DQPSK, capi.R1_2, 40.0, 0.0)
-    sim = linksim.LinkSim(ctx, cfg, "awgn", payload_bytes=PAYLOAD_BYTES, pool=POOL)
-    assert sim.L == FRAME_SAMPLES
-    fpp = args.frames_per_point
-    n_snr = len(SNR_POINTS)
+    if args.workload == "ldpc":
+        return run_ldpc(args, ctx, dev, world, rank)
+    wl = WORKLOADS[args.workload]
+    snr_points = wl["snr"]
+    rate = getattr(capi, wl["rate"])
+    if wl["kind"] == "ofdm":
+        c = list(wl["cfg"])
+        c[8], c[9] = getattr(capi, c[8]), getattr(capi, c[9])
+        cfg = capi.ModemConfig(*c)
+        sim = linksim.LinkSim(ctx, cfg, wl["channel"], payload_bytes=wl["payload"], pool=POOL, code_rate=rate, precision=args.precision)
+    else:
+        cfg = capi.dpsk_config(1, 384)       # DQPSK, 125 baud at 48 kHz (DPSKConfig defaults, tools/test_dpsk_snr.cpp:28-52)
+        sim = linksim.LinkSim(ctx, cfg, wl["channel"], payload_bytes=wl["payload"], pool=16, code_rate=rate, peak=0.5)
+    if args.workload == "m1":
+        assert sim.L == FRAME_SAMPLES
+    L = sim.L
+    fpp = args.frames_per_point if args.workload == "m1" else max(1, args.frames_per_point * FRAME_SAMPLES // L)
+    n_snr = len(snr_points)
     B = fpp * n_snr
+    pb = wl["payload"]
     # this rank's frames: trials [rank*fpp, (rank+1)*fpp) of every SNR point, trial-major so SNR points interleave
     trials = np.repeat(np.arange(rank * fpp, (rank + 1) * fpp, dtype=np.int64), n_snr)
     si = np.tile(np.arange(n_snr, dtype=np.int64), fpp)
-    batch = sim.make_batch(SNR_POINTS, si, trials)
-    rx = linksim.channel_apply(ctx, sim.ch, sim.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"])
-    llr = torch.zeros((B, 648), dtype=torch.float32, device=dev)
-    info = torch.empty((B, sim.ldpc.info_bytes), dtype=torch.uint8, device=dev)
-    ok = torch.empty(B, dtype=torch.uint8, device=dev)
-    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    batch = sim.make_batch(snr_points, si, trials)
+    rx = sim.make_rx(batch)
+    bufs = dict(llr=torch.zeros((B, 648), dtype=torch.float32, device=dev),
+                info=torch.empty((B, sim.ldpc.info_bytes), dtype=torch.uint8, device=dev),
+                ok=torch.empty(B, dtype=torch.uint8, device=dev), iters=torch.empty(B, dtype=torch.int32, device=dev))
     counters = torch.zeros((n_snr, 6), dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
 
     def step(ev=None):
-        if ev is not None:
-            ev[0].record()
-        sim.ofdm.presynced_batch(rx, 2, llr=llr, want_aux=False)
-        if ev is not None:
-            ev[1].record()
-        sim.ldpc.decode_batch(llr, info, ok, iters)
-        if ev is not None:
-            ev[2].record()
-        linksim.count_errors(ctx, info, ok, iters, sim.payload_pool, batch["tx_index"], batch["bins"], PAYLOAD_BYTES, counters)
-        if ev is not None:
-            ev[3].record()
+        sim.receive_count(batch, rx, counters, ev=ev, bufs=bufs)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         step()
@@ -260,95 +353,264 @@ def run_ours(args):
     if sampler:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         sampler.start()
+    # ---- the contract's timed region: EXACTLY --steps steps between two barriers, CUDA events, max over ranks
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = ctx.kernel_launches
     barrier()
-    e0.record()
-    for k in range(args.steps):
-        step(evs[k])
-    linksim.allreduce_counters(counters)          # the path's only collective: once per sweep
-    e1.record()
+    with Timer(torch) as tm:
+        for k in range(args.steps):
+            step(evs[k])
+        linksim.allreduce_counters(counters)          # the path's only collective: once per sweep
     barrier()
     launches = ctx.kernel_launches - n0
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = max_over_ranks(tm.ms())
     ms_demod = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     ms_ldpc = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     ms_count = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
     c = counters.cpu().numpy()
+    demod_kernel = sim.demod.last_kernel if hasattr(sim.demod, "last_kernel") else wl["kind"] + "_demod_kernels"
+    iters_run = float((bufs["iters"].float() + bufs["ok"].float()).clamp(max=50).mean().item())
+
+    # ---- sustained: the same step back to back for >= --sustain-seconds, so that the clocks the part settles at under a long
+    #      run are sampled (the K-step region above is a few tens of ms: a burst)
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms_total / args.steps, 1e-3)) + 1)
+        barrier()
+        mark = time.time()
+        with Timer(torch) as ts:
+            for _ in range(n_sus):
+                step()
+        ms_sus = max_over_ranks(ts.ms())
+        barrier()
+        sustained = {"value": world * B * n_sus / (ms_sus * 1e-3), "unit": UNIT, "steps": n_sus, "seconds": ms_sus * 1e-3,
+                     "ms_per_step": ms_sus / n_sus, "window": [mark, time.time()]}
+
+    # ---- the other precision on the same inputs (OFDM modes with an FMA form): demodulator time + the whole step's counters
+    other = None
+    if wl["kind"] == "ofdm" and demod_kernel in ("ofdm_fast512_kernel", "ofdm_diff512_kernel"):
+        alt = "exact" if sim.ofdm.precision == "fast" else "fast"
+        sim.ofdm.set_precision(alt)
+        c_alt = torch.zeros_like(counters)
+        sim.receive_count(batch, rx, c_alt, bufs=bufs)
+        with Timer(torch) as ta:
+            for _ in range(5):
+                sim.ofdm.presynced_batch(rx, 2, llr_stride=648, llr=bufs["llr"], want_aux=False)
+        ms_alt = ta.ms() / 5
+        other = {"precision": alt, "kernel": sim.ofdm.last_kernel, "ms_per_launch": ms_alt,
+                 "achieved": (4 * L + 4 * 648) * B / (ms_alt * 1e-3) / 1e9,
+                 "fer": [round(float(r[1]) / max(int(r[0]), 1), 5) for r in c_alt.cpu().numpy()],
+                 "frame_error_count_difference": [int(a[1]) * 1 - int(round(b[1] / args.steps)) for a, b in zip(c_alt.cpu().numpy(), c)]
+                 if world == 1 else None}
+        sim.ofdm.set_precision(args.precision)
+
+    # ---- the Monte-Carlo loop itself: channel generation INSIDE the timed region (LinkSim.sweep: descriptors -> channel kernel ->
+    #      demod -> LDPC -> count per batch), on this workload's channel and, for the headline, on Watterson 'good' as well
+    sweeps = {}
+    if args.sweep_batches > 0:
+        for chname in ([wl["channel"]] + (["good"] if args.workload == "m1" else [])):
+            s2 = sim if chname == wl["channel"] else None
+            if s2 is None:
+                s2 = linksim.LinkSim(ctx, cfg, chname, payload_bytes=pb, pool=POOL, code_rate=rate, precision=args.precision)
+            s2.noise_std_table(snr_points)
+            rxb = torch.empty_like(rx)
+            cs = torch.zeros_like(counters)
+            b0 = s2.make_batch(snr_points, si, trials)
+            for _ in range(2):
+                s2.run_batch(b0, cs, rx=rxb)
+            evc = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            evc[0].record(); s2.make_rx(b0, rxb); evc[1].record()
+            torch.cuda.synchronize()
+            ms_ch = evc[0].elapsed_time(evc[1])
+            cs.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.sweep_batches):
+                tr = trials + (k + 1) * world * fpp            # fresh trial indices (fresh seeds) every batch
+                s2.run_batch(s2.make_batch(snr_points, si, tr), cs, rx=rxb)
+            linksim.allreduce_counters(cs)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            kern = "awgn_kernel" if chname == "awgn" else "channel_kernel"
+            sweeps[chname] = {"value": world * B * args.sweep_batches / dt, "unit": UNIT, "batches": args.sweep_batches,
+                              "frames_per_batch_per_gpu": B, "seconds": dt,
+                              "channel_kernel": {"kernel": kern, "ms_per_launch": ms_ch, "bound": "hbm",
+                                                 "algorithmic_bytes_per_frame": 4 * L,
+                                                 "achieved": 4 * L * B / (ms_ch * 1e-3) / 1e9},
+                              "fer": [round(float(r[1]) / max(int(r[0]), 1), 5) for r in cs.cpu().numpy()]}
+            del rxb
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the samples, D2H of the decoded bytes/flags
-    rx_host = torch.empty((B, FRAME_SAMPLES), dtype=torch.float32, pin_memory=True)
-    rx_host.copy_(rx)
-    torch.cuda.synchronize()
-    rx_np = rx_host.numpy()
-    info_h = np.zeros((B, sim.ldpc.info_bytes), np.uint8)
-    ok_h = np.zeros(B, np.uint8)
-    it_h = np.zeros(B, np.int32)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(min(args.warmup, 2)):
-        linksim.receive_decode(sim.ofdm, sim.ldpc, rx_np, info=info_h, ok=ok_h, iters=it_h)
-    barrier()
-    tb0 = ctx.transfer_bytes
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        linksim.receive_decode(sim.ofdm, sim.ldpc, rx_np, info=info_h, ok=ok_h, iters=it_h)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tb1 = ctx.transfer_bytes       # bytes the library actually moved (only the FFT windows of the symbols the kernel reads cross PCIe)
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
-    e2e_matches = bool((info_h == info.cpu().numpy()).all() and (ok_h == ok.cpu().numpy()).all())
+    e2e = None
+    if wl["kind"] == "ofdm":
+        rx_host = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+        rx_host.copy_(rx)
+        torch.cuda.synchronize()
+        rx_np = rx_host.numpy()
+        info_h = np.zeros((B, sim.ldpc.info_bytes), np.uint8)
+        ok_h = np.zeros(B, np.uint8)
+        it_h = np.zeros(B, np.int32)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(min(args.warmup, 2)):
+            linksim.receive_decode(sim.ofdm, sim.ldpc, rx_np, info=info_h, ok=ok_h, iters=it_h)
+        barrier()
+        tb0 = ctx.transfer_bytes
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            linksim.receive_decode(sim.ofdm, sim.ldpc, rx_np, info=info_h, ok=ok_h, iters=it_h)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        tb1 = ctx.transfer_bytes    # bytes the library actually moved (only the FFT windows of the symbols the kernel reads cross PCIe)
+        step()                      # device-path outputs of the same mode for the comparison below
+        torch.cuda.synchronize()
+        e2e_matches = bool((info_h == bufs["info"].cpu().numpy()).all() and (ok_h == bufs["ok"].cpu().numpy()).all())
+        h2d = (tb1[0] - tb0[0]) // e2e_steps
+        e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": world * h2d,
+               "d2h_bytes_per_step": world * (tb1[1] - tb0[1]) // e2e_steps, "steps": e2e_steps,
+               "host_buffer_bytes_per_step": world * B * L * 4, "api": "pu_receive_decode_batch(PU_MEM_HOST)",
+               "matches_device_path": e2e_matches, "h2d_gbs_per_gpu": h2d * e2e_steps / dt / 1e9}
     barrier()
     clocks = sampler.stop(world) if sampler else None
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            with open(peaks_path) as f:
-                peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-        else:
-            peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            if tj.get("ofdm_presynced_kernel_bytes_per_frame"):
-                traffic = tj["ofdm_presynced_kernel_bytes_per_frame"] * B
-        ach = ALG_BYTES_DEMOD * B / (ms_demod * 1e-3) / 1e9
-        demod_kernel = sim.ofdm.last_kernel
-        iters_run = float((iters.float() + ok.float()).clamp(max=50).mean().item())
+        peak, peak_src = measured_peak()
+        alg = 4 * L + 4 * 648
+        ach = alg * B / (ms_demod * 1e-3) / 1e9
+        traffic, traffic_src = traffic_of(demod_kernel)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(base_config(fpp, world), l2="inputs larger than L2: %.0f MB of samples per step per GPU, no flush"
-                               % (B * FRAME_SAMPLES * 4 / 1e6)),
-                "info_bits_per_s": value * INFO_BITS, "gpu_launches": int(launches),
+                "config": dict(base_config(fpp, world) if args.workload == "m1" else
+                               {"workload": "%s x %d frames/point/GPU, demod+demap+LDPC(flooding min-sum, <=50 it)+error count" % (wl["name"], fpp),
+                                "frames_per_step_per_gpu": B, "snr_points_db": [snr_points[0], snr_points[-1], snr_points[1] - snr_points[0]],
+                                "channel": wl["channel"], "payload_bytes": pb,
+                                "parallelism": "frames sharded over %d GPU(s), one counter all-reduce" % world},
+                               l2="inputs larger than L2: %.0f MB of samples per step per GPU, no flush" % (B * L * 4 / 1e6),
+                               precision=("%s (pu_ofdm_set_precision; see `other_precision` for the same inputs through the other arithmetic)"
+                                          % sim.ofdm.precision) if wl["kind"] == "ofdm" else "exact"),
+                "info_bits_per_s": value * wl["info_bits"], "gpu_launches": int(launches),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * (tb1[0] - tb0[0]) // e2e_steps,
-                        "d2h_bytes_per_step": world * (tb1[1] - tb0[1]) // e2e_steps, "steps": e2e_steps,
-                        "host_buffer_bytes_per_step": world * B * FRAME_SAMPLES * 4,
-                        "api": "pu_receive_decode_batch(PU_MEM_HOST)", "matches_device_path": e2e_matches},
                 "roofline": {"kernel": demod_kernel, "bound": "hbm", "achieved": ach, "peak": peak,
-                             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_frame": ALG_BYTES_DEMOD, "ms_per_launch": ms_demod},
+                             "unit": "GB/s", "frac": ach / peak, "traffic": traffic * B if traffic else None,
+                             "traffic_source": traffic_src, "peak_source": peak_src,
+                             "algorithmic_bytes_per_frame": alg, "ms_per_launch": ms_demod},
                 "stages_ms": {demod_kernel: ms_demod, "ldpc_flood_kernel": ms_ldpc, "count_errors_kernel": ms_count},
                 "ldpc": {"codewords_per_s": B / (ms_ldpc * 1e-3), "avg_iterations_run": iters_run,
-                         "edge_updates_per_s": 2 * 1623 * iters_run * B / (ms_ldpc * 1e-3),
-                         "hbm_gbs": ALG_BYTES_LDPC * B / (ms_ldpc * 1e-3) / 1e9},
+                         "edge_updates_per_s": 2 * sim.ldpc.num_edges * iters_run * B / (ms_ldpc * 1e-3),
+                         "hbm_gbs": (4 * 648 + sim.ldpc.info_bytes + 5) * B / (ms_ldpc * 1e-3) / 1e9},
                 "fer": [round(float(r[1]) / max(int(r[0]), 1), 5) for r in c],
                 "frames_counted": int(c[:, 0].sum())}
-        if world == 1 and not args.no_cpu_baseline:
+        if e2e:
+            line["e2e"] = e2e
+        if sustained:
+            w0, w1 = sustained.pop("window")
+            sustained["clocks"] = sampler.window(w0, w1, world) if sampler else None
+            line["sustained"] = sustained
+        if other:
+            other["frac"] = other["achieved"] / peak
+            line["other_precision"] = other
+        if sweeps:
+            for v in sweeps.values():
+                v["channel_kernel"]["frac"] = v["channel_kernel"]["achieved"] / peak
+            line["sweep"] = sweeps
+        if world == 1 and not args.no_cpu_baseline and args.workload == "m1":
             os.sched_setaffinity(0, cpus_before)      # the reference arm uses every host core
             line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_ldpc(args, ctx, dev, world, rank):
+    """BASELINE.json config 2: the LDPC decoder alone on a batch of 1M codewords at R1/4, R1/2, R3/4, R5/6 (BPSK over AWGN at the
+    rate's waterfall: about half of the codewords converge).  A step decodes the four batches once.  The decoder is bound by SM
+    issue / ALU and the shared-memory pipe, not by HBM (north star): `roofline` is the HBM view the contract asks for (tiny by
+    design), `sm` carries edge-message updates/s -- the unit the kernel is optimised in."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from projectultra_b200 import capi
+    B = args.ldpc_codewords
+    rates = [("R1_4", 1.12), ("R1_2", 0.71), ("R3_4", 0.57), ("R5_6", 0.58)]
+    decs, llrs, outs = [], [], []
+    for name, sigma in rates:
+        r = getattr(capi, name)
+        dec = capi.LdpcDecoder(ctx, r)
+        rng = np.random.default_rng(100 + r + 1000 * rank)
+        cws = np.stack([np.unpackbits(capi.ldpc_encode(r, rng.integers(0, 256, dec.info_bytes, dtype=np.uint8)))[:648] for _ in range(64)])
+        bits = torch.from_numpy(cws.astype(np.float32)).to(dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(1 + rank)
+        llr = torch.empty((B, 648), dtype=torch.float32, device=dev)
+        for off in range(0, B, 1 << 18):                 # bounded temporaries
+            n = min(1 << 18, B - off)
+            y = (1 - 2 * bits)[(torch.arange(n, device=dev) + off) % 64] + sigma * torch.randn((n, 648), device=dev, generator=g)
+            llr[off:off + n] = torch.clamp(2 * y / sigma ** 2, -10, 10)
+        decs.append(dec); llrs.append(llr)
+        outs.append((torch.empty((B, dec.info_bytes), dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.uint8, device=dev),
+                     torch.empty(B, dtype=torch.int32, device=dev)))
+
+    def step(ev=None):
+        for i, (dec, llr, o) in enumerate(zip(decs, llrs, outs)):
+            if ev is not None:
+                ev[i].record()
+            dec.decode_batch(llr, *o)
+        if ev is not None:
+            ev[len(decs)].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(os.path.join(ROOT, "gpurun_out", "bench_clocks.csv")) if rank == 0 else None
+    if sampler:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(decs) + 1)] for _ in range(args.steps)]
+    n0 = ctx.kernel_launches
+    barrier()
+    with Timer(torch) as tm:
+        for k in range(args.steps):
+            step(evs[k])
+    barrier()
+    t = torch.tensor([tm.ms()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clocks = sampler.stop(world) if sampler else None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_rate, upd_total = {}, 0.0
+        for i, ((name, sigma), dec, o) in enumerate(zip(rates, decs, outs)):
+            ms = sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps
+            it_run = float((o[2].float() + o[1].float()).clamp(max=50).mean().item())
+            upd = 2 * dec.num_edges * it_run * B
+            upd_total += upd
+            per_rate[name] = {"sigma": sigma, "ms_per_launch": ms, "codewords_per_s": B / (ms * 1e-3), "converged": float(o[1].float().mean().item()),
+                              "avg_iterations_run": it_run, "edge_updates_per_s": upd / (ms * 1e-3),
+                              "hbm_gbs": (4 * 648 + dec.info_bytes + 5) * B / (ms * 1e-3) / 1e9}
+        value = world * 4 * B * args.steps / (ms_total * 1e-3)
+        alg = sum((4 * 648 + d.info_bytes + 5) for d in decs) * B
+        ach = alg / (ms_total / args.steps * 1e-3) / 1e9
+        traffic, traffic_src = traffic_of("ldpc_flood_reg_kernel")
+        line = {"metric": "decoded codewords/sec (LDPC alone)", "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "config 2: LDPC flooding min-sum decoder alone, %d codewords per rate per GPU at R1/4, R1/2, R3/4, R5/6, "
+                                       "BPSK/AWGN at each rate's waterfall, <= 50 iterations, syndrome stop" % B,
+                           "codewords_per_step_per_gpu": 4 * B, "l2": "inputs larger than L2: %.1f GB of LLRs per step, no flush" % (4 * B * 2592 / 1e9)},
+                "gpu_launches": int(ctx.kernel_launches - n0), "clocks": clocks,
+                "roofline": {"kernel": "ldpc_flood_reg_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": traffic * 4 * B if traffic else None, "traffic_source": traffic_src, "peak_source": peak_src,
+                             "note": "not the binding resource: the decoder is SM-issue / shared-memory-pipe bound (see `sm`)"},
+                "sm": {"edge_updates_per_s": upd_total / (ms_total / args.steps * 1e-3), "per_rate": per_rate,
+                       "ncu": "profiles/: smsp__issue_active, sm__inst_executed_pipe_alu, l1tex__data_pipe_lsu_wavefronts_mem_shared of the same kernel"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -381,9 +643,21 @@ def main():
     ap.add_argument("--cpu-frames-per-core", type=int, default=1040, help="reference arm: frames per core per step")
     ap.add_argument("--cpu-steps", type=int, default=10, help="steps of the cpu_baseline leg of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="m1", choices=["m1", "ldpc", "m3", "dpsk"],
+                    help="m1 = the headline (BASELINE.json configs[1]'s mode); ldpc / m3 / dpsk = configs 2 / 3 / 4")
+    ap.add_argument("--precision", default="fast", choices=["fast", "exact"],
+                    help="arithmetic of the OFDM kernels that have an FMA form (pu_ofdm_set_precision); the other one is timed on the "
+                         "same inputs and reported under other_precision")
+    ap.add_argument("--sustain-seconds", type=float, default=2.5, help="length of the back-to-back `sustained` leg (0 = skip)")
+    ap.add_argument("--sweep-batches", type=int, default=12, help="batches of the `sweep` leg (channel inside the timed region; 0 = skip)")
+    ap.add_argument("--ldpc-codewords", type=int, default=1 << 20, help="--workload ldpc: codewords per rate per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        if args.workload != "m1":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference arm is implemented for --workload m1 (the headline) only"}))
+            return 0
         return run_reference(args)
     return run_ours(args)
 

@@ -134,8 +134,20 @@ PU_API int pu_ofdm_bits_per_symbol(const pu_ofdm* h);  /* OFDMModulator::bitsPer
 /* Diagnostic (no reference counterpart): which kernel the last pu_ofdm_presynced_batch / pu_receive_decode_batch launch on
  * this handle used: 0 = none yet, 1 = general presynced kernel (ofdm_demod.cu), 2 = warp-FFT kernel for differential
  * no-pilot modes (ofdm_diff.cu), 3 = persistent TMA-staged packed-fp32 512-FFT kernel (ofdm_diff512.cu), 4 = general presynced
- * kernel in its one-frame-per-warp form (ofdm_demod.cu, WARPG). */
+ * kernel in its one-frame-per-warp form (ofdm_demod.cu, WARPG), 5 = FMA-contracted form of kernel 3 (ofdm_fast512.cu,
+ * PU_PRECISION_FAST). */
 PU_API int pu_ofdm_last_kernel(const pu_ofdm* h);
+/* Arithmetic contract of the receive kernels of this handle (no reference counterpart; the reference has one build).
+ *   PU_PRECISION_EXACT (default): FFT bins, channel estimate, equalised symbols bit-identical to the reference's unfused
+ *     radix-2 fp32 arithmetic (src/dsp/fft.cpp:89-121, compiled without FMA contraction), LLR words >= 99.99 % identical.
+ *   PU_PRECISION_FAST: BASELINE.json's own bar -- LLRs within 1e-4 relative (of max(|LLR|, 0.5)), saturated LLRs exactly
+ *     +-10, decoded bytes identical on every frame the reference decodes with margin; butterflies are fused multiply-adds.
+ *     Only the kernels that have an FMA form honour it (512-FFT differential no-pilot modes at zero CFO); every other
+ *     call runs the exact kernels.
+ * The environment variable PU_OFDM_PRECISION=exact|fast overrides the handle's setting (A/B runs of unmodified callers). */
+typedef enum pu_precision { PU_PRECISION_EXACT = 0, PU_PRECISION_FAST = 1 } pu_precision;
+PU_API pu_status pu_ofdm_set_precision(pu_ofdm* h, pu_precision mode);
+PU_API int pu_ofdm_get_precision(const pu_ofdm* h);
 /* FFT bins of the used carriers, data carriers first then pilots (setupCarriers, demodulator.cpp:45-67) */
 PU_API int pu_ofdm_carrier_bins(const pu_ofdm* h, int32_t* bins, int cap);
 /* Fuse ChannelInterleaver(bits_per_symbol, total_bits)::deinterleave (ldpc_decoder.cpp:612-620) into the LLR

@@ -33,18 +33,43 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _deps():
+    return glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(ROOT, "include", "pu", "*.h")) + [os.path.abspath(__file__)]
+
+
 def build(force=False, verbose=False):
+    """One nvcc process per translation unit (in parallel; objects cached under projectultra_b200/build/), then one link."""
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC] + FLAGS + ["-o", LIB] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if r.returncode != 0:
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in _deps())
+    cflags = [f for f in FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, 0, ""
+        r = subprocess.run([NVCC] + cflags + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, r.returncode, "== " + os.path.basename(src) + "\n" + r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, sources()))
+    logtxt = "".join(t for _, _, t in results)
+    if verbose or any(rc for _, rc, _ in results):
+        sys.stderr.write(logtxt)
+    if any(rc for _, rc, _ in results):
         raise RuntimeError("nvcc failed building libpu_b200.so")
-    log = os.path.join(HERE, "build_ptxas.log")
-    with open(log, "w") as f:
-        f.write(r.stdout + r.stderr)
+    r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for o, _, _ in results],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link of libpu_b200.so failed")
+    if logtxt:
+        with open(os.path.join(HERE, "build_ptxas.log"), "a" if not force else "w") as f:
+            f.write(logtxt)
     return LIB
 
 

@@ -307,7 +307,7 @@ class OfdmDemodulator:
             pass
 
     KERNELS = {0: "none", 1: "ofdm_presynced_kernel", 2: "ofdm_diff_kernel", 3: "ofdm_diff512_kernel",
-               4: "ofdm_presynced_warp_kernel"}
+               4: "ofdm_presynced_warp_kernel", 5: "ofdm_fast512_kernel"}
 
     @property
     def last_kernel(self):
@@ -318,6 +318,15 @@ class OfdmDemodulator:
         buf = (C.c_int32 * 128)()
         n = lib().pu_ofdm_carrier_bins(self._h, buf, 128)
         return np.array(buf[:n], dtype=np.int32)
+
+    def set_precision(self, mode):
+        """'exact' (default: FFT bins bit-identical to the reference) or 'fast' (FMA butterflies, LLRs within 1e-4):
+        pu_ofdm_set_precision."""
+        check(lib().pu_ofdm_set_precision(self._h, {"exact": 0, "fast": 1}[mode]))
+
+    @property
+    def precision(self):
+        return {0: "exact", 1: "fast"}[lib().pu_ofdm_get_precision(self._h)]
 
     def set_deinterleave(self, bits_per_symbol, total_bits=648):
         check(lib().pu_ofdm_set_deinterleave(self._h, C.c_size_t(bits_per_symbol), C.c_size_t(total_bits)))

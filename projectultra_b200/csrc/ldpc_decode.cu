@@ -345,6 +345,7 @@ struct DevArray {
         if (p) { cudaFree(p); p = nullptr; }
         PU_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(v.size() * sizeof(T), 16)));
         PU_CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        PU_CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));   // pageable source: the DMA must have landed before a non-blocking stream reads it
         return PU_OK;
     }
 };

@@ -122,6 +122,9 @@ pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const float* sam
         for (auto& sl : ctx->pipe) PU_CUDA_TRY(cudaStreamWaitEvent(sl.stream, ctx->pipe_ev, 0));
     }
     for (auto& sl : ctx->pipe) {
+        // a previous call that failed half-way may have left copies or kernels of this lane in flight: its staging buffers are
+        // about to be reused, so wait for them (a no-op when the lane is idle)
+        PU_CUDA_TRY(cudaStreamSynchronize(sl.stream));
         sl.nb = 0;
         if ((s = sl.d_in.reserve(slab * (L + 2) * sizeof(float))) != PU_OK) return s;
         if (!src_pinned && (s = sl.h_in.reserve(slab * L * sizeof(float))) != PU_OK) return s;
@@ -146,6 +149,7 @@ pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const float* sam
         return PU_OK;
     };
     size_t lane = 0;
+    auto run = [&]() -> pu_status {
     for (size_t off = 0; off < B; off += slab, lane ^= 1) {
         pu::PipeSlot& sl = ctx->pipe[lane];
         if ((s = drain(sl)) != PU_OK) return s;
@@ -211,6 +215,13 @@ pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const float* sam
     if ((s = drain(ctx->pipe[lane])) != PU_OK) return s;
     if ((s = drain(ctx->pipe[lane ^ 1])) != PU_OK) return s;
     return PU_OK;
+    };
+    const pu_status rs = run();
+    if (rs != PU_OK) {   // leave no lane in flight behind an error: the caller's buffers and the staging buffers must be quiescent
+        for (auto& sl : ctx->pipe) { (void)cudaStreamSynchronize(sl.stream); sl.nb = 0; }
+        (void)cudaGetLastError();
+    }
+    return rs;
 }
 
 }  // extern "C"

@@ -28,6 +28,7 @@
 #include <new>
 
 #include "ofdm_plan.h"
+#include "pu_async.cuh"
 #include "pu_internal.h"
 #include "ref_math.cuh"
 #include "ofdm_dev.cuh"
@@ -826,6 +827,11 @@ bool ofdm_diff_supported(const OfdmDev& d, int n_symbols, int training);
 cudaError_t ofdm_diff_launch(const OfdmDev& d, const float2* host_twiddle, const float* samples, size_t B, size_t frame_stride,
                              int n_symbols, int training, float* llr, size_t llr_stride, int llr_limit, float* snr_db,
                              float* final_cfo, cudaStream_t st);
+// ofdm_fast512.cu
+bool ofdm_fast512_supported(const OfdmDev& d, int n_symbols, int training, const float* samples, size_t frame_stride, size_t B, size_t llr_stride);
+cudaError_t ofdm_fast512_launch(const OfdmDev& d, const float* samples, size_t B, size_t frame_stride, int n_symbols, int training,
+                                float* llr, size_t llr_stride, int llr_limit, float* snr_db, float* final_cfo, int sm_count, cudaStream_t st);
+
 // ofdm_diff512.cu
 bool ofdm_diff512_supported(const OfdmDev& d, int n_symbols, int training, const float* samples, size_t frame_stride, size_t B);
 cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, const float* samples, size_t B, size_t frame_stride,
@@ -887,7 +893,12 @@ struct DevMem {
     pu_status upload(const T* src, size_t n) {
         if (p) { cudaFree(p); p = nullptr; }
         PU_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
-        if (n) PU_CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+        if (n) {
+            // A pageable H2D cudaMemcpy may return once the source is staged, before the DMA has landed, and the kernels that
+            // read these tables / samples run on NON-BLOCKING streams (no implicit ordering with the legacy stream): wait for it.
+            PU_CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+            PU_CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+        }
         return PU_OK;
     }
 };
@@ -979,6 +990,14 @@ struct pu_ofdm {
     }
     int max_symbols = 0;
     int last_kernel = 0;
+    int precision = PU_PRECISION_EXACT;
+    bool fast() const {      // PU_OFDM_PRECISION overrides the handle (read once)
+        static const int env = [] {
+            const char* v = getenv("PU_OFDM_PRECISION");
+            return !v ? -1 : (v[0] == 'f' || v[0] == 'F' || v[0] == '1') ? 1 : 0;
+        }();
+        return env >= 0 ? env == 1 : precision == PU_PRECISION_FAST;
+    }
     size_t smem_bytes = 0;
 
     pu_status ensure_nco(int n_symbols) {
@@ -1062,6 +1081,14 @@ int pu_ofdm_carrier_bins(const pu_ofdm* h, int32_t* bins, int cap) {
     return n;
 }
 
+pu_status pu_ofdm_set_precision(pu_ofdm* h, pu_precision mode) {
+    PU_REQUIRE(h, "pu_ofdm_set_precision: NULL handle");
+    PU_REQUIRE(mode == PU_PRECISION_EXACT || mode == PU_PRECISION_FAST, "pu_ofdm_set_precision: unknown mode");
+    h->precision = mode;
+    return PU_OK;
+}
+int pu_ofdm_get_precision(const pu_ofdm* h) { return h ? (h->fast() ? PU_PRECISION_FAST : PU_PRECISION_EXACT) : -1; }
+
 pu_status pu_ofdm_set_deinterleave(pu_ofdm* h, size_t bits_per_symbol, size_t total_bits) {
     PU_REQUIRE(h, "pu_ofdm_set_deinterleave: NULL handle");
     PU_CUDA_TRY(cudaSetDevice(h->ctx->device));
@@ -1096,6 +1123,15 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
     static const bool no_p512 = getenv("PU_OFDM_NO_PACKED512") != nullptr;   // A/B switch for tests and profiling
     if (!d_fstart && !d_fnsym && !d_cfo && !d_phase && !d_dbg && !no_p512 && pu::ofdm_diff_supported(h->dev, n_symbols, training) &&
         pu::ofdm_diff512_supported(h->dev, n_symbols, training, d_samples, L, B)) {
+        if (h->fast() && pu::ofdm_fast512_supported(h->dev, n_symbols, training, d_samples, L, B, llr_stride)) {
+            // PU_PRECISION_FAST: the same pipeline with FMA-contracted butterflies (ofdm_fast512.cu)
+            const cudaError_t e = pu::ofdm_fast512_launch(h->dev, d_samples, B, L, n_symbols, training, d_llr, llr_stride, limit, d_snr, d_fcfo,
+                                                          h->ctx->sm_count, st);
+            h->last_kernel = 5;
+            h->ctx->launches.fetch_add(1);
+            PU_CUDA_TRY(e);
+            return PU_OK;
+        }
         // 512-FFT differential no-pilot mode: persistent TMA-staged packed-fp32 kernel (ofdm_diff512.cu)
         const cudaError_t e = pu::ofdm_diff512_launch(h->dev, reinterpret_cast<const float2*>(p.twiddle.data()), d_samples, B, L, n_symbols,
                                                       training, d_llr, llr_stride, limit, d_snr, d_fcfo, h->ctx->sm_count, st);
@@ -1138,14 +1174,8 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
                             float*, float*, float*, unsigned, const int*, const int*, int);
         const WK wk = p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1> : pu::ofdm_presynced_kernel<512, true, 2>)
                                     : (diff ? pu::ofdm_presynced_kernel<1024, true, 1> : pu::ofdm_presynced_kernel<1024, true, 2>);
-        static bool attrw = false;
-        if (!attrw) {
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-            cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-            attrw = true;
-        }
+        static std::atomic<uint64_t> attrw[4];      // per kernel instance, one bit per device (pu_async.cuh: smem_optin)
+        PU_CUDA_TRY(pu::smem_optin(attrw[(p.nfft == 512 ? 0 : 2) + (diff ? 0 : 1)], wk, 232448));
         wk<<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr,
                                                                            llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym, wsync ? 1 : 0);
         h->last_kernel = 4;
@@ -1154,13 +1184,13 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         return PU_OK;
     }
     if (p.nfft == 512) {
-        static bool attr512 = false;
-        if (!attr512) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<512, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr512 = true; }
+        static std::atomic<uint64_t> attr512{0};
+        PU_CUDA_TRY(pu::smem_optin(attr512, pu::ofdm_presynced_kernel<512, false, 0>, 65536));
         pu::ofdm_presynced_kernel<512, false, 0><<<grid, 64, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
                                                                             d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym, 0);
     } else {
-        static bool attr1024 = false;
-        if (!attr1024) { cudaFuncSetAttribute(pu::ofdm_presynced_kernel<1024, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); attr1024 = true; }
+        static std::atomic<uint64_t> attr1024{0};
+        PU_CUDA_TRY(pu::smem_optin(attr1024, pu::ofdm_presynced_kernel<1024, false, 0>, 65536));
         pu::ofdm_presynced_kernel<1024, false, 0><<<grid, 128, h->smem_bytes, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase,
                                                                               d_llr, llr_stride, limit, d_snr, d_fcfo, d_dbg, 0u, d_fstart, d_fnsym, 0);
     }

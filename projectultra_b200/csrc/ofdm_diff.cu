@@ -24,6 +24,7 @@
 
 #include "ofdm_dev.cuh"
 #include "ofdm_diff_demap.cuh"
+#include "pu_async.cuh"
 #include "pu_internal.h"
 
 namespace pu {
@@ -260,13 +261,13 @@ cudaError_t ofdm_diff_launch(const OfdmDev& d, const float2* host_twiddle, const
     const size_t smem = ofdm_diff_smem(d, n_symbols);
     const unsigned grid = static_cast<unsigned>(B);
     if (d.nfft == 512) {
-        static size_t attr = 0;
-        if (smem > attr) { cudaFuncSetAttribute(ofdm_diff_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = 100 * 1024; }
+        static std::atomic<uint64_t> attr{0};
+        if (const cudaError_t e = smem_optin(attr, ofdm_diff_kernel<512>, 100 * 1024); e != cudaSuccess) return e;
         ofdm_diff_kernel<512><<<grid, kDiffWarps * 32, smem, st>>>(d, twa, samples, frame_stride, n_symbols, training, llr, llr_stride,
                                                                   llr_limit, snr_db, final_cfo);
     } else {
-        static size_t attr = 0;
-        if (smem > attr) { cudaFuncSetAttribute(ofdm_diff_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = 100 * 1024; }
+        static std::atomic<uint64_t> attr{0};
+        if (const cudaError_t e = smem_optin(attr, ofdm_diff_kernel<1024>, 100 * 1024); e != cudaSuccess) return e;
         ofdm_diff_kernel<1024><<<grid, kDiffWarps * 32, smem, st>>>(d, twa, samples, frame_stride, n_symbols, training, llr, llr_stride,
                                                                    llr_limit, snr_db, final_cfo);
     }

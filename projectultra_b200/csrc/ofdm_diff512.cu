@@ -35,11 +35,11 @@
 
 #include "ofdm_dev.cuh"
 #include "ofdm_diff_demap.cuh"
+#include "pu_async.cuh"
 #include "pu_internal.h"
 
 namespace pu {
 
-typedef unsigned long long u64;
 
 constexpr int kP512MaxWarps = 12;       // frame pairs in flight per CTA (one warp each)
 constexpr int kP512MaxWarpsInplace = 16; // ... of the in-place-transpose variant
@@ -50,12 +50,6 @@ constexpr size_t kP512SmemMax = 227 * 1024;
 struct P512Tw { u64 re[8], im[8]; };    // pass-A twiddles tw[32 m] as broadcast pairs (w.x, w.x), (w.y, w.y)
 
 struct C2 { u64 re, im; };              // one complex quantity of frames (f, f+1): re = (re_f, re_f1), im likewise
-
-__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk(u64 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // t = w * b as GCC lowers std::complex<float> multiplication (ofdm_dev.cuh: cmul), for two symbols at once
 __device__ __forceinline__ C2 cmul2(u64 wre, u64 wim, C2 b, u64 Z) {
@@ -81,29 +75,6 @@ __device__ __forceinline__ C2 bfly2_lo(C2 a, C2 b, u64 wre, u64 wim, u64 Z) {
 __device__ __forceinline__ C2 bfly2_hi(C2 a, C2 b, u64 wre, u64 wim, u64 Z) {
     const C2 t = cmul2(wre, wim, b, Z);
     C2 r; r.re = sub2(a.re, t.re); r.im = sub2(a.im, t.im); return r;
-}
-
-// ---- mbarrier / bulk-copy wrappers (PTX ISA 8.x, sm_90+) ----------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(u64* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, uint32_t bytes) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
-    asm volatile(
-        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 constexpr int kP512Queue = 64;          // per-warp queue of carriers waiting for the exact demapper (flushed 32 at a time)
@@ -543,19 +514,17 @@ cudaError_t ofdm_diff512_launch(const OfdmDev& d, const float2* host_twiddle, co
     const Kernel kernels[5] = {ofdm_diff512_kernel<2, false, false, kP512MaxWarps>, ofdm_diff512_kernel<2, true, false, kP512MaxWarps>,
                                ofdm_diff512_kernel<3, false, false, kP512MaxWarps>, ofdm_diff512_kernel<3, true, false, kP512MaxWarps>,
                                ofdm_diff512_kernel<2, true, true, kP512MaxWarpsInplace>};
-    static bool attr = false;
-    if (!attr) {
-        for (const Kernel k : kernels) {
-            const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kP512SmemMax));
-            if (e != cudaSuccess) return e;
-        }
-        attr = true;
+    static std::atomic<uint64_t> attr_done[5];
+    const int which = inplace ? 4 : (stages == 3 ? 2 : 0) + (half ? 1 : 0);
+    {
+        const cudaError_t e = smem_optin(attr_done[which], kernels[which], static_cast<int>(kP512SmemMax));
+        if (e != cudaSuccess) return e;
     }
     const size_t max_ctas = static_cast<size_t>(sm_count > 0 ? sm_count : 148);      // persistent: one CTA per SM
     const size_t want_ctas = ((B + 1) / 2 + warps - 1) / warps;
     const unsigned grid = static_cast<unsigned>(want_ctas < max_ctas ? want_ctas : max_ctas);
     const u64 Z = 0x8000000080000000ull;    // (-0.0f, -0.0f): see the header comment
-    kernels[inplace ? 4 : (stages == 3 ? 2 : 0) + (half ? 1 : 0)]<<<grid, warps * 32, L.total, st>>>(d, twa, Z, samples, frame_stride, B, n_symbols, training, llr,
+    kernels[which]<<<grid, warps * 32, L.total, st>>>(d, twa, Z, samples, frame_stride, B, n_symbols, training, llr,
                                                                                      llr_stride, llr_limit, snr_db, final_cfo);
     return cudaGetLastError();
 }

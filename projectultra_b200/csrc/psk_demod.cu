@@ -533,7 +533,11 @@ struct PskDevMem {
     pu_status upload(const T* src, size_t n) {
         if (p) { cudaFree(p); p = nullptr; }
         PU_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
-        if (n) PU_CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+        if (n) {
+            // pageable H2D copies may return before the DMA has landed and the kernels run on non-blocking streams: wait for it
+            PU_CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+            PU_CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
+        }
         return PU_OK;
     }
 };

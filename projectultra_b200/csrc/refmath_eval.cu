@@ -35,6 +35,7 @@ extern "C" pu_status pu_refmath_eval(pu_ctx* ctx, int op, const float* a, const 
     PU_CUDA_TRY(cudaMalloc(&dout, n * sizeof(float)));
     PU_CUDA_TRY(cudaMemcpy(da, a, n * sizeof(float), cudaMemcpyHostToDevice));
     if (b) PU_CUDA_TRY(cudaMemcpy(db, b, n * sizeof(float), cudaMemcpyHostToDevice));
+    PU_CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));   // pageable H2D: wait for the DMA before the non-blocking stream's kernel
     pu::refmath_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(op, da, b ? db : nullptr, dout, n);
     ctx->launches.fetch_add(1);
     PU_CUDA_TRY(cudaGetLastError());

@@ -125,9 +125,10 @@ class LinkSim:
 
     def __init__(self, ctx, cfg, channel="awgn", payload_bytes=40, pool=64, snr_convention=None, pool_seed=12345,
                  max_iter=50, device=None, code_rate=None, peak=None, layout="presynced", chunk=960, fresh_payload=False,
-                 acquire=False):
+                 acquire=False, precision="exact"):
         import torch
         self.ctx, self.cfg = ctx, cfg
+        self.precision = precision
         self.device = device or torch.device("cuda", ctx.device)
         self.ch = channel_preset(channel) if isinstance(channel, str) else channel
         self.channel_name = channel if isinstance(channel, str) else "custom"
@@ -137,6 +138,8 @@ class LinkSim:
             self.kind = "ofdm"
             rate = cfg.code_rate if code_rate is None else code_rate
             self.ofdm = self.demod = capi.OfdmDemodulator(ctx, cfg)
+            # "exact": FFT bins bit-identical to the reference; "fast": FMA butterflies, LLRs within 1e-4 (pu_ofdm_set_precision)
+            self.ofdm.set_precision(precision)
             # layout "presynced": 2 LTS + data, genie timing (tools/test_ofdm_chirp_pilots.cpp); layout "sc": generatePreamble()
             # + data fed to process() in `chunk`-sample pieces, i.e. with Schmidl-Cox acquisition (tools/test_mode_snr.cpp:40-105)
             # layout "chirp": OFDM_CHIRP frames = ChirpSync::generate() + training + data, received through dual-chirp detectSync ->
@@ -222,8 +225,12 @@ class LinkSim:
         return self.demod.demod_soft_batch(rx, llr_stride=648, llr=llr, want_cfo=False)[0]
 
     def noise_std_table(self, snr_points):
-        return np.array([[channel_noise_std(self.tx_host[i], s, self.snr_convention) for i in range(self.pool)]
-                         for s in snr_points], dtype=np.float32)
+        key = tuple(float(s) for s in snr_points)
+        cache = self.__dict__.setdefault("_std_cache", {})
+        if key not in cache:
+            cache[key] = np.array([[channel_noise_std(self.tx_host[i], s, self.snr_convention) for i in range(self.pool)]
+                                   for s in key], dtype=np.float32)
+        return cache[key]
 
     @staticmethod
     def frame_seed(snr_idx, trial, base_seed=0xB200):
@@ -281,21 +288,48 @@ class LinkSim:
             count_errors(self.ctx, info, ok, iters, payload, idx, batch["bins"], self.payload_bytes, counters)
             self.last_payload, self.last_tx, self.last_std = payload, tx, std
             return (rx, info, ok, iters) if keep else None
-        rx = channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rx)
+        rx = self.make_rx(batch, rx)
+        info, ok, iters = self.receive_count(batch, rx, counters)
+        return (rx, info, ok, iters) if keep else None
+
+    def make_rx(self, batch, rx=None):
+        """Channel outputs of a prepared batch (pool waveforms): pu_channel_apply_batch on the current stream."""
+        return channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rx)
+
+    def receive_count(self, batch, rx, counters, ev=None, bufs=None):
+        """demod -> LDPC -> counters for channel outputs `rx` of `batch`.  ev: optional list of >= 4 CUDA events recorded before the
+        demodulator, between demodulator and decoder, behind the decoder and behind the counting kernel (bench.py's per-stage times).
+        bufs: optional dict of preallocated device tensors {llr, info, ok, iters}."""
+        bufs = bufs or {}
+        rec = (lambda i: ev[i].record()) if ev is not None else (lambda i: None)
+        rec(0)
         if self.kind == "ofdm" and self.layout in ("sc", "chirp"):
             # no sync or fewer than 648 soft bits is a lost frame (tools/test_mode_snr.cpp:72-77): the decoder's verdict on
             # the zero-filled row is overridden
-            info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))
+            llr = self.demod_llr(rx)
+            rec(1)
+            info, ok, iters = self.ldpc.decode_batch(llr, bufs.get("info"), bufs.get("ok"), bufs.get("iters"))
             ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
-        elif self.kind == "ofdm":
+        elif self.kind == "ofdm" and ev is None and not bufs:
             info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
+        elif self.kind == "ofdm":
+            llr = bufs.get("llr")
+            if llr is not None and self.ofdm.n_llr(rx.shape[1]) < 648:
+                llr.zero_()                                              # frames shorter than a codeword: erasures
+            llr = self.demod.presynced_batch(rx, 2, llr_stride=648, llr=llr, want_aux=False)[0]
+            rec(1)
+            info, ok, iters = self.ldpc.decode_batch(llr, bufs.get("info"), bufs.get("ok"), bufs.get("iters"))
         else:
-            info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))
+            llr = self.demod_llr(rx, bufs.get("llr"))
+            rec(1)
+            info, ok, iters = self.ldpc.decode_batch(llr, bufs.get("info"), bufs.get("ok"), bufs.get("iters"))
             if (self.kind == "dpsk" and self.acquire) or (self.kind == "mcdpsk" and self.layout == "chirp"):
                 ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
+        rec(2)
         count_errors(self.ctx, info, ok, iters, self.payload_pool, batch["tx_index"], batch["bins"], self.payload_bytes,
                      counters)
-        return (rx, info, ok, iters) if keep else None
+        rec(3)
+        return info, ok, iters
 
     def sweep(self, snr_points, trials_per_point, rank=0, world=1, batch_frames=1 << 15, base_seed=0xB200):
         """FER/BER sweep; this rank takes trials t with t % world == rank.  Returns an int64 [n_snr, 6] device tensor

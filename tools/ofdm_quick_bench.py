@@ -26,6 +26,7 @@ else:                          # M3: presets::nvis_mode() 1024-FFT 59 carriers C
     snrs = [float(s) for s in range(6, 19)]
     rate = capi.R3_4
 sim = linksim.LinkSim(ctx, cfg, os.environ.get("QB_CHANNEL", "awgn"), payload_bytes=40 if mode.startswith("m1") else 60, pool=64, code_rate=rate)
+sim.ofdm.set_precision(os.environ.get("QB_PRECISION", "exact"))
 n = len(snrs)
 B = fpp * n
 trials = np.repeat(np.arange(fpp, dtype=np.int64), n)

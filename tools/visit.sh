@@ -1,0 +1,28 @@
+#!/bin/bash
+# Development GPU visit (round 2).  Usage: bash tools/visit.sh <tag> [what...]   what: tests fasttests quick bench workloads ncu
+TAG=${1:-v01}; shift
+WHAT=${@:-fasttests quick}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $OUT/gpu.txt 2>&1
+for w in $WHAT; do case $w in
+tests) ( time python -m pytest tests -m gpu -q -x ) > $OUT/pytest_gpu.log 2>&1; tail -4 $OUT/pytest_gpu.log;;
+fasttests) ( time python -m pytest tests/test_ofdm_fast_gpu.py -q -s ) > $OUT/pytest_fast.log 2>&1; grep -E "^mod|^fast|^against|^frames|passed|failed" $OUT/pytest_fast.log;;
+quick) { python tools/ofdm_quick_bench.py 4096 m1; QB_PRECISION=fast python tools/ofdm_quick_bench.py 4096 m1; } > $OUT/quick.txt 2>&1; cat $OUT/quick.txt;;
+smoke) python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log;;
+bench) python bench.py > $OUT/bench.json 2> $OUT/bench.err; tail -c 6000 $OUT/bench.json; tail -5 $OUT/bench.err;;
+benchref) python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; tail -c 600 $OUT/bench_ref.json;;
+workloads) for wl in ldpc m3 dpsk; do python bench.py --workload $wl --steps 5 > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; tail -c 3000 $OUT/bench_$wl.json; tail -3 $OUT/bench_$wl.err; done;;
+ncu)
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --sustain-seconds 0 --sweep-batches 2 > $OUT/ncu_launch_bench.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:ofdm_fast -s 3 -c 1 -f -o $OUT/prof_ofdm \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --sustain-seconds 0 --sweep-batches 0 > $OUT/ncu_ofdm.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:ldpc_flood -s 3 -c 1 -f -o $OUT/prof_ldpc \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --sustain-seconds 0 --sweep-batches 0 > $OUT/ncu_ldpc.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:awgn_kernel -c 1 -f -o $OUT/prof_awgn \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --sustain-seconds 0 --sweep-batches 0 > $OUT/ncu_awgn.log 2>&1
+  ;;
+*) echo "unknown: $w";;
+esac; done
+ls -la $OUT
