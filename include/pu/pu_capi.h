@@ -376,6 +376,88 @@ PU_API pu_status pu_count_errors(pu_ctx* ctx, const uint8_t* info_bytes, size_t 
                                  const uint32_t* tx_index, const uint32_t* bin, size_t payload_bytes, size_t B,
                                  uint64_t* counters, void* stream);
 
+/* ---------------------------------------------------------------- Monte-Carlo sweep driver (BASELINE.json config 5)
+ * The reference runs its FER/BER waterfalls as a shell matrix over one-process-per-cell tools (tests/regression_matrix.sh:139-243 over
+ * the loop of tools/test_iwaveform.cpp:597-806 and tools/test_mode_snr.cpp:40-105: per trial  payload -> encode -> modulate -> channel
+ * -> sync/demodulate -> decodeSoft -> compare).  pu_linksim_run is that matrix as ONE call per GPU rank: a mode table (waveform x
+ * modulation x code rate x channel) x an SNR grid x trials_per_point seeds is cut into work units (mode, SNR point, seed block), the
+ * units are dealt to the ranks by expected cost (longest-processing-time first: low-SNR blocks run more LDPC iterations, acquisition
+ * modes cost orders of magnitude more per frame), and every rank runs its units in large mixed-SNR batches through
+ * pu_channel_apply_batch -> the waveform's receive entry point -> pu_ldpc_decode_batch -> pu_count_errors.  Frames are pure functions
+ * of (mode, SNR index, trial): seed = base_seed << 40 ^ mode << 56 ^ snr_index << 32 ^ trial, TX waveform = trial % pool; no data is
+ * exchanged between ranks, the counter tables are summed once at the end (pu_counters_allreduce, or the host's own collective).
+ * With manifest_dir set every finished unit is appended to a per-rank shard file; a later call with the same table resumes: finished
+ * units (from ANY earlier world size) are skipped and their counters are returned by rank 0. */
+enum { PU_WF_OFDM = 0,           /* 2 LTS + data, genie timing: processPresynced (tools/test_ofdm_chirp_pilots.cpp:183-260) */
+       PU_WF_OFDM_SC = 1,        /* Schmidl-Cox preamble + data fed to process() in chunks (tools/test_mode_snr.cpp:40-105) */
+       PU_WF_OFDM_CHIRP = 2,     /* dual chirp + training + data: detectSync -> setFrequencyOffset -> process (tools/test_iwaveform.cpp:127-160) */
+       PU_WF_DPSK = 3,           /* Barker preamble + data, genie data start (setReferenceSymbol on the last preamble symbol) */
+       PU_WF_DPSK_ACQ = 4,       /* ... received through findPreamble (tools/test_dpsk_snr.cpp:66-73) */
+       PU_WF_MCDPSK = 5,         /* training + reference + data, externally timed (tools/test_mc_dpsk.cpp:180-196) */
+       PU_WF_MCDPSK_CHIRP = 6 }; /* dual chirp + training + reference + data through MCDPSKWaveform's detectSync / process */
+/* channel presets: ccir:: (src/sim/hf_channel.hpp:305-381) and itu_r_f1487:: (:402-487) */
+enum { PU_CH_AWGN = 0, PU_CH_GOOD = 1, PU_CH_MODERATE = 2, PU_CH_POOR = 3, PU_CH_FLUTTER = 4,
+       PU_CH_ITU_GOOD = 5, PU_CH_ITU_MODERATE = 6, PU_CH_ITU_POOR = 7, PU_CH_ITU_FLUTTER = 8 };
+PU_API pu_status pu_channel_preset(int preset, pu_channel_config* out);
+
+typedef struct {
+    uint32_t waveform;          /* PU_WF_* */
+    pu_modem_config ofdm;       /* PU_WF_OFDM*  */
+    pu_dpsk_config dpsk;        /* PU_WF_DPSK*  */
+    pu_mcdpsk_config mcdpsk;    /* PU_WF_MCDPSK* */
+    uint32_t code_rate;         /* PU_RATE_* */
+    uint32_t payload_bytes;     /* compared bytes (<= k/8) */
+    uint32_t channel;           /* PU_CH_* */
+    uint32_t n_snr;
+    float snr_first_db, snr_step_db;
+    float peak;                 /* > 0: the tools' peak normalisation of every TX waveform (tools/test_mode_snr.cpp:54-56) */
+    uint32_t precision;         /* pu_precision of the OFDM kernels */
+    uint32_t chunk;             /* PU_WF_OFDM_SC: process() chunk, 0 = 960 */
+    float cost;                 /* relative cost of one frame for the partitioner; 0 = built-in estimate */
+} pu_sweep_mode;
+
+typedef struct {
+    const pu_sweep_mode* modes;
+    uint32_t n_modes;
+    uint32_t pool;              /* TX waveforms per mode (0 = 64); payload of waveform i = pu_sweep_payload(base_seed, mode, i) */
+    uint64_t trials_per_point;  /* seeds per (mode, SNR point) */
+    uint32_t block_trials;      /* trials per work unit (0 = 4096) */
+    uint32_t max_iter;          /* LDPC iteration limit (0 = 50) */
+    uint64_t base_seed;         /* 16 bits used (0 = 0xB200) */
+    uint32_t rank, world;
+    uint64_t batch_bytes;       /* device memory for one batch of channel outputs (0 = 1.5 GiB) */
+    const char* manifest_dir;   /* NULL = no persistence / resume */
+    uint64_t max_units;         /* stop after this many units on this rank (0 = run everything): tests of resume */
+    uint64_t run_id;            /* manifest only: equal on all ranks of one launch, different between launches (e.g. the launch time).
+                                 * Shards written under the current run_id are ignored when the finished set is read, so a rank that
+                                 * starts late sees the same finished units -- hence computes the same partition -- as its peers */
+} pu_sweep_desc;
+
+typedef struct {
+    uint64_t units_total, units_resumed, units_run, frames_run;
+    double seconds;             /* wall time of the run loop on this rank */
+    double busy_cost, total_cost; /* this rank's share / the sum of the partitioner's cost estimates (remaining units) */
+} pu_sweep_stats;
+
+/* number of work units of a table, and the offset of mode m's SNR point 0 in the counter table (= sum of n_snr of the modes before) */
+PU_API uint64_t pu_sweep_unit_count(const pu_sweep_desc* d);
+PU_API uint32_t pu_sweep_point_count(const pu_sweep_desc* d);
+/* owner[u] = rank that runs unit u (0xffffffff for units marked in done[u] != 0; done may be NULL); cost[u] may be NULL.
+ * Pure host function of the table: every rank computes the same assignment. */
+PU_API pu_status pu_sweep_partition(const pu_sweep_desc* d, const uint8_t* done, uint32_t* owner, double* cost);
+/* unit u -> (mode, SNR index, first trial, number of trials) */
+PU_API pu_status pu_sweep_unit(const pu_sweep_desc* d, uint64_t u, uint32_t* mode, uint32_t* snr_index, uint64_t* first_trial, uint32_t* n_trials);
+/* payload bytes of TX waveform `index` of mode `mode` (splitmix64 stream; lets any host regenerate the pool) */
+PU_API void pu_sweep_payload(uint64_t base_seed, uint32_t mode, uint32_t index, uint8_t* out, size_t n_bytes);
+/* counters[pu_sweep_point_count][6] (HOST, uint64) = this rank's {frames, frame_errors, bit_errors, payload_bits, decode_failures,
+ * iteration_sum} per (mode, SNR point), rank 0 additionally holding the resumed units; stats may be NULL. */
+PU_API pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters, pu_sweep_stats* stats);
+/* Sum n uint64 counters over the ranks of an NCCL communicator (ncclComm_t passed as void*; libnccl is resolved at run time with
+ * dlopen, the library does not link it).  PU_MEM_HOST stages through the context; comm == NULL is a no-op (single rank). */
+PU_API pu_status pu_counters_allreduce(pu_ctx* ctx, uint64_t* counters, size_t n, void* nccl_comm, pu_memspace space, void* stream);
+/* Wilson score interval of an error rate (the Monte-Carlo confidence interval of BASELINE.json's north star) */
+PU_API void pu_wilson_interval(uint64_t errors, uint64_t n, double z, double* lo, double* hi);
+
 /* ---------------------------------------------------------------- numerics pinning (tests)
  * Evaluates the device restatements of the host libm routines the reference's path calls (csrc/ref_math.cuh):
  * op 0 atan2f(a,b), 1 sinf(a), 2 cosf(a), 3 hypotf(a,b), 4 atanf(a).  ctx == NULL evaluates the same source on

@@ -25,11 +25,11 @@ def sources():
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(os.path.join(HERE, "pu_sweep")):
         return True
     t = os.path.getmtime(LIB)
     deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        glob.glob(os.path.join(ROOT, "include", "pu", "*.h")) + [os.path.abspath(__file__)]
+        glob.glob(os.path.join(ROOT, "include", "pu", "*.h")) + [os.path.abspath(__file__), os.path.join(ROOT, "tools", "pu_sweep.cpp")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -70,7 +70,23 @@ def build(force=False, verbose=False):
     if logtxt:
         with open(os.path.join(HERE, "build_ptxas.log"), "a" if not force else "w") as f:
             f.write(logtxt)
+    build_tools()
     return LIB
+
+
+SWEEP_BIN = os.path.join(HERE, "pu_sweep")
+
+
+def build_tools():
+    """The C++20 host program of the config-5 sweep (tools/pu_sweep.cpp), linked against the in-tree library."""
+    src = os.path.join(ROOT, "tools", "pu_sweep.cpp")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++20", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", SWEEP_BIN,
+           "-L", HERE, "-lpu_b200", "-ldl", "-pthread", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building pu_sweep")
+    return SWEEP_BIN
 
 
 if __name__ == "__main__":

@@ -708,3 +708,106 @@ class McDpskDemodulator:
         check(lib().pu_mcdpsk_demod_soft_batch(self._h, _ptr(x), C.c_size_t(B), C.c_size_t(L), _ptr(llr), C.c_size_t(llr_stride),
                                                _ptr(cfo), sp, _stream(sp)))
         return llr, cfo
+
+
+# ---------------------------------------------------------------------------------------------- sweep driver (pu_linksim_run)
+WF_OFDM, WF_OFDM_SC, WF_OFDM_CHIRP, WF_DPSK, WF_DPSK_ACQ, WF_MCDPSK, WF_MCDPSK_CHIRP = range(7)
+CHANNELS = {"awgn": 0, "good": 1, "moderate": 2, "poor": 3, "flutter": 4,
+            "itu_good": 5, "itu_moderate": 6, "itu_poor": 7, "itu_flutter": 8}
+
+
+class SweepMode(C.Structure):
+    """pu_sweep_mode: one row of the mode table (waveform x modulation x code rate x channel x SNR grid)."""
+    _fields_ = [("waveform", C.c_uint32), ("ofdm", ModemConfig), ("dpsk", DpskConfig), ("mcdpsk", McDpskConfig),
+                ("code_rate", C.c_uint32), ("payload_bytes", C.c_uint32), ("channel", C.c_uint32), ("n_snr", C.c_uint32),
+                ("snr_first_db", C.c_float), ("snr_step_db", C.c_float), ("peak", C.c_float), ("precision", C.c_uint32),
+                ("chunk", C.c_uint32), ("cost", C.c_float)]
+
+    @property
+    def snr_points(self):
+        return [self.snr_first_db + i * self.snr_step_db for i in range(self.n_snr)]
+
+
+class SweepDesc(C.Structure):
+    _fields_ = [("modes", C.POINTER(SweepMode)), ("n_modes", C.c_uint32), ("pool", C.c_uint32), ("trials_per_point", C.c_uint64),
+                ("block_trials", C.c_uint32), ("max_iter", C.c_uint32), ("base_seed", C.c_uint64), ("rank", C.c_uint32),
+                ("world", C.c_uint32), ("batch_bytes", C.c_uint64), ("manifest_dir", C.c_char_p), ("max_units", C.c_uint64),
+                ("run_id", C.c_uint64)]
+
+
+class SweepStats(C.Structure):
+    _fields_ = [("units_total", C.c_uint64), ("units_resumed", C.c_uint64), ("units_run", C.c_uint64), ("frames_run", C.c_uint64),
+                ("seconds", C.c_double), ("busy_cost", C.c_double), ("total_cost", C.c_double)]
+
+
+def sweep_mode(waveform, cfg, code_rate, payload_bytes, channel, snr_first, snr_step, n_snr, peak=0.0, precision="exact", chunk=0, cost=0.0):
+    m = SweepMode()
+    m.waveform = waveform
+    if isinstance(cfg, ModemConfig):
+        m.ofdm = cfg
+    elif isinstance(cfg, DpskConfig):
+        m.dpsk = cfg
+    else:
+        m.mcdpsk = cfg
+    m.code_rate, m.payload_bytes, m.channel, m.n_snr = int(code_rate), int(payload_bytes), CHANNELS[channel] if isinstance(channel, str) else int(channel), int(n_snr)
+    m.snr_first_db, m.snr_step_db, m.peak = float(snr_first), float(snr_step), float(peak or 0.0)
+    m.precision, m.chunk, m.cost = {"exact": 0, "fast": 1}[precision], int(chunk), float(cost)
+    return m
+
+
+class Sweep:
+    """Host view of a pu_sweep_desc: keeps the mode array alive and wraps pu_sweep_* / pu_linksim_run."""
+
+    def __init__(self, modes, trials_per_point, block_trials=4096, pool=64, rank=0, world=1, base_seed=0xB200, max_iter=50,
+                 batch_bytes=0, manifest_dir=None, max_units=0, run_id=0):
+        self.modes = list(modes)
+        self._arr = (SweepMode * len(self.modes))(*self.modes)
+        self._dir = manifest_dir.encode() if manifest_dir else None
+        self.desc = SweepDesc(self._arr, len(self.modes), pool, trials_per_point, block_trials, max_iter, base_seed, rank, world,
+                              batch_bytes, self._dir, max_units, run_id)
+        L = lib()
+        L.pu_sweep_unit_count.restype = C.c_uint64
+        L.pu_sweep_point_count.restype = C.c_uint32
+        self.n_units = int(L.pu_sweep_unit_count(C.byref(self.desc)))
+        self.n_points = int(L.pu_sweep_point_count(C.byref(self.desc)))
+        if self.n_units == 0:
+            raise PuError("invalid sweep description")
+
+    def partition(self, done=None):
+        owner = np.zeros(self.n_units, np.uint32)
+        cost = np.zeros(self.n_units, np.float64)
+        d = None if done is None else np.ascontiguousarray(done, dtype=np.uint8)
+        check(lib().pu_sweep_partition(C.byref(self.desc), _ptr(d), _ptr(owner), _ptr(cost)))
+        return owner, cost
+
+    def unit(self, u):
+        m, s, t0, nt = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint32()
+        check(lib().pu_sweep_unit(C.byref(self.desc), C.c_uint64(u), C.byref(m), C.byref(s), C.byref(t0), C.byref(nt)))
+        return m.value, s.value, t0.value, nt.value
+
+    def payload(self, mode, index):
+        out = np.zeros(self.modes[mode].payload_bytes, np.uint8)
+        lib().pu_sweep_payload(C.c_uint64(self.desc.base_seed), C.c_uint32(mode), C.c_uint32(index), _ptr(out), C.c_size_t(len(out)))
+        return out
+
+    def run(self, ctx):
+        """pu_linksim_run -> (counters [n_points, 6] uint64 on the host, SweepStats)."""
+        counters = np.zeros((self.n_points, 6), np.uint64)
+        st = SweepStats()
+        check(lib().pu_linksim_run(ctx._h, C.byref(self.desc), _ptr(counters), C.byref(st)))
+        return counters, st
+
+    def point_rows(self, counters):
+        """[(mode index, snr_db, counter row)] in counter-table order."""
+        rows, at = [], 0
+        for mi, m in enumerate(self.modes):
+            for s in m.snr_points:
+                rows.append((mi, s, counters[at]))
+                at += 1
+        return rows
+
+
+def wilson_interval(errors, n, z=1.96):
+    lo, hi = C.c_double(), C.c_double()
+    lib().pu_wilson_interval(C.c_uint64(int(errors)), C.c_uint64(int(n)), C.c_double(z), C.byref(lo), C.byref(hi))
+    return lo.value, hi.value

@@ -125,7 +125,7 @@ class LinkSim:
 
     def __init__(self, ctx, cfg, channel="awgn", payload_bytes=40, pool=64, snr_convention=None, pool_seed=12345,
                  max_iter=50, device=None, code_rate=None, peak=None, layout="presynced", chunk=960, fresh_payload=False,
-                 acquire=False, precision="exact"):
+                 acquire=False, precision="exact", payloads=None):
         import torch
         self.ctx, self.cfg = ctx, cfg
         self.precision = precision
@@ -187,7 +187,9 @@ class LinkSim:
         assert not self.fresh_payload or self.kind == "ofdm", "the GPU transmitter covers the OFDM waveforms"
         self.payload_bytes = payload_bytes
         rng = np.random.default_rng(pool_seed)
-        self.payloads = rng.integers(0, 256, (pool, payload_bytes), dtype=np.uint8)
+        # payloads: explicit [pool, payload_bytes] array (e.g. the splitmix64 pool of the C++ sweep driver, capi.Sweep.payload)
+        self.payloads = (rng.integers(0, 256, (pool, payload_bytes), dtype=np.uint8) if payloads is None
+                         else np.ascontiguousarray(payloads, dtype=np.uint8).reshape(pool, payload_bytes))
         waves = [build(capi.ldpc_encode(rate, p)) for p in self.payloads]
         if peak is not None:
             waves = [(w * (np.float32(peak) / np.abs(w).max())).astype(np.float32) for w in waves]

@@ -1,0 +1,102 @@
+"""GPU tests of the C++ sweep driver (pu_linksim_run, csrc/sweep.cu) against the Python link simulator that the parity tests of
+test_linksim_gpu.py pin frame by frame to the oracle: same payload pool, same seeds -> identical counter tables, for one mode of
+every waveform family; two ranks emulated on one GPU sum to the single-rank table; an interrupted sweep resumes from its manifest
+to the uninterrupted totals."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from projectultra_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def small_table(capi):
+    m1 = capi.ModemConfig(48000, 1500, 512, 30, 1, 4, 2, 0, capi.DQPSK, capi.R1_2, 40.0, 0.0)
+    m1q = capi.ModemConfig(48000, 1500, 512, 30, 1, 4, 2, 1, capi.QAM16, capi.R1_2, 40.0, 0.0)
+    return [capi.sweep_mode(capi.WF_OFDM, m1, capi.R1_2, 40, "awgn", -3, 1.5, 5, precision="fast"),
+            capi.sweep_mode(capi.WF_OFDM, m1q, capi.R1_2, 40, "good", 8, 3, 4),
+            capi.sweep_mode(capi.WF_DPSK, capi.dpsk_config(1, 384), capi.R1_4, 20, "poor", -6, 4, 4, peak=0.5),
+            capi.sweep_mode(capi.WF_MCDPSK, capi.mcdpsk_config(8, 2), capi.R1_2, 40, "moderate", 0, 3, 4)]
+
+
+def python_counters(ctx, sw, mi, trials):
+    """The same (mode, SNR point, trial) grid through projectultra_b200.linksim.LinkSim."""
+    import torch
+    from projectultra_b200 import capi, linksim
+    m = sw.modes[mi]
+    pool = sw.desc.pool
+    payloads = np.stack([sw.payload(mi, i) for i in range(pool)])
+    cfg = m.ofdm if m.waveform <= capi.WF_OFDM_CHIRP else m.dpsk if m.waveform <= capi.WF_DPSK_ACQ else m.mcdpsk
+    chan = [k for k, v in capi.CHANNELS.items() if v == m.channel][0]
+    sim = linksim.LinkSim(ctx, cfg, chan, payload_bytes=m.payload_bytes, pool=pool, code_rate=m.code_rate, peak=m.peak or None,
+                          precision="fast" if m.precision else "exact", payloads=payloads)
+    snrs = m.snr_points
+    si = np.repeat(np.arange(len(snrs), dtype=np.int64), trials)
+    tr = np.tile(np.arange(trials, dtype=np.int64), len(snrs))
+    batch = sim.make_batch(snrs, si, tr, base_seed=0xB200 | (mi << 16))      # (mode << 56) of the driver's seed rule
+    c = torch.zeros((len(snrs), 6), dtype=torch.int64, device="cuda")
+    sim.run_batch(batch, c)
+    torch.cuda.synchronize()
+    return c.cpu().numpy().astype(np.uint64)
+
+
+def test_driver_matches_python_linksim_mode_by_mode(ctx):
+    from projectultra_b200 import capi
+    trials = 96
+    sw = capi.Sweep(small_table(capi), trials_per_point=trials, block_trials=40, pool=8)
+    counters, st = sw.run(ctx)
+    assert st.units_run == sw.n_units and st.frames_run == trials * sw.n_points and st.units_resumed == 0
+    at = 0
+    for mi, m in enumerate(sw.modes):
+        want = python_counters(ctx, sw, mi, trials)
+        got = counters[at:at + m.n_snr]
+        assert (got == want).all(), (mi, got.tolist(), want.tolist())
+        assert (got[:, 0] == trials).all()
+        at += m.n_snr
+    # a waterfall: the first SNR point of the fast OFDM mode loses frames, the last one does not
+    assert counters[0, 1] > counters[4, 1] == 0
+
+
+def test_two_ranks_on_one_gpu_sum_to_the_single_rank_table(ctx):
+    from projectultra_b200 import capi
+    one, _ = capi.Sweep(small_table(capi), trials_per_point=64, block_trials=16, pool=8).run(ctx)
+    parts = []
+    for r in range(2):
+        c, st = capi.Sweep(small_table(capi), trials_per_point=64, block_trials=16, pool=8, rank=r, world=2).run(ctx)
+        assert 0 < st.units_run < st.units_total and abs(st.busy_cost / st.total_cost - 0.5) < 0.05
+        parts.append(c)
+    assert (parts[0] + parts[1] == one).all()
+
+
+def test_interrupted_sweep_resumes_from_its_manifest(ctx, tmp_path):
+    from projectultra_b200 import capi
+    d = str(tmp_path / "manifest")
+    full, _ = capi.Sweep(small_table(capi), trials_per_point=48, block_trials=16, pool=8).run(ctx)
+    c1, s1 = capi.Sweep(small_table(capi), trials_per_point=48, block_trials=16, pool=8, manifest_dir=d, max_units=7, run_id=1).run(ctx)
+    assert s1.units_run == 7 and s1.units_resumed == 0
+    shard = [f for f in os.listdir(d) if f.startswith("shard-")]
+    assert len(shard) == 1
+    with open(os.path.join(d, shard[0]), "a") as f:
+        f.write("12 16 3 ")                                                  # a torn record (killed while appending): ignored
+    # resume with a different world size: finished units are skipped whoever ran them, rank 0 returns their counters.  Both ranks of
+    # the new launch (run_id 2) must see the same finished set although rank 1 starts after rank 0 has appended its units.
+    tot = np.zeros_like(full)
+    for r in range(2):
+        c, st = capi.Sweep(small_table(capi), trials_per_point=48, block_trials=16, pool=8, manifest_dir=d, rank=r, world=2, run_id=2).run(ctx)
+        assert st.units_resumed == 7 and st.units_run > 0
+        tot += c
+    assert (tot == full).all()
+    # everything is in the manifest now: nothing left to run, the table comes back from the files
+    c3, s3 = capi.Sweep(small_table(capi), trials_per_point=48, block_trials=16, pool=8, manifest_dir=d, run_id=3).run(ctx)
+    assert s3.units_run == 0 and s3.units_resumed == s3.units_total and (c3 == full).all()
+    # a different table must not resume from this directory
+    with pytest.raises(capi.PuError):
+        capi.Sweep(small_table(capi), trials_per_point=49, block_trials=16, pool=8, manifest_dir=d, run_id=4).run(ctx)

@@ -23,6 +23,8 @@ ncu)
   ncu --set full --clock-control none --import-source on -k regex:awgn_kernel -c 1 -f -o $OUT/prof_awgn \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --sustain-seconds 0 --sweep-batches 0 > $OUT/ncu_awgn.log 2>&1
   ;;
+sweeptests) ( time python -m pytest tests/test_sweep_gpu.py -q -x ) > $OUT/pytest_sweep.log 2>&1; tail -15 $OUT/pytest_sweep.log;;
+sweepsmoke) ( time projectultra_b200/pu_sweep --table smoke --trials 8192 --block 2048 --out $OUT/sweep_smoke.jsonl ) > $OUT/sweep_smoke.log 2>&1; tail -3 $OUT/sweep_smoke.log; tail -1 $OUT/sweep_smoke.jsonl;;
 *) echo "unknown: $w";;
 esac; done
 ls -la $OUT
