@@ -409,38 +409,41 @@ def run_ours(args):
     #      demod -> LDPC -> count per batch), on this workload's channel and, for the headline, on Watterson 'good' as well
     sweeps = {}
     if args.sweep_batches > 0:
+        import ctypes as C
+        wf = {"ofdm": capi.WF_OFDM, "dpsk": capi.WF_DPSK}[wl["kind"]]
         for chname in ([wl["channel"]] + (["good"] if args.workload == "m1" else [])):
-            s2 = sim if chname == wl["channel"] else None
-            if s2 is None:
-                s2 = linksim.LinkSim(ctx, cfg, chname, payload_bytes=pb, pool=POOL, code_rate=rate, precision=args.precision)
-            s2.noise_std_table(snr_points)
-            rxb = torch.empty_like(rx)
-            cs = torch.zeros_like(counters)
-            b0 = s2.make_batch(snr_points, si, trials)
-            for _ in range(2):
-                s2.run_batch(b0, cs, rx=rxb)
-            evc = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-            evc[0].record(); s2.make_rx(b0, rxb); evc[1].record()
-            torch.cuda.synchronize()
-            ms_ch = evc[0].elapsed_time(evc[1])
-            cs.zero_()
+            # the C++ driver (pu_linksim_run, csrc/sweep.cu): descriptors -> channel kernel -> demod -> LDPC -> count per batch, two
+            # batches in flight; this rank's share of the (SNR point, seed block) units, no exchange but the final counter sum
+            mode = capi.sweep_mode(wf, cfg, rate, pb, chname, snr_points[0], snr_points[1] - snr_points[0], n_snr,
+                                   peak=0.5 if wl["kind"] == "dpsk" else 0.0, precision=args.precision if wl["kind"] == "ofdm" else "exact")
+            sw = capi.Sweep([mode], trials_per_point=fpp * args.sweep_batches * world, block_trials=min(4096, fpp), pool=POOL if wl["kind"] == "ofdm" else 16,
+                            rank=rank, world=world, batch_bytes=B * L * 4)
+            capi.Sweep([mode], trials_per_point=fpp, block_trials=min(4096, fpp), pool=POOL if wl["kind"] == "ofdm" else 16).run(ctx)   # warm-up
             barrier()
-            t0 = time.perf_counter()
-            for k in range(args.sweep_batches):
-                tr = trials + (k + 1) * world * fpp            # fresh trial indices (fresh seeds) every batch
-                s2.run_batch(s2.make_batch(snr_points, si, tr), cs, rx=rxb)
+            cs_h, stt = sw.run(ctx)
+            dt = max_over_ranks(stt.seconds)
+            cs = torch.from_numpy(cs_h.astype(np.int64)).to(dev)
             linksim.allreduce_counters(cs)
-            torch.cuda.synchronize()
-            dt = max_over_ranks(time.perf_counter() - t0)
-            barrier()
+            fr = torch.tensor([float(stt.frames_run)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(fr)
+            # the channel kernel alone on one batch of the same shape
+            chcfg = linksim.ChannelConfig()
+            capi.check(capi.lib().pu_channel_preset(capi.CHANNELS[chname], C.byref(chcfg)))
+            rxb = torch.empty_like(rx)
+            linksim.channel_apply(ctx, chcfg, sim.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rxb)
+            with Timer(torch) as tc:
+                linksim.channel_apply(ctx, chcfg, sim.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"], rxb)
+            ms_ch = tc.ms()
+            del rxb
             kern = "awgn_kernel" if chname == "awgn" else "channel_kernel"
-            sweeps[chname] = {"value": world * B * args.sweep_batches / dt, "unit": UNIT, "batches": args.sweep_batches,
-                              "frames_per_batch_per_gpu": B, "seconds": dt,
+            sweeps[chname] = {"value": float(fr.item()) / dt, "value_excluding_setup": float(fr.item()) / max(dt - stt.setup_seconds, 1e-9), "unit": UNIT, "api": "pu_linksim_run (C++ driver, channel generation inside)",
+                              "frames": int(fr.item()), "seconds": dt, "setup_seconds": stt.setup_seconds, "gpu_wait_seconds": stt.wait_seconds, "host_fill_seconds": stt.fill_seconds, "units_per_rank": int(stt.units_run),
                               "channel_kernel": {"kernel": kern, "ms_per_launch": ms_ch, "bound": "hbm",
                                                  "algorithmic_bytes_per_frame": 4 * L,
                                                  "achieved": 4 * L * B / (ms_ch * 1e-3) / 1e9},
                               "fer": [round(float(r[1]) / max(int(r[0]), 1), 5) for r in cs.cpu().numpy()]}
-            del rxb
+            barrier()
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D of the samples, D2H of the decoded bytes/flags
     e2e = None
@@ -649,7 +652,7 @@ def main():
                     help="arithmetic of the OFDM kernels that have an FMA form (pu_ofdm_set_precision); the other one is timed on the "
                          "same inputs and reported under other_precision")
     ap.add_argument("--sustain-seconds", type=float, default=2.5, help="length of the back-to-back `sustained` leg (0 = skip)")
-    ap.add_argument("--sweep-batches", type=int, default=12, help="batches of the `sweep` leg (channel inside the timed region; 0 = skip)")
+    ap.add_argument("--sweep-batches", type=int, default=200, help="batches of the `sweep` leg (channel inside the timed region; 0 = skip)")
     ap.add_argument("--ldpc-codewords", type=int, default=1 << 20, help="--workload ldpc: codewords per rate per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -320,8 +320,9 @@ typedef struct {
     uint32_t sample_rate;
     uint32_t fading_enabled, multipath_enabled, noise_enabled;
 } pu_channel_config;
-/* Derived constants of a config (delay d, IIR coefficient a, sqrt(1/a), (1-a)^(2^s), (1-a)^(l+1)): the numbers
- * the CPU twin needs to regenerate a frame bit for bit.  Any output pointer may be NULL. */
+/* Derived constants of a config (delay d, IIR coefficient a, sqrt(1/a), the scan multipliers (1-a)^(4 2^s) for s < 5 and the
+ * carry weights (1-a)^(4 l) for l < 32): the numbers the CPU twin needs to regenerate a frame bit for bit.  Any output pointer
+ * may be NULL. */
 PU_API pu_status pu_channel_params(const pu_channel_config* cfg, int32_t* delay_samples, float* alpha,
                                    float* noise_scale, float* apow2_5, float* apl_32);
 /* Noise standard deviation for one TX waveform (host): convention 0 = WattersonChannel::process, rms(input) *
@@ -436,6 +437,10 @@ typedef struct {
 typedef struct {
     uint64_t units_total, units_resumed, units_run, frames_run;
     double seconds;             /* wall time of the run loop on this rank */
+    double setup_seconds;       /* ... of which building the modes' TX pools, noise tables and handles on the host, */
+    double wait_seconds;        /* ... blocked on the GPU (batch k-2 not finished when batch k is due): GPU-bound share, */
+    double fill_seconds;        /* ... writing batch descriptors on the host, */
+    double enqueue_seconds;     /* ... inside the C-ABI calls that enqueue a batch (copies + kernel launches) */
     double busy_cost, total_cost; /* this rank's share / the sum of the partitioner's cost estimates (remaining units) */
 } pu_sweep_stats;
 

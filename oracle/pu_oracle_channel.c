@@ -12,8 +12,10 @@
  *      DESIGN.md ("Channel RNG") and is implemented independently of projectultra_b200/csrc/pu_rng.cuh:
  *        Philox4x32-10, key = seed (lo, hi), counter = (index, 0, stream, 0), stream 1 fading / 2 noise;
  *        u = ((w >> 9) + 0.5) 2^-23; Box-Muller with the fixed ln / sin / cos polynomials below (IEEE ops only);
- *        fading normals of sample n from index n; noise normal of sample n from index n>>2, word pair (n&3)>>1,
- *        cosine branch for even n; the one-pole recurrence evaluated per 32-sample group as a Kogge-Stone scan.
+ *        fading innovations of sample n: Philox index n>>1, 16-bit half (n&1) of word c, z = (u16 - 32767.5) sqrt(12)/65536
+ *        (uniform, unit variance: the tap is a sum of >= 385 of them, Gaussian by the central limit theorem);
+ *        noise normal of sample n from index n>>2, word pair (n&3)>>1, cosine branch for even n;
+ *        the one-pole recurrence evaluated per 128-sample group: serial over the 4 samples of a lane, Kogge-Stone over lanes.
  * Output is bit-identical to the CUDA kernels (tests/test_channel_gpu.py); against the reference the channel is
  * compared statistically. */
 #include "pu_oracle.h"
@@ -95,11 +97,14 @@ float orc_noise_normal(uint64_t seed, uint32_t n) {
     return (n & 1) ? zs : zc;
 }
 
+/* the four unit-variance fading innovations of sample n (the name is historical: they are uniform, not normal) */
 void orc_fading_normals(uint64_t seed, uint32_t n, float z[4]) {
-    uint32_t c[4] = {n, 0, 1, 0};
+    uint32_t c[4] = {n >> 1, 0, 1, 0};
     philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    bm(c[0], c[1], &z[0], &z[1]);
-    bm(c[2], c[3], &z[2], &z[3]);
+    for (int k = 0; k < 4; ++k) {
+        uint32_t u = (n & 1) ? (c[k] >> 16) : (c[k] & 0xffffu);
+        z[k] = ((float)u - 32767.5f) * 5.2857806906e-05f;
+    }
 }
 
 /* one frame; returns 0 */
@@ -109,28 +114,40 @@ int orc_channel_apply(float delay_ms, float doppler_hz, float g1, float g2, uint
     float nd = doppler_hz / (float)fs;
     float alpha = (float)(1.0f - exp(-2.0f * 3.14159265358979323846 * nd));
     float ns = alpha > 0.0f ? sqrtf(1.0f / alpha) : 0.0f;
-    float a = 1.0f - alpha, apow2[5], apl[32];
+    float a = 1.0f - alpha, qj[4], qs[5], ql[32];
     float v = a;
-    for (int s = 0; s < 5; ++s) { apow2[s] = v; v = v * v; }
-    v = a;
-    for (int l = 0; l < 32; ++l) { apl[l] = v; v = v * a; }
+    for (int j = 0; j < 4; ++j) { qj[j] = v; v = v * a; }
+    v = qj[3];
+    for (int s = 0; s < 5; ++s) { qs[s] = v; v = v * v; }
+    v = 1.0f;
+    for (int l = 0; l < 32; ++l) { ql[l] = v; v = v * qj[3]; }
     float carry[4] = {1.0f, 0.0f, 1.0f, 0.0f};
-    for (size_t base = 0; base < L; base += 32) {
-        float f[4][32];
+    for (size_t base = 0; base < L; base += 128) {
+        float f[4][128];
         if (fading) {
-            for (int l = 0; l < 32; ++l) {
-                float z[4] = {0, 0, 0, 0};
-                if (base + (size_t)l < L) orc_fading_normals(seed, (uint32_t)(base + (size_t)l), z);
-                for (int c = 0; c < 4; ++c) f[c][l] = alpha * (ns * z[c]);
-            }
             for (int c = 0; c < 4; ++c) {
-                for (int s = 0; s < 5; ++s)
-                    for (int l = 31; l >= (1 << s); --l) f[c][l] = fmaf(apow2[s], f[c][l - (1 << s)], f[c][l]);
-                for (int l = 0; l < 32; ++l) f[c][l] = fmaf(apl[l], carry[c], f[c][l]);
-                carry[c] = f[c][31];
+                float s[32][4], A[32];
+                for (int l = 0; l < 32; ++l) {
+                    for (int j = 0; j < 4; ++j) {
+                        size_t n = base + 4 * (size_t)l + (size_t)j;
+                        float z[4] = {0, 0, 0, 0};
+                        if (n < L) orc_fading_normals(seed, (uint32_t)n, z);
+                        float e = alpha * (ns * z[c]);
+                        s[l][j] = j == 0 ? e : fmaf(a, s[l][j - 1], e);
+                    }
+                    A[l] = s[l][3];
+                }
+                for (int t = 0; t < 5; ++t)
+                    for (int l = 31; l >= (1 << t); --l) A[l] = fmaf(qs[t], A[l - (1 << t)], A[l]);
+                for (int l = 0; l < 32; ++l) {
+                    float e = l ? A[l - 1] : 0.0f;
+                    float pl = fmaf(ql[l], carry[c], e);
+                    for (int j = 0; j < 4; ++j) f[c][4 * l + j] = fmaf(qj[j], pl, s[l][j]);
+                }
+                carry[c] = f[c][127];
             }
         }
-        for (int l = 0; l < 32 && base + (size_t)l < L; ++l) {
+        for (int l = 0; l < 128 && base + (size_t)l < L; ++l) {
             size_t n = base + (size_t)l;
             float m1 = 1.0f, m2 = 1.0f;
             if (fading) {

@@ -737,7 +737,8 @@ class SweepDesc(C.Structure):
 
 class SweepStats(C.Structure):
     _fields_ = [("units_total", C.c_uint64), ("units_resumed", C.c_uint64), ("units_run", C.c_uint64), ("frames_run", C.c_uint64),
-                ("seconds", C.c_double), ("busy_cost", C.c_double), ("total_cost", C.c_double)]
+                ("seconds", C.c_double), ("setup_seconds", C.c_double), ("wait_seconds", C.c_double), ("fill_seconds", C.c_double),
+                ("enqueue_seconds", C.c_double), ("busy_cost", C.c_double), ("total_cost", C.c_double)]
 
 
 def sweep_mode(waveform, cfg, code_rate, payload_bytes, channel, snr_first, snr_step, n_snr, peak=0.0, precision="exact", chunk=0, cost=0.0):

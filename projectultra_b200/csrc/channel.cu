@@ -13,8 +13,8 @@
 // reference the channel is checked statistically (tests/test_channel_gpu.py).  The optional CFO injector of the
 // reference (applyCFO, :173-232) is out of scope: the Monte-Carlo configs are CFO-free.
 //
-// Kernel shape: one warp per frame; lane l owns sample 32 g + l, so global loads/stores are fully coalesced and
-// the recurrence across the 32 samples of a group is a Kogge-Stone scan over warp shuffles (5 fma per component).
+// Kernel shape: one warp per frame; lane l owns samples 128 g + 4 l .. + 3 (16-byte coalesced loads/stores); the recurrence is
+// serial over a lane's four samples and a Kogge-Stone scan over the lanes (see channel_kernel).
 #include <cmath>
 #include <memory>
 #include <new>
@@ -30,10 +30,17 @@ struct ChannelParams {
     int delay;               // d: second path reads x[n - d - 1]
     float g1, g2;
     float alpha, noise_scale;       // a, sqrt(1/a)
-    float apow2[5];          // (1-a)^(2^s)
-    float apl[32];           // (1-a)^(l+1)
+    float qj[4];             // (1-a)^(j+1): carry-in weight of a lane's j-th sample
+    float qs[5];             // (1-a)^(4 * 2^s): Kogge-Stone multipliers over lanes (a lane spans 4 samples)
+    float ql[32];            // (1-a)^(4 l): weight of the group's carry-in at lane l
 };
 
+// One warp per frame, 128 samples per step: lane l owns samples base + 4 l .. 4 l + 3 (one 16-byte load / store, one Philox call
+// for its four noise normals, two for its 16 fading innovations).  The one-pole recurrence f[n] = q f[n-1] + e[n] is evaluated as
+//   in-lane:  s_0 = e_0, s_j = fma(q, s_{j-1}, e_j)                     (the lane's own innovations, zero state before the lane)
+//   lanes:    inclusive Kogge-Stone scan of A_l = s_3 with multipliers q^(4 2^s); E_l = A_{l-1} (0 for lane 0)
+//   carry:    P_l = fma(q^(4 l), C, E_l),  f_j = fma(q^(j+1), P_l, s_j),  C' = f_3 of lane 31
+// -- the evaluation order is part of the simulator's specification (restated by the CPU twin oracle/pu_oracle_channel.c).
 __global__ void __launch_bounds__(256) channel_kernel(ChannelParams p, const float* __restrict__ tx_pool, size_t pool_stride,
                                                       const uint32_t* __restrict__ tx_index, const float* __restrict__ noise_std,
                                                       const uint64_t* __restrict__ seed, size_t B, int L,
@@ -46,42 +53,87 @@ __global__ void __launch_bounds__(256) channel_kernel(ChannelParams p, const flo
     const uint64_t sd = seed[frame];
     const uint32_t k0 = static_cast<uint32_t>(sd), k1 = static_cast<uint32_t>(sd >> 32);
     const float sigma = noise_std[frame];
-    const float apl = p.apl[lane];
+    const float ql = p.ql[lane];
+    const float q = p.qj[0];
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const bool two_path = p.multipath && p.delay > 0;
     float carry[4] = {1.0f, 0.0f, 1.0f, 0.0f};   // fading1_, fading2_ start at (1, 0)
-    for (int base = 0; base < L; base += 32) {
-        const int n = base + lane;
-        const bool in = n < L;
-        const float xv = in ? __ldg(&x[n]) : 0.0f;
-        float m1 = 1.0f, m2 = 1.0f;
+    for (int base = 0; base < L; base += 128) {
+        const int n0 = base + 4 * lane;
+        float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (vec && n0 + 3 < L) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(x + n0));
+            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (n0 + j < L) xv[j] = __ldg(&x[n0 + j]);
+        }
+        float m1[4] = {1.0f, 1.0f, 1.0f, 1.0f}, m2[4] = {1.0f, 1.0f, 1.0f, 1.0f};
         if (p.fading) {
-            float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (in) rng::fading_normals(k0, k1, static_cast<uint32_t>(n), z);
-            float f[4];
+            float z[4][4];      // [sample j][component]
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float zz[2][4];
+                rng::fading_innovations2(k0, k1, static_cast<uint32_t>((n0 >> 1) + h), zz);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    z[2 * h][c] = (n0 + 2 * h < L) ? zz[0][c] : 0.0f;
+                    z[2 * h + 1][c] = (n0 + 2 * h + 1 < L) ? zz[1][c] : 0.0f;
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                float v = rng::r_mul(p.alpha, rng::r_mul(p.noise_scale, z[c]));
+                float s[4];
+                s[0] = rng::r_mul(p.alpha, rng::r_mul(p.noise_scale, z[0][c]));
 #pragma unroll
-                for (int s = 0; s < 5; ++s) {
-                    const float up = __shfl_up_sync(0xffffffffu, v, 1 << s);
-                    if (lane >= (1 << s)) v = rng::r_fma(p.apow2[s], up, v);
+                for (int j = 1; j < 4; ++j) s[j] = rng::r_fma(q, s[j - 1], rng::r_mul(p.alpha, rng::r_mul(p.noise_scale, z[j][c])));
+                float v = s[3];
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    const float up = __shfl_up_sync(0xffffffffu, v, 1 << t);
+                    if (lane >= (1 << t)) v = rng::r_fma(p.qs[t], up, v);
                 }
-                f[c] = rng::r_fma(apl, carry[c], v);
-                carry[c] = __shfl_sync(0xffffffffu, f[c], 31);
+                float e = __shfl_up_sync(0xffffffffu, v, 1);
+                if (lane == 0) e = 0.0f;
+                const float pl = rng::r_fma(ql, carry[c], e);
+                float f[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[j] = rng::r_fma(p.qj[j], pl, s[j]);
+                carry[c] = __shfl_sync(0xffffffffu, f[3], 31);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) z[j][c] = f[j];
             }
-            m1 = rng::r_sqrt(rng::r_fma(f[0], f[0], rng::r_mul(f[1], f[1])));
-            m2 = rng::r_sqrt(rng::r_fma(f[2], f[2], rng::r_mul(f[3], f[3])));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                m1[j] = rng::r_sqrt(rng::r_fma(z[j][0], z[j][0], rng::r_mul(z[j][1], z[j][1])));
+                m2[j] = rng::r_sqrt(rng::r_fma(z[j][2], z[j][2], rng::r_mul(z[j][3], z[j][3])));
+            }
         }
-        if (!in) continue;
-        float out;
-        if (p.multipath && p.delay > 0) {
-            const int nd = n - p.delay - 1;
-            const float xd = nd >= 0 ? __ldg(&x[nd]) : 0.0f;
-            out = rng::r_fma(rng::r_mul(xd, p.g2), m2, rng::r_mul(rng::r_mul(xv, p.g1), m1));
+        if (n0 >= L) continue;
+        float zn[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (p.noise) {
+            const rng::U4 w = rng::philox4x32_10(static_cast<uint32_t>(n0 >> 2), 0u, rng::kStreamNoise, 0u, k0, k1);
+            rng::box_muller(w.x, w.y, &zn[0], &zn[1]);
+            rng::box_muller(w.z, w.w, &zn[2], &zn[3]);
+        }
+        float out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (two_path) {
+                const int nd = n0 + j - p.delay - 1;
+                const float xd = (nd >= 0 && n0 + j < L) ? __ldg(&x[nd]) : 0.0f;
+                out[j] = rng::r_fma(rng::r_mul(xd, p.g2), m2[j], rng::r_mul(rng::r_mul(xv[j], p.g1), m1[j]));
+            } else {
+                out[j] = rng::r_mul(xv[j], m1[j]);
+            }
+            if (p.noise) out[j] = rng::r_fma(sigma, zn[j], out[j]);
+        }
+        if (vec && n0 + 3 < L) {
+            *reinterpret_cast<float4*>(y + n0) = make_float4(out[0], out[1], out[2], out[3]);
         } else {
-            out = rng::r_mul(xv, m1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (n0 + j < L) y[n0 + j] = out[j];
         }
-        if (p.noise) out = rng::r_fma(sigma, rng::noise_normal(k0, k1, static_cast<uint32_t>(n)), out);
-        y[n] = out;
     }
 }
 
@@ -131,9 +183,11 @@ static ChannelParams make_params(const pu_channel_config& c) {
     p.noise_scale = p.alpha > 0.0f ? std::sqrt(1.0f / p.alpha) : 0.0f;                                                  // :264
     const float a = 1.0f - p.alpha;
     float v = a;
-    for (int s = 0; s < 5; ++s) { p.apow2[s] = v; v = v * v; }
-    v = a;
-    for (int l = 0; l < 32; ++l) { p.apl[l] = v; v = v * a; }
+    for (int j = 0; j < 4; ++j) { p.qj[j] = v; v = v * a; }          // q, q^2, q^3, q^4 by repeated multiplication (fp32)
+    v = p.qj[3];
+    for (int s = 0; s < 5; ++s) { p.qs[s] = v; v = v * v; }          // q^4, q^8, ... by repeated squaring
+    v = 1.0f;
+    for (int l = 0; l < 32; ++l) { p.ql[l] = v; v = v * p.qj[3]; }   // 1, q^4, q^8, ... by repeated multiplication
     return p;
 }
 
@@ -165,8 +219,8 @@ pu_status pu_channel_params(const pu_channel_config* cfg, int32_t* delay_samples
     if (delay_samples) *delay_samples = p.delay;
     if (alpha) *alpha = p.alpha;
     if (noise_scale) *noise_scale = p.noise_scale;
-    if (apow2_5) std::memcpy(apow2_5, p.apow2, sizeof(p.apow2));
-    if (apl_32) std::memcpy(apl_32, p.apl, sizeof(p.apl));
+    if (apow2_5) std::memcpy(apow2_5, p.qs, sizeof(p.qs));
+    if (apl_32) std::memcpy(apl_32, p.ql, sizeof(p.ql));
     return PU_OK;
 }
 

@@ -99,7 +99,9 @@ pu_status pu_receive_decode_batch(pu_ofdm* ofdm, pu_ldpc* ldpc, const float* sam
     if (space == PU_MEM_DEVICE) {
         if ((s = ctx->d_aux.reserve(B * PU_LDPC_N * sizeof(float))) != PU_OK) return s;
         float* d_llr = static_cast<float*>(ctx->d_aux.ptr);
-        PU_CUDA_TRY(cudaMemsetAsync(d_llr, 0, B * PU_LDPC_N * sizeof(float), st));   // frames shorter than a codeword: erasures
+        const int n_sym_dev = static_cast<int>(L / static_cast<size_t>(pu_ofdm_symbol_samples(ofdm)));
+        if (static_cast<size_t>(std::max(0, n_sym_dev - training_symbols)) * static_cast<size_t>(pu_ofdm_bits_per_symbol(ofdm)) < PU_LDPC_N)
+            PU_CUDA_TRY(cudaMemsetAsync(d_llr, 0, B * PU_LDPC_N * sizeof(float), st));   // frames shorter than a codeword: erasures
         if ((s = pu_ofdm_presynced_batch(ofdm, samples, B, L, training_symbols, cfo_hz, cfo_phase, d_llr, PU_LDPC_N, nullptr,
                                          nullptr, PU_MEM_DEVICE, st)) != PU_OK) return s;
         return pu_ldpc_decode_batch(ldpc, d_llr, PU_LDPC_N, B, info_bytes, info_stride, ok, iters, PU_MEM_DEVICE, st);

@@ -117,6 +117,8 @@ void pu_destroy(pu_ctx* c) {
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
+    for (auto& b : c->sweep) b.release();
+    for (auto& e : c->sweep_ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -66,6 +66,10 @@ struct pu_ctx {
     pu::Buffer f_llr, f_bytes, f_ok, f_iters, f_out;   // scratch of pu_frame_decode_batch (grow-only, reused across calls)
     pu::PipeSlot pipe[2];
     cudaEvent_t pipe_ev = nullptr;
+    // scratch of pu_linksim_run (sweep.cu), grow-only and reused across calls: [0..6] batch buffers (rx, llr, info, ok, iters, n_llr, sync),
+    // [7 + 4 s .. 10 + 4 s] slot s = {pinned descriptors, device descriptors, device counters, pinned counters}
+    pu::Buffer sweep[15];
+    cudaEvent_t sweep_ev[2] = {nullptr, nullptr};
 };
 
 namespace pu {

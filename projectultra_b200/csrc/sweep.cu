@@ -314,8 +314,8 @@ struct Manifest {
     void flush() { if (f) fflush(f); }
 };
 
-struct Slot {       // one batch in flight
-    Buffer h_desc, d_desc, d_cnt, h_cnt;
+struct Slot {       // one batch in flight; the buffers live in the context (grow-only, reused across calls)
+    Buffer *h_desc = nullptr, *d_desc = nullptr, *d_cnt = nullptr, *h_cnt = nullptr;
     cudaEvent_t ev = nullptr;
     std::vector<uint64_t> units;       // unit ids of the batch, bin order
     uint32_t mode = 0;
@@ -463,23 +463,27 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
 
     // ---- batches in flight
     pu::Slot slots[2];
-    pu::Buffer d_rx, d_llr, d_info, d_ok, d_iters, d_nllr, d_sync;
-    auto cleanup = [&]() {
-        for (auto& sl : slots) {
-            if (sl.ev) cudaEventDestroy(sl.ev);
-            sl.h_desc.release(); sl.d_desc.release(); sl.d_cnt.release(); sl.h_cnt.release();
+    pu::Buffer &d_rx = ctx->sweep[0], &d_llr = ctx->sweep[1], &d_info = ctx->sweep[2], &d_ok = ctx->sweep[3], &d_iters = ctx->sweep[4],
+               &d_nllr = ctx->sweep[5], &d_sync = ctx->sweep[6];
+    for (int i = 0; i < 2; ++i) {
+        pu::Slot& sl = slots[i];
+        sl.h_desc = &ctx->sweep[7 + 4 * i]; sl.d_desc = &ctx->sweep[8 + 4 * i]; sl.d_cnt = &ctx->sweep[9 + 4 * i]; sl.h_cnt = &ctx->sweep[10 + 4 * i];
+        sl.h_desc->pinned_host = true;
+        sl.h_cnt->pinned_host = true;
+        if (!ctx->sweep_ev[i] && cudaEventCreateWithFlags(&ctx->sweep_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            ctx->sweep_ev[i] = nullptr;
+            pu::set_error("pu_linksim_run: cudaEventCreate failed");
+            return PU_ERR_CUDA;
         }
-        d_rx.release(); d_llr.release(); d_info.release(); d_ok.release(); d_iters.release(); d_nllr.release(); d_sync.release();
-    };
-    for (auto& sl : slots) {
-        sl.h_desc.pinned_host = true;
-        sl.h_cnt.pinned_host = true;
-        if (cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming) != cudaSuccess) { cleanup(); pu::set_error("pu_linksim_run: cudaEventCreate failed"); return PU_ERR_CUDA; }
+        sl.ev = ctx->sweep_ev[i];
     }
+    auto cleanup = [&]() {};
     auto harvest = [&](pu::Slot& sl) -> pu_status {
         if (!sl.busy) return PU_OK;
+        const auto t_wait = std::chrono::steady_clock::now();
         PU_CUDA_TRY(cudaEventSynchronize(sl.ev));
-        const uint64_t* hc = static_cast<const uint64_t*>(sl.h_cnt.ptr);
+        stt.wait_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait).count();
+        const uint64_t* hc = static_cast<const uint64_t*>(sl.h_cnt->ptr);
         for (size_t i = 0; i < sl.units.size(); ++i) {
             uint32_t m, s, nt; uint64_t t0;
             pu::unit_decode(d, p, sl.units[i], &m, &s, &t0, &nt);
@@ -503,7 +507,9 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
             if (owner[u] == d->rank) mine.push_back(u);
         if (mine.empty()) continue;
         pu::ModeEngine eng;
+        const auto t_setup = std::chrono::steady_clock::now();
         if ((rs = eng.build(ctx, &d->modes[m], m, p, st)) != PU_OK) break;
+        stt.setup_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count();
         const size_t L = eng.L, kb = eng.kb;
         const size_t max_frames = std::max<size_t>(1, std::min<uint64_t>(p.batch_bytes / (L * sizeof(float)), (uint64_t(1) << 22)));
         const size_t cap = std::max<size_t>(max_frames, p.block);      // a unit is never split: the smallest batch is one unit
@@ -532,15 +538,16 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
             const size_t nu = sl.units.size();
             // descriptors: tx_index u32 | noise_std f32 | bin u32 | seed u64 (8-byte aligned at the end)
             const size_t off_std = B * 4, off_bin = B * 8, off_seed = ((B * 12 + 7) / 8) * 8, desc_bytes = off_seed + B * 8;
-            if ((rs = sl.h_desc.reserve(desc_bytes)) != PU_OK || (rs = sl.d_desc.reserve(desc_bytes)) != PU_OK ||
-                (rs = sl.d_cnt.reserve(nu * 6 * 8)) != PU_OK || (rs = sl.h_cnt.reserve(nu * 6 * 8)) != PU_OK)
+            if ((rs = sl.h_desc->reserve(desc_bytes)) != PU_OK || (rs = sl.d_desc->reserve(desc_bytes)) != PU_OK ||
+                (rs = sl.d_cnt->reserve(nu * 6 * 8)) != PU_OK || (rs = sl.h_cnt->reserve(nu * 6 * 8)) != PU_OK)
                 break;
-            unsigned char* hd = static_cast<unsigned char*>(sl.h_desc.ptr);
+            unsigned char* hd = static_cast<unsigned char*>(sl.h_desc->ptr);
             uint32_t* h_tx = reinterpret_cast<uint32_t*>(hd);
             float* h_std = reinterpret_cast<float*>(hd + off_std);
             uint32_t* h_bin = reinterpret_cast<uint32_t*>(hd + off_bin);
             uint64_t* h_seed = reinterpret_cast<uint64_t*>(hd + off_seed);
             size_t at = 0;
+            const auto t_fill = std::chrono::steady_clock::now();
             for (size_t i = 0; i < nu; ++i) {
                 uint32_t mm, s, nt; uint64_t t0;
                 pu::unit_decode(d, p, sl.units[i], &mm, &s, &t0, &nt);
@@ -552,10 +559,11 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
                     h_tx[at] = tx; h_std[at] = stdrow[tx]; h_bin[at] = static_cast<uint32_t>(i); h_seed[at] = hi ^ trial;
                 }
             }
-            unsigned char* dd = static_cast<unsigned char*>(sl.d_desc.ptr);
+            stt.fill_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fill).count();
+            unsigned char* dd = static_cast<unsigned char*>(sl.d_desc->ptr);
             auto launch = [&]() -> pu_status {
                 PU_CUDA_TRY(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, st));
-                PU_CUDA_TRY(cudaMemsetAsync(sl.d_cnt.ptr, 0, nu * 6 * 8, st));
+                PU_CUDA_TRY(cudaMemsetAsync(sl.d_cnt->ptr, 0, nu * 6 * 8, st));
                 float* rx = static_cast<float*>(d_rx.ptr);
                 pu_status s2 = pu_channel_apply_batch(ctx, &eng.ch, static_cast<const float*>(eng.d_tx.ptr), L, eng.pool, reinterpret_cast<const uint32_t*>(dd),
                                                       reinterpret_cast<const float*>(dd + off_std), reinterpret_cast<const uint64_t*>(dd + off_seed), B, L, rx,
@@ -568,13 +576,15 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
                                  reinterpret_cast<float*>(static_cast<int32_t*>(d_sync.ptr) + 4 * cap), info, ok, iters, st);
                 if (s2 != PU_OK) return s2;
                 s2 = pu_count_errors(ctx, info, kb, ok, iters, static_cast<const uint8_t*>(eng.d_payload.ptr), kb, reinterpret_cast<const uint32_t*>(dd),
-                                     reinterpret_cast<const uint32_t*>(dd + off_bin), d->modes[m].payload_bytes, B, static_cast<uint64_t*>(sl.d_cnt.ptr), st);
+                                     reinterpret_cast<const uint32_t*>(dd + off_bin), d->modes[m].payload_bytes, B, static_cast<uint64_t*>(sl.d_cnt->ptr), st);
                 if (s2 != PU_OK) return s2;
-                PU_CUDA_TRY(cudaMemcpyAsync(sl.h_cnt.ptr, sl.d_cnt.ptr, nu * 6 * 8, cudaMemcpyDeviceToHost, st));
+                PU_CUDA_TRY(cudaMemcpyAsync(sl.h_cnt->ptr, sl.d_cnt->ptr, nu * 6 * 8, cudaMemcpyDeviceToHost, st));
                 PU_CUDA_TRY(cudaEventRecord(sl.ev, st));
                 return PU_OK;
             };
+            const auto t_enq = std::chrono::steady_clock::now();
             if ((rs = launch()) != PU_OK) break;
+            stt.enqueue_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_enq).count();
             sl.busy = true;
         }
         // the engine's device buffers go away with it: drain both slots before leaving the mode
