@@ -164,6 +164,12 @@ PU_API pu_status pu_ofdm_presynced_batch(pu_ofdm* h, const float* samples, size_
                                          const float* cfo_hz, const float* cfo_phase, float* llr_out,
                                          size_t llr_stride, float* snr_db, float* final_cfo_hz,
                                          pu_memspace space, void* stream);
+/* OFDMDemodulator::Impl::estimateCFOFromTraining(samples, training_symbols, 0) (src/ofdm/ofdm_sync.cpp:278-380) for B frames that start
+ * at the first training symbol: the CFO processPresynced adopts when none was set (demodulator.cpp:918-925: after reset(), with
+ * training_symbols >= 2).  cfo_hz[B]; 0 for training_symbols < 2, frames shorter than two symbols, or a correlation below 0.3.
+ * A caller reproduces `reset(); processPresynced(span, n)` with this value as cfo_hz and phase 0 in pu_ofdm_presynced_batch. */
+PU_API pu_status pu_ofdm_training_cfo_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, int training_symbols,
+                                            float* cfo_hz, pu_memspace space, void* stream);
 /* ---------------------------------------------------------------- dual-chirp synchronisation
  * sync::ChirpSync::detectDualChirp (src/sync/chirp_sync.hpp:349-506, configured as OFDMChirpWaveform::getChirpConfig,
  * src/waveform/ofdm_chirp_waveform.cpp:39-49) and the receive sequence of tools/test_iwaveform.cpp:127-160 on OFDM_CHIRP
@@ -206,7 +212,8 @@ PU_API pu_status pu_ofdm_acquire_batch(pu_ofdm* h, const float* samples, size_t 
  * demodulateSymbol with the coarse CFO, no LTS channel estimate) over every complete symbol after the preamble.
  * llr_out[B][llr_stride] (caller-zeroed rows; frames without sync stay untouched), n_llr[B] = soft bits available
  * (capped at llr_stride; < 648 is what the reference's tools count as a lost frame); sync_info / coarse_cfo_hz /
- * snr_db may be NULL. */
+ * snr_db may be NULL.  The preamble search looks at the first 40 000 samples of a row (beyond them the reference trims its
+ * buffer between calls); the data symbols behind a preamble found there run to the end of the row, whatever L is. */
 PU_API pu_status pu_ofdm_process_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, size_t chunk,
                                        float sync_threshold, float* llr_out, size_t llr_stride, int32_t* n_llr,
                                        int32_t* sync_info, float* coarse_cfo_hz, float* snr_db,

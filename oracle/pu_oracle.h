@@ -78,6 +78,7 @@ typedef struct {   /* optional per-stage dumps, same layout as ref_ofdm_presynce
     int32_t* carriers; float* lts_bins; float* h_lts; float* bins; float* h; float* eq; float* nv; float* scalars;
     int max_sym;
 } orc_stage_dump;
+float orc_ofdm_training_cfo(const orc_modem_config* c, const float* samples, size_t L, int num_symbols);
 long orc_ofdm_presynced(const orc_modem_config* c, const float* samples, size_t L, int training,
                         int cfo_mode, float cfo_hz, float cfo_phase, float* llr_out, size_t cap,
                         float* snr_db, float* final_cfo, orc_stage_dump* dump);

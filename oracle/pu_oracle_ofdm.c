@@ -755,11 +755,47 @@ static size_t rx_demod_symbol(rx_t* r, const cf* eq, float* out) {
     return o;
 }
 
+/* estimateCFOFromTraining(samples, num_symbols, coarse_cfo_hz = 0), src/ofdm/ofdm_sync.cpp:278-380: correlation of the FFT parts of the
+ * first two training symbols after a LOCAL mixer (NCO restarted at phase 0) has brought them to baseband. */
+float orc_ofdm_training_cfo(const orc_modem_config* c, const float* samples, size_t L, int num_symbols) {
+    modem_t m;
+    if (num_symbols < 2 || modem_init(&m, c)) return 0.0f;
+    size_t fft_len = (size_t)m.nfft, cp = (size_t)m.cp, sym_len = (size_t)m.sym_len, total = 2 * sym_len;
+    if (L < total) { modem_free(&m); return 0.0f; }
+    nco_t mix;
+    nco_init(&mix, (float)c->center_freq, (float)c->sample_rate);
+    cf* bb = (cf*)malloc(total * sizeof(cf));
+    for (size_t i = 0; i < total; ++i) bb[i] = cscale(samples[i], conjf(nco_next(&mix)));      /* samples[i] * std::conj(osc) */
+    cf P = MKC(0, 0);
+    float E1 = 0.0f, E2 = 0.0f;
+    for (size_t i = 0; i < fft_len; ++i) {
+        cf z1 = bb[cp + i], z2 = bb[sym_len + cp + i];
+        P = P + conjf(z1) * z2;
+        E1 += cnorm(z1);
+        E2 += cnorm(z2);
+    }
+    free(bb);
+    float corr_mag = cabsf(P) / sqrtf(E1 * E2 + 1e-10f);
+    float cfo = 0.0f;
+    if (corr_mag >= 0.3f) {
+        float phase = atan2f(cimagf(P), crealf(P));
+        cfo = (float)((double)(phase * (float)c->sample_rate) / ((double)2.0f * M_PI * (double)sym_len));
+        float max_cfo = (float)c->sample_rate / (2.0f * (float)sym_len);
+        cfo = fmaxf(-max_cfo, fminf(max_cfo, cfo));
+    }
+    modem_free(&m);
+    return cfo;
+}
+
 /* processPresynced, demodulator.cpp:854-985 with the oracle recipe's state at entry */
 long orc_ofdm_presynced(const orc_modem_config* c, const float* samples, size_t L, int training,
                         int cfo_mode, float cfo_hz, float cfo_phase, float* llr_out, size_t cap,
                         float* snr_db, float* final_cfo, orc_stage_dump* dump) {
-    if (cfo_mode != 1 && cfo_mode != 2) return -2; /* estimateCFOFromTraining (cfo_mode 0) is not restated: SURVEY §8(c) */
+    if (cfo_mode < 0 || cfo_mode > 2) return -2;
+    if (cfo_mode == 0) {   /* after reset(): chirp_cfo_estimated is false and freq_offset_hz is 0 -> estimateCFOFromTraining (:920-925) */
+        cfo_hz = (training >= 2) ? orc_ofdm_training_cfo(c, samples, L, training) : 0.0f;
+        cfo_phase = 0.0f;
+    }
     modem_t m;
     if (modem_init(&m, c)) return -1;
     if (L < (size_t)m.sym_len) { modem_free(&m); return 0; } /* :864-866 */

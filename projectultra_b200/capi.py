@@ -374,6 +374,15 @@ class OfdmDemodulator:
                                             _ptr(snr_db), _ptr(final_cfo), sp, _stream(sp)))
         return llr, snr_db, final_cfo
 
+    def training_cfo_batch(self, samples, training=2):
+        """pu_ofdm_training_cfo_batch: estimateCFOFromTraining of every row of samples [B, L] -> cfo_hz [B]."""
+        samples = _frames(samples)
+        B, L = samples.shape
+        out = _like(samples, (B,), np.float32, "float32")
+        sp = _space(samples, out)
+        check(lib().pu_ofdm_training_cfo_batch(self._h, _ptr(samples), C.c_size_t(B), C.c_size_t(L), int(training), _ptr(out), sp, _stream(sp)))
+        return out
+
     def tx_frame_len(self, ldpc, layout=0):
         n = C.c_size_t(0)
         check(lib().pu_ofdm_tx_batch(self._h, ldpc._h, None, C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), int(layout), C.c_float(0.0),

@@ -874,6 +874,46 @@ cudaError_t ofdm_tx_launch(const TxDev& t, const uint8_t* payload, size_t payloa
 std::vector<float> ofdm_modulate_frame(const OfdmPlan& p, int layout, const uint8_t* data, size_t n_bytes);   // ofdm_tx.cpp
 cfloat ofdm_constellation_point(uint32_t bits, uint32_t mod);
 
+// estimateCFOFromTraining(samples, num_symbols, coarse_cfo_hz = 0) (src/ofdm/ofdm_sync.cpp:278-380), what processPresynced runs when no
+// CFO was set (demodulator.cpp:920-925): a LOCAL mixer (NCO restarted at phase 0 = the head of the tabulated oscillator) brings the first
+// two training symbols to baseband, then P = sum conj(z1) z2, E1 = sum |z1|^2, E2 = sum |z2|^2 over their FFT parts -- ordered fp32 sums,
+// one lane each -- quality gate |P| / sqrt(E1 E2 + 1e-10) >= 0.3, CFO = arg(P) fs / (2 pi sym_len) clamped to +- fs / (2 sym_len).
+// One warp per frame; dynamic shared memory: 2 * nfft float2 per warp.
+__global__ void ofdm_training_cfo_kernel(OfdmDev d, const float* __restrict__ samples, size_t frame_stride, size_t B, float* __restrict__ cfo_out) {
+    extern __shared__ __align__(16) unsigned char tcfo_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t b = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (b >= B) return;
+    float2* z1 = reinterpret_cast<float2*>(tcfo_smem) + static_cast<size_t>(warp) * 2 * d.nfft;
+    float2* z2 = z1 + d.nfft;
+    const float* x = samples + b * frame_stride;
+    for (int i = lane; i < d.nfft; i += 32) {
+        const int n1 = d.cp + i, n2 = d.sym_len + d.cp + i;
+        const float2 o1 = __ldg(&d.nco[n1]), o2 = __ldg(&d.nco[n2]);
+        const float s1 = __ldg(&x[n1]), s2 = __ldg(&x[n2]);
+        z1[i] = make_float2(__fmul_rn(o1.x, s1), __fmul_rn(-o1.y, s1));      // samples[i] * std::conj(osc)
+        z2[i] = make_float2(__fmul_rn(o2.x, s2), __fmul_rn(-o2.y, s2));
+    }
+    __syncwarp();
+    float2 P = make_float2(0.0f, 0.0f);
+    float E = 0.0f;
+    if (lane == 0) for (int i = 0; i < d.nfft; ++i) P = cadd(P, cmul(cconj(z1[i]), z2[i]));
+    if (lane == 1) for (int i = 0; i < d.nfft; ++i) E = __fadd_rn(E, cnorm(z1[i]));
+    if (lane == 2) for (int i = 0; i < d.nfft; ++i) E = __fadd_rn(E, cnorm(z2[i]));
+    const float E1 = __shfl_sync(0xffffffffu, E, 1), E2 = __shfl_sync(0xffffffffu, E, 2);
+    if (lane != 0) return;
+    const float corr_mag = __fdiv_rn(cabs_ref(P), __fsqrt_rn(__fadd_rn(__fmul_rn(E1, E2), 1e-10f)));
+    float cfo = 0.0f;
+    if (corr_mag >= 0.3f) {
+        const float phase = refmath::atan2f_ref(P.y, P.x);
+        const double den = __dmul_rn(__dmul_rn(2.0, 3.14159265358979323846), static_cast<double>(d.sym_len));
+        cfo = static_cast<float>(__ddiv_rn(static_cast<double>(__fmul_rn(phase, d.sample_rate)), den));
+        const float max_cfo = __fdiv_rn(d.sample_rate, __fmul_rn(2.0f, static_cast<float>(d.sym_len)));
+        cfo = fmaxf(-max_cfo, fminf(max_cfo, cfo));
+    }
+    cfo_out[b] = cfo;
+}
+
 // frame windows of acquired frames: data symbols start at data_start and run to the end of the row
 __global__ void acquire_windows_kernel(const int4* __restrict__ acq, size_t B, int L, int sym_len, int llr_per_symbol, int llr_stride,
                                        int* __restrict__ start, int* __restrict__ nsym, int* __restrict__ n_llr) {
@@ -1485,9 +1525,19 @@ pu_status pu_ofdm_process_batch(pu_ofdm* h, const float* samples, size_t B, size
     if ((s = dcfo.upload(zi.data(), B)) != PU_OK) return s;
     if ((s = dstart.upload(zi.data(), B)) != PU_OK) return s;
     if ((s = dnsym.upload(zi.data(), B)) != PU_OK) return s;
-    s = pu_ofdm_acquire_batch(h, d_x, B, L, chunk, sync_threshold, static_cast<int32_t*>(dacq.p), static_cast<float*>(dcfo.p),
-                              PU_MEM_DEVICE, st);
-    if (s != PU_OK) return s;
+    {
+        // The search is replayed on the first 2 * OVERLAP_SAMPLES = 40 000 samples only: beyond them the reference starts trimming
+        // its buffer between calls (demodulator.cpp:551-555,593-597), which a whole-frame batch cannot replay.  A frame that
+        // synchronises inside that prefix -- every frame of the tools -- may be as long as it likes: the SYNCED state runs on L.
+        if ((s = h->ensure_acquire()) != PU_OK) return s;
+        pu::AcqDev a = h->acq;
+        if (sync_threshold > 0.0f) a.sync_threshold = sync_threshold;
+        const size_t avail = std::min<size_t>(L, 40000);
+        (void)cudaGetLastError();
+        PU_CUDA_TRY(pu::ofdm_acquire_launch(a, d_x, B, L, static_cast<int>(avail), static_cast<int>(std::min<size_t>(chunk, avail)),
+                                            static_cast<int4*>(dacq.p), static_cast<float*>(dcfo.p), st));
+        ctx->launches.fetch_add(1);
+    }
     pu::acquire_windows_kernel<<<static_cast<unsigned>((B + 255) / 256), 256, 0, st>>>(
         static_cast<const int4*>(dacq.p), B, static_cast<int>(L), p.sym_len, p.n_data * p.bps, static_cast<int>(llr_stride),
         static_cast<int*>(dstart.p), static_cast<int*>(dnsym.p), d_n);
@@ -1507,6 +1557,45 @@ pu_status pu_ofdm_process_batch(pu_ofdm* h, const float* samples, size_t B, size
     } else {
         if (sync_info) PU_CUDA_TRY(cudaMemcpy(sync_info, dacq.p, B * 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice));
         if (coarse_cfo_hz) PU_CUDA_TRY(cudaMemcpy(coarse_cfo_hz, dcfo.p, B * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    return PU_OK;
+}
+
+pu_status pu_ofdm_training_cfo_batch(pu_ofdm* h, const float* samples, size_t B, size_t L, int training_symbols, float* cfo_hz,
+                                     pu_memspace space, void* stream) {
+    PU_REQUIRE(h, "pu_ofdm_training_cfo_batch: NULL handle");
+    if (B == 0) return PU_OK;
+    PU_REQUIRE(samples && cfo_hz, "pu_ofdm_training_cfo_batch: NULL data pointer");
+    pu_ctx* ctx = h->ctx;
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    const pu::OfdmPlan& p = h->plan;
+    pu::DevMem dx, dc;
+    const float* d_x = samples;
+    float* d_c = cfo_hz;
+    pu_status s;
+    if (space == PU_MEM_HOST) {
+        std::vector<float> z(B, 0.0f);
+        if ((s = dx.upload(samples, B * L)) != PU_OK || (s = dc.upload(z.data(), B)) != PU_OK) return s;
+        d_x = static_cast<const float*>(dx.p);
+        d_c = static_cast<float*>(dc.p);
+    }
+    if (training_symbols < 2 || L < 2 * static_cast<size_t>(p.sym_len)) {          // ofdm_sync.cpp:279-282 (and nothing to correlate)
+        PU_CUDA_TRY(cudaMemsetAsync(d_c, 0, B * sizeof(float), st));
+    } else {
+        if ((s = h->ensure_nco(2)) != PU_OK) return s;
+        const int warps = 4;
+        const size_t smem = static_cast<size_t>(warps) * 2 * p.nfft * sizeof(float2);
+        static std::atomic<uint64_t> attr{0};
+        PU_CUDA_TRY(pu::smem_optin(attr, pu::ofdm_training_cfo_kernel, 96 * 1024));
+        (void)cudaGetLastError();
+        pu::ofdm_training_cfo_kernel<<<static_cast<unsigned>((B + warps - 1) / warps), warps * 32, smem, st>>>(h->dev, d_x, L, B, d_c);
+        ctx->launches.fetch_add(1);
+        PU_CUDA_TRY(cudaGetLastError());
+    }
+    if (space == PU_MEM_HOST) {
+        PU_CUDA_TRY(cudaMemcpyAsync(cfo_hz, d_c, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+        PU_CUDA_TRY(cudaStreamSynchronize(st));
     }
     return PU_OK;
 }

@@ -24,4 +24,4 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    return {n: np.load(os.path.join(d, n + "_golden.npz")) for n in ("ldpc", "ofdm", "misc", "psk", "acquire", "dpsk_acquire", "chirp", "mcdpsk_chirp", "frame")}
+    return {n: np.load(os.path.join(d, n + "_golden.npz")) for n in ("ldpc", "ofdm", "misc", "psk", "acquire", "dpsk_acquire", "chirp", "mcdpsk_chirp", "frame", "training_cfo")}

@@ -20,10 +20,14 @@
 #include "ultra/fec.hpp"
 #include "ultra/logging.hpp"
 #include "ultra/ofdm.hpp"
+#include "psk/dpsk.hpp"
+#include "waveform/waveform_factory.hpp"
 
 using namespace ultra;
 
+#include "waveform/ofdm_chirp_waveform.hpp"
 static int g_fail = 0, g_pass = 0;
+static bool close_llrs(const std::vector<float>& a, const std::vector<float>& b);
 #define CHECK(cond, ...)                                   \
     do {                                                   \
         if (cond) { ++g_pass; }                            \
@@ -226,14 +230,22 @@ static void ofdm_section() {
                       "%s trial %d decoded bytes / flags", c.name, trial);
             }
             // the IWaveform surface: configure -> setFrequencyOffset -> process -> getSoftBits (tools/test_iwaveform.cpp:597-806)
+            // against the reference's own OFDMChirpWaveform, which forces a differential modulation without pilots whatever it is given
+            // (ofdm_chirp_waveform.cpp:20-31,68-84): for the coherent cases both sides then demodulate the frame as DQPSK
             if (trial == 0) {
                 std::unique_ptr<IWaveform> wf = std::make_unique<pu::OfdmChirpWaveform>(cfg);
+                std::unique_ptr<IWaveform> rwf = std::make_unique<OFDMChirpWaveform>(cfg);
                 wf->configure(c.mod, c.rate);
-                wf->reset();
-                wf->setFrequencyOffset(0.0f);
+                rwf->configure(c.mod, c.rate);
+                wf->reset(); rwf->reset();
+                wf->setFrequencyOffset(0.0f); rwf->setFrequencyOffset(0.0f);
                 const bool wready = wf->process(SampleSpan(rx.data(), rx.size()));
+                const bool rready = rwf->process(SampleSpan(rx.data(), rx.size()));
                 const auto wsoft = wf->getSoftBits();
-                CHECK(wready == ref_ready && same_words(wsoft, soft), "%s IWaveform::process/getSoftBits", c.name);
+                const auto rsoft = rwf->getSoftBits();
+                CHECK(wready == rready && close_llrs(wsoft, rsoft) && wf->getModulation() == rwf->getModulation(), "%s IWaveform::process/getSoftBits (%d/%d, %zu/%zu)",
+                      c.name, (int)wready, (int)rready, wsoft.size(), rsoft.size());
+                if (!c.pilots) CHECK(wready == ref_ready && same_words(wsoft, soft), "%s IWaveform soft bits == OFDMDemodulator's", c.name);
                 CHECK(wf->getSamplesPerSymbol() == static_cast<int>(cfg.getSymbolDuration()) && wf->getCarrierCount() == static_cast<int>(cfg.num_carriers),
                       "%s IWaveform geometry", c.name);
                 SyncResult sr;
@@ -449,6 +461,182 @@ static void mcdpsk_section() {
     }
 }
 
+// ultra::WaveformFactory against pu::WaveformFactory: for every mode the factory knows, the reference's own IWaveform implementation
+// (src/waveform/*.cpp compiled unmodified into libpu_ref.so) and the drop-in are driven through the IWaveform interface with the
+// receive sequence of tools/test_iwaveform.cpp:127-160 (detectSync -> setFrequencyOffset -> process(span from start_sample) ->
+// getSoftBits) on the same noisy audio.
+static bool quiet_detect(IWaveform& w, SampleSpan audio, SyncResult& sr, float thr) {
+    std::fflush(stdout);
+    const int saved = dup(1), nul = open("/dev/null", O_WRONLY);
+    if (nul >= 0) { dup2(nul, 1); close(nul); }
+    const bool ok = w.detectSync(audio, sr, thr);
+    std::fflush(stdout);
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+    return ok;
+}
+static bool close_llrs(const std::vector<float>& a, const std::vector<float>& b) {   // 1e-4 relative, floor 0.5 (tests/test_ofdm_gpu.py)
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (std::fabs(a[i] - b[i]) > 1e-4f * std::max(std::fabs(b[i]), 0.5f)) return false;
+    return true;
+}
+static void factory_section() {
+    using protocol::WaveformMode;
+    CHECK(pu::WaveformFactory::getAvailableModes() == WaveformFactory::getAvailableModes(), "getAvailableModes");
+    for (WaveformMode m : {WaveformMode::OFDM_COX, WaveformMode::OTFS_EQ, WaveformMode::OTFS_RAW, WaveformMode::MFSK, WaveformMode::MC_DPSK,
+                           WaveformMode::OFDM_CHIRP, WaveformMode::AUTO}) {
+        CHECK(pu::WaveformFactory::isSupported(m) == WaveformFactory::isSupported(m), "isSupported %d", (int)m);
+        auto a = WaveformFactory::create(m);
+        auto b = pu::WaveformFactory::create(m);
+        CHECK((a != nullptr) == (b != nullptr) && (!a || a->getMode() == b->getMode()), "create(%d) maps to the same implementation", (int)m);
+    }
+    LDPCEncoder enc(CodeRate::R1_4);
+    std::mt19937 rng(4242);
+    int trial = 0;
+    for (WaveformMode mode : {WaveformMode::MC_DPSK, WaveformMode::OFDM_CHIRP, WaveformMode::OFDM_COX}) {
+        for (int with_cfg = 0; with_cfg < 2; ++with_cfg, ++trial) {
+            ModemConfig cfg;
+            WaveformPtr ref = with_cfg ? WaveformFactory::create(mode, cfg) : WaveformFactory::create(mode);
+            pu::WaveformPtr mine = with_cfg ? pu::WaveformFactory::create(mode, cfg) : pu::WaveformFactory::create(mode);
+            const int tag = static_cast<int>(mode) * 10 + with_cfg;
+            ref->configure(Modulation::DQPSK, CodeRate::R1_4);
+            mine->configure(Modulation::DQPSK, CodeRate::R1_4);
+            CHECK(ref->getMode() == mine->getMode() && ref->getModulation() == mine->getModulation() && ref->getCodeRate() == mine->getCodeRate(), "wf %d identity", tag);
+            CHECK(ref->getCarrierCount() == mine->getCarrierCount() && ref->getSamplesPerSymbol() == mine->getSamplesPerSymbol() &&
+                      ref->getPreambleSamples() == mine->getPreambleSamples() && ref->getMinSamplesForFrame() == mine->getMinSamplesForFrame(),
+                  "wf %d geometry (%d/%d carriers, %d/%d sps, %d/%d preamble, %d/%d min)", tag, ref->getCarrierCount(), mine->getCarrierCount(),
+                  ref->getSamplesPerSymbol(), mine->getSamplesPerSymbol(), ref->getPreambleSamples(), mine->getPreambleSamples(),
+                  ref->getMinSamplesForFrame(), mine->getMinSamplesForFrame());
+            const WaveformCapabilities ca = ref->getCapabilities(), cb = mine->getCapabilities();
+            CHECK(ca.requires_pilots == cb.requires_pilots && ca.supports_differential == cb.supports_differential && ca.min_snr_db == cb.min_snr_db &&
+                      ca.max_snr_db == cb.max_snr_db,
+                  "wf %d capabilities", tag);
+            if (mode != WaveformMode::OFDM_CHIRP)      // OFDM_CHIRP quotes a fixed 7200 bps (ofdm_chirp_waveform.cpp:60-72); the others compute it
+                CHECK(std::fabs(ref->getThroughput(CodeRate::R1_2) - mine->getThroughput(CodeRate::R1_2)) < 1e-3f * ref->getThroughput(CodeRate::R1_2),
+                      "wf %d throughput %.2f vs %.2f", tag, ref->getThroughput(CodeRate::R1_2), mine->getThroughput(CodeRate::R1_2));
+            Bytes payload(20);
+            for (auto& b : payload) b = static_cast<uint8_t>(rng() & 0xFF);
+            const Bytes coded = enc.encode(payload);
+            const Samples ref_pre = ref->generatePreamble(), ref_data = ref->modulate(coded);
+            const Samples pre = mine->generatePreamble(), data = mine->modulate(coded);
+            CHECK(pre.size() == ref_pre.size() && std::memcmp(pre.data(), ref_pre.data(), pre.size() * sizeof(float)) == 0, "wf %d generatePreamble (%zu vs %zu)", tag, pre.size(), ref_pre.size());
+            CHECK(data.size() == ref_data.size() && std::memcmp(data.data(), ref_data.data(), data.size() * sizeof(float)) == 0, "wf %d modulate (%zu vs %zu)", tag, data.size(), ref_data.size());
+            for (float snr : {20.0f, 9.0f}) {
+                Samples tx(static_cast<size_t>(200 + 137 * trial), 0.0f);
+                tx.insert(tx.end(), ref_pre.begin(), ref_pre.end());
+                tx.insert(tx.end(), ref_data.begin(), ref_data.end());
+                tx.insert(tx.end(), 700, 0.0f);
+                float mx = 0.0f;
+                for (float v : tx) mx = std::max(mx, std::fabs(v));
+                for (float& v : tx) v *= 0.5f / mx;                         // the tools' peak normalisation
+                const Samples rx = add_noise(tx, snr, 9000u + static_cast<uint32_t>(trial * 7) + static_cast<uint32_t>(snr));
+                const SampleSpan audio(rx.data(), rx.size());
+                ref->reset(); mine->reset();
+                SyncResult ra, rb;
+                const bool fa = quiet_detect(*ref, audio, ra, 0.15f), fb = quiet_detect(*mine, audio, rb, 0.15f);
+                CHECK(fa == fb, "wf %d snr %.0f detectSync %d vs %d", tag, snr, (int)fa, (int)fb);
+                if (!fa || !fb) continue;
+                CHECK(ra.start_sample == rb.start_sample && std::memcmp(&ra.cfo_hz, &rb.cfo_hz, 4) == 0 && ra.has_training == rb.has_training,
+                      "wf %d snr %.0f sync result: start %d vs %d, cfo %.6f vs %.6f", tag, snr, ra.start_sample, rb.start_sample, ra.cfo_hz, rb.cfo_hz);
+                ref->setFrequencyOffset(ra.cfo_hz);
+                mine->setFrequencyOffset(rb.cfo_hz);
+                if (ra.start_sample < 0 || static_cast<size_t>(ra.start_sample) >= rx.size()) continue;
+                const SampleSpan span(rx.data() + ra.start_sample, rx.size() - ra.start_sample);
+                const bool pa = ref->process(span), pb = mine->process(span);
+                const auto sa = ref->getSoftBits(), sb = mine->getSoftBits();
+                CHECK(pa == pb && sa.size() == sb.size(), "wf %d snr %.0f process %d vs %d, %zu vs %zu soft bits", tag, snr, (int)pa, (int)pb, sa.size(), sb.size());
+                const bool psk = mode == WaveformMode::MC_DPSK;
+                CHECK(psk ? same_words(sa, sb) : close_llrs(sb, sa), "wf %d snr %.0f soft bits differ", tag, snr);
+                CHECK(ref->isSynced() == mine->isSynced(), "wf %d snr %.0f isSynced", tag, snr);
+                if (!sa.empty() && sa.size() >= 648) {
+                    LDPCDecoder da(CodeRate::R1_4);
+                    pu::LDPCDecoder db(CodeRate::R1_4);
+                    const Bytes ba = da.decodeSoft(std::vector<float>(sa.begin(), sa.begin() + 648)), bb = db.decodeSoft(std::vector<float>(sb.begin(), sb.begin() + 648));
+                    CHECK(da.lastDecodeSuccess() == db.lastDecodeSuccess() && (!da.lastDecodeSuccess() || ba == bb), "wf %d snr %.0f decoded payload", tag, snr);
+                    if (snr >= 20.0f) CHECK(da.lastDecodeSuccess() && std::equal(payload.begin(), payload.end(), bb.begin()), "wf %d snr %.0f payload recovered", tag, snr);
+                }
+            }
+        }
+    }
+}
+
+// ultra::DPSKDemodulator / ultra::MultiCarrierDPSKDemodulator against the pu:: classes of the same names: the receive sequence of
+// tools/test_dpsk_snr.cpp:66-73 (findPreamble -> demodulateSoft from the returned offset) and setChirpDetected -> process -> getSoftBits.
+static void psk_class_section() {
+    LDPCEncoder enc(CodeRate::R1_4);
+    std::mt19937 rng(99);
+    for (int mod = 0; mod < 3; ++mod) {
+        DPSKConfig rc;
+        rc.samples_per_symbol = 384;
+        rc.modulation = static_cast<DPSKModulation>(mod);
+        pu::DPSKConfig pc;
+        pc.samples_per_symbol = 384;
+        pc.modulation = mod;
+        DPSKModulator tx(rc);
+        Bytes payload(20);
+        for (auto& b : payload) b = static_cast<uint8_t>(rng() & 0xFF);
+        const Bytes coded = enc.encode(payload);
+        Samples wave(static_cast<size_t>(500 + 211 * mod), 0.0f);
+        const Samples pre = tx.generatePreamble(), data = tx.modulate(ByteSpan(coded.data(), coded.size()));
+        wave.insert(wave.end(), pre.begin(), pre.end());
+        wave.insert(wave.end(), data.begin(), data.end());
+        wave.insert(wave.end(), 300, 0.0f);
+        for (float snr : {15.0f, 3.0f}) {
+            const Samples rx = add_noise(wave, snr, 3100u + static_cast<uint32_t>(10 * mod) + static_cast<uint32_t>(snr));
+            DPSKDemodulator ref(rc);
+            pu::DPSKDemodulator mine(pc);
+            const SampleSpan audio(rx.data(), rx.size());
+            const int a = ref.findPreamble(audio), b = mine.findPreamble(audio);
+            CHECK(a == b, "dpsk mod %d snr %.0f findPreamble %d vs %d", mod, snr, a, b);
+            if (a < 0 || a != b) continue;
+            const float ca = ref.getEstimatedCFO(), cb = mine.getEstimatedCFO();
+            CHECK(std::memcmp(&ca, &cb, 4) == 0, "dpsk mod %d snr %.0f cfo %.6f vs %.6f", mod, snr, ca, cb);
+            // demodulateSoft in two pieces: the second continues from the last symbol of the first (prev_symbol_)
+            const size_t sps = 384, nsym = (rx.size() - a) / sps, half = nsym / 2;
+            auto s1 = ref.demodulateSoft(SampleSpan(rx.data() + a, half * sps));
+            auto s2 = ref.demodulateSoft(SampleSpan(rx.data() + a + half * sps, (nsym - half) * sps));
+            auto t1 = mine.demodulateSoft(SampleSpan(rx.data() + a, half * sps));
+            auto t2 = mine.demodulateSoft(SampleSpan(rx.data() + a + half * sps, (nsym - half) * sps));
+            CHECK(same_words(s1, t1) && same_words(s2, t2), "dpsk mod %d snr %.0f soft bits (%zu+%zu vs %zu+%zu)", mod, snr, s1.size(), s2.size(), t1.size(), t2.size());
+            // reset() + setReferenceSymbol + hard decisions
+            ref.reset(); mine.reset();
+            ref.setReferenceSymbol(SampleSpan(rx.data() + a - sps, sps));
+            mine.setReferenceSymbol(SampleSpan(rx.data() + a - sps, sps));
+            CHECK(ref.demodulate(SampleSpan(rx.data() + a, 64 * sps)) == mine.demodulate(SampleSpan(rx.data() + a, 64 * sps)), "dpsk mod %d snr %.0f demodulate", mod, snr);
+        }
+    }
+    for (int nc : {8, 13}) {
+        MultiCarrierDPSKConfig rc;
+        rc.num_carriers = nc;
+        pu::McDpskConfig pc;
+        pc.num_carriers = nc;
+        MultiCarrierDPSKModulator tx(rc);
+        Bytes payload(20);
+        for (auto& b : payload) b = static_cast<uint8_t>(rng() & 0xFF);
+        const Bytes coded = enc.encode(payload);
+        Samples wave = tx.generateTrainingSequence();
+        const Samples refsym = tx.generateReferenceSymbol(), data = tx.modulate(coded);
+        wave.insert(wave.end(), refsym.begin(), refsym.end());
+        wave.insert(wave.end(), data.begin(), data.end());
+        const Samples rx = add_noise(wave, 12.0f, 7700u + static_cast<uint32_t>(nc));
+        for (float cfo : {0.0f, 3.5f}) {
+            MultiCarrierDPSKDemodulator ref(rc);
+            pu::MultiCarrierDPSKDemodulator mine(pc);
+            ref.setChirpDetected(cfo);
+            mine.setChirpDetected(cfo);
+            // fed in two pieces: the first is too short for a frame
+            const size_t cut = 6 * 512;
+            const bool a1 = ref.process(SampleSpan(rx.data(), cut)), b1 = mine.process(SampleSpan(rx.data(), cut));
+            const bool a2 = ref.process(SampleSpan(rx.data() + cut, rx.size() - cut)), b2 = mine.process(SampleSpan(rx.data() + cut, rx.size() - cut));
+            CHECK(a1 == b1 && a2 == b2 && ref.isFrameReady() == mine.isFrameReady(), "mcdpsk class nc %d cfo %.1f process %d%d vs %d%d", nc, cfo, a1, a2, b1, b2);
+            const float ea = ref.getEstimatedCFO(), eb = mine.getEstimatedCFO();
+            CHECK(std::memcmp(&ea, &eb, 4) == 0, "mcdpsk class nc %d cfo %.1f estimated cfo %.6f vs %.6f", nc, cfo, ea, eb);
+            CHECK(same_words(ref.getSoftBits(), mine.getSoftBits()), "mcdpsk class nc %d cfo %.1f soft bits", nc, cfo);
+            CHECK(ref.isSynced() == mine.isSynced(), "mcdpsk class nc %d cfo %.1f state after getSoftBits", nc, cfo);
+        }
+    }
+}
+
 int main() {
     setLogLevel(LogLevel::ERROR);
     if (!std::freopen("/dev/null", "w", stderr)) return 2;   // the reference prints unconditionally on the hot path
@@ -459,6 +647,8 @@ int main() {
         process_section();
         chirp_section();
         mcdpsk_section();
+        factory_section();
+        psk_class_section();
     } catch (const std::exception& e) {
         std::printf("EXCEPTION: %s\n", e.what());
         return 2;

@@ -293,8 +293,39 @@ def frame_vectors():
     np.savez_compressed(os.path.join(HERE, "frame_golden.npz"), **out)
 
 
+TRAINING_CFO_CASES = [("m1", R.DQPSK, R.R1_2, 40, 0.0, 20.0), ("m1", R.DQPSK, R.R1_2, 40, 12.0, 6.0), ("m1", R.QAM16, R.R1_2, 40, -7.5, 15.0),
+                      ("m3", R.QAM32, R.R3_4, 60, 3.0, 18.0), ("m3", R.DQPSK, R.R3_4, 60, -7.5, 2.0), ("m1", R.D8PSK, R.R1_2, 40, 3.0, -20.0)]
+
+
+def training_cfo_frame(i):
+    preset, mod, rate, nbytes, tx_cfo, snr = TRAINING_CFO_CASES[i]
+    rng = np.random.default_rng(4400 + i)
+    cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    cfg.tx_cfo_hz = tx_cfo
+    return cfg, rng.integers(0, 256, nbytes, dtype=np.uint8), rate, snr, rng
+
+
+def training_cfo_vectors():
+    """`reset(); processPresynced(span, 2)` WITHOUT setFrequencyOffset: the reference estimates the CFO from the two training symbols
+    (estimateCFOFromTraining, src/ofdm/ofdm_sync.cpp:278-380).  Stored: the received frame, the CFO the reference adopts (as
+    getFrequencyOffset() reports it for the differential no-pilot modes, whose tracker never moves it) and all soft bits."""
+    out = {}
+    for i in range(len(TRAINING_CFO_CASES)):
+        cfg, data, rate, snr, rng = training_cfo_frame(i)
+        rx = awgn(R.ofdm_tx(cfg, R.ldpc_encode(rate, data), 0), snr, rng)
+        llr, snr_db, fc = R.ofdm_presynced(cfg, rx, 2, 0)
+        out["c%d_cfg" % i] = np.frombuffer(bytes(cfg), dtype=np.uint8).copy()
+        out["c%d_rx" % i] = rx
+        out["c%d_llr" % i] = llr
+        out["c%d_final_cfo" % i] = np.float32(fc)
+    np.savez_compressed(os.path.join(HERE, "training_cfo_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "build oracle/_ref first: make -C oracle/ref_build"
+    if "--only-training-cfo" in sys.argv:
+        training_cfo_vectors()
+        sys.exit(0)
     ldpc_vectors()
     ofdm_vectors()
     misc_vectors()
@@ -304,6 +335,7 @@ if __name__ == "__main__":
     chirp_vectors()
     mcdpsk_got_chirp_vectors()
     frame_vectors()
+    training_cfo_vectors()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -166,6 +166,14 @@ def ofdm_presynced(cfg, samples, training=2, cfo_mode=1, cfo_hz=0.0, cfo_phase=0
     return out[:n].copy(), snr.value, fc.value
 
 
+def ofdm_training_cfo(cfg, samples, num_symbols=2):
+    """estimateCFOFromTraining(samples, num_symbols, 0) (src/ofdm/ofdm_sync.cpp:278-380)."""
+    x = _f32(samples)
+    f = lib().orc_ofdm_training_cfo
+    f.restype = C.c_float
+    return float(f(C.byref(cfg), _p(x, C.c_float), C.c_size_t(len(x)), int(num_symbols)))
+
+
 def ofdm_process(cfg, samples, chunk=960, sync_threshold=0.0):
     """OFDMDemodulator::process in chunk-sample pieces + getSoftBits() (first <= 648 soft bits):
     (llr, synced, sync_offset, coarse_cfo, data_start, calls)."""

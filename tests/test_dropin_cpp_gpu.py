@@ -20,12 +20,29 @@ def test_cpp_dropin_driver_all_pass():
     assert r.returncode == 0 and "ALL PASS" in r.stdout, tail
 
 
+@pytest.mark.gpu
+@pytest.mark.ref
+def test_reference_multiblock_ldpc_test_runs_unmodified_on_the_dropin_classes():
+    """/root/reference/tests/test_multiblock_ldpc.cpp compiled UNMODIFIED against tests/cpp/shim/ultra/{fec,ofdm}.hpp (aliases of the
+    pu:: classes; no reference object code linked): the reference's own assertions -- 5 rates x {1, 2, 5} blocks, boundary bytes,
+    protocol frame sizes, and the full modem pipeline generatePreamble + modulate -> process -> getSoftBits -> decodeSoft for
+    60...279-byte frames -- must all pass on libpu_b200.so."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "test_multiblock_ldpc_pu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/test_multiblock_ldpc_pu not built (needs the reference sources)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    tail = "\n".join(r.stdout.splitlines()[-30:])
+    assert r.returncode == 0 and "ALL TESTS PASSED" in r.stdout, tail + r.stderr[-2000:]
+
+
 def test_dropin_header_compiles_standalone(tmp_path):
     """Without the reference headers the drop-in header must still compile (stand-alone type mirrors) and link."""
     src = tmp_path / "t.cpp"
     src.write_text('#include "pu/pu_dropin.hpp"\nint main() { pu::ChannelInterleaver ci(60, 648); pu::Interleaver il(6, 108);\n'
                    'pu::LDPCEncoder e(pu::CodeRate::R1_2); auto c = e.encode(pu::Bytes(40, 0x5A));\n'
-                   'return (c.size() == 81 && ci.getStep() == 181 && il.getPermutation(1) == 6) ? 0 : 1; }\n')
+                   'pu::WaveformPtr (*mk)(pu::protocol::WaveformMode) = &pu::WaveformFactory::create;   // needs a GPU to call\n'
+                   'return (c.size() == 81 && ci.getStep() == 181 && il.getPermutation(1) == 6 && pu::WaveformFactory::isSupported(pu::protocol::WaveformMode::AUTO)'
+                   ' && sizeof(pu::DPSKDemodulator) > 0 && sizeof(pu::MultiCarrierDPSKDemodulator) > 0 && sizeof(pu::OFDMNvisWaveform) > 0 && mk != nullptr) ? 0 : 1; }\n')
     exe = tmp_path / "t"
     lib = os.path.join(ROOT, "projectultra_b200")
     from projectultra_b200 import build

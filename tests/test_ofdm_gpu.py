@@ -284,3 +284,31 @@ def test_warp_granular_kernel_matches_cta_kernel(ctx, preset, mod):
             assert same_bits(llr[b, :n], dbg["llr"][:n]), (b, float(cfo[b]), Lcut, training)
             if dbg["n_sym"]:
                 assert same_bits(fc[b:b + 1], dbg["scalars"][-1, 1:2]), (b, "tracked CFO")
+
+
+def test_training_cfo_estimate_and_presynced_without_preset_cfo(ctx, golden):
+    """pu_ofdm_training_cfo_batch == estimateCFOFromTraining bit for bit (ordered fp32 sums, atan2f restatement), and presynced with that
+    CFO reproduces `reset(); processPresynced(span, 2)` of the reference (golden vectors from the compiled reference + the oracle)."""
+    import torch
+    from projectultra_b200 import capi
+    g = golden["training_cfo"]
+    n = len([k for k in g.files if k.endswith("_rx")])
+    for i in range(n):
+        cfg = R.ModemConfig.from_buffer_copy(bytes(g["c%d_cfg" % i]))
+        dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+        rx = g["c%d_rx" % i]
+        want_cfo = np.float32(O.ofdm_training_cfo(cfg, rx, 2))
+        got = dem.training_cfo_batch(rx[None, :])
+        assert got[0].view(np.uint32) == want_cfo.view(np.uint32), (i, got, want_cfo)
+        dev = dem.training_cfo_batch(torch.from_numpy(np.stack([rx, rx * np.float32(0.5), np.zeros_like(rx)])).cuda())
+        torch.cuda.synchronize()
+        dev = dev.cpu().numpy()
+        assert dev[0].view(np.uint32) == want_cfo.view(np.uint32) and dev[2] == 0.0
+        assert dev[1].view(np.uint32) == np.float32(O.ofdm_training_cfo(cfg, rx * np.float32(0.5), 2)).view(np.uint32)
+        assert dem.training_cfo_batch(rx[None, :], training=1)[0] == 0.0
+        llr, _, fc = dem.presynced_batch(rx[None, :], 2, got, np.zeros(1, np.float32))
+        want = g["c%d_llr" % i]
+        bad = llr_mismatches(llr[0][:len(want)], want)
+        assert llr.shape[1] == len(want) and len(bad) == 0, (i, bad[:10])
+        if cfg.use_pilots == 0:
+            assert fc[0].view(np.uint32) == g["c%d_final_cfo" % i].view(np.uint32)

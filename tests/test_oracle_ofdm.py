@@ -168,3 +168,38 @@ def test_chirp_sync_matches_reference():
         assert (ri == oi).all() and _same_words(np.float32(rc), np.float32(oc)) and _same_words(rl, ol), (snr, lead, tx_cfo, ri, oi)
         found += int(oi[0])
     assert found >= 3
+
+
+def test_training_cfo_path_against_golden(golden):
+    """reset(); processPresynced(span, 2) without setFrequencyOffset -> estimateCFOFromTraining (ofdm_sync.cpp:278-380): the oracle's
+    restatement reproduces the reference's soft bits and adopted CFO bit for bit (vectors generated from the compiled reference)."""
+    g = golden["training_cfo"]
+    n = len([k for k in g.files if k.endswith("_rx")])
+    assert n >= 6
+    for i in range(n):
+        cfg = R.ModemConfig.from_buffer_copy(bytes(g["c%d_cfg" % i]))
+        rx = g["c%d_rx" % i]
+        llr, snr, fc = O.ofdm_presynced(cfg, rx, 2, 0)
+        want = g["c%d_llr" % i]
+        assert len(llr) == len(want) and (llr.view(np.uint32) == want.view(np.uint32)).all(), i
+        assert np.float32(fc).view(np.uint32) == g["c%d_final_cfo" % i].view(np.uint32), i
+
+
+@pytest.mark.ref
+def test_training_cfo_path_against_compiled_reference():
+    from golden.make_golden import awgn
+    for k, (mod, preset, tx_cfo, snr) in enumerate(((R.DQPSK, "m1", 0.0, 25.0), (R.DQPSK, "m1", 12.0, 0.0), (R.QAM16, "m1", 3.0, 8.0),
+                                                    (R.QAM32, "m3", -7.5, 12.0), (R.DBPSK, "m3", 3.0, 4.0), (R.QPSK, "m1", -7.5, 10.0))):
+        rate = R.R1_2 if preset == "m1" else R.R3_4
+        cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+        cfg.tx_cfo_hz = tx_cfo
+        rng = np.random.default_rng(900 + k)
+        rx = awgn(O.ofdm_tx(cfg, O.ldpc_encode(rate, rng.integers(0, 256, 40, dtype=np.uint8)), 0), snr, rng)
+        a, _, fa = R.ofdm_presynced(cfg, rx, 2, 0)
+        b, _, fb = O.ofdm_presynced(cfg, rx, 2, 0)
+        assert len(a) == len(b) and (a.view(np.uint32) == b.view(np.uint32)).all(), k
+        assert np.float32(fa).view(np.uint32) == np.float32(fb).view(np.uint32), k
+        # one training symbol: no estimate, CFO 0 (ofdm_sync.cpp:279-282)
+        a1, _, f1 = R.ofdm_presynced(cfg, rx, 1, 0)
+        b1, _, g1 = O.ofdm_presynced(cfg, rx, 1, 0)
+        assert (a1.view(np.uint32) == b1.view(np.uint32)).all() and f1 == g1

@@ -28,6 +28,7 @@ sweepsmoke) ( time projectultra_b200/pu_sweep --table smoke --trials 8192 --bloc
 sweep2) for r in 0 1; do RANK=$r WORLD_SIZE=2 LOCAL_RANK=$r MASTER_PORT=29700 projectultra_b200/pu_sweep --table smoke --trials 8192 --block 1024 --rendezvous /tmp --out $OUT/sweep2.jsonl > $OUT/sweep2_r$r.log 2>&1 & done; wait; tail -2 $OUT/sweep2_r0.log $OUT/sweep2_r1.log; tail -1 $OUT/sweep2.jsonl;;
 bench2) python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus 2 > $OUT/bench2.json 2> $OUT/bench2.err; tail -c 2500 $OUT/bench2.json; tail -3 $OUT/bench2.err;;
 chantests) ( time python -m pytest tests/test_channel.py tests/test_linksim_gpu.py tests/test_sweep_gpu.py -q -x ) > $OUT/pytest_chan.log 2>&1; tail -6 $OUT/pytest_chan.log;;
+dropin) ( time python -m pytest tests/test_dropin_cpp_gpu.py tests/test_ofdm_gpu.py -q -x ) > $OUT/pytest_dropin.log 2>&1; tail -30 $OUT/pytest_dropin.log; oracle/_ref/dropin_driver > $OUT/dropin_driver.log 2>&1; tail -30 $OUT/dropin_driver.log; oracle/_ref/test_multiblock_ldpc_pu > $OUT/multiblock.log 2>&1; tail -12 $OUT/multiblock.log;;
 *) echo "unknown: $w";;
 esac; done
 ls -la $OUT
