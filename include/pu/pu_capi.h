@@ -272,6 +272,13 @@ PU_API pu_status pu_dpsk_receive_batch(pu_dpsk* h, const float* samples, size_t 
                                        pu_memspace space, void* stream);
 PU_API pu_status pu_dpsk_tx(const pu_dpsk_config* cfg, int layout, const uint8_t* data, size_t n_bytes, float* out,
                             size_t out_cap, size_t* out_len);
+/* Batched transmitter on the GPU: LDPCEncoder::encode of one block (payload zero-padded to k bits) followed by
+ * DPSKModulator::generatePreamble() + modulate() (dpsk.hpp:118-153,212-279) for B payloads at once, i.e. the frame of
+ * tools/test_dpsk_snr.cpp:40-60 with a fresh payload per trial; peak > 0 rescales every frame to that peak amplitude.  `code`
+ * supplies the code rate.  out[B][out_stride] receives *frame_len samples per row; B = 0 queries *frame_len.  Waveforms are
+ * bit-identical to pu_ldpc_encode + pu_dpsk_tx(layout 0). */
+PU_API pu_status pu_dpsk_tx_batch(pu_dpsk* h, const pu_ldpc* code, const uint8_t* payload, size_t payload_stride, size_t payload_bytes,
+                                  size_t B, float peak, float* out, size_t out_stride, size_t* frame_len, pu_memspace space, void* stream);
 
 /* ---------------------------------------------------------------- multi-carrier DPSK (externally timed)
  * Replaces ultra::MultiCarrierDPSKDemodulator (src/psk/multi_carrier_dpsk.hpp:258-701) on frames that start at the
@@ -316,6 +323,10 @@ PU_API pu_status pu_mcdpsk_chirp_receive_batch(pu_mcdpsk* h, const float* sample
 /* MultiCarrierDPSKModulator (:91-257), host: generateTrainingSequence + generateReferenceSymbol + modulate(data). */
 PU_API pu_status pu_mcdpsk_tx(const pu_mcdpsk_config* cfg, const uint8_t* data, size_t n_bytes, float* out, size_t out_cap,
                               size_t* out_len);
+/* The same on the GPU for B payloads: LDPCEncoder::encode + generateTrainingSequence + generateReferenceSymbol + modulate
+ * (multi_carrier_dpsk.hpp:118-243); bit-identical to pu_ldpc_encode + pu_mcdpsk_tx.  Arguments as pu_dpsk_tx_batch. */
+PU_API pu_status pu_mcdpsk_tx_batch(pu_mcdpsk* h, const pu_ldpc* code, const uint8_t* payload, size_t payload_stride, size_t payload_bytes,
+                                    size_t B, float peak, float* out, size_t out_stride, size_t* frame_len, pu_memspace space, void* stream);
 
 /* ---------------------------------------------------------------- channel simulator
  * Replaces sim::WattersonChannel (src/sim/hf_channel.hpp:34-299) for batches of frames.  POD mirror of

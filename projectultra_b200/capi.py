@@ -571,6 +571,29 @@ def _like(samples, shape, dtype_np, dtype_torch_name):
     return np.zeros(shape, dtype_np)
 
 
+def _psk_tx_batch(fn, h, ldpc, payload, peak, out):
+    """Shared body of DpskDemodulator.tx_batch / McDpskDemodulator.tx_batch (pu_dpsk_tx_batch / pu_mcdpsk_tx_batch)."""
+    n = C.c_size_t(0)
+    check(fn(h, ldpc._h, None, C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_float(0.0), None, C.c_size_t(0), C.byref(n), 0, None))
+    L = n.value
+    tor = _is_torch(payload)
+    if tor:
+        import torch
+        assert payload.dtype == torch.uint8 and payload.dim() == 2
+        B = payload.shape[0]
+        out = torch.empty((B, L), dtype=torch.float32, device=payload.device) if out is None else out
+        stride = payload.stride(0)
+    else:
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        B = payload.shape[0]
+        out = np.zeros((B, L), np.float32) if out is None else out
+        stride = payload.shape[1]
+    sp = _space(payload, out)
+    check(fn(h, ldpc._h, _ptr(payload), C.c_size_t(stride), C.c_size_t(payload.shape[1]), C.c_size_t(B), C.c_float(peak), _ptr(out),
+             C.c_size_t(L), C.byref(n), sp, _stream(sp)))
+    return out
+
+
 class DpskDemodulator:
     """pu_dpsk: batched drop-in for ultra::DPSKDemodulator::demodulateSoft with external timing."""
 
@@ -590,6 +613,10 @@ class DpskDemodulator:
             self.close()
         except Exception:
             pass
+
+    def tx_batch(self, ldpc, payload, peak=0.0, out=None):
+        """pu_dpsk_tx_batch: LDPC encode + Barker preamble + DPSK modulate for every row of payload [B, bytes] on the GPU."""
+        return _psk_tx_batch(lib().pu_dpsk_tx_batch, self._h, ldpc, payload, peak, out)
 
     def n_llr(self, L, data_start):
         return max(0, (L - data_start) // self.cfg.samples_per_symbol) * self.bits_per_symbol
@@ -657,6 +684,10 @@ class McDpskDemodulator:
             self.close()
         except Exception:
             pass
+
+    def tx_batch(self, ldpc, payload, peak=0.0, out=None):
+        """pu_mcdpsk_tx_batch: LDPC encode + training + reference + MC-DPSK modulate for every row of payload [B, bytes] on the GPU."""
+        return _psk_tx_batch(lib().pu_mcdpsk_tx_batch, self._h, ldpc, payload, peak, out)
 
     def n_llr(self, L):
         c = self.cfg

@@ -333,13 +333,14 @@ LdpcLayout make_ldpc_layout(const LdpcCode& code) {
     L.inf_slot = L.kpad;
     L.tot_words = L.kpad + 32;    // + one +INF word per bank
     L.scratch_slot = L.dv * L.kpad;
-    L.msg_words = L.dv * L.kpad + 32;
+    L.msg_words = L.dv * L.kpad + (L.threads + 31) / 32 * 32 * kMaxInfoEdgesPerCheck;   // + scratch words of the absent edges: 32 per (warp, slot)
     L.cn_ninfo.assign(L.threads, 0);
     L.cn_check.assign(L.threads, 0);
     L.cn_rd.assign(static_cast<size_t>(kMaxInfoEdgesPerCheck) * L.threads, static_cast<uint16_t>(L.inf_slot));
     L.cn_wr.assign(static_cast<size_t>(kMaxInfoEdgesPerCheck) * L.threads, 0);
     for (int e = 0; e < kMaxInfoEdgesPerCheck; ++e)
-        for (int p = 0; p < L.threads; ++p) L.cn_wr[static_cast<size_t>(e) * L.threads + p] = static_cast<uint16_t>(L.scratch_slot + (p & 31));
+        for (int p = 0; p < L.threads; ++p)
+            L.cn_wr[static_cast<size_t>(e) * L.threads + p] = static_cast<uint16_t>(L.scratch_slot + ((p >> 5) * kMaxInfoEdgesPerCheck + e) * 32 + (p & 31));
 
     // ---- per warp: colour the (check, bank) multigraph; the colour of an edge is its instruction slot e
     L.conflicts = 0;
@@ -375,18 +376,23 @@ LdpcLayout make_ldpc_layout(const LdpcCode& code) {
             emit_real(r.p, r.e_row, col.add_conflicting(r.p - p0));
             ++L.conflicts;
         }
-        // absent edges (rows shorter than the warp's longest, lanes past the last check) read a +INF word and write a
-        // scratch word in a bank that no real edge of the same instruction uses; all of them share one address, so
-        // they add no shared-memory wavefront
+        // absent edges (rows shorter than the warp's longest, lanes past the last check) read a +INF word in a bank that no real
+        // edge of the same instruction uses (one shared read-only address: no extra wavefront) and write a scratch word of their
+        // OWN: every (warp, instruction slot) has 32 scratch words in 32 banks, and an instruction has exactly as many unused banks as
+        // it has absent edges, so every absent lane gets a distinct unused bank -- no wavefront added, and no two threads ever store
+        // to the same word (a shared dump word is a write-write race, harmless but flagged by compute-sanitizer --tool racecheck)
         for (int e = 0; e < ne_w[w] && e < kMaxInfoEdgesPerCheck; ++e) {
             int fb = -1;
             for (int b = 0; b < 32; ++b)
                 if (!(used[e] & (1u << b))) { fb = b; break; }
             if (fb < 0) continue;
+            int nb = 0;
             for (int lane = 0; lane < 32 && p0 + lane < L.threads; ++lane) {
                 if (real[static_cast<size_t>(e) * 32 + lane]) continue;
+                while (nb < 32 && (used[e] & (1u << nb))) ++nb;
+                const int wb = nb < 32 ? nb++ : fb;
                 L.cn_rd[static_cast<size_t>(e) * L.threads + p0 + lane] = static_cast<uint16_t>(L.inf_slot + fb);
-                L.cn_wr[static_cast<size_t>(e) * L.threads + p0 + lane] = static_cast<uint16_t>(L.scratch_slot + fb);
+                L.cn_wr[static_cast<size_t>(e) * L.threads + p0 + lane] = static_cast<uint16_t>(L.scratch_slot + (w * kMaxInfoEdgesPerCheck + e) * 32 + wb);
             }
         }
     }

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(T, MINB) ldpc_flood_reg_kernel(LdpcRegDev t, c
                                                           uint8_t* __restrict__ info, size_t info_stride,
                                                           uint8_t* __restrict__ ok, int32_t* __restrict__ iters, int max_iter) {
     extern __shared__ float smem[];
-    constexpr int kMsgWords = DV * KP + 32;
+    constexpr int kMsgWords = DV * KP + (T + 31) / 32 * 32 * kMaxInfoEdgesPerCheck;     // + 32 scratch words per (warp, edge slot)
     const int K = t.k, M = t.m;
     float* msg = smem;                       // [DV][KP] + scratch row
     float* tot = smem + kMsgWords;           // [KP] + the +INF word

@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                     }
                 }
                 for (int i = d.cp + NFFT; i < d.sym_len; i += 32) (void)window(min(32, d.sym_len - i));
+                __syncwarp();                    // every lane has read S.rot_phase (the shuffles of window() order execution, not memory)
                 if (lane == 0) S.rot_phase = ph;
                 __syncwarp();
             }

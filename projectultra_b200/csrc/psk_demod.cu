@@ -526,44 +526,9 @@ __global__ void __launch_bounds__(kCfoThreads) mcdpsk_cfo_correct_kernel(Hilbert
     }
 }
 
-struct PskDevMem {
-    void* p = nullptr;
-    ~PskDevMem() { if (p) cudaFree(p); }
-    template <class T>
-    pu_status upload(const T* src, size_t n) {
-        if (p) { cudaFree(p); p = nullptr; }
-        PU_CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
-        if (n) {
-            // pageable H2D copies may return before the DMA has landed and the kernels run on non-blocking streams: wait for it
-            PU_CUDA_TRY(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
-            PU_CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));
-        }
-        return PU_OK;
-    }
-};
-
 }  // namespace pu
 
-struct pu_dpsk {
-    pu_ctx* ctx = nullptr;
-    int device = 0;
-    pu_dpsk_config cfg{};
-    pu::PskDevMem d_cos, d_sin;
-    pu::PskDevMem d_mf;        // matched-filter template of refineTimingWithMatchedFilter (cfo 0), 6 symbols
-    float mf_energy = 0.0f;
-    pu::Buffer corr;
-};
-
-struct pu_mcdpsk {
-    pu_ctx* ctx = nullptr;
-    int device = 0;
-    pu_mcdpsk_config cfg{};
-    pu::PskDevMem d_mixer, d_expected;
-    pu::Buffer corr;
-    pu::PskDevMem d_chirp;     // dual-chirp templates (built on first use)
-    pu::ChirpDev chirp{};
-    bool chirp_ready = false;
-};
+#include "psk_handles.h"
 
 // Shared host-staging helper: samples (+ up to two per-frame float arrays) up, `out_floats` per frame (+ one per-frame
 // float array) back.

@@ -184,7 +184,7 @@ class LinkSim:
         assert not self.acquire or self.kind == "dpsk", "acquire=True is the DPSK Barker path; OFDM uses layout='sc'"
         self.fresh_payload = bool(fresh_payload)
         self.peak = peak
-        assert not self.fresh_payload or self.kind == "ofdm", "the GPU transmitter covers the OFDM waveforms"
+        assert not self.fresh_payload or self.layout != "chirp", "fresh payloads behind a chirp: use the host-built pool"
         self.payload_bytes = payload_bytes
         rng = np.random.default_rng(pool_seed)
         # payloads: explicit [pool, payload_bytes] array (e.g. the splitmix64 pool of the C++ sweep driver, capi.Sweep.payload)
@@ -263,8 +263,11 @@ class LinkSim:
         payload = torch.zeros((B, kb), dtype=torch.uint8, device=self.device)
         payload[:, :self.payload_bytes] = torch.randint(0, 256, (B, self.payload_bytes), dtype=torch.uint8, device=self.device, generator=g)
         assert self.layout != "chirp", "fresh payloads behind a chirp: build the pool on the host (layout='chirp' without fresh_payload)"
-        tx = self.demod.tx_batch(self.ldpc, payload[:, :self.payload_bytes], layout=1 if self.layout == "sc" else 0,
-                                 peak=float(self.peak) if self.peak else 0.0)
+        if self.kind == "ofdm":
+            tx = self.demod.tx_batch(self.ldpc, payload[:, :self.payload_bytes], layout=1 if self.layout == "sc" else 0,
+                                     peak=float(self.peak) if self.peak else 0.0)
+        else:     # pu_dpsk_tx_batch / pu_mcdpsk_tx_batch
+            tx = self.demod.tx_batch(self.ldpc, payload[:, :self.payload_bytes], peak=float(self.peak) if self.peak else 0.0)
         snr = np.asarray(snr_points, np.float32)
         fac = (np.power(np.float32(10.0), -snr / np.float32(20.0)) if self.snr_convention == 0
                else np.power(np.float32(10.0), snr / np.float32(10.0))).astype(np.float32)
@@ -283,10 +286,12 @@ class LinkSim:
             payload, tx, std = self.fresh_frames(batch, snr_points)
             idx = torch.arange(tx.shape[0], dtype=torch.int32, device=self.device)
             rx = channel_apply(self.ctx, self.ch, tx, idx, std, batch["seed"], rx)
-            info, ok, iters = (self.ldpc.decode_batch(self.demod_llr(rx)) if self.layout in ("sc", "chirp")
-                               else receive_decode(self.ofdm, self.ldpc, rx))
-            if self.layout in ("sc", "chirp"):
-                ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
+            if self.kind == "ofdm" and self.layout == "presynced":
+                info, ok, iters = receive_decode(self.ofdm, self.ldpc, rx)
+            else:
+                info, ok, iters = self.ldpc.decode_batch(self.demod_llr(rx))
+                if self.layout in ("sc", "chirp") or (self.kind == "dpsk" and self.acquire):
+                    ok = ok * (self.last_n_llr >= 648).to(ok.dtype)
             count_errors(self.ctx, info, ok, iters, payload, idx, batch["bins"], self.payload_bytes, counters)
             self.last_payload, self.last_tx, self.last_std = payload, tx, std
             return (rx, info, ok, iters) if keep else None

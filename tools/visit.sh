@@ -29,6 +29,19 @@ sweep2) for r in 0 1; do RANK=$r WORLD_SIZE=2 LOCAL_RANK=$r MASTER_PORT=29700 pr
 bench2) python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus 2 > $OUT/bench2.json 2> $OUT/bench2.err; tail -c 2500 $OUT/bench2.json; tail -3 $OUT/bench2.err;;
 chantests) ( time python -m pytest tests/test_channel.py tests/test_linksim_gpu.py tests/test_sweep_gpu.py -q -x ) > $OUT/pytest_chan.log 2>&1; tail -6 $OUT/pytest_chan.log;;
 dropin) ( time python -m pytest tests/test_dropin_cpp_gpu.py tests/test_ofdm_gpu.py -q -x ) > $OUT/pytest_dropin.log 2>&1; tail -30 $OUT/pytest_dropin.log; oracle/_ref/dropin_driver > $OUT/dropin_driver.log 2>&1; tail -30 $OUT/dropin_driver.log; oracle/_ref/test_multiblock_ldpc_pu > $OUT/multiblock.log 2>&1; tail -12 $OUT/multiblock.log;;
+ncu3)
+  for m in m3 m1qam16; do ncu --set full --clock-control none --import-source on -k regex:ofdm_presynced -s 3 -c 1 -f -o $OUT/prof_$m python tools/ofdm_quick_bench.py 4096 $m > $OUT/ncu_$m.log 2>&1; done
+  QB_CHANNEL=good ncu --set full --clock-control none --import-source on -k regex:channel_kernel -c 1 -f -o $OUT/prof_channel python tools/ofdm_quick_bench.py 4096 m1 > $OUT/ncu_channel.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:awgn_kernel -c 1 -f -o $OUT/prof_awgn python tools/ofdm_quick_bench.py 4096 m1 > $OUT/ncu_awgn.log 2>&1
+  for m in m3 m1qam16; do python tools/ofdm_quick_bench.py 4096 $m; done > $OUT/quick3.txt 2>&1; cat $OUT/quick3.txt;;
+sanitize)
+  # compute-sanitizer over a reduced subset that launches every kernel family; PU_SANITIZE=1 shrinks the batches
+  export PU_SANITIZE=1
+  for tool in memcheck racecheck; do
+    ( time compute-sanitizer --tool $tool --error-exitcode 9 --log-file $OUT/sanitizer_$tool.log python -m pytest tests/test_sanitize_gpu.py -q -x ) > $OUT/sanitize_$tool.out 2>&1
+    echo "$tool rc=$?"; tail -3 $OUT/sanitize_$tool.out; grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $OUT/sanitizer_$tool.log | tail -2
+  done;;
+psktx) ( time python -m pytest tests/test_psk_tx_gpu.py tests/test_ldpc_gpu.py -q -x ) > $OUT/pytest_psktx.log 2>&1; tail -25 $OUT/pytest_psktx.log;;
 *) echo "unknown: $w";;
 esac; done
 ls -la $OUT
