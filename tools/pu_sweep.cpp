@@ -99,7 +99,7 @@ std::vector<pu_sweep_mode> make_table(const std::string& name, bool fast) {
             t.push_back(mcdpsk_mode(PU_WF_MCDPSK, 8, PU_RATE_1_2, ch, -6, 1, 16));
             t.push_back(dpsk_mode(PU_WF_DPSK, 1, PU_RATE_1_4, ch, -11, 2, 15));
         }
-        t.push_back(ofdm_mode(PU_WF_OFDM_SC, 512, PU_MOD_DQPSK, PU_RATE_1_2, PU_CH_AWGN, -2, 2, 8, fast));
+        t.push_back(ofdm_mode(PU_WF_OFDM_SC, 512, PU_MOD_DQPSK, PU_RATE_1_2, PU_CH_AWGN, 10, 3, 8, fast));   // Schmidl-Cox needs its 0.8 plateau
     } else {   // config5: all waveforms x 5 rates x 40 SNR points (-12 ... +27.5 dB in 1 dB steps shifted per family)
         const unsigned rates[] = {PU_RATE_1_4, PU_RATE_1_2, PU_RATE_2_3, PU_RATE_3_4, PU_RATE_5_6};
         for (unsigned r : rates) {
