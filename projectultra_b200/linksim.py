@@ -352,6 +352,107 @@ class LinkSim:
         return counters
 
 
+FRAME_COUNTER_NAMES = ("frames", "frame_errors", "codewords_failed", "codewords", "header_failures", "unused")
+V2_BYTES_PER_CODEWORD = {capi.R1_4: 20, capi.R1_3: 27, capi.R1_2: 40, capi.R2_3: 54, capi.R3_4: 60, capi.R5_6: 67}
+
+
+def v2_crc16(data):
+    """CRC-16/CCITT (0x1021, init 0xFFFF) of src/protocol/frame_v2.cpp:111-124."""
+    crc = 0xFFFF
+    for b in bytes(data):
+        crc ^= b << 8
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+    return crc
+
+
+def v2_data_frame(payload, rate, seq=7, src_hash=0x123456, dst_hash=0xABCDEF, ftype=0x30, flags=0x01):
+    """Bytes of a protocol-v2 DATA frame as DataFrame::serialize writes them (src/protocol/frame_v2.cpp:502-555): magic 0x554C, type,
+    flags, seq, 24-bit source / destination hashes, TOTAL_CW (calculateCodewords, :439-460), payload length, header CRC, payload,
+    frame CRC.  Only the simulator's stimulus: frame CONTENTS stay with the reference's protocol layer."""
+    p = bytes(payload)
+    total, bpc = 17 + len(p) + 2, V2_BYTES_PER_CODEWORD[rate]
+    tcw = 1 if total <= bpc else 1 + -(-(total - bpc) // (bpc - 2))
+    h = bytes([0x55, 0x4C, ftype, flags, seq >> 8, seq & 0xFF, src_hash >> 16, (src_hash >> 8) & 0xFF, src_hash & 0xFF,
+               dst_hash >> 16, (dst_hash >> 8) & 0xFF, dst_hash & 0xFF, tcw, len(p) >> 8, len(p) & 0xFF])
+    c = v2_crc16(h)
+    body = h + bytes([c >> 8, c & 0xFF]) + p
+    f = v2_crc16(body)
+    return np.frombuffer(body + bytes([f >> 8, f & 0xFF]), np.uint8).copy()
+
+
+class FrameLinkSim:
+    """Whole-frame FER through the OFDM path (SURVEY §8f next-4 wired into the link simulation): every trial carries a protocol-v2 DATA
+    frame of `payload_bytes` bytes = several LDPC codewords in one OFDM frame, and a trial succeeds iff RxPipeline::decodeFrame
+    (src/gui/modem/rx_pipeline.cpp:348-445: CW0 -> header -> expected codewords -> all decoded -> reassemble) returns exactly the frame
+    that was sent -- the reference's link-level statistic rather than the codeword FER of LinkSim.
+
+        v2_data_frame -> pu_frame_encode -> pu_ofdm_tx (pool, host)  |  pu_channel_apply_batch -> pu_ofdm_presynced_batch (all
+        codewords of the frame, llr_stride = n_cw * 648) -> pu_frame_decode_batch -> compare with the frame sent -> counters
+
+    counters [n_snr, 6] = FRAME_COUNTER_NAMES."""
+
+    def __init__(self, ctx, cfg, channel="awgn", payload_bytes=200, pool=16, pool_seed=12345, max_iter=50, precision="exact", code_rate=None):
+        import torch
+        assert isinstance(cfg, capi.ModemConfig), "whole frames ride on the OFDM waveforms"
+        self.ctx, self.cfg = ctx, cfg
+        self.device = torch.device("cuda", ctx.device)
+        self.ch = channel_preset(channel) if isinstance(channel, str) else channel
+        self.snr_convention = 1 if channel == "awgn" else 0
+        self.rate = cfg.code_rate if code_rate is None else code_rate
+        self.ofdm = capi.OfdmDemodulator(ctx, cfg)
+        self.ofdm.set_precision(precision)
+        self.ldpc = capi.LdpcDecoder(ctx, self.rate, max_iter)
+        rng = np.random.default_rng(pool_seed)
+        self.frames_host = [v2_data_frame(rng.integers(0, 256, payload_bytes, dtype=np.uint8), self.rate, seq=i + 1) for i in range(pool)]
+        cws = [capi.frame_encode(self.rate, f) for f in self.frames_host]
+        self.n_cw = len(cws[0])
+        assert all(len(c) == self.n_cw for c in cws)
+        self.tx_host = np.stack([ofdm_tx(cfg, c.reshape(-1), 0) for c in cws])
+        self.L = self.tx_host.shape[1]
+        assert self.ofdm.n_llr(self.L) >= self.n_cw * 648
+        self.tx_pool = torch.from_numpy(self.tx_host).to(self.device)
+        self.frame_len = len(self.frames_host[0])
+        self.frame_pool = torch.from_numpy(np.stack(self.frames_host)).to(self.device)
+        self.pool = pool
+
+    def make_batch(self, snr_points, snr_idx, trials, base_seed=0xB200):
+        import torch
+        snr_idx = np.asarray(snr_idx, dtype=np.int64)
+        trials = np.asarray(trials, dtype=np.int64)
+        tx_index = (trials % self.pool).astype(np.uint32)
+        table = np.array([[channel_noise_std(self.tx_host[i], s, self.snr_convention) for i in range(self.pool)] for s in snr_points], np.float32)
+        std = table[snr_idx, tx_index].astype(np.float32)
+        seeds = (np.uint64(base_seed) << np.uint64(40)) ^ (snr_idx.astype(np.uint64) << np.uint64(32)) ^ trials.astype(np.uint64)
+        to = lambda a, dt: torch.from_numpy(a.view(dt) if a.dtype != dt else a).to(self.device)
+        return dict(tx_index=to(tx_index.view(np.int32), np.int32), noise_std=to(std, np.float32), seed=to(seeds.view(np.int64), np.int64),
+                    bins=to(snr_idx, np.int64), host=dict(tx_index=tx_index, noise_std=std, seed=seeds, snr_idx=snr_idx))
+
+    def run_batch(self, batch, counters, keep=False):
+        """channel -> demod (every codeword of the frame) -> decodeFrame -> counters, on the current stream."""
+        import torch
+        rx = channel_apply(self.ctx, self.ch, self.tx_pool, batch["tx_index"], batch["noise_std"], batch["seed"])
+        llr = self.ofdm.presynced_batch(rx, 2, llr_stride=self.n_cw * 648, want_aux=False)[0]
+        frames, flen, info = self.ldpc.frame_decode_batch(llr, self.n_cw, frame_cap=self.frame_len)
+        want = self.frame_pool[batch["tx_index"].long()]
+        good = (info[:, 0] == 1) & (flen == self.frame_len) & (frames == want).all(dim=1)
+        upd = torch.stack([torch.ones_like(flen, dtype=torch.int64), (~good).to(torch.int64), info[:, 3].to(torch.int64),
+                           torch.full_like(flen, self.n_cw, dtype=torch.int64), (info[:, 4] == 0).to(torch.int64),
+                           torch.zeros_like(flen, dtype=torch.int64)], dim=1)
+        counters.index_add_(0, batch["bins"], upd)
+        return (rx, llr, frames, flen, info, good) if keep else None
+
+    def sweep(self, snr_points, trials_per_point, rank=0, world=1, batch_frames=1 << 13, base_seed=0xB200):
+        import torch
+        counters = torch.zeros((len(snr_points), 6), dtype=torch.int64, device=self.device)
+        mine = np.arange(rank, trials_per_point, world, dtype=np.int64)
+        si = np.repeat(np.arange(len(snr_points), dtype=np.int64), len(mine))
+        tr = np.tile(mine, len(snr_points))
+        for off in range(0, len(si), batch_frames):
+            self.run_batch(self.make_batch(snr_points, si[off:off + batch_frames], tr[off:off + batch_frames], base_seed), counters)
+        return counters
+
+
 def shard_trials(trials_per_point, rank, world):
     """Trial indices of this rank: t % world == rank (disjoint, exhaustive; no data-path collective)."""
     return np.arange(rank, trials_per_point, world, dtype=np.int64)

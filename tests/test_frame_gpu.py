@@ -127,3 +127,41 @@ def test_v2_frame_large_batch_property(ctx):
     assert (frames[good][:, :want.shape[1]] == want[good]).all()
     assert (info[broken, 0] == 0).all() and (info[broken, 3] == 1).all() and (info[broken, 2] == ncw - 1).all() and (flen[broken] == 0).all()
     dec.close()
+
+
+def test_whole_frame_link_simulation_against_the_oracle(ctx):
+    """linksim.FrameLinkSim: multi-codeword protocol-v2 frames through channel -> OFDM demod -> RxPipeline::decodeFrame on the GPU; every
+    frame's verdict and bytes against the oracle (orc_ofdm_presynced + orc_frame_decode, both pinned to the compiled reference) on the
+    same channel outputs; whole-frame FER falls with SNR and is never below the codeword-level failure it is made of."""
+    import torch
+    import oracleapi as O
+    import refapi as R
+    import v2frames
+    from projectultra_b200 import capi, linksim
+    for cfgargs, rate, chan, snrs, nbytes in (((48000, 1500, 512, 30, 1, 4, 2, 0, capi.DQPSK, capi.R1_2, 40.0, 0.0), capi.R1_2, "awgn", [0.0, 2.0, 6.0], 150),
+                                              ((48000, 1500, 512, 30, 1, 4, 2, 1, capi.QAM16, capi.R3_4, 40.0, 0.0), capi.R3_4, "good", [8.0, 16.0, 30.0], 200)):
+        cfg = capi.ModemConfig(*cfgargs)
+        sim = linksim.FrameLinkSim(ctx, cfg, chan, payload_bytes=nbytes, pool=3, code_rate=rate)
+        assert sim.n_cw == v2frames.codewords_for(nbytes, rate) and sim.n_cw >= 4
+        assert (sim.frames_host[0] == v2frames.data_frame(sim.frames_host[0][17:17 + nbytes], rate, seq=1)).all()
+        trials = 5
+        si = np.repeat(np.arange(len(snrs)), trials)
+        tr = np.tile(np.arange(trials), len(snrs))
+        batch = sim.make_batch(snrs, si, tr)
+        counters = torch.zeros((len(snrs), 6), dtype=torch.int64, device="cuda")
+        rx, llr, frames, flen, info, good = sim.run_batch(batch, counters, keep=True)
+        torch.cuda.synchronize()
+        rx_h, info_h, flen_h, frames_h, good_h = rx.cpu().numpy(), info.cpu().numpy(), flen.cpu().numpy(), frames.cpu().numpy(), good.cpu().numpy()
+        rcfg = R.ModemConfig.from_buffer_copy(bytes(cfg))
+        for b in range(len(si)):
+            soft, _, _ = O.ofdm_presynced(rcfg, rx_h[b], 2, 1, 0.0, 0.0)
+            want_bytes, want_info = O.frame_decode(rate, soft[:sim.n_cw * 648], sim.n_cw)
+            assert (info_h[b] == want_info).all(), (b, info_h[b], want_info)
+            assert flen_h[b] == len(want_bytes) and (frames_h[b, :len(want_bytes)] == want_bytes).all(), b
+            sent = sim.frames_host[batch["host"]["tx_index"][b]]
+            assert bool(good_h[b]) == (want_info[0] == 1 and len(want_bytes) == len(sent) and (want_bytes == sent).all()), b
+        c = counters.cpu().numpy()
+        assert (c[:, 0] == trials).all() and (c[:, 3] == trials * sim.n_cw).all()
+        assert c[0, 1] >= c[-1, 1] and (c[:, 1] * sim.n_cw >= c[:, 2]).all()
+        if chan == "awgn":
+            assert c[-1, 1] == 0

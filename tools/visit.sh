@@ -47,6 +47,7 @@ sweepred) ( time projectultra_b200/pu_sweep --table reduced --trials ${TRIALS:-4
 sweepN) N=${NGPU:-8}; for r in $(seq 0 $((N-1))); do RANK=$r WORLD_SIZE=$N LOCAL_RANK=$r MASTER_PORT=29700 projectultra_b200/pu_sweep --table reduced --trials ${TRIALS:-16384} --block 1024 --rendezvous /tmp --manifest $OUT/manifest_N$N --out $OUT/sweep_N$N.jsonl > $OUT/sweepN_r$r.log 2>&1 & done; wait; tail -n 2 $OUT/sweepN_r0.log; tail -1 $OUT/sweep_N$N.jsonl;;
 h2dN) N=${NGPU:-8}; for n in 1 2 4 8; do [ $n -le $N ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2972$n tools/h2d_bench.py 2>/dev/null | grep '^{' | tee -a $OUT/h2d.jsonl | cut -c1-400; done;;
 benchN) N=${NGPU:-8}; for n in ${BENCH_NS:-4 8}; do [ $n -le $N ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2973$n bench.py --gpus $n 2>$OUT/bench_N$n.err | grep '^{' > $OUT/bench_N$n.json; python -c "import json,sys; j=json.load(open('$OUT/bench_N$n.json')); print($n, 'value', j['value'], 'e2e', j['e2e']['value'], j['e2e'].get('h2d_gbs_per_gpu'), 'sweep', {k:v['value'] for k,v in j.get('sweep',{}).items()})"; done;;
+frames) ( time python -m pytest tests/test_frame_gpu.py -q -x ) > $OUT/pytest_frames.log 2>&1; tail -25 $OUT/pytest_frames.log;;
 *) echo "unknown: $w";;
 esac; done
 ls -la $OUT
