@@ -330,7 +330,7 @@ PU_API pu_status pu_mcdpsk_tx_batch(pu_mcdpsk* h, const pu_ldpc* code, const uin
 
 /* ---------------------------------------------------------------- channel simulator
  * Replaces sim::WattersonChannel (src/sim/hf_channel.hpp:34-299) for batches of frames.  POD mirror of
- * WattersonChannel::Config (:36-65) without the CFO injector fields (out of scope). */
+ * WattersonChannel::Config (:36-65); the CFO injector fields (cfo_hz) are a separate call, pu_channel_apply_cfo_batch. */
 typedef struct {
     float delay_spread_ms;      /* second path delay; effective delay is floor(ms*fs/1000)+1 samples (Q11) */
     float doppler_spread_hz;
@@ -359,6 +359,13 @@ PU_API pu_status pu_channel_apply_batch(pu_ctx* ctx, const pu_channel_config* cf
                                         size_t pool_stride, size_t pool_count, const uint32_t* tx_index,
                                         const float* noise_std, const uint64_t* seed, size_t B, size_t L,
                                         float* rx, pu_memspace space, void* stream);
+
+/* WattersonChannel::applyCFO (hf_channel.hpp:173-232), the channel's optional carrier-frequency-offset injector, applied IN PLACE to
+ * every row of samples[B][stride] (L samples each) with cfo_hz[b] and a CFO phase of 0 at the start of the row: down-mix around
+ * 1500 Hz, 48-tap running-sum lowpass, rotation, up-mix.  Rows with |cfo| <= 0.001 Hz or fewer than 256 samples are left untouched, as
+ * in the reference.  Deterministic: bit-identical to the reference (no random draw is involved). */
+PU_API pu_status pu_channel_apply_cfo_batch(pu_ctx* ctx, float* samples, size_t B, size_t L, size_t stride, const float* cfo_hz,
+                                            uint32_t sample_rate, pu_memspace space, void* stream);
 
 /* ---------------------------------------------------------------- receive + decode, error counting
  * One call per batch of frames = the body of the reference's Monte-Carlo trial loop after the channel

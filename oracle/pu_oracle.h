@@ -115,6 +115,7 @@ float orc_noise_normal(uint64_t seed, uint32_t n);
 void orc_fading_normals(uint64_t seed, uint32_t n, float z[4]);
 int orc_channel_apply(float delay_ms, float doppler_hz, float g1, float g2, uint32_t fs, int fading, int multipath,
                       int noise, const float* x, size_t L, float noise_std, uint64_t seed, float* y);
+int orc_channel_apply_cfo(const float* x, size_t L, float cfo_hz, uint32_t sample_rate, float* y);
 float orc_channel_noise_std(const float* tx, size_t L, float snr_db, int convention);
 #ifdef __cplusplus
 }

@@ -168,6 +168,46 @@ int orc_channel_apply(float delay_ms, float doppler_hz, float g1, float g2, uint
     return 0;
 }
 
+/* WattersonChannel::applyCFO (src/sim/hf_channel.hpp:173-232) with cfo_phase_ = 0 at entry: mix to baseband around 1500 Hz, 48-tap
+ * running-sum lowpass, rotate by the CFO phase recurrence, mix back up.  Frames shorter than 256 samples are returned unchanged. */
+int orc_channel_apply_cfo(const float* x, size_t L, float cfo_hz, uint32_t sample_rate, float* y) {
+    memcpy(y, x, L * sizeof(float));
+    if (L < 256 || !(fabsf(cfo_hz) > 0.001f)) return 0;      /* :163 (process) and :174 */
+    const float fc = 1500.0f, fs = (float)sample_rate;
+    float* I_bb = (float*)malloc(L * sizeof(float));
+    float* Q_bb = (float*)malloc(L * sizeof(float));
+    float* I_f = (float*)malloc(L * sizeof(float));
+    float* Q_f = (float*)malloc(L * sizeof(float));
+    for (size_t i = 0; i < L; ++i) {
+        float t = (float)i / fs;
+        float mix_phase = (float)(2.0f * M_PI * fc * t);
+        I_bb[i] = x[i] * cosf(mix_phase);
+        Q_bb[i] = x[i] * sinf(mix_phase);
+    }
+    const size_t win = 48;
+    float I_sum = 0, Q_sum = 0;
+    for (size_t i = 0; i < L; ++i) {
+        I_sum += I_bb[i];
+        Q_sum += Q_bb[i];
+        if (i >= win) { I_sum -= I_bb[i - win]; Q_sum -= Q_bb[i - win]; }
+        size_t n = i + 1 < win ? i + 1 : win;
+        I_f[i] = I_sum / (float)n;
+        Q_f[i] = Q_sum / (float)n;
+    }
+    float phase = 0.0f, phase_inc = (float)(2.0f * M_PI * cfo_hz / (double)sample_rate);
+    for (size_t i = 0; i < L; ++i) {
+        float t = (float)i / fs;
+        float mix_phase = (float)(2.0f * M_PI * fc * t);
+        float cc = cosf(phase), cs = sinf(phase);
+        float I_c = I_f[i] * cc - Q_f[i] * cs, Q_c = I_f[i] * cs + Q_f[i] * cc;
+        y[i] = 2.0f * (I_c * cosf(mix_phase) - Q_c * sinf(mix_phase));
+        phase += phase_inc;
+        if (phase > 2.0f * M_PI) phase = (float)(phase - 2.0f * M_PI);
+    }
+    free(I_bb); free(Q_bb); free(I_f); free(Q_f);
+    return 0;
+}
+
 /* noise sigma conventions: 0 = WattersonChannel::process (hf_channel.hpp:110-119), 1 = AWGN tools (test_mode_snr.cpp:58-61) */
 float orc_channel_noise_std(const float* tx, size_t L, float snr_db, int convention) {
     float acc = 0.0f;

@@ -460,6 +460,24 @@ int ref_watterson(float snr_db, float delay_ms, float doppler_hz, float g1, floa
     return 0;
 }
 
+// WattersonChannel with ONLY the CFO injector active (applyCFO, src/sim/hf_channel.hpp:173-232): no fading, multipath or noise, so the
+// output is deterministic and pins the twin / the CUDA kernel bit for bit.
+int ref_watterson_cfo(float cfo_hz, const float* in, size_t n, float* out) {
+    sim::WattersonChannel::Config cc;
+    cc.snr_db = 100.0f;
+    cc.delay_spread_ms = 0.0f;
+    cc.doppler_spread_hz = 0.0f;
+    cc.cfo_hz = cfo_hz;
+    cc.fading_enabled = false;
+    cc.multipath_enabled = false;
+    cc.noise_enabled = false;
+    cc.cfo_enabled = true;
+    sim::WattersonChannel ch(cc, 1);
+    Samples r = ch.process(SampleSpan(in, n));
+    std::memcpy(out, r.data(), n * sizeof(float));
+    return 0;
+}
+
 // ---------------------------------------------------------------- single-carrier DPSK
 // DPSKModulator / DPSKDemodulator (src/psk/dpsk.hpp).  mod: 0 DBPSK(2), 1 DQPSK(4), 2 D8PSK(8)
 static DPSKConfig dpsk_cfg(int mod_order, int samples_per_symbol) {

@@ -22,6 +22,7 @@
 
 #include "pu_internal.h"
 #include "pu_rng.cuh"
+#include "ref_math.cuh"
 
 namespace pu {
 
@@ -170,6 +171,62 @@ __global__ void __launch_bounds__(256) awgn_kernel(const float* __restrict__ tx_
     }
 }
 
+// WattersonChannel::applyCFO (src/sim/hf_channel.hpp:173-232), the channel's optional CFO injector, in place on one frame per warp:
+// mix to baseband around 1500 Hz, 48-tap running-sum lowpass, rotate by the CFO phase, mix back up.  The running sums and the phase
+// are serial float recurrences (`sum += x[i]; sum -= x[i-48]`, `phase += inc` with its one-sided wrap): three lanes walk them 32
+// samples at a time out of shared memory while the mixing before and after them runs on all lanes.  Deterministic (no random draw),
+// so this kernel IS pinned bit for bit to the reference (tests/test_channel.py) -- the mixer table comes from the host libm as the
+// reference evaluates it, the rotator's cos/sin are the glibc restatements of ref_math.cuh (|phase| stays far below 120).
+constexpr int kCfoWin = 48;
+__global__ void __launch_bounds__(128) channel_cfo_kernel(float* __restrict__ samples, size_t stride, size_t B, int L, const float* __restrict__ cfo_hz,
+                                                          double fs_d, const float2* __restrict__ mix) {
+    __shared__ float ring[4][2][96];       // I_bb / Q_bb of the last 96 samples (index i % 96)
+    __shared__ float stage[4][3][32];      // I_filt, Q_filt, phase of the chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t frame = static_cast<size_t>(blockIdx.x) * 4 + warp;
+    if (frame >= B) return;
+    const float cfo = cfo_hz[frame];
+    if (L < 256 || !(fabsf(cfo) > 0.001f)) return;        // :163, :174
+    float* x = samples + frame * stride;
+    const float phase_inc = static_cast<float>(__ddiv_rn(__dmul_rn(2.0f * 3.14159265358979323846, static_cast<double>(cfo)), fs_d));   // :101
+    float acc = 0.0f;          // lane 0: I_sum, lane 1: Q_sum, lane 2: phase
+    for (int base = 0; base < L; base += 32) {
+        const int i = base + lane;
+        float2 m = make_float2(0.0f, 0.0f);
+        if (i < L) {
+            m = __ldg(&mix[i]);
+            const float xv = x[i];
+            ring[warp][0][i % 96] = __fmul_rn(xv, m.x);
+            ring[warp][1][i % 96] = __fmul_rn(xv, m.y);
+        }
+        __syncwarp();
+        const int cnt = min(32, L - base);
+        if (lane < 2) {
+            const float* r = ring[warp][lane];
+            for (int k = 0; k < cnt; ++k) {
+                const int j = base + k;
+                acc = __fadd_rn(acc, r[j % 96]);
+                if (j >= kCfoWin) acc = __fsub_rn(acc, r[(j - kCfoWin) % 96]);
+                stage[warp][lane][k] = __fdiv_rn(acc, static_cast<float>(min(j + 1, kCfoWin)));
+            }
+        } else if (lane == 2) {
+            for (int k = 0; k < cnt; ++k) {
+                stage[warp][2][k] = acc;
+                acc = __fadd_rn(acc, phase_inc);
+                if (static_cast<double>(acc) > 2.0f * 3.14159265358979323846) acc = static_cast<float>(static_cast<double>(acc) - 2.0f * 3.14159265358979323846);
+            }
+        }
+        __syncwarp();
+        if (i < L) {
+            const float fi = stage[warp][0][lane], fq = stage[warp][1][lane], ph = stage[warp][2][lane];
+            const float cc = refmath::cosf_ref(ph), cs = refmath::sinf_ref(ph);
+            const float ic = __fsub_rn(__fmul_rn(fi, cc), __fmul_rn(fq, cs)), qc = __fadd_rn(__fmul_rn(fi, cs), __fmul_rn(fq, cc));
+            x[i] = __fmul_rn(2.0f, __fsub_rn(__fmul_rn(ic, m.x), __fmul_rn(qc, m.y)));
+        }
+        __syncwarp();
+    }
+}
+
 static ChannelParams make_params(const pu_channel_config& c) {
     ChannelParams p{};
     p.fading = c.fading_enabled != 0;
@@ -248,6 +305,55 @@ float pu_channel_noise_std(const float* tx, size_t L, float snr_db, int conventi
     }
     const float sp = acc / L;       // tools/test_mode_snr.cpp:58-61 (mean frame power, AWGN tools)
     return std::sqrt(sp / std::pow(10.0f, snr_db / 10.0f));
+}
+
+pu_status pu_channel_apply_cfo_batch(pu_ctx* ctx, float* samples, size_t B, size_t L, size_t stride, const float* cfo_hz, uint32_t sample_rate,
+                                     pu_memspace space, void* stream) {
+    PU_REQUIRE(ctx, "pu_channel_apply_cfo_batch: NULL context");
+    if (B == 0 || L == 0) return PU_OK;
+    PU_REQUIRE(samples && cfo_hz && stride >= L && sample_rate > 0 && L < (1u << 30), "pu_channel_apply_cfo_batch: bad argument");
+    PU_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = pu::pick_stream(ctx, stream, space);
+    if (ctx->cfo_mix_len < L || ctx->cfo_mix_fs != sample_rate) {
+        // mix_phase = 2 pi fc t with t = float(i) / fs, evaluated as the reference does (double product stored to float, host cosf / sinf)
+        std::vector<float2> tab(L);
+        const float fc = 1500.0f, fs = static_cast<float>(sample_rate);
+        for (size_t i = 0; i < L; ++i) {
+            const float t = static_cast<float>(i) / fs;
+            const float mix_phase = static_cast<float>(2.0f * 3.14159265358979323846 * fc * t);
+            tab[i] = make_float2(std::cos(mix_phase), std::sin(mix_phase));
+        }
+        pu_status s = ctx->cfo_mix.reserve(L * sizeof(float2));
+        if (s != PU_OK) return s;
+        PU_CUDA_TRY(cudaMemcpyAsync(ctx->cfo_mix.ptr, tab.data(), L * sizeof(float2), cudaMemcpyHostToDevice, st));
+        PU_CUDA_TRY(cudaStreamSynchronize(st));       // `tab` is pageable and goes out of scope
+        ctx->cfo_mix_len = L;
+        ctx->cfo_mix_fs = sample_rate;
+    }
+    float* d_x = samples;
+    const float* d_cfo = cfo_hz;
+    float *dx = nullptr, *dc = nullptr;
+    if (space == PU_MEM_HOST) {
+        PU_CUDA_TRY(cudaMalloc(&dx, B * stride * sizeof(float)));
+        PU_CUDA_TRY(cudaMalloc(&dc, B * sizeof(float)));
+        PU_CUDA_TRY(cudaMemcpyAsync(dx, samples, B * stride * sizeof(float), cudaMemcpyHostToDevice, st));
+        PU_CUDA_TRY(cudaMemcpyAsync(dc, cfo_hz, B * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_x = dx; d_cfo = dc;
+    }
+    (void)cudaGetLastError();
+    pu::channel_cfo_kernel<<<static_cast<unsigned>((B + 3) / 4), 128, 0, st>>>(d_x, stride, B, static_cast<int>(L), d_cfo, static_cast<double>(sample_rate),
+                                                                              static_cast<const float2*>(ctx->cfo_mix.ptr));
+    ctx->launches.fetch_add(1);
+    pu_status rs = PU_OK;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && space == PU_MEM_HOST) {
+        e = cudaMemcpyAsync(samples, dx, B * stride * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) { pu::set_error("pu_channel_apply_cfo_batch: %s", cudaGetErrorString(e)); rs = PU_ERR_CUDA; }
+    if (dx) cudaFree(dx);
+    if (dc) cudaFree(dc);
+    return rs;
 }
 
 pu_status pu_channel_apply_batch(pu_ctx* ctx, const pu_channel_config* cfg, const float* tx_pool, size_t pool_stride,

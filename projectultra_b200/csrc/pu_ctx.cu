@@ -117,6 +117,7 @@ void pu_destroy(pu_ctx* c) {
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     if (c->pipe_ev) cudaEventDestroy(c->pipe_ev);
+    c->cfo_mix.release();
     for (auto& b : c->sweep) b.release();
     for (auto& e : c->sweep_ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);

@@ -68,6 +68,9 @@ struct pu_ctx {
     cudaEvent_t pipe_ev = nullptr;
     // scratch of pu_linksim_run (sweep.cu), grow-only and reused across calls: [0..6] batch buffers (rx, llr, info, ok, iters, n_llr, sync),
     // [7 + 4 s .. 10 + 4 s] slot s = {pinned descriptors, device descriptors, device counters, pinned counters}
+    pu::Buffer cfo_mix;            // pu_channel_apply_cfo_batch: (cos, sin)(2 pi 1500 i / fs) per sample index, host libm
+    size_t cfo_mix_len = 0;
+    uint32_t cfo_mix_fs = 0;
     pu::Buffer sweep[15];
     cudaEvent_t sweep_ev[2] = {nullptr, nullptr};
 };

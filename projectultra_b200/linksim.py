@@ -67,6 +67,16 @@ def channel_apply(ctx, ch, tx_pool, tx_index, noise_std, seed, rx=None):
     return rx
 
 
+def channel_apply_cfo(ctx, rx, cfo_hz, sample_rate=48000):
+    """pu_channel_apply_cfo_batch: WattersonChannel::applyCFO in place on every row of rx [B, L] (numpy => host, torch.cuda => device)."""
+    B, L = rx.shape
+    sp = capi._space(rx, cfo_hz)
+    stride = rx.stride(0) if capi._is_torch(rx) else L
+    capi.check(capi.lib().pu_channel_apply_cfo_batch(ctx._h, capi._ptr(rx), C.c_size_t(B), C.c_size_t(L), C.c_size_t(stride), capi._ptr(cfo_hz),
+                                                     C.c_uint32(sample_rate), sp, capi._stream(sp)))
+    return rx
+
+
 def receive_decode(ofdm, ldpc, samples, training=2, cfo_hz=None, cfo_phase=None, info=None, ok=None, iters=None):
     """pu_receive_decode_batch: demodulate + LDPC decode; LLRs stay on the device."""
     tor = capi._is_torch(samples)

@@ -52,3 +52,12 @@ def noise_std(x, snr_db, convention=0):
     x = np.ascontiguousarray(x, dtype=np.float32)
     return float(_lib().orc_channel_noise_std(x.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(len(x)),
                                               C.c_float(snr_db), int(convention)))
+
+
+def channel_apply_cfo(x, cfo_hz, sample_rate=48000):
+    """orc_channel_apply_cfo: WattersonChannel::applyCFO (hf_channel.hpp:173-232), CFO phase 0 at entry."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.zeros_like(x)
+    _lib().orc_channel_apply_cfo(x.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(len(x)), C.c_float(cfo_hz), C.c_uint32(sample_rate),
+                                 y.ctypes.data_as(C.POINTER(C.c_float)))
+    return y

@@ -290,6 +290,14 @@ def watterson(x, snr_db, delay_ms, doppler_hz, g1=0.707, g2=0.707, fading=True, 
     return out
 
 
+def watterson_cfo(x, cfo_hz):
+    """WattersonChannel::process with only the CFO injector active (applyCFO, hf_channel.hpp:173-232)."""
+    x = _f32(x)
+    out = np.zeros_like(x)
+    lib().ref_watterson_cfo(C.c_float(cfo_hz), _p(x, C.c_float), C.c_size_t(len(x)), _p(out, C.c_float))
+    return out
+
+
 def dpsk_modulate(mod_order, sps, data, with_preamble=True):
     d = _u8(data)
     cap = 2_000_000

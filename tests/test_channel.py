@@ -112,3 +112,32 @@ def test_statistics_match_reference_watterson():
             assert abs(mg / mr - 1) < tol, (name, sl, mg, mr)
         assert abs(g[:, :5].mean() - 1.0) < 0.05     # starts at (1, 0), hf_channel.hpp:91-92
     del ctx
+
+
+@pytest.mark.ref
+def test_cfo_injector_twin_matches_reference_bitwise():
+    """WattersonChannel::applyCFO (hf_channel.hpp:173-232) is deterministic: the oracle's restatement equals the compiled reference."""
+    rng = np.random.default_rng(8)
+    for L in (7332, 300, 200, 24000):
+        x = (rng.standard_normal(L) * 0.3).astype(np.float32)
+        for cfo in (30.0, -12.5, 50.0, 0.0005, 0.0):
+            a, b = R.watterson_cfo(x, cfo), CH.channel_apply_cfo(x, cfo)
+            assert (a.view(np.uint32) == b.view(np.uint32)).all(), (L, cfo)
+
+
+@pytest.mark.gpu
+def test_cfo_injector_kernel_matches_twin_bitwise():
+    import torch
+    from projectultra_b200 import capi, linksim
+    ctx = capi.Context(0)
+    rng = np.random.default_rng(9)
+    for L in (7332, 300, 200, 7001):
+        x = (rng.standard_normal((9, L)) * 0.3).astype(np.float32)
+        cfo = np.array([30.0, -12.5, 50.0, 0.0005, 0.0, 7.0, -50.0, 1.0, 33.3], np.float32)
+        want = np.stack([CH.channel_apply_cfo(x[b], float(cfo[b])) for b in range(9)])
+        host = linksim.channel_apply_cfo(ctx, x.copy(), cfo)
+        assert (host.view(np.uint32) == want.view(np.uint32)).all(), (L, "host")
+        dev = linksim.channel_apply_cfo(ctx, torch.from_numpy(x).cuda(), torch.from_numpy(cfo).cuda())
+        torch.cuda.synchronize()
+        assert (dev.cpu().numpy().view(np.uint32) == want.view(np.uint32)).all(), (L, "device")
+    del ctx
