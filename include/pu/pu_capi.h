@@ -135,15 +135,17 @@ PU_API int pu_ofdm_bits_per_symbol(const pu_ofdm* h);  /* OFDMModulator::bitsPer
  * this handle used: 0 = none yet, 1 = general presynced kernel (ofdm_demod.cu), 2 = warp-FFT kernel for differential
  * no-pilot modes (ofdm_diff.cu), 3 = persistent TMA-staged packed-fp32 512-FFT kernel (ofdm_diff512.cu), 4 = general presynced
  * kernel in its one-frame-per-warp form (ofdm_demod.cu, WARPG), 5 = FMA-contracted form of kernel 3 (ofdm_fast512.cu,
- * PU_PRECISION_FAST). */
+ * PU_PRECISION_FAST), 6 = kernel 4 with FMA butterflies and MUFU sin/cos in the CFO rotator (PU_PRECISION_FAST). */
 PU_API int pu_ofdm_last_kernel(const pu_ofdm* h);
 /* Arithmetic contract of the receive kernels of this handle (no reference counterpart; the reference has one build).
  *   PU_PRECISION_EXACT (default): FFT bins, channel estimate, equalised symbols bit-identical to the reference's unfused
  *     radix-2 fp32 arithmetic (src/dsp/fft.cpp:89-121, compiled without FMA contraction), LLR words >= 99.99 % identical.
  *   PU_PRECISION_FAST: BASELINE.json's own bar -- LLRs within 1e-4 relative (of max(|LLR|, 0.5)), saturated LLRs exactly
  *     +-10, decoded bytes identical on every frame the reference decodes with margin; butterflies are fused multiply-adds.
- *     Only the kernels that have an FMA form honour it (512-FFT differential no-pilot modes at zero CFO); every other
- *     call runs the exact kernels.
+ *     The 512-FFT differential no-pilot modes at zero CFO take ofdm_fast512.cu; every other whole-frame call (pilots, coherent QAM,
+ *     CFO, 1024-FFT pilot modes, acquired frames) takes the general warp kernel with FMA butterflies and MUFU sin/cos in the CFO
+ *     rotator (the rotator's phases stay the reference's float recurrence); the remaining kernels (1024-FFT differential
+ *     no-pilot, debug dumps) have no fast form and run exact.
  * The environment variable PU_OFDM_PRECISION=exact|fast overrides the handle's setting (A/B runs of unmodified callers). */
 typedef enum pu_precision { PU_PRECISION_EXACT = 0, PU_PRECISION_FAST = 1 } pu_precision;
 PU_API pu_status pu_ofdm_set_precision(pu_ofdm* h, pu_precision mode);

@@ -307,7 +307,7 @@ class OfdmDemodulator:
             pass
 
     KERNELS = {0: "none", 1: "ofdm_presynced_kernel", 2: "ofdm_diff_kernel", 3: "ofdm_diff512_kernel",
-               4: "ofdm_presynced_warp_kernel", 5: "ofdm_fast512_kernel"}
+               4: "ofdm_presynced_warp_kernel", 5: "ofdm_fast512_kernel", 6: "ofdm_presynced_warp_fast_kernel"}
 
     @property
     def last_kernel(self):

@@ -100,6 +100,35 @@ struct WgTw { float2 a[16]; };                               // pass-A twiddles 
 __device__ __forceinline__ float2 wg_lo(float2 a, float2 b, float2 w) { return cadd(a, cmul(w, b)); }
 __device__ __forceinline__ float2 wg_hi(float2 a, float2 b, float2 w) { return csub(a, cmul(w, b)); }
 
+// PU_PRECISION_FAST forms of the same butterflies (BASELINE.json's 1e-4 LLR contract instead of bit-identical bins): fused
+// multiply-adds, a - w b as 2a - (a + w b), and no multiplication at all for the twiddles 1 and -j.
+__device__ __forceinline__ float2 fwg_lo(float2 a, float2 b, float2 w) {
+    return make_float2(__fmaf_rn(w.x, b.x, __fmaf_rn(-w.y, b.y, a.x)), __fmaf_rn(w.x, b.y, __fmaf_rn(w.y, b.x, a.y)));
+}
+__device__ __forceinline__ float2 fwg_hi(float2 a, float2 b, float2 w) {
+    return make_float2(__fmaf_rn(-w.x, b.x, __fmaf_rn(w.y, b.y, a.x)), __fmaf_rn(-w.x, b.y, __fmaf_rn(-w.y, b.x, a.y)));
+}
+__device__ __forceinline__ void fbutterfly(float2& a, float2& b, float2 w) {
+    const float2 s = fwg_lo(a, b, w);
+    b = make_float2(__fmaf_rn(2.0f, a.x, -s.x), __fmaf_rn(2.0f, a.y, -s.y));
+    a = s;
+}
+// m = twiddle index out of QUARTER * 4 (compile-time after unrolling): 0 -> w = 1, QUARTER -> w = -j
+template <int QUARTER>
+__device__ __forceinline__ void fbutterfly_m(float2& a, float2& b, int m, float2 w) {
+    if (m == 0) {
+        const float2 t = b;
+        b = make_float2(__fsub_rn(a.x, t.x), __fsub_rn(a.y, t.y));
+        a = make_float2(__fadd_rn(a.x, t.x), __fadd_rn(a.y, t.y));
+    } else if (m == QUARTER) {          // t = -j b = (b.y, -b.x)
+        const float2 t = make_float2(b.y, -b.x);
+        b = make_float2(__fsub_rn(a.x, t.x), __fsub_rn(a.y, t.y));
+        a = make_float2(__fadd_rn(a.x, t.x), __fadd_rn(a.y, t.y));
+    } else {
+        fbutterfly(a, b, w);
+    }
+}
+
 struct RxShared {
     float2 Hd[kMaxCarr];      // channel_estimate at data carriers
     float2 Hp[kMaxCarr];      // channel_estimate at pilot carriers
@@ -128,7 +157,11 @@ struct RxShared {
 #define PU_GSYNC() do { if constexpr (WARPG) __syncwarp(); else __syncthreads(); } while (0)
 // FAM: 0 = modulation family decided at run time, 1 = differential (DBPSK/DQPSK/D8PSK), 2 = coherent: the warp form is
 // compiled once per family so that each instance carries only its own equaliser and demappers (instruction-cache footprint).
-template <int NFFT, bool WARPG, int FAM>
+// FAST (warp form only): PU_PRECISION_FAST arithmetic -- FMA butterflies (above) and MUFU sin/cos (2^-21 absolute) + FMA mixing in the
+// CFO rotator instead of the exact libm restatements.  The rotator PHASES stay the reference's (the per-sample float recurrence walked
+// with bit-for-bit link checks): a closed form ph0 + i * inc was measured (v20) to drift from the recurrence by its systematic rounding
+// bias -- up to 1e-3 rad over a frame when |phase| ~ pi -- which moves coherent-QAM LLRs by 1e-2 and more.
+template <int NFFT, bool WARPG, int FAM, bool FAST = false>
 __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kernel(
     OfdmDev d, WgTw twa, const float* __restrict__ samples, size_t frame_stride, size_t B, int n_symbols, int training,
     const float* __restrict__ cfo_hz, const float* __restrict__ cfo_phase,
@@ -203,6 +236,31 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
     }
     PU_GSYNC();
 
+    // Warp form: the FFT window of the NEXT symbol is staged into shared memory with per-lane cp.async while the equaliser /
+    // tracker / demapper part of the current one runs (v26 capture of the synchronous form: 2.4 long-scoreboard stall cycles per
+    // issued instruction, 31 % of all stall samples on the pass-A loads -- with one CTA per SM walking the symbols in step,
+    // nothing else was there to cover the DRAM latency).  The staging area is the upper half of the transpose buffer (floats
+    // [NFFT, 2 NFFT) of buf), free between the pass-B reads of one symbol and pass A of the next; the rotated samples
+    // zbuf[k] (bytes 8k..8k+7) are written in ascending k and overwrite only staged samples 2k - NFFT (+1) <= k, already used.
+    float* xsm = reinterpret_cast<float*>(buf) + NFFT;
+    auto next_fft_symbol = [&](int after) {           // first symbol > after that runs an FFT (LTS symbols but the last do not when np == 0)
+        const int c = after + 1;
+        return (np == 0 && c < training - 1) ? training - 1 : c;
+    };
+    auto stage = [&](int sn) {
+        if (sn >= n_symbols) return;
+        const float* src = x + static_cast<size_t>(sn) * d.sym_len + d.cp;
+        const uint32_t dst = smem_u32(xsm);
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+            for (int m = 0; m < NFFT / 128; ++m) cp_async16(dst + 16 * (32 * m + lane), src + 4 * (32 * m + lane));
+        } else {                                      // acquired frames start on any sample
+#pragma unroll 8
+            for (int m = 0; m < NFFT / 32; ++m) cp_async4(dst + 4 * (32 * m + lane), src + 32 * m + lane);
+        }
+        cp_async_commit();
+    };
+    if constexpr (WARPG) stage(next_fft_symbol(-1));
     int llr_pos = 0;   // LLRs emitted so far (same for all threads)
     for (int s = 0; s < (WARPG && phase_sync ? n_symbols_cta : n_symbols); ++s) {
         if (WARPG && phase_sync) {
@@ -230,9 +288,20 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
         const float rot_inc = static_cast<float>(__ddiv_rn(__dmul_rn(-2.0f * 3.14159265358979323846, (double)S.cfo_hz), (double)d.sample_rate));
         auto rot_step = [&](float ph) {
             const float pi_hi = 3.14159274101257324f;   // smallest float > M_PI: (double)ph > M_PI  <=>  ph >= pi_hi
+            // 2 pi = two_hi + two_lo (float + float).  For pi <= |ph| < 4.2 the reference's float((double)ph -+ 2 pi) equals
+            // fl(fl(ph -+ two_hi) -+ two_lo): the first difference is exact (Sterbenz) and lands on the 2^-22 grid of [2, 4), and
+            // two_lo = -0.733 ulp of that grid, far from a rounding tie in either precision (tests/test_oracle_ofdm.py checks all
+            // 4 019 851 floats of the interval).  Anything larger (|cfo| > 7 kHz) takes the double path, on a warp-uniform branch
+            // so that the common case issues no FP64 conversion at all.
+            const float two_hi = 6.2831854820251465f, two_lo = -1.7484555e-7f;
             ph = __fadd_rn(ph, rot_inc);
-            if (ph >= pi_hi) ph = static_cast<float>((double)ph - 2.0f * 3.14159265358979323846);
-            else if (ph <= -pi_hi) ph = static_cast<float>((double)ph + 2.0f * 3.14159265358979323846);
+            const float a = fabsf(ph);
+            if (__any_sync(0xffffffffu, !(a < 4.2f))) {
+                if (ph >= pi_hi) ph = static_cast<float>((double)ph - 2.0f * 3.14159265358979323846);
+                else if (ph <= -pi_hi) ph = static_cast<float>((double)ph + 2.0f * 3.14159265358979323846);
+            } else if (a >= pi_hi) {
+                ph = ph > 0.0f ? __fsub_rn(__fsub_rn(ph, two_hi), two_lo) : __fadd_rn(__fadd_rn(ph, two_hi), two_lo);
+            }
             return ph;
         };
         if (!WARPG && rot) {
@@ -264,46 +333,85 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
         if constexpr (WARPG) {
             constexpr int EPL = G::EPL, LA = G::LA, CW = G::CW;
             float2* zbuf = buf;                                   // [NFFT] rotated samples in natural order (rot only)
+            if (!skip_fft) {
+                cp_async_wait_all();                              // this symbol's FFT window has landed in xsm
+                __syncwarp();
+            }
             if (rot) {
-                // ---------------- rotator (channel_equalizer.cpp:23,39-51): the per-sample recurrence walked 32 samples at a
-                //   time with the bit-for-bit link check described above; lane t of a window holds the phase of sample
-                //   base + t and mixes that sample itself, so the phases never leave registers.
+                // ---------------- rotator (channel_equalizer.cpp:23,39-51): the per-sample phase recurrence of the whole symbol
+                //   with the bit-for-bit link check described above; the lane that holds the phase of a sample of the FFT window
+                //   mixes that sample itself, so the phases never leave registers.
+                // The chain (b0, delta, i0) -- sample i0 has phase bits b0 and every link adds delta ulps -- persists across the symbol.
+                // Samples are taken 128 at a time: each lane forms its four candidates b0 + t delta and their float successors
+                // (independent instructions, no loop-carried dependency) and ONE vote says whether all 128 links hold and none comes
+                // near +-pi; that is the common case (a break needs a binade change, a zero crossing or a wrap) and costs ~8
+                // instructions per 32 samples.  Otherwise the four windows are re-walked one by one with the full rot_step, the
+                // chain restarting behind each broken link from the true successor computed by the lane that owns it.
                 float ph = S.rot_phase;
-                auto window = [&](int len) {                      // phases of the next len (<= 32) samples; advances ph
+                unsigned b0 = __float_as_uint(ph), delta = __float_as_uint(rot_step(ph)) - b0;
+                int i0 = 0, wbase = 0;
+                const bool keep = !skip_fft;
+                auto mix = [&](int i, float th) {                 // sample i of the symbol, rotator phase th
+                    const int k = i - d.cp;
+                    if (keep && k >= 0 && k < NFFT) {
+                        const float xv = xsm[k];
+                        const float2 o = __ldg(&nco[i]);
+                        float sn, cs;
+                        const float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
+                        if constexpr (FAST) {        // the reference's phase, MUFU sin/cos (2^-21 absolute), FMA mix
+                            __sincosf(th, &sn, &cs);
+                            zbuf[k] = make_float2(__fmaf_rn(z.x, cs, -__fmul_rn(z.y, sn)), __fmaf_rn(z.x, sn, __fmul_rn(z.y, cs)));
+                        } else {
+                            nl::sincosf_ref(th, &sn, &cs);
+                            zbuf[k] = cmul(z, make_float2(cs, sn));                               // mixed *= correction (:42)
+                        }
+                    }
+                };
+                auto window = [&](int len) {                      // the next len (<= 32) samples, link by link
                     float mine = 0.0f;
                     int done = 0;
                     while (done < len) {
-                        const unsigned b0 = __float_as_uint(ph);
-                        const unsigned delta = __float_as_uint(rot_step(ph)) - b0;
-                        const int t = lane - done;
+                        const int t = wbase + lane - i0;
                         const float cand = __uint_as_float(b0 + static_cast<unsigned>(t) * delta);
                         const float nxt = rot_step(cand);
-                        const bool inside = t >= 0 && lane < len;
+                        const bool inside = lane >= done && lane < len;
                         const bool broken = inside && __float_as_uint(nxt) != b0 + static_cast<unsigned>(t + 1) * delta;
                         const unsigned bal = __ballot_sync(0xffffffffu, broken);
                         const int last = bal ? (__ffs(bal) - 1) : (len - 1);      // lane of the last accepted value
                         if (inside && lane <= last) mine = cand;
-                        ph = __shfl_sync(0xffffffffu, nxt, last);                  // its true successor restarts the chain
+                        if (bal) {                                                 // its true successor restarts the chain
+                            ph = __shfl_sync(0xffffffffu, nxt, last);
+                            i0 = wbase + last + 1;
+                            b0 = __float_as_uint(ph);
+                            delta = __float_as_uint(rot_step(ph)) - b0;
+                        }
                         done = last + 1;
                     }
-                    return mine;
+                    if (lane < len) mix(wbase + lane, mine);
+                    wbase += len;
                 };
-                for (int i = 0; i < d.cp; i += 32) (void)window(min(32, d.cp - i));
-                for (int m = 0; m < NFFT / 32; ++m) {
-                    const float th = window(32);
-                    if (!skip_fft) {
-                        const int n = d.cp + 32 * m + lane;
-                        const float xv = __ldg(&xs[n]);
-                        const float2 o = __ldg(&nco[n]);
-                        float sn, cs;
-                        nl::sincosf_ref(th, &sn, &cs);
-                        const float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
-                        zbuf[32 * m + lane] = cmul(z, make_float2(cs, sn));                       // mixed *= correction (:42)
+                const float pi_lo = 3.1415925f;                   // largest float below pi_hi: |nxt| <= pi_lo  <=>  rot_step does not wrap
+                while (wbase < d.sym_len) {
+                    float cand[4];
+                    bool brk = false;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = wbase + 32 * k + lane;
+                        const unsigned cb = b0 + static_cast<unsigned>(i - i0) * delta;
+                        cand[k] = __uint_as_float(cb);
+                        const float nxt = __fadd_rn(cand[k], rot_inc);
+                        brk |= i < d.sym_len && (__float_as_uint(nxt) != cb + delta || !(fabsf(nxt) <= pi_lo));
+                    }
+                    if (!__any_sync(0xffffffffu, brk)) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mix(wbase + 32 * k + lane, cand[k]);
+                        wbase += 128;
+                    } else {
+                        for (int k = 0; k < 4 && wbase < d.sym_len; ++k) window(min(32, d.sym_len - wbase));
                     }
                 }
-                for (int i = d.cp + NFFT; i < d.sym_len; i += 32) (void)window(min(32, d.sym_len - i));
                 __syncwarp();                    // every lane has read S.rot_phase (the shuffles of window() order execution, not memory)
-                if (lane == 0) S.rot_phase = ph;
+                if (lane == 0) S.rot_phase = __uint_as_float(b0 + static_cast<unsigned>(d.sym_len - i0) * delta);   // phase behind the last sample
                 __syncwarp();
             }
             if (!skip_fft) {
@@ -316,7 +424,7 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                     if (rot) {
                         v[q] = zbuf[n];
                     } else {
-                        const float xv = __ldg(&xs[d.cp + n]);
+                        const float xv = xsm[n];
                         const float2 o = __ldg(&nco[d.cp + n]);
                         v[q] = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));               // samples[i] * conj(osc) (:36)
                     }
@@ -328,7 +436,8 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                     for (int pr = 0; pr < EPL / 2; ++pr) {
                         const int kq = pr & (half - 1);
                         const int a = ((pr >> (t - 1)) << t) | kq;
-                        butterfly(v[a], v[a + half], twa.a[kq << (LA - t)]);
+                        if constexpr (FAST) fbutterfly_m<(1 << LA) / 4>(v[a], v[a + half], kq << (LA - t), twa.a[kq << (LA - t)]);
+                        else butterfly(v[a], v[a + half], twa.a[kq << (LA - t)]);
                     }
                 }
                 __syncwarp();                                       // zbuf has been read by every lane
@@ -344,15 +453,25 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                     const int p = wc + CW * j + 256 * wb8;
                     v[j] = buf[p + (p >> G::PADSH)];
                 }
+                __syncwarp();                                       // buf has been read by every lane:
+                stage(next_fft_symbol(s));                          // the next FFT window travels during the rest of this symbol
 #pragma unroll
-                for (int j = 0; j < EPL; j += 2) butterfly(v[j], v[j + 1], wl[0]);
+                for (int j = 0; j < EPL; j += 2) {
+                    if constexpr (FAST) fbutterfly(v[j], v[j + 1], wl[0]);
+                    else butterfly(v[j], v[j + 1], wl[0]);
+                }
 #pragma unroll
                 for (int q = 1; q < LA; ++q) {
                     const int step = 1 << (q + 1), hh = 1 << q;
 #pragma unroll
                     for (int j = 0; j < EPL; j += step) {
-                        v[j] = wg_lo(v[j], v[j + hh], wl[q]);
-                        v[j + step - 1] = wg_hi(v[j + step - 1 - hh], v[j + step - 1], wh[q]);
+                        if constexpr (FAST) {
+                            v[j] = fwg_lo(v[j], v[j + hh], wl[q]);
+                            v[j + step - 1] = fwg_hi(v[j + step - 1 - hh], v[j + step - 1], wh[q]);
+                        } else {
+                            v[j] = wg_lo(v[j], v[j + hh], wl[q]);
+                            v[j + step - 1] = wg_hi(v[j + step - 1 - hh], v[j + step - 1], wh[q]);
+                        }
                     }
                 }
                 if (NFFT == 512) {
@@ -361,7 +480,8 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                     float2 recv;
                     recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
                     recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
-                    binbuf[lane] = wb8 ? wg_hi(recv, v[EPL - 1], wlast) : wg_lo(v[0], recv, wlast);
+                    if constexpr (FAST) binbuf[lane] = wb8 ? fwg_hi(recv, v[EPL - 1], wlast) : fwg_lo(v[0], recv, wlast);
+                    else binbuf[lane] = wb8 ? wg_hi(recv, v[EPL - 1], wlast) : wg_lo(v[0], recv, wlast);
                 } else {
                     binbuf[wc] = v[0];                              // bin c
                     binbuf[CW + wc] = v[EPL - 1];                   // bin N - CW + c
@@ -1213,13 +1333,16 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         const bool diff = pu::is_differential(p.cfg.modulation);
         using WK = void (*)(pu::OfdmDev, pu::WgTw, const float*, size_t, size_t, int, int, const float*, const float*, float*, size_t, int,
                             float*, float*, float*, unsigned, const int*, const int*, int);
-        const WK wk = p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1> : pu::ofdm_presynced_kernel<512, true, 2>)
-                                    : (diff ? pu::ofdm_presynced_kernel<1024, true, 1> : pu::ofdm_presynced_kernel<1024, true, 2>);
-        static std::atomic<uint64_t> attrw[4];      // per kernel instance, one bit per device (pu_async.cuh: smem_optin)
-        PU_CUDA_TRY(pu::smem_optin(attrw[(p.nfft == 512 ? 0 : 2) + (diff ? 0 : 1)], wk, 232448));
+        const bool fastk = h->fast();     // PU_PRECISION_FAST: FMA butterflies + closed-form rotator (see the kernel's FAST parameter)
+        const WK wk = fastk ? (p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1, true> : pu::ofdm_presynced_kernel<512, true, 2, true>)
+                                             : (diff ? pu::ofdm_presynced_kernel<1024, true, 1, true> : pu::ofdm_presynced_kernel<1024, true, 2, true>))
+                            : (p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1> : pu::ofdm_presynced_kernel<512, true, 2>)
+                                             : (diff ? pu::ofdm_presynced_kernel<1024, true, 1> : pu::ofdm_presynced_kernel<1024, true, 2>));
+        static std::atomic<uint64_t> attrw[8];      // per kernel instance, one bit per device (pu_async.cuh: smem_optin)
+        PU_CUDA_TRY(pu::smem_optin(attrw[(fastk ? 4 : 0) + (p.nfft == 512 ? 0 : 2) + (diff ? 0 : 1)], wk, 232448));
         wk<<<wgrid, warps * 32, static_cast<size_t>(warps) * group, st>>>(h->dev, twa, d_samples, L, B, n_symbols, training, d_cfo, d_phase, d_llr,
                                                                            llr_stride, limit, d_snr, d_fcfo, nullptr, group, d_fstart, d_fnsym, wsync ? 1 : 0);
-        h->last_kernel = 4;
+        h->last_kernel = fastk ? 6 : 4;
         h->ctx->launches.fetch_add(1);
         PU_CUDA_TRY(cudaGetLastError());
         return PU_OK;

@@ -196,13 +196,70 @@ def test_fast_hard_decisions_match_on_frames_decoded_with_margin(ctx):
     assert (llr2.cpu().numpy().view(np.uint32) == lf.view(np.uint32)).all()
 
 
+GENERAL_CASES = [("m1", R.QPSK, R.R1_2, 40, (4.0, 10.0, 18.0), None), ("m1", R.QAM16, R.R1_2, 40, (8.0, 14.0, 22.0), None),
+                 ("m1", R.BPSK, R.R1_2, 40, (0.0, 6.0, 12.0), None), ("m1", R.QAM64, R.R3_4, 60, (18.0, 24.0, 30.0), None),
+                 ("m3", R.QAM32, R.R3_4, 60, (12.0, 18.0, 26.0), None), ("m3", R.QAM16, R.R3_4, 60, (10.0, 16.0, 24.0), None),
+                 ("m1", R.DQPSK, R.R1_2, 40, (2.0, 8.0, 16.0), (6.5, -1.3)), ("m1", R.QAM16, R.R1_2, 40, (10.0, 16.0, 24.0), (-12.0, 0.4)),
+                 ("m3", R.QAM32, R.R3_4, 60, (14.0, 20.0, 28.0), (3.0, 2.0))]
+
+
+@pytest.mark.parametrize("case", range(len(GENERAL_CASES)))
+def test_fast_general_kernel_against_exact_kernel_and_oracle(ctx, case):
+    """PU_PRECISION_FAST of the general warp kernel (pilots, coherent QAM, CFO rotator: FMA butterflies + closed-form rotator) against
+    the exact kernel on the same frames, and against the oracle on a subset: LLRs within 1e-4 * max(|ref|, 0.5) up to the few that sit
+    next to a zero of their law or ride on the tracked CFO's last bits, LDPC verdicts and bytes identical on frames decoded with margin,
+    the tracked CFO and SNR reports equal to ~1e-4."""
+    from projectultra_b200 import capi
+    preset, mod, rate, nbytes, snrs, cfo = GENERAL_CASES[case]
+    cfg = (R.config_m1 if preset == "m1" else R.config_m3)(mod, rate)
+    if cfo:
+        cfg.tx_cfo_hz = cfo[0]
+    dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
+    frames = []
+    for i, snr in enumerate(snrs):
+        for j in range(12):
+            rng = np.random.default_rng(5000 + 100 * case + 20 * i + j)
+            data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+            frames.append(awgn(O.ofdm_tx(cfg, O.ldpc_encode(rate, data), 0), snr, rng))
+    frames = np.stack(frames)
+    B = len(frames)
+    cf = np.full(B, cfo[0], np.float32) if cfo else None
+    ph = np.full(B, cfo[1], np.float32) if cfo else None
+    lx, snr_x, fc_x = dem.presynced_batch(frames, 2, cf, ph)
+    assert dem.last_kernel == "ofdm_presynced_warp_kernel"
+    dem.set_precision("fast")
+    lf, snr_f, fc_f = dem.presynced_batch(frames, 2, cf, ph)
+    assert dem.last_kernel == "ofdm_presynced_warp_fast_kernel"
+    bad, floor, gate, same = classify(lf, lx)
+    d = np.abs(lf.astype(np.float64) - lx)
+    print("case %d (%s mod %d cfo %s): %d LLRs, outside 1e-4 rel %d (%.2e), clip-floor flips %d, gate flips %d, bit-identical %.4f, max |d| %.2e, "
+          "p99.9 |d| %.2e; tracked CFO max |d| %.2e Hz, SNR max |d| %.2e dB"
+          % (case, preset, mod, cfo, lx.size, bad, bad / lx.size, floor, gate, same, d.max(), np.quantile(d, 0.999),
+             np.abs(fc_f - fc_x).max(), np.abs(snr_f - snr_x).max()))
+    assert bad <= 5e-3 * lx.size, (bad, lx.size)
+    assert np.quantile(d, 0.999) <= 2e-3 and d.max() <= 0.05 or floor + gate > 0
+    assert np.abs(fc_f - fc_x).max() <= 2e-3 and np.abs(snr_f - snr_x).max() <= 1e-2
+    dec = capi.LdpcDecoder(ctx, rate)
+    ix, okx, itx = dec.decode_batch(lx[:, :648].copy())
+    i_f, okf, itf = dec.decode_batch(lf[:, :648].copy())
+    margin = (okx == 1) & (itx <= 40)
+    assert (okf[margin] == 1).all() and (i_f[margin] == ix[margin]).all()
+    assert (okf != okx).sum() <= 1
+    # the oracle on the first frame of every SNR point
+    rcfg = cfg
+    for b in range(0, B, 12):
+        want, _, _ = O.ofdm_presynced(rcfg, frames[b], 2, 2 if cfo else 1, cfo[0] if cfo else 0.0, cfo[1] if cfo else 0.0)
+        bo, fo, go, _ = classify(lf[b][:len(want)], want)
+        assert bo <= 5e-3 * len(want) + 2, (b, bo)
+
+
 def test_fast_falls_back_to_exact_kernels_outside_its_coverage(ctx):
     from projectultra_b200 import capi
-    cfg = R.config_m1(R.QPSK, R.R1_2)          # coherent: no FMA form -> exact kernel, identical results in both modes
+    cfg = R.config_m3(R.DQPSK, R.R3_4)          # 1024-FFT differential no-pilot at zero CFO: ofdm_diff_kernel has no fast form
     dem = capi.OfdmDemodulator(ctx, to_capi_cfg(cfg))
-    frames = frames_for(cfg, R.R1_2, (6.0, 15.0), 2, 9100)
+    frames = frames_for(cfg, R.R3_4, (6.0, 15.0), 2, 9100)
     a = dem.presynced_batch(frames)[0]
     dem.set_precision("fast")
     b = dem.presynced_batch(frames)[0]
-    assert dem.last_kernel != "ofdm_fast512_kernel"
+    assert dem.last_kernel == "ofdm_diff_kernel"
     assert (a.view(np.uint32) == b.view(np.uint32)).all()

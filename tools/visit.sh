@@ -48,6 +48,10 @@ sweepN) N=${NGPU:-8}; for r in $(seq 0 $((N-1))); do RANK=$r WORLD_SIZE=$N LOCAL
 h2dN) N=${NGPU:-8}; for n in 1 2 4 8; do [ $n -le $N ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2972$n tools/h2d_bench.py 2>/dev/null | grep '^{' | tee -a $OUT/h2d.jsonl | cut -c1-400; done;;
 benchN) N=${NGPU:-8}; for n in ${BENCH_NS:-4 8}; do [ $n -le $N ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2973$n bench.py --gpus $n 2>$OUT/bench_N$n.err | grep '^{' > $OUT/bench_N$n.json; python -c "import json,sys; j=json.load(open('$OUT/bench_N$n.json')); print($n, 'value', j['value'], 'e2e', j['e2e']['value'], j['e2e'].get('h2d_gbs_per_gpu'), 'sweep', {k:v['value'] for k,v in j.get('sweep',{}).items()})"; done;;
 frames) ( time python -m pytest tests/test_frame_gpu.py -q -x ) > $OUT/pytest_frames.log 2>&1; tail -25 $OUT/pytest_frames.log;;
+fastgen) ( time python -m pytest tests/test_ofdm_fast_gpu.py -q -s -k "general or falls" ) > $OUT/pytest_fastgen.log 2>&1; grep -E "^case|passed|failed|Error|assert" $OUT/pytest_fastgen.log | cut -c1-400 | tail -30
+  { for m in m3 m1qam16; do python tools/ofdm_quick_bench.py 4096 $m; QB_PRECISION=fast python tools/ofdm_quick_bench.py 4096 $m; done; QB_CHANNEL=good QB_PRECISION=fast python tools/ofdm_quick_bench.py 4096 m3; } > $OUT/quick_fastgen.txt 2>&1; cat $OUT/quick_fastgen.txt;;
+ncu4)
+  for m in m3 m1qam16; do QB_PRECISION=fast ncu --set full --clock-control none --import-source on -k regex:ofdm_presynced -s 3 -c 1 -f -o $OUT/prof_fast_$m python tools/ofdm_quick_bench.py 4096 $m > $OUT/ncu_fast_$m.log 2>&1; done;;
 *) echo "unknown: $w";;
 esac; done
 ls -la $OUT
