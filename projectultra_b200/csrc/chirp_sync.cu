@@ -8,9 +8,14 @@
 // thread); what runs in parallel are the search positions, which the reference evaluates independently.  The first-maximum
 // rule of the reference's ascending scans is kept by the reductions (larger value wins, equal value -> smaller position).
 #include <cfloat>
+#include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
+#include "pu_async.cuh"
 #include "pu_internal.h"
 
 namespace pu {
@@ -172,31 +177,368 @@ __device__ int chirp_detect_template(ChirpShared& S, ChirpWarpBuf* WB, const flo
     return best >= threshold ? best_pos : -1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Two-tier form of detectChirpTemplate.  What the reference computes at every one of the ~870 coarse positions -- three ordered
+// 24 000-tap fp32 sums -- decides only (a) which position holds the first maximum and (b) the value there.  So the positions are
+// RANKED with a cheap estimate and only the leaders are evaluated the reference's way:
+//   tier 1  the window is low-passed (47 taps, 4 kHz) and decimated 6:1 -- the template occupies 300..2700 Hz, so
+//           sum_i x[p+i] t[i] ~ 6 sum_j xf[p+6j] t[6j] -- and every coarse position (48 samples = 8 decimated ones apart) gets a
+//           4 000-tap FMA correlation from shared memory, in any summation order; energies come from 48-sample partial sums.
+//           Measured against the ordered sums: rms error 1-2 % of the correlation floor of a noise-only window.
+//   tier 2  the 32 best-ranked positions are evaluated exactly (lane = position; the three sums are three independent chains and
+//           run in three warps), the result is the first maximum among them, and the search ends when every unverified position
+//           is out of reach:  estimate + 4 x (largest |exact - estimate| seen) < best exact value.  Otherwise the next 32 are
+//           verified, down to all of them -- the result is then the brute-force one by construction.
+// The fine search (+-48 positions, parabolic neighbours included) stays exact, as 12 concurrent chains over one linear tile.
+// tests/test_chirp_sync_gpu.py runs both forms on the same frames (PU_CHIRP_SEARCH=exact selects the brute-force kernel).
+constexpr int kRankD = 6, kRankNT = 47, kRankC = 23;   // decimation, low-pass taps, centre tap
+constexpr int kC2Threads = 384, kC2Warps = kC2Threads / 32;
+constexpr int kC2N = 24000, kC2Nd = kC2N / kRankD;     // the 48 kHz chirp: 24 000 taps, 4 000 decimated
+constexpr int kC2MaxPos = 3000;                         // coarse positions per window the shared-memory budget of one SM allows
+constexpr int kC2TileIn = kC2Threads * kRankD + kRankNT - 1;
+constexpr int kC2Row = 65;                              // verify tile: 64 taps per row, odd stride
+// Shared memory of one frame, carved from the dynamic allocation for the window's coarse-position budget `maxpos` (host: chirp2_smem_bytes;
+// 65 KB for 66 000-sample buffers, 84 KB for 84 000: two frames per SM up to ~110 000 samples, one beyond).
+struct Chirp2Smem {
+    float* xd;                        // tier 1: decimated window, whole tiles.  tier 2: rows[2][32][kC2Row].  fine: lin[2][256]
+    float* tile;                      // low-pass input tile (tier 1b only); the same storage then holds acc, a, order
+    float (*acc)[2];
+    float* a;                         // estimate of the normalised correlation
+    unsigned short* order;            // order[rank] = coarse index, best estimate first
+    float* seg;                       // 48-sample energies -> exclusive prefix
+    float* lp;                        // [48] low-pass taps
+    float* exq; float* exe; float* ex;   // [128] each
+    int* cand;                        // [32]
+    float* best_c; int* best_p; int* go;
+};
+__host__ __device__ inline int chirp2_tiles(int maxpos) { return (8 * maxpos + kC2Nd + kC2Threads - 1) / kC2Threads; }
+__host__ __device__ inline int chirp2_union_floats(int maxpos) {
+    const int r = 2 * maxpos + maxpos + (maxpos + 1) / 2;
+    return (r > kC2TileIn + 2 ? r : kC2TileIn + 2) + 3 & ~3;
+}
+__host__ __device__ inline size_t chirp2_smem_floats(int maxpos) {
+    return static_cast<size_t>(chirp2_tiles(maxpos)) * kC2Threads + chirp2_union_floats(maxpos) +
+           (chirp2_tiles(maxpos) * (kC2Threads / 8) + 8) + 48 + 3 * 128 + 32 + 4;
+}
+__device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos) {
+    Chirp2Smem S;
+    float* p = reinterpret_cast<float*>(base);
+    S.xd = p; p += static_cast<size_t>(chirp2_tiles(maxpos)) * kC2Threads;
+    S.tile = p;
+    S.acc = reinterpret_cast<float (*)[2]>(p);
+    S.a = p + 2 * maxpos;
+    S.order = reinterpret_cast<unsigned short*>(p + 3 * maxpos);
+    p += chirp2_union_floats(maxpos);
+    S.seg = p; p += chirp2_tiles(maxpos) * (kC2Threads / 8) + 8;
+    S.lp = p; p += 48;
+    S.exq = p; p += 128;
+    S.exe = p; p += 128;
+    S.ex = p; p += 128;
+    S.cand = reinterpret_cast<int*>(p); p += 32;
+    S.best_c = p; S.best_p = reinterpret_cast<int*>(p + 1); S.go = reinterpret_cast<int*>(p + 2);
+    return S;
+}
+
+// the reference's closing arithmetic (:655-661)
+__device__ __forceinline__ float chirp_norm(float ci, float cq, float se, float te) {
+    const float denom = __fsqrt_rn(__fmul_rn(se, te));
+    if (denom < 1e-10f) return 0.0f;
+    return __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ci, ci), __fmul_rn(cq, cq))), denom);
+}
+
+__device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool valid) {
+    const int bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+
+// x = frame, L = its length, w0 = window start, Lw = window length: detectChirpTemplate(x + w0, Lw) (:560-629)
+__device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restrict__ x, int L, int w0, int Lw, const float* __restrict__ ts,
+                                      const float* __restrict__ tc, const float* __restrict__ tds, const float* __restrict__ tdc, float te,
+                                      float threshold, float* corr_out) {
+    constexpr int n = kC2N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    *corr_out = 0.0f;
+    if (Lw < n) return -1;
+    const int search_len = Lw - n;
+    const int n_pos = (search_len + 47) / 48;
+    if (n_pos == 0) return -1;
+    const float* xw = x + w0;
+    __syncthreads();                                         // the previous call's shared state is dead
+    // ---------------- tier 1b: low-pass + 6:1 decimation, 48-sample energies
+    const int nxd = 8 * (n_pos - 1) + kC2Nd;                 // decimated samples the positions touch
+    const int ntile = (nxd + kC2Threads - 1) / kC2Threads;
+    for (int tl = 0; tl < ntile; ++tl) {
+        const int q0 = tl * kC2Threads * kRankD - kRankC;    // window index of tile[0]
+        for (int j = tid; j < kC2TileIn; j += kC2Threads) {
+            const int g = w0 + q0 + j;
+            S.tile[j] = (g >= 0 && g < L) ? x[g] : 0.0f;
+        }
+        __syncthreads();
+        {
+            const float* t = S.tile + kRankD * tid;
+            float y = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kRankNT; ++k) y = fmaf(S.lp[k], t[k], y);
+            S.xd[tl * kC2Threads + tid] = y;
+            float e = 0.0f;                                   // 6 samples per thread, 8 threads per 48-sample segment
+#pragma unroll
+            for (int k = 0; k < kRankD; ++k) { const float v = t[kRankC + k]; e = fmaf(v, v, e); }
+            e += __shfl_xor_sync(0xffffffffu, e, 1);
+            e += __shfl_xor_sync(0xffffffffu, e, 2);
+            e += __shfl_xor_sync(0xffffffffu, e, 4);
+            if ((tid & 7) == 0) S.seg[tl * (kC2Threads / 8) + (tid >> 3)] = e;
+        }
+        __syncthreads();
+    }
+    for (int j = tid; j < n_pos; j += kC2Threads) { S.acc[j][0] = 0.0f; S.acc[j][1] = 0.0f; }   // (the tile is dead: same storage)
+    // exclusive prefix of the segment energies (one warp)
+    const int nseg = ntile * (kC2Threads / 8);
+    if (warp == 0) {
+        float carry = 0.0f;
+        for (int b = 0; b < nseg + 1; b += 32) {
+            const float v = (b + lane < nseg) ? S.seg[b + lane] : 0.0f;
+            float incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (b + lane <= nseg) S.seg[b + lane] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one third of the taps); lane l starts 4 l taps
+    // into its third and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
+    {
+        const int nblk = (n_pos + 7) / 8;
+        if (tid < 3 * nblk) {
+            const int sg = tid / nblk, pb = tid - sg * nblk;
+            const int j0 = sg * 1336, len = sg == 2 ? kC2Nd - 2672 : 1336;
+            float ac[8], as[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { ac[r] = 0.0f; as[r] = 0.0f; }
+            const float* xb = S.xd + 64 * pb;
+            for (int jj = 0; jj < len; jj += 4) {
+                int j = jj + 4 * lane;
+                if (j >= len) j -= len;
+                j += j0;
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(tdc + j));   // 32 KB per template, shared by every frame: L1 / L2
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(tds + j));
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float4 v = *reinterpret_cast<const float4*>(xb + 8 * r + j);
+                    ac[r] = fmaf(v.x, c4.x, fmaf(v.y, c4.y, fmaf(v.z, c4.z, fmaf(v.w, c4.w, ac[r]))));
+                    as[r] = fmaf(v.x, s4.x, fmaf(v.y, s4.y, fmaf(v.z, s4.z, fmaf(v.w, s4.w, as[r]))));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int m = 8 * pb + r;
+                if (m < n_pos) { atomicAdd(&S.acc[m][0], ac[r]); atomicAdd(&S.acc[m][1], as[r]); }
+            }
+        }
+    }
+    __syncthreads();
+    for (int m = tid; m < n_pos; m += kC2Threads) {
+        const float se = S.seg[m + n / 48] - S.seg[m];
+        const float denom = sqrtf(fmaxf(se, 0.0f) * te);
+        S.a[m] = denom < 1e-10f ? 0.0f : sqrtf(S.acc[m][0] * S.acc[m][0] + S.acc[m][1] * S.acc[m][1]) / denom;
+    }
+    __syncthreads();
+    for (int m = tid; m < n_pos; m += kC2Threads) {          // rank by counting: larger estimate first, ties by position
+        const float am = S.a[m];
+        int rk = 0;
+        for (int o = 0; o < n_pos; ++o) {
+            const float ao = S.a[o];
+            rk += (ao > am || (ao == am && o < m)) ? 1 : 0;
+        }
+        S.order[rk] = static_cast<unsigned short>(m);
+    }
+    if (tid == 0) { (*S.best_c) = 0.0f; (*S.best_p) = -1; }
+    __syncthreads();
+    // ---------------- tier 2: exact evaluation of the leaders, 32 per round
+    float (*rows)[32][kC2Row] = reinterpret_cast<float (*)[32][kC2Row]>(S.xd);
+    float errmax = 0.0f;                                     // thread 0
+    for (int nv = 0; nv < n_pos; nv += 32) {
+        const int cnt = min(32, n_pos - nv);
+        if (tid < 32) S.cand[tid] = tid < cnt ? 48 * static_cast<int>(S.order[nv + tid]) : 0;
+        __syncthreads();
+        auto stage = [&](int tile, int buf) {
+            for (int r = warp; r < 32; r += kC2Warps) {
+                const float* src = xw + S.cand[r] + 64 * tile;
+                const uint32_t dst = smem_u32(&rows[buf][r][0]);
+                cp_async4(dst + 4 * lane, src + lane);
+                cp_async4(dst + 4 * (lane + 32), src + lane + 32);
+            }
+            cp_async_commit();
+        };
+        float sum = 0.0f;
+        const float* tpl = warp == 0 ? tc : ts;
+        stage(0, 0);
+        for (int tile = 0; tile < n / 64; ++tile) {
+            cp_async_wait_all();
+            __syncthreads();
+            if (tile + 1 < n / 64) stage(tile + 1, (tile + 1) & 1);
+            if (warp < 3) {
+                const float* row = rows[tile & 1][lane];
+                if (warp < 2) {
+#pragma unroll 4
+                    for (int t = 0; t < 64; t += 4) {
+                        const float4 tv = __ldg(reinterpret_cast<const float4*>(tpl + 64 * tile + t));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t], tv.x));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 1], tv.y));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 2], tv.z));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 3], tv.w));
+                    }
+                } else {
+#pragma unroll 16
+                    for (int t = 0; t < 64; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
+                }
+            }
+        }
+        if (warp == 1) S.exq[lane] = sum;
+        if (warp == 2) S.exe[lane] = sum;
+        __syncthreads();
+        if (warp == 0) S.ex[lane] = chirp_norm(sum, S.exq[lane], S.exe[lane], te);
+        __syncthreads();
+        if (tid == 0) {
+            float bc = (*S.best_c);
+            int bp = (*S.best_p);
+            for (int r = 0; r < cnt; ++r) {
+                const float c = S.ex[r];
+                const int pos = S.cand[r];
+                errmax = fmaxf(errmax, fabsf(c - S.a[S.order[nv + r]]));
+                if (c > bc || (c == bc && bp >= 0 && pos < bp)) { bc = c; bp = pos; }   // the ascending scan's first maximum
+            }
+            (*S.best_c) = bc;
+            (*S.best_p) = bp;
+            int go = 0;
+            if (nv + 32 < n_pos) {
+                const float next = S.a[S.order[nv + 32]];     // the largest unverified estimate
+                go = !(next == 0.0f || next + 4.0f * errmax + 1e-6f < bc);
+            }
+            (*S.go) = go;
+        }
+        __syncthreads();
+        if (!(*S.go)) break;
+    }
+    float best = (*S.best_c);
+    int best_pos = (*S.best_p);
+    __syncthreads();
+    *corr_out = best;
+    if (best_pos < 0 || best < __fmul_rn(threshold, 0.3f)) return -1;
+    // ---------------- fine search (:600-612) and the parabola's neighbours (:615-625): every position of [fine_start - 1, fine_end + 1]
+    // exactly, 32 positions x {ci, cq, se} per warp triple over one linear tile (lane l reads lin[t + l]: consecutive banks)
+    const int fine_start = max(0, best_pos - 48), fine_end = min(search_len, best_pos + 48);
+    const int q0 = max(0, fine_start - 1), q1 = min(search_len, fine_end + 1);
+    {
+        float (*lin)[256] = reinterpret_cast<float (*)[256]>(S.xd);
+        auto stage = [&](int tile, int buf) {
+            if (tid < 256) {
+                const int wi = q0 + 128 * tile + tid;         // window index; positions past q1 read on into the frame or zeros
+                const bool ok = w0 + wi < L;
+                cp_async4_zfill(smem_u32(&lin[buf][tid]), ok ? xw + wi : x, ok);
+            }
+            cp_async_commit();
+        };
+        const int grp = warp / 3, kind = warp - 3 * grp;
+        const float* tpl = kind == 0 ? tc : ts;
+        float sum = 0.0f;
+        stage(0, 0);
+        for (int tile = 0; tile < (n + 127) / 128; ++tile) {
+            cp_async_wait_all();
+            __syncthreads();
+            if (128 * (tile + 1) < n) stage(tile + 1, (tile + 1) & 1);
+            const float* row = lin[tile & 1] + 32 * grp + lane;
+            const int tn = min(128, n - 128 * tile);
+            if (kind < 2) {
+#pragma unroll 4
+                for (int t = 0; t < tn; t += 4) {
+                    const float4 tv = __ldg(reinterpret_cast<const float4*>(tpl + 128 * tile + t));
+                    sum = __fadd_rn(sum, __fmul_rn(row[t], tv.x));
+                    sum = __fadd_rn(sum, __fmul_rn(row[t + 1], tv.y));
+                    sum = __fadd_rn(sum, __fmul_rn(row[t + 2], tv.z));
+                    sum = __fadd_rn(sum, __fmul_rn(row[t + 3], tv.w));
+                }
+            } else {
+#pragma unroll 16
+                for (int t = 0; t < tn; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
+            }
+        }
+        if (kind == 1) S.exq[32 * grp + lane] = sum;
+        if (kind == 2) S.exe[32 * grp + lane] = sum;
+        __syncthreads();
+        if (kind == 0) S.ex[32 * grp + lane] = chirp_norm(sum, S.exq[32 * grp + lane], S.exe[32 * grp + lane], te);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int pos = fine_start; pos <= fine_end; ++pos) {
+            const float c = S.ex[pos - q0];
+            if (c > best) { best = c; best_pos = pos; }
+        }
+        if (best_pos > 0 && best_pos < search_len - 1) {
+            const float c0 = S.ex[best_pos - 1 - q0], c1 = best, c2 = S.ex[best_pos + 1 - q0];
+            const float denom = __fmul_rn(2.0f, __fadd_rn(__fsub_rn(c0, __fmul_rn(2.0f, c1)), c2));
+            if (fabsf(denom) > 1e-10f) {
+                float delta = __fdiv_rn(__fsub_rn(c0, c2), denom);
+                delta = fmaxf(-1.0f, fminf(1.0f, delta));
+                best_pos = static_cast<int>(roundf(__fadd_rn(static_cast<float>(best_pos), delta)));
+            }
+        }
+        (*S.best_c) = best;
+        (*S.best_p) = best_pos;
+    }
+    __syncthreads();
+    best = (*S.best_c);
+    best_pos = (*S.best_p);
+    (void)q1;
+    *corr_out = best;
+    return best >= threshold ? best_pos : -1;
+}
+
 // out_info[b] = {success, up_chirp_start, down_chirp_start, start_sample (training start) or -1}; out_f[b] = {cfo_hz, up corr, down corr,
 // initial rotator phase}.  frame_start / frame_nsym (optional) = the window handed to the presynced kernel (0 symbols when not found).
-__global__ void __launch_bounds__(kChirpThreads) chirp_detect_kernel(ChirpDev c, const float* __restrict__ samples, size_t frame_stride, int L,
+template <bool TWO_TIER>
+__global__ void __launch_bounds__(TWO_TIER ? kC2Threads : kChirpThreads, TWO_TIER ? 2 : 1) chirp_detect_kernel(ChirpDev c, const float* __restrict__ samples, size_t frame_stride, int L,
                                                                      float threshold, int sym_len, int4* __restrict__ out_info,
                                                                      float4* __restrict__ out_f, int* __restrict__ frame_start,
                                                                      int* __restrict__ frame_nsym, float* __restrict__ cfo_out,
                                                                      float* __restrict__ phase_out, int* __restrict__ n_llr,
-                                                                     int llr_per_symbol, int llr_stride) {
+                                                                     int llr_per_symbol, int llr_stride, int maxpos) {
     __shared__ ChirpShared S;
     extern __shared__ __align__(16) unsigned char chirp_smem[];
-    ChirpWarpBuf* WB = reinterpret_cast<ChirpWarpBuf*>(chirp_smem);   // one staging buffer per warp
+    ChirpWarpBuf* WB = reinterpret_cast<ChirpWarpBuf*>(chirp_smem);   // brute-force form: one staging buffer per warp
+    const Chirp2Smem S2 = chirp2_carve(chirp_smem, maxpos);           // two-tier form
     const int tid = threadIdx.x;
     const float* x = samples + static_cast<size_t>(blockIdx.x) * frame_stride;
+    if constexpr (TWO_TIER) {
+        if (tid < 48) S2.lp[tid] = tid < kRankNT ? __ldg(&c.lp[tid]) : 0.0f;
+    }
+    // detectChirpTemplate on the window [w0, w0 + Lw) of the frame with the up (0) or down (1) template
+    auto detect = [&](int w0, int Lw, int down, float* corr) {
+        const float* ts = down ? c.dn_s : c.up_s;
+        const float* tc = down ? c.dn_c : c.up_c;
+        const float te = down ? c.dn_e : c.up_e;
+        if constexpr (TWO_TIER) {
+            const float* dec = c.dec + (down ? 2 : 0) * static_cast<size_t>(c.nd);
+            return chirp_detect_template2(S2, x, L, w0, Lw, ts, tc, dec, dec + c.nd, te, threshold, corr);
+        } else {
+            return chirp_detect_template(S, WB, x + w0, Lw, ts, tc, c.n, te, threshold, corr);
+        }
+    };
     int success = 0, up_start = -1, down_start = -1, start = -1;   // DualChirpResult defaults (chirp_sync.hpp:317-324)
     float cfo = 0.0f, up_corr = 0.0f, dn_corr = 0.0f, phase = 0.0f;
     do {
         if (L < 2 * c.n + c.gap) break;                                                       // :368-372
-        const int up_pos = chirp_detect_template(S, WB, x, L, c.up_s, c.up_c, c.n, c.up_e, threshold, &up_corr);
+        const int up_pos = detect(0, L, 0, &up_corr);
         if (up_pos < 0) break;
         const int ds = up_pos + c.n / 2, expected = up_pos + c.n + c.gap, margin = 2 * c.n;      // :423-435
         int de = min(L, expected + margin);
         if (ds >= L) break;
         if (de <= ds + c.n) de = min(L, ds + 2 * c.n);
         float dc;
-        const int rel = chirp_detect_template(S, WB, x + ds, de - ds, c.dn_s, c.dn_c, c.n, c.dn_e, threshold, &dc);
+        const int rel = detect(ds, de - ds, 1, &dc);
         if (rel < 0) break;
         const int down_pos = rel + ds;
         dn_corr = dc;
@@ -238,11 +580,28 @@ cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t 
                                 int4* out_info, float4* out_f, int* frame_start, int* frame_nsym, float* cfo_out, float* phase_out,
                                 int* n_llr, int llr_per_symbol, int llr_stride, cudaStream_t st) {
     if (B == 0) return cudaSuccess;
-    const size_t smem = sizeof(ChirpWarpBuf) * (kChirpThreads / 32);
-    cudaFuncSetAttribute(chirp_detect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    chirp_detect_kernel<<<static_cast<unsigned>(B), kChirpThreads, smem, st>>>(c, samples, frame_stride, L, threshold, sym_len, out_info, out_f,
-                                                                           frame_start, frame_nsym, cfo_out, phase_out, n_llr,
-                                                                           llr_per_symbol, llr_stride);
+    // two-tier search for the 48 kHz chirp (24 000 taps) and windows of at most 3 000 coarse positions (168 000-sample buffers); PU_CHIRP_SEARCH=exact keeps the
+    // brute-force kernel (the A/B reference of tests/test_chirp_sync_gpu.py), which also serves every other geometry
+    const char* env = std::getenv("PU_CHIRP_SEARCH");   // read per call: the A/B test flips it
+    const bool force_exact = env && std::strcmp(env, "exact") == 0;
+    const int maxpos = (std::max(L - c.n, 0) + 47) / 48 + 1;
+    const bool two_tier = !force_exact && c.n == kC2N && c.nd == kC2Nd && maxpos <= kC2MaxPos;
+    cudaError_t e;
+    if (two_tier) {
+        const size_t smem = chirp2_smem_floats(maxpos) * sizeof(float);
+        static std::atomic<uint64_t> done{0};
+        if ((e = smem_optin(done, chirp_detect_kernel<true>, 232448)) != cudaSuccess) return e;
+        chirp_detect_kernel<true><<<static_cast<unsigned>(B), kC2Threads, smem, st>>>(c, samples, frame_stride, L, threshold, sym_len, out_info, out_f,
+                                                                                     frame_start, frame_nsym, cfo_out, phase_out, n_llr,
+                                                                                     llr_per_symbol, llr_stride, maxpos);
+    } else {
+        const size_t smem = sizeof(ChirpWarpBuf) * (kChirpThreads / 32);
+        static std::atomic<uint64_t> done{0};
+        if ((e = smem_optin(done, chirp_detect_kernel<false>, static_cast<int>(smem))) != cudaSuccess) return e;
+        chirp_detect_kernel<false><<<static_cast<unsigned>(B), kChirpThreads, smem, st>>>(c, samples, frame_stride, L, threshold, sym_len, out_info,
+                                                                                         out_f, frame_start, frame_nsym, cfo_out, phase_out,
+                                                                                         n_llr, llr_per_symbol, llr_stride, 0);
+    }
     return cudaGetLastError();
 }
 
@@ -272,6 +631,23 @@ void chirp_templates_host(float fs, std::vector<float>& t, ChirpDev& c) {
     c.cfo_to_samples = fs / ((f_end - f_start) / T);
     c.up_e = ue; c.dn_e = de;
     c.up_s = c.up_c = c.dn_s = c.dn_c = nullptr;
+    // ranking tables of the two-tier search: every 6th template sample times 6, then the Kaiser-windowed (beta 4.5) 4 kHz low-pass
+    const size_t nd = (n + kRankD - 1) / kRankD;
+    c.nd = static_cast<int>(nd);
+    c.dec = c.lp = nullptr;
+    t.resize(4 * n + 4 * nd + 64, 0.0f);
+    for (size_t q = 0; q < 4; ++q)
+        for (size_t j = 0; j < nd; ++j) t[4 * n + q * nd + j] = static_cast<float>(kRankD) * t[q * n + kRankD * j];
+    auto bessel_i0 = [](double v) { double s = 1.0, term = 1.0; for (int k = 1; k < 40; ++k) { term *= (v / (2.0 * k)) * (v / (2.0 * k)); s += term; } return s; };
+    const double fc = 4000.0 / static_cast<double>(fs), beta = 4.5;
+    double h[kRankNT], hs = 0.0;
+    for (int k = 0; k < kRankNT; ++k) {
+        const double m = k - kRankC, r = m / kRankC;
+        const double sinc = m == 0.0 ? 2.0 * fc : std::sin(2.0 * 3.14159265358979323846 * fc * m) / (3.14159265358979323846 * m);
+        h[k] = sinc * bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / bessel_i0(beta);
+        hs += h[k];
+    }
+    for (int k = 0; k < kRankNT; ++k) t[4 * n + 4 * nd + k] = static_cast<float>(h[k] / hs);
 }
 
 }  // namespace pu

@@ -91,13 +91,19 @@ struct ChirpDev {
     float fs, cfo_to_samples;          // sample rate; sample_rate / chirp_rate
     const float* up_s; const float* up_c; const float* dn_s; const float* dn_c;   // templates (generateTemplate, chirp_sync.hpp:706-735)
     float up_e, dn_e;                  // template energies
+    // ranking pass of the two-tier coarse search (chirp_sync.cu): the templates taken every 6th sample and scaled by 6,
+    // {up sin, up cos, down sin, down cos} x nd floats, and the 47-tap low-pass in front of the 6:1 decimation of the samples
+    const float* dec; const float* lp; int nd;
 };
 // templates of the 300 -> 2700 Hz, 500 ms chirp pair with 100 ms gaps (OFDMChirpWaveform::getChirpConfig, ofdm_chirp_waveform.cpp:39-49 ==
-// MultiCarrierDPSKConfig::getChirpConfig, multi_carrier_dpsk.hpp:78-88): host table of 4 n floats {up sin, up cos, down sin, down cos};
+// MultiCarrierDPSKConfig::getChirpConfig, multi_carrier_dpsk.hpp:78-88): host table of 4 n floats {up sin, up cos, down sin, down cos}
+// followed by the ranking tables (4 nd decimated template floats, 64 low-pass taps);
 // the caller uploads it and chirp_dev_bind points the descriptor at the device copy
 void chirp_templates_host(float fs, std::vector<float>& table, ChirpDev& c);
 inline void chirp_dev_bind(ChirpDev& c, const float* dev_table) {
     c.up_s = dev_table; c.up_c = dev_table + c.n; c.dn_s = dev_table + 2 * static_cast<size_t>(c.n); c.dn_c = dev_table + 3 * static_cast<size_t>(c.n);
+    c.dec = dev_table + 4 * static_cast<size_t>(c.n);
+    c.lp = c.dec + 4 * static_cast<size_t>(c.nd);
 }
 cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t B, size_t frame_stride, int L, float threshold, int sym_len,
                                 int4* out_info, float4* out_f, int* frame_start, int* frame_nsym, float* cfo_out, float* phase_out,

@@ -73,3 +73,47 @@ def test_chirp_receive_matches_oracle(preset, mod):
     assert (d[2].cpu().numpy() == info).all() and (d[1].cpu().numpy() == n).all()
     assert (d[0].cpu().numpy().view(np.uint32) == llr.view(np.uint32)).all()
     del ctx
+
+
+def test_two_tier_search_equals_brute_force_search():
+    """The two-tier coarse search (decimated ranking, exact evaluation of the leaders, csrc/chirp_sync.cu) against the brute-force kernel
+    that evaluates every coarse position the reference's way (PU_CHIRP_SEARCH=exact): the exact first maximum must always lie inside
+    the verified set, i.e. every output -- flags, positions, CFO bits, correlation bits, LLR bits -- is identical, over frames from
+    +20 to -25 dB, with TX CFO, noise only, silence, a chirp pair cut short and a lone up chirp."""
+    import os
+    from projectultra_b200 import capi
+    cfg = R.config_m1(R.DQPSK, R.R1_2)
+    ctx = capi.Context(0)
+    total = 57600 + 11000
+    rng = np.random.default_rng(77)
+    body = O.ofdm_tx(cfg, O.ldpc_encode(R.R1_2, np.zeros(40, np.uint8)), 0)
+    frames = []
+    for i in range(160):
+        snr = float(rng.uniform(-25.0, 20.0))
+        lead = int(rng.integers(0, total - 57600 - len(body)))
+        tx_cfo = float(rng.choice([0.0, 0.0, 7.5, -18.0, 33.0]))
+        frames.append(frame(cfg, R.R1_2, 40, snr, 9000 + i, lead, total - 57600 - len(body) - lead, tx_cfo))
+    for i in range(24):
+        frames.append(rng.normal(0, 0.05 + 0.1 * i, total).astype(np.float32))
+    frames.append(np.zeros(total, np.float32))
+    cut = frames[0].copy(); cut[40000:] = 0.0; frames.append(cut)                         # down chirp cut off
+    lone = rng.normal(0, 0.05, total).astype(np.float32); lone[1000:25000] += capi.chirp_generate()[:24000]; frames.append(lone)
+    x = np.stack(frames)
+    dem = capi.OfdmDemodulator(ctx, capi.ModemConfig.from_buffer_copy(bytes(cfg)))
+    os.environ.pop("PU_CHIRP_SEARCH", None)
+    fast = dem.chirp_receive_batch(x, llr_stride=700)
+    os.environ["PU_CHIRP_SEARCH"] = "exact"
+    try:
+        slow = dem.chirp_receive_batch(x, llr_stride=700)
+    finally:
+        os.environ.pop("PU_CHIRP_SEARCH", None)
+    llr_f, n_f, info_f, val_f = fast[:4]
+    llr_s, n_s, info_s, val_s = slow[:4]
+    assert (info_f == info_s).all(), np.flatnonzero((info_f != info_s).any(axis=1))
+    assert (n_f == n_s).all()
+    assert (np.asarray(val_f).view(np.uint32) == np.asarray(val_s).view(np.uint32)).all()
+    assert (llr_f.view(np.uint32) == llr_s.view(np.uint32)).all()
+    found = int((info_f[:, 0] != 0).sum())
+    print("two-tier == brute force on %d frames, %d with both chirps found" % (len(x), found))
+    assert 60 <= found < len(x) - 10
+    del ctx

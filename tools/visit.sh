@@ -50,6 +50,8 @@ benchN) N=${NGPU:-8}; for n in ${BENCH_NS:-4 8}; do [ $n -le $N ] && python -m t
 frames) ( time python -m pytest tests/test_frame_gpu.py -q -x ) > $OUT/pytest_frames.log 2>&1; tail -25 $OUT/pytest_frames.log;;
 fastgen) ( time python -m pytest tests/test_ofdm_fast_gpu.py -q -s -k "general or falls" ) > $OUT/pytest_fastgen.log 2>&1; grep -E "^case|passed|failed|Error|assert" $OUT/pytest_fastgen.log | cut -c1-400 | tail -30
   { for m in m3 m1qam16; do python tools/ofdm_quick_bench.py 4096 $m; QB_PRECISION=fast python tools/ofdm_quick_bench.py 4096 $m; done; QB_CHANNEL=good QB_PRECISION=fast python tools/ofdm_quick_bench.py 4096 m3; } > $OUT/quick_fastgen.txt 2>&1; cat $OUT/quick_fastgen.txt;;
+chirp) ( time python -m pytest tests/test_chirp_sync_gpu.py tests/test_psk_gpu.py tests/test_dropin_cpp_gpu.py -q -s -x ) > $OUT/pytest_chirp.log 2>&1; grep -E "two-tier|passed|failed|Error|assert" $OUT/pytest_chirp.log | cut -c1-300 | tail -12
+  { python tools/chirp_quick_bench.py 2048; python tools/chirp_quick_bench.py 2048 mcdpsk; PU_CHIRP_SEARCH=exact python tools/chirp_quick_bench.py 1024; } > $OUT/quick_chirp.txt 2>&1; grep -v "^ *$" $OUT/quick_chirp.txt | cut -c1-220;;
 ncu4)
   for m in m3 m1qam16; do QB_PRECISION=fast ncu --set full --clock-control none --import-source on -k regex:ofdm_presynced -s 3 -c 1 -f -o $OUT/prof_fast_$m python tools/ofdm_quick_bench.py 4096 $m > $OUT/ncu_fast_$m.log 2>&1; done;;
 *) echo "unknown: $w";;
