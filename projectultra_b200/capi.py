@@ -238,6 +238,13 @@ class LdpcDecoder:
         return out[:n.value].copy(), bool(ok.value), it.value
 
 
+def chirp_search_stats():
+    """(searches, exact verification rounds) of the two-tier chirp search on the current device since the last call."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    check(lib().pu_chirp_search_stats(C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
+
+
 def chirp_generate(sample_rate=48000.0, tx_cfo_hz=0.0):
     """ChirpSync::generate (host): [up chirp][gap][down chirp][gap]."""
     n = C.c_size_t(0)

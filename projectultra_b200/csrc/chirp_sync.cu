@@ -185,14 +185,13 @@ __device__ int chirp_detect_template(ChirpShared& S, ChirpWarpBuf* WB, const flo
 //           sum_i x[p+i] t[i] ~ 6 sum_j xf[p+6j] t[6j] -- and every coarse position (48 samples = 8 decimated ones apart) gets a
 //           4 000-tap FMA correlation from shared memory, in any summation order; energies come from 48-sample partial sums.
 //           Measured against the ordered sums: rms error 1-2 % of the correlation floor of a noise-only window.
-//   tier 2  the 32 best-ranked positions are evaluated exactly (lane = position; the three sums are three independent chains and
-//           run in three warps), the result is the first maximum among them, and the search ends when every unverified position
+//   tier 2  the 32 best-ranked positions are evaluated exactly (lane = position, its three sums three independent chains), the result is the first maximum among them, and the search ends when every unverified position
 //           is out of reach:  estimate + 4 x (largest |exact - estimate| seen) < best exact value.  Otherwise the next 32 are
 //           verified, down to all of them -- the result is then the brute-force one by construction.
-// The fine search (+-48 positions, parabolic neighbours included) stays exact, as 12 concurrent chains over one linear tile.
+// The fine search (+-48 positions, parabolic neighbours included) stays exact: 99 positions in four warps over one linear tile.
 // tests/test_chirp_sync_gpu.py runs both forms on the same frames (PU_CHIRP_SEARCH=exact selects the brute-force kernel).
 constexpr int kRankD = 6, kRankNT = 47, kRankC = 23;   // decimation, low-pass taps, centre tap
-constexpr int kC2Threads = 384, kC2Warps = kC2Threads / 32;
+constexpr int kC2Threads = 256, kC2Warps = kC2Threads / 32;
 constexpr int kC2N = 24000, kC2Nd = kC2N / kRankD;     // the 48 kHz chirp: 24 000 taps, 4 000 decimated
 constexpr int kC2MaxPos = 3000;                         // coarse positions per window the shared-memory budget of one SM allows
 constexpr int kC2TileIn = kC2Threads * kRankD + kRankNT - 1;
@@ -200,7 +199,7 @@ constexpr int kC2Row = 65;                              // verify tile: 64 taps 
 // Shared memory of one frame, carved from the dynamic allocation for the window's coarse-position budget `maxpos` (host: chirp2_smem_bytes;
 // 65 KB for 66 000-sample buffers, 84 KB for 84 000: two frames per SM up to ~110 000 samples, one beyond).
 struct Chirp2Smem {
-    float* xd;                        // tier 1: decimated window, whole tiles.  tier 2: rows[2][32][kC2Row].  fine: lin[2][256]
+    float* xd;                        // tier 1: decimated window, whole tiles.  tier 2: rows[3][32][kC2Row].  fine: lin[3][256]
     float* tile;                      // low-pass input tile (tier 1b only); the same storage then holds acc, a, order
     float (*acc)[2];
     float* a;                         // estimate of the normalised correlation
@@ -238,6 +237,8 @@ __device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos) {
     S.best_c = p; S.best_p = reinterpret_cast<int*>(p + 1); S.go = reinterpret_cast<int*>(p + 2);
     return S;
 }
+
+__device__ unsigned long long g_chirp2_stats[2];          // {searches, verification rounds}: pu_chirp_search_stats
 
 // the reference's closing arithmetic (:655-661)
 __device__ __forceinline__ float chirp_norm(float ci, float cq, float se, float te) {
@@ -308,13 +309,14 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
         }
     }
     __syncthreads();
-    // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one third of the taps); lane l starts 4 l taps
-    // into its third and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
+    // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one half of the taps); lane l starts 4 l taps
+    // into its half and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
     {
         const int nblk = (n_pos + 7) / 8;
-        if (tid < 3 * nblk) {
-            const int sg = tid / nblk, pb = tid - sg * nblk;
-            const int j0 = sg * 1336, len = sg == 2 ? kC2Nd - 2672 : 1336;
+        for (int item = tid; item < 2 * nblk; item += kC2Threads) {
+            const int sg = item / nblk, pb = item - sg * nblk;
+            constexpr int len = kC2Nd / 2;
+            const int j0 = sg * len;
             float ac[8], as[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) { ac[r] = 0.0f; as[r] = 0.0f; }
@@ -359,6 +361,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     __syncthreads();
     // ---------------- tier 2: exact evaluation of the leaders, 32 per round
     float (*rows)[32][kC2Row] = reinterpret_cast<float (*)[32][kC2Row]>(S.xd);
+    float (*tpl)[2][64] = reinterpret_cast<float (*)[2][64]>(S.xd + 3 * 32 * kC2Row);   // [3][cos, sin][64], 16-byte aligned
     float errmax = 0.0f;                                     // thread 0
     for (int nv = 0; nv < n_pos; nv += 32) {
         const int cnt = min(32, n_pos - nv);
@@ -371,36 +374,35 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                 cp_async4(dst + 4 * lane, src + lane);
                 cp_async4(dst + 4 * (lane + 32), src + lane + 32);
             }
+            if (warp == kC2Warps - 1)                         // the template tile travels with the samples (192 KB per chirp: L2, not L1)
+                cp_async16(smem_u32(&tpl[buf][lane >> 4][4 * (lane & 15)]), (lane < 16 ? tc : ts) + 64 * tile + 4 * (lane & 15));
             cp_async_commit();
         };
-        float sum = 0.0f;
-        const float* tpl = warp == 0 ? tc : ts;
+        // The three ordered sums of a position stay in one lane (one shared load feeds all three; they are independent chains, so the
+        // warp issues back to back); warp 0 sums, every warp stages.  Three buffers: tile t + 2 travels while tile t is summed (a group
+        // is committed every iteration, empty ones past the end, so "all groups but the newest" always means "tile t has landed").
+        float ci = 0.0f, cq = 0.0f, se = 0.0f;
         stage(0, 0);
+        stage(1, 1);
         for (int tile = 0; tile < n / 64; ++tile) {
-            cp_async_wait_all();
+            cp_async_wait_but_one();
             __syncthreads();
-            if (tile + 1 < n / 64) stage(tile + 1, (tile + 1) & 1);
-            if (warp < 3) {
-                const float* row = rows[tile & 1][lane];
-                if (warp < 2) {
+            if (tile + 2 < n / 64) stage(tile + 2, (tile + 2) % 3); else cp_async_commit();
+            if (warp == 0) {
+                const float* row = rows[tile % 3][lane];
 #pragma unroll 4
-                    for (int t = 0; t < 64; t += 4) {
-                        const float4 tv = __ldg(reinterpret_cast<const float4*>(tpl + 64 * tile + t));
-                        sum = __fadd_rn(sum, __fmul_rn(row[t], tv.x));
-                        sum = __fadd_rn(sum, __fmul_rn(row[t + 1], tv.y));
-                        sum = __fadd_rn(sum, __fmul_rn(row[t + 2], tv.z));
-                        sum = __fadd_rn(sum, __fmul_rn(row[t + 3], tv.w));
-                    }
-                } else {
-#pragma unroll 16
-                    for (int t = 0; t < 64; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
+                for (int t = 0; t < 64; t += 4) {
+                    const float4 vc = *reinterpret_cast<const float4*>(&tpl[tile % 3][0][t]);
+                    const float4 vs = *reinterpret_cast<const float4*>(&tpl[tile % 3][1][t]);
+                    const float s0 = row[t], s1 = row[t + 1], s2 = row[t + 2], s3 = row[t + 3];
+                    ci = __fadd_rn(ci, __fmul_rn(s0, vc.x)); cq = __fadd_rn(cq, __fmul_rn(s0, vs.x)); se = __fadd_rn(se, __fmul_rn(s0, s0));
+                    ci = __fadd_rn(ci, __fmul_rn(s1, vc.y)); cq = __fadd_rn(cq, __fmul_rn(s1, vs.y)); se = __fadd_rn(se, __fmul_rn(s1, s1));
+                    ci = __fadd_rn(ci, __fmul_rn(s2, vc.z)); cq = __fadd_rn(cq, __fmul_rn(s2, vs.z)); se = __fadd_rn(se, __fmul_rn(s2, s2));
+                    ci = __fadd_rn(ci, __fmul_rn(s3, vc.w)); cq = __fadd_rn(cq, __fmul_rn(s3, vs.w)); se = __fadd_rn(se, __fmul_rn(s3, s3));
                 }
             }
         }
-        if (warp == 1) S.exq[lane] = sum;
-        if (warp == 2) S.exe[lane] = sum;
-        __syncthreads();
-        if (warp == 0) S.ex[lane] = chirp_norm(sum, S.exq[lane], S.exe[lane], te);
+        if (warp == 0) S.ex[lane] = chirp_norm(ci, cq, se, te);
         __syncthreads();
         if (tid == 0) {
             float bc = (*S.best_c);
@@ -421,7 +423,10 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
             (*S.go) = go;
         }
         __syncthreads();
-        if (!(*S.go)) break;
+        if (!(*S.go)) {
+            if (tid == 0) { atomicAdd(&g_chirp2_stats[0], 1ull); atomicAdd(&g_chirp2_stats[1], static_cast<unsigned long long>(nv / 32 + 1)); }
+            break;
+        }
     }
     float best = (*S.best_c);
     int best_pos = (*S.best_p);
@@ -429,47 +434,45 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     *corr_out = best;
     if (best_pos < 0 || best < __fmul_rn(threshold, 0.3f)) return -1;
     // ---------------- fine search (:600-612) and the parabola's neighbours (:615-625): every position of [fine_start - 1, fine_end + 1]
-    // exactly, 32 positions x {ci, cq, se} per warp triple over one linear tile (lane l reads lin[t + l]: consecutive banks)
+    // exactly, 32 positions per warp (warps 0..3) over one linear tile (lane l reads lin[t + l]: consecutive banks)
     const int fine_start = max(0, best_pos - 48), fine_end = min(search_len, best_pos + 48);
     const int q0 = max(0, fine_start - 1), q1 = min(search_len, fine_end + 1);
     {
         float (*lin)[256] = reinterpret_cast<float (*)[256]>(S.xd);
+        float (*ftpl)[2][128] = reinterpret_cast<float (*)[2][128]>(S.xd + 3 * 256);   // [3][cos, sin][128]
         auto stage = [&](int tile, int buf) {
-            if (tid < 256) {
+            {
                 const int wi = q0 + 128 * tile + tid;         // window index; positions past q1 read on into the frame or zeros
                 const bool ok = w0 + wi < L;
                 cp_async4_zfill(smem_u32(&lin[buf][tid]), ok ? xw + wi : x, ok);
             }
+            if (tid < 64 && 128 * tile + 4 * (tid & 31) < n)
+                cp_async16(smem_u32(&ftpl[buf][tid >> 5][4 * (tid & 31)]), (tid < 32 ? tc : ts) + 128 * tile + 4 * (tid & 31));
             cp_async_commit();
         };
-        const int grp = warp / 3, kind = warp - 3 * grp;
-        const float* tpl = kind == 0 ? tc : ts;
-        float sum = 0.0f;
+        float ci = 0.0f, cq = 0.0f, se = 0.0f;                 // warps 0..3: positions q0 + 32 warp + lane
         stage(0, 0);
+        stage(1, 1);
         for (int tile = 0; tile < (n + 127) / 128; ++tile) {
-            cp_async_wait_all();
+            cp_async_wait_but_one();
             __syncthreads();
-            if (128 * (tile + 1) < n) stage(tile + 1, (tile + 1) & 1);
-            const float* row = lin[tile & 1] + 32 * grp + lane;
-            const int tn = min(128, n - 128 * tile);
-            if (kind < 2) {
+            if (128 * (tile + 2) < n) stage(tile + 2, (tile + 2) % 3); else cp_async_commit();
+            if (warp < 4) {
+                const float* row = lin[tile % 3] + 32 * warp + lane;
+                const int tn = min(128, n - 128 * tile);
 #pragma unroll 4
                 for (int t = 0; t < tn; t += 4) {
-                    const float4 tv = __ldg(reinterpret_cast<const float4*>(tpl + 128 * tile + t));
-                    sum = __fadd_rn(sum, __fmul_rn(row[t], tv.x));
-                    sum = __fadd_rn(sum, __fmul_rn(row[t + 1], tv.y));
-                    sum = __fadd_rn(sum, __fmul_rn(row[t + 2], tv.z));
-                    sum = __fadd_rn(sum, __fmul_rn(row[t + 3], tv.w));
+                    const float4 vc = *reinterpret_cast<const float4*>(&ftpl[tile % 3][0][t]);
+                    const float4 vs = *reinterpret_cast<const float4*>(&ftpl[tile % 3][1][t]);
+                    const float s0 = row[t], s1 = row[t + 1], s2 = row[t + 2], s3 = row[t + 3];
+                    ci = __fadd_rn(ci, __fmul_rn(s0, vc.x)); cq = __fadd_rn(cq, __fmul_rn(s0, vs.x)); se = __fadd_rn(se, __fmul_rn(s0, s0));
+                    ci = __fadd_rn(ci, __fmul_rn(s1, vc.y)); cq = __fadd_rn(cq, __fmul_rn(s1, vs.y)); se = __fadd_rn(se, __fmul_rn(s1, s1));
+                    ci = __fadd_rn(ci, __fmul_rn(s2, vc.z)); cq = __fadd_rn(cq, __fmul_rn(s2, vs.z)); se = __fadd_rn(se, __fmul_rn(s2, s2));
+                    ci = __fadd_rn(ci, __fmul_rn(s3, vc.w)); cq = __fadd_rn(cq, __fmul_rn(s3, vs.w)); se = __fadd_rn(se, __fmul_rn(s3, s3));
                 }
-            } else {
-#pragma unroll 16
-                for (int t = 0; t < tn; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
             }
         }
-        if (kind == 1) S.exq[32 * grp + lane] = sum;
-        if (kind == 2) S.exe[32 * grp + lane] = sum;
-        __syncthreads();
-        if (kind == 0) S.ex[32 * grp + lane] = chirp_norm(sum, S.exq[32 * grp + lane], S.exe[32 * grp + lane], te);
+        if (warp < 4) S.ex[32 * warp + lane] = chirp_norm(ci, cq, se, te);
         __syncthreads();
     }
     if (tid == 0) {
@@ -500,7 +503,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
 // out_info[b] = {success, up_chirp_start, down_chirp_start, start_sample (training start) or -1}; out_f[b] = {cfo_hz, up corr, down corr,
 // initial rotator phase}.  frame_start / frame_nsym (optional) = the window handed to the presynced kernel (0 symbols when not found).
 template <bool TWO_TIER>
-__global__ void __launch_bounds__(TWO_TIER ? kC2Threads : kChirpThreads, TWO_TIER ? 2 : 1) chirp_detect_kernel(ChirpDev c, const float* __restrict__ samples, size_t frame_stride, int L,
+__global__ void __launch_bounds__(TWO_TIER ? kC2Threads : kChirpThreads, TWO_TIER ? 3 : 1) chirp_detect_kernel(ChirpDev c, const float* __restrict__ samples, size_t frame_stride, int L,
                                                                      float threshold, int sym_len, int4* __restrict__ out_info,
                                                                      float4* __restrict__ out_f, int* __restrict__ frame_start,
                                                                      int* __restrict__ frame_nsym, float* __restrict__ cfo_out,
@@ -603,6 +606,14 @@ cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t 
                                                                                          n_llr, llr_per_symbol, llr_stride, 0);
     }
     return cudaGetLastError();
+}
+
+cudaError_t chirp_search_stats(unsigned long long* out) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemcpyFromSymbol(out, g_chirp2_stats, sizeof(g_chirp2_stats))) != cudaSuccess) return e;
+    const unsigned long long zero[2] = {0, 0};
+    return cudaMemcpyToSymbol(g_chirp2_stats, zero, sizeof(zero));
 }
 
 void chirp_templates_host(float fs, std::vector<float>& t, ChirpDev& c) {

@@ -1482,6 +1482,14 @@ pu_status pu_ofdm_chirp_receive_batch(pu_ofdm* h, const float* samples, size_t B
     return PU_OK;
 }
 
+pu_status pu_chirp_search_stats(uint64_t* searches, uint64_t* rounds) {
+    unsigned long long v[2] = {0, 0};
+    PU_CUDA_TRY(pu::chirp_search_stats(v));
+    if (searches) *searches = v[0];
+    if (rounds) *rounds = v[1];
+    return PU_OK;
+}
+
 pu_status pu_chirp_generate(float sample_rate, float tx_cfo_hz, float* out, size_t out_cap, size_t* out_len) {
     PU_REQUIRE(out_len && sample_rate > 0, "pu_chirp_generate: bad argument");
     // sync::ChirpSync::generate (src/sync/chirp_sync.hpp:58-108), host side: [up chirp][gap][down chirp][gap]

@@ -52,6 +52,8 @@ fastgen) ( time python -m pytest tests/test_ofdm_fast_gpu.py -q -s -k "general o
   { for m in m3 m1qam16; do python tools/ofdm_quick_bench.py 4096 $m; QB_PRECISION=fast python tools/ofdm_quick_bench.py 4096 $m; done; QB_CHANNEL=good QB_PRECISION=fast python tools/ofdm_quick_bench.py 4096 m3; } > $OUT/quick_fastgen.txt 2>&1; cat $OUT/quick_fastgen.txt;;
 chirp) ( time python -m pytest tests/test_chirp_sync_gpu.py tests/test_psk_gpu.py tests/test_dropin_cpp_gpu.py -q -s -x ) > $OUT/pytest_chirp.log 2>&1; grep -E "two-tier|passed|failed|Error|assert" $OUT/pytest_chirp.log | cut -c1-300 | tail -12
   { python tools/chirp_quick_bench.py 2048; python tools/chirp_quick_bench.py 2048 mcdpsk; PU_CHIRP_SEARCH=exact python tools/chirp_quick_bench.py 1024; } > $OUT/quick_chirp.txt 2>&1; grep -v "^ *$" $OUT/quick_chirp.txt | cut -c1-220;;
+ncu5)
+  ncu --set full --clock-control none --import-source on -k regex:chirp_detect -c 1 -f -o $OUT/prof_chirp2 python tools/chirp_quick_bench.py 1024 > $OUT/ncu_chirp2.log 2>&1;;
 ncu4)
   for m in m3 m1qam16; do QB_PRECISION=fast ncu --set full --clock-control none --import-source on -k regex:ofdm_presynced -s 3 -c 1 -f -o $OUT/prof_fast_$m python tools/ofdm_quick_bench.py 4096 $m > $OUT/ncu_fast_$m.log 2>&1; done;;
 *) echo "unknown: $w";;
