@@ -777,6 +777,7 @@ void pu_mcdpsk_destroy(pu_mcdpsk* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     h->corr.release();
+    h->corrected.release();
     delete h;
 }
 
@@ -835,7 +836,7 @@ static pu_status mcdpsk_got_chirp(pu_mcdpsk* h, const float* d_x, size_t B, size
                                   std::vector<float>& after_h, cudaStream_t st) {
     pu_ctx* ctx = h->ctx;
     const size_t pre = static_cast<size_t>(h->cfg.training_symbols + 1) * h->cfg.samples_per_symbol;
-    pu::PskDevMem dy, dres;
+    pu::PskDevMem dres;
     pu_status s;
     std::vector<float> res(B, 0.0f), cfo_h(B);
     size_t Lmax = 0;                                     // longest per-frame span
@@ -845,7 +846,8 @@ static pu_status mcdpsk_got_chirp(pu_mcdpsk* h, const float* d_x, size_t B, size
         Lmax = std::max(Lmax, Lb[b]);
     }
     if (Lmax > pre) {   // processGotChirp needs data behind the preamble; otherwise it keeps waiting (no soft bits)
-        PU_CUDA_TRY(cudaMalloc(&dy.p, B * L * sizeof(float)));
+        if ((s = h->corrected.reserve(B * L * sizeof(float))) != PU_OK) return s;   // 0.7 GB at 2 048 x 84 200: not per call
+        float* dy = static_cast<float*>(h->corrected.ptr);
         if ((s = dres.upload(res.data(), B)) != PU_OK) return s;
         pu::HilbertTaps taps;
         const int M = (pu::kHilbertTaps - 1) / 2;
@@ -859,10 +861,10 @@ static pu_status mcdpsk_got_chirp(pu_mcdpsk* h, const float* d_x, size_t B, size
         }
         (void)cudaGetLastError();
         pu::mcdpsk_cfo_correct_kernel<<<static_cast<unsigned>(B), pu::kCfoThreads, 0, st>>>(taps, d_x, L, static_cast<int>(L), h->cfg.sample_rate,
-                                                                                            d_cfo, static_cast<float*>(dy.p), d_start);
+                                                                                            d_cfo, dy, d_start);
         ctx->launches.fetch_add(1);
         PU_CUDA_TRY(cudaGetLastError());
-        if ((s = mcdpsk_launch(h, static_cast<const float*>(dy.p), B, L, d_llr, llr_stride, static_cast<float*>(dres.p), st)) != PU_OK) return s;
+        if ((s = mcdpsk_launch(h, dy, B, L, d_llr, llr_stride, static_cast<float*>(dres.p), st)) != PU_OK) return s;
         PU_CUDA_TRY(cudaStreamSynchronize(st));
         PU_CUDA_TRY(cudaMemcpy(res.data(), dres.p, B * sizeof(float), cudaMemcpyDeviceToHost));
     }

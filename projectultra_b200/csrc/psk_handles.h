@@ -45,6 +45,7 @@ struct pu_mcdpsk {
     pu_mcdpsk_config cfg{};
     pu::PskDevMem d_mixer, d_expected;
     pu::Buffer corr;
+    pu::Buffer corrected;      // CFO-corrected copy of the batch (mcdpsk_got_chirp): kept between calls, grows on demand
     pu::PskDevMem d_chirp;     // dual-chirp templates (built on first use)
     pu::ChirpDev chirp{};
     bool chirp_ready = false;

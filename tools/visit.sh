@@ -54,6 +54,9 @@ chirp) ( time python -m pytest tests/test_chirp_sync_gpu.py tests/test_psk_gpu.p
   { python tools/chirp_quick_bench.py 2048; python tools/chirp_quick_bench.py 2048 mcdpsk; PU_CHIRP_SEARCH=exact python tools/chirp_quick_bench.py 1024; } > $OUT/quick_chirp.txt 2>&1; grep -v "^ *$" $OUT/quick_chirp.txt | cut -c1-220;;
 ncu5)
   ncu --set full --clock-control none --import-source on -k regex:chirp_detect -c 1 -f -o $OUT/prof_chirp2 python tools/chirp_quick_bench.py 1024 > $OUT/ncu_chirp2.log 2>&1;;
+ncu6)
+  ncu --set full --clock-control none --import-source on -k regex:dpsk_find_preamble -c 1 -f -o $OUT/prof_bk python tools/dpsk_acquire_quick_bench.py 1024 > $OUT/ncu_bk.log 2>&1; tail -5 $OUT/ncu_bk.log
+  ncu --set full --clock-control none --import-source on -k regex:ofdm_acquire_kernel -c 1 -f -o $OUT/prof_acq python tools/acquire_quick_bench.py 1024 > $OUT/ncu_acq.log 2>&1; tail -5 $OUT/ncu_acq.log;;
 ncu4)
   for m in m3 m1qam16; do QB_PRECISION=fast ncu --set full --clock-control none --import-source on -k regex:ofdm_presynced -s 3 -c 1 -f -o $OUT/prof_fast_$m python tools/ofdm_quick_bench.py 4096 $m > $OUT/ncu_fast_$m.log 2>&1; done;;
 *) echo "unknown: $w";;
