@@ -203,3 +203,20 @@ def test_training_cfo_path_against_compiled_reference():
         a1, _, f1 = R.ofdm_presynced(cfg, rx, 1, 0)
         b1, _, g1 = O.ofdm_presynced(cfg, rx, 1, 0)
         assert (a1.view(np.uint32) == b1.view(np.uint32)).all() and f1 == g1
+
+
+def test_float_only_two_pi_wrap_equals_the_double_wrap():
+    """The CFO rotator's phase wrap (channel_equalizer.cpp:47-50: `phase -= 2 * M_PI` on a float, i.e. float((double)ph - 2 pi)) as the
+    warp kernel evaluates it without FP64 (csrc/ofdm_demod.cu: rot_step): fl(fl(ph -+ two_hi) -+ two_lo).  Every float of [pi, 4.2),
+    both signs -- beyond that the kernel takes the double path."""
+    pi_hi = np.float32(3.14159274101257324)
+    bits = np.arange(pi_hi.view(np.uint32), np.float32(4.2).view(np.uint32), dtype=np.uint32)
+    ph = bits.view(np.float32)
+    assert len(ph) == 4019851
+    two_hi, two_lo = np.float32(6.2831854820251465), np.float32(-1.7484555e-7)
+    ref = (ph.astype(np.float64) - 2.0 * np.pi).astype(np.float32)
+    got = (ph - two_hi) - two_lo
+    assert (ref.view(np.uint32) == got.view(np.uint32)).all()
+    ref = ((-ph).astype(np.float64) + 2.0 * np.pi).astype(np.float32)
+    got = ((-ph) + two_hi) + two_lo
+    assert (ref.view(np.uint32) == got.view(np.uint32)).all()
