@@ -351,21 +351,23 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                 unsigned b0 = __float_as_uint(ph), delta = __float_as_uint(rot_step(ph)) - b0;
                 int i0 = 0, wbase = 0;
                 const bool keep = !skip_fft;
-                auto mix = [&](int i, float th) {                 // sample i of the symbol, rotator phase th
+                // sample i of the symbol rotated by phase th -> out; false outside the FFT window.  Reads and writes of the warp are
+                // separated by __syncwarp (the rotated samples overwrite staged samples other lanes have read, see above).
+                auto mix = [&](int i, float th, float2& out) {
                     const int k = i - d.cp;
-                    if (keep && k >= 0 && k < NFFT) {
-                        const float xv = xsm[k];
-                        const float2 o = __ldg(&nco[i]);
-                        float sn, cs;
-                        const float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));   // samples[i] * conj(osc) (:36)
-                        if constexpr (FAST) {        // the reference's phase, MUFU sin/cos (2^-21 absolute), FMA mix
-                            __sincosf(th, &sn, &cs);
-                            zbuf[k] = make_float2(__fmaf_rn(z.x, cs, -__fmul_rn(z.y, sn)), __fmaf_rn(z.x, sn, __fmul_rn(z.y, cs)));
-                        } else {
-                            nl::sincosf_ref(th, &sn, &cs);
-                            zbuf[k] = cmul(z, make_float2(cs, sn));                               // mixed *= correction (:42)
-                        }
+                    if (!(keep && k >= 0 && k < NFFT)) return false;
+                    const float xv = xsm[k];
+                    const float2 o = __ldg(&nco[i]);
+                    float sn, cs;
+                    const float2 z = make_float2(__fmul_rn(o.x, xv), __fmul_rn(-o.y, xv));       // samples[i] * conj(osc) (:36)
+                    if constexpr (FAST) {            // the reference's phase, MUFU sin/cos (2^-21 absolute), FMA mix
+                        __sincosf(th, &sn, &cs);
+                        out = make_float2(__fmaf_rn(z.x, cs, -__fmul_rn(z.y, sn)), __fmaf_rn(z.x, sn, __fmul_rn(z.y, cs)));
+                    } else {
+                        nl::sincosf_ref(th, &sn, &cs);
+                        out = cmul(z, make_float2(cs, sn));                                       // mixed *= correction (:42)
                     }
+                    return true;
                 };
                 auto window = [&](int len) {                      // the next len (<= 32) samples, link by link
                     float mine = 0.0f;
@@ -387,7 +389,10 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                         }
                         done = last + 1;
                     }
-                    if (lane < len) mix(wbase + lane, mine);
+                    float2 r;
+                    const bool ok = lane < len && mix(wbase + lane, mine, r);
+                    __syncwarp();
+                    if (ok) zbuf[wbase + lane - d.cp] = r;
                     wbase += len;
                 };
                 const float pi_lo = 3.1415925f;                   // largest float below pi_hi: |nxt| <= pi_lo  <=>  rot_step does not wrap
@@ -403,8 +408,14 @@ __global__ void __launch_bounds__(WARPG ? 512 : NFFT / 8, 1) ofdm_presynced_kern
                         brk |= i < d.sym_len && (__float_as_uint(nxt) != cb + delta || !(fabsf(nxt) <= pi_lo));
                     }
                     if (!__any_sync(0xffffffffu, brk)) {
+                        float2 r[4];
+                        bool ok[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) mix(wbase + 32 * k + lane, cand[k]);
+                        for (int k = 0; k < 4; ++k) ok[k] = mix(wbase + 32 * k + lane, cand[k], r[k]);
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (ok[k]) zbuf[wbase + 32 * k + lane - d.cp] = r[k];
                         wbase += 128;
                     } else {
                         for (int k = 0; k < 4 && wbase < d.sym_len; ++k) window(min(32, d.sym_len - wbase));
