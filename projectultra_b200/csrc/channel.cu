@@ -295,16 +295,30 @@ pu_status pu_channel_noise_std_batch(pu_ctx* ctx, const float* tx, size_t tx_str
     return PU_OK;
 }
 
-float pu_channel_noise_std(const float* tx, size_t L, float snr_db, int convention) {
-    if (!tx || L == 0) return 0.0f;
+}  // extern "C"
+
+namespace pu {
+// the ordered fp32 power sum of pu_channel_noise_std, separately: a sweep needs it once per waveform, not once per SNR point
+float channel_power_sum(const float* tx, size_t L) {
     float acc = 0.0f;
     for (size_t i = 0; i < L; ++i) acc += tx[i] * tx[i];
+    return acc;
+}
+float channel_noise_std_from_sum(float acc, size_t L, float snr_db, int convention) {
     if (convention == 0) {          // WattersonChannel::process, hf_channel.hpp:110-119
         const float rms = std::sqrt(acc / L);
         return rms * std::pow(10.0f, -snr_db / 20.0f);
     }
     const float sp = acc / L;       // tools/test_mode_snr.cpp:58-61 (mean frame power, AWGN tools)
     return std::sqrt(sp / std::pow(10.0f, snr_db / 10.0f));
+}
+}  // namespace pu
+
+extern "C" {
+
+float pu_channel_noise_std(const float* tx, size_t L, float snr_db, int convention) {
+    if (!tx || L == 0) return 0.0f;
+    return pu::channel_noise_std_from_sum(pu::channel_power_sum(tx, L), L, snr_db, convention);
 }
 
 pu_status pu_channel_apply_cfo_batch(pu_ctx* ctx, float* samples, size_t B, size_t L, size_t stride, const float* cfo_hz, uint32_t sample_rate,

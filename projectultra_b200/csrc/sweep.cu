@@ -59,8 +59,9 @@ bool make_plan(const pu_sweep_desc* d, SweepPlan* p) {
 }
 
 // Built-in relative cost of one frame (GPU time, arbitrary unit), from the measured throughputs of DESIGN.md §4: the 512-FFT
-// differential kernels run ~100 M frames/s, the general presynced kernel 9-20 M, Schmidl-Cox acquisition 0.37 M, Barker acquisition and
-// the dual-chirp search tens of thousands; LDPC is added per SNR point by unit_cost().
+// differential kernels run ~100 M frames/s, the general presynced kernel 10-30 M, Schmidl-Cox acquisition 0.3 M, Barker acquisition
+// 0.18 M (139 392-sample frames), the two-tier dual-chirp search 0.19 M (OFDM_CHIRP) / 0.10 M (MC-DPSK, 84 200 samples); LDPC is
+// added per SNR point by unit_cost().
 double mode_cost(const pu_sweep_mode& m) {
     if (m.cost > 0) return m.cost;
     switch (m.waveform) {
@@ -69,11 +70,11 @@ double mode_cost(const pu_sweep_mode& m) {
             return (diff && !m.ofdm.use_pilots && m.ofdm.fft_size == 512) ? 1.0 : (diff && !m.ofdm.use_pilots) ? 2.0 : 8.0;
         }
         case PU_WF_OFDM_SC: return 250.0;
-        case PU_WF_OFDM_CHIRP: return 3000.0;
+        case PU_WF_OFDM_CHIRP: return 600.0;
         case PU_WF_DPSK: return 30.0;
-        case PU_WF_DPSK_ACQ: return 2500.0;
+        case PU_WF_DPSK_ACQ: return 700.0;
         case PU_WF_MCDPSK: return 10.0;
-        default: return 4500.0;     // PU_WF_MCDPSK_CHIRP
+        default: return 1100.0;     // PU_WF_MCDPSK_CHIRP
     }
 }
 // LDPC share: ~50 iterations at the bottom of the grid, ~2 at the top; in units of the demodulator cost of the cheapest mode
@@ -132,6 +133,7 @@ struct ModeEngine {
     pu_dpsk* dpsk = nullptr;
     pu_mcdpsk* mcd = nullptr;
     pu_ldpc* ldpc = nullptr;
+    bool own_ldpc = true;                // false: the decoder of this code rate is shared by the run (pu_linksim_run keeps one per rate)
     pu_channel_config ch{};
     size_t L = 0, kb = 0;
     uint32_t pool = 0;
@@ -143,17 +145,23 @@ struct ModeEngine {
         if (ofdm) pu_ofdm_destroy(ofdm);
         if (dpsk) pu_dpsk_destroy(dpsk);
         if (mcd) pu_mcdpsk_destroy(mcd);
-        if (ldpc) pu_ldpc_destroy(ldpc);
+        if (ldpc && own_ldpc) pu_ldpc_destroy(ldpc);
         d_tx.release(); d_payload.release();
     }
 
-    pu_status build(pu_ctx* c, const pu_sweep_mode* m, uint32_t mode_index, const SweepPlan& p, cudaStream_t st) {
+    pu_status build(pu_ctx* c, const pu_sweep_mode* m, uint32_t mode_index, const SweepPlan& p, cudaStream_t st, pu_ldpc* shared_ldpc = nullptr) {
         ctx = c; md = m; pool = p.pool;
         pu_status s;
+        const bool trace = std::getenv("PU_SWEEP_TRACE") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        const auto t0 = now();
         if ((s = pu_channel_preset(static_cast<int>(m->channel), &ch)) != PU_OK) return s;
         // AWGN tools define SNR on mean frame power, WattersonChannel on input rms (same number, different rounding)
         convention = m->channel == PU_CH_AWGN ? 1 : 0;
-        if ((s = pu_ldpc_create(c, static_cast<int>(m->code_rate), static_cast<int>(p.max_iter), &ldpc)) != PU_OK) return s;
+        if (shared_ldpc) { ldpc = shared_ldpc; own_ldpc = false; }
+        else if ((s = pu_ldpc_create(c, static_cast<int>(m->code_rate), static_cast<int>(p.max_iter), &ldpc)) != PU_OK) return s;
+        const auto t_ldpc = now();
         kb = static_cast<size_t>((pu_ldpc_info_bits(ldpc) + 7) / 8);
         PU_REQUIRE(m->payload_bytes >= 1 && m->payload_bytes <= kb, "pu_linksim_run: payload_bytes exceeds the code's information bytes");
         const bool is_ofdm = m->waveform <= PU_WF_OFDM_CHIRP, is_dpsk = m->waveform == PU_WF_DPSK || m->waveform == PU_WF_DPSK_ACQ;
@@ -165,6 +173,7 @@ struct ModeEngine {
         } else {
             if ((s = pu_mcdpsk_create(c, &m->mcdpsk, &mcd)) != PU_OK) return s;
         }
+        const auto t1 = now();
         // TX pool on the host (the reference's modulators run per trial on the CPU too): payload -> LDPC encode -> modulate [-> chirp in front]
         std::vector<float> chirp;
         if (m->waveform == PU_WF_OFDM_CHIRP || m->waveform == PU_WF_MCDPSK_CHIRP) {
@@ -201,12 +210,15 @@ struct ModeEngine {
             }
             waves[i] = std::move(w);
         }
+        const auto t2 = now();
         L = waves[0].size();
         for (const auto& w : waves) PU_REQUIRE(w.size() == L, "pu_linksim_run: TX waveforms of one mode differ in length");
         noise_std.resize(static_cast<size_t>(m->n_snr) * pool);
-        for (uint32_t si = 0; si < m->n_snr; ++si)
-            for (uint32_t i = 0; i < pool; ++i)
-                noise_std[static_cast<size_t>(si) * pool + i] = pu_channel_noise_std(waves[i].data(), L, m->snr_first_db + si * m->snr_step_db, convention);
+        for (uint32_t i = 0; i < pool; ++i) {             // pu_channel_noise_std with the power sum taken once per waveform, not per SNR point
+            const float acc = channel_power_sum(waves[i].data(), L);
+            for (uint32_t si = 0; si < m->n_snr; ++si)
+                noise_std[static_cast<size_t>(si) * pool + i] = channel_noise_std_from_sum(acc, L, m->snr_first_db + si * m->snr_step_db, convention);
+        }
         if ((s = d_tx.reserve(static_cast<size_t>(pool) * L * sizeof(float))) != PU_OK) return s;
         if ((s = d_payload.reserve(payloads.size())) != PU_OK) return s;
         std::vector<float> flat(static_cast<size_t>(pool) * L);
@@ -214,6 +226,8 @@ struct ModeEngine {
         PU_CUDA_TRY(cudaMemcpyAsync(d_tx.ptr, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         PU_CUDA_TRY(cudaMemcpyAsync(d_payload.ptr, payloads.data(), payloads.size(), cudaMemcpyHostToDevice, st));
         PU_CUDA_TRY(cudaStreamSynchronize(st));       // `flat` / `payloads` are pageable and go out of scope
+        if (trace) fprintf(stderr, "[engine] mode %u: decoder %.3f s, demodulator %.3f s, TX pool %.3f s, noise levels + upload %.3f s\n", mode_index, secs(t0, t_ldpc),
+                           secs(t_ldpc, t1), secs(t1, t2), secs(t2, now()));
         return PU_OK;
     }
 
@@ -499,6 +513,7 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
 
     const auto t_begin = std::chrono::steady_clock::now();
     pu_status rs = PU_OK;
+    pu_ldpc* decoders[8] = {};
     uint64_t budget = d->max_units ? d->max_units : ~uint64_t(0);
     int k = 0;
     for (uint32_t m = 0; m < d->n_modes && rs == PU_OK && budget > 0; ++m) {
@@ -508,8 +523,14 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
         if (mine.empty()) continue;
         pu::ModeEngine eng;
         const auto t_setup = std::chrono::steady_clock::now();
-        if ((rs = eng.build(ctx, &d->modes[m], m, p, st)) != PU_OK) break;
-        stt.setup_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count();
+        const unsigned rate = d->modes[m].code_rate;      // one decoder per code rate for the whole run (its tables take longer to build than a mode's)
+        if (rate < 8 && !decoders[rate] && (rs = pu_ldpc_create(ctx, static_cast<int>(rate), static_cast<int>(p.max_iter), &decoders[rate])) != PU_OK) break;
+        if ((rs = eng.build(ctx, &d->modes[m], m, p, st, rate < 8 ? decoders[rate] : nullptr)) != PU_OK) break;
+        const double t_build = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_setup).count();
+        stt.setup_seconds += t_build;
+        if (std::getenv("PU_SWEEP_TRACE"))
+            fprintf(stderr, "[pu_linksim_run] rank %u mode %u waveform %u: engine set-up %.3f s (%zu samples per frame, pool %u)\n", d->rank, m,
+                    d->modes[m].waveform, t_build, eng.L, eng.pool);
         const size_t L = eng.L, kb = eng.kb;
         const size_t max_frames = std::max<size_t>(1, std::min<uint64_t>(p.batch_bytes / (L * sizeof(float)), (uint64_t(1) << 22)));
         const size_t cap = std::max<size_t>(max_frames, p.block);      // a unit is never split: the smallest batch is one unit
@@ -591,6 +612,7 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
         for (auto& sl : slots) { const pu_status hs = harvest(sl); if (rs == PU_OK) rs = hs; }
     }
     if (rs != PU_OK) (void)cudaStreamSynchronize(st);
+    for (pu_ldpc* h : decoders) if (h) pu_ldpc_destroy(h);
     for (auto& sl : slots) sl.busy = false;
     stt.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     cleanup();

@@ -245,10 +245,12 @@ int main(int argc, char** argv) {
         per_rank += "]";
         fprintf(out, "{\"summary\": true, \"table\": \"%s\", \"modes\": %u, \"points\": %u, \"trials_per_point\": %llu, \"world\": %d, "
                      "\"units\": %llu, \"units_resumed\": %llu, \"frames_counted\": %llu, \"frames_run\": %llu, \"seconds_per_rank\": %s, "
-                     "\"seconds\": %.3f, \"frames_per_s\": %.6g, \"balance_efficiency\": %.4f, \"gpu_launches\": %llu, \"precision\": \"%s\"}\n",
+                     "\"seconds\": %.3f, \"frames_per_s\": %.6g, \"balance_efficiency\": %.4f, \"gpu_launches\": %llu, \"precision\": \"%s\", "
+                     "\"rank0_seconds\": {\"setup\": %.3f, \"wait\": %.3f, \"fill\": %.3f, \"enqueue\": %.3f}}\n",
                 table.c_str(), d.n_modes, n_points, (unsigned long long)d.trials_per_point, world, (unsigned long long)st.units_total,
                 (unsigned long long)st.units_resumed, (unsigned long long)frames_all, (unsigned long long)frames_run, per_rank.c_str(), tmax,
-                tmax > 0 ? frames_run / tmax : 0.0, tmax > 0 ? tsum / world / tmax : 1.0, (unsigned long long)launches, fast ? "fast" : "exact");
+                tmax > 0 ? frames_run / tmax : 0.0, tmax > 0 ? tsum / world / tmax : 1.0, (unsigned long long)launches, fast ? "fast" : "exact",
+                st.setup_seconds, st.wait_seconds, st.fill_seconds, st.enqueue_seconds);
         if (out != stdout) fclose(out);
     }
     if (comm) nccl.CommDestroy(comm);

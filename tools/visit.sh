@@ -57,6 +57,8 @@ ncu5)
 ncu6)
   ncu --set full --clock-control none --import-source on -k regex:dpsk_find_preamble -c 1 -f -o $OUT/prof_bk python tools/dpsk_acquire_quick_bench.py 1024 > $OUT/ncu_bk.log 2>&1; tail -5 $OUT/ncu_bk.log
   ncu --set full --clock-control none --import-source on -k regex:ofdm_acquire_kernel -c 1 -f -o $OUT/prof_acq python tools/acquire_quick_bench.py 1024 > $OUT/ncu_acq.log 2>&1; tail -5 $OUT/ncu_acq.log;;
+sweep5) ( time projectultra_b200/pu_sweep --table config5 --trials ${TRIALS:-1024} --block 1024 --out $OUT/sweep_config5.jsonl ) > $OUT/sweep_config5.log 2>&1; tail -6 $OUT/sweep_config5.log; tail -1 $OUT/sweep_config5.jsonl | cut -c1-600;;
+sweep5N) N=${NGPU:-8}; for r in $(seq 0 $((N-1))); do RANK=$r WORLD_SIZE=$N LOCAL_RANK=$r MASTER_PORT=29700 projectultra_b200/pu_sweep --table config5 --trials ${TRIALS:-8192} --block 1024 --rendezvous /tmp --manifest $OUT/manifest5_N$N --out $OUT/sweep_config5_N$N.jsonl > $OUT/sweep5N_r$r.log 2>&1 & done; wait; tail -n 3 $OUT/sweep5N_r0.log; tail -1 $OUT/sweep_config5_N$N.jsonl | cut -c1-800;;
 ncu4)
   for m in m3 m1qam16; do QB_PRECISION=fast ncu --set full --clock-control none --import-source on -k regex:ofdm_presynced -s 3 -c 1 -f -o $OUT/prof_fast_$m python tools/ofdm_quick_bench.py 4096 $m > $OUT/ncu_fast_$m.log 2>&1; done;;
 *) echo "unknown: $w";;
