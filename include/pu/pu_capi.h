@@ -446,6 +446,8 @@ typedef struct {
     uint32_t precision;         /* pu_precision of the OFDM kernels */
     uint32_t chunk;             /* PU_WF_OFDM_SC: process() chunk, 0 = 960 */
     float cost;                 /* relative cost of one frame for the partitioner; 0 = built-in estimate */
+    uint32_t lead_samples;      /* silence in front of / behind every TX waveform (tools/test_iwaveform.cpp:396-459 surrounds its frames with */
+    uint32_t tail_samples;      /* 1.5 s / 1 s of it): an acquired frame whose tail the channel's delay pushes out of the buffer loses its last symbol */
 } pu_sweep_mode;
 
 typedef struct {

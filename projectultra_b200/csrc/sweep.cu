@@ -202,6 +202,8 @@ struct ModeEngine {
             w.resize(n);
             if ((s = tx(w.data(), n, &n)) != PU_OK) return s;
             if (!chirp.empty()) w.insert(w.begin(), chirp.begin(), chirp.end());
+            if (m->lead_samples) w.insert(w.begin(), m->lead_samples, 0.0f);       // the tools' silence around a frame (test_iwaveform.cpp:396-459)
+            if (m->tail_samples) w.insert(w.end(), m->tail_samples, 0.0f);
             if (m->peak > 0) {
                 float mx = 0.0f;
                 for (float v : w) mx = std::max(mx, std::fabs(v));

@@ -100,3 +100,22 @@ def test_interrupted_sweep_resumes_from_its_manifest(ctx, tmp_path):
     # a different table must not resume from this directory
     with pytest.raises(capi.PuError):
         capi.Sweep(small_table(capi), trials_per_point=49, block_trials=16, pool=8, manifest_dir=d, run_id=4).run(ctx)
+
+
+def test_acquired_modes_need_the_tools_silence_behind_the_frame(ctx):
+    """tools/test_iwaveform.cpp:396-459 surrounds every frame with silence.  Without a tail, the delayed path of a Watterson channel pushes
+    the end of the last symbol out of the buffer: the receiver then reports fewer than 648 soft bits and the frame counts as lost at any
+    SNR (the 0.99 floor of the first config-5 table, profiles/r2_v44_config5_sweep.md).  pu_sweep_mode.lead_samples / tail_samples."""
+    from projectultra_b200 import capi
+    mc = capi.mcdpsk_config(8, 2)
+    m1 = capi.ModemConfig.from_buffer_copy(bytes(__import__("refapi").config_m1(__import__("refapi").DQPSK, __import__("refapi").R1_4)))
+    fer = {}
+    for tail in (0, 2400):
+        modes = [capi.sweep_mode(capi.WF_MCDPSK_CHIRP, mc, capi.R1_4, 20, "moderate", 20, 5, 2, peak=0.5, lead_samples=480 if tail else 0, tail_samples=tail),
+                 capi.sweep_mode(capi.WF_OFDM_CHIRP, m1, capi.R1_4, 20, "good", 20, 5, 2, peak=0.5, precision="fast", lead_samples=480 if tail else 0,
+                                 tail_samples=tail)]
+        counters, _ = capi.Sweep(modes, trials_per_point=128, block_trials=64, pool=8).run(ctx)
+        fer[tail] = counters[:, 1].astype(np.float64) / counters[:, 0]
+    print("FER without / with silence:", fer[0].round(3).tolist(), fer[2400].round(3).tolist())
+    assert (fer[0] > 0.7).all()                       # every frame short of a codeword
+    assert (fer[2400] < 0.45).all() and fer[2400][2:].max() < 0.1      # MC-DPSK: the moderate channel's fades; OFDM_CHIRP R1/4 on good: clean

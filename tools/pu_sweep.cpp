@@ -55,6 +55,11 @@ unsigned payload_of(unsigned rate) {   // floor(k / 8): k = 162, 216, 324, 432, 
     return k[rate] / 8;
 }
 
+// Acquired frames are surrounded by silence as the reference's tools do (test_iwaveform.cpp:396-459: 1.5 s before, 1 s behind; here 10 ms
+// and 50 ms -- enough for the channel's path delays and the acquisition's jitter, without tripling the search buffers): without a tail
+// the delayed path pushes the last symbol out of the buffer and the receiver hands out fewer than 648 soft bits.
+constexpr unsigned kLead = 480, kTail = 2400;
+
 pu_sweep_mode ofdm_mode(unsigned wf, unsigned fft, unsigned mod, unsigned rate, unsigned ch, float s0, float ds, unsigned n, bool fast) {
     pu_sweep_mode m{};
     const bool diff = mod == PU_MOD_DBPSK || mod == PU_MOD_DQPSK || mod == PU_MOD_D8PSK;
@@ -66,6 +71,7 @@ pu_sweep_mode ofdm_mode(unsigned wf, unsigned fft, unsigned mod, unsigned rate, 
     m.code_rate = rate; m.payload_bytes = payload_of(rate); m.channel = ch; m.n_snr = n; m.snr_first_db = s0; m.snr_step_db = ds;
     m.peak = wf == PU_WF_OFDM ? 0.0f : 0.5f;
     m.precision = fast ? PU_PRECISION_FAST : PU_PRECISION_EXACT;
+    if (wf != PU_WF_OFDM) { m.lead_samples = kLead; m.tail_samples = kTail; }
     return m;
 }
 pu_sweep_mode dpsk_mode(unsigned wf, unsigned mod, unsigned rate, unsigned ch, float s0, float ds, unsigned n) {
@@ -73,6 +79,7 @@ pu_sweep_mode dpsk_mode(unsigned wf, unsigned mod, unsigned rate, unsigned ch, f
     m.waveform = wf;
     m.dpsk = pu_dpsk_config{48000.0f, 1500.0f, 384, mod};            // 125 baud (tools/test_dpsk_snr.cpp:22)
     m.code_rate = rate; m.payload_bytes = payload_of(rate); m.channel = ch; m.n_snr = n; m.snr_first_db = s0; m.snr_step_db = ds; m.peak = 0.5f;
+    if (wf == PU_WF_DPSK_ACQ) { m.lead_samples = kLead; m.tail_samples = kTail; }
     return m;
 }
 pu_sweep_mode mcdpsk_mode(unsigned wf, unsigned carriers, unsigned rate, unsigned ch, float s0, float ds, unsigned n) {
@@ -80,6 +87,7 @@ pu_sweep_mode mcdpsk_mode(unsigned wf, unsigned carriers, unsigned rate, unsigne
     m.waveform = wf;
     m.mcdpsk = pu_mcdpsk_config{48000.0f, 500.0f, 2500.0f, carriers, 512, 2, 8};   // MultiCarrierDPSKConfig defaults (multi_carrier_dpsk.hpp:26-60)
     m.code_rate = rate; m.payload_bytes = payload_of(rate); m.channel = ch; m.n_snr = n; m.snr_first_db = s0; m.snr_step_db = ds; m.peak = 0.5f;
+    if (wf == PU_WF_MCDPSK_CHIRP) { m.lead_samples = kLead; m.tail_samples = kTail; }
     return m;
 }
 
@@ -100,7 +108,7 @@ std::vector<pu_sweep_mode> make_table(const std::string& name, bool fast) {
             t.push_back(dpsk_mode(PU_WF_DPSK, 1, PU_RATE_1_4, ch, -11, 2, 15));
         }
         t.push_back(ofdm_mode(PU_WF_OFDM_SC, 512, PU_MOD_DQPSK, PU_RATE_1_2, PU_CH_AWGN, 10, 3, 8, fast));   // Schmidl-Cox needs its 0.8 plateau
-    } else {   // config5: all waveforms x 5 rates x 40 SNR points (-12 ... +27.5 dB in 1 dB steps shifted per family)
+    } else {   // config5: all waveforms x 5 rates x 40 SNR points in 1 dB steps, the grid shifted per family (-8, -14, -28 dB upwards)
         const unsigned rates[] = {PU_RATE_1_4, PU_RATE_1_2, PU_RATE_2_3, PU_RATE_3_4, PU_RATE_5_6};
         for (unsigned r : rates) {
             for (unsigned mod : {PU_MOD_DBPSK, PU_MOD_DQPSK, PU_MOD_D8PSK, PU_MOD_BPSK, PU_MOD_QPSK, PU_MOD_QAM16, PU_MOD_QAM32, PU_MOD_QAM64})
@@ -108,8 +116,8 @@ std::vector<pu_sweep_mode> make_table(const std::string& name, bool fast) {
             for (unsigned mod : {PU_MOD_DQPSK, PU_MOD_QAM16, PU_MOD_QAM32, PU_MOD_QAM64})
                 t.push_back(ofdm_mode(PU_WF_OFDM, 1024, mod, r, PU_CH_GOOD, -8, 1, 40, fast));
             t.push_back(ofdm_mode(PU_WF_OFDM_CHIRP, 512, PU_MOD_DQPSK, r, PU_CH_GOOD, -8, 1, 40, fast));
-            for (unsigned nc : {3u, 5u, 8u, 13u, 20u}) t.push_back(mcdpsk_mode(PU_WF_MCDPSK_CHIRP, nc, r, PU_CH_POOR, -12, 1, 40));
-            for (unsigned mod : {0u, 1u, 2u}) t.push_back(dpsk_mode(PU_WF_DPSK_ACQ, mod, r, PU_CH_POOR, -12, 1, 40));
+            for (unsigned nc : {3u, 5u, 8u, 13u, 20u}) t.push_back(mcdpsk_mode(PU_WF_MCDPSK_CHIRP, nc, r, PU_CH_POOR, -14, 1, 40));
+            for (unsigned mod : {0u, 1u, 2u}) t.push_back(dpsk_mode(PU_WF_DPSK_ACQ, mod, r, PU_CH_POOR, -28, 1, 40));
         }
     }
     return t;
