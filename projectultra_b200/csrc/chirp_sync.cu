@@ -196,11 +196,13 @@ constexpr int kC2N = 24000, kC2Nd = kC2N / kRankD;     // the 48 kHz chirp: 24 0
 constexpr int kC2MaxPos = 3000;                         // coarse positions per window the shared-memory budget of one SM allows
 constexpr int kC2TileIn = kC2Threads * kRankD + kRankNT - 1;
 constexpr int kC2Row = 65;                              // verify tile: 64 taps per row, odd stride
-// Shared memory of one frame, carved from the dynamic allocation for the window's coarse-position budget `maxpos` (host: chirp2_smem_bytes;
-// 65 KB for 66 000-sample buffers, 84 KB for 84 000: two frames per SM up to ~110 000 samples, one beyond).
+// Shared memory of one frame, carved from the dynamic allocation for the window's coarse-position budget `maxpos` and the number of
+// positions ranked per pass `ppart` (host: chirp2_layout): the decimated window is the large item, so long windows are ranked in
+// several passes over a buffer that holds one part (+ the 4 000-tap overhang) -- 65 KB at 66 000 samples in one pass, 73 KB at
+// 86 600 in two: three frames per SM either way.
 struct Chirp2Smem {
-    float* xd;                        // tier 1: decimated window, whole tiles.  tier 2: rows[3][32][kC2Row].  fine: lin[3][256]
-    float* tile;                      // low-pass input tile (tier 1b only); the same storage then holds acc, a, order
+    float* xd;                        // tier 1: decimated part of the window, whole tiles.  tier 2: rows[3][32][kC2Row].  fine: lin[3][256]
+    float* tile;                      // low-pass input tile
     float (*acc)[2];
     float* a;                         // estimate of the normalised correlation
     unsigned short* order;            // order[rank] = coarse index, best estimate first
@@ -210,25 +212,26 @@ struct Chirp2Smem {
     int* cand;                        // [32]
     float* best_c; int* best_p; int* go;
 };
-__host__ __device__ inline int chirp2_tiles(int maxpos) { return (8 * maxpos + kC2Nd + kC2Threads - 1) / kC2Threads; }
-__host__ __device__ inline int chirp2_union_floats(int maxpos) {
-    const int r = 2 * maxpos + maxpos + (maxpos + 1) / 2;
-    return (r > kC2TileIn + 2 ? r : kC2TileIn + 2) + 3 & ~3;
+__host__ __device__ inline int chirp2_tiles(int ppart) {       // never less than the exact phases need: rows[3][32][65] + 3 template tiles
+    const int t = (8 * ppart + kC2Nd + kC2Threads - 1) / kC2Threads, floor_t = (3 * 32 * kC2Row + 3 * 2 * 64 + kC2Threads - 1) / kC2Threads;
+    return t > floor_t ? t : floor_t;
 }
-__host__ __device__ inline size_t chirp2_smem_floats(int maxpos) {
-    return static_cast<size_t>(chirp2_tiles(maxpos)) * kC2Threads + chirp2_union_floats(maxpos) +
-           (chirp2_tiles(maxpos) * (kC2Threads / 8) + 8) + 48 + 3 * 128 + 32 + 4;
+__host__ __device__ inline int chirp2_rank_floats(int maxpos) { return (2 * maxpos + maxpos + (maxpos + 1) / 2 + 3) & ~3; }
+__host__ __device__ inline int chirp2_seg_floats(int maxpos) { return (maxpos + kC2N / 48 + 2 * (kC2Threads / 8) + 8 + 3) & ~3; }
+__host__ __device__ inline size_t chirp2_smem_floats(int maxpos, int ppart) {
+    return static_cast<size_t>(chirp2_tiles(ppart)) * kC2Threads + ((kC2TileIn + 2 + 3) & ~3) + chirp2_rank_floats(maxpos) + chirp2_seg_floats(maxpos) +
+           48 + 3 * 128 + 32 + 4;
 }
-__device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos) {
+__device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos, int ppart) {
     Chirp2Smem S;
     float* p = reinterpret_cast<float*>(base);
-    S.xd = p; p += static_cast<size_t>(chirp2_tiles(maxpos)) * kC2Threads;
-    S.tile = p;
+    S.xd = p; p += static_cast<size_t>(chirp2_tiles(ppart)) * kC2Threads;
+    S.tile = p; p += (kC2TileIn + 2 + 3) & ~3;
     S.acc = reinterpret_cast<float (*)[2]>(p);
     S.a = p + 2 * maxpos;
     S.order = reinterpret_cast<unsigned short*>(p + 3 * maxpos);
-    p += chirp2_union_floats(maxpos);
-    S.seg = p; p += chirp2_tiles(maxpos) * (kC2Threads / 8) + 8;
+    p += chirp2_rank_floats(maxpos);
+    S.seg = p; p += chirp2_seg_floats(maxpos);
     S.lp = p; p += 48;
     S.exq = p; p += 128;
     S.exe = p; p += 128;
@@ -236,6 +239,19 @@ __device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos) {
     S.cand = reinterpret_cast<int*>(p); p += 32;
     S.best_c = p; S.best_p = reinterpret_cast<int*>(p + 1); S.go = reinterpret_cast<int*>(p + 2);
     return S;
+}
+// positions per ranking pass (a multiple of 8): the fewest passes that keep three frames on an SM, else the smallest footprint of <= 4 passes
+inline int chirp2_layout(int maxpos, size_t* bytes) {
+    int best = 0;
+    size_t best_b = 0;
+    for (int parts = 1; parts <= 4; ++parts) {
+        const int ppart = ((maxpos + parts - 1) / parts + 7) & ~7;
+        const size_t b = chirp2_smem_floats(maxpos, ppart) * sizeof(float);
+        if (!best || b < best_b) { best = ppart; best_b = b; }
+        if (b <= 74 * 1024) break;
+    }
+    *bytes = best_b;
+    return best;
 }
 
 __device__ unsigned long long g_chirp2_stats[2];          // {searches, verification rounds}: pu_chirp_search_stats
@@ -255,7 +271,7 @@ __device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, b
 // x = frame, L = its length, w0 = window start, Lw = window length: detectChirpTemplate(x + w0, Lw) (:560-629)
 __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restrict__ x, int L, int w0, int Lw, const float* __restrict__ ts,
                                       const float* __restrict__ tc, const float* __restrict__ tds, const float* __restrict__ tdc, float te,
-                                      float threshold, float* corr_out) {
+                                      float threshold, int ppart, float* corr_out) {
     constexpr int n = kC2N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     *corr_out = 0.0f;
@@ -265,54 +281,40 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     if (n_pos == 0) return -1;
     const float* xw = x + w0;
     __syncthreads();                                         // the previous call's shared state is dead
-    // ---------------- tier 1b: low-pass + 6:1 decimation, 48-sample energies
-    const int nxd = 8 * (n_pos - 1) + kC2Nd;                 // decimated samples the positions touch
-    const int ntile = (nxd + kC2Threads - 1) / kC2Threads;
-    for (int tl = 0; tl < ntile; ++tl) {
-        const int q0 = tl * kC2Threads * kRankD - kRankC;    // window index of tile[0]
-        for (int j = tid; j < kC2TileIn; j += kC2Threads) {
-            const int g = w0 + q0 + j;
-            S.tile[j] = (g >= 0 && g < L) ? x[g] : 0.0f;
-        }
-        __syncthreads();
-        {
-            const float* t = S.tile + kRankD * tid;
-            float y = 0.0f;
-#pragma unroll
-            for (int k = 0; k < kRankNT; ++k) y = fmaf(S.lp[k], t[k], y);
-            S.xd[tl * kC2Threads + tid] = y;
-            float e = 0.0f;                                   // 6 samples per thread, 8 threads per 48-sample segment
-#pragma unroll
-            for (int k = 0; k < kRankD; ++k) { const float v = t[kRankC + k]; e = fmaf(v, v, e); }
-            e += __shfl_xor_sync(0xffffffffu, e, 1);
-            e += __shfl_xor_sync(0xffffffffu, e, 2);
-            e += __shfl_xor_sync(0xffffffffu, e, 4);
-            if ((tid & 7) == 0) S.seg[tl * (kC2Threads / 8) + (tid >> 3)] = e;
-        }
-        __syncthreads();
-    }
-    for (int j = tid; j < n_pos; j += kC2Threads) { S.acc[j][0] = 0.0f; S.acc[j][1] = 0.0f; }   // (the tile is dead: same storage)
-    // exclusive prefix of the segment energies (one warp)
-    const int nseg = ntile * (kC2Threads / 8);
-    if (warp == 0) {
-        float carry = 0.0f;
-        for (int b = 0; b < nseg + 1; b += 32) {
-            const float v = (b + lane < nseg) ? S.seg[b + lane] : 0.0f;
-            float incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float u = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += u;
+    for (int j = tid; j < n_pos; j += kC2Threads) { S.acc[j][0] = 0.0f; S.acc[j][1] = 0.0f; }
+    int nseg = 0;
+    for (int p0 = 0; p0 < n_pos; p0 += ppart) {                // ranking passes over [p0, p0 + np)
+        const int np = min(ppart, n_pos - p0);
+        // ---------------- tier 1b: low-pass + 6:1 decimation of the part (decimated index 8 p0 + i -> xd[i]), 48-sample energies
+        const int nxd = 8 * (np - 1) + kC2Nd;                  // decimated samples the part's positions touch
+        const int ntile = (nxd + kC2Threads - 1) / kC2Threads;
+        for (int tl = 0; tl < ntile; ++tl) {
+            const int q0 = (8 * p0 + tl * kC2Threads) * kRankD - kRankC;    // window index of tile[0]
+            for (int j = tid; j < kC2TileIn; j += kC2Threads) {
+                const int g = w0 + q0 + j;
+                S.tile[j] = (g >= 0 && g < L) ? x[g] : 0.0f;
             }
-            if (b + lane <= nseg) S.seg[b + lane] = carry + incl - v;
-            carry += __shfl_sync(0xffffffffu, incl, 31);
+            __syncthreads();
+            {
+                const float* t = S.tile + kRankD * tid;
+                float y = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kRankNT; ++k) y = fmaf(S.lp[k], t[k], y);
+                S.xd[tl * kC2Threads + tid] = y;
+                float e = 0.0f;                                 // 6 samples per thread, 8 threads per 48-sample segment
+#pragma unroll
+                for (int k = 0; k < kRankD; ++k) { const float v = t[kRankC + k]; e = fmaf(v, v, e); }
+                e += __shfl_xor_sync(0xffffffffu, e, 1);
+                e += __shfl_xor_sync(0xffffffffu, e, 2);
+                e += __shfl_xor_sync(0xffffffffu, e, 4);
+                if ((tid & 7) == 0) S.seg[p0 + tl * (kC2Threads / 8) + (tid >> 3)] = e;   // (parts overlap: same values)
+            }
+            __syncthreads();
         }
-    }
-    __syncthreads();
-    // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one half of the taps); lane l starts 4 l taps
-    // into its half and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
-    {
-        const int nblk = (n_pos + 7) / 8;
+        nseg = p0 + ntile * (kC2Threads / 8);
+        // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one half of the taps); lane l starts 4 l taps
+        // into its half and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
+        const int nblk = (np + 7) / 8;
         for (int item = tid; item < 2 * nblk; item += kC2Threads) {
             const int sg = item / nblk, pb = item - sg * nblk;
             constexpr int len = kC2Nd / 2;
@@ -336,9 +338,25 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                const int m = 8 * pb + r;
+                const int m = p0 + 8 * pb + r;
                 if (m < n_pos) { atomicAdd(&S.acc[m][0], ac[r]); atomicAdd(&S.acc[m][1], as[r]); }
             }
+        }
+        __syncthreads();                                       // the next part overwrites xd
+    }
+    // exclusive prefix of the segment energies (one warp)
+    if (warp == 0) {
+        float carry = 0.0f;
+        for (int b = 0; b < nseg + 1; b += 32) {
+            const float v = (b + lane < nseg) ? S.seg[b + lane] : 0.0f;
+            float incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (b + lane <= nseg) S.seg[b + lane] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
     __syncthreads();
@@ -508,11 +526,11 @@ __global__ void __launch_bounds__(TWO_TIER ? kC2Threads : kChirpThreads, TWO_TIE
                                                                      float4* __restrict__ out_f, int* __restrict__ frame_start,
                                                                      int* __restrict__ frame_nsym, float* __restrict__ cfo_out,
                                                                      float* __restrict__ phase_out, int* __restrict__ n_llr,
-                                                                     int llr_per_symbol, int llr_stride, int maxpos) {
+                                                                     int llr_per_symbol, int llr_stride, int maxpos, int ppart) {
     __shared__ ChirpShared S;
     extern __shared__ __align__(16) unsigned char chirp_smem[];
     ChirpWarpBuf* WB = reinterpret_cast<ChirpWarpBuf*>(chirp_smem);   // brute-force form: one staging buffer per warp
-    const Chirp2Smem S2 = chirp2_carve(chirp_smem, maxpos);           // two-tier form
+    const Chirp2Smem S2 = chirp2_carve(chirp_smem, maxpos, ppart);           // two-tier form
     const int tid = threadIdx.x;
     const float* x = samples + static_cast<size_t>(blockIdx.x) * frame_stride;
     if constexpr (TWO_TIER) {
@@ -525,7 +543,7 @@ __global__ void __launch_bounds__(TWO_TIER ? kC2Threads : kChirpThreads, TWO_TIE
         const float te = down ? c.dn_e : c.up_e;
         if constexpr (TWO_TIER) {
             const float* dec = c.dec + (down ? 2 : 0) * static_cast<size_t>(c.nd);
-            return chirp_detect_template2(S2, x, L, w0, Lw, ts, tc, dec, dec + c.nd, te, threshold, corr);
+            return chirp_detect_template2(S2, x, L, w0, Lw, ts, tc, dec, dec + c.nd, te, threshold, ppart, corr);
         } else {
             return chirp_detect_template(S, WB, x + w0, Lw, ts, tc, c.n, te, threshold, corr);
         }
@@ -591,19 +609,20 @@ cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t 
     const bool two_tier = !force_exact && c.n == kC2N && c.nd == kC2Nd && maxpos <= kC2MaxPos;
     cudaError_t e;
     if (two_tier) {
-        const size_t smem = chirp2_smem_floats(maxpos) * sizeof(float);
+        size_t smem = 0;
+        const int ppart = chirp2_layout(maxpos, &smem);
         static std::atomic<uint64_t> done{0};
         if ((e = smem_optin(done, chirp_detect_kernel<true>, 232448)) != cudaSuccess) return e;
         chirp_detect_kernel<true><<<static_cast<unsigned>(B), kC2Threads, smem, st>>>(c, samples, frame_stride, L, threshold, sym_len, out_info, out_f,
                                                                                      frame_start, frame_nsym, cfo_out, phase_out, n_llr,
-                                                                                     llr_per_symbol, llr_stride, maxpos);
+                                                                                     llr_per_symbol, llr_stride, maxpos, ppart);
     } else {
         const size_t smem = sizeof(ChirpWarpBuf) * (kChirpThreads / 32);
         static std::atomic<uint64_t> done{0};
         if ((e = smem_optin(done, chirp_detect_kernel<false>, static_cast<int>(smem))) != cudaSuccess) return e;
         chirp_detect_kernel<false><<<static_cast<unsigned>(B), kChirpThreads, smem, st>>>(c, samples, frame_stride, L, threshold, sym_len, out_info,
                                                                                          out_f, frame_start, frame_nsym, cfo_out, phase_out,
-                                                                                         n_llr, llr_per_symbol, llr_stride, 0);
+                                                                                         n_llr, llr_per_symbol, llr_stride, 0, 0);
     }
     return cudaGetLastError();
 }
