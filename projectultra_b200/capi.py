@@ -239,10 +239,10 @@ class LdpcDecoder:
 
 
 def chirp_search_stats():
-    """(searches, exact verification rounds) of the two-tier chirp search on the current device since the last call."""
-    a, b = C.c_uint64(0), C.c_uint64(0)
-    check(lib().pu_chirp_search_stats(C.byref(a), C.byref(b)))
-    return int(a.value), int(b.value)
+    """(searches, coarse verification rounds, fine runs) of the two-tier chirp search on the current device since the last call."""
+    a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    check(lib().pu_chirp_search_stats(C.byref(a), C.byref(b), C.byref(c)))
+    return int(a.value), int(b.value), int(c.value)
 
 
 def chirp_generate(sample_rate=48000.0, tx_cfo_hz=0.0):

@@ -210,7 +210,7 @@ struct Chirp2Smem {
     float* lp;                        // [48] low-pass taps
     float* exq; float* exe; float* ex;   // [128] each
     int* cand;                        // [32]
-    float* best_c; int* best_p; int* go;
+    float* best_c; int* best_p; int* go; float* best_se;
 };
 __host__ __device__ inline int chirp2_tiles(int ppart) {       // never less than the exact phases need: rows[3][32][65] + 3 template tiles
     const int t = (8 * ppart + kC2Nd + kC2Threads - 1) / kC2Threads, floor_t = (3 * 32 * kC2Row + 3 * 2 * 64 + kC2Threads - 1) / kC2Threads;
@@ -237,7 +237,7 @@ __device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos, int p
     S.exe = p; p += 128;
     S.ex = p; p += 128;
     S.cand = reinterpret_cast<int*>(p); p += 32;
-    S.best_c = p; S.best_p = reinterpret_cast<int*>(p + 1); S.go = reinterpret_cast<int*>(p + 2);
+    S.best_c = p; S.best_p = reinterpret_cast<int*>(p + 1); S.go = reinterpret_cast<int*>(p + 2); S.best_se = p + 3;
     return S;
 }
 // positions per ranking pass (a multiple of 8): the fewest passes that keep three frames on an SM, else the smallest footprint of <= 4 passes
@@ -254,7 +254,7 @@ inline int chirp2_layout(int maxpos, size_t* bytes) {
     return best;
 }
 
-__device__ unsigned long long g_chirp2_stats[2];          // {searches, verification rounds}: pu_chirp_search_stats
+__device__ unsigned long long g_chirp2_stats[3];          // {searches, coarse verification rounds, fine runs}: pu_chirp_search_stats
 
 // the reference's closing arithmetic (:655-661)
 __device__ __forceinline__ float chirp_norm(float ci, float cq, float se, float te) {
@@ -281,15 +281,10 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     if (n_pos == 0) return -1;
     const float* xw = x + w0;
     __syncthreads();                                         // the previous call's shared state is dead
-    for (int j = tid; j < n_pos; j += kC2Threads) { S.acc[j][0] = 0.0f; S.acc[j][1] = 0.0f; }
-    int nseg = 0;
-    for (int p0 = 0; p0 < n_pos; p0 += ppart) {                // ranking passes over [p0, p0 + np)
-        const int np = min(ppart, n_pos - p0);
-        // ---------------- tier 1b: low-pass + 6:1 decimation of the part (decimated index 8 p0 + i -> xd[i]), 48-sample energies
-        const int nxd = 8 * (np - 1) + kC2Nd;                  // decimated samples the part's positions touch
-        const int ntile = (nxd + kC2Threads - 1) / kC2Threads;
+    // low-pass + 6:1 decimation: xd[i] = xf[base + 6 i] (window index) for ntile x 256 outputs; seg_base >= 0: 48-sample energies too
+    auto decimate = [&](int base, int ntile, int seg_base) {
         for (int tl = 0; tl < ntile; ++tl) {
-            const int q0 = (8 * p0 + tl * kC2Threads) * kRankD - kRankC;    // window index of tile[0]
+            const int q0 = base + tl * kC2Threads * kRankD - kRankC;        // window index of tile[0]
             for (int j = tid; j < kC2TileIn; j += kC2Threads) {
                 const int g = w0 + q0 + j;
                 S.tile[j] = (g >= 0 && g < L) ? x[g] : 0.0f;
@@ -301,16 +296,27 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
 #pragma unroll
                 for (int k = 0; k < kRankNT; ++k) y = fmaf(S.lp[k], t[k], y);
                 S.xd[tl * kC2Threads + tid] = y;
-                float e = 0.0f;                                 // 6 samples per thread, 8 threads per 48-sample segment
+                if (seg_base >= 0) {
+                    float e = 0.0f;                             // 6 samples per thread, 8 threads per 48-sample segment
 #pragma unroll
-                for (int k = 0; k < kRankD; ++k) { const float v = t[kRankC + k]; e = fmaf(v, v, e); }
-                e += __shfl_xor_sync(0xffffffffu, e, 1);
-                e += __shfl_xor_sync(0xffffffffu, e, 2);
-                e += __shfl_xor_sync(0xffffffffu, e, 4);
-                if ((tid & 7) == 0) S.seg[p0 + tl * (kC2Threads / 8) + (tid >> 3)] = e;   // (parts overlap: same values)
+                    for (int k = 0; k < kRankD; ++k) { const float v = t[kRankC + k]; e = fmaf(v, v, e); }
+                    e += __shfl_xor_sync(0xffffffffu, e, 1);
+                    e += __shfl_xor_sync(0xffffffffu, e, 2);
+                    e += __shfl_xor_sync(0xffffffffu, e, 4);
+                    if ((tid & 7) == 0) S.seg[seg_base + tl * (kC2Threads / 8) + (tid >> 3)] = e;   // (parts overlap: same values)
+                }
             }
             __syncthreads();
         }
+    };
+    for (int j = tid; j < n_pos; j += kC2Threads) { S.acc[j][0] = 0.0f; S.acc[j][1] = 0.0f; }
+    int nseg = 0;
+    for (int p0 = 0; p0 < n_pos; p0 += ppart) {                // ranking passes over [p0, p0 + np)
+        const int np = min(ppart, n_pos - p0);
+        // ---------------- tier 1b: the part's decimated samples (decimated index 8 p0 + i -> xd[i]) and 48-sample energies
+        const int nxd = 8 * (np - 1) + kC2Nd;                  // decimated samples the part's positions touch
+        const int ntile = (nxd + kC2Threads - 1) / kC2Threads;
+        decimate(48 * p0, ntile, p0);
         nseg = p0 + ntile * (kC2Threads / 8);
         // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one half of the taps); lane l starts 4 l taps
         // into its half and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
@@ -420,7 +426,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                 }
             }
         }
-        if (warp == 0) S.ex[lane] = chirp_norm(ci, cq, se, te);
+        if (warp == 0) { S.ex[lane] = chirp_norm(ci, cq, se, te); S.exe[lane] = se; }
         __syncthreads();
         if (tid == 0) {
             float bc = (*S.best_c);
@@ -429,7 +435,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                 const float c = S.ex[r];
                 const int pos = S.cand[r];
                 errmax = fmaxf(errmax, fabsf(c - S.a[S.order[nv + r]]));
-                if (c > bc || (c == bc && bp >= 0 && pos < bp)) { bc = c; bp = pos; }   // the ascending scan's first maximum
+                if (c > bc || (c == bc && bp >= 0 && pos < bp)) { bc = c; bp = pos; (*S.best_se) = S.exe[r]; }   // the ascending scan's first maximum
             }
             (*S.best_c) = bc;
             (*S.best_p) = bp;
@@ -451,47 +457,102 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     __syncthreads();
     *corr_out = best;
     if (best_pos < 0 || best < __fmul_rn(threshold, 0.3f)) return -1;
-    // ---------------- fine search (:600-612) and the parabola's neighbours (:615-625): every position of [fine_start - 1, fine_end + 1]
-    // exactly, 32 positions per warp (warps 0..3) over one linear tile (lane l reads lin[t + l]: consecutive banks)
+    // ---------------- fine search (:600-612) and the parabola's neighbours (:615-625), two-tier as well.  The correlation magnitude is
+    // band-limited (2.4 kHz: main lobe 40 samples null to null), so estimates every 6 samples -- the decimated correlation again, on the
+    // grid best_pos + 6k -- locate its maximum; a run of 32 consecutive positions around it is evaluated exactly (lane = position over
+    // one linear tile: consecutive banks), and further runs follow while (a) a neighbour of the current first maximum is not exact yet
+    // or (b) an unverified grid point is within reach: 1.15 x estimate (the most the magnitude can rise between two grid points)
+    // + 4 x the largest |exact - estimate| seen.  S.ex[pos - q0] = exact value or -1 (not evaluated: cannot win, cannot be needed).
     const int fine_start = max(0, best_pos - 48), fine_end = min(search_len, best_pos + 48);
     const int q0 = max(0, fine_start - 1), q1 = min(search_len, fine_end + 1);
     {
-        float (*lin)[256] = reinterpret_cast<float (*)[256]>(S.xd);
-        float (*ftpl)[2][128] = reinterpret_cast<float (*)[2][128]>(S.xd + 3 * 256);   // [3][cos, sin][128]
-        auto stage = [&](int tile, int buf) {
-            {
-                const int wi = q0 + 128 * tile + tid;         // window index; positions past q1 read on into the frame or zeros
-                const bool ok = w0 + wi < L;
-                cp_async4_zfill(smem_u32(&lin[buf][tid]), ok ? xw + wi : x, ok);
+        const int klo = -((best_pos - fine_start) / 6), khi = (fine_end - best_pos) / 6, nk = khi - klo + 1;
+        const int gbase = best_pos + 6 * klo;                  // window index of grid point 0
+        decimate(gbase, (nk - 1 + kC2Nd + kC2Threads - 1) / kC2Threads, -1);
+        float* est = S.exq;                                    // [nk <= 17]
+        const float dn = sqrtf(fmaxf(*S.best_se, 0.0f) * te);  // the window energy moves by < 0.5 % over +-48 samples
+        for (int k = warp; k < nk; k += kC2Warps) {
+            float ac = 0.0f, as = 0.0f;
+            for (int j = lane; j < kC2Nd; j += 32) {
+                const float v = S.xd[k + j];
+                ac = fmaf(v, __ldg(&tdc[j]), ac);
+                as = fmaf(v, __ldg(&tds[j]), as);
             }
-            if (tid < 64 && 128 * tile + 4 * (tid & 31) < n)
-                cp_async16(smem_u32(&ftpl[buf][tid >> 5][4 * (tid & 31)]), (tid < 32 ? tc : ts) + 128 * tile + 4 * (tid & 31));
-            cp_async_commit();
-        };
-        float ci = 0.0f, cq = 0.0f, se = 0.0f;                 // warps 0..3: positions q0 + 32 warp + lane
-        stage(0, 0);
-        stage(1, 1);
-        for (int tile = 0; tile < (n + 127) / 128; ++tile) {
-            cp_async_wait_but_one();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { ac += __shfl_xor_sync(0xffffffffu, ac, o); as += __shfl_xor_sync(0xffffffffu, as, o); }
+            if (lane == 0) est[k] = dn < 1e-10f ? 0.0f : sqrtf(ac * ac + as * as) / dn;
+        }
+        for (int i = tid; i < 128; i += kC2Threads) S.ex[i] = -1.0f;
+        __syncthreads();
+        if (tid == 0) S.ex[best_pos - q0] = best;              // exact from the coarse stage
+        float (*lin)[192] = reinterpret_cast<float (*)[192]>(S.xd);
+        float (*ftpl)[2][128] = reinterpret_cast<float (*)[2][128]>(S.xd + 3 * 192);   // [3][cos, sin][128]
+        float ferr = 0.0f;                                     // thread 0
+        for (int it = 0;; ++it) {
+            if (tid == 0) {
+                int centre = -1;
+                if (it == 0) {
+                    int kb = 0;
+                    for (int k = 1; k < nk; ++k) if (est[k] > est[kb]) kb = k;
+                    centre = gbase + 6 * kb;
+                } else {
+                    for (int k = 0; k < nk; ++k) {
+                        const float v = S.ex[gbase + 6 * k - q0];
+                        if (v >= 0.0f) ferr = fmaxf(ferr, fabsf(v - est[k]));
+                    }
+                    float fb = best;
+                    int fp = best_pos;
+                    for (int pos = fine_start; pos <= fine_end; ++pos) {
+                        const float c = S.ex[pos - q0];
+                        if (c > fb) { fb = c; fp = pos; }
+                    }
+                    if (fp > 0 && fp < search_len - 1 && (S.ex[fp - 1 - q0] < 0.0f || S.ex[fp + 1 - q0] < 0.0f)) centre = fp;
+                    for (int k = 0; k < nk && centre < 0; ++k)
+                        if (S.ex[gbase + 6 * k - q0] < 0.0f && est[k] * 1.15f + 4.0f * ferr + 1e-6f >= fb) centre = gbase + 6 * k;
+                }
+                S.cand[0] = centre < 0 ? -1 : min(max(centre - 16, q0), max(q0, q1 - 31));
+                if (centre >= 0) atomicAdd(&g_chirp2_stats[2], 1ull);
+            }
             __syncthreads();
-            if (128 * (tile + 2) < n) stage(tile + 2, (tile + 2) % 3); else cp_async_commit();
-            if (warp < 4) {
-                const float* row = lin[tile % 3] + 32 * warp + lane;
-                const int tn = min(128, n - 128 * tile);
+            const int r0 = S.cand[0];
+            if (r0 < 0) break;
+            auto stage = [&](int tile, int buf) {
+                if (tid < 160) {
+                    const int wi = r0 + 128 * tile + tid;     // window index; lanes past q1 read on into the frame or zeros
+                    const bool ok = w0 + wi < L;
+                    cp_async4_zfill(smem_u32(&lin[buf][tid]), ok ? xw + wi : x, ok);
+                } else if (tid < 224) {
+                    const int u = tid - 160;
+                    if (128 * tile + 4 * (u & 31) < n)
+                        cp_async16(smem_u32(&ftpl[buf][u >> 5][4 * (u & 31)]), (u < 32 ? tc : ts) + 128 * tile + 4 * (u & 31));
+                }
+                cp_async_commit();
+            };
+            float ci = 0.0f, cq = 0.0f, se = 0.0f;             // warp 0: position r0 + lane
+            stage(0, 0);
+            stage(1, 1);
+            for (int tile = 0; tile < (n + 127) / 128; ++tile) {
+                cp_async_wait_but_one();
+                __syncthreads();
+                if (128 * (tile + 2) < n) stage(tile + 2, (tile + 2) % 3); else cp_async_commit();
+                if (warp == 0) {
+                    const float* row = lin[tile % 3] + lane;
+                    const int tn = min(128, n - 128 * tile);
 #pragma unroll 4
-                for (int t = 0; t < tn; t += 4) {
-                    const float4 vc = *reinterpret_cast<const float4*>(&ftpl[tile % 3][0][t]);
-                    const float4 vs = *reinterpret_cast<const float4*>(&ftpl[tile % 3][1][t]);
-                    const float s0 = row[t], s1 = row[t + 1], s2 = row[t + 2], s3 = row[t + 3];
-                    ci = __fadd_rn(ci, __fmul_rn(s0, vc.x)); cq = __fadd_rn(cq, __fmul_rn(s0, vs.x)); se = __fadd_rn(se, __fmul_rn(s0, s0));
-                    ci = __fadd_rn(ci, __fmul_rn(s1, vc.y)); cq = __fadd_rn(cq, __fmul_rn(s1, vs.y)); se = __fadd_rn(se, __fmul_rn(s1, s1));
-                    ci = __fadd_rn(ci, __fmul_rn(s2, vc.z)); cq = __fadd_rn(cq, __fmul_rn(s2, vs.z)); se = __fadd_rn(se, __fmul_rn(s2, s2));
-                    ci = __fadd_rn(ci, __fmul_rn(s3, vc.w)); cq = __fadd_rn(cq, __fmul_rn(s3, vs.w)); se = __fadd_rn(se, __fmul_rn(s3, s3));
+                    for (int t = 0; t < tn; t += 4) {
+                        const float4 vc = *reinterpret_cast<const float4*>(&ftpl[tile % 3][0][t]);
+                        const float4 vs = *reinterpret_cast<const float4*>(&ftpl[tile % 3][1][t]);
+                        const float s0 = row[t], s1 = row[t + 1], s2 = row[t + 2], s3 = row[t + 3];
+                        ci = __fadd_rn(ci, __fmul_rn(s0, vc.x)); cq = __fadd_rn(cq, __fmul_rn(s0, vs.x)); se = __fadd_rn(se, __fmul_rn(s0, s0));
+                        ci = __fadd_rn(ci, __fmul_rn(s1, vc.y)); cq = __fadd_rn(cq, __fmul_rn(s1, vs.y)); se = __fadd_rn(se, __fmul_rn(s1, s1));
+                        ci = __fadd_rn(ci, __fmul_rn(s2, vc.z)); cq = __fadd_rn(cq, __fmul_rn(s2, vs.z)); se = __fadd_rn(se, __fmul_rn(s2, s2));
+                        ci = __fadd_rn(ci, __fmul_rn(s3, vc.w)); cq = __fadd_rn(cq, __fmul_rn(s3, vs.w)); se = __fadd_rn(se, __fmul_rn(s3, s3));
+                    }
                 }
             }
+            if (warp == 0 && r0 + lane <= q1) S.ex[r0 + lane - q0] = chirp_norm(ci, cq, se, te);
+            __syncthreads();
         }
-        if (warp < 4) S.ex[32 * warp + lane] = chirp_norm(ci, cq, se, te);
-        __syncthreads();
     }
     if (tid == 0) {
         for (int pos = fine_start; pos <= fine_end; ++pos) {
@@ -513,7 +574,6 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     __syncthreads();
     best = (*S.best_c);
     best_pos = (*S.best_p);
-    (void)q1;
     *corr_out = best;
     return best >= threshold ? best_pos : -1;
 }
@@ -627,11 +687,11 @@ cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t 
     return cudaGetLastError();
 }
 
-cudaError_t chirp_search_stats(unsigned long long* out) {
+cudaError_t chirp_search_stats(unsigned long long* out /* [3] */) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return e;
     if ((e = cudaMemcpyFromSymbol(out, g_chirp2_stats, sizeof(g_chirp2_stats))) != cudaSuccess) return e;
-    const unsigned long long zero[2] = {0, 0};
+    const unsigned long long zero[3] = {0, 0, 0};
     return cudaMemcpyToSymbol(g_chirp2_stats, zero, sizeof(zero));
 }
 

@@ -1493,11 +1493,12 @@ pu_status pu_ofdm_chirp_receive_batch(pu_ofdm* h, const float* samples, size_t B
     return PU_OK;
 }
 
-pu_status pu_chirp_search_stats(uint64_t* searches, uint64_t* rounds) {
-    unsigned long long v[2] = {0, 0};
+pu_status pu_chirp_search_stats(uint64_t* searches, uint64_t* rounds, uint64_t* fine_runs) {
+    unsigned long long v[3] = {0, 0, 0};
     PU_CUDA_TRY(pu::chirp_search_stats(v));
     if (searches) *searches = v[0];
     if (rounds) *rounds = v[1];
+    if (fine_runs) *fine_runs = v[2];
     return PU_OK;
 }
 

@@ -103,7 +103,7 @@ def test_two_tier_search_equals_brute_force_search():
     os.environ.pop("PU_CHIRP_SEARCH", None)
     capi.chirp_search_stats()
     fast = dem.chirp_receive_batch(x, llr_stride=700)
-    searches, rounds = capi.chirp_search_stats()
+    searches, rounds, fine_runs = capi.chirp_search_stats()
     os.environ["PU_CHIRP_SEARCH"] = "exact"
     try:
         slow = dem.chirp_receive_batch(x, llr_stride=700)
@@ -116,8 +116,8 @@ def test_two_tier_search_equals_brute_force_search():
     assert (np.asarray(val_f).view(np.uint32) == np.asarray(val_s).view(np.uint32)).all()
     assert (llr_f.view(np.uint32) == llr_s.view(np.uint32)).all()
     found = int((info_f[:, 0] != 0).sum())
-    print("two-tier == brute force on %d frames, %d with both chirps found; %d template searches, %d verification rounds of 32 positions"
-          % (len(x), found, searches, rounds))
+    print("two-tier == brute force on %d frames, %d with both chirps found; %d template searches, %d coarse verification rounds of 32 positions, "
+          "%d fine runs of 32 positions" % (len(x), found, searches, rounds, fine_runs))
     assert searches >= len(x) - 1 and rounds <= 2 * searches        # the ranking does the work: ~1 round per search, not ~30
     assert 60 <= found < len(x) - 10
     del ctx

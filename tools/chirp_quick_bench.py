@@ -25,8 +25,8 @@ if len(sys.argv) > 2 and sys.argv[2] == "mcdpsk":
         e0.record(); out = dem.chirp_receive_batch(x, llr_stride=648); e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         st = capi.chirp_search_stats()
-        print("snr=%5.1f cfo=%.1f MC-DPSK detectDualChirp+process B=%d L=%d ms=%.1f  %.1f kframes/s  detected=%.3f  with soft bits=%.3f  searches=%d verify rounds=%d" % (
-            snr, cfo, B, L, ms, B / ms, out[2][:, 0].float().mean().item(), (out[1] > 0).float().mean().item(), st[0], st[1]), flush=True)
+        print("snr=%5.1f cfo=%.1f MC-DPSK detectDualChirp+process B=%d L=%d ms=%.1f  %.1f kframes/s  detected=%.3f  with soft bits=%.3f  searches=%d verify rounds=%d fine runs=%d" % (
+            snr, cfo, B, L, ms, B / ms, out[2][:, 0].float().mean().item(), (out[1] > 0).float().mean().item(), st[0], st[1], st[2]), flush=True)
         if R.available():
             xs = x[:2].cpu().numpy()
             t0 = time.perf_counter()
@@ -52,8 +52,8 @@ for snr in (15.0, -5.0):
     e0.record(); out = dem.chirp_receive_batch(x); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     st = capi.chirp_search_stats()
-    print("snr=%5.1f detectDualChirp+process B=%d L=%d ms=%.1f  %.1f kframes/s  detected=%.3f  searches=%d verify rounds=%d" % (
-        snr, B, L, ms, B / ms, out[2][:, 0].float().mean().item(), st[0], st[1]), flush=True)
+    print("snr=%5.1f detectDualChirp+process B=%d L=%d ms=%.1f  %.1f kframes/s  detected=%.3f  searches=%d verify rounds=%d fine runs=%d" % (
+        snr, B, L, ms, B / ms, out[2][:, 0].float().mean().item(), st[0], st[1], st[2]), flush=True)
     if R.available():
         xs = x[:2].cpu().numpy()
         t0 = time.perf_counter()
