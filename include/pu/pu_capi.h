@@ -190,6 +190,9 @@ PU_API pu_status pu_chirp_generate(float sample_rate, float tx_cfo_hz, float* ou
  * position within the error bound of the best one) and exact runs of the fine search (32 consecutive positions each; 4 cover the
  * whole +-48 range).  Synchronises the device.  Any pointer may be NULL. */
 PU_API pu_status pu_chirp_search_stats(uint64_t* searches, uint64_t* rounds, uint64_t* fine_runs);
+/* SM cycles the searches since the last call spent per phase (summed over frames, thread 0's clock): [0] low-pass + decimation,
+ * [1] correlation estimates, [2] energies + ranking, [3] exact evaluation of the coarse leaders, [4] fine ranking, [5] exact fine runs. */
+PU_API pu_status pu_chirp_phase_cycles(uint64_t cycles[8]);
 
 /* ---------------------------------------------------------------- batched transmitter
  * LDPCEncoder::encode (src/fec/ldpc_encoder.cpp:193-257, one 648-bit block, payload zero-padded to k bits) followed by

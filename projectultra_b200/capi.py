@@ -245,6 +245,13 @@ def chirp_search_stats():
     return int(a.value), int(b.value), int(c.value)
 
 
+def chirp_phase_cycles():
+    """Cycles per phase of the two-tier chirp search since the last call (pu_chirp_phase_cycles)."""
+    out = (C.c_uint64 * 8)()
+    check(lib().pu_chirp_phase_cycles(out))
+    return [int(v) for v in out]
+
+
 def chirp_generate(sample_rate=48000.0, tx_cfo_hz=0.0):
     """ChirpSync::generate (host): [up chirp][gap][down chirp][gap]."""
     n = C.c_size_t(0)

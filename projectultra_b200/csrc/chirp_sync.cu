@@ -201,7 +201,7 @@ constexpr int kC2Row = 65;                              // verify tile: 64 taps 
 // several passes over a buffer that holds one part (+ the 4 000-tap overhang) -- 65 KB at 66 000 samples in one pass, 73 KB at
 // 86 600 in two: three frames per SM either way.
 struct Chirp2Smem {
-    float* xd;                        // tier 1: decimated part of the window, whole tiles.  tier 2: rows[3][32][kC2Row].  fine: lin[3][256]
+    float* xd;                        // tier 1: decimated part of the window, whole tiles.  tier 2: rows[nbuf][32][kC2Row] + template tiles.  fine: lin[6][192] + template tiles
     float* tile;                      // low-pass input tile
     float (*acc)[2];
     float* a;                         // estimate of the normalised correlation
@@ -254,6 +254,7 @@ inline int chirp2_layout(int maxpos, size_t* bytes) {
     return best;
 }
 
+__device__ unsigned long long g_chirp2_clk[8];            // cycles of thread 0 per phase (diagnostics): ranking 1b, 1c, select, coarse exact, fine ranking, fine exact
 __device__ unsigned long long g_chirp2_stats[3];          // {searches, coarse verification rounds, fine runs}: pu_chirp_search_stats
 
 // the reference's closing arithmetic (:655-661)
@@ -309,6 +310,8 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
             __syncthreads();
         }
     };
+    long long tk = clock64();
+    auto mark = [&](int phase) { if (tid == 0) { const long long t = clock64(); atomicAdd(&g_chirp2_clk[phase], static_cast<unsigned long long>(t - tk)); tk = t; } };
     for (int j = tid; j < n_pos; j += kC2Threads) { S.acc[j][0] = 0.0f; S.acc[j][1] = 0.0f; }
     int nseg = 0;
     for (int p0 = 0; p0 < n_pos; p0 += ppart) {                // ranking passes over [p0, p0 + np)
@@ -317,6 +320,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
         const int nxd = 8 * (np - 1) + kC2Nd;                  // decimated samples the part's positions touch
         const int ntile = (nxd + kC2Threads - 1) / kC2Threads;
         decimate(48 * p0, ntile, p0);
+        mark(0);
         nseg = p0 + ntile * (kC2Threads / 8);
         // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one half of the taps); lane l starts 4 l taps
         // into its half and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
@@ -349,6 +353,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
             }
         }
         __syncthreads();                                       // the next part overwrites xd
+        mark(1);
     }
     // exclusive prefix of the segment energies (one warp)
     if (warp == 0) {
@@ -383,9 +388,13 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     }
     if (tid == 0) { (*S.best_c) = 0.0f; (*S.best_p) = -1; }
     __syncthreads();
+    mark(2);
     // ---------------- tier 2: exact evaluation of the leaders, 32 per round
+    // staging ring of the exact phases: as many (sample rows + template tile) buffers as the decimated window's storage holds, 3..6 --
+    // a tile takes ~1 000 cycles from L2 and is summed in ~300, so two tiles in flight starve the summing warps
+    const int nbuf = min(6, (chirp2_tiles(ppart) * kC2Threads) / (32 * kC2Row + 2 * 64));
     float (*rows)[32][kC2Row] = reinterpret_cast<float (*)[32][kC2Row]>(S.xd);
-    float (*tpl)[2][64] = reinterpret_cast<float (*)[2][64]>(S.xd + 3 * 32 * kC2Row);   // [3][cos, sin][64], 16-byte aligned
+    float (*tpl)[2][64] = reinterpret_cast<float (*)[2][64]>(S.xd + nbuf * 32 * kC2Row);   // [nbuf][cos, sin][64], 16-byte aligned
     float errmax = 0.0f;                                     // thread 0
     for (int nv = 0; nv < n_pos; nv += 32) {
         const int cnt = min(32, n_pos - nv);
@@ -402,31 +411,40 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                 cp_async16(smem_u32(&tpl[buf][lane >> 4][4 * (lane & 15)]), (lane < 16 ? tc : ts) + 64 * tile + 4 * (lane & 15));
             cp_async_commit();
         };
-        // The three ordered sums of a position stay in one lane (one shared load feeds all three; they are independent chains, so the
-        // warp issues back to back); warp 0 sums, every warp stages.  Three buffers: tile t + 2 travels while tile t is summed (a group
-        // is committed every iteration, empty ones past the end, so "all groups but the newest" always means "tile t has landed").
-        float ci = 0.0f, cq = 0.0f, se = 0.0f;
-        stage(0, 0);
-        stage(1, 1);
-        for (int tile = 0; tile < n / 64; ++tile) {
-            cp_async_wait_but_one();
+        // The three ordered sums of a position are three independent chains: warps 0 / 1 / 2 run ci / cq / se of the 32 candidates
+        // (a phase then lasts 24 000 x the 4-cycle add latency instead of 24 000 x 7.5 issue slots of one warp; the exact phases are
+        // 60 % of the kernel's time and run with the other warps idle); every warp stages.  Three buffers: tile t + 2 travels while tile t
+        // is summed (a group is committed every iteration, empty ones past the end, so "all groups but the newest" always means "tile t
+        // has landed").
+        float sum = 0.0f;
+        float* xch = &S.acc[0][0];                              // [32] cq (the ranking accumulators are dead)
+        for (int i = 0; i < nbuf - 1; ++i) stage(i, i);
+        for (int tile = 0, buf = 0; tile < n / 64; ++tile, buf = buf + 1 == nbuf ? 0 : buf + 1) {
+            cp_async_wait_but(nbuf - 2);
             __syncthreads();
-            if (tile + 2 < n / 64) stage(tile + 2, (tile + 2) % 3); else cp_async_commit();
-            if (warp == 0) {
-                const float* row = rows[tile % 3][lane];
+            if (tile + nbuf - 1 < n / 64) stage(tile + nbuf - 1, buf == 0 ? nbuf - 1 : buf - 1); else cp_async_commit();
+            if (warp < 3) {
+                const float* row = rows[buf][lane];
+                if (warp < 2) {
+                    const float* tv = tpl[buf][warp];
 #pragma unroll 4
-                for (int t = 0; t < 64; t += 4) {
-                    const float4 vc = *reinterpret_cast<const float4*>(&tpl[tile % 3][0][t]);
-                    const float4 vs = *reinterpret_cast<const float4*>(&tpl[tile % 3][1][t]);
-                    const float s0 = row[t], s1 = row[t + 1], s2 = row[t + 2], s3 = row[t + 3];
-                    ci = __fadd_rn(ci, __fmul_rn(s0, vc.x)); cq = __fadd_rn(cq, __fmul_rn(s0, vs.x)); se = __fadd_rn(se, __fmul_rn(s0, s0));
-                    ci = __fadd_rn(ci, __fmul_rn(s1, vc.y)); cq = __fadd_rn(cq, __fmul_rn(s1, vs.y)); se = __fadd_rn(se, __fmul_rn(s1, s1));
-                    ci = __fadd_rn(ci, __fmul_rn(s2, vc.z)); cq = __fadd_rn(cq, __fmul_rn(s2, vs.z)); se = __fadd_rn(se, __fmul_rn(s2, s2));
-                    ci = __fadd_rn(ci, __fmul_rn(s3, vc.w)); cq = __fadd_rn(cq, __fmul_rn(s3, vs.w)); se = __fadd_rn(se, __fmul_rn(s3, s3));
+                    for (int t = 0; t < 64; t += 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(tv + t);
+                        sum = __fadd_rn(sum, __fmul_rn(row[t], v.x));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 1], v.y));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 2], v.z));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 3], v.w));
+                    }
+                } else {
+#pragma unroll 16
+                    for (int t = 0; t < 64; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
                 }
             }
         }
-        if (warp == 0) { S.ex[lane] = chirp_norm(ci, cq, se, te); S.exe[lane] = se; }
+        if (warp == 1) xch[lane] = sum;
+        if (warp == 2) S.exe[lane] = sum;
+        __syncthreads();
+        if (warp == 0) S.ex[lane] = chirp_norm(sum, xch[lane], S.exe[lane], te);
         __syncthreads();
         if (tid == 0) {
             float bc = (*S.best_c);
@@ -455,6 +473,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     float best = (*S.best_c);
     int best_pos = (*S.best_p);
     __syncthreads();
+    mark(3);
     *corr_out = best;
     if (best_pos < 0 || best < __fmul_rn(threshold, 0.3f)) return -1;
     // ---------------- fine search (:600-612) and the parabola's neighbours (:615-625), two-tier as well.  The correlation magnitude is
@@ -484,9 +503,11 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
         }
         for (int i = tid; i < 128; i += kC2Threads) S.ex[i] = -1.0f;
         __syncthreads();
+        mark(4);
         if (tid == 0) S.ex[best_pos - q0] = best;              // exact from the coarse stage
+        constexpr int NB = 6;                                  // staging ring (see the coarse stage)
         float (*lin)[192] = reinterpret_cast<float (*)[192]>(S.xd);
-        float (*ftpl)[2][128] = reinterpret_cast<float (*)[2][128]>(S.xd + 3 * 192);   // [3][cos, sin][128]
+        float (*ftpl)[2][128] = reinterpret_cast<float (*)[2][128]>(S.xd + NB * 192);   // [NB][cos, sin][128]
         float ferr = 0.0f;                                     // thread 0
         for (int it = 0;; ++it) {
             if (tid == 0) {
@@ -528,32 +549,40 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                 }
                 cp_async_commit();
             };
-            float ci = 0.0f, cq = 0.0f, se = 0.0f;             // warp 0: position r0 + lane
-            stage(0, 0);
-            stage(1, 1);
+            float sum = 0.0f;                                  // warps 0 / 1 / 2: ci / cq / se of position r0 + lane
+            float* xch = &S.acc[0][0];                         // [64] cq, se
+            for (int i = 0; i < NB - 1; ++i) stage(i, i);
             for (int tile = 0; tile < (n + 127) / 128; ++tile) {
-                cp_async_wait_but_one();
+                cp_async_wait_but(NB - 2);
                 __syncthreads();
-                if (128 * (tile + 2) < n) stage(tile + 2, (tile + 2) % 3); else cp_async_commit();
-                if (warp == 0) {
-                    const float* row = lin[tile % 3] + lane;
+                if (128 * (tile + NB - 1) < n) stage(tile + NB - 1, (tile + NB - 1) % NB); else cp_async_commit();
+                if (warp < 3) {
+                    const float* row = lin[tile % NB] + lane;
                     const int tn = min(128, n - 128 * tile);
+                    if (warp < 2) {
+                        const float* tv = ftpl[tile % NB][warp];
 #pragma unroll 4
-                    for (int t = 0; t < tn; t += 4) {
-                        const float4 vc = *reinterpret_cast<const float4*>(&ftpl[tile % 3][0][t]);
-                        const float4 vs = *reinterpret_cast<const float4*>(&ftpl[tile % 3][1][t]);
-                        const float s0 = row[t], s1 = row[t + 1], s2 = row[t + 2], s3 = row[t + 3];
-                        ci = __fadd_rn(ci, __fmul_rn(s0, vc.x)); cq = __fadd_rn(cq, __fmul_rn(s0, vs.x)); se = __fadd_rn(se, __fmul_rn(s0, s0));
-                        ci = __fadd_rn(ci, __fmul_rn(s1, vc.y)); cq = __fadd_rn(cq, __fmul_rn(s1, vs.y)); se = __fadd_rn(se, __fmul_rn(s1, s1));
-                        ci = __fadd_rn(ci, __fmul_rn(s2, vc.z)); cq = __fadd_rn(cq, __fmul_rn(s2, vs.z)); se = __fadd_rn(se, __fmul_rn(s2, s2));
-                        ci = __fadd_rn(ci, __fmul_rn(s3, vc.w)); cq = __fadd_rn(cq, __fmul_rn(s3, vs.w)); se = __fadd_rn(se, __fmul_rn(s3, s3));
+                        for (int t = 0; t < tn; t += 4) {
+                            const float4 v = *reinterpret_cast<const float4*>(tv + t);
+                            sum = __fadd_rn(sum, __fmul_rn(row[t], v.x));
+                            sum = __fadd_rn(sum, __fmul_rn(row[t + 1], v.y));
+                            sum = __fadd_rn(sum, __fmul_rn(row[t + 2], v.z));
+                            sum = __fadd_rn(sum, __fmul_rn(row[t + 3], v.w));
+                        }
+                    } else {
+#pragma unroll 16
+                        for (int t = 0; t < tn; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
                     }
                 }
             }
-            if (warp == 0 && r0 + lane <= q1) S.ex[r0 + lane - q0] = chirp_norm(ci, cq, se, te);
+            if (warp == 1) xch[lane] = sum;
+            if (warp == 2) xch[32 + lane] = sum;
+            __syncthreads();
+            if (warp == 0 && r0 + lane <= q1) S.ex[r0 + lane - q0] = chirp_norm(sum, xch[lane], xch[32 + lane], te);
             __syncthreads();
         }
     }
+    mark(5);
     if (tid == 0) {
         for (int pos = fine_start; pos <= fine_end; ++pos) {
             const float c = S.ex[pos - q0];
@@ -685,6 +714,14 @@ cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t 
                                                                                          n_llr, llr_per_symbol, llr_stride, 0, 0);
     }
     return cudaGetLastError();
+}
+
+cudaError_t chirp_phase_cycles(unsigned long long* out /* [8] */) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemcpyFromSymbol(out, g_chirp2_clk, sizeof(g_chirp2_clk))) != cudaSuccess) return e;
+    const unsigned long long zero[8] = {};
+    return cudaMemcpyToSymbol(g_chirp2_clk, zero, sizeof(zero));
 }
 
 cudaError_t chirp_search_stats(unsigned long long* out /* [3] */) {

@@ -1493,6 +1493,14 @@ pu_status pu_ofdm_chirp_receive_batch(pu_ofdm* h, const float* samples, size_t B
     return PU_OK;
 }
 
+pu_status pu_chirp_phase_cycles(uint64_t cycles[8]) {
+    PU_REQUIRE(cycles, "pu_chirp_phase_cycles: NULL output");
+    unsigned long long v[8] = {};
+    PU_CUDA_TRY(pu::chirp_phase_cycles(v));
+    for (int i = 0; i < 8; ++i) cycles[i] = v[i];
+    return PU_OK;
+}
+
 pu_status pu_chirp_search_stats(uint64_t* searches, uint64_t* rounds, uint64_t* fine_runs) {
     unsigned long long v[3] = {0, 0, 0};
     PU_CUDA_TRY(pu::chirp_search_stats(v));

@@ -47,6 +47,14 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all groups but the newest
+__device__ __forceinline__ void cp_async_wait_but(int pending) {     // all groups but the newest `pending` (1..4)
+    switch (pending) {
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))

@@ -107,7 +107,8 @@ inline void chirp_dev_bind(ChirpDev& c, const float* dev_table) {
 }
 float channel_power_sum(const float* tx, size_t L);                                   // channel.cu: the two halves of pu_channel_noise_std
 float channel_noise_std_from_sum(float acc, size_t L, float snr_db, int convention);
-cudaError_t chirp_search_stats(unsigned long long* out);   // {searches, rounds} since the last call, then cleared
+cudaError_t chirp_search_stats(unsigned long long* out);
+cudaError_t chirp_phase_cycles(unsigned long long* out);   // [8] thread-0 cycles per phase of the two-tier search, then cleared   // {searches, rounds} since the last call, then cleared
 cudaError_t chirp_detect_launch(const ChirpDev& c, const float* samples, size_t B, size_t frame_stride, int L, float threshold, int sym_len,
                                 int4* out_info, float4* out_f, int* frame_start, int* frame_nsym, float* cfo_out, float* phase_out,
                                 int* n_llr, int llr_per_symbol, int llr_stride, cudaStream_t st);

@@ -48,12 +48,14 @@ for snr in (15.0, -5.0):
     del tx
     dem.chirp_receive_batch(x); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    capi.chirp_search_stats()
+    capi.chirp_search_stats(); capi.chirp_phase_cycles()
     e0.record(); out = dem.chirp_receive_batch(x); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     st = capi.chirp_search_stats()
     print("snr=%5.1f detectDualChirp+process B=%d L=%d ms=%.1f  %.1f kframes/s  detected=%.3f  searches=%d verify rounds=%d fine runs=%d" % (
         snr, B, L, ms, B / ms, out[2][:, 0].float().mean().item(), st[0], st[1], st[2]), flush=True)
+    cyc = capi.chirp_phase_cycles()
+    print("   cycles per search: decimate %d, estimates %d, rank %d, exact coarse %d, fine ranking %d, exact fine %d" % tuple(c // max(st[0], 1) for c in cyc[:6]))
     if R.available():
         xs = x[:2].cpu().numpy()
         t0 = time.perf_counter()
