@@ -370,6 +370,12 @@ PU_API pu_status pu_channel_apply_batch(pu_ctx* ctx, const pu_channel_config* cf
                                         const float* noise_std, const uint64_t* seed, size_t B, size_t L,
                                         float* rx, pu_memspace space, void* stream);
 
+/* The CFO injector of the reference's tools (tools/test_iwaveform.cpp:67-118): analytic signal through FFT / inverse FFT over the next
+ * power of two, rotation by the float phase recurrence, real part -- applied by the tools to the CLEAN transmit audio before the
+ * channel (:501-506), which is where pu_linksim_run applies it (pu_sweep_mode.cfo_hz, once per TX pool waveform).  Host function, in
+ * place; arrays shorter than 128 samples or |cfo| < 0.001 Hz are left untouched.  Bit-identical to the tool. */
+PU_API pu_status pu_tools_apply_cfo(float* samples, size_t n, float cfo_hz, float sample_rate);
+
 /* WattersonChannel::applyCFO (hf_channel.hpp:173-232), the channel's optional carrier-frequency-offset injector, applied IN PLACE to
  * every row of samples[B][stride] (L samples each) with cfo_hz[b] and a CFO phase of 0 at the start of the row: down-mix around
  * 1500 Hz, 48-tap running-sum lowpass, rotation, up-mix.  Rows with |cfo| <= 0.001 Hz or fewer than 256 samples are left untouched, as
@@ -452,6 +458,7 @@ typedef struct {
     float cost;                 /* relative cost of one frame for the partitioner; 0 = built-in estimate */
     uint32_t lead_samples;      /* silence in front of / behind every TX waveform (tools/test_iwaveform.cpp:396-459 surrounds its frames with */
     uint32_t tail_samples;      /* 1.5 s / 1 s of it): an acquired frame whose tail the channel's delay pushes out of the buffer loses its last symbol */
+    float cfo_hz;               /* the tools' --cfo: pu_tools_apply_cfo on every TX waveform (silence included) before the channel; 0 = none */
 } pu_sweep_mode;
 
 typedef struct {

@@ -478,6 +478,34 @@ int ref_watterson_cfo(float cfo_hz, const float* in, size_t n, float* out) {
     return 0;
 }
 
+// The tools' CFO injector (tools/test_iwaveform.cpp:67-118) lives in a program, not in the library: this is its loop around the
+// reference's own FFT class (the arithmetic that matters), so that the product's restatement of both (csrc/tools_cfo.cpp) is pinned to
+// compiled reference code.
+int ref_tools_apply_cfo(float* samples, size_t N, float cfo_hz, float sample_rate) {
+    if (N < 128 || std::abs(cfo_hz) < 0.001f) return 0;
+    size_t fft_size = 1;
+    while (fft_size < N) fft_size *= 2;
+    std::vector<Complex> freq(fft_size);
+    FFT fft(fft_size);
+    std::vector<Complex> time_in(fft_size, Complex(0, 0));
+    for (size_t i = 0; i < N; i++) time_in[i] = Complex(samples[i], 0);
+    fft.forward(time_in.data(), freq.data());
+    for (size_t i = 1; i < fft_size / 2; i++) freq[i] *= 2.0f;
+    for (size_t i = fft_size / 2 + 1; i < fft_size; i++) freq[i] = Complex(0, 0);
+    std::vector<Complex> analytic(fft_size);
+    fft.inverse(freq.data(), analytic.data());
+    float phase = 0.0f;
+    float phase_inc = 2.0f * static_cast<float>(M_PI) * cfo_hz / sample_rate;
+    for (size_t i = 0; i < N; i++) {
+        Complex rot(std::cos(phase), std::sin(phase));
+        samples[i] = std::real(analytic[i] * rot);
+        phase += phase_inc;
+        if (phase > M_PI) phase -= 2.0f * M_PI;
+        else if (phase < -M_PI) phase += 2.0f * M_PI;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------- single-carrier DPSK
 // DPSKModulator / DPSKDemodulator (src/psk/dpsk.hpp).  mod: 0 DBPSK(2), 1 DQPSK(4), 2 D8PSK(8)
 static DPSKConfig dpsk_cfg(int mod_order, int samples_per_symbol) {

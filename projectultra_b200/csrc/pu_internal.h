@@ -105,6 +105,7 @@ inline void chirp_dev_bind(ChirpDev& c, const float* dev_table) {
     c.dec = dev_table + 4 * static_cast<size_t>(c.n);
     c.lp = c.dec + 4 * static_cast<size_t>(c.nd);
 }
+void tools_apply_cfo(float* samples, size_t n, float cfo_hz, float sample_rate);     // tools_cfo.cpp
 float channel_power_sum(const float* tx, size_t L);                                   // channel.cu: the two halves of pu_channel_noise_std
 float channel_noise_std_from_sum(float acc, size_t L, float snr_db, int convention);
 cudaError_t chirp_search_stats(unsigned long long* out);

@@ -210,6 +210,10 @@ struct ModeEngine {
                 const float g = m->peak / mx;
                 for (float& v : w) v *= g;
             }
+            if (m->cfo_hz != 0.0f) {                          // the tools' --cfo: the clean audio, before the channel (test_iwaveform.cpp:501-506)
+                const float fs = is_ofdm ? static_cast<float>(m->ofdm.sample_rate) : is_dpsk ? m->dpsk.sample_rate : m->mcdpsk.sample_rate;
+                tools_apply_cfo(w.data(), w.size(), m->cfo_hz, fs);
+            }
             waves[i] = std::move(w);
         }
         const auto t2 = now();

@@ -298,6 +298,13 @@ def watterson_cfo(x, cfo_hz):
     return out
 
 
+def tools_apply_cfo(x, cfo_hz, sample_rate=48000.0):
+    """tools/test_iwaveform.cpp:67-118 around the compiled reference FFT (ref_harness.cpp: ref_tools_apply_cfo)."""
+    out = _f32(x).copy()
+    lib().ref_tools_apply_cfo(_p(out, C.c_float), C.c_size_t(len(out)), C.c_float(cfo_hz), C.c_float(sample_rate))
+    return out
+
+
 def dpsk_modulate(mod_order, sps, data, with_preamble=True):
     d = _u8(data)
     cap = 2_000_000

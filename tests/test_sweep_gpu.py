@@ -119,3 +119,24 @@ def test_acquired_modes_need_the_tools_silence_behind_the_frame(ctx):
     print("FER without / with silence:", fer[0].round(3).tolist(), fer[2400].round(3).tolist())
     assert (fer[0] > 0.7).all()                       # every frame short of a codeword
     assert (fer[2400] < 0.45).all() and fer[2400][2:].max() < 0.1      # MC-DPSK: the moderate channel's fades; OFDM_CHIRP R1/4 on good: clean
+
+
+def test_tuning_error_rows_of_the_regression_matrix(ctx):
+    """tests/regression_matrix.sh:139-243 runs the chirp-acquired waveforms with --cfo 0 / 30 / 50: the tools' FFT-Hilbert injector on the
+    clean TX audio (pu_sweep_mode.cfo_hz -> pu_tools_apply_cfo), estimated by the dual chirp and removed by the receiver.  The rows the
+    matrix expects to pass ("--snr 17 --cfo 30/50 awgn ofdm_chirp", "--snr 5 --cfo 30 awgn mc_dpsk") decode here too, and a tuning error
+    of 30 Hz without the chirp's estimate would not (the same frames through the genie-timed receiver lose every frame)."""
+    import refapi as R
+    from projectultra_b200 import capi
+    m1 = capi.ModemConfig.from_buffer_copy(bytes(R.config_m1(R.DQPSK, R.R1_2)))
+    mc = capi.mcdpsk_config(8, 2)
+    kw = dict(peak=0.5, lead_samples=480, tail_samples=2400)
+    modes = [capi.sweep_mode(capi.WF_OFDM_CHIRP, m1, capi.R1_2, 40, "awgn", 17, 1, 1, precision="fast", cfo_hz=c, **kw) for c in (0.0, 30.0, 50.0)]
+    modes += [capi.sweep_mode(capi.WF_MCDPSK_CHIRP, mc, capi.R1_2, 40, "awgn", 5, 1, 1, cfo_hz=c, **kw) for c in (0.0, 30.0, -30.0)]
+    modes += [capi.sweep_mode(capi.WF_MCDPSK, mc, capi.R1_2, 40, "awgn", 5, 1, 1, cfo_hz=c, peak=0.5) for c in (0.0, 30.0)]      # no chirp: no estimate
+    counters, _ = capi.Sweep(modes, trials_per_point=128, block_trials=64, pool=8).run(ctx)
+    fer = counters[:, 1].astype(np.float64) / counters[:, 0]
+    print("FER  OFDM_CHIRP 17 dB cfo 0/30/50:", fer[:3].round(3).tolist(), " MC-DPSK behind the chirp 5 dB cfo 0/30/-30:", fer[3:6].round(3).tolist(),
+          " MC-DPSK genie-timed cfo 0/30:", fer[6:].round(3).tolist())
+    assert (fer[:6] < 0.1).all()
+    assert fer[6] < 0.1 and fer[7] > 0.9

@@ -5,7 +5,7 @@
 //
 //   torchrun-style launch (RANK / WORLD_SIZE / LOCAL_RANK in the environment), or a single process:
 //     projectultra_b200/pu_sweep --table reduced --trials 16384 [--block 2048] [--manifest DIR] [--out rows.jsonl]
-//   tables: smoke (4 modes, seconds), reduced (one mode per waveform family and channel), config5 (105 modes x 40 SNR points)
+//   tables: smoke (4 modes, seconds), reduced (one mode per waveform family and channel + the chirp-acquired CFO rows of the regression matrix), config5 (105 modes x 40 SNR points)
 //
 // Rank 0 prints one JSON object per (mode, SNR point) with the Wilson 95 % interval of the FER, then one summary line with the
 // per-rank run times (scaling efficiency = mean / max of the ranks' times: ranks never wait for each other before the final sum).
@@ -108,6 +108,24 @@ std::vector<pu_sweep_mode> make_table(const std::string& name, bool fast) {
             t.push_back(dpsk_mode(PU_WF_DPSK, 1, PU_RATE_1_4, ch, -11, 2, 15));
         }
         t.push_back(ofdm_mode(PU_WF_OFDM_SC, 512, PU_MOD_DQPSK, PU_RATE_1_2, PU_CH_AWGN, 10, 3, 8, fast));   // Schmidl-Cox needs its 0.8 plateau
+        // the chirp-acquired rows of tests/regression_matrix.sh:139-243 with their tuning error (--cfo 0 / 30 / 50 / -30): the tools'
+        // FFT-Hilbert injector on the clean TX audio (pu_sweep_mode.cfo_hz)
+        for (float cfo : {0.0f, 30.0f, 50.0f}) {
+            pu_sweep_mode m = ofdm_mode(PU_WF_OFDM_CHIRP, 512, PU_MOD_DQPSK, PU_RATE_1_2, PU_CH_AWGN, 5, 1, 16, fast);   // "--snr 17 --cfo 30/50 awgn ofdm_chirp"
+            m.cfo_hz = cfo;
+            t.push_back(m);
+        }
+        for (unsigned ch : {PU_CH_AWGN, PU_CH_MODERATE, PU_CH_POOR})
+            for (float cfo : {0.0f, 30.0f, -30.0f}) {
+                pu_sweep_mode m = mcdpsk_mode(PU_WF_MCDPSK_CHIRP, 8, PU_RATE_1_2, ch, -6, 1, 16);                       // "--snr 5/0/15 --cfo 30 mc_dpsk"
+                m.cfo_hz = cfo;
+                t.push_back(m);
+            }
+        {
+            pu_sweep_mode m = ofdm_mode(PU_WF_OFDM_CHIRP, 512, PU_MOD_DQPSK, PU_RATE_1_4, PU_CH_MODERATE, 5, 1, 16, fast);   // "--snr 15 --cfo 30 moderate --rate r1_4"
+            m.cfo_hz = 30.0f;
+            t.push_back(m);
+        }
     } else {   // config5: all waveforms x 5 rates x 40 SNR points in 1 dB steps, the grid shifted per family (-8, -14, -28 dB upwards)
         const unsigned rates[] = {PU_RATE_1_4, PU_RATE_1_2, PU_RATE_2_3, PU_RATE_3_4, PU_RATE_5_6};
         for (unsigned r : rates) {
@@ -229,10 +247,10 @@ int main(int argc, char** argv) {
                 double lo, hi;
                 pu_wilson_interval(c[1], c[0], 1.96, &lo, &hi);
                 frames_all += c[0];
-                fprintf(out, "{\"mode\": %u, \"waveform\": \"%s\", \"modem\": \"%s\", \"code_rate\": \"%s\", \"channel\": \"%s\", \"snr_db\": %.2f, "
+                fprintf(out, "{\"mode\": %u, \"waveform\": \"%s\", \"modem\": \"%s\", \"code_rate\": \"%s\", \"channel\": \"%s\", \"cfo_hz\": %.1f, \"snr_db\": %.2f, "
                              "\"frames\": %llu, \"frame_errors\": %llu, \"fer\": %.6g, \"fer_ci95\": [%.6g, %.6g], \"ber\": %.6g, \"decode_fail\": %.6g, "
                              "\"avg_iters\": %.4g}\n",
-                        m, kWaveform[md.waveform], desc, kRate[md.code_rate], kChannel[md.channel], md.snr_first_db + s * md.snr_step_db,
+                        m, kWaveform[md.waveform], desc, kRate[md.code_rate], kChannel[md.channel], md.cfo_hz, md.snr_first_db + s * md.snr_step_db,
                         (unsigned long long)c[0], (unsigned long long)c[1], c[0] ? double(c[1]) / c[0] : 0.0, lo, hi, c[3] ? double(c[2]) / c[3] : 0.0,
                         c[0] ? double(c[4]) / c[0] : 0.0, c[0] ? double(c[5]) / c[0] : 0.0);
             }
