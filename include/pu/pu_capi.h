@@ -459,6 +459,9 @@ typedef struct {
     uint32_t lead_samples;      /* silence in front of / behind every TX waveform (tools/test_iwaveform.cpp:396-459 surrounds its frames with */
     uint32_t tail_samples;      /* 1.5 s / 1 s of it): an acquired frame whose tail the channel's delay pushes out of the buffer loses its last symbol */
     float cfo_hz;               /* the tools' --cfo: pu_tools_apply_cfo on every TX waveform (silence included) before the channel; 0 = none */
+    uint32_t fresh_payloads;    /* 1: a new payload per trial, encoded and modulated on the GPU (pu_*_tx_batch) inside the batch, as the tools do
+                                 * (tools/test_dpsk_snr.cpp:40-60, tools/test_mode_snr.cpp:40-60), instead of the pool of TX waveforms; the
+                                 * payload is a pure function of (base_seed, mode, SNR index, trial).  Not with the chirp waveforms or cfo_hz. */
 } pu_sweep_mode;
 
 typedef struct {

@@ -783,7 +783,7 @@ class SweepMode(C.Structure):
                 ("code_rate", C.c_uint32), ("payload_bytes", C.c_uint32), ("channel", C.c_uint32), ("n_snr", C.c_uint32),
                 ("snr_first_db", C.c_float), ("snr_step_db", C.c_float), ("peak", C.c_float), ("precision", C.c_uint32),
                 ("chunk", C.c_uint32), ("cost", C.c_float), ("lead_samples", C.c_uint32), ("tail_samples", C.c_uint32),
-                ("cfo_hz", C.c_float)]
+                ("cfo_hz", C.c_float), ("fresh_payloads", C.c_uint32)]
 
     @property
     def snr_points(self):
@@ -804,7 +804,7 @@ class SweepStats(C.Structure):
 
 
 def sweep_mode(waveform, cfg, code_rate, payload_bytes, channel, snr_first, snr_step, n_snr, peak=0.0, precision="exact", chunk=0, cost=0.0,
-               lead_samples=0, tail_samples=0, cfo_hz=0.0):
+               lead_samples=0, tail_samples=0, cfo_hz=0.0, fresh_payloads=False):
     m = SweepMode()
     m.waveform = waveform
     if isinstance(cfg, ModemConfig):
@@ -816,7 +816,7 @@ def sweep_mode(waveform, cfg, code_rate, payload_bytes, channel, snr_first, snr_
     m.code_rate, m.payload_bytes, m.channel, m.n_snr = int(code_rate), int(payload_bytes), CHANNELS[channel] if isinstance(channel, str) else int(channel), int(n_snr)
     m.snr_first_db, m.snr_step_db, m.peak = float(snr_first), float(snr_step), float(peak or 0.0)
     m.precision, m.chunk, m.cost = {"exact": 0, "fast": 1}[precision], int(chunk), float(cost)
-    m.lead_samples, m.tail_samples, m.cfo_hz = int(lead_samples), int(tail_samples), float(cfo_hz)
+    m.lead_samples, m.tail_samples, m.cfo_hz, m.fresh_payloads = int(lead_samples), int(tail_samples), float(cfo_hz), int(bool(fresh_payloads))
     return m
 
 

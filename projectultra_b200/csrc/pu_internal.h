@@ -71,7 +71,7 @@ struct pu_ctx {
     pu::Buffer cfo_mix;            // pu_channel_apply_cfo_batch: (cos, sin)(2 pi 1500 i / fs) per sample index, host libm
     size_t cfo_mix_len = 0;
     uint32_t cfo_mix_fs = 0;
-    pu::Buffer sweep[15];
+    pu::Buffer sweep[18];
     cudaEvent_t sweep_ev[2] = {nullptr, nullptr};
 };
 

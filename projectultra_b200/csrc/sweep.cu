@@ -119,6 +119,20 @@ uint64_t desc_key(const pu_sweep_desc* d, const SweepPlan& p) {      // FNV-1a o
     return h;
 }
 
+// fresh_payloads: byte i of frame b's payload = byte (i & 7) of splitmix64(seed[b] ^ kPayloadStream ^ (i >> 3) * golden ratio); rows are kb bytes,
+// zero past payload_bytes.  The frame seed also drives the channel; the stream constant keeps the two independent.
+__global__ void fresh_payload_kernel(uint8_t* __restrict__ pay, size_t kb, uint32_t payload_bytes, const uint64_t* __restrict__ seed, size_t B) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    const size_t words = (kb + 7) / 8;
+    if (i >= B * words) return;
+    const size_t b = i / words, w = i - b * words;
+    uint64_t z = (seed[b] ^ 0x5041594c4f414421ull) + 0x9e3779b97f4a7c15ull * (w + 1);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    for (size_t k = 0; k < 8 && 8 * w + k < kb; ++k) pay[b * kb + 8 * w + k] = 8 * w + k < payload_bytes ? static_cast<uint8_t>(z >> (8 * k)) : 0;
+}
+
 __global__ void mask_short_kernel(uint8_t* __restrict__ ok, const int32_t* __restrict__ n_llr, size_t B) {
     // no sync / fewer than one codeword of soft bits is a lost frame (tools/test_mode_snr.cpp:72-77): override the decoder's verdict
     const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -138,8 +152,10 @@ struct ModeEngine {
     size_t L = 0, kb = 0;
     uint32_t pool = 0;
     int convention = 0;
-    std::vector<float> noise_std;        // [n_snr][pool]
+    std::vector<float> noise_std;        // [n_snr][pool]; fresh payloads: [n_snr] SNR factors of pu_channel_noise_std_batch
     Buffer d_tx, d_payload;              // [pool][L] floats, [pool][kb] bytes
+    bool fresh = false;                  // pu_sweep_mode.fresh_payloads: TX inside the batch
+    size_t body_len = 0;                 // samples the transmitter writes per frame (L = lead + body + tail)
 
     ~ModeEngine() {
         if (ofdm) pu_ofdm_destroy(ofdm);
@@ -174,6 +190,20 @@ struct ModeEngine {
             if ((s = pu_mcdpsk_create(c, &m->mcdpsk, &mcd)) != PU_OK) return s;
         }
         const auto t1 = now();
+        fresh = m->fresh_payloads != 0;
+        if (fresh) {
+            PU_REQUIRE(m->waveform != PU_WF_OFDM_CHIRP && m->waveform != PU_WF_MCDPSK_CHIRP && m->cfo_hz == 0.0f,
+                       "pu_linksim_run: fresh_payloads is not available with the chirp waveforms or cfo_hz (the preamble pair and the tools' CFO injector are built on the host)");
+            if ((s = tx_batch(nullptr, 0, nullptr, 0, st)) != PU_OK) return s;      // queries body_len
+            L = m->lead_samples + body_len + m->tail_samples;
+            noise_std.resize(m->n_snr);
+            for (uint32_t si = 0; si < m->n_snr; ++si) {
+                const float snr = m->snr_first_db + si * m->snr_step_db;
+                noise_std[si] = convention == 0 ? std::pow(10.0f, -snr / 20.0f) : std::pow(10.0f, snr / 10.0f);   // pu_channel_noise_std's factors
+            }
+            if (trace) fprintf(stderr, "[engine] mode %u: fresh payloads, %zu samples per frame\n", mode_index, L);
+            return PU_OK;
+        }
         // TX pool on the host (the reference's modulators run per trial on the CPU too): payload -> LDPC encode -> modulate [-> chirp in front]
         std::vector<float> chirp;
         if (m->waveform == PU_WF_OFDM_CHIRP || m->waveform == PU_WF_MCDPSK_CHIRP) {
@@ -235,6 +265,18 @@ struct ModeEngine {
         if (trace) fprintf(stderr, "[engine] mode %u: decoder %.3f s, demodulator %.3f s, TX pool %.3f s, noise levels + upload %.3f s\n", mode_index, secs(t0, t_ldpc),
                            secs(t_ldpc, t1), secs(t1, t2), secs(t2, now()));
         return PU_OK;
+    }
+
+    // fresh payloads: LDPC encode + modulate B payloads on the device into out[B][L] at column lead_samples (the caller clears the rows when
+    // the mode has silence); B = 0 queries body_len
+    pu_status tx_batch(const uint8_t* d_pay, size_t B, float* out, size_t row, cudaStream_t st) {
+        float* at = out ? out + md->lead_samples : nullptr;
+        const unsigned wf = md->waveform;
+        if (wf == PU_WF_OFDM || wf == PU_WF_OFDM_SC)
+            return pu_ofdm_tx_batch(ofdm, ldpc, d_pay, kb, md->payload_bytes, B, wf == PU_WF_OFDM_SC ? 1 : 0, md->peak, at, row, &body_len, PU_MEM_DEVICE, st);
+        if (wf == PU_WF_DPSK || wf == PU_WF_DPSK_ACQ)
+            return pu_dpsk_tx_batch(dpsk, ldpc, d_pay, kb, md->payload_bytes, B, md->peak, at, row, &body_len, PU_MEM_DEVICE, st);
+        return pu_mcdpsk_tx_batch(mcd, ldpc, d_pay, kb, md->payload_bytes, B, md->peak, at, row, &body_len, PU_MEM_DEVICE, st);
     }
 
     // demodulate -> decode (device pointers, stream st); scratch: llr [B][648], n_llr [B], sync [B][8] (int/float)
@@ -484,7 +526,7 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
     // ---- batches in flight
     pu::Slot slots[2];
     pu::Buffer &d_rx = ctx->sweep[0], &d_llr = ctx->sweep[1], &d_info = ctx->sweep[2], &d_ok = ctx->sweep[3], &d_iters = ctx->sweep[4],
-               &d_nllr = ctx->sweep[5], &d_sync = ctx->sweep[6];
+               &d_nllr = ctx->sweep[5], &d_sync = ctx->sweep[6], &d_ftx = ctx->sweep[15], &d_fpay = ctx->sweep[16], &d_fstd = ctx->sweep[17];
     for (int i = 0; i < 2; ++i) {
         pu::Slot& sl = slots[i];
         sl.h_desc = &ctx->sweep[7 + 4 * i]; sl.d_desc = &ctx->sweep[8 + 4 * i]; sl.d_cnt = &ctx->sweep[9 + 4 * i]; sl.h_cnt = &ctx->sweep[10 + 4 * i];
@@ -538,11 +580,15 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
             fprintf(stderr, "[pu_linksim_run] rank %u mode %u waveform %u: engine set-up %.3f s (%zu samples per frame, pool %u)\n", d->rank, m,
                     d->modes[m].waveform, t_build, eng.L, eng.pool);
         const size_t L = eng.L, kb = eng.kb;
-        const size_t max_frames = std::max<size_t>(1, std::min<uint64_t>(p.batch_bytes / (L * sizeof(float)), (uint64_t(1) << 22)));
+        // (fresh payloads keep the clean TX batch next to the received one: half as many frames per batch)
+        const size_t max_frames = std::max<size_t>(1, std::min<uint64_t>(p.batch_bytes / (L * sizeof(float) * (eng.fresh ? 2 : 1)), (uint64_t(1) << 22)));
         const size_t cap = std::max<size_t>(max_frames, p.block);      // a unit is never split: the smallest batch is one unit
         if ((rs = d_rx.reserve(cap * L * sizeof(float))) != PU_OK || (rs = d_llr.reserve(cap * PU_LDPC_N * sizeof(float))) != PU_OK ||
             (rs = d_info.reserve(cap * kb)) != PU_OK || (rs = d_ok.reserve(cap)) != PU_OK || (rs = d_iters.reserve(cap * 4)) != PU_OK ||
             (rs = d_nllr.reserve(cap * 4)) != PU_OK || (rs = d_sync.reserve(cap * 12 * 4)) != PU_OK)
+            break;
+        if (eng.fresh && ((rs = d_ftx.reserve(cap * L * sizeof(float))) != PU_OK || (rs = d_fpay.reserve(cap * kb)) != PU_OK ||
+                          (rs = d_fstd.reserve(cap * sizeof(float))) != PU_OK))
             break;
         size_t next = 0;
         while (next < mine.size() && budget > 0 && rs == PU_OK) {
@@ -579,11 +625,16 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
                 uint32_t mm, s, nt; uint64_t t0;
                 pu::unit_decode(d, p, sl.units[i], &mm, &s, &t0, &nt);
                 const uint64_t hi = (p.base_seed << 40) ^ (static_cast<uint64_t>(m) << 56) ^ (static_cast<uint64_t>(s) << 32);
-                const float* stdrow = eng.noise_std.data() + static_cast<size_t>(s) * eng.pool;
+                const float* stdrow = eng.fresh ? nullptr : eng.noise_std.data() + static_cast<size_t>(s) * eng.pool;
                 for (uint32_t j = 0; j < nt; ++j, ++at) {
                     const uint64_t trial = t0 + j;
-                    const uint32_t tx = static_cast<uint32_t>(trial % eng.pool);
-                    h_tx[at] = tx; h_std[at] = stdrow[tx]; h_bin[at] = static_cast<uint32_t>(i); h_seed[at] = hi ^ trial;
+                    if (eng.fresh) {             // the batch is its own pool; the "std" column carries the SNR factor of pu_channel_noise_std_batch
+                        h_tx[at] = static_cast<uint32_t>(at); h_std[at] = eng.noise_std[s];
+                    } else {
+                        const uint32_t tx = static_cast<uint32_t>(trial % eng.pool);
+                        h_tx[at] = tx; h_std[at] = stdrow[tx];
+                    }
+                    h_bin[at] = static_cast<uint32_t>(i); h_seed[at] = hi ^ trial;
                 }
             }
             stt.fill_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_fill).count();
@@ -592,9 +643,26 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
                 PU_CUDA_TRY(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, st));
                 PU_CUDA_TRY(cudaMemsetAsync(sl.d_cnt->ptr, 0, nu * 6 * 8, st));
                 float* rx = static_cast<float*>(d_rx.ptr);
-                pu_status s2 = pu_channel_apply_batch(ctx, &eng.ch, static_cast<const float*>(eng.d_tx.ptr), L, eng.pool, reinterpret_cast<const uint32_t*>(dd),
-                                                      reinterpret_cast<const float*>(dd + off_std), reinterpret_cast<const uint64_t*>(dd + off_seed), B, L, rx,
-                                                      PU_MEM_DEVICE, st);
+                const float* tx_pool = static_cast<const float*>(eng.d_tx.ptr);
+                const float* stds = reinterpret_cast<const float*>(dd + off_std);
+                const uint8_t* payloads = static_cast<const uint8_t*>(eng.d_payload.ptr);
+                size_t pool_count = eng.pool;
+                pu_status s2;
+                if (eng.fresh) {                 // payload -> encode -> modulate for every frame of the batch, then its own noise level
+                    uint8_t* pay = static_cast<uint8_t*>(d_fpay.ptr);
+                    float* ftx = static_cast<float*>(d_ftx.ptr);
+                    const size_t words = B * ((kb + 7) / 8);
+                    pu::fresh_payload_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, st>>>(pay, kb, d->modes[m].payload_bytes,
+                                                                                                       reinterpret_cast<const uint64_t*>(dd + off_seed), B);
+                    ctx->launches.fetch_add(1);
+                    PU_CUDA_TRY(cudaGetLastError());
+                    if (d->modes[m].lead_samples || d->modes[m].tail_samples) PU_CUDA_TRY(cudaMemsetAsync(ftx, 0, B * L * sizeof(float), st));
+                    if ((s2 = eng.tx_batch(pay, B, ftx, L, st)) != PU_OK) return s2;
+                    if ((s2 = pu_channel_noise_std_batch(ctx, ftx, L, L, B, stds, eng.convention, static_cast<float*>(d_fstd.ptr), st)) != PU_OK) return s2;
+                    tx_pool = ftx; stds = static_cast<const float*>(d_fstd.ptr); payloads = pay; pool_count = B;
+                }
+                s2 = pu_channel_apply_batch(ctx, &eng.ch, tx_pool, L, pool_count, reinterpret_cast<const uint32_t*>(dd), stds,
+                                            reinterpret_cast<const uint64_t*>(dd + off_seed), B, L, rx, PU_MEM_DEVICE, st);
                 if (s2 != PU_OK) return s2;
                 uint8_t* info = static_cast<uint8_t*>(d_info.ptr);
                 uint8_t* ok = static_cast<uint8_t*>(d_ok.ptr);
@@ -602,7 +670,7 @@ pu_status pu_linksim_run(pu_ctx* ctx, const pu_sweep_desc* d, uint64_t* counters
                 s2 = eng.receive(rx, B, static_cast<float*>(d_llr.ptr), static_cast<int32_t*>(d_nllr.ptr), static_cast<int32_t*>(d_sync.ptr),
                                  reinterpret_cast<float*>(static_cast<int32_t*>(d_sync.ptr) + 4 * cap), info, ok, iters, st);
                 if (s2 != PU_OK) return s2;
-                s2 = pu_count_errors(ctx, info, kb, ok, iters, static_cast<const uint8_t*>(eng.d_payload.ptr), kb, reinterpret_cast<const uint32_t*>(dd),
+                s2 = pu_count_errors(ctx, info, kb, ok, iters, payloads, kb, reinterpret_cast<const uint32_t*>(dd),
                                      reinterpret_cast<const uint32_t*>(dd + off_bin), d->modes[m].payload_bytes, B, static_cast<uint64_t*>(sl.d_cnt->ptr), st);
                 if (s2 != PU_OK) return s2;
                 PU_CUDA_TRY(cudaMemcpyAsync(sl.h_cnt->ptr, sl.d_cnt->ptr, nu * 6 * 8, cudaMemcpyDeviceToHost, st));

@@ -140,3 +140,39 @@ def test_tuning_error_rows_of_the_regression_matrix(ctx):
           " MC-DPSK genie-timed cfo 0/30:", fer[6:].round(3).tolist())
     assert (fer[:6] < 0.1).all()
     assert fer[6] < 0.1 and fer[7] > 0.9
+
+
+def test_fresh_payload_per_trial_matches_the_pool_statistically(ctx):
+    """pu_sweep_mode.fresh_payloads: payload -> LDPC encode -> modulate on the GPU for every trial of a batch (tools/test_dpsk_snr.cpp:40-60,
+    tools/test_mode_snr.cpp:40-60 draw a new payload per trial) instead of the pool of host-built TX waveforms.  Same FER within the
+    binomial spread, a waterfall in every mode, reproducible, and two ranks sum to the single-rank table."""
+    import refapi as R
+    from projectultra_b200 import capi
+    m1 = capi.ModemConfig.from_buffer_copy(bytes(R.config_m1(R.DQPSK, R.R1_2)))
+    m1q = capi.ModemConfig.from_buffer_copy(bytes(R.config_m1(R.QAM16, R.R1_2)))
+
+    def table(fresh):
+        return [capi.sweep_mode(capi.WF_OFDM, m1, capi.R1_2, 40, "awgn", -1, 1.5, 4, precision="fast", fresh_payloads=fresh),
+                capi.sweep_mode(capi.WF_OFDM, m1q, capi.R1_2, 40, "good", 10, 4, 3, fresh_payloads=fresh),
+                capi.sweep_mode(capi.WF_DPSK, capi.dpsk_config(1, 384), capi.R1_4, 20, "awgn", -22, 2, 4, peak=0.5, fresh_payloads=fresh),
+                capi.sweep_mode(capi.WF_DPSK_ACQ, capi.dpsk_config(1, 384), capi.R1_4, 20, "poor", -20, 4, 3, peak=0.5, lead_samples=480, tail_samples=2400,
+                                fresh_payloads=fresh),
+                capi.sweep_mode(capi.WF_MCDPSK, capi.mcdpsk_config(8, 2), capi.R1_2, 40, "moderate", 0, 3, 4, peak=0.5, fresh_payloads=fresh)]
+
+    trials = 512
+    pool, _ = capi.Sweep(table(False), trials_per_point=trials, block_trials=128, pool=32).run(ctx)
+    fresh, st = capi.Sweep(table(True), trials_per_point=trials, block_trials=128, pool=32).run(ctx)
+    again, _ = capi.Sweep(table(True), trials_per_point=trials, block_trials=128, pool=32).run(ctx)
+    assert (fresh == again).all()
+    parts = [capi.Sweep(table(True), trials_per_point=trials, block_trials=128, pool=32, rank=r, world=2).run(ctx)[0] for r in range(2)]
+    assert (parts[0] + parts[1] == fresh).all()
+    assert (fresh[:, 0] == trials).all() and (fresh[:, 3] == pool[:, 3]).all()            # frames, payload bits compared
+    fp, ff = pool[:, 1] / trials, fresh[:, 1] / trials
+    print("FER pool :", fp.round(3).tolist())
+    print("FER fresh:", ff.round(3).tolist())
+    sigma = np.sqrt(np.maximum(fp * (1 - fp), 0.02) * 2 / trials)
+    assert (np.abs(fp - ff) < 5 * sigma + 0.02).all(), (fp - ff).tolist()
+    at = 0
+    for m in table(True):
+        assert ff[at] > ff[at + m.n_snr - 1] or ff[at] == 0.0                           # a waterfall (or already clean)
+        at += m.n_snr

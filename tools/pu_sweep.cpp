@@ -4,7 +4,7 @@
 // SNR, CFO) matrix of tests/regression_matrix.sh:139-243 over the trial loop of tools/test_iwaveform.cpp:597-806.
 //
 //   torchrun-style launch (RANK / WORLD_SIZE / LOCAL_RANK in the environment), or a single process:
-//     projectultra_b200/pu_sweep --table reduced --trials 16384 [--block 2048] [--manifest DIR] [--out rows.jsonl]
+//     projectultra_b200/pu_sweep --table reduced --trials 16384 [--block 2048] [--manifest DIR] [--out rows.jsonl] [--fresh]
 //   tables: smoke (4 modes, seconds), reduced (one mode per waveform family and channel + the chirp-acquired CFO rows of the regression matrix), config5 (105 modes x 40 SNR points)
 //
 // Rank 0 prints one JSON object per (mode, SNR point) with the Wilson 95 % interval of the FER, then one summary line with the
@@ -158,6 +158,7 @@ int env_int(const char* n, int d) { const char* v = getenv(n); return v ? atoi(v
 int main(int argc, char** argv) {
     const int rank = env_int("RANK", 0), world = env_int("WORLD_SIZE", 1), local = env_int("LOCAL_RANK", rank);
     const std::string table = arg(argc, argv, "--table", "smoke");
+    const bool fresh = flag(argc, argv, "--fresh");      // a new payload per trial (TX on the GPU inside the batch) wherever the waveform allows it
     const std::string manifest = arg(argc, argv, "--manifest", "");
     const std::string out_path = arg(argc, argv, "--out", "");
     const std::string rdv = arg(argc, argv, "--rendezvous", manifest.empty() ? "/tmp" : manifest.c_str());
@@ -202,6 +203,9 @@ int main(int argc, char** argv) {
     }
 
     std::vector<pu_sweep_mode> modes = make_table(table, fast);
+    if (fresh)
+        for (auto& m : modes)
+            if (m.waveform != PU_WF_OFDM_CHIRP && m.waveform != PU_WF_MCDPSK_CHIRP && m.cfo_hz == 0.0f) m.fresh_payloads = 1;
     pu_sweep_desc d{};
     d.modes = modes.data();
     d.n_modes = static_cast<uint32_t>(modes.size());
@@ -271,11 +275,11 @@ int main(int argc, char** argv) {
         per_rank += "]";
         fprintf(out, "{\"summary\": true, \"table\": \"%s\", \"modes\": %u, \"points\": %u, \"trials_per_point\": %llu, \"world\": %d, "
                      "\"units\": %llu, \"units_resumed\": %llu, \"frames_counted\": %llu, \"frames_run\": %llu, \"seconds_per_rank\": %s, "
-                     "\"seconds\": %.3f, \"frames_per_s\": %.6g, \"balance_efficiency\": %.4f, \"gpu_launches\": %llu, \"precision\": \"%s\", "
+                     "\"seconds\": %.3f, \"frames_per_s\": %.6g, \"balance_efficiency\": %.4f, \"gpu_launches\": %llu, \"precision\": \"%s\", \"fresh_payloads\": %s, "
                      "\"rank0_seconds\": {\"setup\": %.3f, \"wait\": %.3f, \"fill\": %.3f, \"enqueue\": %.3f}}\n",
                 table.c_str(), d.n_modes, n_points, (unsigned long long)d.trials_per_point, world, (unsigned long long)st.units_total,
                 (unsigned long long)st.units_resumed, (unsigned long long)frames_all, (unsigned long long)frames_run, per_rank.c_str(), tmax,
-                tmax > 0 ? frames_run / tmax : 0.0, tmax > 0 ? tsum / world / tmax : 1.0, (unsigned long long)launches, fast ? "fast" : "exact",
+                tmax > 0 ? frames_run / tmax : 0.0, tmax > 0 ? tsum / world / tmax : 1.0, (unsigned long long)launches, fast ? "fast" : "exact", fresh ? "true" : "false",
                 st.setup_seconds, st.wait_seconds, st.fill_seconds, st.enqueue_seconds);
         if (out != stdout) fclose(out);
     }
