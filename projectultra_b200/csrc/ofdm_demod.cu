@@ -1344,7 +1344,7 @@ static pu_status launch_ofdm(pu_ofdm* h, const float* d_samples, size_t B, size_
         const bool diff = pu::is_differential(p.cfg.modulation);
         using WK = void (*)(pu::OfdmDev, pu::WgTw, const float*, size_t, size_t, int, int, const float*, const float*, float*, size_t, int,
                             float*, float*, float*, unsigned, const int*, const int*, int);
-        const bool fastk = h->fast();     // PU_PRECISION_FAST: FMA butterflies + closed-form rotator (see the kernel's FAST parameter)
+        const bool fastk = h->fast();     // PU_PRECISION_FAST: FMA butterflies + MUFU rotator sin/cos (see the kernel's FAST parameter)
         const WK wk = fastk ? (p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1, true> : pu::ofdm_presynced_kernel<512, true, 2, true>)
                                              : (diff ? pu::ofdm_presynced_kernel<1024, true, 1, true> : pu::ofdm_presynced_kernel<1024, true, 2, true>))
                             : (p.nfft == 512 ? (diff ? pu::ofdm_presynced_kernel<512, true, 1> : pu::ofdm_presynced_kernel<512, true, 2>)

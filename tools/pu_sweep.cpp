@@ -117,7 +117,7 @@ std::vector<pu_sweep_mode> make_table(const std::string& name, bool fast) {
         }
         for (unsigned ch : {PU_CH_AWGN, PU_CH_MODERATE, PU_CH_POOR})
             for (float cfo : {0.0f, 30.0f, -30.0f}) {
-                pu_sweep_mode m = mcdpsk_mode(PU_WF_MCDPSK_CHIRP, 8, PU_RATE_1_2, ch, -6, 1, 16);                       // "--snr 5/0/15 --cfo 30 mc_dpsk"
+                pu_sweep_mode m = mcdpsk_mode(PU_WF_MCDPSK_CHIRP, 8, PU_RATE_1_2, ch, -6, 1, 22);                       // "--snr 5/0/10/15 --cfo 30 mc_dpsk"
                 m.cfo_hz = cfo;
                 t.push_back(m);
             }
