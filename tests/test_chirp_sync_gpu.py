@@ -109,6 +109,18 @@ def test_two_tier_search_equals_brute_force_search():
         slow = dem.chirp_receive_batch(x, llr_stride=700)
     finally:
         os.environ.pop("PU_CHIRP_SEARCH", None)
+    # the multi-round paths (a further 32 coarse positions / a further fine run whenever the stop rule does not hold) are rare by design:
+    # force them on every search and require the same outputs once more
+    os.environ["PU_CHIRP_GUARD"] = "1e30"
+    try:
+        capi.chirp_search_stats()
+        forced = dem.chirp_receive_batch(x[:48], llr_stride=700)
+        s2, r2, f2 = capi.chirp_search_stats()
+    finally:
+        os.environ.pop("PU_CHIRP_GUARD", None)
+    assert r2 >= 20 * s2 and f2 >= 3 * (s2 // 2), (s2, r2, f2)            # ~28 rounds of 32 = every coarse position; 4 runs = the whole fine range
+    for a, b in zip(forced[:4], fast[:4]):
+        assert (np.asarray(a).view(np.uint32) == np.asarray(b)[:48].view(np.uint32)).all()
     llr_f, n_f, info_f, val_f = fast[:4]
     llr_s, n_s, info_s, val_s = slow[:4]
     assert (info_f == info_s).all(), np.flatnonzero((info_f != info_s).any(axis=1))
