@@ -298,7 +298,19 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     cpus_before = bind_near_cpus(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: whatever NCCL prints while the communicator comes up (its "NCCL version ..." banner when
+        # the box exports NCCL_DEBUG) is sent to stderr by pointing fd 1 there for the duration of the first collective
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     ctx = capi.Context(local)
     if args.workload == "ldpc":
         return run_ldpc(args, ctx, dev, world, rank)
