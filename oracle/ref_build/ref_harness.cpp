@@ -481,27 +481,24 @@ int ref_watterson_cfo(float cfo_hz, const float* in, size_t n, float* out) {
 // The tools' CFO injector (tools/test_iwaveform.cpp:67-118) lives in a program, not in the library: this is its loop around the
 // reference's own FFT class (the arithmetic that matters), so that the product's restatement of both (csrc/tools_cfo.cpp) is pinned to
 // compiled reference code.
-int ref_tools_apply_cfo(float* samples, size_t N, float cfo_hz, float sample_rate) {
-    if (N < 128 || std::abs(cfo_hz) < 0.001f) return 0;
-    size_t fft_size = 1;
-    while (fft_size < N) fft_size *= 2;
-    std::vector<Complex> freq(fft_size);
-    FFT fft(fft_size);
-    std::vector<Complex> time_in(fft_size, Complex(0, 0));
-    for (size_t i = 0; i < N; i++) time_in[i] = Complex(samples[i], 0);
-    fft.forward(time_in.data(), freq.data());
-    for (size_t i = 1; i < fft_size / 2; i++) freq[i] *= 2.0f;
-    for (size_t i = fft_size / 2 + 1; i < fft_size; i++) freq[i] = Complex(0, 0);
-    std::vector<Complex> analytic(fft_size);
-    fft.inverse(freq.data(), analytic.data());
-    float phase = 0.0f;
-    float phase_inc = 2.0f * static_cast<float>(M_PI) * cfo_hz / sample_rate;
-    for (size_t i = 0; i < N; i++) {
-        Complex rot(std::cos(phase), std::sin(phase));
-        samples[i] = std::real(analytic[i] * rot);
-        phase += phase_inc;
-        if (phase > M_PI) phase -= 2.0f * M_PI;
-        else if (phase < -M_PI) phase += 2.0f * M_PI;
+int ref_tools_apply_cfo(float* x, size_t n, float cfo_hz, float fs) {
+    if (n < 128 || std::abs(cfo_hz) < 0.001f) return 0;                    // the tool's early return
+    size_t m = 1;
+    while (m < n) m *= 2;                                                   // next power of two
+    FFT engine(m);                                                          // the reference's FFT class does both transforms
+    std::vector<Complex> t(m, Complex(0, 0)), f(m), z(m);
+    for (size_t i = 0; i < n; ++i) t[i] = Complex(x[i], 0);
+    engine.forward(t.data(), f.data());
+    for (size_t k = 1; k < m / 2; ++k) f[k] *= 2.0f;                        // one-sided spectrum: analytic signal
+    std::fill(f.begin() + m / 2 + 1, f.end(), Complex(0, 0));
+    engine.inverse(f.data(), z.data());
+    const float step = 2.0f * static_cast<float>(M_PI) * cfo_hz / fs;
+    float ph = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+        x[i] = std::real(z[i] * Complex(std::cos(ph), std::sin(ph)));
+        ph += step;
+        if (ph > M_PI) ph -= 2.0f * M_PI;                                   // float phase, double constants: as the tool wraps it
+        else if (ph < -M_PI) ph += 2.0f * M_PI;
     }
     return 0;
 }
