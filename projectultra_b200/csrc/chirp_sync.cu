@@ -210,7 +210,7 @@ struct Chirp2Smem {
     float* lp;                        // [48] low-pass taps
     float* exq; float* exe; float* ex;   // [128] each
     int* cand;                        // [32]
-    float* best_c; int* best_p; int* go; float* best_se;
+    float* best_c; int* best_p; int* go; float* best_se; int* nranked;
 };
 __host__ __device__ inline int chirp2_tiles(int ppart) {       // never less than the exact phases need: rows[3][32][65] + 3 template tiles
     const int t = (8 * ppart + kC2Nd + kC2Threads - 1) / kC2Threads, floor_t = (3 * 32 * kC2Row + 3 * 2 * 64 + kC2Threads - 1) / kC2Threads;
@@ -220,7 +220,7 @@ __host__ __device__ inline int chirp2_rank_floats(int maxpos) { return (2 * maxp
 __host__ __device__ inline int chirp2_seg_floats(int maxpos) { return (maxpos + kC2N / 48 + 2 * (kC2Threads / 8) + 8 + 3) & ~3; }
 __host__ __device__ inline size_t chirp2_smem_floats(int maxpos, int ppart) {
     return static_cast<size_t>(chirp2_tiles(ppart)) * kC2Threads + ((kC2TileIn + 2 + 3) & ~3) + chirp2_rank_floats(maxpos) + chirp2_seg_floats(maxpos) +
-           48 + 3 * 128 + 32 + 4;
+           48 + 3 * 128 + 32 + 8;
 }
 __device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos, int ppart) {
     Chirp2Smem S;
@@ -238,6 +238,7 @@ __device__ inline Chirp2Smem chirp2_carve(unsigned char* base, int maxpos, int p
     S.ex = p; p += 128;
     S.cand = reinterpret_cast<int*>(p); p += 32;
     S.best_c = p; S.best_p = reinterpret_cast<int*>(p + 1); S.go = reinterpret_cast<int*>(p + 2); S.best_se = p + 3;
+    S.nranked = reinterpret_cast<int*>(p + 4);
     return S;
 }
 // positions per ranking pass (a multiple of 8): the fewest passes that keep three frames on an SM, else the smallest footprint of <= 4 passes
@@ -377,14 +378,73 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
         S.a[m] = denom < 1e-10f ? 0.0f : sqrtf(S.acc[m][0] * S.acc[m][0] + S.acc[m][1] * S.acc[m][1]) / denom;
     }
     __syncthreads();
-    for (int m = tid; m < n_pos; m += kC2Threads) {          // rank by counting: larger estimate first, ties by position
-        const float am = S.a[m];
-        int rk = 0;
-        for (int o = 0; o < n_pos; ++o) {
-            const float ao = S.a[o];
-            rk += (ao > am || (ao == am && o < m)) ? 1 : 0;
+    // Ranking: order[r] = the position with the r-th largest estimate (ties by position).  Only the leaders are ever needed unless the stop
+    // rule fails, so the full rank-by-counting (n_pos^2 comparisons: 9 % of the kernel's instructions) is replaced by a selection: a
+    // 4 096-bin histogram of the estimates' bit patterns (they are >= 0, so the patterns order like the values) finds the bin that holds
+    // the 32nd largest, the positions from that bin upwards are compacted and ranked among themselves.  A later round that reaches
+    // beyond them ranks everything (rank_all).
+    auto rank_all = [&]() {
+        for (int m = tid; m < n_pos; m += kC2Threads) {
+            const float am = S.a[m];
+            int rk = 0;
+            for (int o = 0; o < n_pos; ++o) {
+                const float ao = S.a[o];
+                rk += (ao > am || (ao == am && o < m)) ? 1 : 0;
+            }
+            S.order[rk] = static_cast<unsigned short>(m);
         }
-        S.order[rk] = static_cast<unsigned short>(m);
+        __syncthreads();
+        if (tid == 0) *S.nranked = n_pos;
+        __syncthreads();
+    };
+    {
+        unsigned* hist = reinterpret_cast<unsigned*>(S.xd);                           // the decimated window is dead
+        unsigned short* list = reinterpret_cast<unsigned short*>(S.xd + 4096);        // (xd holds >= 6 656 floats)
+        for (int i = tid; i < 4096; i += kC2Threads) hist[i] = 0;
+        if (tid == 0) *S.nranked = 0;
+        __syncthreads();
+        for (int m = tid; m < n_pos; m += kC2Threads) atomicAdd(&hist[__float_as_uint(S.a[m]) >> 19], 1u);
+        __syncthreads();
+        if (warp == 0) {                                       // lane l owns bins [128 l, 128 l + 128)
+            unsigned own = 0;
+            for (int b = 0; b < 128; ++b) own += hist[128 * lane + b];
+            unsigned suf = own;                                // positions in this lane's bins and above
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += u;
+            }
+            const unsigned target = static_cast<unsigned>(min(33, n_pos));   // 33: the stop rule looks at the first position not verified
+            const unsigned has = __ballot_sync(0xffffffffu, suf >= target);
+            const int top = 31 - __clz(static_cast<int>(has));             // the highest lane whose suffix still reaches the target
+            if (lane == top) {
+                unsigned run = suf - own;
+                int b = 127;
+                for (; b > 0; --b) {
+                    run += hist[128 * lane + b];
+                    if (run >= target) break;
+                }
+                *S.go = 128 * lane + b;
+            }
+        }
+        __syncthreads();
+        const unsigned bstar = static_cast<unsigned>(*S.go);
+        for (int m = tid; m < n_pos; m += kC2Threads)
+            if ((__float_as_uint(S.a[m]) >> 19) >= bstar) list[atomicAdd(S.nranked, 1)] = static_cast<unsigned short>(m);
+        __syncthreads();
+        const int cntl = *S.nranked;
+        for (int i = tid; i < cntl; i += kC2Threads) {
+            const int m = list[i];
+            const float am = S.a[m];
+            int rk = 0;
+            for (int j = 0; j < cntl; ++j) {
+                const int o = list[j];
+                const float ao = S.a[o];
+                rk += (ao > am || (ao == am && o < m)) ? 1 : 0;
+            }
+            S.order[rk] = static_cast<unsigned short>(m);
+        }
+        __syncthreads();
     }
     if (tid == 0) { (*S.best_c) = 0.0f; (*S.best_p) = -1; }
     __syncthreads();
@@ -398,6 +458,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     float errmax = 0.0f;                                     // thread 0
     for (int nv = 0; nv < n_pos; nv += 32) {
         const int cnt = min(32, n_pos - nv);
+        if (nv + cnt > *S.nranked) rank_all();                 // (uniform: shared value)
         if (tid < 32) S.cand[tid] = tid < cnt ? 48 * static_cast<int>(S.order[nv + tid]) : 0;
         __syncthreads();
         auto stage = [&](int tile, int buf) {
@@ -459,7 +520,8 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
             (*S.best_p) = bp;
             int go = 0;
             if (nv + 32 < n_pos) {
-                const float next = S.a[S.order[nv + 32]];     // the largest unverified estimate
+                // the largest unverified estimate (or, past the ranked leaders, an upper bound of it: the smallest ranked one)
+                const float next = S.a[S.order[min(nv + 32, *S.nranked - 1)]];
                 go = !(next == 0.0f || next + guard * errmax + 1e-6f < bc);
             }
             (*S.go) = go;
