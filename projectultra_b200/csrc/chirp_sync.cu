@@ -185,8 +185,8 @@ __device__ int chirp_detect_template(ChirpShared& S, ChirpWarpBuf* WB, const flo
 //           sum_i x[p+i] t[i] ~ 6 sum_j xf[p+6j] t[6j] -- and every coarse position (48 samples = 8 decimated ones apart) gets a
 //           4 000-tap FMA correlation from shared memory, in any summation order; energies come from 48-sample partial sums.
 //           Measured against the ordered sums: rms error 1-2 % of the correlation floor of a noise-only window.
-//   tier 2  the 32 best-ranked positions are evaluated exactly (lane = position, its three sums three independent chains), the result is the first maximum among them, and the search ends when every unverified position
-//           is out of reach:  estimate + 4 x (largest |exact - estimate| seen) < best exact value.  Otherwise the next 32 are
+//   tier 2  the 16 best-ranked positions are evaluated exactly (lane = position, its three sums three independent chains), the result is the first maximum among them, and the search ends when every unverified position
+//           is out of reach:  estimate + 4 x (largest |exact - estimate| seen) < best exact value.  Otherwise the next 16 are
 //           verified, down to all of them -- the result is then the brute-force one by construction.
 // The fine search (+-48 positions, parabolic neighbours included) stays exact: 99 positions in four warps over one linear tile.
 // tests/test_chirp_sync_gpu.py runs both forms on the same frames (PU_CHIRP_SEARCH=exact selects the brute-force kernel).
@@ -195,13 +195,15 @@ constexpr int kC2Threads = 256, kC2Warps = kC2Threads / 32;
 constexpr int kC2N = 24000, kC2Nd = kC2N / kRankD;     // the 48 kHz chirp: 24 000 taps, 4 000 decimated
 constexpr int kC2MaxPos = 3000;                         // coarse positions per window the shared-memory budget of one SM allows
 constexpr int kC2TileIn = kC2Threads * kRankD + kRankNT - 1;
-constexpr int kC2Row = 65;                              // verify tile: 64 taps per row, odd stride
+constexpr int kC2Cand = 16, kC2VTaps = 128;             // exact coarse stage: leaders per round, taps per staged tile
+constexpr int kC2Row = kC2VTaps + 1;                    // odd row stride: lane = candidate reads conflict-free
+constexpr int kC2VBuf = kC2Cand * kC2Row + 2 * kC2VTaps;   // floats per staging buffer: sample rows + template tile (cos, sin)
 // Shared memory of one frame, carved from the dynamic allocation for the window's coarse-position budget `maxpos` and the number of
 // positions ranked per pass `ppart` (host: chirp2_layout): the decimated window is the large item, so long windows are ranked in
 // several passes over a buffer that holds one part (+ the 4 000-tap overhang) -- 65 KB at 66 000 samples in one pass, 73 KB at
 // 86 600 in two: three frames per SM either way.
 struct Chirp2Smem {
-    float* xd;                        // tier 1: decimated part of the window, whole tiles.  tier 2: rows[nbuf][32][kC2Row] + template tiles.  fine: lin[6][192] + template tiles
+    float* xd;                        // tier 1: decimated part of the window, whole tiles.  tier 2: rows[nbuf][16][kC2Row] + template tiles.  fine: lin[6][192] + template tiles
     float* tile;                      // low-pass input tile
     float (*acc)[2];
     float* a;                         // estimate of the normalised correlation
@@ -212,8 +214,8 @@ struct Chirp2Smem {
     int* cand;                        // [32]
     float* best_c; int* best_p; int* go; float* best_se; int* nranked;
 };
-__host__ __device__ inline int chirp2_tiles(int ppart) {       // never less than the exact phases need: rows[3][32][65] + 3 template tiles
-    const int t = (8 * ppart + kC2Nd + kC2Threads - 1) / kC2Threads, floor_t = (3 * 32 * kC2Row + 3 * 2 * 64 + kC2Threads - 1) / kC2Threads;
+__host__ __device__ inline int chirp2_tiles(int ppart) {       // never less than the exact phases need: three staging buffers
+    const int t = (8 * ppart + kC2Nd + kC2Threads - 1) / kC2Threads, floor_t = (3 * kC2VBuf + kC2Threads - 1) / kC2Threads;
     return t > floor_t ? t : floor_t;
 }
 __host__ __device__ inline int chirp2_rank_floats(int maxpos) { return (2 * maxpos + maxpos + (maxpos + 1) / 2 + 3) & ~3; }
@@ -381,7 +383,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     // Ranking: order[r] = the position with the r-th largest estimate (ties by position).  Only the leaders are ever needed unless the stop
     // rule fails, so the full rank-by-counting (n_pos^2 comparisons: 9 % of the kernel's instructions) is replaced by a selection: a
     // 4 096-bin histogram of the estimates' bit patterns (they are >= 0, so the patterns order like the values) finds the bin that holds
-    // the 32nd largest, the positions from that bin upwards are compacted and ranked among themselves.  A later round that reaches
+    // the 17th largest, the positions from that bin upwards are compacted and ranked among themselves.  A later round that reaches
     // beyond them ranks everything (rank_all).
     auto rank_all = [&]() {
         for (int m = tid; m < n_pos; m += kC2Threads) {
@@ -414,7 +416,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                 const unsigned u = __shfl_down_sync(0xffffffffu, suf, o);
                 if (lane + o < 32) suf += u;
             }
-            const unsigned target = static_cast<unsigned>(min(33, n_pos));   // 33: the stop rule looks at the first position not verified
+            const unsigned target = static_cast<unsigned>(min(kC2Cand + 1, n_pos));   // + 1: the stop rule looks at the first position not verified
             const unsigned has = __ballot_sync(0xffffffffu, suf >= target);
             const int top = 31 - __clz(static_cast<int>(has));             // the highest lane whose suffix still reaches the target
             if (lane == top) {
@@ -449,63 +451,64 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     if (tid == 0) { (*S.best_c) = 0.0f; (*S.best_p) = -1; }
     __syncthreads();
     mark(2);
-    // ---------------- tier 2: exact evaluation of the leaders, 32 per round
-    // staging ring of the exact phases: as many (sample rows + template tile) buffers as the decimated window's storage holds, 3..6 --
-    // a tile takes ~1 000 cycles from L2 and is summed in ~300, so two tiles in flight starve the summing warps
-    const int nbuf = min(6, (chirp2_tiles(ppart) * kC2Threads) / (32 * kC2Row + 2 * 64));
-    float (*rows)[32][kC2Row] = reinterpret_cast<float (*)[32][kC2Row]>(S.xd);
-    float (*tpl)[2][64] = reinterpret_cast<float (*)[2][64]>(S.xd + nbuf * 32 * kC2Row);   // [nbuf][cos, sin][64], 16-byte aligned
+    // ---------------- tier 2: exact evaluation of the leaders, 16 per round.
+    // Lane = candidate: warp 0 runs the ci chains in lanes 0..15 and the cq chains of the same candidates in lanes 16..31 (the two halves
+    // read the same sample word: a broadcast), warp 1 the energy chains; every warp stages.  Tiles of 128 taps: 16 sample rows (odd stride)
+    // + the template tile travel through a cp.async ring of as many buffers as the decimated window's storage holds (3..6); a group is
+    // committed every iteration, empty ones past the end, so "all groups but the newest nbuf - 2" always means "tile t has landed".
+    // (v48 breakdown per 64-tap tile of 32 candidates: ~250 cycles barrier + wait, ~730 staging -- 64 four-byte LDGSTS, the rows of scattered
+    // candidates have no common alignment --, ~820 summing under contention: half the rows and twice the taps per tile halve the first two.)
+    const int nbuf = min(6, (chirp2_tiles(ppart) * kC2Threads) / kC2VBuf);
+    float (*rows)[kC2Cand][kC2Row] = reinterpret_cast<float (*)[kC2Cand][kC2Row]>(S.xd);
+    float (*tpl)[2][kC2VTaps] = reinterpret_cast<float (*)[2][kC2VTaps]>(S.xd + ((nbuf * kC2Cand * kC2Row + 3) & ~3));   // 16-byte aligned
+    constexpr int ntv = (n + kC2VTaps - 1) / kC2VTaps;
     float errmax = 0.0f;                                     // thread 0
-    for (int nv = 0; nv < n_pos; nv += 32) {
-        const int cnt = min(32, n_pos - nv);
+    for (int nv = 0; nv < n_pos; nv += kC2Cand) {
+        const int cnt = min(kC2Cand, n_pos - nv);
         if (nv + cnt > *S.nranked) rank_all();                 // (uniform: shared value)
-        if (tid < 32) S.cand[tid] = tid < cnt ? 48 * static_cast<int>(S.order[nv + tid]) : 0;
+        if (tid < kC2Cand) S.cand[tid] = tid < cnt ? 48 * static_cast<int>(S.order[nv + tid]) : 0;
         __syncthreads();
         auto stage = [&](int tile, int buf) {
-            for (int r = warp; r < 32; r += kC2Warps) {
-                const float* src = xw + S.cand[r] + 64 * tile;
+            for (int r = warp; r < kC2Cand; r += kC2Warps) {
+                const float* src = xw + S.cand[r] + kC2VTaps * tile;
                 const uint32_t dst = smem_u32(&rows[buf][r][0]);
-                cp_async4(dst + 4 * lane, src + lane);
-                cp_async4(dst + 4 * (lane + 32), src + lane + 32);
+#pragma unroll
+                for (int q = 0; q < kC2VTaps / 32; ++q)
+                    if (kC2VTaps * tile + 32 * q + lane < n) cp_async4(dst + 4 * (32 * q + lane), src + 32 * q + lane);
             }
-            if (warp == kC2Warps - 1)                         // the template tile travels with the samples (192 KB per chirp: L2, not L1)
-                cp_async16(smem_u32(&tpl[buf][lane >> 4][4 * (lane & 15)]), (lane < 16 ? tc : ts) + 64 * tile + 4 * (lane & 15));
+            if (warp >= kC2Warps - 2 && kC2VTaps * tile + 4 * lane < n)     // the template tile travels with the samples (192 KB per chirp: L2, not L1)
+                cp_async16(smem_u32(&tpl[buf][warp - (kC2Warps - 2)][4 * lane]), (warp == kC2Warps - 2 ? tc : ts) + kC2VTaps * tile + 4 * lane);
             cp_async_commit();
         };
-        // The three ordered sums of a position are three independent chains: warps 0 / 1 / 2 run ci / cq / se of the 32 candidates
-        // (a phase then lasts 24 000 x the 4-cycle add latency instead of 24 000 x 7.5 issue slots of one warp; the exact phases are
-        // 60 % of the kernel's time and run with the other warps idle); every warp stages.  Three buffers: tile t + 2 travels while tile t
-        // is summed (a group is committed every iteration, empty ones past the end, so "all groups but the newest" always means "tile t
-        // has landed").
         float sum = 0.0f;
-        float* xch = &S.acc[0][0];                              // [32] cq (the ranking accumulators are dead)
+        float* xch = &S.acc[0][0];                              // [16] cq (the ranking accumulators are dead)
         for (int i = 0; i < nbuf - 1; ++i) stage(i, i);
-        for (int tile = 0, buf = 0; tile < n / 64; ++tile, buf = buf + 1 == nbuf ? 0 : buf + 1) {
+        for (int tile = 0, buf = 0; tile < ntv; ++tile, buf = buf + 1 == nbuf ? 0 : buf + 1) {
             cp_async_wait_but(nbuf - 2);
             __syncthreads();
-            if (tile + nbuf - 1 < n / 64) stage(tile + nbuf - 1, buf == 0 ? nbuf - 1 : buf - 1); else cp_async_commit();
-            if (warp < 3) {
-                const float* row = rows[buf][lane];
-                if (warp < 2) {
-                    const float* tv = tpl[buf][warp];
+            if (tile + nbuf - 1 < ntv) stage(tile + nbuf - 1, buf == 0 ? nbuf - 1 : buf - 1); else cp_async_commit();
+            const int tn = min(kC2VTaps, n - kC2VTaps * tile);
+            if (warp == 0) {
+                const float* row = rows[buf][lane & (kC2Cand - 1)];
+                const float* tv = tpl[buf][lane >> 4];
 #pragma unroll 4
-                    for (int t = 0; t < 64; t += 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(tv + t);
-                        sum = __fadd_rn(sum, __fmul_rn(row[t], v.x));
-                        sum = __fadd_rn(sum, __fmul_rn(row[t + 1], v.y));
-                        sum = __fadd_rn(sum, __fmul_rn(row[t + 2], v.z));
-                        sum = __fadd_rn(sum, __fmul_rn(row[t + 3], v.w));
-                    }
-                } else {
-#pragma unroll 16
-                    for (int t = 0; t < 64; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
+                for (int t = 0; t < tn; t += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(tv + t);
+                    sum = __fadd_rn(sum, __fmul_rn(row[t], v.x));
+                    sum = __fadd_rn(sum, __fmul_rn(row[t + 1], v.y));
+                    sum = __fadd_rn(sum, __fmul_rn(row[t + 2], v.z));
+                    sum = __fadd_rn(sum, __fmul_rn(row[t + 3], v.w));
                 }
+            } else if (warp == 1) {
+                const float* row = rows[buf][lane & (kC2Cand - 1)];
+#pragma unroll 16
+                for (int t = 0; t < tn; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
             }
         }
-        if (warp == 1) xch[lane] = sum;
-        if (warp == 2) S.exe[lane] = sum;
+        if (warp == 0 && lane >= kC2Cand) xch[lane - kC2Cand] = sum;
+        if (warp == 1 && lane < kC2Cand) S.exe[lane] = sum;
         __syncthreads();
-        if (warp == 0) S.ex[lane] = chirp_norm(sum, xch[lane], S.exe[lane], te);
+        if (warp == 0 && lane < kC2Cand) S.ex[lane] = chirp_norm(sum, xch[lane], S.exe[lane], te);
         __syncthreads();
         if (tid == 0) {
             float bc = (*S.best_c);
@@ -519,16 +522,16 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
             (*S.best_c) = bc;
             (*S.best_p) = bp;
             int go = 0;
-            if (nv + 32 < n_pos) {
+            if (nv + kC2Cand < n_pos) {
                 // the largest unverified estimate (or, past the ranked leaders, an upper bound of it: the smallest ranked one)
-                const float next = S.a[S.order[min(nv + 32, *S.nranked - 1)]];
+                const float next = S.a[S.order[min(nv + kC2Cand, *S.nranked - 1)]];
                 go = !(next == 0.0f || next + guard * errmax + 1e-6f < bc);
             }
             (*S.go) = go;
         }
         __syncthreads();
         if (!(*S.go)) {
-            if (tid == 0) { atomicAdd(&g_chirp2_stats[0], 1ull); atomicAdd(&g_chirp2_stats[1], static_cast<unsigned long long>(nv / 32 + 1)); }
+            if (tid == 0) { atomicAdd(&g_chirp2_stats[0], 1ull); atomicAdd(&g_chirp2_stats[1], static_cast<unsigned long long>(nv / kC2Cand + 1)); }
             break;
         }
     }
