@@ -187,7 +187,7 @@ PU_API pu_status pu_ofdm_chirp_receive_batch(pu_ofdm* h, const float* samples, s
 PU_API pu_status pu_chirp_generate(float sample_rate, float tx_cfo_hz, float* out, size_t out_cap, size_t* out_len);
 /* Diagnostics of the two-tier chirp search (csrc/chirp_sync.cu) on the current device since the last call: templates searched, exact
  * verification rounds of the coarse search (one round = 16 coarse positions; a search that needs more than one had an unverified
- * position within the error bound of the best one) and exact runs of the fine search (32 consecutive positions each; 4 cover the
+ * position within the error bound of the best one) and exact runs of the fine search (16 consecutive positions each; 7 cover the
  * whole +-48 range).  Synchronises the device.  Any pointer may be NULL. */
 PU_API pu_status pu_chirp_search_stats(uint64_t* searches, uint64_t* rounds, uint64_t* fine_runs);
 /* SM cycles the searches since the last call spent per phase (summed over frames, thread 0's clock): [0] low-pass + decimation,

@@ -203,7 +203,7 @@ constexpr int kC2VBuf = kC2Cand * kC2Row + 2 * kC2VTaps;   // floats per staging
 // several passes over a buffer that holds one part (+ the 4 000-tap overhang) -- 65 KB at 66 000 samples in one pass, 73 KB at
 // 86 600 in two: three frames per SM either way.
 struct Chirp2Smem {
-    float* xd;                        // tier 1: decimated part of the window, whole tiles.  tier 2: rows[nbuf][16][kC2Row] + template tiles.  fine: lin[6][192] + template tiles
+    float* xd;                        // tier 1: decimated part of the window, whole tiles.  tier 2: rows[nbuf][16][kC2Row] + template tiles.  fine: lin[6][272] + template tiles
     float* tile;                      // low-pass input tile
     float (*acc)[2];
     float* a;                         // estimate of the normalised correlation
@@ -296,9 +296,9 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
             __syncthreads();
             {
                 const float* t = S.tile + kRankD * tid;
-                float y = 0.0f;
+                float y = S.lp[kRankC] * t[kRankC];            // symmetric taps: lp[k] == lp[kRankNT - 1 - k], half the multiplies
 #pragma unroll
-                for (int k = 0; k < kRankNT; ++k) y = fmaf(S.lp[k], t[k], y);
+                for (int k = 0; k < kRankC; ++k) y = fmaf(S.lp[k], t[k] + t[kRankNT - 1 - k], y);
                 S.xd[tl * kC2Threads + tid] = y;
                 if (seg_base >= 0) {
                     float e = 0.0f;                             // 6 samples per thread, 8 threads per 48-sample segment
@@ -543,7 +543,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     if (best_pos < 0 || best < __fmul_rn(threshold, 0.3f)) return -1;
     // ---------------- fine search (:600-612) and the parabola's neighbours (:615-625), two-tier as well.  The correlation magnitude is
     // band-limited (2.4 kHz: main lobe 40 samples null to null), so estimates every 6 samples -- the decimated correlation again, on the
-    // grid best_pos + 6k -- locate its maximum; a run of 32 consecutive positions around it is evaluated exactly (lane = position over
+    // grid best_pos + 6k -- locate its maximum; a run of 16 consecutive positions around it is evaluated exactly (lane = position over
     // one linear tile: consecutive banks), and further runs follow while (a) a neighbour of the current first maximum is not exact yet
     // or (b) an unverified grid point is within reach: 1.15 x estimate (the most the magnitude can rise between two grid points)
     // + 4 x the largest |exact - estimate| seen.  S.ex[pos - q0] = exact value or -1 (not evaluated: cannot win, cannot be needed).
@@ -570,9 +570,9 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
         __syncthreads();
         mark(4);
         if (tid == 0) S.ex[best_pos - q0] = best;              // exact from the coarse stage
-        constexpr int NB = 6;                                  // staging ring (see the coarse stage)
-        float (*lin)[192] = reinterpret_cast<float (*)[192]>(S.xd);
-        float (*ftpl)[2][128] = reinterpret_cast<float (*)[2][128]>(S.xd + NB * 192);   // [NB][cos, sin][128]
+        constexpr int NB = 6, FR = 16, FT = 256;               // staging ring (see the coarse stage); positions per exact run; taps per tile
+        float (*lin)[FT + FR] = reinterpret_cast<float (*)[FT + FR]>(S.xd);
+        float (*ftpl)[2][FT] = reinterpret_cast<float (*)[2][FT]>(S.xd + NB * (FT + FR));   // [NB][cos, sin][FT], 16-byte aligned
         float ferr = 0.0f;                                     // thread 0
         for (int it = 0;; ++it) {
             if (tid == 0) {
@@ -596,54 +596,52 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                     for (int k = 0; k < nk && centre < 0; ++k)
                         if (S.ex[gbase + 6 * k - q0] < 0.0f && est[k] * 1.15f + guard * ferr + 1e-6f >= fb) centre = gbase + 6 * k;
                 }
-                S.cand[0] = centre < 0 ? -1 : min(max(centre - 16, q0), max(q0, q1 - 31));
+                S.cand[0] = centre < 0 ? -1 : min(max(centre - FR / 2, q0), max(q0, q1 - (FR - 1)));
                 if (centre >= 0) atomicAdd(&g_chirp2_stats[2], 1ull);
             }
             __syncthreads();
             const int r0 = S.cand[0];
             if (r0 < 0) break;
             auto stage = [&](int tile, int buf) {
-                if (tid < 160) {
-                    const int wi = r0 + 128 * tile + tid;     // window index; lanes past q1 read on into the frame or zeros
+                for (int j = tid; j < FT + FR; j += kC2Threads) {
+                    const int wi = r0 + FT * tile + j;        // window index; lanes past q1 read on into the frame or zeros
                     const bool ok = w0 + wi < L;
-                    cp_async4_zfill(smem_u32(&lin[buf][tid]), ok ? xw + wi : x, ok);
-                } else if (tid < 224) {
-                    const int u = tid - 160;
-                    if (128 * tile + 4 * (u & 31) < n)
-                        cp_async16(smem_u32(&ftpl[buf][u >> 5][4 * (u & 31)]), (u < 32 ? tc : ts) + 128 * tile + 4 * (u & 31));
+                    cp_async4_zfill(smem_u32(&lin[buf][j]), ok ? xw + wi : x, ok);
                 }
+                if (tid < FT / 2 && FT * tile + 4 * (tid & 63) < n)
+                    cp_async16(smem_u32(&ftpl[buf][tid >> 6][4 * (tid & 63)]), (tid < 64 ? tc : ts) + FT * tile + 4 * (tid & 63));
                 cp_async_commit();
             };
-            float sum = 0.0f;                                  // warps 0 / 1 / 2: ci / cq / se of position r0 + lane
-            float* xch = &S.acc[0][0];                         // [64] cq, se
+            // warp 0: ci of position r0 + lane in lanes 0..15, cq of the same positions in lanes 16..31; warp 1: their energies
+            float sum = 0.0f;
+            float* xch = &S.acc[0][0];                         // [32] cq, se
+            constexpr int nft = (n + FT - 1) / FT;
             for (int i = 0; i < NB - 1; ++i) stage(i, i);
-            for (int tile = 0; tile < (n + 127) / 128; ++tile) {
+            for (int tile = 0; tile < nft; ++tile) {
                 cp_async_wait_but(NB - 2);
                 __syncthreads();
-                if (128 * (tile + NB - 1) < n) stage(tile + NB - 1, (tile + NB - 1) % NB); else cp_async_commit();
-                if (warp < 3) {
-                    const float* row = lin[tile % NB] + lane;
-                    const int tn = min(128, n - 128 * tile);
-                    if (warp < 2) {
-                        const float* tv = ftpl[tile % NB][warp];
+                if (tile + NB - 1 < nft) stage(tile + NB - 1, (tile + NB - 1) % NB); else cp_async_commit();
+                const float* row = lin[tile % NB] + (lane & (FR - 1));
+                const int tn = min(FT, n - FT * tile);
+                if (warp == 0) {
+                    const float* tv = ftpl[tile % NB][lane >> 4];
 #pragma unroll 4
-                        for (int t = 0; t < tn; t += 4) {
-                            const float4 v = *reinterpret_cast<const float4*>(tv + t);
-                            sum = __fadd_rn(sum, __fmul_rn(row[t], v.x));
-                            sum = __fadd_rn(sum, __fmul_rn(row[t + 1], v.y));
-                            sum = __fadd_rn(sum, __fmul_rn(row[t + 2], v.z));
-                            sum = __fadd_rn(sum, __fmul_rn(row[t + 3], v.w));
-                        }
-                    } else {
-#pragma unroll 16
-                        for (int t = 0; t < tn; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
+                    for (int t = 0; t < tn; t += 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(tv + t);
+                        sum = __fadd_rn(sum, __fmul_rn(row[t], v.x));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 1], v.y));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 2], v.z));
+                        sum = __fadd_rn(sum, __fmul_rn(row[t + 3], v.w));
                     }
+                } else if (warp == 1) {
+#pragma unroll 16
+                    for (int t = 0; t < tn; ++t) { const float v = row[t]; sum = __fadd_rn(sum, __fmul_rn(v, v)); }
                 }
             }
-            if (warp == 1) xch[lane] = sum;
-            if (warp == 2) xch[32 + lane] = sum;
+            if (warp == 0 && lane >= FR) xch[lane - FR] = sum;
+            if (warp == 1 && lane < FR) xch[FR + lane] = sum;
             __syncthreads();
-            if (warp == 0 && r0 + lane <= q1) S.ex[r0 + lane - q0] = chirp_norm(sum, xch[lane], xch[32 + lane], te);
+            if (warp == 0 && lane < FR && r0 + lane <= q1) S.ex[r0 + lane - q0] = chirp_norm(sum, xch[lane], xch[FR + lane], te);
             __syncthreads();
         }
     }
