@@ -183,7 +183,8 @@ __device__ int chirp_detect_template(ChirpShared& S, ChirpWarpBuf* WB, const flo
 // RANKED with a cheap estimate and only the leaders are evaluated the reference's way:
 //   tier 1  the window is low-passed (47 taps, 4 kHz) and decimated 6:1 -- the template occupies 300..2700 Hz, so
 //           sum_i x[p+i] t[i] ~ 6 sum_j xf[p+6j] t[6j] -- and every coarse position (48 samples = 8 decimated ones apart) gets a
-//           4 000-tap FMA correlation from shared memory, in any summation order; energies come from 48-sample partial sums.
+//           4 000-tap correlation from shared memory on the tensor cores (tf32, diagonal sums of a small GEMM); energies come from
+//           48-sample partial sums.
 //           Measured against the ordered sums: rms error 1-2 % of the correlation floor of a noise-only window.
 //   tier 2  the 16 best-ranked positions are evaluated exactly (lane = position, its three sums three independent chains), the result is the first maximum among them, and the search ends when every unverified position
 //           is out of reach:  estimate + 4 x (largest |exact - estimate| seen) < best exact value.  Otherwise the next 16 are
@@ -215,7 +216,8 @@ struct Chirp2Smem {
     float* best_c; int* best_p; int* go; float* best_se; int* nranked;
 };
 __host__ __device__ inline int chirp2_tiles(int ppart) {       // never less than the exact phases need: three staging buffers
-    const int t = (8 * ppart + kC2Nd + kC2Threads - 1) / kC2Threads, floor_t = (3 * kC2VBuf + kC2Threads - 1) / kC2Threads;
+    // (+ 288: the last band of the tensor-core estimates reads up to 8 (ppart + 533) + 7, feeding diagonals past the last position)
+    const int t = (8 * ppart + kC2Nd + 288 + kC2Threads - 1) / kC2Threads, floor_t = (3 * kC2VBuf + kC2Threads - 1) / kC2Threads;
     return t > floor_t ? t : floor_t;
 }
 __host__ __device__ inline int chirp2_rank_floats(int maxpos) { return (2 * maxpos + maxpos + (maxpos + 1) / 2 + 3) & ~3; }
@@ -265,6 +267,14 @@ __device__ __forceinline__ float chirp_norm(float ci, float cq, float se, float 
     const float denom = __fsqrt_rn(__fmul_rn(se, te));
     if (denom < 1e-10f) return 0.0f;
     return __fdiv_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(ci, ci), __fmul_rn(cq, cq))), denom);
+}
+
+// D (16 x 8, fp32) += A (16 x 8, tf32, row) x B (8 x 8, tf32, col): the warp-level tensor-core instruction.  fp32 bit patterns are
+// passed as they are (the unit reads the upper 19 bits: truncation to tf32), fine for a ranking estimate.
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 __device__ __forceinline__ void cp_async4_zfill(uint32_t dst, const void* src, bool valid) {
@@ -322,37 +332,49 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
         // ---------------- tier 1b: the part's decimated samples (decimated index 8 p0 + i -> xd[i]) and 48-sample energies
         const int nxd = 8 * (np - 1) + kC2Nd;                  // decimated samples the part's positions touch
         const int ntile = (nxd + kC2Threads - 1) / kC2Threads;
+        // (the band walk below reads a little past the last tile, against zero template rows: keep that finite)
+        for (int i = ntile * kC2Threads + tid; i < chirp2_tiles(ppart) * kC2Threads; i += kC2Threads) S.xd[i] = 0.0f;
         decimate(48 * p0, ntile, p0);
         mark(0);
         nseg = p0 + ntile * (kC2Threads / 8);
-        // ---------------- tier 1c: correlation estimates.  Item = (8 consecutive positions, one half of the taps); lane l starts 4 l taps
-        // into its half and wraps, which spreads the 128-bit shared loads of a warp over all banks (positions sit 64 floats apart).
-        const int nblk = (np + 7) / 8;
-        for (int item = tid; item < 2 * nblk; item += kC2Threads) {
-            const int sg = item / nblk, pb = item - sg * nblk;
-            constexpr int len = kC2Nd / 2;
-            const int j0 = sg * len;
-            float ac[8], as[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) { ac[r] = 0.0f; as[r] = 0.0f; }
-            const float* xb = S.xd + 64 * pb;
-            for (int jj = 0; jj < len; jj += 4) {
-                int j = jj + 4 * lane;
-                if (j >= len) j -= len;
-                j += j0;
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(tdc + j));   // 32 KB per template, shared by every frame: L1 / L2
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(tds + j));
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const float4 v = *reinterpret_cast<const float4*>(xb + 8 * r + j);
-                    ac[r] = fmaf(v.x, c4.x, fmaf(v.y, c4.y, fmaf(v.z, c4.z, fmaf(v.w, c4.w, ac[r]))));
-                    as[r] = fmaf(v.x, s4.x, fmaf(v.y, s4.y, fmaf(v.z, s4.z, fmaf(v.w, s4.w, as[r]))));
+        // ---------------- tier 1c: correlation estimates on the tensor cores.  With X[i][s] = xd[8 i + s] (one row per coarse step) and
+        // T_q[s] = t[8 q + s] (the decimated template cut into 500 rows of 8), the estimate of position m is the sum over q of
+        // <X[m + q], T_q>: the sums along the diagonals of G = X T^T.  A warp walks one band of diagonals: step s multiplies the 16 rows
+        // X[16 b + 8 s ..] by the 8 template rows T[8 s ..] (one m16n8k8 per template; element (r, n) belongs to diagonal 16 b + r - n at
+        // EVERY step, so the band's sums accumulate in the same registers), and the rows 8..15 of a step are the rows 0..7 of the next:
+        // two shared loads, four template loads and two MMAs per 2 048 multiply-adds, against 74 instructions per 64 with FMAs.
+        {
+            const int g = lane >> 2, t4 = lane & 3;
+            const int nband = (np + 6) / 16 + 1;               // position m takes part in bands (m .. m + 7) / 16
+            for (int bnd = warp; bnd < nband; bnd += kC2Warps) {
+                const int i0 = 16 * bnd;
+                float dc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ds[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                const float* xa = S.xd + 8 * (i0 + g) + t4;
+                uint32_t af[4];
+                af[0] = __float_as_uint(xa[0]);
+                af[2] = __float_as_uint(xa[4]);
+#pragma unroll 3
+                for (int st = 0; st < (kC2Nd / 8 + 7) / 8; ++st) {
+                    af[1] = __float_as_uint(xa[64 * st + 64]);
+                    af[3] = __float_as_uint(xa[64 * st + 68]);
+                    const int q = 8 * st + g;                   // template row of this lane's B column
+                    uint32_t c0 = 0, c1 = 0, s0 = 0, s1 = 0;
+                    if (q < kC2Nd / 8) {
+                        c0 = __float_as_uint(__ldg(&tdc[8 * q + t4]));
+                        c1 = __float_as_uint(__ldg(&tdc[8 * q + t4 + 4]));
+                        s0 = __float_as_uint(__ldg(&tds[8 * q + t4]));
+                        s1 = __float_as_uint(__ldg(&tds[8 * q + t4 + 4]));
+                    }
+                    mma_tf32_16x8x8(dc, af, c0, c1);
+                    mma_tf32_16x8x8(ds, af, s0, s1);
+                    af[0] = af[1];
+                    af[2] = af[3];
                 }
-            }
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int m = p0 + 8 * pb + r;
-                if (m < n_pos) { atomicAdd(&S.acc[m][0], ac[r]); atomicAdd(&S.acc[m][1], as[r]); }
+                for (int v = 0; v < 4; ++v) {                   // fragment element v of lane (g, t4): row g + 8 (v >> 1), column 2 t4 + (v & 1)
+                    const int ml = i0 + g + 8 * (v >> 1) - (2 * t4 + (v & 1));
+                    if (ml >= 0 && ml < np) { atomicAdd(&S.acc[p0 + ml][0], dc[v]); atomicAdd(&S.acc[p0 + ml][1], ds[v]); }
+                }
             }
         }
         __syncthreads();                                       // the next part overwrites xd
