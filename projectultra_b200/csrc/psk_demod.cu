@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "ofdm_dev.cuh"
+#include "pu_async.cuh"
 #include "pu_internal.h"
 
 namespace pu {
@@ -213,16 +214,35 @@ __global__ void __launch_bounds__(kBkThreads) dpsk_find_preamble_kernel(const fl
     bool alive = L >= preamble + preamble / 2;                        // :354-355
     const int max_search = min(L - preamble, preamble * 4);           // :393
     const int n_starts = alive ? (max_search + sps - 1) / sps : 0;    // coarse positions 0, sps, ... < max_search
-    // ---- energy gate (:359-368, thread 0) next to the coarse symbol correlations (all other warps)
+    // ---- coarse symbol correlations (all threads), then the energy gate (:359-368): ONE ordered sum over up to 2 preambles of samples.
+    // Read by its thread straight from global memory it was the kernel: ~30 000 dependent load-multiply-adds with a handful of loads
+    // in flight (the v34 capture: issue-active 32 %, every other warp at the barrier).  Now all threads stage 2 048-sample chunks into
+    // shared memory with cp.async, one chunk ahead, and thread 0 sums from there at the add latency.
     if (alive) {
-        if (tid == 0) {
-            const int check = min(L, preamble * 2);
-            float energy = 0.0f;
-            for (int i = 0; i < check; ++i) energy = __fadd_rn(energy, __fmul_rn(x[i], x[i]));
-            S.rms = __fsqrt_rn(__fdiv_rn(energy, static_cast<float>(check)));
-        } else if (tid >= 32) {
-            for (int m = tid - 32; m < n_starts + kBkDiffs; m += T - 32) S.c0[m] = bk_correlate(x + m * sps, sps, tcos, tsin);
+        for (int m = tid; m < n_starts + kBkDiffs; m += T) S.c0[m] = bk_correlate(x + m * sps, sps, tcos, tsin);
+        constexpr int CH = 2048;
+        float* stg = reinterpret_cast<float*>(C);                     // [2][CH]: the fine correlations' storage is idle until later
+        const int check = min(L, preamble * 2), nch = (check + CH - 1) / CH;
+        auto fetch = [&](int k, int buf) {
+            for (int j = tid; j < CH; j += T)
+                if (k * CH + j < check) cp_async4(smem_u32(stg + buf * CH + j), x + k * CH + j);
+            cp_async_commit();
+        };
+        float energy = 0.0f;
+        fetch(0, 0);
+        for (int k = 0; k < nch; ++k) {
+            if (k + 1 < nch) fetch(k + 1, (k + 1) & 1); else cp_async_commit();
+            cp_async_wait_but_one();
+            __syncthreads();
+            if (tid == 0) {
+                const float* pch = stg + (k & 1) * CH;
+                const int cnt = min(CH, check - k * CH);
+#pragma unroll 8
+                for (int i = 0; i < cnt; ++i) energy = __fadd_rn(energy, __fmul_rn(pch[i], pch[i]));
+            }
+            __syncthreads();                                          // the chunk is fetched again two steps on
         }
+        if (tid == 0) S.rms = __fsqrt_rn(__fdiv_rn(energy, static_cast<float>(check)));
     }
     __syncthreads();
     alive = alive && !(S.rms < 0.01f);
@@ -625,7 +645,7 @@ static pu_status dpsk_find_launch(pu_dpsk* h, const float* d_samples, size_t B, 
         pu::set_error("pu_dpsk_find_preamble_batch: samples_per_symbol > 512 is not supported (shared-memory budget of the fine search)");
         return PU_ERR_UNSUPPORTED;
     }
-    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(sps) + 2 * 40 * static_cast<size_t>(sps));
+    const size_t smem = sizeof(float) * (2 * static_cast<size_t>(sps) + std::max<size_t>(2 * 40 * static_cast<size_t>(sps), 4096));   // (4096: the energy gate's staging chunks)
     (void)cudaGetLastError();
     cudaFuncSetAttribute(pu::dpsk_find_preamble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     pu::dpsk_find_preamble_kernel<<<static_cast<unsigned>(B), pu::kBkThreads, smem, st>>>(
