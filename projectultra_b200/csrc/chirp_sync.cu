@@ -197,6 +197,12 @@ constexpr int kC2N = 24000, kC2Nd = kC2N / kRankD;     // the 48 kHz chirp: 24 0
 constexpr int kC2MaxPos = 3000;                         // coarse positions per window the shared-memory budget of one SM allows
 constexpr int kC2TileIn = kC2Threads * kRankD + kRankNT - 1;
 constexpr int kC2TilePad = (kC2TileIn + 2 + 3) & ~3;     // one input tile buffer (two of them: double-buffered)
+// Fine stage: how far the correlation magnitude can rise between a grid point and a position <= 1.5 samples away (grid every 3 samples).
+// The complex correlation is band-limited to the template's 300..2700 Hz, i.e. +-1200 Hz around 1500 Hz, so by Bernstein's inequality its
+// magnitude changes by at most 2 pi 1200 / 48000 = 0.157 of its supremum per sample: a maximum M within 1.5 samples of a grid point implies
+// an estimate of at least (1 - 0.236) M there.  (A 6-sample grid with the single-path main lobe's 1.15 missed 2 of 16 384 two-path frames:
+// the paths' interference pattern has a 32-sample period.  tools/chirp_ab.py is that experiment.)
+constexpr float kFineReach = 1.0f / (1.0f - 1.5f * 0.157f);
 constexpr int kC2Cand = 16, kC2VTaps = 128;             // exact coarse stage: leaders per round, taps per staged tile
 constexpr int kC2Row = kC2VTaps + 1;                    // odd row stride: lane = candidate reads conflict-free
 constexpr int kC2VBuf = kC2Cand * kC2Row + 2 * kC2VTaps;   // floats per staging buffer: sample rows + template tile (cos, sin)
@@ -575,29 +581,36 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
     *corr_out = best;
     if (best_pos < 0 || best < __fmul_rn(threshold, 0.3f)) return -1;
     // ---------------- fine search (:600-612) and the parabola's neighbours (:615-625), two-tier as well.  The correlation magnitude is
-    // band-limited (2.4 kHz: main lobe 40 samples null to null), so estimates every 6 samples -- the decimated correlation again, on the
-    // grid best_pos + 6k -- locate its maximum; a run of 16 consecutive positions around it is evaluated exactly (lane = position over
+    // band-limited (2.4 kHz: main lobe 40 samples null to null), so estimates every 3 samples -- the decimated correlation again, two phases,
+    // on the grid gbase + 3k -- locate its maximum; a run of 16 consecutive positions around it is evaluated exactly (lane = position over
     // one linear tile: consecutive banks), and further runs follow while (a) a neighbour of the current first maximum is not exact yet
-    // or (b) an unverified grid point is within reach: 1.15 x estimate (the most the magnitude can rise between two grid points)
+    // or (b) an unverified grid point is within reach: kFineReach x estimate (the most the magnitude can rise next to a grid point)
     // + 4 x the largest |exact - estimate| seen.  S.ex[pos - q0] = exact value or -1 (not evaluated: cannot win, cannot be needed).
     const int fine_start = max(0, best_pos - 48), fine_end = min(search_len, best_pos + 48);
     const int q0 = max(0, fine_start - 1), q1 = min(search_len, fine_end + 1);
     {
-        const int klo = -((best_pos - fine_start) / 6), khi = (fine_end - best_pos) / 6, nk = khi - klo + 1;
-        const int gbase = best_pos + 6 * klo;                  // window index of grid point 0
-        decimate(gbase, (nk - 1 + kC2Nd + kC2Threads - 1) / kC2Threads, -1);
-        float* est = S.exq;                                    // [nk <= 17]
+        // grid of estimates every 3 samples: two decimation phases (offsets 0 and 3) of the 6:1 low-passed window
+        const int klo = -((best_pos - fine_start) / 6);
+        const int gbase = best_pos + 6 * klo;                  // window index of grid point 0 (>= fine_start)
+        const int nk = (fine_end - gbase) / 3 + 1;             // grid point kk sits at gbase + 3 kk (<= 33 points)
+        float* est = S.exq;
         const float dn = sqrtf(fmaxf(*S.best_se, 0.0f) * te);  // the window energy moves by < 0.5 % over +-48 samples
-        for (int k = warp; k < nk; k += kC2Warps) {
-            float ac = 0.0f, as = 0.0f;
-            for (int j = lane; j < kC2Nd; j += 32) {
-                const float v = S.xd[k + j];
-                ac = fmaf(v, __ldg(&tdc[j]), ac);
-                as = fmaf(v, __ldg(&tds[j]), as);
-            }
+        for (int ph = 0; ph < 2; ++ph) {
+            const int nph = (nk - ph + 1) / 2;                 // points of this phase: kk = ph, ph + 2, ...
+            if (nph <= 0) break;
+            decimate(gbase + 3 * ph, (nph - 1 + kC2Nd + kC2Threads - 1) / kC2Threads, -1);
+            for (int k = warp; k < nph; k += kC2Warps) {
+                float ac = 0.0f, as = 0.0f;
+                for (int j = lane; j < kC2Nd; j += 32) {
+                    const float v = S.xd[k + j];
+                    ac = fmaf(v, __ldg(&tdc[j]), ac);
+                    as = fmaf(v, __ldg(&tds[j]), as);
+                }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { ac += __shfl_xor_sync(0xffffffffu, ac, o); as += __shfl_xor_sync(0xffffffffu, as, o); }
-            if (lane == 0) est[k] = dn < 1e-10f ? 0.0f : sqrtf(ac * ac + as * as) / dn;
+                for (int o = 16; o > 0; o >>= 1) { ac += __shfl_xor_sync(0xffffffffu, ac, o); as += __shfl_xor_sync(0xffffffffu, as, o); }
+                if (lane == 0) est[2 * k + ph] = dn < 1e-10f ? 0.0f : sqrtf(ac * ac + as * as) / dn;
+            }
+            __syncthreads();                                   // the next phase overwrites xd
         }
         for (int i = tid; i < 128; i += kC2Threads) S.ex[i] = -1.0f;
         __syncthreads();
@@ -613,10 +626,10 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                 if (it == 0) {
                     int kb = 0;
                     for (int k = 1; k < nk; ++k) if (est[k] > est[kb]) kb = k;
-                    centre = gbase + 6 * kb;
+                    centre = gbase + 3 * kb;
                 } else {
                     for (int k = 0; k < nk; ++k) {
-                        const float v = S.ex[gbase + 6 * k - q0];
+                        const float v = S.ex[gbase + 3 * k - q0];
                         if (v >= 0.0f) ferr = fmaxf(ferr, fabsf(v - est[k]));
                     }
                     float fb = best;
@@ -627,7 +640,7 @@ __device__ int chirp_detect_template2(const Chirp2Smem& S, const float* __restri
                     }
                     if (fp > 0 && fp < search_len - 1 && (S.ex[fp - 1 - q0] < 0.0f || S.ex[fp + 1 - q0] < 0.0f)) centre = fp;
                     for (int k = 0; k < nk && centre < 0; ++k)
-                        if (S.ex[gbase + 6 * k - q0] < 0.0f && est[k] * 1.15f + guard * ferr + 1e-6f >= fb) centre = gbase + 6 * k;
+                        if (S.ex[gbase + 3 * k - q0] < 0.0f && est[k] * kFineReach + guard * ferr + 1e-6f >= fb) centre = gbase + 3 * k;
                 }
                 S.cand[0] = centre < 0 ? -1 : min(max(centre - FR / 2, q0), max(q0, q1 - (FR - 1)));
                 if (centre >= 0) atomicAdd(&g_chirp2_stats[2], 1ull);

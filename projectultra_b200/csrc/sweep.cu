@@ -60,7 +60,8 @@ bool make_plan(const pu_sweep_desc* d, SweepPlan* p) {
 
 // Built-in relative cost of one frame (GPU time, arbitrary unit), from the measured throughputs of DESIGN.md §4: the 512-FFT
 // differential kernels run ~100 M frames/s, the general presynced kernel 10-30 M, Schmidl-Cox acquisition 0.3 M, Barker acquisition
-// 0.18 M (139 392-sample frames), the two-tier dual-chirp search 0.19 M (OFDM_CHIRP) / 0.10 M (MC-DPSK, 84 200 samples); LDPC is
+// 0.25 M (139 392-sample frames), the two-tier dual-chirp search 0.34 M (OFDM_CHIRP) / 0.18 M (MC-DPSK, 84 200 samples), plus the
+// channel kernel's share for these long frames; LDPC is
 // added per SNR point by unit_cost().
 double mode_cost(const pu_sweep_mode& m) {
     if (m.cost > 0) return m.cost;
@@ -70,11 +71,11 @@ double mode_cost(const pu_sweep_mode& m) {
             return (diff && !m.ofdm.use_pilots && m.ofdm.fft_size == 512) ? 1.0 : (diff && !m.ofdm.use_pilots) ? 2.0 : 8.0;
         }
         case PU_WF_OFDM_SC: return 250.0;
-        case PU_WF_OFDM_CHIRP: return 600.0;
+        case PU_WF_OFDM_CHIRP: return 350.0;
         case PU_WF_DPSK: return 30.0;
-        case PU_WF_DPSK_ACQ: return 700.0;
+        case PU_WF_DPSK_ACQ: return 480.0;
         case PU_WF_MCDPSK: return 10.0;
-        default: return 1100.0;     // PU_WF_MCDPSK_CHIRP
+        default: return 620.0;      // PU_WF_MCDPSK_CHIRP
     }
 }
 // LDPC share: ~50 iterations at the bottom of the grid, ~2 at the top; in units of the demodulator cost of the cheapest mode
