@@ -133,3 +133,41 @@ def test_two_tier_search_equals_brute_force_search():
     assert searches >= len(x) - 1 and rounds <= 2 * searches        # the ranking does the work: ~1 round per search, not ~30
     assert 60 <= found < len(x) - 10
     del ctx
+
+
+def test_two_tier_search_equals_brute_force_search_on_two_path_channels():
+    """Two propagation paths 24 samples apart (Watterson "good") put two comparable peaks and their interference pattern (32-sample period)
+    inside the fine search range: the case that defeated a 6-sample estimate grid with a main-lobe reach factor (2 of 16 384 frames took the
+    lower peak).  With estimates every 3 samples and the Bernstein bound as reach factor every output equals the brute-force search."""
+    import os
+    import torch
+    from projectultra_b200 import capi, linksim
+    ctx = capi.Context(0)
+    cfg = capi.ModemConfig.from_buffer_copy(bytes(R.config_m1(R.DQPSK, R.R1_2)))
+    differ = 0
+    for chan, snr, B in (("good", 12.0, 3072), ("poor", 0.0, 1024)):
+        sim = linksim.LinkSim(ctx, cfg, chan, payload_bytes=40, pool=16, layout="chirp", peak=0.5, precision="fast")
+        pool = torch.cat([sim.tx_pool, torch.zeros(sim.tx_pool.shape[0], 2400, device=sim.tx_pool.device)], dim=1).contiguous()
+        idx = (torch.arange(B, device=pool.device) % pool.shape[0]).to(torch.int32)
+        std = ((pool.double() ** 2).mean(dim=1).sqrt() * 10 ** (-snr / 20)).float()[idx.long()].contiguous()
+        seed = torch.arange(B, device=pool.device, dtype=torch.int64) + 4242
+        rx = linksim.channel_apply(ctx, sim.ch, pool, idx, std, seed, None)
+        os.environ.pop("PU_CHIRP_SEARCH", None)
+        capi.chirp_search_stats()
+        fast = sim.ofdm.chirp_receive_batch(rx, llr_stride=648)
+        searches, rounds, runs = capi.chirp_search_stats()
+        os.environ["PU_CHIRP_SEARCH"] = "exact"
+        try:
+            slow = sim.ofdm.chirp_receive_batch(rx, llr_stride=648)
+        finally:
+            os.environ.pop("PU_CHIRP_SEARCH", None)
+        torch.cuda.synchronize()
+        fi, si = fast[2].cpu().numpy(), slow[2].cpu().numpy()
+        fv, sv = fast[3].cpu().numpy().view(np.uint32), slow[3].cpu().numpy().view(np.uint32)
+        bad = np.flatnonzero((fi != si).any(axis=1) | (fv != sv).any(axis=1))
+        print("%s %.0f dB: %d frames, %d detected, %d differ; %d searches, %d coarse rounds, %d fine runs" % (
+            chan, snr, B, int((si[:, 0] != 0).sum()), len(bad), searches, rounds, runs))
+        differ += len(bad)
+        assert int((si[:, 0] != 0).sum()) > B // 2
+    assert differ == 0
+    del ctx
