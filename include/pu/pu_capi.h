@@ -190,6 +190,10 @@ PU_API pu_status pu_chirp_generate(float sample_rate, float tx_cfo_hz, float* ou
  * position within the error bound of the best one) and exact runs of the fine search (16 consecutive positions each; 7 cover the
  * whole +-48 range).  Synchronises the device.  Any pointer may be NULL. */
 PU_API pu_status pu_chirp_search_stats(uint64_t* searches, uint64_t* rounds, uint64_t* fine_runs);
+/* sizeof of the public PODs, for bindings that mirror them by hand (ctypes, cgo, JNI): out[] = {pu_modem_config, pu_dpsk_config,
+ * pu_mcdpsk_config, pu_channel_config, pu_sweep_mode, pu_sweep_desc, pu_sweep_stats, 0}.  Returns the number of entries filled. */
+PU_API int pu_abi_sizes(uint32_t out[8]);
+
 /* SM cycles the searches since the last call spent per phase (summed over frames, thread 0's clock): [0] low-pass + decimation,
  * [1] correlation estimates, [2] energies + ranking, [3] exact evaluation of the coarse leaders, [4] fine ranking, [5] exact fine runs. */
 PU_API pu_status pu_chirp_phase_cycles(uint64_t cycles[8]);

@@ -76,3 +76,12 @@ extern "C" pu_status pu_tools_apply_cfo(float* samples, size_t n, float cfo_hz, 
     pu::tools_apply_cfo(samples, n, cfo_hz, sample_rate);
     return PU_OK;
 }
+
+// sizeof of the public PODs (include/pu/pu_capi.h: pu_abi_sizes): a binding that mirrors a struct by hand can check itself
+extern "C" int pu_abi_sizes(uint32_t out[8]) {
+    if (!out) return 0;
+    const uint32_t v[8] = {sizeof(pu_modem_config), sizeof(pu_dpsk_config), sizeof(pu_mcdpsk_config), sizeof(pu_channel_config),
+                           sizeof(pu_sweep_mode),   sizeof(pu_sweep_desc),  sizeof(pu_sweep_stats),   0};
+    for (int i = 0; i < 8; ++i) out[i] = v[i];
+    return 7;
+}

@@ -124,3 +124,13 @@ def test_two_gloo_ranks_cover_the_grid_once_and_sum_to_the_single_process_table(
     assert one["owned_once"] and two["owned_once"]
     assert one["c"] == two["c"]
     assert all(row[0] == 9000 for row in one["c"])
+
+
+def test_ctypes_mirrors_have_the_c_structs_sizes():
+    """The Python mirrors of the public PODs are written by hand; pu_abi_sizes reports what the C side compiled."""
+    import ctypes as C
+    from projectultra_b200 import capi, linksim
+    out = (C.c_uint32 * 8)()
+    assert capi.lib().pu_abi_sizes(out) == 7
+    want = [capi.ModemConfig, capi.DpskConfig, capi.McDpskConfig, linksim.ChannelConfig, capi.SweepMode, capi.SweepDesc, capi.SweepStats]
+    assert [int(v) for v in out[:7]] == [C.sizeof(t) for t in want]
