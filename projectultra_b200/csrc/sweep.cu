@@ -229,9 +229,11 @@ struct ModeEngine {
                 if (is_dpsk) return pu_dpsk_tx(&m->dpsk, 0, coded, nc, out, cap, len);
                 return pu_mcdpsk_tx(&m->mcdpsk, coded, nc, out, cap, len);
             };
-            tx(nullptr, 0, &n);
-            w.resize(n);
-            if ((s = tx(w.data(), n, &n)) != PU_OK) return s;
+            // every waveform of a mode has the same length: the host modulators are asked for it once (a query runs the whole modulation)
+            if (body_len == 0) { tx(nullptr, 0, &n); body_len = n; }
+            w.resize(body_len);
+            if ((s = tx(w.data(), body_len, &n)) != PU_OK) return s;
+            PU_REQUIRE(n == body_len, "pu_linksim_run: TX waveforms of one mode differ in length");
             if (!chirp.empty()) w.insert(w.begin(), chirp.begin(), chirp.end());
             if (m->lead_samples) w.insert(w.begin(), m->lead_samples, 0.0f);       // the tools' silence around a frame (test_iwaveform.cpp:396-459)
             if (m->tail_samples) w.insert(w.end(), m->tail_samples, 0.0f);
