@@ -84,6 +84,36 @@ int orc_fft(size_t n, const float* in, float* out, int inverse) {
     return 0;
 }
 
+/* ------------------------------------------------------------------ the tools' CFO injector
+ * tools/test_iwaveform.cpp:67-118 (applyCFO): zero-padded FFT over the next power of two -> positive frequencies doubled,
+ * negative ones zeroed -> inverse FFT = analytic signal; rotation by the float phase recurrence (phase += 2 pi cfo / fs,
+ * wrapped against the double pi) and the real part.  Applied by the tools to the clean TX audio before the channel (:501-506). */
+int orc_tools_apply_cfo(float* x, size_t n, float cfo_hz, float fs) {
+    if (n < 128 || fabsf(cfo_hz) < 0.001f) return 0;                       /* :68 */
+    size_t m = 1;
+    while (m < n) m *= 2;                                                   /* :74-75 */
+    cf* tw = (cf*)malloc(sizeof(cf) * m);
+    cf* z = (cf*)calloc(m, sizeof(cf));
+    fft_twiddles(m, tw);
+    for (size_t i = 0; i < n; ++i) z[i] = MKC(x[i], 0.0f);                  /* :81-84 */
+    fft_inplace(z, m, tw, 0);
+    for (size_t i = 1; i < m / 2; ++i) z[i] = cscale(2.0f, z[i]);           /* :93-95 */
+    for (size_t i = m / 2 + 1; i < m; ++i) z[i] = MKC(0.0f, 0.0f);          /* :96-98 */
+    fft_inplace(z, m, tw, 1);
+    float phase = 0.0f;
+    const float inc = 2.0f * (float)M_PI * cfo_hz / fs;                     /* :106 */
+    for (size_t i = 0; i < n; ++i) {
+        const cf rot = MKC(cosf(phase), sinf(phase));
+        x[i] = crealf(z[i] * rot);                                          /* :109-110 */
+        phase += inc;
+        if (phase > M_PI) phase = (float)((double)phase - 2.0f * M_PI);     /* :112-113: float -= double */
+        else if (phase < -M_PI) phase = (float)((double)phase + 2.0f * M_PI);
+    }
+    free(z);
+    free(tw);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ NCO
  * filters.cpp:228-238: phase_inc = 2*pi*f/fs (double expr -> float); out = (cos,sin)(phase);
  * phase += inc; wrap compares against the double 2*pi. */

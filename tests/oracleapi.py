@@ -123,6 +123,13 @@ def block_interleave(rows, cols, x, inverse=False):
     return out
 
 
+def tools_apply_cfo(x, cfo_hz, sample_rate=48000.0):
+    """tools/test_iwaveform.cpp:67-118 (oracle/pu_oracle_ofdm.c: orc_tools_apply_cfo) on a copy of x."""
+    out = np.ascontiguousarray(x, np.float32).copy()
+    lib().orc_tools_apply_cfo(_p(out, C.c_float), C.c_size_t(len(out)), C.c_float(cfo_hz), C.c_float(sample_rate))
+    return out
+
+
 def fft(x, inverse=False):
     z = np.ascontiguousarray(x, dtype=np.complex64)
     out = np.zeros_like(z)

@@ -9,6 +9,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(__file__))
 import refapi as R
+import oracleapi as O
 
 
 def signal(n, seed):
@@ -26,6 +27,17 @@ def test_matches_the_loop_around_the_compiled_reference_fft(n, cfo):
     assert (got.view(np.uint32) == want.view(np.uint32)).all()
     if n < 128 or abs(cfo) < 0.001:
         assert (got.view(np.uint32) == x.view(np.uint32)).all()           # untouched (:68)
+
+
+@pytest.mark.parametrize("n,cfo", [(127, 30.0), (4096, 30.0), (5000, -50.0), (65537, 12.5), (9000, 0.0005)])
+def test_matches_the_plain_c_oracle(n, cfo):
+    """The same against oracle/pu_oracle_ofdm.c: orc_tools_apply_cfo (which the test above pins to the compiled reference where it is present)."""
+    from projectultra_b200 import capi
+    x = signal(n, 2 * n + 1)
+    got, want = capi.tools_apply_cfo(x, cfo), O.tools_apply_cfo(x, cfo)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    if R.available():
+        assert (R.tools_apply_cfo(x, cfo).view(np.uint32) == want.view(np.uint32)).all()
 
 
 def test_shifts_every_component_by_the_offset():
